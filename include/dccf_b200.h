@@ -1,0 +1,181 @@
+/*
+ * dccf_b200.h — C-ABI of the B200-native DCCF hot path (libdccf_b200.so).
+ *
+ * The reference (rutgerswiselab/DCCF) has no FFI of its own: its hot path is eager PyTorch
+ * inside Python classes.  Each entry point below replaces a span of reference Python, cited
+ * as `file:line` relative to the reference root.  All pointers are DEVICE pointers unless a
+ * parameter is documented as host; buffers are owned by the caller (PyTorch allocator on the
+ * Python side); nothing is allocated or freed by the library; every call is asynchronous on
+ * `stream` (a cudaStream_t passed as void*).
+ *
+ * Return value: 0 on success, negative dccf_status otherwise; dccf_last_error() returns a
+ * thread-local message for the last failure.
+ *
+ * Shapes use the reference's names: U users, I items, D = u_vector_size (= 64 in this build),
+ * F = feature width (768), S = --sample-num, A = --attribute-num, Z = S+1 slots,
+ * R = Z*A predictor rows per (user,item) pair, P pairs per call, N = P*R rows.
+ * Row r of a call is (p, z, a) with r = (p*Z + z)*A + a   (src/models/DCCF.py:76-82).
+ */
+#ifndef DCCF_B200_H
+#define DCCF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCCF_ABI_VERSION 4
+#define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
+
+typedef enum dccf_status {
+    DCCF_OK = 0,
+    DCCF_ERR_ARG = -1,     /* bad argument (null pointer, unsupported size) */
+    DCCF_ERR_CUDA = -2,    /* a CUDA runtime call failed; see dccf_last_error() */
+    DCCF_ERR_UNSUPPORTED = -3
+} dccf_status;
+
+/* Model geometry (src/models/DCCF.py:23-34 ctor arguments). */
+typedef struct dccf_dims {
+    int32_t n_users;   /* U */
+    int32_t n_items;   /* I */
+    int32_t dim;       /* D, must equal DCCF_DIM */
+    int32_t feat_dim;  /* F, multiple of 64 */
+    int32_t n_samples; /* S  (--sample-num) */
+    int32_t n_attr;    /* A  (--attribute-num) */
+} dccf_dims;
+
+/* Exposure source for softmax_z(expo_prob[u, item_z])  (src/models/DCCF.py:64,98). */
+typedef struct dccf_expo {
+    int32_t mode;            /* 0: dense [U,I] f32 matrix (ips_expo_prob.npy);
+                                1: on the fly from IPSBiasedMF factors (src/models/IPSBiasedMF.py:37-57) */
+    int32_t _pad;
+    const float* dense;      /* mode 0 */
+    const float* mf_user;    /* mode 1: [U,D] */
+    const float* mf_item;    /* mode 1: [I,D] */
+    const float* mf_user_bias; /* [U] */
+    const float* mf_item_bias; /* [I] */
+    const float* propensity; /* [I] */
+    float mf_global_bias;
+    float mf_min_propensity; /* M */
+} dccf_expo;
+
+/* Random inputs of one predict call (src/models/DCCF.py:87 noise, :94 dropout).
+ * mode 0: absent (std == 0 / p == 0); mode 1: explicit tensor supplied by the caller (parity
+ * runs feed the reference's own draws); mode 2: counter-based Philox4x32-10 generated in
+ * registers — bit-identical to what dccf_noise_fill / dccf_dropout_mask_fill materialise for
+ * the same (seed, offset). */
+typedef struct dccf_rng {
+    int32_t noise_mode;
+    int32_t mask_mode;
+    const float* noise; /* mode 1: [N,F] = eps (already scaled by std) */
+    const float* mask;  /* mode 1: [N,D] = bernoulli(1-p)/(1-p)       */
+    float noise_std;    /* mode 2 */
+    float p_drop;       /* mode 2 */
+    uint64_t seed;      /* mode 2 */
+    uint64_t offset;    /* mode 2: call counter, distinct per predict call */
+    const uint64_t* offset_dev; /* mode 2, optional DEVICE pointer: when non-NULL the kernels read the
+                                   call counter from here instead of `offset` (lets a captured CUDA
+                                   graph be replayed; see dccf_state_advance) */
+} dccf_rng;
+
+const char* dccf_last_error(void);
+int dccf_abi_version(void);
+
+/* ---- RNG materialisers (host-visible definition of the mode-2 streams) ------------------ */
+/* out[r,f] = std * normal(seed, offset, row0 + r, f)          replaces DCCF.py:87 `normal_` */
+int dccf_noise_fill(float* out, int64_t n_rows, int32_t feat_dim, float std,
+                    uint64_t seed, uint64_t offset, int64_t row0, void* stream);
+/* out[r,j] = (uniform(seed, offset, row0 + r, j) < 1-p) / (1-p)   replaces DCCF.py:94 Dropout */
+int dccf_dropout_mask_fill(float* out, int64_t n_rows, int32_t dim, float p_drop,
+                           uint64_t seed, uint64_t offset, int64_t row0, void* stream);
+
+/* ---- (a)+(b): fused gather + predictor rows + backdoor-adjusted score ------------------- */
+/* Replaces DCCF.predict lines 74-100 (src/models/DCCF.py).
+ *   X            [P,2] int64, col 0 = uid, col 1 = iid           (feed_dict['X'])
+ *   sample_item  [P,S] int64 confounder items                    (DCCF.py:72, drawn by caller)
+ *   W            [D, D+F] row-major  (mlp.0.weight),  b [D]      (mlp.0.bias)
+ *   out_pred     [P]
+ *   ws_rows      [N] workspace: s[r] = <E_user[u], dropout(relu(W x_r + b))>
+ *   ws_wt        [(D+F)*D] workspace: W transposed (k-major)
+ *   save_h       [N,D] or NULL: post-dropout activations kept for the backward pass
+ *   save_w       [P,Z] or NULL: softmax exposure weights
+ *   err_flag     int32[1]: set to 1 if any id was out of range (ids are clamped, never faulting)
+ */
+int dccf_score_fwd(const dccf_dims* dims, const float* E_user, const float* E_item,
+                   const float* Feat, const float* W, const float* b, const dccf_expo* expo,
+                   const int64_t* X, const int64_t* sample_item, int64_t n_pairs,
+                   const dccf_rng* rng, float* out_pred, float* ws_rows, float* ws_wt,
+                   float* save_h, float* save_w, int32_t* err_flag, void* stream);
+
+/* ---- (c) part 1: pairwise loss forward + full backward ---------------------------------- */
+/* Replaces DCCF.forward lines 116-125 (src/models/DCCF.py) + autograd backward
+ * (src/runners/BaseRunner.py:183).  One launch.
+ *   loss_mode 0: BPR  -sum_j log sigmoid(pred[j]-pred[j+P/2])   (rank==1, P even)
+ *   loss_mode 1: MSE  mean_p (pred[p]-Y[p])^2                    (rank==0)
+ *   pred [P], save_h [N,D], save_w [P,Z] from dccf_score_fwd called with the SAME rng.
+ *   out_loss     float[1]
+ *   gW_part      [n_splits, D, D+F], gb_part [n_splits, D]: per-row-split partial sums of
+ *                d loss/d W and d loss/d b, summed in ascending split order by dccf_adam_dense
+ *   gu_rec       [P,D]    gradient record for user row X[p,0]
+ *   gi_rec       [P*Z,D]  gradient record for item row items[p,z]
+ *   rec_keys_u   [P] int32, rec_keys_i [P*Z] int32: the table rows those records belong to
+ * n_splits must equal dccf_bwd_splits(N) with N = P*Z*A.
+ */
+int32_t dccf_bwd_splits(int64_t n_rows);
+int dccf_bpr_bwd(const dccf_dims* dims, const float* E_user, const float* E_item,
+                 const float* Feat, const float* W, const int64_t* X, const int64_t* sample_item,
+                 const float* Y, int64_t n_pairs, const dccf_rng* rng, int32_t loss_mode,
+                 const float* pred, const float* save_h, const float* save_w, float* out_loss,
+                 float* gW_part, float* gb_part, float* gu_rec, float* gi_rec,
+                 int32_t* rec_keys_u, int32_t* rec_keys_i, void* stream);
+
+/* ---- (c) part 2: l2 + clip + Adam, dense over every row --------------------------------- */
+/* Replaces model.l2()*l2 (BaseRunner.py:181, BaseModel.py:179-187), clip_grad_value_
+ * (BaseRunner.py:185) and torch.optim.Adam(weight_decay=l2).step (BaseRunner.py:100,187):
+ *   g = clamp(g_sparse + 2*l2*p, -clip, clip) + wd*p ; m,v,p updated as torch 2.11
+ *   optim/adam.py (_multi_tensor_adam, non-capturable branch).
+ * Embedding-table variant: the gradient arrives as n_rec records (row id + D floats); records
+ * with equal ids are summed in ascending record order (deterministic).
+ *   head  int32[n_table_rows], persistent, must be -1 everywhere on entry; is -1 again on exit
+ *   next  int32[n_rec] workspace
+ */
+typedef struct dccf_adam {
+    double lr, beta1, beta2, eps; /* Python doubles, as torch.optim.Adam receives them */
+    double l2;          /* weight of sum p^2 in the loss  (--l2) */
+    double weight_decay;/* Adam weight_decay               (--l2) */
+    double clip;        /* clip_grad_value_ bound, 50; <= 0 disables */
+    int32_t step;       /* t = 1,2,... */
+    int32_t _pad;
+    const int32_t* step_dev; /* optional DEVICE pointer overriding `step` (graph replay) */
+} dccf_adam;
+
+int dccf_adam_sweep(float* table, float* m, float* v, int64_t n_table_rows,
+                    const int32_t* rec_keys, const float* rec_grads, int64_t n_rec,
+                    int32_t* head, int32_t* next, const dccf_adam* hp, void* stream);
+/* Dense variant for mlp.0.weight / mlp.0.bias: g = sum over n_parts partial buffers of n floats. */
+int dccf_adam_dense(float* p, float* m, float* v, int64_t n, const float* g_parts,
+                    int32_t n_parts, int64_t part_stride, const dccf_adam* hp, void* stream);
+/* step_dev[0] += 1 ; offset_dev[0] += offset_inc  (either pointer may be NULL) — the last node
+ * of a captured training step, so that a replay sees t+1 and a fresh rng counter. */
+int dccf_state_advance(int32_t* step_dev, uint64_t* offset_dev, uint64_t offset_inc, void* stream);
+
+/* ---- (d): evaluation ranker -------------------------------------------------------------- */
+/* Replaces BaseModel.evaluate_method ranking branch (src/models/BaseModel.py:82-126) and
+ * src/utils/rank_metrics.py:61-87,130-201 for binary labels.
+ *   scores [n_rows] f32, labels [n_rows] f32 (0/1), iids [n_rows] int64, all in data order
+ *   cand_rows [n_cand] int32: row indices grouped by user; user g owns cand_rows[off[g]..off[g+1])
+ *   user_off  [n_users+1] int64
+ * Ranking order: score descending, ties by item id ascending, then by row index ascending.
+ *   out_topk_iid [n_users,k] int64 (-1 padded), out_topk_row [n_users,k] int32 (may be NULL)
+ *   out_metrics  [n_users,5] f64: ndcg@k, hit@k, precision@k, recall@k, f1@k
+ */
+int dccf_rank_eval(const float* scores, const float* labels, const int64_t* iids,
+                   const int32_t* cand_rows, const int64_t* user_off, int64_t n_users, int32_t k,
+                   int64_t* out_topk_iid, int32_t* out_topk_row, double* out_metrics,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCCF_B200_H */
