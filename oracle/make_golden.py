@@ -1,0 +1,223 @@
+"""TEST INFRASTRUCTURE.  Generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference/src, through oracle/ref_harness.py) on CPU.  Run in the build container only:
+
+    python oracle/make_golden.py
+
+The fixtures are committed; the GPU box never needs the reference.
+"""
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh  # noqa: E402
+from dccf_b200 import synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+SENT = synth.DEFAULT_SENTENCE_MODEL
+
+
+def _params_of(model):
+    return {
+        'E_user': model.uid_embeddings.weight.detach().numpy().copy(),
+        'E_item': model.iid_embeddings.weight.detach().numpy().copy(),
+        'W': model.mlp[0].weight.detach().numpy().copy(),
+        'b': model.mlp[0].bias.detach().numpy().copy(),
+    }
+
+
+class _StubDP:
+    """prepare_batches() provider for BaseRunner.fit / predict (BaseRunner.py:170,143)."""
+    rank = 1
+
+    def __init__(self, batches):
+        self.batches = batches
+
+    def prepare_batches(self, data, batch_size, train):
+        return self.batches
+
+
+def make_train_fixture(name, U, I, F, P, steps, S=10, A=2, std=0.1, dropout=0.2, seed=2019, l2=1e-4, lr=1e-3):
+    ref = rh.load_reference()
+    tmp = tempfile.mkdtemp()
+    try:
+        d = os.path.join(tmp, 'g')
+        os.makedirs(d)
+        rs = np.random.RandomState(seed)
+        feat = (rs.standard_normal((I, F)) / np.sqrt(F)).astype(np.float32)
+        expo = rs.random_sample((U, I)).astype(np.float32)
+        np.save(os.path.join(d, 'g_%s.npy' % SENT), feat)
+        np.save(os.path.join(d, 'g.ips_expo_prob.npy'), expo)
+        with rh.cpu_shims():
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+            model = rh.build_reference_model(ref, d, 'g', SENT, U, I, sample_num=S, attribute_num=A, std=std,
+                                             random_seed=seed, model_path=os.path.join(tmp, 'm.pt'))
+            init = _params_of(model)
+            b = P // 2
+            batches, Xs = [], []
+            for t in range(steps):
+                u = rs.randint(0, U, size=b)
+                pos = rs.randint(0, I, size=b)
+                neg = rs.randint(0, I, size=b)
+                X = np.concatenate([np.stack([u, pos], 1), np.stack([u, neg], 1)]).astype(np.int64)
+                Y = np.concatenate([np.ones(b, np.float32), np.zeros(b, np.float32)])
+                Xs.append(X)
+                batches.append({'X': torch.from_numpy(X), 'Y': torch.from_numpy(Y), 'rank': 1,
+                                'sample_id': np.arange(2 * b), 'real_batch_size': b, 'total_batch_size': 2 * b})
+            outs = []
+            model.register_forward_hook(lambda m, i, o: outs.append(
+                (o['prediction'].detach().numpy().copy(), float(o['loss'].detach()))))
+            runner = ref.BaseRunner(optimizer='Adam', learning_rate=lr, epoch=1, batch_size=b, eval_batch_size=16384,
+                                    dropout=dropout, l2=l2, metrics='ndcg@5', check_epoch=1, early_stop=1)
+            rh.reset_tape()
+            runner.fit(model, None, _StubDP(batches), epoch=0)
+            calls = rh.tape().calls
+            final = _params_of(model)
+            opt = model.optimizer
+            names = ['E_user', 'E_item', 'W', 'b']
+            plist = [model.uid_embeddings.weight, model.iid_embeddings.weight, model.mlp[0].weight, model.mlp[0].bias]
+            out = {'feat': feat, 'expo': expo, 'S': S, 'A': A, 'std': std, 'dropout': dropout, 'l2': l2, 'lr': lr,
+                   'steps': steps, 'seed': seed}
+            for k, v in init.items():
+                out['init_' + k] = v
+            for k, v in final.items():
+                out['final_' + k] = v
+            for n, p in zip(names, plist):
+                out['m_' + n] = opt.state[p]['exp_avg'].numpy().copy()
+                out['v_' + n] = opt.state[p]['exp_avg_sq'].numpy().copy()
+                out['lastgrad_' + n] = p.grad.numpy().copy()    # after l2 term and clip (BaseRunner.py:181-185)
+            for t in range(steps):
+                out['X_%d' % t] = Xs[t]
+                out['sample_item_%d' % t] = calls[t]['sample_item'].numpy()
+                out['noise_%d' % t] = calls[t]['noise'].numpy()
+                if dropout > 0:
+                    out['mask_%d' % t] = calls[t]['masks'][0].numpy()
+                out['pred_%d' % t] = outs[t][0]
+                out['loss_%d' % t] = outs[t][1]
+
+            # an eval-mode predict through BaseRunner.predict (dropout off, ragged batch)
+            Pe = 37
+            Xe = np.stack([rs.randint(0, U, size=Pe), rs.randint(0, I, size=Pe)], 1).astype(np.int64)
+            ebatch = {'X': torch.from_numpy(Xe), 'Y': torch.zeros(Pe), 'rank': 1, 'sample_id': np.arange(Pe)}
+            rh.reset_tape()
+            pe = runner.predict(model, {'sample_id': np.arange(Pe)}, _StubDP([ebatch]))
+            c = rh.tape().calls[0]
+            out['eval_X'] = Xe
+            out['eval_sample_item'] = c['sample_item'].numpy()
+            out['eval_noise'] = c['noise'].numpy()
+            out['eval_pred'] = np.asarray(pe, dtype=np.float32)
+        np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), **out)
+        print(name, 'losses', [outs[t][1] for t in range(steps)])
+    finally:
+        shutil.rmtree(tmp)
+
+
+def make_sampler_fixture(name='sampler', U=30, I=40, seed=2019, test_neg_n=5, epochs=2, batch_size=16):
+    ref = rh.load_reference()
+    tmp = tempfile.mkdtemp()
+    try:
+        d = os.path.join(tmp, 's')
+        os.makedirs(d)
+        rs = np.random.RandomState(seed + 7)
+        rows = {'train': [], 'validation': [], 'test': []}
+        t = 0
+        for u in range(U):
+            # user 0: 17 train rows of 40 items -> the per-epoch negative pool shrinks below 20 % (np.random.choice
+            # branch, DP:490-493,505-512) during TRAIN sampling; user 1: 34 items overall -> the same branch when
+            # the TEST negatives are drawn (DP:482)
+            if u == 0:
+                n_train, n_val, n_test = 17, 1, 2
+            elif u == 1:
+                n_train, n_val, n_test = 14, 10, 10
+            else:
+                n_train, n_val, n_test = int(rs.randint(3, 9)), 1, (2 if u % 3 else 1)
+            n = n_train + n_val + n_test
+            items = rs.choice(I, n, replace=False)
+            for j, it in enumerate(items):
+                split = 'train' if j < n_train else ('validation' if j < n_train + n_val else 'test')
+                rows[split].append((u, int(it), int(rs.randint(1, 6)), t))
+                t += 1
+        for k, v in rows.items():
+            np.savetxt(os.path.join(d, 's.%s.csv' % k), np.array(v, dtype=np.int64), fmt='%d', delimiter=',')
+        np.save(os.path.join(d, 's_%s.npy' % SENT), np.zeros((I, 64), np.float32))
+        np.save(os.path.join(d, 's.ips_expo_prob.npy'), np.zeros((U, I), np.float32))
+        out = {'train_csv': np.array(rows['train']), 'validation_csv': np.array(rows['validation']),
+               'test_csv': np.array(rows['test']), 'seed': seed, 'test_neg_n': test_neg_n, 'epochs': epochs,
+               'batch_size': batch_size}
+        with rh.cpu_shims():
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+            dl = ref.DataLoader(path=tmp, dataset='s', label='label', sep=',')
+            model = rh.build_reference_model(ref, d, 's', SENT, dl.user_num, dl.item_num, random_seed=seed,
+                                             model_path=os.path.join(tmp, 'm.pt'))
+            dl.drop_neg()
+            dp = ref.DataProcessor(dl, model, rank=1, test_neg_n=test_neg_n)
+            out['user_num'], out['item_num'] = dl.user_num, dl.item_num
+            te = dp.get_test_data()                    # main.py:181-182 order: test first,
+            va = dp.get_validation_data()              # then validation (BaseRunner.py:223)
+            for nm, dd in (('test', te), ('validation', va)):
+                for k in ('uid', 'iid', 'Y', 'X', 'sample_id'):
+                    out['%s_%s' % (nm, k)] = np.asarray(dd[k])
+            tr = dp.get_train_data(epoch=-1)
+            out['train0_X'] = np.asarray(tr['X']).copy()
+            for ep in range(epochs):
+                data = dp.get_train_data(epoch=ep)
+                out['train_ep%d_order' % ep] = np.asarray(data['sample_id']).copy()
+                batches = dp.prepare_batches(data, batch_size, train=True)
+                out['train_ep%d_X' % ep] = np.concatenate([b['X'].numpy() for b in batches])
+                out['train_ep%d_Y' % ep] = np.concatenate([b['Y'].numpy() for b in batches])
+                out['train_ep%d_sample_id' % ep] = np.concatenate([b['sample_id'] for b in batches])
+                out['train_ep%d_nbatches' % ep] = len(batches)
+            out['np_state_after'] = np.random.get_state()[1][:8].astype(np.int64)
+        np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), **out)
+        print(name, 'test rows', len(out['test_X']), 'train rows', len(out['train0_X']))
+    finally:
+        shutil.rmtree(tmp)
+
+
+def make_metrics_fixture(name='metrics', seed=5):
+    ref = rh.load_reference()
+    rs = np.random.RandomState(seed)
+    uid, iid, Y = [], [], []
+    for u in range(25):
+        n_pos = rs.randint(1, 4)
+        n = n_pos + 50
+        items = rs.choice(500, n, replace=False)
+        uid += [u * 3] * n
+        iid += list(items)
+        Y += [1.0] * n_pos + [0.0] * 50
+    uid, iid, Y = np.array(uid), np.array(iid), np.array(Y, dtype=np.float32)
+    perm = rs.permutation(len(uid))
+    uid, iid, Y = uid[perm], iid[perm], Y[perm]
+    p = (rs.standard_normal(len(uid)) + 0.8 * Y).astype(np.float32)      # continuous -> no ties
+    data = {'uid': uid, 'iid': iid, 'Y': Y}
+    metrics = ['ndcg@5', 'hit@5', 'precision@5', 'recall@5', 'f1@5', 'ndcg@10', 'recall@1', 'precision@20']
+    vals = ref.BaseModel.evaluate_method(p, data, metrics)
+    kat = {
+        'ndcg_2120_k4_m1': ref.rank_metrics.ndcg_at_k([2, 1, 2, 0], 4, method=1),
+        'dcg_k2_m1': ref.rank_metrics.dcg_at_k([3, 2, 3, 0, 0, 1, 2, 2, 3, 0], 2, method=1),
+        'prec_001_k3': ref.rank_metrics.precision_at_k([0, 0, 1], 3),
+        'ndcg_0_k1': ref.rank_metrics.ndcg_at_k([0], 1, method=1),
+        'ndcg_1_k2': ref.rank_metrics.ndcg_at_k([1], 2, method=1),
+    }
+    np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), uid=uid, iid=iid, Y=Y, p=p, metrics=np.array(metrics),
+                        values=np.array([float(v) for v in vals], dtype=np.float64),
+                        **{'kat_' + k: np.float64(v) for k, v in kat.items()})
+    print(name, dict(zip(metrics, vals)), kat)
+
+
+if __name__ == '__main__':
+    os.makedirs(GOLDEN, exist_ok=True)
+    if '--skip-train' not in sys.argv:
+      make_train_fixture('train_f64', U=40, I=50, F=64, P=16, steps=3)
+      make_train_fixture('train_f768', U=24, I=30, F=768, P=8, steps=2)
+      make_train_fixture('train_nodrop', U=40, I=50, F=64, P=12, steps=2, dropout=0.0, std=0.0, S=4, A=3)
+    make_sampler_fixture()
+    make_metrics_fixture()
