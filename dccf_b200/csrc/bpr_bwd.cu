@@ -66,6 +66,7 @@ __device__ __forceinline__ float dpred_of(const BwdParams& prm, int64_t p) {
         const float g = -(1.f - sg);
         return is_pos ? g : -g;
     }
+    if (prm.loss_mode == 2) return __ldg(prm.Y + p);  // upstream gradient supplied by the caller (autograd)
     return 2.f * (__ldg(prm.pred + p) - __ldg(prm.Y + p)) / (float)prm.n_pairs;
 }
 
@@ -252,7 +253,7 @@ __device__ void bwd_record_role(const BwdParams& prm, int cta) {
 // role 3: scalar loss, fixed summation order (one warp, lane-strided then shuffle tree)
 // ---------------------------------------------------------------------------------------------
 __device__ void bwd_loss_role(const BwdParams& prm) {
-    if (threadIdx.x >= 32) return;
+    if (threadIdx.x >= 32 || prm.loss_mode == 2 || prm.out_loss == nullptr) return;
     const int lane = threadIdx.x;
     float s = 0.f;
     if (prm.loss_mode == 0) {
@@ -313,12 +314,13 @@ extern "C" int dccf_bpr_bwd(const dccf_dims* dims, const float* E_user, const fl
     DCCF_CHECK_ARG(dims->dim == D, "dccf_bpr_bwd: dim=%d but this build has D=%d", dims->dim, D);
     DCCF_CHECK_ARG(dims->feat_dim > 0 && dims->feat_dim % 64 == 0, "dccf_bpr_bwd: feat_dim=%d must be a positive multiple of 64", dims->feat_dim);
     DCCF_CHECK_ARG(dims->n_samples >= 0 && dims->n_attr >= 1, "dccf_bpr_bwd: bad n_samples/n_attr");
-    DCCF_CHECK_ARG(loss_mode == 0 || loss_mode == 1, "dccf_bpr_bwd: loss_mode must be 0 (BPR) or 1 (MSE)");
-    DCCF_CHECK_ARG(E_user && E_item && Feat && W && X && pred && save_h && save_w && out_loss && gW_part && gb_part &&
+    DCCF_CHECK_ARG(loss_mode >= 0 && loss_mode <= 2, "dccf_bpr_bwd: loss_mode must be 0 (BPR), 1 (MSE) or 2 (external d loss/d pred in Y)");
+    DCCF_CHECK_ARG(E_user && E_item && Feat && W && X && pred && save_h && save_w && gW_part && gb_part &&
                        gu_rec && gi_rec && rec_keys_u && rec_keys_i,
                    "dccf_bpr_bwd: null buffer");
+    DCCF_CHECK_ARG(loss_mode == 2 || out_loss, "dccf_bpr_bwd: out_loss is null");
     DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item, "dccf_bpr_bwd: sample_item is null");
-    DCCF_CHECK_ARG(loss_mode == 0 || Y, "dccf_bpr_bwd: MSE needs Y");
+    DCCF_CHECK_ARG(loss_mode == 0 || Y, "dccf_bpr_bwd: loss_mode %d needs Y", loss_mode);
     DCCF_CHECK_ARG(rng->noise_mode >= 0 && rng->noise_mode <= 2 && rng->mask_mode >= 0 && rng->mask_mode <= 2, "dccf_bpr_bwd: bad rng mode");
     DCCF_CHECK_ARG(rng->noise_mode != 1 || rng->noise, "dccf_bpr_bwd: noise_mode 1 needs the noise tensor");
     DCCF_CHECK_ARG(rng->mask_mode != 1 || rng->mask, "dccf_bpr_bwd: mask_mode 1 needs the mask tensor");

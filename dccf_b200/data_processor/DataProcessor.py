@@ -1,0 +1,320 @@
+"""Batch producer / negative sampler with the interface and the exact sampling semantics of the
+reference's src/data_processor/DataProcessor.py:15-524.
+
+Index parity contract: every `np.random` call the reference makes is made here in
+the same order with the same arguments — `np.random.randint(item_num)` rejection draws
+(DataProcessor.py:498-504), the `np.random.choice(remain, neg_n, replace=False)` branch when fewer than
+20 % of the items remain (DP:490-493,505-512) and the replayed-state epoch shuffle
+(src/utils/utils.py:82-92) — so negatives and batch contents are bit-identical under the same seed
+(checked against fixtures produced by the reference: tests/golden/sampler.npz).
+
+What is different is the data movement: the reference uploads every tensor of every batch separately
+(`numpy_to_torch` per field, DP:138-207); here one epoch is assembled into a single [rows,2] int64 array,
+uploaded once, and the per-batch feed dicts hold views of it.
+"""
+import logging
+from collections import defaultdict
+
+import numpy as np
+import pandas as pd
+import torch
+
+from ..utils import global_p, utils
+
+
+class DataProcessor(object):
+    data_columns = ['X']
+
+    @staticmethod
+    def parse_dp_args(parser):
+        """--test_neg_n, default 100 (DataProcessor.py:19-27)."""
+        parser.add_argument('--test_neg_n', type=int, default=100,
+                            help='Negative sample num for each instance in test/validation set.')
+        return parser
+
+    def __init__(self, data_loader, model, rank, test_neg_n):
+        self.data_loader = data_loader
+        self.model = model
+        self.rank = rank
+        self.test_neg_n = test_neg_n
+        self.train_data = self.validation_data = self.test_data = None
+        if self.rank == 1:
+            # per-user positive sets: what a negative must avoid (DataProcessor.py:44-53)
+            self.train_history_dict = defaultdict(set)
+            for uid, items in data_loader.train_user_his.items():
+                self.train_history_dict[uid] = set(items)
+            self.vt_history_dict = defaultdict(set)
+            for uid, items in data_loader.vt_user_his.items():
+                self.vt_history_dict[uid] = set(items)
+        self.vt_batches_buffer = {}
+
+    # ---- data dicts --------------------------------------------------------------------------
+    def get_train_data(self, epoch):
+        """Train dict; shuffled in place (cumulatively) when epoch >= 0 (DataProcessor.py:57-71)."""
+        if self.train_data is None or epoch < 0:
+            logging.info('Prepare Train Data...')
+            self.train_data = self.format_data_dict(self.data_loader.train_df)
+            self.train_data[global_p.K_SAMPLE_ID] = np.arange(0, len(self.train_data['Y']))
+        if epoch >= 0:
+            utils.shuffle_in_unison_scary(self.train_data)
+        return self.train_data
+
+    def _vt_data(self, df):
+        if self.rank == 1:
+            neg_df = self.generate_neg_df(uid_list=df['uid'].tolist(), iid_list=df['iid'].tolist(), df=df,
+                                          neg_n=self.test_neg_n, train=False)
+            df = pd.concat([df, neg_df], ignore_index=True)
+        data = self.format_data_dict(df)
+        data[global_p.K_SAMPLE_ID] = np.arange(0, len(data['Y']))
+        return data
+
+    def get_validation_data(self):
+        """Validation positives + test_neg_n negatives per distinct user, built once (DP:73-90)."""
+        if self.validation_data is None:
+            logging.info('Prepare Validation Data...')
+            self.validation_data = self._vt_data(self.data_loader.validation_df)
+        return self.validation_data
+
+    def get_test_data(self):
+        """Test positives + test_neg_n negatives per distinct user, built once (DP:92-111)."""
+        if self.test_data is None:
+            logging.info('Prepare Test Data...')
+            self.test_data = self._vt_data(self.data_loader.test_df)
+        return self.test_data
+
+    def get_train_batches(self, batch_size, epoch):
+        return self.prepare_batches(self.get_train_data(epoch), batch_size, train=True)
+
+    def get_validation_batches(self, batch_size):
+        return self.prepare_batches(self.get_validation_data(), batch_size, train=False)
+
+    def get_test_batches(self, batch_size):
+        return self.prepare_batches(self.get_test_data(), batch_size, train=False)
+
+    # ---- feed dicts --------------------------------------------------------------------------
+    def _get_feed_dict_rt(self, data, batch_start, batch_size, train):
+        """Plain slice of the data dict (DataProcessor.py:138-158)."""
+        end = min(len(data['X']), batch_start + batch_size)
+        real = end - batch_start
+        feed = {'train': train, 'rank': 0, global_p.K_SAMPLE_ID: data[global_p.K_SAMPLE_ID][batch_start:end]}
+        y = data['Y'][batch_start:end] if 'Y' in data else np.zeros(shape=real)
+        feed['Y'] = utils.numpy_to_torch(y)
+        for c in self.data_columns:
+            feed[c] = utils.numpy_to_torch(data[c][batch_start:end])
+        return feed
+
+    def _get_feed_dict_rk(self, data, batch_start, batch_size, train, neg_data=None):
+        """Top-n batch: eval = plain slice with rank 1; train = [positives ; their negatives]
+        (DataProcessor.py:160-207)."""
+        if not train:
+            feed = self._get_feed_dict_rt(data, batch_start, batch_size, train)
+            feed['rank'] = 1
+            return feed
+        end = min(len(data['X']), batch_start + batch_size)
+        real = end - batch_start
+        if neg_data is None:
+            logging.warning('neg_data is None')
+            neg_df = self.generate_neg_df(uid_list=data['uid'][batch_start:end], iid_list=data['iid'][batch_start:end],
+                                          df=self.data_loader.train_df, neg_n=1, train=True)
+            neg_cols = {c: self.format_data_dict(neg_df)[c] for c in self.data_columns}
+        else:
+            neg_cols = {c: neg_data[c][batch_start:end] for c in self.data_columns}
+        y = np.concatenate([np.ones(real, dtype=np.float32), np.zeros(real, dtype=np.float32)])
+        sample_id = data[global_p.K_SAMPLE_ID][batch_start:end]
+        feed = {'train': train, 'rank': 1, 'Y': utils.numpy_to_torch(y),
+                global_p.K_SAMPLE_ID: np.concatenate([sample_id, sample_id + len(self.train_data['Y'])]),
+                global_p.REAL_BATCH_SIZE: real, global_p.TOTAL_BATCH_SIZE: real * 2}
+        for c in self.data_columns:
+            feed[c] = utils.numpy_to_torch(np.concatenate([data[c][batch_start:end], neg_cols[c]]))
+        return feed
+
+    def get_feed_dict(self, data, batch_start, batch_size, train, neg_data=None):
+        if self.rank == 1:
+            return self._get_feed_dict_rk(data, batch_start, batch_size, train, neg_data)
+        return self._get_feed_dict_rt(data, batch_start, batch_size, train)
+
+    # ---- whole-epoch batch lists -----------------------------------------------------------------
+    def _epoch_views(self, rows_X, rows_Y, bounds):
+        """One host->device copy for the whole list, feed dicts get views (replaces the per-field
+        `numpy_to_torch` uploads of DP:138-207)."""
+        X = torch.from_numpy(np.ascontiguousarray(rows_X))
+        Y = torch.from_numpy(np.ascontiguousarray(rows_Y))
+        if torch.cuda.device_count() > 0:
+            X = X.pin_memory().cuda(non_blocking=True)
+            Y = Y.pin_memory().cuda(non_blocking=True)
+        return [(X[a:b], Y[a:b]) for a, b in bounds]
+
+    def _prepare_batches_rt(self, data, batch_size, train):
+        """Rating/click prediction batches (DataProcessor.py:209-225)."""
+        if data is None:
+            return None
+        n = len(data['X'])
+        assert n > 0
+        total = (n + batch_size - 1) // batch_size
+        bounds = [(k * batch_size, min(n, (k + 1) * batch_size)) for k in range(total)]
+        y = data['Y'] if 'Y' in data else np.zeros(n, dtype=np.float32)
+        views = self._epoch_views(np.asarray(data['X']), np.asarray(y), bounds)
+        batches = []
+        for (a, b), (xv, yv) in zip(bounds, views):
+            batches.append({'train': train, 'rank': 0, global_p.K_SAMPLE_ID: data[global_p.K_SAMPLE_ID][a:b],
+                            'Y': yv, 'X': xv})
+        return batches
+
+    def _prepare_batches_rk(self, data, batch_size, train):
+        """Top-n batches; for training one negative per positive is drawn for the WHOLE epoch first, in
+        the current row order (DataProcessor.py:227-250)."""
+        if data is None:
+            return None
+        n = len(data['X'])
+        assert n > 0
+        if not train:
+            batches = self._prepare_batches_rt(data, batch_size, train)
+            for b in batches:
+                b['rank'] = 1
+            return batches
+        neg_df = self.generate_neg_df(uid_list=data['uid'], iid_list=data['iid'], df=self.data_loader.train_df,
+                                      neg_n=1, train=True)
+        neg_X = self.format_data_dict(neg_df)['X']
+        pos_X = np.asarray(data['X'])
+        total = (n + batch_size - 1) // batch_size
+        rows_X = np.empty((2 * n, pos_X.shape[1]), dtype=pos_X.dtype)
+        rows_Y = np.empty(2 * n, dtype=np.float32)
+        bounds, spans = [], []
+        for k in range(total):
+            a, b = k * batch_size, min(n, (k + 1) * batch_size)
+            real = b - a
+            rows_X[2 * a:2 * a + real] = pos_X[a:b]
+            rows_X[2 * a + real:2 * b] = neg_X[a:b]
+            rows_Y[2 * a:2 * a + real] = 1.0
+            rows_Y[2 * a + real:2 * b] = 0.0
+            bounds.append((2 * a, 2 * b))
+            spans.append((a, b))
+        views = self._epoch_views(rows_X, rows_Y, bounds)
+        n_train = len(self.train_data['Y'])
+        batches = []
+        for (a, b), (xv, yv) in zip(spans, views):
+            sid = data[global_p.K_SAMPLE_ID][a:b]
+            batches.append({'train': train, 'rank': 1, 'Y': yv, 'X': xv,
+                            global_p.K_SAMPLE_ID: np.concatenate([sid, sid + n_train]),
+                            global_p.REAL_BATCH_SIZE: b - a, global_p.TOTAL_BATCH_SIZE: 2 * (b - a)})
+        return batches
+
+    def prepare_batches(self, data, batch_size, train):
+        """All batches of a data dict; validation/test lists are cached (DataProcessor.py:252-275)."""
+        key = ''
+        if data is self.validation_data:
+            key = 'validation_' + str(batch_size)
+        elif data is self.test_data:
+            key = 'test_' + str(batch_size)
+        if key in self.vt_batches_buffer:
+            return self.vt_batches_buffer[key]
+        if self.rank == 1:
+            batches = self._prepare_batches_rk(data, batch_size, train)
+        else:
+            batches = self._prepare_batches_rt(data, batch_size, train)
+        if key:
+            self.vt_batches_buffer[key] = batches
+        return batches
+
+    # ---- DataFrame -> data dict ------------------------------------------------------------------
+    def format_data_dict(self, df):
+        """uid / iid / Y / X of a DataFrame; X = [uid, iid] (+ offset feature ids when the model uses
+        side features) as int64 (DataProcessor.py:292-356)."""
+        loader, model = self.data_loader, self.model
+        data, id_cols = {}, []
+        for c in ('uid', 'iid'):
+            if c in df:
+                id_cols.append(c)
+                data[c] = np.array(df[c].values, copy=True)
+        if loader.label in df.columns:
+            data['Y'] = np.array(df[loader.label], dtype=np.float32)
+        else:
+            logging.warning('No Labels In Data: ' + loader.label)
+            data['Y'] = np.zeros(len(df), dtype=np.float32)
+        ui = df[id_cols]
+        out = ui
+        if loader.user_df is not None and model.include_user_features:
+            out = pd.merge(out, loader.user_df, on='uid', how='left')
+        if loader.item_df is not None and model.include_item_features:
+            out = pd.merge(out, loader.item_df, on='iid', how='left')
+        out = out.fillna(0)
+        if model.include_context_features:
+            out = pd.concat([out, df[loader.context_features]], axis=1, ignore_index=True)
+        if not model.include_id:
+            out = out.drop(columns=['uid', 'iid'])
+        base = 0
+        shifted = {}
+        for f in out.columns:
+            shifted[f] = out[f].values + base
+            base += int(loader.column_max[f] + 1)
+        feats = np.stack([shifted[f] for f in out.columns], axis=1) if len(out.columns) else \
+            np.zeros((len(df), 0), dtype=np.int64)
+        if model.append_id:
+            data['X'] = np.concatenate([ui.values, feats], axis=1).astype(int)
+        else:
+            data['X'] = feats.astype(int)
+        assert len(data['X']) == len(data['Y'])
+        return data
+
+    # ---- negative sampling -----------------------------------------------------------------------
+    def generate_neg_df(self, uid_list, iid_list, df, neg_n, train):
+        """DataFrame of sampled negatives with df's columns and label 0 (DataProcessor.py:408-444).
+        Evaluation: neg_n per DISTINCT user, in first-appearance order (DP:420-430)."""
+        if not train:
+            seen, f_u, f_i = set(), [], []
+            for u, i in zip(uid_list, iid_list):
+                if u not in seen:
+                    seen.add(u)
+                    f_u.append(u)
+                    f_i.append(i)
+        else:
+            f_u, f_i = uid_list, iid_list
+        neg_df = self._sample_neg_from_uid_list(uids=f_u, neg_n=neg_n, train=train, other_infos={'iid': f_i})
+        other_cols = [c for c in df.columns if c not in ('uid', 'iid')]
+        if other_cols:
+            # the positive row's remaining columns travel with its negatives (DP:437-442)
+            first = df.drop_duplicates(subset=['uid', 'iid'])
+            neg_df = pd.merge(neg_df, first, on=['uid', 'iid'], how='left')
+        neg_df = neg_df.drop(columns=['iid']).rename(columns={'iid_neg': 'iid'})
+        neg_df = neg_df[list(df.columns)]
+        neg_df[self.data_loader.label] = 0
+        return neg_df
+
+    def _sample_neg_from_uid_list(self, uids, neg_n, train, other_infos=None):
+        """The rejection sampler (DataProcessor.py:446-524), draw for draw."""
+        other_infos = other_infos or {}
+        item_num = self.data_loader.item_num
+        randint, choice = np.random.randint, np.random.choice
+        train_hist, vt_hist = self.train_history_dict, self.vt_history_dict
+        out_u, out_i = [], []
+        drawn = defaultdict(set)            # negatives already handed to a user (kept across the epoch when train)
+        for uid in uids:
+            if train:
+                taken = train_hist[uid] | drawn[uid]
+            else:
+                taken = train_hist[uid] | vt_hist[uid] | drawn[uid]
+            remain = item_num - len(taken)
+            pool = None
+            if 1.0 * remain / item_num < 0.2:
+                pool = [i for i in range(1, item_num) if i not in taken]      # item 0 excluded here only (DP:493)
+            assert remain >= neg_n
+            mine = drawn[uid]
+            if pool is None:
+                for _ in range(neg_n):
+                    iid = randint(item_num)
+                    while iid in taken or iid in mine:
+                        iid = randint(item_num)
+                    out_u.append(uid)
+                    out_i.append(iid)
+                    mine.add(iid)
+            else:
+                iids = choice(pool, neg_n, replace=False)
+                out_u.extend([uid] * neg_n)
+                out_i.extend(iids)
+                mine.update(iids)
+            if not train:
+                drawn = defaultdict(set)
+        neg_df = pd.DataFrame({'uid': np.asarray(out_u, dtype=np.int64), 'iid_neg': np.asarray(out_i, dtype=np.int64)})
+        for info, values in other_infos.items():
+            neg_df[info] = np.repeat(np.asarray(values), neg_n)
+        return neg_df

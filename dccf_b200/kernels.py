@@ -1,0 +1,125 @@
+"""Tensor-level wrappers over the C-ABI (dccf_b200/_lib.py).  Each function launches hand-written
+sm_100a kernels on the current CUDA stream; none has a CPU implementation.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import Adam, Dims, Expo, Rng, check, ptr, stream_ptr
+
+D = _lib.DIM
+
+
+def make_dims(n_users, n_items, feat_dim, n_samples, n_attr, dim=D):
+    return Dims(int(n_users), int(n_items), int(dim), int(feat_dim), int(n_samples), int(n_attr))
+
+
+def make_expo(dense=None, ipsmf=None):
+    """Exposure source: a dense [U,I] matrix (src/models/DCCF.py:64) or IPSBiasedMF factors
+    (src/models/IPSBiasedMF.py:37-57) as a dict of CUDA tensors + two floats."""
+    e = Expo()
+    if ipsmf is not None:
+        e.mode = 1
+        e.mf_user = ptr(ipsmf['mf_user']).value
+        e.mf_item = ptr(ipsmf['mf_item']).value
+        e.mf_user_bias = ptr(ipsmf['mf_user_bias']).value
+        e.mf_item_bias = ptr(ipsmf['mf_item_bias']).value
+        e.propensity = ptr(ipsmf['propensity']).value
+        e.mf_global_bias = float(ipsmf['mf_global_bias'])
+        e.mf_min_propensity = float(ipsmf['mf_min_propensity'])
+    else:
+        e.mode = 0
+        e.dense = ptr(dense).value
+    return e
+
+
+def make_rng(noise=None, mask=None, noise_std=0.0, p_drop=0.0, seed=0, offset=0, offset_dev=None,
+             generate_noise=False, generate_mask=False):
+    """mode 1 when a tensor is given, mode 2 when generate_* is set, else mode 0 (absent)."""
+    r = Rng()
+    r.noise_mode = 1 if noise is not None else (2 if generate_noise else 0)
+    r.mask_mode = 1 if mask is not None else (2 if generate_mask else 0)
+    r.noise = ptr(noise).value if noise is not None else None
+    r.mask = ptr(mask).value if mask is not None else None
+    r.noise_std = float(noise_std)
+    r.p_drop = float(p_drop)
+    r.seed = int(seed) & 0xffffffffffffffff
+    r.offset = int(offset) & 0xffffffffffffffff
+    r.offset_dev = ptr(offset_dev).value if offset_dev is not None else None
+    return r
+
+
+def make_adam(lr, l2, weight_decay, step=1, step_dev=None, beta1=0.9, beta2=0.999, eps=1e-8, clip=50.0):
+    a = Adam()
+    a.lr, a.beta1, a.beta2, a.eps = float(lr), float(beta1), float(beta2), float(eps)
+    a.l2, a.weight_decay, a.clip = float(l2), float(weight_decay), float(clip)
+    a.step = int(step)
+    a.step_dev = ptr(step_dev).value if step_dev is not None else None
+    return a
+
+
+def noise_fill(out, std, seed, offset, row0=0):
+    lib = _lib.load()
+    n_rows, F = out.shape
+    check(lib.dccf_noise_fill(ptr(out), n_rows, F, float(std), int(seed), int(offset), int(row0), stream_ptr()),
+          'dccf_noise_fill')
+    return out
+
+
+def dropout_mask_fill(out, p_drop, seed, offset, row0=0):
+    lib = _lib.load()
+    n_rows, dim = out.shape
+    check(lib.dccf_dropout_mask_fill(ptr(out), n_rows, dim, float(p_drop), int(seed), int(offset), int(row0),
+                                     stream_ptr()), 'dccf_dropout_mask_fill')
+    return out
+
+
+def score_fwd(dims, E_user, E_item, Feat, W, b, expo, X, sample_item, rng, out_pred, ws_rows, ws_wt, save_h=None,
+              save_w=None, err_flag=None):
+    lib = _lib.load()
+    n_pairs = X.shape[0]
+    check(lib.dccf_score_fwd(ctypes.byref(dims), ptr(E_user), ptr(E_item), ptr(Feat), ptr(W), ptr(b),
+                             ctypes.byref(expo), ptr(X), ptr(sample_item), n_pairs, ctypes.byref(rng), ptr(out_pred),
+                             ptr(ws_rows), ptr(ws_wt), ptr(save_h), ptr(save_w), ptr(err_flag), stream_ptr()),
+          'dccf_score_fwd')
+    return out_pred
+
+
+def bwd_splits(n_rows):
+    return int(_lib.load().dccf_bwd_splits(int(n_rows)))
+
+
+def bpr_bwd(dims, E_user, E_item, Feat, W, X, sample_item, Y, rng, loss_mode, pred, save_h, save_w, out_loss, gW_part,
+            gb_part, gu_rec, gi_rec, rec_keys_u, rec_keys_i):
+    lib = _lib.load()
+    n_pairs = X.shape[0]
+    check(lib.dccf_bpr_bwd(ctypes.byref(dims), ptr(E_user), ptr(E_item), ptr(Feat), ptr(W), ptr(X), ptr(sample_item),
+                           ptr(Y), n_pairs, ctypes.byref(rng), int(loss_mode), ptr(pred), ptr(save_h), ptr(save_w),
+                           ptr(out_loss), ptr(gW_part), ptr(gb_part), ptr(gu_rec), ptr(gi_rec), ptr(rec_keys_u),
+                           ptr(rec_keys_i), stream_ptr()), 'dccf_bpr_bwd')
+
+
+def adam_sweep(table, m, v, rec_keys, rec_grads, n_rec, head, nxt, hp):
+    lib = _lib.load()
+    check(lib.dccf_adam_sweep(ptr(table), ptr(m), ptr(v), table.shape[0], ptr(rec_keys), ptr(rec_grads), int(n_rec),
+                              ptr(head), ptr(nxt), ctypes.byref(hp), stream_ptr()), 'dccf_adam_sweep')
+
+
+def adam_dense(p, m, v, g_parts, n_parts, part_stride, hp):
+    lib = _lib.load()
+    check(lib.dccf_adam_dense(ptr(p), ptr(m), ptr(v), p.numel(), ptr(g_parts), int(n_parts), int(part_stride),
+                              ctypes.byref(hp), stream_ptr()), 'dccf_adam_dense')
+
+
+def state_advance(step_dev, offset_dev, offset_inc=1):
+    lib = _lib.load()
+    check(lib.dccf_state_advance(ptr(step_dev), ptr(offset_dev), int(offset_inc), stream_ptr()), 'dccf_state_advance')
+
+
+def rank_eval(scores, labels, iids, cand_rows, user_off, k, out_metrics, out_topk_iid=None, out_topk_row=None):
+    lib = _lib.load()
+    n_users = user_off.shape[0] - 1
+    check(lib.dccf_rank_eval(ptr(scores), ptr(labels), ptr(iids), ptr(cand_rows), ptr(user_off), n_users, int(k),
+                             ptr(out_topk_iid), ptr(out_topk_row), ptr(out_metrics), stream_ptr()), 'dccf_rank_eval')
+    return out_metrics

@@ -1,0 +1,324 @@
+"""DCCF with the reference's model protocol (src/models/DCCF.py:14-127) on hand-written sm_100a kernels.
+
+`predict` / `forward` keep the reference's feed_dict contract and outputs.  The device work of
+DCCF.predict lines 74-100 (index expansion, three gathers, noise, cat, Linear+ReLU+Dropout, dot,
+exposure softmax, backdoor sum) is one call of dccf_score_fwd; the backward of the whole graph is one
+call of dccf_bpr_bwd; l2 + clip + Adam is dccf_adam_sweep / dccf_adam_dense.  Two ways to train:
+
+  * `train_step(feed_dict, ...)` — the fused path used by dccf_b200's BaseRunner (no autograd at all);
+  * `forward(feed_dict)` under autograd — the prediction is a torch.autograd.Function whose backward
+    calls the same CUDA kernel, so an unmodified reference-style runner (loss.backward(), any torch
+    optimizer) also works.
+
+Random inputs.  The reference draws confounder items on the torch CPU generator (DCCF.py:72), noise
+and dropout on the CUDA generator (DCCF.py:87,94).  Here: confounders are drawn by the same
+`torch.randint` call on the CPU generator (bit-identical indices); noise and dropout come from the
+library's counter-based Philox stream generated inside the kernels (seed = random_seed, one counter
+per predict call) unless the feed_dict carries explicit tensors under 'sample_item', 'noise',
+'dropout_mask' — that is how the parity tests inject the reference's own draws.
+
+There is no CPU implementation: calling predict without CUDA raises.
+"""
+import os
+
+import numpy as np
+import torch
+
+from .. import kernels
+from .DMF import DMF
+
+
+class FusedAdamState(object):
+    """Optimizer state of the fused path: exp_avg / exp_avg_sq per parameter, step count, and the
+    persistent per-row list heads of the gradient-record scatter.  Stands where the reference keeps a
+    torch.optim.Adam in `model.optimizer` (src/runners/BaseRunner.py:168-169)."""
+
+    def __init__(self, model, lr, l2, weight_decay, beta1=0.9, beta2=0.999, eps=1e-8, clip=50.0):
+        self.lr, self.l2, self.weight_decay = lr, l2, weight_decay
+        self.beta1, self.beta2, self.eps, self.clip = beta1, beta2, eps, clip
+        self.step_count = 0
+        self.params = {'E_user': model.uid_embeddings.weight, 'E_item': model.iid_embeddings.weight,
+                       'W': model.mlp[0].weight, 'b': model.mlp[0].bias}
+        self.exp_avg = {k: torch.zeros_like(p.data) for k, p in self.params.items()}
+        self.exp_avg_sq = {k: torch.zeros_like(p.data) for k, p in self.params.items()}
+        dev = model.uid_embeddings.weight.device
+        self.head_u = torch.full((model.user_num,), -1, dtype=torch.int32, device=dev)
+        self.head_i = torch.full((model.item_num,), -1, dtype=torch.int32, device=dev)
+
+    def hp(self, step=None):
+        return kernels.make_adam(self.lr, self.l2, self.weight_decay, step=self.step_count if step is None else step,
+                                 beta1=self.beta1, beta2=self.beta2, eps=self.eps, clip=self.clip)
+
+    def zero_grad(self):
+        pass
+
+    def state_dict(self):
+        return {'step': self.step_count, 'exp_avg': self.exp_avg, 'exp_avg_sq': self.exp_avg_sq,
+                'lr': self.lr, 'l2': self.l2, 'weight_decay': self.weight_decay}
+
+
+class _ScoreFn(torch.autograd.Function):
+    """pred = DCCF score; backward through dccf_bpr_bwd with the upstream gradient (loss_mode 2)."""
+
+    @staticmethod
+    def forward(ctx, E_user, E_item, W, b, model, call):
+        pred = model._launch_fwd(call, save=True)
+        ctx.model, ctx.call = model, call
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        model, call = ctx.model, ctx.call
+        rec = model._launch_bwd(call, loss_mode=2, Y=dpred.contiguous().float())
+        gE_user = torch.zeros_like(model.uid_embeddings.weight)
+        gE_item = torch.zeros_like(model.iid_embeddings.weight)
+        gE_user.index_add_(0, rec['keys_u'].long(), rec['gu_rec'])
+        gE_item.index_add_(0, rec['keys_i'].long(), rec['gi_rec'])
+        gW = rec['gW_part'].sum(dim=0)
+        gb = rec['gb_part'].sum(dim=0)
+        return gE_user, gE_item, gW, gb, None, None
+
+
+class DCCF(DMF):
+    @staticmethod
+    def parse_model_args(parser, model_name='DCCF'):
+        """Flags and defaults of DCCF.py:15-21 (note the dashes)."""
+        parser.add_argument('--sentence-model', type=str, default='paraphrase-distilroberta-base-v1',
+                            help='the name of sentence model')
+        parser.add_argument('--sample-num', type=int, default=10, help='the number of sampled items')
+        parser.add_argument('--attribute-num', type=int, default=2, help='the number of item features')
+        parser.add_argument('--std', type=float, default=0.1, help='std of feature distribution')
+        return DMF.parse_model_args(parser, model_name)
+
+    def __init__(self, path, dataset, sentence_model, sample_num, attribute_num, std, label_min, label_max,
+                 feature_num, user_num, item_num, u_vector_size, i_vector_size, n_layers, random_seed, model_path,
+                 feature_embedding=None, expo_prob=None, expo_factors=None):
+        """Reference constructor arguments (src/main.py:137-145).  The three trailing keyword arguments
+        are additions: in-memory tables instead of the .npy files, and IPSBiasedMF factors for
+        on-the-fly exposure (scaled config) instead of the dense user x item matrix."""
+        self.path = path
+        self.dataset = dataset
+        self.sentence_model = sentence_model
+        self.sample_num = sample_num
+        self.attribute_num = attribute_num
+        self.std = std
+        self._given = (feature_embedding, expo_prob, expo_factors)
+        DMF.__init__(self, label_min=label_min, label_max=label_max, feature_num=feature_num, user_num=user_num,
+                     item_num=item_num, u_vector_size=u_vector_size, i_vector_size=i_vector_size, n_layers=n_layers,
+                     random_seed=random_seed, model_path=model_path)
+        self._rng_offset = 0
+        self._ws = {}
+        self._err_flag = None
+
+    # ---- construction ------------------------------------------------------------------------
+    @staticmethod
+    def _table_device():
+        return torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
+
+    def _init_weights(self):
+        """Same modules in the same order as DCCF.py:47-64, so the torch CPU generator is consumed
+        identically and `apply(init_paras)` yields the reference's initial weights for a given seed."""
+        feature_embedding, expo_prob, expo_factors = self._given
+        dev = self._table_device()
+        self.uid_embeddings = torch.nn.Embedding(self.user_num, self.ui_vector_size)
+        self.iid_embeddings = torch.nn.Embedding(self.item_num, self.ui_vector_size)
+        if feature_embedding is None:
+            feature_embedding = np.load(os.path.join(self.path, self.dataset + '_' + self.sentence_model + '.npy'))
+        # plain attributes, not parameters/buffers: absent from state_dict like in the reference (DCCF.py:55,64)
+        self.feature_embedding = torch.as_tensor(feature_embedding, dtype=torch.float32).to(dev).contiguous()
+        self.mlp = torch.nn.ModuleList([torch.nn.Linear(self.ui_vector_size + self.feature_embedding.shape[1],
+                                                        self.ui_vector_size)])
+        for _ in range(self.n_layers - 1):
+            self.mlp.append(torch.nn.Linear(self.ui_vector_size, self.ui_vector_size))
+        self.expo_factors = None
+        self.expo_prob = None
+        if expo_factors is not None:
+            self.expo_factors = {k: (torch.as_tensor(v, dtype=torch.float32).to(dev).contiguous()
+                                     if k not in ('mf_global_bias', 'mf_min_propensity') else float(v))
+                                 for k, v in expo_factors.items()}
+        else:
+            if expo_prob is None:
+                expo_prob = np.load(os.path.join(self.path, self.dataset + '.ips_expo_prob.npy'))
+            self.expo_prob = torch.as_tensor(expo_prob, dtype=torch.float32).to(dev).contiguous()
+
+    # ---- kernel plumbing ---------------------------------------------------------------------
+    def _dims(self):
+        return kernels.make_dims(self.user_num, self.item_num, self.feature_embedding.shape[1], self.sample_num,
+                                 self.attribute_num, dim=self.ui_vector_size)
+
+    def _expo(self):
+        if self.expo_factors is not None:
+            return kernels.make_expo(ipsmf=self.expo_factors)
+        return kernels.make_expo(dense=self.expo_prob)
+
+    def _buf(self, name, shape, dtype):
+        """Grow-only workspace tensor on the parameters' device."""
+        n = 1
+        for s in shape:
+            n *= int(s)
+        cur = self._ws.get(name)
+        if cur is None or cur.numel() < n or cur.dtype != dtype:
+            cur = torch.empty(max(n, 1), dtype=dtype, device=self.uid_embeddings.weight.device)
+            self._ws[name] = cur
+        return cur[:n].view(*shape) if n > 0 else cur[:0].view(*shape)
+
+    def _check_ready(self):
+        w = self.uid_embeddings.weight
+        if not w.is_cuda:
+            raise RuntimeError('DCCF (dccf_b200) runs on CUDA only: move the model with .cuda() on a B200; there is no '
+                               'CPU fallback')
+        if self.n_layers != 1:
+            raise NotImplementedError('the fused kernels implement the default --n_layers 1 (one Linear(D+F -> D))')
+        if self.ui_vector_size != kernels.D:
+            raise NotImplementedError('the kernels are compiled for u_vector_size = i_vector_size = %d' % kernels.D)
+        if self.feature_embedding.device != w.device:
+            self.feature_embedding = self.feature_embedding.to(w.device)
+            if self.expo_prob is not None:
+                self.expo_prob = self.expo_prob.to(w.device)
+            if self.expo_factors is not None:
+                self.expo_factors = {k: (v.to(w.device) if torch.is_tensor(v) else v)
+                                     for k, v in self.expo_factors.items()}
+        if self._err_flag is None or self._err_flag.device != w.device:
+            self._err_flag = torch.zeros(1, dtype=torch.int32, device=w.device)
+
+    def _make_call(self, feed_dict):
+        """Resolve the inputs of one predict call: ids, confounder draw, rng modes."""
+        self._check_ready()
+        dev = self.uid_embeddings.weight.device
+        X = feed_dict['X']
+        if not torch.is_tensor(X):
+            X = torch.as_tensor(np.asarray(X))
+        X = X.to(dev, torch.int64)
+        if X.dim() != 2 or X.shape[1] < 2:
+            raise ValueError("feed_dict['X'] must be [P, >=2] with uid in column 0 and iid in column 1")
+        if X.shape[1] != 2 or not X.is_contiguous():
+            X = X[:, :2].contiguous()
+        P = X.shape[0]
+        S, A = self.sample_num, self.attribute_num
+        sample_item = feed_dict.get('sample_item')
+        if sample_item is None:
+            # DCCF.py:72 — same call on the same (CPU) generator as the reference
+            sample_item = torch.randint(self.item_num, size=(P, S))
+        sample_item = sample_item.to(dev, torch.int64, non_blocking=True).contiguous()
+        p_drop = float(feed_dict.get('dropout', 0.0))
+        noise, mask = feed_dict.get('noise'), feed_dict.get('dropout_mask')
+        if noise is not None:
+            noise = noise.to(dev, torch.float32).contiguous()
+        if mask is not None:
+            mask = mask.to(dev, torch.float32).contiguous()
+        self._rng_offset += 1
+        rng = kernels.make_rng(noise=noise, mask=mask, noise_std=self.std, p_drop=p_drop, seed=self.random_seed,
+                               offset=self._rng_offset, generate_noise=(noise is None and self.std > 0),
+                               generate_mask=(mask is None and p_drop > 0))
+        return {'X': X, 'sample_item': sample_item, 'rng': rng, 'noise': noise, 'mask': mask, 'P': P,
+                'N': P * (S + 1) * A}
+
+    def _launch_fwd(self, call, save):
+        P, N = call['P'], call['N']
+        D, Z = self.ui_vector_size, self.sample_num + 1
+        K = D + self.feature_embedding.shape[1]
+        dev = self.uid_embeddings.weight.device
+        pred = torch.empty(P, dtype=torch.float32, device=dev)
+        if P == 0:
+            return pred
+        ws_rows = self._buf('ws_rows', (N,), torch.float32)
+        ws_wt = self._buf('ws_wt', (K * D,), torch.float32)
+        save_h = save_w = None
+        if save:
+            call['save_h'] = save_h = torch.empty((N, D), dtype=torch.float32, device=dev)
+            call['save_w'] = save_w = torch.empty((P, Z), dtype=torch.float32, device=dev)
+        kernels.score_fwd(self._dims(), self.uid_embeddings.weight.data, self.iid_embeddings.weight.data,
+                          self.feature_embedding, self.mlp[0].weight.data, self.mlp[0].bias.data, self._expo(),
+                          call['X'], call['sample_item'], call['rng'], pred, ws_rows, ws_wt, save_h, save_w,
+                          self._err_flag)
+        call['pred'] = pred
+        return pred
+
+    def _launch_bwd(self, call, loss_mode, Y):
+        P, N = call['P'], call['N']
+        D, Z = self.ui_vector_size, self.sample_num + 1
+        K = D + self.feature_embedding.shape[1]
+        n_splits = kernels.bwd_splits(N)
+        rec = {
+            'gW_part': self._buf('gW_part', (n_splits, D, K), torch.float32),
+            'gb_part': self._buf('gb_part', (n_splits, D), torch.float32),
+            'gu_rec': self._buf('gu_rec', (P, D), torch.float32),
+            'gi_rec': self._buf('gi_rec', (P * Z, D), torch.float32),
+            'keys_u': self._buf('keys_u', (P,), torch.int32),
+            'keys_i': self._buf('keys_i', (P * Z,), torch.int32),
+            'loss': self._buf('loss', (1,), torch.float32),
+            'n_splits': n_splits,
+        }
+        kernels.bpr_bwd(self._dims(), self.uid_embeddings.weight.data, self.iid_embeddings.weight.data,
+                        self.feature_embedding, self.mlp[0].weight.data, call['X'], call['sample_item'], Y,
+                        call['rng'], loss_mode, call['pred'], call['save_h'], call['save_w'], rec['loss'],
+                        rec['gW_part'], rec['gb_part'], rec['gu_rec'], rec['gi_rec'], rec['keys_u'], rec['keys_i'])
+        return rec
+
+    def check_ids(self):
+        """Raise if any kernel since the last check met a user/item id outside the tables (the kernels clamp
+        such ids and raise a device flag instead of faulting; the reference would raise an IndexError)."""
+        if self._err_flag is not None and int(self._err_flag.item()) != 0:
+            self._err_flag.zero_()
+            raise IndexError('user or item id out of range in feed_dict[\'X\'] / sample_item')
+
+    # ---- reference protocol ------------------------------------------------------------------
+    def predict(self, feed_dict):
+        """{'prediction': Tensor[P], 'check': [('prediction', Tensor)]} (DCCF.py:66-107)."""
+        call = self._make_call(feed_dict)
+        need_grad = torch.is_grad_enabled() and bool(feed_dict.get('train', False)) and \
+            any(p.requires_grad for p in self.parameters())
+        if need_grad:
+            prediction = _ScoreFn.apply(self.uid_embeddings.weight, self.iid_embeddings.weight, self.mlp[0].weight,
+                                        self.mlp[0].bias, self, call)
+        else:
+            prediction = self._launch_fwd(call, save=False)
+        return {'prediction': prediction, 'check': [('prediction', prediction)]}
+
+    def forward(self, feed_dict):
+        """predict + BPR (rank 1; first half positives, second half their negatives) or MSE loss
+        (DCCF.py:109-127)."""
+        out_dict = self.predict(feed_dict)
+        if feed_dict['rank'] == 1:
+            b = int(feed_dict['Y'].shape[0] / 2)
+            pos, neg = out_dict['prediction'][:b], out_dict['prediction'][b:]
+            loss = -(pos - neg).sigmoid().log().sum()
+        else:
+            loss = torch.nn.MSELoss()(out_dict['prediction'], feed_dict['Y'].to(out_dict['prediction'].device))
+        out_dict['loss'] = loss
+        return out_dict
+
+    # ---- fused training step -----------------------------------------------------------------
+    def make_fused_optimizer(self, lr, l2, weight_decay=None, **kw):
+        self._check_ready()
+        return FusedAdamState(self, lr=lr, l2=l2, weight_decay=l2 if weight_decay is None else weight_decay, **kw)
+
+    def train_step(self, feed_dict, opt=None):
+        """One iteration of BaseRunner.fit (src/runners/BaseRunner.py:175-188): forward, loss, l2 term,
+        backward, clip, Adam — four kernel launches plus the transposition of W, no autograd, no host sync.
+        Returns the reference's out_dict (prediction, check, loss) with detached tensors."""
+        opt = opt or self.optimizer
+        if not isinstance(opt, FusedAdamState):
+            raise RuntimeError('train_step needs the fused optimizer state (model.make_fused_optimizer)')
+        call = self._make_call(feed_dict)
+        pred = self._launch_fwd(call, save=True)
+        loss_mode = 0 if feed_dict['rank'] == 1 else 1
+        Y = feed_dict.get('Y')
+        if loss_mode == 1:
+            Y = Y.to(pred.device, torch.float32).contiguous()
+        else:
+            Y = None
+        rec = self._launch_bwd(call, loss_mode=loss_mode, Y=Y)
+        opt.step_count += 1
+        hp = opt.hp()
+        P, Z = call['P'], self.sample_num + 1
+        nxt = self._buf('next', (P * Z,), torch.int32)
+        kernels.adam_sweep(self.uid_embeddings.weight.data, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'],
+                           rec['keys_u'], rec['gu_rec'], P, opt.head_u, nxt, hp)
+        kernels.adam_sweep(self.iid_embeddings.weight.data, opt.exp_avg['E_item'], opt.exp_avg_sq['E_item'],
+                           rec['keys_i'], rec['gi_rec'], P * Z, opt.head_i, nxt, hp)
+        W, b = self.mlp[0].weight.data, self.mlp[0].bias.data
+        kernels.adam_dense(W, opt.exp_avg['W'], opt.exp_avg_sq['W'], rec['gW_part'], rec['n_splits'], W.numel(), hp)
+        kernels.adam_dense(b, opt.exp_avg['b'], opt.exp_avg_sq['b'], rec['gb_part'], rec['n_splits'], b.numel(), hp)
+        loss = rec['loss'][0].clone()
+        return {'prediction': pred, 'check': [('prediction', pred)], 'loss': loss}

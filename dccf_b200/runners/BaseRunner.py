@@ -1,0 +1,261 @@
+"""Train / evaluate driver with the interface of the reference's src/runners/BaseRunner.py:16-355.
+
+Same flags, constructor, `train / fit / predict / evaluate / check / eva_termination`, same log lines and
+model-selection rules.  Differences are confined to where the time goes:
+
+  * `fit` — when the optimizer is Adam and the model offers `train_step` (dccf_b200's DCCF), each batch
+    is ONE fused step (forward, loss, l2 term, backward, clip(+-50), Adam; BaseRunner.py:175-188) with no
+    autograd and no host synchronisation; the loss of the last batch is read back once per epoch.
+    Any other optimizer/model goes through the reference's autograd sequence unchanged.
+  * `predict` — predictions stay on the device across batches and are re-ordered to data order with one
+    vectorised scatter instead of a Python dict with one entry per row (BaseRunner.py:148-156).
+  * `evaluate` — ranking metrics come from the dccf_rank_eval kernel on the device-resident predictions.
+"""
+import logging
+import os
+from time import time
+
+import numpy as np
+import pandas as pd
+import torch
+from tqdm import tqdm
+
+from ..utils import global_p, utils
+
+
+class BaseRunner(object):
+    @staticmethod
+    def parse_runner_args(parser):
+        """Flags and defaults of BaseRunner.py:18-48."""
+        parser.add_argument('--load', type=int, default=0, help='Whether load model and continue to train')
+        parser.add_argument('--epoch', type=int, default=100, help='Number of epochs.')
+        parser.add_argument('--check_epoch', type=int, default=1, help='Check every epochs.')
+        parser.add_argument('--early_stop', type=int, default=1, help='whether to early-stop.')
+        parser.add_argument('--lr', type=float, default=0.01, help='Learning rate.')
+        parser.add_argument('--batch_size', type=int, default=128, help='Batch size during training.')
+        parser.add_argument('--eval_batch_size', type=int, default=128 * 128, help='Batch size during testing.')
+        parser.add_argument('--dropout', type=float, default=0.2, help='Dropout probability for each deep layer')
+        parser.add_argument('--l2', type=float, default=1e-4, help='Weight of l2_regularize in loss.')
+        parser.add_argument('--optimizer', type=str, default='GD', help='optimizer: GD, Adam, Adagrad')
+        parser.add_argument('--metric', type=str, default='RMSE',
+                            help='metrics: RMSE, MAE, AUC, F1, Accuracy, Precision, Recall')
+        parser.add_argument('--skip_eval', type=int, default=0, help='number of epochs without evaluation')
+        return parser
+
+    def __init__(self, optimizer='GD', learning_rate=0.01, epoch=100, batch_size=128, eval_batch_size=128 * 128,
+                 dropout=0.2, l2=1e-5, metrics='RMSE', check_epoch=10, early_stop=1):
+        self.optimizer_name = optimizer
+        self.learning_rate = learning_rate
+        self.epoch = epoch
+        self.batch_size = batch_size
+        self.eval_batch_size = eval_batch_size
+        self.dropout = dropout
+        self.no_dropout = 0.0
+        self.l2_weight = l2
+        self.metrics = metrics.lower().split(',')
+        self.check_epoch = check_epoch
+        self.early_stop = early_stop
+        self.time = None
+        self.train_results, self.valid_results, self.test_results = [], [], []
+        self.show_progress = True
+
+    # ---- optimizer ---------------------------------------------------------------------------
+    def _build_optimizer(self, model):
+        """SGD / Adagrad / Adam, all with weight_decay = l2 (BaseRunner.py:83-107).  Adam on a model that has
+        the fused step keeps its state in a FusedAdamState instead of torch.optim.Adam."""
+        name = self.optimizer_name.lower()
+        if name == 'adam':
+            logging.info('Optimizer: Adam')
+            if hasattr(model, 'make_fused_optimizer'):
+                return model.make_fused_optimizer(lr=self.learning_rate, l2=self.l2_weight, weight_decay=self.l2_weight)
+            return torch.optim.Adam(model.parameters(), lr=self.learning_rate, weight_decay=self.l2_weight)
+        if name == 'adagrad':
+            logging.info('Optimizer: Adagrad')
+            return torch.optim.Adagrad(model.parameters(), lr=self.learning_rate, weight_decay=self.l2_weight)
+        if name == 'gd':
+            logging.info('Optimizer: GD')
+            return torch.optim.SGD(model.parameters(), lr=self.learning_rate, weight_decay=self.l2_weight)
+        logging.error('Unknown Optimizer: ' + self.optimizer_name)
+        assert self.optimizer_name in ['GD', 'Adagrad', 'Adam']
+        return torch.optim.SGD(model.parameters(), lr=self.learning_rate, weight_decay=self.l2_weight)
+
+    def _check_time(self, start=False):
+        """[start, last] wall-clock pair; returns seconds since the previous call (BaseRunner.py:109-120)."""
+        if self.time is None or start:
+            self.time = [time()] * 2
+            return self.time[0]
+        last = self.time[1]
+        self.time[1] = time()
+        return self.time[1] - last
+
+    def batches_add_control(self, batches, train):
+        """'train' flag and dropout probability per batch: --dropout when training, 0 otherwise
+        (BaseRunner.py:122-132)."""
+        for batch in batches:
+            batch['train'] = train
+            batch['dropout'] = self.dropout if train else self.no_dropout
+        return batches
+
+    def _bar(self, it, **kw):
+        return tqdm(it, leave=False, ncols=100, mininterval=1, disable=not self.show_progress, **kw)
+
+    # ---- inference ---------------------------------------------------------------------------
+    def _predict_device(self, model, data, data_processor):
+        """Predictions in DATA order as one device tensor (no per-batch device->host copy)."""
+        batches = data_processor.prepare_batches(data, self.eval_batch_size, train=False)
+        batches = self.batches_add_control(batches, train=False)
+        model.eval()
+        outs = []
+        with torch.no_grad():
+            for batch in self._bar(batches, desc='Predict'):
+                outs.append(model.predict(batch)['prediction'].detach())
+        pred = torch.cat(outs) if len(outs) > 1 else outs[0]
+        sample_ids = np.concatenate([b[global_p.K_SAMPLE_ID] for b in batches])
+        want = np.asarray(data[global_p.K_SAMPLE_ID])
+        if len(sample_ids) == len(want) and np.array_equal(sample_ids, want):
+            return pred
+        # general case: position of every requested sample id inside the batch stream
+        order = np.argsort(sample_ids, kind='stable')
+        pos = order[np.searchsorted(sample_ids[order], want)]
+        return pred[torch.from_numpy(pos).to(pred.device)]
+
+    def predict(self, model, data, data_processor):
+        """np.ndarray of predictions aligned with `data` (BaseRunner.py:134-157)."""
+        return self._predict_device(model, data, data_processor).cpu().numpy()
+
+    # ---- training ----------------------------------------------------------------------------
+    def fit(self, model, data, data_processor, epoch=-1):
+        """One epoch over `data`; returns the out_dict of the last batch (BaseRunner.py:159-191)."""
+        if model.optimizer is None:
+            model.optimizer = self._build_optimizer(model)
+        batches = data_processor.prepare_batches(data, self.batch_size, train=True)
+        batches = self.batches_add_control(batches, train=True)
+        batch_size = self.batch_size if data_processor.rank == 0 else self.batch_size * 2
+        model.train()
+        fused = hasattr(model, 'train_step') and not isinstance(model.optimizer, torch.optim.Optimizer)
+        accumulate_size = 0
+        output_dict = None
+        for batch in self._bar(batches, desc='Epoch %5d' % (epoch + 1)):
+            if fused:
+                # forward + (loss + l2) backward + clip + step in one go: the reference steps on every batch
+                # (accumulate_size >= batch_size always holds for its batch layout, BaseRunner.py:176,186-188)
+                output_dict = model.train_step(batch)
+                continue
+            accumulate_size += len(batch['Y'])
+            model.optimizer.zero_grad()
+            output_dict = model(batch)
+            loss = output_dict['loss'] + model.l2() * self.l2_weight
+            loss.backward()
+            torch.nn.utils.clip_grad_value_(model.parameters(), 50)
+            if accumulate_size >= batch_size or batch is batches[-1]:
+                model.optimizer.step()
+                accumulate_size = 0
+        model.eval()
+        if hasattr(model, 'check_ids'):
+            model.check_ids()
+        return output_dict
+
+    def eva_termination(self, model):
+        """Early-stopping rule on the validation history (BaseRunner.py:193-210)."""
+        metric = self.metrics[0]
+        valid = self.valid_results
+        if len(valid) > 20 and metric in utils.LOWER_METRIC_LIST and utils.strictly_increasing(valid[-5:]):
+            return True
+        if len(valid) > 20 and metric not in utils.LOWER_METRIC_LIST and utils.strictly_decreasing(valid[-5:]):
+            return True
+        if len(valid) - valid.index(utils.best_result(metric, valid)) > 20:
+            return True
+        return False
+
+    def _eval_or_default(self, model, data, data_processor, metrics=None):
+        if data is None:
+            return [-1.0] * len(self.metrics)
+        return self.evaluate(model, data, data_processor, metrics=metrics)
+
+    def train(self, model, data_processor, skip_eval=0):
+        """The epoch loop with evaluation, model selection and early stop (BaseRunner.py:212-303)."""
+        train_data = data_processor.get_train_data(epoch=-1)
+        validation_data = data_processor.get_validation_data()
+        test_data = data_processor.get_test_data()
+        self._check_time(start=True)
+        init_train = self._eval_or_default(model, train_data, data_processor, metrics=['rmse', 'mae'])
+        init_valid = self._eval_or_default(model, validation_data, data_processor)
+        init_test = self._eval_or_default(model, test_data, data_processor)
+        logging.info('Init: \t train= %s validation= %s test= %s [%.1f s] ' % (
+            utils.format_metric(init_train), utils.format_metric(init_valid), utils.format_metric(init_test),
+            self._check_time()) + ','.join(self.metrics))
+        try:
+            for epoch in range(self.epoch):
+                self._check_time()
+                epoch_train_data = data_processor.get_train_data(epoch=epoch)
+                last_batch = self.fit(model, epoch_train_data, data_processor, epoch=epoch)
+                if self.check_epoch > 0 and (epoch == 1 or epoch % self.check_epoch == 0):
+                    self.check(model, last_batch)
+                training_time = self._check_time()
+                if epoch >= skip_eval:
+                    train_result = self._eval_or_default(model, train_data, data_processor, metrics=['rmse', 'mae'])
+                    valid_result = self._eval_or_default(model, validation_data, data_processor)
+                    test_result = self._eval_or_default(model, test_data, data_processor)
+                    testing_time = self._check_time()
+                    self.train_results.append(train_result)
+                    self.valid_results.append(valid_result)
+                    self.test_results.append(test_result)
+                    logging.info('Epoch %5d [%.1f s]\t train= %s validation= %s test= %s [%.1f s] '
+                                 % (epoch + 1, training_time, utils.format_metric(train_result),
+                                    utils.format_metric(valid_result), utils.format_metric(test_result), testing_time)
+                                 + ','.join(self.metrics))
+                    if utils.best_result(self.metrics[0], self.valid_results) == self.valid_results[-1]:
+                        model.save_model()
+                    if self.eva_termination(model) and self.early_stop == 1:
+                        logging.info('Early stop at %d based on validation result.' % (epoch + 1))
+                        break
+                if epoch < skip_eval:
+                    logging.info('Epoch %5d [%.1f s]' % (epoch + 1, training_time))
+        except KeyboardInterrupt:
+            logging.info('Early stop manually')
+            save_here = input('Save here? (1/0) (default 0):')
+            if str(save_here).lower().startswith('1'):
+                model.save_model()
+        if self.valid_results:
+            for name, results in (('validation', self.valid_results), ('test', self.test_results)):
+                best = utils.best_result(self.metrics[0], results)
+                best_epoch = results.index(best)
+                logging.info('Best Iter(%s)= %5d\t train= %s valid= %s test= %s [%.1f s] '
+                             % (name, best_epoch + 1, utils.format_metric(self.train_results[best_epoch]),
+                                utils.format_metric(self.valid_results[best_epoch]),
+                                utils.format_metric(self.test_results[best_epoch]), self.time[1] - self.time[0])
+                             + ','.join(self.metrics))
+            model.load_model()
+
+    # ---- evaluation --------------------------------------------------------------------------
+    def evaluate(self, model, data, data_processor, metrics=None, write_rank=False):
+        """Metric values of the model on `data` (BaseRunner.py:305-332); `write_rank` dumps
+        uid/iid/score/label sorted by uid to <dataset dir>/rank.csv (tab separated)."""
+        if metrics is None:
+            metrics = self.metrics
+        pred = self._predict_device(model, data, data_processor)
+        if write_rank:
+            df = pd.DataFrame()
+            df['uid'] = data['uid']
+            df['iid'] = data['iid']
+            df['score'] = pred.cpu().numpy()
+            df['label'] = data['Y']
+            df = df.sort_values(by='uid')
+            df.to_csv(os.path.join(data_processor.data_loader.path, global_p.RANK_FILE_NAME), sep='\t', index=False)
+        needs_host = any('@' not in m for m in metrics)
+        p = pred.cpu().numpy() if needs_host else pred
+        return model.evaluate_method(p, data, metrics=metrics)
+
+    def check(self, model, out_dict):
+        """Log the 'check' tensors, loss and l2 of a batch; warn when l2 is out of proportion
+        (BaseRunner.py:334-355)."""
+        logging.info(os.linesep)
+        for name, t in out_dict['check']:
+            d = np.array(t.detach().cpu())
+            logging.info(os.linesep.join([name + '\t' + str(d.shape), np.array2string(d, threshold=20)]) + os.linesep)
+        loss = out_dict['loss'].detach()
+        with torch.no_grad():
+            l2 = model.l2() * self.l2_weight
+        logging.info('loss = %.4f, l2 = %.4f' % (loss, l2))
+        if not (loss.abs() * 0.005 < l2 < loss.abs() * 0.1):
+            logging.warning('l2 inappropriate: loss = %.4f, l2 = %.4f' % (loss, l2))

@@ -113,6 +113,8 @@ int dccf_score_fwd(const dccf_dims* dims, const float* E_user, const float* E_it
  * (src/runners/BaseRunner.py:183).  One launch.
  *   loss_mode 0: BPR  -sum_j log sigmoid(pred[j]-pred[j+P/2])   (rank==1, P even)
  *   loss_mode 1: MSE  mean_p (pred[p]-Y[p])^2                    (rank==0)
+ *   loss_mode 2: no loss: Y[p] holds d loss/d pred[p] computed by the caller (autograd path);
+ *                out_loss may be NULL
  *   pred [P], save_h [N,D], save_w [P,Z] from dccf_score_fwd called with the SAME rng.
  *   out_loss     float[1]
  *   gW_part      [n_splits, D, D+F], gb_part [n_splits, D]: per-row-split partial sums of

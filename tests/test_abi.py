@@ -1,0 +1,59 @@
+"""The C-ABI library builds for sm_100a, loads, and exports every symbol include/dccf_b200.h declares.
+No compute calls here (no GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from dccf_b200 import _lib, build
+
+
+@pytest.fixture(scope='module')
+def lib_path():
+    return build.build()
+
+
+def test_header_symbols_are_exported_and_bound(lib_path):
+    header = open(os.path.join(ROOT, 'include', 'dccf_b200.h')).read()
+    body = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(dccf_[a-z0-9_]+)\s*\(', body))
+    assert declared, 'no declarations found'
+    lib = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.exported_symbols())
+
+
+def test_library_loads_and_reports_abi(lib_path):
+    lib = _lib.load()
+    assert lib.dccf_abi_version() == _lib.ABI_VERSION
+    header = open(os.path.join(ROOT, 'include', 'dccf_b200.h')).read()
+    assert '#define DCCF_ABI_VERSION %d' % _lib.ABI_VERSION in header
+
+
+def test_argument_errors_are_reported_without_a_gpu(lib_path):
+    """Argument validation happens before any CUDA call."""
+    lib = _lib.load()
+    rc = lib.dccf_rank_eval(None, None, None, None, None, 1, 5, None, None, None, None)
+    assert rc == -1
+    assert b'null buffer' in lib.dccf_last_error()
+    rc = lib.dccf_noise_fill(None, 4, 768, 0.1, 1, 1, 0, None)
+    assert rc == -1 and b'null output' in lib.dccf_last_error()
+    assert lib.dccf_bwd_splits(5632) >= 1
+
+
+def test_sass_is_sm100a(lib_path):
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    out = subprocess.run([cuobjdump, '-lelf', lib_path], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    with pytest.raises(_lib.DccfError, match='no CPU fallback'):
+        _lib.load(str(tmp_path / 'nope.so'))

@@ -1,0 +1,171 @@
+"""Host side of the path (no GPU): DataLoader / DataProcessor / model init / runner bookkeeping compared with
+fixtures produced by the unmodified reference (tests/golden/sampler.npz, train_*.npz)."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dccf_b200 import synth
+from dccf_b200.data_loaders.DataLoader import DataLoader
+from dccf_b200.data_processor.DataProcessor import DataProcessor
+from dccf_b200.models.DCCF import DCCF
+from dccf_b200.runners.BaseRunner import BaseRunner
+from dccf_b200.utils import utils
+
+SENT = synth.DEFAULT_SENTENCE_MODEL
+
+
+def _write_sampler_dataset(g, root):
+    d = os.path.join(root, 's')
+    os.makedirs(d)
+    for split in ('train', 'validation', 'test'):
+        np.savetxt(os.path.join(d, 's.%s.csv' % split), g[split + '_csv'], fmt='%d', delimiter=',')
+    I, U = int(g['item_num']), int(g['user_num'])
+    np.save(os.path.join(d, 's_%s.npy' % SENT), np.zeros((I, 64), np.float32))
+    np.save(os.path.join(d, 's.ips_expo_prob.npy'), np.zeros((U, I), np.float32))
+    return d
+
+
+def _make_model(d, dataset, U, I, seed=2019, **kw):
+    model = DCCF(path=d, dataset=dataset, sentence_model=SENT, sample_num=kw.get('S', 10),
+                 attribute_num=kw.get('A', 2), std=kw.get('std', 0.1), label_min=0, label_max=1, feature_num=0,
+                 user_num=U, item_num=I, u_vector_size=64, i_vector_size=64, n_layers=1, random_seed=seed,
+                 model_path=os.path.join(d, 'm.pt'))
+    model.apply(model.init_paras)
+    return model
+
+
+def test_loader_and_sampler_bit_exact(golden, tmp_path):
+    """Same seed -> the same test/validation negatives, epoch shuffles and training negatives, bit for bit
+    (src/data_processor/DataProcessor.py:57-111, 227-250, 408-524; src/utils/utils.py:82-92)."""
+    g = golden('sampler')
+    d = _write_sampler_dataset(g, str(tmp_path))
+    seed = int(g['seed'])
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    dl = DataLoader(path=str(tmp_path), dataset='s', label='label', sep=',')
+    assert dl.user_num == int(g['user_num']) and dl.item_num == int(g['item_num'])
+    model = _make_model(d, 's', dl.user_num, dl.item_num, seed=seed)
+    dl.drop_neg()
+    dp = DataProcessor(dl, model, rank=1, test_neg_n=int(g['test_neg_n']))
+    te = dp.get_test_data()
+    va = dp.get_validation_data()
+    for nm, dd in (('test', te), ('validation', va)):
+        for k in ('uid', 'iid', 'Y', 'X', 'sample_id'):
+            assert np.array_equal(np.asarray(dd[k]), g['%s_%s' % (nm, k)]), (nm, k)
+    tr = dp.get_train_data(epoch=-1)
+    assert np.array_equal(tr['X'], g['train0_X'])
+    for ep in range(int(g['epochs'])):
+        data = dp.get_train_data(epoch=ep)
+        assert np.array_equal(data['sample_id'], g['train_ep%d_order' % ep])
+        batches = dp.prepare_batches(data, int(g['batch_size']), train=True)
+        assert len(batches) == int(g['train_ep%d_nbatches' % ep])
+        X = np.concatenate([b['X'].cpu().numpy() for b in batches])
+        Y = np.concatenate([b['Y'].cpu().numpy() for b in batches])
+        sid = np.concatenate([b['sample_id'] for b in batches])
+        assert np.array_equal(X, g['train_ep%d_X' % ep])                 # negatives bit-exact
+        assert np.array_equal(Y, g['train_ep%d_Y' % ep])
+        assert np.array_equal(sid, g['train_ep%d_sample_id' % ep])
+        for b in batches:                                                 # layout contract (DP:160-207)
+            r = b['real_batch_size']
+            assert b['X'].shape[0] == 2 * r and b['total_batch_size'] == 2 * r
+            assert torch.equal(b['X'][:r, 0], b['X'][r:, 0])
+    assert np.array_equal(np.random.get_state()[1][:8].astype(np.int64), g['np_state_after'])
+
+
+def test_eval_batches_are_cached_and_plain(golden, tmp_path):
+    g = golden('sampler')
+    d = _write_sampler_dataset(g, str(tmp_path))
+    np.random.seed(1)
+    dl = DataLoader(path=str(tmp_path), dataset='s', label='label', sep=',')
+    model = _make_model(d, 's', dl.user_num, dl.item_num)
+    dl.drop_neg()
+    dp = DataProcessor(dl, model, rank=1, test_neg_n=3)
+    te = dp.get_test_data()
+    b1 = dp.prepare_batches(te, 50, train=False)
+    b2 = dp.prepare_batches(te, 50, train=False)
+    assert b1 is b2
+    assert all(b['rank'] == 1 for b in b1)
+    assert sum(b['X'].shape[0] for b in b1) == len(te['Y'])
+    # one negative set per distinct user (DP:420-430)
+    n_users = len(set(te['uid'].tolist()))
+    assert int((te['Y'] == 0).sum()) == 3 * n_users
+
+
+@pytest.mark.parametrize('name', ['train_f64', 'train_f768'])
+def test_initial_weights_equal_reference(golden, tmp_path, name):
+    """Same constructor order + apply(init_paras) on the torch CPU generator -> identical initial parameters
+    (src/models/DCCF.py:47-64, src/models/BaseModel.py:131-151, src/main.py:150)."""
+    g = golden(name)
+    U, I = g['init_E_user'].shape[0], g['init_E_item'].shape[0]
+    d = str(tmp_path)
+    np.save(os.path.join(d, 'g_%s.npy' % SENT), g['feat'])
+    np.save(os.path.join(d, 'g.ips_expo_prob.npy'), g['expo'])
+    seed = int(g['seed'])
+    torch.manual_seed(seed)
+    model = _make_model(d, 'g', U, I, seed=seed)
+    assert np.array_equal(model.uid_embeddings.weight.detach().numpy(), g['init_E_user'])
+    assert np.array_equal(model.iid_embeddings.weight.detach().numpy(), g['init_E_item'])
+    assert np.array_equal(model.mlp[0].weight.detach().numpy(), g['init_W'])
+    assert np.array_equal(model.mlp[0].bias.detach().numpy(), g['init_b'])
+    assert sorted(model.state_dict().keys()) == ['iid_embeddings.weight', 'mlp.0.bias', 'mlp.0.weight',
+                                                 'uid_embeddings.weight']
+    assert model.total_parameters == (U + I) * 64 + 64 * (64 + g['feat'].shape[1]) + 64
+
+
+def test_model_refuses_cpu(golden, tmp_path):
+    """No CPU fallback: predict on a CPU model must fail loudly."""
+    g = golden('train_f64')
+    d = str(tmp_path)
+    np.save(os.path.join(d, 'g_%s.npy' % SENT), g['feat'])
+    np.save(os.path.join(d, 'g.ips_expo_prob.npy'), g['expo'])
+    model = _make_model(d, 'g', 40, 50)
+    if torch.cuda.is_available():
+        pytest.skip('CPU-only check')
+    with pytest.raises(RuntimeError, match='CUDA only'):
+        model.predict({'X': torch.from_numpy(g['X_0']), 'dropout': 0.0})
+
+
+def test_cli_flags_and_defaults():
+    """Appendix A of SURVEY.md: flag names and defaults of the reference CLI."""
+    p = argparse.ArgumentParser()
+    utils.parse_global_args(p)
+    DataLoader.parse_data_args(p)
+    DCCF.parse_model_args(p, model_name='DCCF')
+    BaseRunner.parse_runner_args(p)
+    DataProcessor.parse_dp_args(p)
+    a = p.parse_args([])
+    assert (a.gpu, a.random_seed, a.train) == ('0', 2019, 1)
+    assert (a.path, a.dataset, a.sep, a.label) == ('../datasets/', 'ml100k-1-5', ',', 'label')
+    assert (a.u_vector_size, a.i_vector_size, a.n_layers) == (64, 64, 1)
+    assert (a.sentence_model, a.sample_num, a.attribute_num, a.std) == ('paraphrase-distilroberta-base-v1', 10, 2, 0.1)
+    assert (a.optimizer, a.lr, a.l2, a.batch_size, a.eval_batch_size, a.dropout) == ('GD', 0.01, 1e-4, 128, 16384, 0.2)
+    assert (a.epoch, a.check_epoch, a.early_stop, a.skip_eval, a.load, a.metric) == (100, 1, 1, 0, 0, 'RMSE')
+    assert a.test_neg_n == 100
+    assert a.model_path == '../model/DCCF/DCCF.pt'
+    assert (DCCF.append_id, DCCF.include_id, DCCF.include_user_features, DCCF.include_item_features,
+            DCCF.include_context_features) == (True, False, False, False, False)
+
+
+def test_utils_behaviour():
+    assert utils.format_metric([0.123456, np.float32(0.5), 3]) == '0.1235,0.5000,3'
+    assert utils.best_result('ndcg@5', [[0.1, 0.9], [0.2, 0.0]]) == [0.2, 0.0]       # lexicographic (utils.py:95-106)
+    assert utils.best_result('rmse', [3.0, 1.0, 2.0]) == 1.0
+    np.random.seed(3)
+    data = {'a': np.arange(10), 'b': np.arange(10) * 2, 'c': np.stack([np.arange(10), np.arange(10)], 1)}
+    utils.shuffle_in_unison_scary(data)
+    assert np.array_equal(data['b'], data['a'] * 2) and np.array_equal(data['c'][:, 0], data['a'])
+    assert not np.array_equal(data['a'], np.arange(10))
+
+
+def test_runner_bookkeeping():
+    r = BaseRunner(optimizer='Adam', learning_rate=1e-3, metrics='NDCG@5,Recall@5', dropout=0.2)
+    assert r.metrics == ['ndcg@5', 'recall@5']
+    batches = r.batches_add_control([{}, {}], train=True)
+    assert all(b['dropout'] == 0.2 and b['train'] for b in batches)
+    batches = r.batches_add_control([{}], train=False)
+    assert batches[0]['dropout'] == 0.0 and not batches[0]['train']
+    r.valid_results = [[0.5]] + [[0.1]] * 21
+    assert r.eva_termination(None)            # best result more than 20 evaluations ago

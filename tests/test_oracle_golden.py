@@ -1,0 +1,97 @@
+"""The numpy oracle (oracle/dccf_oracle.py) pinned against fixtures produced by the UNMODIFIED reference
+(tests/golden/*.npz, written by oracle/make_golden.py) and against the reference's docstring values."""
+import numpy as np
+import pytest
+
+from conftest import golden_params, rel_err
+from oracle import dccf_oracle as O
+
+TRAIN_FIXTURES = ['train_f64', 'train_f768', 'train_nodrop']
+
+
+@pytest.mark.parametrize('name', TRAIN_FIXTURES)
+def test_predict_matches_reference(golden, name):
+    g = golden(name)
+    A, drop = int(g['A']), float(g['dropout'])
+    params = golden_params(g)
+    mask = g['mask_0'] if drop > 0 else None
+    out = O.predict(params, g['X_0'], g['sample_item_0'], g['noise_0'], mask, A)
+    assert rel_err(out['pred'], g['pred_0']) < 1e-5                     # north_star: 1e-5 relative, fp32
+    assert abs(O.loss_bpr(out['pred']) - float(g['loss_0'])) < 1e-5 * abs(float(g['loss_0']))
+
+
+@pytest.mark.parametrize('name', TRAIN_FIXTURES)
+def test_eval_predict_matches_reference(golden, name):
+    g = golden(name)
+    params = golden_params(g, 'final_')
+    out = O.predict(params, g['eval_X'], g['eval_sample_item'], g['eval_noise'], None, int(g['A']))
+    assert rel_err(out['pred'], g['eval_pred']) < 1e-5
+
+
+@pytest.mark.parametrize('name', TRAIN_FIXTURES)
+def test_training_steps_match_reference(golden, name):
+    """Forward, backward, l2 + clip + Adam restated; compared after `steps` reference steps."""
+    g = golden(name)
+    A, steps, drop = int(g['A']), int(g['steps']), float(g['dropout'])
+    params = golden_params(g)
+    state = {k: {'m': np.zeros_like(params[k]), 'v': np.zeros_like(params[k])} for k in ('E_user', 'E_item', 'W', 'b')}
+    hp = dict(lr=float(g['lr']), l2=float(g['l2']), weight_decay=float(g['l2']))
+    for t in range(steps):
+        mask = g['mask_%d' % t] if drop > 0 else None
+        params, state, loss, pred = O.train_step(params, state, t + 1, g['X_%d' % t], g['sample_item_%d' % t],
+                                                 g['noise_%d' % t], mask, A, hp)
+        assert rel_err(pred, g['pred_%d' % t]) < 2e-5
+        assert abs(loss - float(g['loss_%d' % t])) < 1e-5 * abs(float(g['loss_%d' % t]))
+    for k in ('E_user', 'E_item', 'W', 'b'):
+        # exp_avg / exp_avg_sq are linear / quadratic in the gradient: well conditioned
+        assert rel_err(state[k]['m'], g['m_' + k]) < 2e-5, k
+        assert rel_err(state[k]['v'], g['v_' + k]) < 2e-5, k
+    # the parameters: p -= lr * m_hat / (sqrt(v_hat) + 1e-8).  Where |g| << eps (elements of W whose data
+    # gradient cancels the l2 term) d(update)/dg = lr/eps = 1e5, so fp32 summation noise of 1e-10 in g moves
+    # the weight by 1e-5 absolute: the reference differs from itself across BLAS builds by that much.
+    assert rel_err(params['E_user'], g['final_E_user']) < 1e-5
+    assert rel_err(params['E_item'], g['final_E_item']) < 1e-5
+    assert rel_err(params['b'], g['final_b']) < 1e-5
+    assert rel_err(params['W'], g['final_W']) < 5e-4
+
+
+def test_ranking_metrics_match_reference(golden):
+    g = golden('metrics')
+    data = {'uid': g['uid'], 'iid': g['iid'], 'Y': g['Y']}
+    vals = O.evaluate_method(g['p'], data, [str(m) for m in g['metrics']])
+    assert np.abs(np.array(vals) - g['values']).max() < 1e-6             # north_star: metrics to 1e-6
+
+
+def test_metric_known_answers(golden):
+    """Values printed in the reference's docstrings (src/utils/rank_metrics.py:64-70,143-144,179-187)."""
+    g = golden('metrics')
+    assert abs(O.ndcg_at_k([2, 1, 2, 0], 4) - 0.96519546960144276) < 1e-12
+    assert abs(O.dcg_at_k([3, 2, 3, 0, 0, 1, 2, 2, 3, 0], 2) - 4.2618595071429155) < 1e-12
+    assert O.ndcg_at_k([0], 1) == 0.0
+    assert O.ndcg_at_k([1], 2) == 1.0
+    assert abs(float(g['kat_ndcg_2120_k4_m1']) - 0.96519546960144276) < 1e-12
+    assert abs(float(g['kat_dcg_k2_m1']) - 4.2618595071429155) < 1e-12
+    assert abs(float(g['kat_prec_001_k3']) - 1.0 / 3.0) < 1e-12
+
+
+def test_rank_users_tie_break():
+    """Total order: score desc, then item id asc, then row asc; NaN last."""
+    scores = np.array([0.5, 0.5, 0.5, np.nan, 0.9, 0.5], dtype=np.float32)
+    uid = np.zeros(6, dtype=np.int64)
+    iid = np.array([7, 3, 3, 1, 9, 2])
+    Y = np.array([0, 1, 0, 1, 0, 0], dtype=np.float32)
+    users, topk, rows, m = O.rank_users(scores, uid, Y, iid, 6)
+    assert list(topk[0]) == [9, 2, 3, 3, 7, 1]
+    assert list(rows[0]) == [4, 5, 1, 2, 0, 3]
+
+
+def test_mt19937_matches_numpy_and_torch():
+    """SURVEY.md Appendix C recipes: numpy legacy randint / torch CPU randint from raw MT19937 words."""
+    import torch
+    np.random.seed(2019)
+    mt = O.MT19937(2019)
+    assert [int(np.random.randint(5000)) for _ in range(50)] == [mt.np_randint(5000) for _ in range(50)]
+    torch.manual_seed(77)
+    want = torch.randint(16000, size=(4, 10)).reshape(-1).numpy()
+    got = O.MT19937(77).torch_randint(16000, 40)
+    assert np.array_equal(want, got)
