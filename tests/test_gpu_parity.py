@@ -1,0 +1,419 @@
+"""Parity of the CUDA path (through the C-ABI) with the reference fixtures and the oracle.  Needs a GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_params, rel_err
+from oracle import dccf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TRAIN_FIXTURES = ['train_f64', 'train_f768', 'train_nodrop']
+
+
+def make_model(params, S, A, std, seed=2019, expo_factors=None):
+    from dccf_b200.models.DCCF import DCCF
+    U, I = params['E_user'].shape[0], params['E_item'].shape[0]
+    model = DCCF(path='', dataset='', sentence_model='', sample_num=S, attribute_num=A, std=std, label_min=0,
+                 label_max=1, feature_num=0, user_num=U, item_num=I, u_vector_size=64, i_vector_size=64, n_layers=1,
+                 random_seed=seed, model_path='/tmp/dccf_test_model.pt', feature_embedding=params['Feat'],
+                 expo_prob=None if expo_factors is not None else params['expo'], expo_factors=expo_factors)
+    with torch.no_grad():
+        model.uid_embeddings.weight.copy_(torch.from_numpy(params['E_user']))
+        model.iid_embeddings.weight.copy_(torch.from_numpy(params['E_item']))
+        model.mlp[0].weight.copy_(torch.from_numpy(params['W']))
+        model.mlp[0].bias.copy_(torch.from_numpy(params['b']))
+    return model.cuda()
+
+
+def feed(g, t, drop, rank=1, train=True):
+    X = g['X_%d' % t]
+    b = X.shape[0] // 2
+    fd = {'X': torch.from_numpy(X).cuda(), 'rank': rank, 'train': train, 'dropout': drop,
+          'Y': torch.cat([torch.ones(b), torch.zeros(X.shape[0] - b)]).cuda(),
+          'sample_item': torch.from_numpy(g['sample_item_%d' % t]), 'noise': torch.from_numpy(g['noise_%d' % t])}
+    if drop > 0:
+        fd['dropout_mask'] = torch.from_numpy(g['mask_%d' % t])
+    return fd
+
+
+def model_params(model):
+    return {'E_user': model.uid_embeddings.weight.detach().cpu().numpy(),
+            'E_item': model.iid_embeddings.weight.detach().cpu().numpy(),
+            'W': model.mlp[0].weight.detach().cpu().numpy(), 'b': model.mlp[0].bias.detach().cpu().numpy()}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# against the reference's own outputs (golden fixtures)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', TRAIN_FIXTURES)
+def test_predict_matches_reference(golden, name):
+    g = golden(name)
+    drop = float(g['dropout'])
+    model = make_model(golden_params(g), int(g['S']), int(g['A']), float(g['std']))
+    out = model.predict(feed(g, 0, drop, train=False))
+    assert rel_err(out['prediction'].cpu().numpy(), g['pred_0']) < 1e-5          # 1e-5 relative, fp32
+    model.check_ids()
+
+
+@pytest.mark.parametrize('name', TRAIN_FIXTURES)
+def test_eval_predict_matches_reference(golden, name):
+    """Ragged batch (37 pairs), dropout off, after training (final weights)."""
+    g = golden(name)
+    model = make_model(golden_params(g, 'final_'), int(g['S']), int(g['A']), float(g['std']))
+    fd = {'X': torch.from_numpy(g['eval_X']).cuda(), 'rank': 1, 'train': False, 'dropout': 0.0,
+          'sample_item': torch.from_numpy(g['eval_sample_item']), 'noise': torch.from_numpy(g['eval_noise'])}
+    out = model.predict(fd)
+    assert rel_err(out['prediction'].cpu().numpy(), g['eval_pred']) < 1e-5
+
+
+def _check_trained(model, opt_state, g):
+    got = model_params(model)
+    for k in ('E_user', 'E_item', 'W', 'b'):
+        assert rel_err(opt_state['m'][k], g['m_' + k]) < 2e-5, k
+        assert rel_err(opt_state['v'][k], g['v_' + k]) < 2e-5, k
+    # see tests/test_oracle_golden.py for why W gets a looser bound (lr/eps conditioning of Adam where |g| << eps)
+    assert rel_err(got['E_user'], g['final_E_user']) < 1e-5
+    assert rel_err(got['E_item'], g['final_E_item']) < 1e-5
+    assert rel_err(got['b'], g['final_b']) < 1e-5
+    assert rel_err(got['W'], g['final_W']) < 5e-4
+
+
+@pytest.mark.parametrize('name', TRAIN_FIXTURES)
+def test_fused_training_matches_reference(golden, name):
+    """model.train_step x steps == reference BaseRunner.fit (forward, BPR, l2, backward, clip, Adam)."""
+    g = golden(name)
+    drop, steps = float(g['dropout']), int(g['steps'])
+    model = make_model(golden_params(g), int(g['S']), int(g['A']), float(g['std']))
+    model.optimizer = model.make_fused_optimizer(lr=float(g['lr']), l2=float(g['l2']))
+    for t in range(steps):
+        out = model.train_step(feed(g, t, drop))
+        assert rel_err(out['prediction'].cpu().numpy(), g['pred_%d' % t]) < 2e-5
+        assert abs(float(out['loss']) - float(g['loss_%d' % t])) < 1e-5 * abs(float(g['loss_%d' % t]))
+    opt = model.optimizer
+    _check_trained(model, {'m': {k: v.cpu().numpy() for k, v in opt.exp_avg.items()},
+                           'v': {k: v.cpu().numpy() for k, v in opt.exp_avg_sq.items()}}, g)
+    assert int((opt.head_u != -1).sum()) == 0 and int((opt.head_i != -1).sum()) == 0
+    model.check_ids()
+
+
+@pytest.mark.parametrize('name', ['train_f64', 'train_nodrop'])
+def test_autograd_training_matches_reference(golden, name):
+    """The reference's own sequence — loss + l2*model.l2(), backward, clip_grad_value_, torch Adam — on top of
+    the CUDA forward/backward kernels (drop-in for an unmodified runner)."""
+    g = golden(name)
+    drop, steps = float(g['dropout']), int(g['steps'])
+    model = make_model(golden_params(g), int(g['S']), int(g['A']), float(g['std']))
+    optim = torch.optim.Adam(model.parameters(), lr=float(g['lr']), weight_decay=float(g['l2']))
+    model.train()
+    for t in range(steps):
+        optim.zero_grad()
+        out = model(feed(g, t, drop))
+        loss = out['loss'] + model.l2() * float(g['l2'])
+        loss.backward()
+        torch.nn.utils.clip_grad_value_(model.parameters(), 50)
+        optim.step()
+        assert abs(float(out['loss']) - float(g['loss_%d' % t])) < 1e-5 * abs(float(g['loss_%d' % t]))
+    plist = {'E_user': model.uid_embeddings.weight, 'E_item': model.iid_embeddings.weight,
+             'W': model.mlp[0].weight, 'b': model.mlp[0].bias}
+    for k, p in plist.items():
+        assert rel_err(p.grad.cpu().numpy(), g['lastgrad_' + k]) < 2e-5, k
+    _check_trained(model, {'m': {k: optim.state[p]['exp_avg'].cpu().numpy() for k, p in plist.items()},
+                           'v': {k: optim.state[p]['exp_avg_sq'].cpu().numpy() for k, p in plist.items()}}, g)
+
+
+def test_ranker_matches_reference_metrics(golden):
+    from dccf_b200.models.BaseModel import BaseModel
+    g = golden('metrics')
+    data = {'uid': g['uid'], 'iid': g['iid'], 'Y': g['Y']}
+    vals = BaseModel.evaluate_method(g['p'], data, [str(m) for m in g['metrics']])
+    assert np.abs(np.array(vals) - g['values']).max() < 1e-6                      # metrics to 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# against the oracle on seeded inputs
+# ---------------------------------------------------------------------------------------------------------
+def random_problem(seed, U, I, F, P, S, A, std, drop):
+    rs = np.random.RandomState(seed)
+    params = {'E_user': (rs.standard_normal((U, 64)) * 0.05).astype(np.float32),
+              'E_item': (rs.standard_normal((I, 64)) * 0.05).astype(np.float32),
+              'W': (rs.standard_normal((64, 64 + F)) * 0.05).astype(np.float32),
+              'b': (rs.standard_normal(64) * 0.05).astype(np.float32),
+              'Feat': (rs.standard_normal((I, F)) / np.sqrt(F)).astype(np.float32),
+              'expo': rs.random_sample((U, I)).astype(np.float32)}
+    b = P // 2
+    u = rs.randint(0, U, size=b)
+    X = np.concatenate([np.stack([u, rs.randint(0, I, size=b)], 1), np.stack([u, rs.randint(0, I, size=b)], 1)])
+    if P % 2:
+        X = np.concatenate([X, [[rs.randint(0, U), rs.randint(0, I)]]])
+    X = X.astype(np.int64)
+    si = rs.randint(0, I, size=(P, S)).astype(np.int64)
+    N = P * (S + 1) * A
+    noise = (rs.standard_normal((N, F)) * std).astype(np.float32) if std > 0 else None
+    mask = ((rs.random_sample((N, 64)) < 1 - drop) / (1 - drop)).astype(np.float32) if drop > 0 else None
+    return params, X, si, noise, mask
+
+
+@pytest.mark.parametrize('U,I,F,P,S,A,std,drop', [
+    (300, 500, 768, 256, 10, 2, 0.1, 0.2),     # the reference's training step shape
+    (50, 70, 128, 37, 3, 1, 0.1, 0.0),         # ragged: 37*4 rows is not a multiple of the 128-row tile
+    (20, 30, 64, 2, 0, 1, 0.0, 0.0),           # no confounders: single slot
+    (64, 64, 256, 130, 5, 3, 0.0, 0.5),
+])
+def test_forward_backward_vs_oracle(U, I, F, P, S, A, std, drop):
+    params, X, si, noise, mask = random_problem(11, U, I, F, P, S, A, std, drop)
+    Xe = X[:P - (P % 2)]
+    sie = si[:len(Xe)]
+    R = (S + 1) * A
+    noise_e = noise[:len(Xe) * R] if noise is not None else None
+    mask_e = mask[:len(Xe) * R] if mask is not None else None
+    model = make_model(params, S, A, std)
+    # forward on the full (possibly odd) batch
+    fd = {'X': torch.from_numpy(X).cuda(), 'rank': 1, 'train': False, 'dropout': drop,
+          'sample_item': torch.from_numpy(si)}
+    if noise is not None:
+        fd['noise'] = torch.from_numpy(noise)
+    if mask is not None:
+        fd['dropout_mask'] = torch.from_numpy(mask)
+    ref = O.predict(params, X, si, noise, mask, A, dtype=np.float64)
+    got = model.predict(fd)['prediction'].cpu().numpy()
+    assert rel_err(got, ref['pred']) < 1e-5
+    # gradients through the autograd path on the even part
+    fd = {'X': torch.from_numpy(Xe).cuda(), 'rank': 1, 'train': True, 'dropout': drop,
+          'Y': torch.zeros(len(Xe)).cuda(), 'sample_item': torch.from_numpy(sie)}
+    if noise_e is not None:
+        fd['noise'] = torch.from_numpy(noise_e)
+    if mask_e is not None:
+        fd['dropout_mask'] = torch.from_numpy(mask_e)
+    model.train()
+    out = model(fd)
+    out['loss'].backward()
+    fwd = O.predict(params, Xe, sie, noise_e, mask_e, A, dtype=np.float64)
+    grads = O.backward(params, Xe, sie, noise_e, mask_e, A, fwd, dtype=np.float64)
+    assert abs(float(out['loss']) - O.loss_bpr(fwd['pred'])) < 1e-5 * abs(O.loss_bpr(fwd['pred']))
+    assert rel_err(model.uid_embeddings.weight.grad.cpu().numpy(), grads['E_user']) < 1e-5
+    assert rel_err(model.iid_embeddings.weight.grad.cpu().numpy(), grads['E_item']) < 1e-5
+    assert rel_err(model.mlp[0].weight.grad.cpu().numpy(), grads['W']) < 1e-5
+    assert rel_err(model.mlp[0].bias.grad.cpu().numpy(), grads['b']) < 1e-5
+    model.check_ids()
+
+
+def test_mse_loss_mode_vs_oracle():
+    """rank == 0: MSELoss(prediction, Y) (src/models/DCCF.py:123-125) through the fused step."""
+    U, I, F, P, S, A = 40, 60, 64, 24, 4, 2
+    params, X, si, noise, mask = random_problem(5, U, I, F, P, S, A, 0.1, 0.2)
+    Y = np.random.RandomState(1).random_sample(P).astype(np.float32)
+    model = make_model(params, S, A, 0.1)
+    model.optimizer = model.make_fused_optimizer(lr=1e-3, l2=1e-4)
+    fd = {'X': torch.from_numpy(X).cuda(), 'rank': 0, 'train': True, 'dropout': 0.2, 'Y': torch.from_numpy(Y).cuda(),
+          'sample_item': torch.from_numpy(si), 'noise': torch.from_numpy(noise), 'dropout_mask': torch.from_numpy(mask)}
+    out = model.train_step(fd)
+    state = {k: {'m': np.zeros_like(params[k]), 'v': np.zeros_like(params[k])} for k in ('E_user', 'E_item', 'W', 'b')}
+    hp = dict(lr=1e-3, l2=1e-4, weight_decay=1e-4)
+    p2, s2, loss, pred = O.train_step(params, state, 1, X, si, noise, mask, A, hp, loss_mode=1, Y=Y)
+    assert abs(float(out['loss']) - loss) < 1e-5 * abs(loss)
+    opt = model.optimizer
+    for k in ('E_user', 'E_item', 'W', 'b'):
+        assert rel_err(opt.exp_avg[k].cpu().numpy(), s2[k]['m']) < 2e-5, k
+
+
+def test_ipsmf_exposure_vs_oracle():
+    """Exposure computed on the fly from IPSBiasedMF factors (src/models/IPSBiasedMF.py:42-53) instead of the
+    dense user x item matrix (scaled config)."""
+    from dccf_b200 import synth
+    U, I, F, P, S, A = 80, 120, 64, 64, 10, 2
+    params, X, si, noise, mask = random_problem(7, U, I, F, P, S, A, 0.1, 0.0)
+    fac = synth.make_ipsmf_factors(U, I, seed=3)
+    model = make_model(params, S, A, 0.1, expo_factors=fac)
+    fd = {'X': torch.from_numpy(X).cuda(), 'rank': 1, 'train': False, 'dropout': 0.0,
+          'sample_item': torch.from_numpy(si), 'noise': torch.from_numpy(noise)}
+    got = model.predict(fd)['prediction'].cpu().numpy()
+    ref = O.predict(params, X, si, noise, None, A, dtype=np.float64, expo=fac)
+    assert rel_err(got, ref['pred']) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the library's own random streams
+# ---------------------------------------------------------------------------------------------------------
+def test_fused_rng_equals_materialised_rng():
+    """rng mode 2 (Philox in registers) is bit-identical to mode 1 fed with dccf_noise_fill /
+    dccf_dropout_mask_fill output for the same (seed, offset): forward AND gradients."""
+    from dccf_b200 import kernels
+    U, I, F, P, S, A, std, drop = 100, 150, 768, 64, 10, 2, 0.1, 0.2
+    params, X, si, _, _ = random_problem(3, U, I, F, P, S, A, 0.0, 0.0)
+    N = P * (S + 1) * A
+    seed = 2019
+    results = []
+    for explicit in (False, True):
+        model = make_model(params, S, A, std, seed=seed)
+        model.optimizer = model.make_fused_optimizer(lr=1e-3, l2=1e-4)
+        fd = {'X': torch.from_numpy(X).cuda(), 'rank': 1, 'train': True, 'dropout': drop,
+              'Y': torch.zeros(P).cuda(), 'sample_item': torch.from_numpy(si)}
+        if explicit:
+            noise = torch.empty((N, F), device='cuda')
+            mask = torch.empty((N, 64), device='cuda')
+            kernels.noise_fill(noise, std, seed, 1)          # first predict call of a fresh model -> offset 1
+            kernels.dropout_mask_fill(mask, drop, seed, 1)
+            fd['noise'], fd['dropout_mask'] = noise, mask
+        out = model.train_step(fd)
+        results.append((out['prediction'].cpu().numpy(), model_params(model)))
+    assert np.array_equal(results[0][0], results[1][0])
+    for k in ('E_user', 'E_item', 'W', 'b'):
+        assert np.array_equal(results[0][1][k], results[1][1][k]), k
+
+
+def test_noise_and_mask_statistics():
+    from dccf_b200 import kernels
+    noise = torch.empty((4096, 768), device='cuda')
+    kernels.noise_fill(noise, 0.1, 2019, 5)
+    n = noise.double()
+    assert abs(float(n.mean())) < 2e-4 and abs(float(n.std()) - 0.1) < 2e-4
+    z = n / 0.1
+    assert abs(float((z ** 3).mean())) < 0.01 and abs(float((z ** 4).mean()) - 3.0) < 0.02
+    assert abs(float((n[:, ::2] * n[:, 1::2]).mean())) < 1e-5            # neighbouring columns uncorrelated
+    other = torch.empty_like(noise)
+    kernels.noise_fill(other, 0.1, 2019, 6)
+    assert abs(float((n * other.double()).mean())) < 1e-5                # calls are independent
+    mask = torch.empty((4096, 64), device='cuda')
+    kernels.dropout_mask_fill(mask, 0.2, 2019, 5)
+    vals = torch.unique(mask).cpu().numpy()
+    assert np.allclose(vals, [0.0, 1.25])
+    assert abs(float((mask > 0).double().mean()) - 0.8) < 5e-3
+    # row0 offsets address the same stream
+    part = torch.empty((100, 768), device='cuda')
+    kernels.noise_fill(part, 0.1, 2019, 5, row0=1000)
+    assert torch.equal(part, noise[1000:1100])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ranker: ties, ragged and tiny users, top-k ids bit-exact
+# ---------------------------------------------------------------------------------------------------------
+def test_ranker_topk_ids_bit_exact_with_ties():
+    from dccf_b200.models.BaseModel import group_candidates, rank_metrics_device
+    rs = np.random.RandomState(4)
+    uid, iid, Y = [], [], []
+    for u in range(200):
+        n = int(rs.choice([1, 2, 4, 5, 37, 1001, 1003]))
+        uid += [u] * n
+        iid += list(rs.choice(5000, n, replace=False))
+        Y += list((rs.random_sample(n) < 0.1).astype(np.float32))
+        Y[-1] = 1.0
+    uid, iid, Y = np.array(uid), np.array(iid, dtype=np.int64), np.array(Y, dtype=np.float32)
+    perm = rs.permutation(len(uid))
+    uid, iid, Y = uid[perm], iid[perm], Y[perm]
+    scores = np.round(rs.standard_normal(len(uid)), 1).astype(np.float32)       # coarse grid -> many ties
+    scores[rs.randint(0, len(uid), 20)] = np.nan
+    for k in (1, 5, 10):
+        users, want_ids, want_rows, want_m = O.rank_users(scores, uid, Y, iid, k)
+        _, rows, off = group_candidates(uid)
+        m, topk = rank_metrics_device(torch.from_numpy(scores).cuda(), torch.from_numpy(Y).cuda(),
+                                      torch.from_numpy(iid).cuda(), torch.from_numpy(rows).cuda(),
+                                      torch.from_numpy(off).cuda(), k, want_topk=True)
+        assert np.array_equal(topk.cpu().numpy(), want_ids)                      # bit-exact ids, ties by item id
+        assert np.abs(m.cpu().numpy() - want_m).max() < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------
+# optimizer sweep
+# ---------------------------------------------------------------------------------------------------------
+def test_adam_sweep_duplicates_and_determinism():
+    """Many records on one row, records on no row, result independent of atomics timing."""
+    from dccf_b200 import kernels
+    rs = np.random.RandomState(9)
+    rows, n_rec = 1000, 700
+    keys = rs.randint(0, rows, size=n_rec).astype(np.int32)
+    keys[:300] = 17                                                              # 300 records on the same row
+    grads = rs.standard_normal((n_rec, 64)).astype(np.float32) * 0.01
+    table = rs.standard_normal((rows, 64)).astype(np.float32) * 0.05
+    dense = np.zeros((rows, 64), dtype=np.float32)
+    for r in range(n_rec):                                                       # ascending record order, fp32
+        dense[keys[r]] += grads[r]
+    want_p, want_m, want_v = O.adam_step(table, dense, np.zeros_like(table), np.zeros_like(table), 1)
+    outs = []
+    for _ in range(2):
+        t = torch.from_numpy(table).cuda()
+        m = torch.zeros_like(t)
+        v = torch.zeros_like(t)
+        head = torch.full((rows,), -1, dtype=torch.int32, device='cuda')
+        nxt = torch.empty(n_rec, dtype=torch.int32, device='cuda')
+        hp = kernels.make_adam(1e-3, 1e-4, 1e-4, step=1)
+        kernels.adam_sweep(t, m, v, torch.from_numpy(keys).cuda(), torch.from_numpy(grads).cuda(), n_rec, head, nxt, hp)
+        assert int((head != -1).sum()) == 0
+        outs.append((t.cpu().numpy(), m.cpu().numpy(), v.cpu().numpy()))
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
+    assert rel_err(outs[0][1], want_m) < 1e-6 and rel_err(outs[0][2], want_v) < 1e-6
+    assert rel_err(outs[0][0], want_p) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------
+# full-size properties and edge cases
+# ---------------------------------------------------------------------------------------------------------
+def test_eval_batch_full_size_properties():
+    """eval_batch_size = 16384 pairs (360 448 predictor rows): deterministic, finite, linear in the user
+    embedding (s = <E_user, h>) and invariant to a constant shift of the exposure row (softmax)."""
+    U, I, F, P, S, A = 2000, 5000, 768, 16384, 10, 2
+    params, X, si, _, _ = random_problem(21, U, I, F, P, S, A, 0.0, 0.0)
+    model = make_model(params, S, A, 0.1)
+    fd = {'X': torch.from_numpy(X).cuda(), 'rank': 1, 'train': False, 'dropout': 0.0,
+          'sample_item': torch.from_numpy(si)}
+    model._rng_offset = 0
+    a = model.predict(fd)['prediction']
+    model._rng_offset = 0
+    b = model.predict(fd)['prediction']
+    assert torch.equal(a, b) and bool(torch.isfinite(a).all())
+    c = model.predict(fd)['prediction']                       # next call -> new noise
+    assert not torch.equal(a, c)
+    with torch.no_grad():
+        model.uid_embeddings.weight.mul_(2.0)
+        model.expo_prob.add_(3.0)
+    model._rng_offset = 0
+    d = model.predict(fd)['prediction']
+    assert rel_err(d.cpu().numpy(), 2.0 * a.cpu().numpy()) < 1e-5
+    # spot check against the oracle with the materialised noise of the first 64 pairs
+    from dccf_b200 import kernels
+    R = (S + 1) * A
+    noise = torch.empty((64 * R, F), device='cuda')
+    kernels.noise_fill(noise, 0.1, model.random_seed, 1)
+    p2 = dict(params)
+    p2['E_user'] = params['E_user'] * 2
+    ref = O.predict(p2, X[:64], si[:64], noise.cpu().numpy(), None, A, dtype=np.float64)
+    assert rel_err(d[:64].cpu().numpy(), ref['pred']) < 1e-5
+
+
+def test_out_of_range_ids_are_reported():
+    params, X, si, _, _ = random_problem(2, 30, 40, 64, 8, 2, 1, 0.0, 0.0)
+    model = make_model(params, 2, 1, 0.0)
+    X = X.copy()
+    X[3, 1] = 40
+    fd = {'X': torch.from_numpy(X).cuda(), 'rank': 1, 'train': False, 'dropout': 0.0,
+          'sample_item': torch.from_numpy(si)}
+    model.predict(fd)
+    with pytest.raises(IndexError):
+        model.check_ids()
+
+
+def test_empty_batch():
+    params, X, si, _, _ = random_problem(2, 30, 40, 64, 8, 2, 1, 0.0, 0.0)
+    model = make_model(params, 2, 1, 0.0)
+    fd = {'X': torch.zeros((0, 2), dtype=torch.int64).cuda(), 'rank': 1, 'train': False, 'dropout': 0.0}
+    assert model.predict(fd)['prediction'].shape == (0,)
+
+
+def test_confounders_come_from_the_torch_cpu_stream():
+    """Without an injected 'sample_item' the model draws torch.randint(item_num, (P, S)) on the CPU generator,
+    like src/models/DCCF.py:72 — same indices as the reference for the same seed and call sequence."""
+    params, X, si, _, _ = random_problem(2, 30, 40, 64, 8, 4, 1, 0.0, 0.0)
+    model = make_model(params, 4, 1, 0.0)
+    fd = {'X': torch.from_numpy(X).cuda(), 'rank': 1, 'train': False, 'dropout': 0.0}
+    torch.manual_seed(123)
+    a = model.predict(fd)['prediction'].cpu().numpy()
+    torch.manual_seed(123)
+    draw = torch.randint(40, size=(8, 4))
+    fd2 = dict(fd)
+    fd2['sample_item'] = draw
+    b = model.predict(fd2)['prediction'].cpu().numpy()
+    assert np.array_equal(a, b)
+    want = O.MT19937(123).torch_randint(40, 32).reshape(8, 4)
+    assert np.array_equal(draw.numpy(), want)

@@ -95,3 +95,27 @@ def test_mt19937_matches_numpy_and_torch():
     want = torch.randint(16000, size=(4, 10)).reshape(-1).numpy()
     got = O.MT19937(77).torch_randint(16000, 40)
     assert np.array_equal(want, got)
+
+
+@pytest.mark.parametrize('name', ['train_f64', 'train_nodrop'])
+def test_torch_port_matches_reference(golden, name):
+    """oracle/torch_port.py (bench.py's CPU baseline arm) reproduces the reference's training trajectory."""
+    import torch
+    from oracle import torch_port
+    g = golden(name)
+    A, S, steps, drop = int(g['A']), int(g['S']), int(g['steps']), float(g['dropout'])
+    U, I = g['init_E_user'].shape[0], g['init_E_item'].shape[0]
+    model = torch_port.DCCFPort(U, I, g['feat'], g['expo'], sample_num=S, attribute_num=A, std=float(g['std']),
+                                seed=int(g['seed']))
+    assert np.array_equal(model.mlp[0].weight.detach().numpy(), g['init_W'])       # same init stream
+    optim = torch.optim.Adam(model.parameters(), lr=float(g['lr']), weight_decay=float(g['l2']))
+    for t in range(steps):
+        X = torch.from_numpy(g['X_%d' % t])
+        fd = {'X': X, 'Y': torch.zeros(X.shape[0]), 'dropout': drop,
+              'sample_item': torch.from_numpy(g['sample_item_%d' % t]), 'noise': torch.from_numpy(g['noise_%d' % t])}
+        if drop > 0:
+            fd['dropout_mask'] = torch.from_numpy(g['mask_%d' % t])
+        out = torch_port.fit_step(model, optim, fd, float(g['l2']))
+        assert rel_err(out['prediction'].detach().numpy(), g['pred_%d' % t]) < 1e-6
+    assert rel_err(model.uid_embeddings.weight.detach().numpy(), g['final_E_user']) < 1e-6
+    assert rel_err(model.mlp[0].weight.detach().numpy(), g['final_W']) < 1e-5
