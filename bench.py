@@ -1,0 +1,485 @@
+"""bench.py — DCCF training (samples/s) and 1000-negative evaluation (users/s) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--preset electronics]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  A "step" is one training batch of the reference configuration
+(--batch_size 128 -> 256 scored pairs: 128 positives + their sampled negatives; S=10 confounders, A=2,
+std 0.1, dropout 0.2, Adam lr 1e-3, l2 1e-4) on synthetic Electronics-shaped data; `value` is train
+samples/s with the batches already in HBM, `e2e` the same through the public API from pinned host
+buffers (confounder draw on the CPU generator, H2D of ids, D2H of the loss every step).  The `eval`
+object holds the evaluation half of the metric: users/s for ranking each test user's positive against
+test_neg_n = 1000 sampled negatives (scoring + on-device top-k/ndcg/recall/precision@5).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+PRESETS = {            # (users, items) — the reference ships no data, shapes are ours
+    'tiny': (2000, 5000),
+    'electronics': (48000, 16000),
+    'cds': (24000, 20000),
+    'yelp': (32000, 38000),
+}
+D, F, S, A = 64, 768, 10, 2
+Z, R = S + 1, (S + 1) * A
+BATCH = 128
+EVAL_BATCH = 16384
+TEST_NEG_N = 1000
+LR, L2, DROPOUT, STD = 1e-3, 1e-4, 0.2, 0.1
+SEED = 2019
+
+# algorithmic work per scored pair
+FLOP_FWD_PAIR = R * (2 * (D + F) * D + 4 * D)
+FLOP_BWD_PAIR = R * (2 * (D + F) * D + 2 * D * D + 2 * D)
+BYTES_PAIR = 16 + 4 * D + 4 * D * Z + 4 * F + 4 * Z
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        try:
+            proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
+                                     '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                    stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        try:
+            while not self._stop.is_set():
+                line = proc.stdout.readline()
+                if not line:
+                    break
+                self.samples.append([x.strip() for x in line.split(',')])
+        finally:
+            proc.terminate()
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        time.sleep(0.15)
+        self._stop.set()
+        self._thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, s[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def synth_batches(n_steps, U, I, seed):
+    """[n_steps, 2*BATCH, 2] int64: rows [0,128) positives, [128,256) their negatives, same user."""
+    rs = np.random.RandomState(seed)
+    pop = 1.0 / np.arange(1, I + 1, dtype=np.float64) ** 0.8
+    cdf = np.cumsum(pop / pop.sum())
+    u = rs.randint(0, U, size=(n_steps, BATCH))
+    pos = np.minimum(np.searchsorted(cdf, rs.random_sample((n_steps, BATCH))), I - 1)
+    neg = rs.randint(0, I, size=(n_steps, BATCH))
+    X = np.empty((n_steps, 2 * BATCH, 2), dtype=np.int64)
+    X[:, :BATCH, 0] = u
+    X[:, BATCH:, 0] = u
+    X[:, :BATCH, 1] = pos
+    X[:, BATCH:, 1] = neg
+    return X
+
+
+def synth_eval_set(n_users, U, I, seed):
+    """n_users test users x (1 positive + TEST_NEG_N sampled negatives): X [rows,2], uid, iid, Y."""
+    rs = np.random.RandomState(seed + 1)
+    users = rs.choice(U, n_users, replace=False)
+    n_c = 1 + TEST_NEG_N
+    uid = np.repeat(users, n_c)
+    iid = np.empty((n_users, n_c), dtype=np.int64)
+    for g in range(n_users):
+        iid[g] = rs.choice(I, n_c, replace=False)
+    Y = np.zeros((n_users, n_c), dtype=np.float32)
+    Y[:, 0] = 1.0
+    iid, Y = iid.reshape(-1), Y.reshape(-1)
+    return np.stack([uid, iid], 1).astype(np.int64), uid, iid, Y
+
+
+def build_model(U, I, device):
+    from dccf_b200.models.DCCF import DCCF
+    g = torch.Generator(device='cpu').manual_seed(SEED + 5)
+    feat = torch.randn((I, F), generator=g) / (F ** 0.5)
+    gd = torch.Generator(device=device).manual_seed(SEED + 6)
+    expo = torch.rand((U, I), generator=gd, device=device)              # "random ips_expo_prob" (BASELINE.json)
+    torch.manual_seed(SEED)
+    model = DCCF(path='', dataset='', sentence_model='', sample_num=S, attribute_num=A, std=STD, label_min=0,
+                 label_max=1, feature_num=0, user_num=U, item_num=I, u_vector_size=D, i_vector_size=D, n_layers=1,
+                 random_seed=SEED, model_path='/tmp/dccf_bench.pt', feature_embedding=feat, expo_prob=expo)
+    model.apply(model.init_paras)                                         # N(0, 0.01) random-init weights
+    model = model.to(device)
+    model.optimizer = model.make_fused_optimizer(lr=LR, l2=L2)
+    return model
+
+
+class L2Flusher(object):
+    """Writes a 256 MiB buffer (> the 126 MB L2) between timed iterations."""
+
+    def __init__(self, device):
+        self.buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)
+        self.v = 0.0
+
+    def __call__(self):
+        self.v += 1.0
+        self.buf.fill_(self.v)
+
+
+def dist_max(x, world):
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device='cuda')
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def bench_train(model, X_all, steps, warmup, world, flush):
+    """Returns dict with device-resident timing (CUDA events per step, L2 flushed in between, max over ranks),
+    per-stage times and the end-to-end timing from pinned host buffers."""
+    from dccf_b200 import kernels
+    dev = next(model.parameters()).device
+    n = warmup + steps
+    Y = torch.cat([torch.ones(BATCH), torch.zeros(BATCH)]).to(dev)
+    I = model.item_num
+
+    # ---- value: inputs resident in HBM --------------------------------------------------------
+    X_dev = torch.from_numpy(X_all[:n]).to(dev)
+    torch.manual_seed(SEED + 11)
+    si_dev = torch.randint(I, size=(n, 2 * BATCH, S)).to(dev)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n)]
+    stage_ms = np.zeros(3)
+    launches0 = kernels.LAUNCHES[0]
+    barrier(world)
+    for i in range(n):
+        if i == warmup:
+            barrier(world)
+            launches0 = kernels.LAUNCHES[0]
+        flush()
+        fd = {'X': X_dev[i], 'Y': Y, 'rank': 1, 'train': True, 'dropout': DROPOUT, 'sample_item': si_dev[i]}
+        model.train_step(fd, stage_events=ev[i])
+    barrier(world)
+    launches = kernels.LAUNCHES[0] - launches0
+    per_step = [ev[i][0].elapsed_time(ev[i][3]) for i in range(warmup, n)]
+    for i in range(warmup, n):
+        for s in range(3):
+            stage_ms[s] += ev[i][s].elapsed_time(ev[i][s + 1])
+    total_ms = dist_max(float(np.sum(per_step)), world)
+    model.check_ids()
+
+    # ---- e2e: public API from pinned host memory, loss read back every step ---------------------
+    X_pin = torch.from_numpy(X_all[:n]).pin_memory()
+    si_pin = torch.empty((2 * BATCH, S), dtype=torch.int64).pin_memory()
+    e2e_s = 0.0
+    torch.manual_seed(SEED + 12)
+    barrier(world)
+    for i in range(n):
+        flush()
+        torch.cuda.synchronize()
+        if i == warmup:
+            barrier(world)
+        t0 = time.perf_counter()
+        si_pin.copy_(torch.randint(I, size=(2 * BATCH, S)))            # DCCF.py:72 on the CPU generator
+        fd = {'X': X_pin[i].to(dev, non_blocking=True), 'Y': Y, 'rank': 1, 'train': True, 'dropout': DROPOUT,
+              'sample_item': si_pin}
+        out = model.train_step(fd)
+        loss = float(out['loss'].item())                                # D2H + sync
+        t1 = time.perf_counter()
+        if i >= warmup:
+            e2e_s += t1 - t0
+    assert np.isfinite(loss)
+    e2e_s = dist_max(e2e_s, world)
+    return {'total_ms': total_ms, 'stage_ms': stage_ms / steps, 'launches': launches, 'e2e_s': e2e_s,
+            'h2d': 2 * BATCH * 2 * 8 + 2 * BATCH * S * 8, 'd2h': 4, 'last_loss': loss}
+
+
+def bench_eval(model, n_users, warm_batches, world, rank, flush):
+    """Scores n_users x 1001 candidates in eval batches of 16384 pairs and ranks them on the device."""
+    from dccf_b200.models.BaseModel import group_candidates, rank_metrics_device
+    dev = next(model.parameters()).device
+    U, I = model.user_num, model.item_num
+    X, uid, iid, Y = synth_eval_set(n_users, U, I, SEED + 100 * rank)
+    rows = X.shape[0]
+    bounds = [(a, min(rows, a + EVAL_BATCH)) for a in range(0, rows, EVAL_BATCH)]
+    _, cand, off = group_candidates(uid)
+    cand_d, off_d = torch.from_numpy(cand).to(dev), torch.from_numpy(off).to(dev)
+    Y_d, iid_d = torch.from_numpy(Y).to(dev), torch.from_numpy(iid).to(dev)
+    X_d = torch.from_numpy(X).to(dev)
+    torch.manual_seed(SEED + 13)
+    si_d = torch.randint(I, size=(rows, S)).to(dev)
+    model.eval()
+
+    def run(from_host, X_src, timed):
+        preds = []
+        ev_pairs = []
+        for bi, (a, b) in enumerate(bounds):
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if from_host:
+                fd = {'X': X_src[a:b].to(dev, non_blocking=True), 'rank': 1, 'train': False, 'dropout': 0.0}
+            else:
+                fd = {'X': X_src[a:b], 'rank': 1, 'train': False, 'dropout': 0.0, 'sample_item': si_d[a:b]}
+            preds.append(model.predict(fd)['prediction'])
+            e1.record()
+            ev_pairs.append((e0, e1))
+        pred = torch.cat(preds)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        m = rank_metrics_device(pred, Y_d, iid_d, cand_d, off_d, 5)
+        sums = m.sum(dim=0)
+        e1.record()
+        ev_pairs.append((e0, e1))
+        return sums, ev_pairs
+
+    # warm-up
+    for _ in range(3):
+        model.predict({'X': X_d[:EVAL_BATCH], 'rank': 1, 'train': False, 'dropout': 0.0,
+                       'sample_item': si_d[:EVAL_BATCH]})
+    barrier(world)
+    sums, evs = run(False, X_d, True)
+    barrier(world)
+    score_ms = sum(a.elapsed_time(b) for a, b in evs[:-1])
+    rank_ms = evs[-1][0].elapsed_time(evs[-1][1])
+    dev_ms = dist_max(score_ms + rank_ms, world)
+
+    # e2e: ids from pinned host memory, confounders drawn on the CPU generator per batch (as the reference),
+    # metric sums read back at the end
+    X_pin = torch.from_numpy(X).pin_memory()
+    barrier(world)
+    t0 = time.perf_counter()
+    sums, _ = run(True, X_pin, True)
+    host_sums = sums.cpu().numpy()
+    t1 = time.perf_counter()
+    e2e_s = dist_max(t1 - t0, world)
+    flush_s = 0.0
+    metrics = host_sums / n_users
+    return {'dev_ms': dev_ms, 'score_ms': score_ms, 'rank_ms': rank_ms, 'e2e_s': e2e_s, 'rows': rows,
+            'n_batches': len(bounds), 'h2d': rows * 16 + rows * S * 8, 'd2h': 40,
+            'ndcg@5': float(metrics[0]), 'recall@5': float(metrics[3]), 'precision@5': float(metrics[2]),
+            'flush_s': flush_s}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: eager-PyTorch port of the reference path on the host cores (oracle/torch_port.py)
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(U, I, X_all, budget_s, steps=None, warmup=1, eval_rows=4096):
+    from oracle import torch_port
+    threads = torch.get_num_threads()
+    g = torch.Generator(device='cpu').manual_seed(SEED + 5)
+    feat = torch.randn((I, F), generator=g) / (F ** 0.5)
+    expo = torch.rand((U, I), generator=torch.Generator(device='cpu').manual_seed(SEED + 6))
+    model = torch_port.DCCFPort(U, I, feat, expo, sample_num=S, attribute_num=A, std=STD, seed=SEED)
+    optim = torch.optim.Adam(model.parameters(), lr=LR, weight_decay=L2)
+    Y = torch.cat([torch.ones(BATCH), torch.zeros(BATCH)])
+    model.train()
+    times = []
+    i = 0
+    t_begin = time.perf_counter()
+    while True:
+        fd = {'X': torch.from_numpy(X_all[i % len(X_all)]), 'Y': Y, 'dropout': DROPOUT}
+        t0 = time.perf_counter()
+        torch_port.fit_step(model, optim, fd, L2)
+        t1 = time.perf_counter()
+        if i >= warmup:
+            times.append(t1 - t0)
+        i += 1
+        if steps is not None:
+            if len(times) >= steps:
+                break
+        elif time.perf_counter() - t_begin > budget_s and len(times) >= 2:
+            break
+    train_sps = BATCH * len(times) / sum(times)
+    # evaluation sample: eval_rows candidate rows (≈ eval_rows/1001 users), scoring + host ranking
+    Xe, uid, iid, Yl = synth_eval_set(max(1, eval_rows // (1 + TEST_NEG_N)), U, I, SEED)
+    model.eval()
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        pred = model.predict({'X': torch.from_numpy(Xe), 'dropout': 0.0})['prediction'].numpy()
+        torch_port.evaluate_users(pred, uid, iid, Yl, 5)
+        t1 = time.perf_counter()
+    n_eval_users = len(set(uid.tolist()))
+    return {'train_samples_per_s': train_sps, 'train_steps': len(times), 'eval_users_per_s': n_eval_users / (t1 - t0),
+            'eval_users': n_eval_users, 'cores': threads}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--preset', default='electronics', choices=sorted(PRESETS))
+    ap.add_argument('--eval-users', type=int, default=256)
+    ap.add_argument('--cpu-budget', type=float, default=12.0, help='seconds of CPU work for the cpu_baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    U, I = PRESETS[args.preset]
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    config = {'workload': 'DCCF Adam lr=1e-3 on synthetic %s-shape data: U=%d I=%d F=768 D=64, batch 128 (+128 sampled '
+                          'negatives), S=10 A=2 std=0.1 dropout=0.2 l2=1e-4; eval test_neg_n=1000, eval_batch 16384, '
+                          'ndcg/recall/precision@5' % (args.preset, U, I),
+              'preset': args.preset, 'users': U, 'items': I, 'batch_size': BATCH, 'eval_users_per_rank': args.eval_users,
+              'parallelism': 'dp%d' % world, 'l2_cache': 'flushed between timed iterations (256 MiB write)'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        X_all = synth_batches(64, U, I, SEED)
+        steps = args.steps if args.steps <= 50 else None
+        r = cpu_arm(U, I, X_all, budget_s=max(args.cpu_budget, 20.0), steps=steps, warmup=min(args.warmup, 3))
+        sample = '%d train steps of 128 samples; eval of %d users x 1001 candidates' % (r['train_steps'], r['eval_users'])
+        line = {'impl': 'reference', 'metric': 'train_samples_per_s', 'value': r['train_samples_per_s'],
+                'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': r['train_steps'], 'warmup': min(args.warmup, 3),
+                'ms_per_step': 1e3 * BATCH / r['train_samples_per_s'], 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                'cpu_baseline': {'value': r['train_samples_per_s'], 'unit': 'samples/s', 'cores': r['cores'],
+                                 'kind': 'port', 'sample': sample},
+                'e2e': {'value': r['train_samples_per_s'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0},
+                'eval': {'metric': 'eval_users_per_s', 'value': r['eval_users_per_s'], 'unit': 'users/s'},
+                'note': 'reference CPU path = eager-PyTorch port of src/models/DCCF.py + BaseRunner.fit '
+                        '(oracle/torch_port.py): the reference is Python and hard-codes CUDA, it cannot travel'}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        torch.distributed.init_process_group('nccl', device_id=dev)
+    from dccf_b200 import kernels
+    model = build_model(U, I, dev)
+    if world > 1:
+        model.enable_data_parallel()
+    flush = L2Flusher(dev)
+    X_all = synth_batches(args.warmup + args.steps, U, I, SEED + rank)
+    with ClockSampler(local_rank) as clocks:
+        tr = bench_train(model, X_all, args.steps, args.warmup, world, flush)
+        evl = bench_eval(model, args.eval_users, 3, world, rank, flush)
+    clk = clocks.summary()
+
+    hbm_peak, peak_src = measured_peaks()
+    ms_per_step = tr['total_ms'] / args.steps
+    value = world * BATCH * args.steps / (tr['total_ms'] / 1e3)
+    e2e_value = world * BATCH * args.steps / tr['e2e_s']
+    n_params = (U + I) * D + D * (D + F) + D
+    stage = tr['stage_ms']                                   # fwd, bwd, adam  (ms per step)
+    pairs = 2 * BATCH
+    stages = {
+        'score_fwd': {'ms': float(stage[0]), 'gflop': pairs * FLOP_FWD_PAIR / 1e9, 'mbytes': pairs * BYTES_PAIR / 1e6},
+        'bpr_bwd': {'ms': float(stage[1]), 'gflop': pairs * FLOP_BWD_PAIR / 1e9,
+                    'mbytes': pairs * (BYTES_PAIR + 4 * D * (1 + Z)) / 1e6},
+        'adam_sweep': {'ms': float(stage[2]), 'gflop': 0.0, 'mbytes': 24.0 * n_params / 1e6},
+    }
+    for s in stages.values():
+        s['gbs'] = s['mbytes'] / 1e3 / (s['ms'] / 1e3) if s['ms'] > 0 else 0.0
+        s['tflops'] = s['gflop'] / 1e3 / (s['ms'] / 1e3) if s['ms'] > 0 else 0.0
+    dom = max(stages, key=lambda k: stages[k]['ms'])
+    roof = {'kernel': dom, 'bound': 'hbm', 'achieved': stages[dom]['gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
+            'frac': stages[dom]['gbs'] / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+            'fp32_simt': {'achieved': stages[dom]['tflops'], 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+                          'frac': stages[dom]['tflops'] / FP32_PEAK_TFLOPS},
+            'stages': stages}
+    eval_pairs = evl['rows']
+    eval_users_s = world * args.eval_users / (evl['dev_ms'] / 1e3)
+    eval_tflops = eval_pairs * FLOP_FWD_PAIR / 1e12 / (evl['score_ms'] / 1e3)
+    eval_obj = {'metric': 'eval_users_per_s', 'value': eval_users_s, 'unit': 'users/s',
+                'users': world * args.eval_users, 'candidates_per_user': 1 + TEST_NEG_N,
+                'ms_per_batch': evl['score_ms'] / evl['n_batches'], 'rank_ms': evl['rank_ms'],
+                'e2e': {'value': world * args.eval_users / evl['e2e_s'], 'unit': 'users/s',
+                        'h2d_bytes': evl['h2d'], 'd2h_bytes': evl['d2h']},
+                'roofline': {'kernel': 'k_row_scores', 'bound': 'hbm',
+                             'achieved': eval_pairs * BYTES_PAIR / 1e9 / (evl['score_ms'] / 1e3), 'peak': hbm_peak,
+                             'unit': 'GB/s', 'frac': eval_pairs * BYTES_PAIR / 1e9 / (evl['score_ms'] / 1e3) / hbm_peak,
+                             'traffic': None,
+                             'fp32_simt': {'achieved': eval_tflops, 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+                                           'frac': eval_tflops / FP32_PEAK_TFLOPS}},
+                'ndcg@5': evl['ndcg@5'], 'recall@5': evl['recall@5'], 'precision@5': evl['precision@5']}
+    line = {'metric': 'train_samples_per_s', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+            'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': tr['h2d'],
+                    'd2h_bytes_per_step': tr['d2h']},
+            'gpu_launches': int(tr['launches']), 'clocks': clk, 'roofline': roof, 'eval': eval_obj,
+            'last_loss': tr['last_loss']}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        X_cpu = synth_batches(32, U, I, SEED)
+        c = cpu_arm(U, I, X_cpu, budget_s=args.cpu_budget)
+        line['cpu_baseline'] = {'value': c['train_samples_per_s'], 'unit': 'samples/s', 'cores': c['cores'],
+                                'kind': 'port',
+                                'sample': '%d train steps of 128 samples (eager-PyTorch port of the reference path, '
+                                          'oracle/torch_port.py); eval sample %d users -> %.3f users/s'
+                                          % (c['train_steps'], c['eval_users'], c['eval_users_per_s']),
+                                'eval_users_per_s': c['eval_users_per_s']}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -10,6 +10,9 @@ from ._lib import Adam, Dims, Expo, Rng, check, ptr, stream_ptr
 
 D = _lib.DIM
 
+# number of kernels of this library launched so far (bench.py reports it as gpu_launches)
+LAUNCHES = [0]
+
 
 def make_dims(n_users, n_items, feat_dim, n_samples, n_attr, dim=D):
     return Dims(int(n_users), int(n_items), int(dim), int(feat_dim), int(n_samples), int(n_attr))
@@ -64,6 +67,7 @@ def noise_fill(out, std, seed, offset, row0=0):
     n_rows, F = out.shape
     check(lib.dccf_noise_fill(ptr(out), n_rows, F, float(std), int(seed), int(offset), int(row0), stream_ptr()),
           'dccf_noise_fill')
+    LAUNCHES[0] += 1
     return out
 
 
@@ -72,6 +76,7 @@ def dropout_mask_fill(out, p_drop, seed, offset, row0=0):
     n_rows, dim = out.shape
     check(lib.dccf_dropout_mask_fill(ptr(out), n_rows, dim, float(p_drop), int(seed), int(offset), int(row0),
                                      stream_ptr()), 'dccf_dropout_mask_fill')
+    LAUNCHES[0] += 1
     return out
 
 
@@ -83,6 +88,7 @@ def score_fwd(dims, E_user, E_item, Feat, W, b, expo, X, sample_item, rng, out_p
                              ctypes.byref(expo), ptr(X), ptr(sample_item), n_pairs, ctypes.byref(rng), ptr(out_pred),
                              ptr(ws_rows), ptr(ws_wt), ptr(save_h), ptr(save_w), ptr(err_flag), stream_ptr()),
           'dccf_score_fwd')
+    LAUNCHES[0] += 3 if n_pairs > 0 else 0      # k_transpose_w, k_row_scores, k_backdoor
     return out_pred
 
 
@@ -98,23 +104,27 @@ def bpr_bwd(dims, E_user, E_item, Feat, W, X, sample_item, Y, rng, loss_mode, pr
                            ptr(Y), n_pairs, ctypes.byref(rng), int(loss_mode), ptr(pred), ptr(save_h), ptr(save_w),
                            ptr(out_loss), ptr(gW_part), ptr(gb_part), ptr(gu_rec), ptr(gi_rec), ptr(rec_keys_u),
                            ptr(rec_keys_i), stream_ptr()), 'dccf_bpr_bwd')
+    LAUNCHES[0] += 1 if n_pairs > 0 else 0
 
 
 def adam_sweep(table, m, v, rec_keys, rec_grads, n_rec, head, nxt, hp):
     lib = _lib.load()
     check(lib.dccf_adam_sweep(ptr(table), ptr(m), ptr(v), table.shape[0], ptr(rec_keys), ptr(rec_grads), int(n_rec),
                               ptr(head), ptr(nxt), ctypes.byref(hp), stream_ptr()), 'dccf_adam_sweep')
+    LAUNCHES[0] += 2 if n_rec > 0 else 1        # k_link_records, k_adam_sweep
 
 
 def adam_dense(p, m, v, g_parts, n_parts, part_stride, hp):
     lib = _lib.load()
     check(lib.dccf_adam_dense(ptr(p), ptr(m), ptr(v), p.numel(), ptr(g_parts), int(n_parts), int(part_stride),
                               ctypes.byref(hp), stream_ptr()), 'dccf_adam_dense')
+    LAUNCHES[0] += 1
 
 
 def state_advance(step_dev, offset_dev, offset_inc=1):
     lib = _lib.load()
     check(lib.dccf_state_advance(ptr(step_dev), ptr(offset_dev), int(offset_inc), stream_ptr()), 'dccf_state_advance')
+    LAUNCHES[0] += 1
 
 
 def rank_eval(scores, labels, iids, cand_rows, user_off, k, out_metrics, out_topk_iid=None, out_topk_row=None):
@@ -122,4 +132,5 @@ def rank_eval(scores, labels, iids, cand_rows, user_off, k, out_metrics, out_top
     n_users = user_off.shape[0] - 1
     check(lib.dccf_rank_eval(ptr(scores), ptr(labels), ptr(iids), ptr(cand_rows), ptr(user_off), n_users, int(k),
                              ptr(out_topk_iid), ptr(out_topk_row), ptr(out_metrics), stream_ptr()), 'dccf_rank_eval')
+    LAUNCHES[0] += 1
     return out_metrics

@@ -293,7 +293,7 @@ class DCCF(DMF):
         self._check_ready()
         return FusedAdamState(self, lr=lr, l2=l2, weight_decay=l2 if weight_decay is None else weight_decay, **kw)
 
-    def train_step(self, feed_dict, opt=None):
+    def train_step(self, feed_dict, opt=None, stage_events=None):
         """One iteration of BaseRunner.fit (src/runners/BaseRunner.py:175-188): forward, loss, l2 term,
         backward, clip, Adam — four kernel launches plus the transposition of W, no autograd, no host sync.
         Returns the reference's out_dict (prediction, check, loss) with detached tensors."""
@@ -301,7 +301,11 @@ class DCCF(DMF):
         if not isinstance(opt, FusedAdamState):
             raise RuntimeError('train_step needs the fused optimizer state (model.make_fused_optimizer)')
         call = self._make_call(feed_dict)
+        if stage_events is not None:
+            stage_events[0].record()
         pred = self._launch_fwd(call, save=True)
+        if stage_events is not None:
+            stage_events[1].record()
         loss_mode = 0 if feed_dict['rank'] == 1 else 1
         Y = feed_dict.get('Y')
         if loss_mode == 1:
@@ -309,6 +313,8 @@ class DCCF(DMF):
         else:
             Y = None
         rec = self._launch_bwd(call, loss_mode=loss_mode, Y=Y)
+        if stage_events is not None:
+            stage_events[2].record()
         opt.step_count += 1
         hp = opt.hp()
         P, Z = call['P'], self.sample_num + 1
@@ -320,5 +326,7 @@ class DCCF(DMF):
         W, b = self.mlp[0].weight.data, self.mlp[0].bias.data
         kernels.adam_dense(W, opt.exp_avg['W'], opt.exp_avg_sq['W'], rec['gW_part'], rec['n_splits'], W.numel(), hp)
         kernels.adam_dense(b, opt.exp_avg['b'], opt.exp_avg_sq['b'], rec['gb_part'], rec['n_splits'], b.numel(), hp)
+        if stage_events is not None:
+            stage_events[3].record()
         loss = rec['loss'][0].clone()
         return {'prediction': pred, 'check': [('prediction', pred)], 'loss': loss}
