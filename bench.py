@@ -290,10 +290,12 @@ def bench_eval(model, n_users, warm_batches, world, rank, flush):
         ev_pairs.append((e0, e1))
         return sums, ev_pairs
 
-    # warm-up
+    # warm-up (also loads the ranker's module: CUDA loads kernels lazily on first launch)
     for _ in range(3):
-        model.predict({'X': X_d[:EVAL_BATCH], 'rank': 1, 'train': False, 'dropout': 0.0,
-                       'sample_item': si_d[:EVAL_BATCH]})
+        wp = model.predict({'X': X_d[:EVAL_BATCH], 'rank': 1, 'train': False, 'dropout': 0.0,
+                            'sample_item': si_d[:EVAL_BATCH]})['prediction']
+        n_w = int(off[min(len(off) - 1, max(1, EVAL_BATCH // (1 + TEST_NEG_N) - 1))])
+        rank_metrics_device(torch.zeros(rows, device=dev), Y_d, iid_d, cand_d, off_d, 5)
     barrier(world)
     sums, evs = run(False, X_d, True)
     barrier(world)

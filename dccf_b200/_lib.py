@@ -11,7 +11,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libdccf_b200.so')
-ABI_VERSION = 4
+ABI_VERSION = 5
 DIM = 64
 
 
@@ -60,6 +60,9 @@ _SIGNATURES = {
                                     ctypes.POINTER(Rng), ctypes.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'dccf_adam_sweep': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int64, _P, _P,
                                        ctypes.POINTER(Adam), _P]),
+    'dccf_adam_sweep_seg': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int32, ctypes.c_int64,
+                                           ctypes.c_int64, ctypes.c_int64, _P, _P, ctypes.POINTER(Adam), _P]),
+    'dccf_sum_parts': (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, _P, _P]),
     'dccf_adam_dense': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, _P, ctypes.c_int32, ctypes.c_int64,
                                        ctypes.POINTER(Adam), _P]),
     'dccf_state_advance': (ctypes.c_int, [_P, _P, ctypes.c_uint64, _P]),

@@ -61,11 +61,27 @@ __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g_
     p = fmaf(s.step_size, __fdiv_rn(m, denom), p);               // param.addcdiv_(exp_avg, denom, value = step_size)
 }
 
-__global__ void k_link_records(const int32_t* __restrict__ keys, int64_t n_rec, int64_t n_rows,
+// Records may arrive in n_seg segments of seg_len records each (one segment per data-parallel rank after the
+// all-gather): record r lives in segment r / seg_len at local index r % seg_len.
+struct RecLayout {
+    int64_t seg_len;
+    int64_t key_seg_stride;   // int32 elements between the key arrays of consecutive segments
+    int64_t grad_seg_stride;  // floats between the gradient arrays of consecutive segments
+};
+__device__ __forceinline__ size_t rec_key_index(const RecLayout& L, int64_t r) {
+    const int64_t seg = r / L.seg_len;
+    return (size_t)(seg * L.key_seg_stride + (r - seg * L.seg_len));
+}
+__device__ __forceinline__ size_t rec_grad_index(const RecLayout& L, int64_t r) {
+    const int64_t seg = r / L.seg_len;
+    return (size_t)(seg * L.grad_seg_stride + (r - seg * L.seg_len) * D);
+}
+
+__global__ void k_link_records(const int32_t* __restrict__ keys, int64_t n_rec, int64_t n_rows, RecLayout L,
                                int32_t* __restrict__ head, int32_t* __restrict__ next) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rec) return;
-    const int32_t k = keys[r];
+    const int32_t k = keys[rec_key_index(L, r)];
     if (k < 0 || k >= n_rows) {
         next[r] = -1;
         return;
@@ -76,7 +92,7 @@ __global__ void k_link_records(const int32_t* __restrict__ keys, int64_t n_rec, 
 // 16 lanes per table row (one float4 each); a warp covers two consecutive rows = 512 contiguous bytes.
 __global__ void __launch_bounds__(256) k_adam_sweep(float* __restrict__ table, float* __restrict__ m_,
                                                     float* __restrict__ v_, int64_t n_rows,
-                                                    const float* __restrict__ rec_grads,
+                                                    const float* __restrict__ rec_grads, RecLayout L,
                                                     int32_t* __restrict__ head, const int32_t* __restrict__ next,
                                                     const AdamHost hp) {
     const AdamScalars s = resolve_adam(hp);
@@ -103,7 +119,7 @@ __global__ void __launch_bounds__(256) k_adam_sweep(float* __restrict__ table, f
                 for (int32_t r = h; r >= 0; r = __ldg(next + r))
                     if (r > last && r < best) best = r;
                 if (best == 0x7fffffff) break;
-                const float4 rg = ldg4(rec_grads + (size_t)best * D + sub * 4);
+                const float4 rg = ldg4(rec_grads + rec_grad_index(L, best) + sub * 4);
                 g.x += rg.x; g.y += rg.y; g.z += rg.z; g.w += rg.w;
                 last = best;
             }
@@ -136,6 +152,17 @@ __global__ void __launch_bounds__(256) k_adam_dense(float* __restrict__ p_, floa
     }
 }
 
+// out[i] = sum_k parts[k * stride + i], ascending k (fixed order)
+__global__ void __launch_bounds__(256) k_sum_parts(const float* __restrict__ parts, int32_t n_parts, int64_t stride,
+                                                   int64_t n, float* __restrict__ out) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        float g = 0.f;
+        for (int32_t k = 0; k < n_parts; ++k) g += __ldg(parts + (size_t)k * stride + i);
+        out[i] = g;
+    }
+}
+
 __global__ void k_state_advance(int32_t* step_dev, uint64_t* offset_dev, uint64_t inc) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         if (step_dev) step_dev[0] += 1;
@@ -157,27 +184,55 @@ static int check_hp(const dccf_adam* hp, AdamHost* out, const char* who) {
 
 using namespace dccf;
 
-extern "C" int dccf_adam_sweep(float* table, float* m, float* v, int64_t n_table_rows, const int32_t* rec_keys,
-                               const float* rec_grads, int64_t n_rec, int32_t* head, int32_t* next,
-                               const dccf_adam* hp, void* stream_) {
+extern "C" int dccf_adam_sweep_seg(float* table, float* m, float* v, int64_t n_table_rows, const int32_t* rec_keys,
+                                   const float* rec_grads, int32_t n_seg, int64_t seg_len, int64_t key_seg_stride,
+                                   int64_t grad_seg_stride, int32_t* head, int32_t* next, const dccf_adam* hp,
+                                   void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     AdamHost h;
     int rc = check_hp(hp, &h, "dccf_adam_sweep");
     if (rc != DCCF_OK) return rc;
     DCCF_CHECK_ARG(table && m && v && head, "dccf_adam_sweep: null buffer");
+    DCCF_CHECK_ARG(n_seg >= 0 && seg_len >= 0, "dccf_adam_sweep: negative record layout");
+    const int64_t n_rec = (int64_t)n_seg * seg_len;
     DCCF_CHECK_ARG(n_rec == 0 || (rec_keys && rec_grads && next), "dccf_adam_sweep: %lld records but a null record buffer", (long long)n_rec);
-    DCCF_CHECK_ARG(n_rec >= 0 && n_rec < ((int64_t)1 << 31) && n_table_rows < ((int64_t)1 << 31), "dccf_adam_sweep: sizes exceed int32 indexing");
+    DCCF_CHECK_ARG(n_rec < ((int64_t)1 << 31) && n_table_rows < ((int64_t)1 << 31), "dccf_adam_sweep: sizes exceed int32 indexing");
+    DCCF_CHECK_ARG(n_seg <= 1 || (key_seg_stride >= seg_len && grad_seg_stride >= seg_len * D), "dccf_adam_sweep: segment strides overlap");
     if (n_table_rows <= 0) return DCCF_OK;
+    RecLayout L;
+    L.seg_len = seg_len > 0 ? seg_len : 1;
+    L.key_seg_stride = key_seg_stride;
+    L.grad_seg_stride = grad_seg_stride;
     if (n_rec > 0) {
-        k_link_records<<<(unsigned)((n_rec + 255) / 256), 256, 0, stream>>>(rec_keys, n_rec, n_table_rows, head, next);
+        k_link_records<<<(unsigned)((n_rec + 255) / 256), 256, 0, stream>>>(rec_keys, n_rec, n_table_rows, L, head, next);
         DCCF_CHECK_LAUNCH("k_link_records");
     }
     // 16 rows per 256-thread CTA per pass; cap the grid at 8 CTAs per SM and grid-stride beyond
     int64_t ctas = (n_table_rows + 15) / 16;
     const int64_t cap = 148 * 8;
     if (ctas > cap) ctas = cap;
-    k_adam_sweep<<<(unsigned)ctas, 256, 0, stream>>>(table, m, v, n_table_rows, rec_grads, head, next, h);
+    k_adam_sweep<<<(unsigned)ctas, 256, 0, stream>>>(table, m, v, n_table_rows, rec_grads, L, head, next, h);
     DCCF_CHECK_LAUNCH("k_adam_sweep");
+    return DCCF_OK;
+}
+
+extern "C" int dccf_adam_sweep(float* table, float* m, float* v, int64_t n_table_rows, const int32_t* rec_keys,
+                               const float* rec_grads, int64_t n_rec, int32_t* head, int32_t* next,
+                               const dccf_adam* hp, void* stream_) {
+    DCCF_CHECK_ARG(n_rec >= 0, "dccf_adam_sweep: negative record count");
+    return dccf_adam_sweep_seg(table, m, v, n_table_rows, rec_keys, rec_grads, 1, n_rec, n_rec, n_rec * D, head, next,
+                               hp, stream_);
+}
+
+extern "C" int dccf_sum_parts(const float* parts, int32_t n_parts, int64_t part_stride, int64_t n, float* out,
+                              void* stream_) {
+    DCCF_CHECK_ARG(out && (n_parts == 0 || parts), "dccf_sum_parts: null buffer");
+    DCCF_CHECK_ARG(n_parts >= 0 && part_stride >= 0, "dccf_sum_parts: bad layout");
+    if (n <= 0) return DCCF_OK;
+    int64_t ctas = (n + 255) / 256;
+    if (ctas > 148 * 8) ctas = 148 * 8;
+    k_sum_parts<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream_>>>(parts, n_parts, part_stride, n, out);
+    DCCF_CHECK_LAUNCH("k_sum_parts");
     return DCCF_OK;
 }
 

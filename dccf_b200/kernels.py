@@ -114,6 +114,22 @@ def adam_sweep(table, m, v, rec_keys, rec_grads, n_rec, head, nxt, hp):
     LAUNCHES[0] += 2 if n_rec > 0 else 1        # k_link_records, k_adam_sweep
 
 
+def adam_sweep_seg(table, m, v, rec_keys, rec_grads, n_seg, seg_len, key_seg_stride, grad_seg_stride, head, nxt, hp):
+    """Records in n_seg segments (one per data-parallel rank); strides in elements of the key / gradient arrays."""
+    lib = _lib.load()
+    check(lib.dccf_adam_sweep_seg(ptr(table), ptr(m), ptr(v), table.shape[0], ptr(rec_keys), ptr(rec_grads),
+                                  int(n_seg), int(seg_len), int(key_seg_stride), int(grad_seg_stride), ptr(head),
+                                  ptr(nxt), ctypes.byref(hp), stream_ptr()), 'dccf_adam_sweep_seg')
+    LAUNCHES[0] += 2 if n_seg * seg_len > 0 else 1
+
+
+def sum_parts(parts, n_parts, part_stride, n, out):
+    lib = _lib.load()
+    check(lib.dccf_sum_parts(ptr(parts), int(n_parts), int(part_stride), int(n), ptr(out), stream_ptr()),
+          'dccf_sum_parts')
+    LAUNCHES[0] += 1
+
+
 def adam_dense(p, m, v, g_parts, n_parts, part_stride, hp):
     lib = _lib.load()
     check(lib.dccf_adam_dense(ptr(p), ptr(m), ptr(v), p.numel(), ptr(g_parts), int(n_parts), int(part_stride),

@@ -111,6 +111,30 @@ class BaseModel(torch.nn.Module):
         return evaluations
 
     @staticmethod
+    def evaluate_sums(p, data, metrics):
+        """(sums, counts) per metric over the rows of `data`, so that partial results of user shards can be
+        added across ranks: rank metrics sum over users, mae sums |err| and rmse sums err^2 over rows."""
+        sums, counts = [], []
+        ctx = None
+        for metric in metrics:
+            if metric in ('rmse', 'mae'):
+                pl = p.detach().cpu().numpy() if torch.is_tensor(p) else np.asarray(p)
+                d = np.asarray(data['Y'], dtype=np.float64) - pl.astype(np.float64)
+                sums.append(float(np.sum(d * d) if metric == 'rmse' else np.sum(np.abs(d))))
+                counts.append(float(len(d)))
+                continue
+            name, k = metric.split('@')
+            if ctx is None:
+                dev = p.device if (torch.is_tensor(p) and p.is_cuda) else torch.device('cuda', torch.cuda.current_device())
+                ctx = rank_context(data, dev)
+                scores = p.to(dev, torch.float32).contiguous() if torch.is_tensor(p) else \
+                    torch.from_numpy(np.ascontiguousarray(p, dtype=np.float32)).to(dev)
+            m = rank_metrics_device(scores, ctx['labels'], ctx['iids'], ctx['rows'], ctx['off'], int(k))
+            sums.append(float(m[:, METRIC_COLUMN[name]].sum().item()))
+            counts.append(float(m.shape[0]))
+        return sums, counts
+
+    @staticmethod
     def init_paras(m):
         """N(0, 0.01) for Linear weights/biases and Embedding weights (BaseModel.py:131-141); applied
         through `model.apply` in module order, on the torch CPU generator (src/main.py:150)."""

@@ -109,6 +109,7 @@ class DCCF(DMF):
         self._rng_offset = 0
         self._ws = {}
         self._err_flag = None
+        self._dp = None
 
     # ---- construction ------------------------------------------------------------------------
     @staticmethod
@@ -207,7 +208,10 @@ class DCCF(DMF):
         if mask is not None:
             mask = mask.to(dev, torch.float32).contiguous()
         self._rng_offset += 1
-        rng = kernels.make_rng(noise=noise, mask=mask, noise_std=self.std, p_drop=p_drop, seed=self.random_seed,
+        seed = self.random_seed
+        if self._dp is not None:                       # decorrelate the ranks' noise / dropout streams
+            seed = (seed + 0x9E3779B97F4A7C15 * self._dp['rank']) & 0xffffffffffffffff
+        rng = kernels.make_rng(noise=noise, mask=mask, noise_std=self.std, p_drop=p_drop, seed=seed,
                                offset=self._rng_offset, generate_noise=(noise is None and self.std > 0),
                                generate_mask=(mask is None and p_drop > 0))
         return {'X': X, 'sample_item': sample_item, 'rng': rng, 'noise': noise, 'mask': mask, 'P': P,
@@ -242,13 +246,19 @@ class DCCF(DMF):
         rec = {
             'gW_part': self._buf('gW_part', (n_splits, D, K), torch.float32),
             'gb_part': self._buf('gb_part', (n_splits, D), torch.float32),
-            'gu_rec': self._buf('gu_rec', (P, D), torch.float32),
-            'gi_rec': self._buf('gi_rec', (P * Z, D), torch.float32),
-            'keys_u': self._buf('keys_u', (P,), torch.int32),
-            'keys_i': self._buf('keys_i', (P * Z,), torch.int32),
-            'loss': self._buf('loss', (1,), torch.float32),
             'n_splits': n_splits,
         }
+        if self._dp is not None and loss_mode != 2:
+            ex = self._exchange_for(P)
+            v = ex.send_views()
+            rec.update({'gu_rec': v['gu_rec'], 'gi_rec': v['gi_rec'], 'keys_u': v['keys_u'], 'keys_i': v['keys_i'],
+                        'loss': v['loss'], 'exchange': ex, 'send': v})
+        else:
+            rec.update({'gu_rec': self._buf('gu_rec', (P, D), torch.float32),
+                        'gi_rec': self._buf('gi_rec', (P * Z, D), torch.float32),
+                        'keys_u': self._buf('keys_u', (P,), torch.int32),
+                        'keys_i': self._buf('keys_i', (P * Z,), torch.int32),
+                        'loss': self._buf('loss', (1,), torch.float32)})
         kernels.bpr_bwd(self._dims(), self.uid_embeddings.weight.data, self.iid_embeddings.weight.data,
                         self.feature_embedding, self.mlp[0].weight.data, call['X'], call['sample_item'], Y,
                         call['rng'], loss_mode, call['pred'], call['save_h'], call['save_w'], rec['loss'],
@@ -288,6 +298,24 @@ class DCCF(DMF):
         out_dict['loss'] = loss
         return out_dict
 
+    # ---- data parallel ----------------------------------------------------------------------
+    def enable_data_parallel(self, group=None):
+        """Replicated parameters, per-rank batches, gradients exchanged with one all-gather per step
+        (dccf_b200/dist.py).  Requires an initialised torch.distributed process group."""
+        import torch.distributed as dist
+        self._dp = {'world': dist.get_world_size(group), 'rank': dist.get_rank(group), 'group': group, 'ex': {}}
+        return self
+
+    def _exchange_for(self, P):
+        from ..dist import GradExchange
+        ex = self._dp['ex'].get(P)
+        if ex is None:
+            D, Z = self.ui_vector_size, self.sample_num + 1
+            ex = GradExchange(P, Z, D, D + self.feature_embedding.shape[1], self._dp['world'], self._dp['rank'],
+                              self.uid_embeddings.weight.device, group=self._dp['group'])
+            self._dp['ex'][P] = ex
+        return ex
+
     # ---- fused training step -----------------------------------------------------------------
     def make_fused_optimizer(self, lr, l2, weight_decay=None, **kw):
         self._check_ready()
@@ -318,12 +346,32 @@ class DCCF(DMF):
         opt.step_count += 1
         hp = opt.hp()
         P, Z = call['P'], self.sample_num + 1
+        W, b = self.mlp[0].weight.data, self.mlp[0].bias.data
+        if 'exchange' in rec:
+            # fold the row-split partials, then ONE all-gather of the packed segment (records, dW, db, keys, loss)
+            ex, v = rec['exchange'], rec['send']
+            kernels.sum_parts(rec['gW_part'], rec['n_splits'], W.numel(), W.numel(), v['gW'])
+            kernels.sum_parts(rec['gb_part'], rec['n_splits'], b.numel(), b.numel(), v['gb'])
+            recv = ex.exchange()
+            world, seg = ex.world, ex.seg
+            nxt = self._buf('next', (world * P * Z,), torch.int32)
+            kernels.adam_sweep_seg(self.uid_embeddings.weight.data, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'],
+                                   ex.part(recv, 'keys_u'), ex.part(recv, 'gu'), world, P, seg, seg, opt.head_u, nxt,
+                                   hp)
+            kernels.adam_sweep_seg(self.iid_embeddings.weight.data, opt.exp_avg['E_item'], opt.exp_avg_sq['E_item'],
+                                   ex.part(recv, 'keys_i'), ex.part(recv, 'gi'), world, P * Z, seg, seg, opt.head_i,
+                                   nxt, hp)
+            kernels.adam_dense(W, opt.exp_avg['W'], opt.exp_avg_sq['W'], ex.part(recv, 'gW'), world, seg, hp)
+            kernels.adam_dense(b, opt.exp_avg['b'], opt.exp_avg_sq['b'], ex.part(recv, 'gb'), world, seg, hp)
+            if stage_events is not None:
+                stage_events[3].record()
+            loss = ex.total_loss()
+            return {'prediction': pred, 'check': [('prediction', pred)], 'loss': loss}
         nxt = self._buf('next', (P * Z,), torch.int32)
         kernels.adam_sweep(self.uid_embeddings.weight.data, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'],
                            rec['keys_u'], rec['gu_rec'], P, opt.head_u, nxt, hp)
         kernels.adam_sweep(self.iid_embeddings.weight.data, opt.exp_avg['E_item'], opt.exp_avg_sq['E_item'],
                            rec['keys_i'], rec['gi_rec'], P * Z, opt.head_i, nxt, hp)
-        W, b = self.mlp[0].weight.data, self.mlp[0].bias.data
         kernels.adam_dense(W, opt.exp_avg['W'], opt.exp_avg_sq['W'], rec['gW_part'], rec['n_splits'], W.numel(), hp)
         kernels.adam_dense(b, opt.exp_avg['b'], opt.exp_avg_sq['b'], rec['gb_part'], rec['n_splits'], b.numel(), hp)
         if stage_events is not None:

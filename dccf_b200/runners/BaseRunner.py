@@ -58,6 +58,7 @@ class BaseRunner(object):
         self.time = None
         self.train_results, self.valid_results, self.test_results = [], [], []
         self.show_progress = True
+        self._shards = {}          # id(data) -> (data, rows, shard dict, batches): user-sharded evaluation sets
 
     # ---- optimizer ---------------------------------------------------------------------------
     def _build_optimizer(self, model):
@@ -120,8 +121,52 @@ class BaseRunner(object):
         return pred[torch.from_numpy(pos).to(pred.device)]
 
     def predict(self, model, data, data_processor):
-        """np.ndarray of predictions aligned with `data` (BaseRunner.py:134-157)."""
+        """np.ndarray of predictions aligned with `data` (BaseRunner.py:134-157).  Under data parallelism every
+        rank scores its own users and the pieces are gathered, so all ranks return the full array."""
+        if self._world(model) > 1:
+            import torch.distributed as dist
+            rows, pred, _ = self._predict_shard(model, data, data_processor)
+            pieces = [None] * dist.get_world_size()
+            dist.all_gather_object(pieces, (rows, pred.cpu().numpy()))
+            out = np.empty(len(data['Y']), dtype=np.float32)
+            for r, p in pieces:
+                out[r] = p
+            return out
         return self._predict_device(model, data, data_processor).cpu().numpy()
+
+    # ---- user-sharded evaluation (new: the reference is single-process, SURVEY.md §8e) ---------------
+    @staticmethod
+    def _world(model):
+        from ..dist import is_distributed
+        if getattr(model, '_dp', None) is None or not is_distributed():
+            return 1
+        return model._dp['world']
+
+    def _predict_shard(self, model, data, data_processor):
+        """(row indices owned by this rank, device predictions for them): contiguous user blocks, all
+        candidates of a user on one rank."""
+        from ..dist import shard_users
+        hit = self._shards.get(id(data))
+        if hit is None or hit[0] is not data:
+            rows = shard_users(data['uid'], model._dp['rank'], model._dp['world'])
+            shard = {k: (np.asarray(v)[rows] if hasattr(v, '__len__') and len(v) == len(data['Y']) else v)
+                     for k, v in data.items()}
+            shard[global_p.K_SAMPLE_ID] = np.arange(len(rows))
+            hit = (data, rows, shard)
+            self._shards[id(data)] = hit
+        _, rows, shard = hit
+        saved = data_processor.vt_batches_buffer
+        key = ('shard', id(data), self.eval_batch_size)
+        if key not in saved:
+            saved[key] = data_processor._prepare_batches_rk(shard, self.eval_batch_size, train=False) \
+                if data_processor.rank == 1 else data_processor._prepare_batches_rt(shard, self.eval_batch_size, False)
+        batches = self.batches_add_control(saved[key], train=False)
+        model.eval()
+        outs = []
+        with torch.no_grad():
+            for batch in self._bar(batches, desc='Predict'):
+                outs.append(model.predict(batch)['prediction'].detach())
+        return rows, (torch.cat(outs) if len(outs) > 1 else outs[0]), shard
 
     # ---- training ----------------------------------------------------------------------------
     def fit(self, model, data, data_processor, epoch=-1):
@@ -233,6 +278,15 @@ class BaseRunner(object):
         uid/iid/score/label sorted by uid to <dataset dir>/rank.csv (tab separated)."""
         if metrics is None:
             metrics = self.metrics
+        if self._world(model) > 1 and not write_rank:
+            # every rank evaluates its users; sums and user counts are all-reduced (one small collective)
+            from ..dist import all_reduce_sum
+            rows, pred, shard = self._predict_shard(model, data, data_processor)
+            sums, counts = model.evaluate_sums(pred, shard, metrics)
+            tot = all_reduce_sum(list(sums) + list(counts))
+            n = len(metrics)
+            return [float(np.sqrt(tot[i] / tot[n + i])) if metrics[i] == 'rmse' else float(tot[i] / tot[n + i])
+                    for i in range(n)]
         pred = self._predict_device(model, data, data_processor)
         if write_rank:
             df = pd.DataFrame()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 4
+#define DCCF_ABI_VERSION 5
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -155,6 +155,17 @@ typedef struct dccf_adam {
 int dccf_adam_sweep(float* table, float* m, float* v, int64_t n_table_rows,
                     const int32_t* rec_keys, const float* rec_grads, int64_t n_rec,
                     int32_t* head, int32_t* next, const dccf_adam* hp, void* stream);
+/* Same, with the records in n_seg segments of seg_len records (one segment per data-parallel rank after
+ * the gradient all-gather): segment s has its keys at rec_keys + s*key_seg_stride (int32 units) and its
+ * gradients at rec_grads + s*grad_seg_stride (float units).  Records are summed in ascending global index
+ * (segment-major), so every rank computes bit-identical updates. */
+int dccf_adam_sweep_seg(float* table, float* m, float* v, int64_t n_table_rows,
+                        const int32_t* rec_keys, const float* rec_grads, int32_t n_seg, int64_t seg_len,
+                        int64_t key_seg_stride, int64_t grad_seg_stride,
+                        int32_t* head, int32_t* next, const dccf_adam* hp, void* stream);
+/* out[i] = sum_k parts[k*part_stride + i], ascending k: folds the row-split partials of dccf_bpr_bwd into one
+ * [D, D+F] gradient before it is exchanged between ranks. */
+int dccf_sum_parts(const float* parts, int32_t n_parts, int64_t part_stride, int64_t n, float* out, void* stream);
 /* Dense variant for mlp.0.weight / mlp.0.bias: g = sum over n_parts partial buffers of n floats. */
 int dccf_adam_dense(float* p, float* m, float* v, int64_t n, const float* g_parts,
                     int32_t n_parts, int64_t part_stride, const dccf_adam* hp, void* stream);

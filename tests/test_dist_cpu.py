@@ -1,0 +1,76 @@
+"""Host side of the multi-GPU path on CPU: world_size-2 gloo exchange of the packed gradient segments,
+user sharding of the evaluation set, metric all-reduce."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dccf_b200.dist import GradExchange, all_reduce_sum, shard_users
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        P, Z, D, K = 6, 3, 64, 128
+        ex = GradExchange(P, Z, D, K, world, rank, torch.device('cpu'))
+        v = ex.send_views()
+        g = torch.Generator().manual_seed(100 + rank)
+        v['gu_rec'].copy_(torch.randn(P, D, generator=g))
+        v['gi_rec'].copy_(torch.randn(P * Z, D, generator=g))
+        v['gW'].copy_(torch.randn(D, K, generator=g))
+        v['gb'].copy_(torch.randn(D, generator=g))
+        v['keys_u'].copy_(torch.arange(P, dtype=torch.int32) + 1000 * rank)
+        v['keys_i'].copy_(torch.arange(P * Z, dtype=torch.int32) + 5000 * rank)
+        v['loss'].fill_(float(rank + 1))
+        recv = ex.exchange()
+        # every rank sees every segment, rank-major, keys intact as int32
+        for r in range(world):
+            gr = torch.Generator().manual_seed(100 + r)
+            assert torch.equal(ex.part(recv, 'gu', r).view(P, D), torch.randn(P, D, generator=gr))
+            assert torch.equal(ex.part(recv, 'gi', r).view(P * Z, D), torch.randn(P * Z, D, generator=gr))
+            assert torch.equal(ex.part(recv, 'gW', r).view(D, K), torch.randn(D, K, generator=gr))
+            assert torch.equal(ex.part(recv, 'keys_u', r), torch.arange(P, dtype=torch.int32) + 1000 * r)
+            assert torch.equal(ex.part(recv, 'keys_i', r), torch.arange(P * Z, dtype=torch.int32) + 5000 * r)
+        assert float(ex.total_loss()) == sum(range(1, world + 1))
+        assert ex.seg % 4 == 0 and all(a % 4 == 0 for a, _ in ex.off.values())
+        # evaluation: users partitioned, metric sums reduced
+        rs = np.random.RandomState(0)
+        uid = rs.randint(0, 37, size=500)
+        mine = shard_users(uid, rank, world)
+        sums = all_reduce_sum([float(len(mine)), float(len(set(uid[mine].tolist())))])
+        assert sums[0] == 500 and sums[1] == len(set(uid.tolist()))
+        np.save(os.path.join(out_dir, 'rows_%d.npy' % rank), mine)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_exchange_and_sharding(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    rs = np.random.RandomState(0)
+    uid = rs.randint(0, 37, size=500)
+    rows = [np.load(os.path.join(str(tmp_path), 'rows_%d.npy' % r)) for r in range(2)]
+    assert len(np.intersect1d(rows[0], rows[1])) == 0
+    assert len(rows[0]) + len(rows[1]) == 500
+    # a user's candidates never straddle two ranks
+    assert len(set(uid[rows[0]].tolist()) & set(uid[rows[1]].tolist())) == 0
+
+
+def test_shard_users_single_rank_and_balance():
+    uid = np.repeat(np.arange(100), 11)
+    assert np.array_equal(shard_users(uid, 0, 1), np.arange(1100))
+    sizes = [len(shard_users(uid, r, 8)) for r in range(8)]
+    assert sum(sizes) == 1100 and max(sizes) - min(sizes) <= 11
