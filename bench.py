@@ -201,12 +201,11 @@ def bench_train(model, X_all, steps, warmup, world, flush):
     Y = torch.cat([torch.ones(BATCH), torch.zeros(BATCH)]).to(dev)
     I = model.item_num
 
-    # ---- value: inputs resident in HBM --------------------------------------------------------
+    # ---- value: inputs resident in HBM, the step replayed as one CUDA graph ----------------------
     X_dev = torch.from_numpy(X_all[:n]).to(dev)
     torch.manual_seed(SEED + 11)
     si_dev = torch.randint(I, size=(n, 2 * BATCH, S)).to(dev)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n)]
-    stage_ms = np.zeros(3)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(n)]
     launches0 = kernels.LAUNCHES[0]
     barrier(world)
     for i in range(n):
@@ -215,15 +214,28 @@ def bench_train(model, X_all, steps, warmup, world, flush):
             launches0 = kernels.LAUNCHES[0]
         flush()
         fd = {'X': X_dev[i], 'Y': Y, 'rank': 1, 'train': True, 'dropout': DROPOUT, 'sample_item': si_dev[i]}
-        model.train_step(fd, stage_events=ev[i])
+        ev[i][0].record()
+        model.train_step(fd)
+        ev[i][1].record()
     barrier(world)
     launches = kernels.LAUNCHES[0] - launches0
-    per_step = [ev[i][0].elapsed_time(ev[i][3]) for i in range(warmup, n)]
-    for i in range(warmup, n):
-        for s in range(3):
-            stage_ms[s] += ev[i][s].elapsed_time(ev[i][s + 1])
+    per_step = [ev[i][0].elapsed_time(ev[i][1]) for i in range(warmup, n)]
     total_ms = dist_max(float(np.sum(per_step)), world)
     model.check_ids()
+
+    # ---- stage breakdown: the same step launched kernel by kernel with events between the stages ------
+    n_s = min(n, warmup + 50)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_s)]
+    stage_ms = np.zeros(3)
+    for i in range(n_s):
+        flush()
+        fd = {'X': X_dev[i], 'Y': Y, 'rank': 1, 'train': True, 'dropout': DROPOUT, 'sample_item': si_dev[i]}
+        model.train_step(fd, stage_events=evs[i])
+    barrier(world)
+    for i in range(warmup, n_s):
+        for st in range(3):
+            stage_ms[st] += evs[i][st].elapsed_time(evs[i][st + 1])
+    stage_ms /= max(1, n_s - warmup)
 
     # ---- e2e: public API from pinned host memory, loss read back every step ---------------------
     X_pin = torch.from_numpy(X_all[:n]).pin_memory()
@@ -247,7 +259,7 @@ def bench_train(model, X_all, steps, warmup, world, flush):
             e2e_s += t1 - t0
     assert np.isfinite(loss)
     e2e_s = dist_max(e2e_s, world)
-    return {'total_ms': total_ms, 'stage_ms': stage_ms / steps, 'launches': launches, 'e2e_s': e2e_s,
+    return {'total_ms': total_ms, 'stage_ms': stage_ms, 'launches': launches, 'e2e_s': e2e_s,
             'h2d': 2 * BATCH * 2 * 8 + 2 * BATCH * S * 8, 'd2h': 4, 'last_loss': loss}
 
 
@@ -292,9 +304,8 @@ def bench_eval(model, n_users, warm_batches, world, rank, flush):
 
     # warm-up (also loads the ranker's module: CUDA loads kernels lazily on first launch)
     for _ in range(3):
-        wp = model.predict({'X': X_d[:EVAL_BATCH], 'rank': 1, 'train': False, 'dropout': 0.0,
-                            'sample_item': si_d[:EVAL_BATCH]})['prediction']
-        n_w = int(off[min(len(off) - 1, max(1, EVAL_BATCH // (1 + TEST_NEG_N) - 1))])
+        model.predict({'X': X_d[:EVAL_BATCH], 'rank': 1, 'train': False, 'dropout': 0.0,
+                            'sample_item': si_d[:EVAL_BATCH]})
         rank_metrics_device(torch.zeros(rows, device=dev), Y_d, iid_d, cand_d, off_d, 5)
     barrier(world)
     sums, evs = run(False, X_d, True)

@@ -11,7 +11,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libdccf_b200.so')
-ABI_VERSION = 5
+ABI_VERSION = 6
 DIM = 64
 
 
@@ -44,6 +44,19 @@ class Adam(ctypes.Structure):
                 ('step_dev', ctypes.c_void_p)]
 
 
+class AdamTable(ctypes.Structure):
+    _fields_ = [('table', ctypes.c_void_p), ('m', ctypes.c_void_p), ('v', ctypes.c_void_p), ('n_rows', ctypes.c_int64),
+                ('rec_keys', ctypes.c_void_p), ('rec_grads', ctypes.c_void_p), ('n_seg', ctypes.c_int32),
+                ('_pad', ctypes.c_int32), ('seg_len', ctypes.c_int64), ('key_seg_stride', ctypes.c_int64),
+                ('grad_seg_stride', ctypes.c_int64), ('head', ctypes.c_void_p), ('next', ctypes.c_void_p)]
+
+
+class AdamTensor(ctypes.Structure):
+    _fields_ = [('p', ctypes.c_void_p), ('m', ctypes.c_void_p), ('v', ctypes.c_void_p), ('n', ctypes.c_int64),
+                ('g_parts', ctypes.c_void_p), ('n_parts', ctypes.c_int32), ('_pad', ctypes.c_int32),
+                ('part_stride', ctypes.c_int64)]
+
+
 _P = ctypes.c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)   — one entry per symbol declared in include/dccf_b200.h
@@ -65,6 +78,8 @@ _SIGNATURES = {
     'dccf_sum_parts': (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, _P, _P]),
     'dccf_adam_dense': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, _P, ctypes.c_int32, ctypes.c_int64,
                                        ctypes.POINTER(Adam), _P]),
+    'dccf_adam_step': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(AdamTensor),
+                                      ctypes.c_int32, ctypes.POINTER(Adam), _P]),
     'dccf_state_advance': (ctypes.c_int, [_P, _P, ctypes.c_uint64, _P]),
     'dccf_rank_eval': (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, _P, _P]),
 }

@@ -163,6 +163,127 @@ __global__ void __launch_bounds__(256) k_sum_parts(const float* __restrict__ par
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One launch for the whole optimizer step: every embedding table and every dense tensor.  The grid is
+// partitioned by block ranges; each range grid-strides over its own tensor.
+// ---------------------------------------------------------------------------------------------
+constexpr int ADAM_MAX_T = 4;
+
+struct AdamTableArgs {
+    float *table, *m, *v;
+    int64_t n_rows;
+    const int32_t* keys;
+    const float* grads;
+    int64_t n_rec;
+    RecLayout L;
+    int32_t* head;
+    int32_t* next;
+    int32_t block_lo, block_n;    // block range of the sweep kernel
+    int32_t link_lo, link_n;      // block range of the link kernel
+};
+struct AdamDenseArgs {
+    float *p, *m, *v;
+    int64_t n;
+    const float* g_parts;
+    int32_t n_parts;
+    int64_t part_stride;
+    int32_t block_lo, block_n;
+};
+struct AdamAllArgs {
+    AdamTableArgs t[ADAM_MAX_T];
+    AdamDenseArgs d[ADAM_MAX_T];
+    int32_t n_tables, n_dense;
+    AdamHost hp;
+};
+
+__global__ void k_link_all(const AdamAllArgs a) {
+    for (int i = 0; i < a.n_tables; ++i) {
+        const AdamTableArgs& t = a.t[i];
+        const int b = (int)blockIdx.x - t.link_lo;
+        if (b < 0 || b >= t.link_n) continue;
+        const int64_t r = (int64_t)b * blockDim.x + threadIdx.x;
+        if (r >= t.n_rec) return;
+        const int32_t k = t.keys[rec_key_index(t.L, r)];
+        t.next[r] = (k < 0 || k >= t.n_rows) ? -1 : atomicExch(&t.head[k], (int32_t)r);
+        return;
+    }
+}
+
+// gradient of one table row from its record list, ascending record index
+__device__ __forceinline__ float4 gather_row_grad(const AdamTableArgs& t, int32_t h, int sub) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    int32_t last = -1;
+    while (true) {
+        int32_t best = 0x7fffffff;
+        for (int32_t r = h; r >= 0; r = __ldg(t.next + r))
+            if (r > last && r < best) best = r;
+        if (best == 0x7fffffff) break;
+        const float4 rg = ldg4(t.grads + rec_grad_index(t.L, best) + sub * 4);
+        g.x += rg.x; g.y += rg.y; g.z += rg.z; g.w += rg.w;
+        last = best;
+    }
+    return g;
+}
+
+__global__ void __launch_bounds__(256) k_adam_all(const AdamAllArgs a) {
+    const AdamScalars s = resolve_adam(a.hp);
+    const int bid = (int)blockIdx.x;
+    for (int i = 0; i < a.n_tables; ++i) {
+        const AdamTableArgs& t = a.t[i];
+        const int b = bid - t.block_lo;
+        if (b < 0 || b >= t.block_n) continue;
+        const int sub = threadIdx.x & 15;
+        const int half = (threadIdx.x >> 4) & 1;
+        const int64_t warp = ((int64_t)b * blockDim.x + threadIdx.x) >> 5;
+        const int64_t n_warps = ((int64_t)t.block_n * blockDim.x) >> 5;
+        // a warp owns rows 4w .. 4w+3 per trip (two per half-warp): six 16-byte loads in flight per lane
+        for (int64_t w = warp; 4 * w < t.n_rows; w += n_warps) {
+            const int64_t r0 = 4 * w + half, r1 = r0 + 2;
+            const bool v0 = r0 < t.n_rows, v1 = r1 < t.n_rows;
+            const size_t o0 = (size_t)(v0 ? r0 : 0) * D + sub * 4, o1 = (size_t)(v1 ? r1 : 0) * D + sub * 4;
+            float4 p0 = ld4(t.table + o0), m0 = ld4(t.m + o0), q0 = ld4(t.v + o0);
+            float4 p1 = ld4(t.table + o1), m1 = ld4(t.m + o1), q1 = ld4(t.v + o1);
+            const int32_t h0 = v0 ? t.head[r0] : -1;
+            const int32_t h1 = v1 ? t.head[r1] : -1;
+            __syncwarp();  // every lane holds its list heads before any lane resets them
+            float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+            if (h0 >= 0) {
+                g0 = gather_row_grad(t, h0, sub);
+                if (sub == 0) t.head[r0] = -1;
+            }
+            if (h1 >= 0) {
+                g1 = gather_row_grad(t, h1, sub);
+                if (sub == 0) t.head[r1] = -1;
+            }
+            if (v0) {
+                adam_elem(p0.x, m0.x, q0.x, g0.x, s); adam_elem(p0.y, m0.y, q0.y, g0.y, s);
+                adam_elem(p0.z, m0.z, q0.z, g0.z, s); adam_elem(p0.w, m0.w, q0.w, g0.w, s);
+                st4(t.table + o0, p0); st4(t.m + o0, m0); st4(t.v + o0, q0);
+            }
+            if (v1) {
+                adam_elem(p1.x, m1.x, q1.x, g1.x, s); adam_elem(p1.y, m1.y, q1.y, g1.y, s);
+                adam_elem(p1.z, m1.z, q1.z, g1.z, s); adam_elem(p1.w, m1.w, q1.w, g1.w, s);
+                st4(t.table + o1, p1); st4(t.m + o1, m1); st4(t.v + o1, q1);
+            }
+        }
+        return;
+    }
+    for (int i = 0; i < a.n_dense; ++i) {
+        const AdamDenseArgs& d = a.d[i];
+        const int b = bid - d.block_lo;
+        if (b < 0 || b >= d.block_n) continue;
+        const int64_t stride = (int64_t)d.block_n * blockDim.x;
+        for (int64_t e = (int64_t)b * blockDim.x + threadIdx.x; e < d.n; e += stride) {
+            float g = 0.f;
+            for (int32_t k = 0; k < d.n_parts; ++k) g += __ldg(d.g_parts + (size_t)k * d.part_stride + e);
+            float p = d.p[e], m = d.m[e], v = d.v[e];
+            adam_elem(p, m, v, g, s);
+            d.p[e] = p; d.m[e] = m; d.v[e] = v;
+        }
+        return;
+    }
+}
+
 __global__ void k_state_advance(int32_t* step_dev, uint64_t* offset_dev, uint64_t inc) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         if (step_dev) step_dev[0] += 1;
@@ -258,5 +379,62 @@ extern "C" int dccf_state_advance(int32_t* step_dev, uint64_t* offset_dev, uint6
     if (!step_dev && !offset_dev) return DCCF_OK;
     k_state_advance<<<1, 32, 0, stream>>>(step_dev, offset_dev, offset_inc);
     DCCF_CHECK_LAUNCH("k_state_advance");
+    return DCCF_OK;
+}
+
+extern "C" int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
+                              int32_t n_dense, const dccf_adam* hp, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AdamAllArgs a;
+    int rc = check_hp(hp, &a.hp, "dccf_adam_step");
+    if (rc != DCCF_OK) return rc;
+    DCCF_CHECK_ARG(n_tables >= 0 && n_tables <= ADAM_MAX_T && n_dense >= 0 && n_dense <= ADAM_MAX_T,
+                   "dccf_adam_step: at most %d tables and %d dense tensors per call", ADAM_MAX_T, ADAM_MAX_T);
+    DCCF_CHECK_ARG((n_tables == 0 || tables) && (n_dense == 0 || dense), "dccf_adam_step: null descriptor array");
+    a.n_tables = n_tables;
+    a.n_dense = n_dense;
+    int64_t total_rows = 0;
+    for (int i = 0; i < n_tables; ++i) total_rows += tables[i].n_rows > 0 ? tables[i].n_rows : 0;
+    int32_t blocks = 0, link_blocks = 0;
+    const int64_t budget = 148 * 8;   // CTAs for the table sweeps, shared in proportion to the row counts
+    for (int i = 0; i < n_tables; ++i) {
+        const dccf_adam_table& t = tables[i];
+        DCCF_CHECK_ARG(t.table && t.m && t.v && t.head, "dccf_adam_step: table %d has a null buffer", i);
+        const int64_t n_rec = (int64_t)t.n_seg * t.seg_len;
+        DCCF_CHECK_ARG(t.n_seg >= 0 && t.seg_len >= 0, "dccf_adam_step: table %d has a negative record layout", i);
+        DCCF_CHECK_ARG(n_rec == 0 || (t.rec_keys && t.rec_grads && t.next), "dccf_adam_step: table %d has records but a null record buffer", i);
+        DCCF_CHECK_ARG(n_rec < ((int64_t)1 << 31) && t.n_rows < ((int64_t)1 << 31), "dccf_adam_step: table %d exceeds int32 indexing", i);
+        DCCF_CHECK_ARG(t.n_seg <= 1 || (t.key_seg_stride >= t.seg_len && t.grad_seg_stride >= t.seg_len * D), "dccf_adam_step: table %d segment strides overlap", i);
+        AdamTableArgs& o = a.t[i];
+        o.table = t.table; o.m = t.m; o.v = t.v; o.n_rows = t.n_rows > 0 ? t.n_rows : 0;
+        o.keys = t.rec_keys; o.grads = t.rec_grads; o.n_rec = n_rec;
+        o.L.seg_len = t.seg_len > 0 ? t.seg_len : 1; o.L.key_seg_stride = t.key_seg_stride; o.L.grad_seg_stride = t.grad_seg_stride;
+        o.head = t.head; o.next = t.next;
+        int64_t want = (o.n_rows + 31) / 32;                       // 32 rows per 256-thread CTA per trip
+        int64_t share = total_rows > 0 ? (budget * o.n_rows + total_rows - 1) / total_rows : 0;
+        if (want > share) want = share;
+        if (want < 1 && o.n_rows > 0) want = 1;
+        o.block_lo = blocks; o.block_n = (int32_t)want; blocks += (int32_t)want;
+        o.link_lo = link_blocks; o.link_n = (int32_t)((n_rec + 255) / 256); link_blocks += o.link_n;
+    }
+    for (int i = 0; i < n_dense; ++i) {
+        const dccf_adam_tensor& d = dense[i];
+        DCCF_CHECK_ARG(d.p && d.m && d.v, "dccf_adam_step: dense tensor %d has a null buffer", i);
+        DCCF_CHECK_ARG(d.n_parts == 0 || d.g_parts, "dccf_adam_step: dense tensor %d has a null gradient", i);
+        AdamDenseArgs& o = a.d[i];
+        o.p = d.p; o.m = d.m; o.v = d.v; o.n = d.n > 0 ? d.n : 0; o.g_parts = d.g_parts; o.n_parts = d.n_parts;
+        o.part_stride = d.part_stride;
+        int64_t want = (o.n + 255) / 256;
+        if (want > 148) want = 148;
+        o.block_lo = blocks; o.block_n = (int32_t)want; blocks += (int32_t)want;
+    }
+    if (link_blocks > 0) {
+        k_link_all<<<(unsigned)link_blocks, 256, 0, stream>>>(a);
+        DCCF_CHECK_LAUNCH("k_link_all");
+    }
+    if (blocks > 0) {
+        k_adam_all<<<(unsigned)blocks, 256, 0, stream>>>(a);
+        DCCF_CHECK_LAUNCH("k_adam_all");
+    }
     return DCCF_OK;
 }

@@ -70,19 +70,6 @@ __device__ __forceinline__ float dpred_of(const BwdParams& prm, int64_t p) {
     return 2.f * (__ldg(prm.pred + p) - __ldg(prm.Y + p)) / (float)prm.n_pairs;
 }
 
-// gate value for 4 columns of row r given the saved activations
-__device__ __forceinline__ float4 gate4(const BwdParams& prm, int64_t r, int col, const float4& h) {
-    float4 g;
-    if (prm.mask_mode == 1) {
-        const float4 m = ldg4(prm.mask + (size_t)r * D + col);
-        g = make_float4(h.x > 0.f ? m.x : 0.f, h.y > 0.f ? m.y : 0.f, h.z > 0.f ? m.z : 0.f, h.w > 0.f ? m.w : 0.f);
-    } else {
-        const float s = (prm.mask_mode == 2) ? prm.drop_scale : 1.f;
-        g = make_float4(h.x > 0.f ? s : 0.f, h.y > 0.f ? s : 0.f, h.z > 0.f ? s : 0.f, h.w > 0.f ? s : 0.f);
-    }
-    return g;
-}
-
 // ---------------------------------------------------------------------------------------------
 // role 1: partial gW tile.  CTA (chunk c, split s): acc[j][col] = sum_{r in split} dpre[r][j] * x[r][c*64+col]
 // ---------------------------------------------------------------------------------------------
@@ -92,7 +79,7 @@ __device__ void bwd_gw_role(const BwdParams& prm, int chunk, int split) {
 
     const int tid = threadIdx.x;
     const int fr = tid >> 3;         // fill: row within chunk (0..15)
-    const int fc = (tid & 7) * 8;    // fill: first of 8 columns
+    const int fc = (tid & 7) * 4;    // fill: columns fc..fc+3 and 32+fc..32+fc+3 (conflict-free float4 stores)
     const int jg = (tid >> 4) * 8;   // compute: first of 8 j
     const int cg = (tid & 15) * 4;   // compute: first of 4 columns
     const RngKey key_noise = resolve_rng_key(prm.rng, DOMAIN_NOISE);
@@ -107,52 +94,88 @@ __device__ void bwd_gw_role(const BwdParams& prm, int chunk, int split) {
     const int64_t row_lo = (int64_t)split * prm.rows_per_split;
     const int64_t row_hi = min(row_lo + prm.rows_per_split, prm.n_rows);
     const int col0 = chunk * BWD_CW;  // column of W; < D means item-embedding part
+    const bool item_part = col0 < D;
+    const int f0 = col0 - D + fc;     // feature column of x0 (x1 is 32 further)
 
-    for (int64_t rb = row_lo; rb < row_hi; rb += BWD_RC) {
-        // ---- stage dpre and x for 16 rows ---------------------------------------------------
+    // raw operands of one staged row, loaded a chunk ahead of their use
+    struct Raw {
+        float4 h0, h1, e0, e1, m0, m1, x0, x1, n0, n1;
+        float ds;
+        bool live;
+    };
+    auto fetch = [&](int64_t rb, Raw& w) {
         const int64_t r = rb + fr;
+        w.live = r < row_hi;
+        if (!w.live) return;
+        const int64_t p = r / prm.R;
+        const int rem = (int)(r - p * prm.R);
+        const int z = rem / prm.A;
+        const int32_t u = checked_id(prm.X[2 * p], prm.n_users, nullptr);
+        const int32_t fi = checked_id(prm.X[2 * p + 1], prm.n_items, nullptr);
+        w.ds = dpred_of(prm, p) * __ldg(prm.save_w + p * prm.Z + z) * prm.inv_A;
+        w.h0 = ldg4(prm.save_h + (size_t)r * D + fc);
+        w.h1 = ldg4(prm.save_h + (size_t)r * D + 32 + fc);
+        w.e0 = ldg4(prm.E_user + (size_t)u * D + fc);
+        w.e1 = ldg4(prm.E_user + (size_t)u * D + 32 + fc);
+        if (prm.mask_mode == 1) {
+            w.m0 = ldg4(prm.mask + (size_t)r * D + fc);
+            w.m1 = ldg4(prm.mask + (size_t)r * D + 32 + fc);
+        }
+        if (item_part) {
+            const int32_t it = (z == 0) ? fi : checked_id(prm.sample_item[p * prm.S + (z - 1)], prm.n_items, nullptr);
+            w.x0 = ldg4(prm.E_item + (size_t)it * D + fc);
+            w.x1 = ldg4(prm.E_item + (size_t)it * D + 32 + fc);
+        } else {
+            w.x0 = ldg4(prm.Feat + (size_t)fi * prm.F + f0);
+            w.x1 = ldg4(prm.Feat + (size_t)fi * prm.F + f0 + 32);
+            if (prm.noise_mode == 1) {
+                w.n0 = ldg4(prm.noise + (size_t)r * prm.F + f0);
+                w.n1 = ldg4(prm.noise + (size_t)r * prm.F + f0 + 32);
+            }
+        }
+    };
+    auto gate = [&](const float4& h, const float4& m) {
+        if (prm.mask_mode == 1)
+            return make_float4(h.x > 0.f ? m.x : 0.f, h.y > 0.f ? m.y : 0.f, h.z > 0.f ? m.z : 0.f, h.w > 0.f ? m.w : 0.f);
+        const float s = (prm.mask_mode == 2) ? prm.drop_scale : 1.f;
+        return make_float4(h.x > 0.f ? s : 0.f, h.y > 0.f ? s : 0.f, h.z > 0.f ? s : 0.f, h.w > 0.f ? s : 0.f);
+    };
+    auto add4 = [](float4& a, const float4& b) {
+        a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+    };
+    auto store = [&](int64_t rb, const Raw& w) {
         float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0, x0 = d0, x1 = d0;
-        if (r < row_hi) {
-            const int64_t p = r / prm.R;
-            const int rem = (int)(r - p * prm.R);
-            const int z = rem / prm.A;
-            const int32_t u = checked_id(prm.X[2 * p], prm.n_users, nullptr);
-            const int32_t fi = checked_id(prm.X[2 * p + 1], prm.n_items, nullptr);
-            const float ds = dpred_of(prm, p) * __ldg(prm.save_w + p * prm.Z + z) * prm.inv_A;
-            const float4 h0 = ldg4(prm.save_h + (size_t)r * D + fc);
-            const float4 h1 = ldg4(prm.save_h + (size_t)r * D + fc + 4);
-            const float4 g0 = gate4(prm, r, fc, h0), g1 = gate4(prm, r, fc + 4, h1);
-            const float4 e0 = ldg4(prm.E_user + (size_t)u * D + fc);
-            const float4 e1 = ldg4(prm.E_user + (size_t)u * D + fc + 4);
-            d0 = make_float4(ds * e0.x * g0.x, ds * e0.y * g0.y, ds * e0.z * g0.z, ds * e0.w * g0.w);
-            d1 = make_float4(ds * e1.x * g1.x, ds * e1.y * g1.y, ds * e1.z * g1.z, ds * e1.w * g1.w);
-            if (col0 < D) {
-                const int32_t it = (z == 0) ? fi : checked_id(prm.sample_item[p * prm.S + (z - 1)], prm.n_items, nullptr);
-                x0 = ldg4(prm.E_item + (size_t)it * D + fc);
-                x1 = ldg4(prm.E_item + (size_t)it * D + fc + 4);
-            } else {
-                const int f0 = col0 - D + fc;
-                x0 = ldg4(prm.Feat + (size_t)fi * prm.F + f0);
-                x1 = ldg4(prm.Feat + (size_t)fi * prm.F + f0 + 4);
+        if (w.live) {
+            const float4 g0 = gate(w.h0, w.m0), g1 = gate(w.h1, w.m1);
+            d0 = make_float4(w.ds * w.e0.x * g0.x, w.ds * w.e0.y * g0.y, w.ds * w.e0.z * g0.z, w.ds * w.e0.w * g0.w);
+            d1 = make_float4(w.ds * w.e1.x * g1.x, w.ds * w.e1.y * g1.y, w.ds * w.e1.z * g1.z, w.ds * w.e1.w * g1.w);
+            x0 = w.x0;
+            x1 = w.x1;
+            if (!item_part) {
                 if (prm.noise_mode == 1) {
-                    const float4 n0 = ldg4(prm.noise + (size_t)r * prm.F + f0);
-                    const float4 n1 = ldg4(prm.noise + (size_t)r * prm.F + f0 + 4);
-                    x0.x = __fadd_rn(x0.x, n0.x); x0.y = __fadd_rn(x0.y, n0.y); x0.z = __fadd_rn(x0.z, n0.z); x0.w = __fadd_rn(x0.w, n0.w);
-                    x1.x = __fadd_rn(x1.x, n1.x); x1.y = __fadd_rn(x1.y, n1.y); x1.z = __fadd_rn(x1.z, n1.z); x1.w = __fadd_rn(x1.w, n1.w);
+                    add4(x0, w.n0);
+                    add4(x1, w.n1);
                 } else if (prm.noise_mode == 2) {
-                    const float4 n0 = noise_quad(key_noise, (uint32_t)r, (uint32_t)(f0 / 4), prm.noise_std);
-                    const float4 n1 = noise_quad(key_noise, (uint32_t)r, (uint32_t)(f0 / 4 + 1), prm.noise_std);
-                    x0.x = __fadd_rn(x0.x, n0.x); x0.y = __fadd_rn(x0.y, n0.y); x0.z = __fadd_rn(x0.z, n0.z); x0.w = __fadd_rn(x0.w, n0.w);
-                    x1.x = __fadd_rn(x1.x, n1.x); x1.y = __fadd_rn(x1.y, n1.y); x1.z = __fadd_rn(x1.z, n1.z); x1.w = __fadd_rn(x1.w, n1.w);
+                    const uint32_t r32 = (uint32_t)(rb + fr);
+                    add4(x0, noise_quad(key_noise, r32, (uint32_t)(f0 / 4), prm.noise_std));
+                    add4(x1, noise_quad(key_noise, r32, (uint32_t)(f0 / 4 + 8), prm.noise_std));
                 }
             }
         }
-        __syncthreads();  // previous chunk fully consumed
         st4(&dp_s[fr][fc], d0);
-        st4(&dp_s[fr][fc + 4], d1);
+        st4(&dp_s[fr][32 + fc], d1);
         st4(&x_s[fr][fc], x0);
-        st4(&x_s[fr][fc + 4], x1);
+        st4(&x_s[fr][32 + fc], x1);
+    };
+
+    Raw cur;
+    cur.live = false;
+    if (row_lo < row_hi) fetch(row_lo, cur);
+    for (int64_t rb = row_lo; rb < row_hi; rb += BWD_RC) {
+        __syncthreads();  // previous chunk fully consumed
+        store(rb, cur);
         __syncthreads();
+        if (rb + BWD_RC < row_hi) fetch(rb + BWD_RC, cur);   // in flight during the FMAs below
 
         // ---- rank-16 update of the 64x64 tile -----------------------------------------------
 #pragma unroll

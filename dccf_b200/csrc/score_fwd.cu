@@ -197,6 +197,164 @@ __global__ void __launch_bounds__(FWD_NT) k_row_scores(const FwdParams prm) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Small-batch variant (training step: 256 pairs = 5 632 rows would give the 128-row kernel only 44 CTAs
+// for 148 SMs).  A CTA owns 32 rows; its 4 warps split K four ways and each runs a private
+// register-tiled pipeline (8x8 outputs per lane, warp-private staging buffers, __syncwarp only);
+// the four partial 32x64 tiles are summed through shared memory before the fused epilogue.
+// ----------------------------------------------------------------------------------------------
+constexpr int SK_BM = 32;     // rows per CTA
+constexpr int SK_WARPS = 4;   // K splits
+constexpr int SK_NT = SK_WARPS * 32;
+
+template <int NOISE_MODE>
+__global__ void __launch_bounds__(SK_NT) k_row_scores_splitk(const FwdParams prm) {
+    // staging: per warp As[16][32] + Ws[16][64] = 1536 floats; reduction: 4 x 32 x 64 floats (aliased)
+    __shared__ __align__(16) float smem[SK_WARPS * SK_BM * D];
+    __shared__ int32_t u_row_s[SK_BM];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = lane & 7, ty = lane >> 3;
+    const int64_t row_base = (int64_t)blockIdx.x * SK_BM;
+    const RngKey key_noise = resolve_rng_key(prm.rng, DOMAIN_NOISE);
+    const RngKey key_drop = resolve_rng_key(prm.rng, DOMAIN_DROPOUT);
+    float* As = smem + warp * (FWD_KC * SK_BM + FWD_KC * D);   // [16][32]
+    float* Ws = As + FWD_KC * SK_BM;                           // [16][64]
+
+    // lane l stages row l of the tile
+    const int64_t my_row = min(row_base + lane, prm.n_rows - 1);
+    const float* item_ptr;
+    const float* feat_ptr;
+    {
+        const int64_t p = my_row / prm.R;
+        const int rem = (int)(my_row - p * prm.R);
+        const int z = rem / prm.A;
+        const int32_t u = checked_id(prm.X[2 * p], prm.n_users, prm.err_flag);
+        const int32_t fi = checked_id(prm.X[2 * p + 1], prm.n_items, prm.err_flag);
+        const int32_t it = (z == 0) ? fi : checked_id(prm.sample_item[p * prm.S + (z - 1)], prm.n_items, prm.err_flag);
+        if (warp == 0) u_row_s[lane] = u;
+        item_ptr = prm.E_item + (size_t)it * D;
+        feat_ptr = prm.Feat + (size_t)fi * prm.F;
+    }
+    const float* noise_ptr = (NOISE_MODE == 1) ? prm.noise + (size_t)my_row * prm.F : nullptr;
+    const uint32_t my_row32 = (uint32_t)my_row;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    const int n_chunks = (D + prm.F) / FWD_KC;
+    const int per_warp = n_chunks / SK_WARPS;          // (D+F)/16 is a multiple of 4 because F % 64 == 0
+    const int c_lo = warp * per_warp, c_hi = c_lo + per_warp;
+
+    float4 a_reg[4], n_reg[4], w_reg[8];
+    auto prefetch = [&](int c) {
+        const int k0 = c * FWD_KC;
+        const float* src = (k0 < D) ? item_ptr + k0 : feat_ptr + (k0 - D);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a_reg[q] = ldg4(src + 4 * q);
+        if (NOISE_MODE == 1 && k0 >= D) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) n_reg[q] = ldg4(noise_ptr + (k0 - D) + 4 * q);
+        }
+        const float* wsrc = prm.Wt + (size_t)k0 * D;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) w_reg[q] = ldg4(wsrc + (q * 32 + lane) * 4);
+    };
+    auto stage = [&](int c) {
+        const int k0 = c * FWD_KC;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 v = a_reg[q];
+            if (NOISE_MODE != 0 && k0 >= D) {
+                float4 e;
+                if (NOISE_MODE == 1) e = n_reg[q];
+                else e = noise_quad(key_noise, my_row32, (uint32_t)((k0 - D) / 4 + q), prm.noise_std);
+                v.x = __fadd_rn(v.x, e.x);
+                v.y = __fadd_rn(v.y, e.y);
+                v.z = __fadd_rn(v.z, e.z);
+                v.w = __fadd_rn(v.w, e.w);
+            }
+            As[(4 * q + 0) * SK_BM + lane] = v.x;
+            As[(4 * q + 1) * SK_BM + lane] = v.y;
+            As[(4 * q + 2) * SK_BM + lane] = v.z;
+            As[(4 * q + 3) * SK_BM + lane] = v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) st4(Ws + (q * 32 + lane) * 4, w_reg[q]);
+    };
+
+    prefetch(c_lo);
+    stage(c_lo);
+    __syncwarp();
+    for (int c = c_lo; c < c_hi; ++c) {
+        if (c + 1 < c_hi) prefetch(c + 1);
+#pragma unroll
+        for (int k = 0; k < FWD_KC; ++k) {
+            const float4 a0 = ld4(As + k * SK_BM + ty * 4);
+            const float4 a1 = ld4(As + k * SK_BM + 16 + ty * 4);
+            const float4 b0 = ld4(Ws + k * D + tx * 4);
+            const float4 b1 = ld4(Ws + k * D + 32 + tx * 4);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncwarp();
+        if (c + 1 < c_hi) stage(c + 1);
+        __syncwarp();
+    }
+
+    // ---- cross-warp reduction of the 4 partial tiles (staging buffers are dead now) ---------------
+    __syncthreads();
+    float* part = smem + warp * (SK_BM * D);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = (i < 4) ? (ty * 4 + i) : (16 + ty * 4 + (i - 4));
+        st4(part + m * D + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+        st4(part + m * D + 32 + tx * 4, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+    }
+    __syncthreads();
+
+    // ---- epilogue: warp w finishes rows w*8 .. w*8+7; lane owns columns 2*lane, 2*lane+1 -------------
+    const int c2 = lane * 2;
+    const float2 bia = __ldg(reinterpret_cast<const float2*>(prm.bias + c2));
+#pragma unroll 2
+    for (int rr = 0; rr < SK_BM / SK_WARPS; ++rr) {
+        const int m = warp * (SK_BM / SK_WARPS) + rr;
+        const int64_t grow_raw = row_base + m;
+        const bool valid = grow_raw < prm.n_rows;
+        const int64_t grow = valid ? grow_raw : prm.n_rows - 1;
+        float2 pre = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < SK_WARPS; ++w) {
+            const float2 v = *reinterpret_cast<const float2*>(smem + w * (SK_BM * D) + m * D + c2);
+            pre.x += v.x;
+            pre.y += v.y;
+        }
+        float hx = fmaxf(pre.x + bia.x, 0.f), hy = fmaxf(pre.y + bia.y, 0.f);
+        if (prm.mask_mode == 1) {
+            const float2 mk = __ldg(reinterpret_cast<const float2*>(prm.mask + (size_t)grow * D + c2));
+            hx *= mk.x;
+            hy *= mk.y;
+        } else if (prm.mask_mode == 2) {
+            const float4 mk = dropout_quad(key_drop, (uint32_t)grow, (uint32_t)(lane >> 1), prm.keep_prob, prm.drop_scale);
+            hx *= (lane & 1) ? mk.z : mk.x;
+            hy *= (lane & 1) ? mk.w : mk.y;
+        }
+        if (prm.save_h != nullptr && valid)
+            *reinterpret_cast<float2*>(prm.save_h + (size_t)grow * D + c2) = make_float2(hx, hy);
+        const float2 eu = __ldg(reinterpret_cast<const float2*>(prm.E_user + (size_t)u_row_s[m] * D + c2));
+        float part_dot = fmaf(hy, eu.y, hx * eu.x);
+        part_dot = warp_sum(part_dot);
+        if (lane == 0 && valid) prm.ws_rows[grow] = part_dot;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // exposure value of (user u, item it):  expo_prob[u, it]  or the IPSBiasedMF formula
 // (src/models/DCCF.py:98 lookup; src/models/IPSBiasedMF.py:42-53 on the fly)
 // ----------------------------------------------------------------------------------------------
@@ -302,13 +460,25 @@ extern "C" int dccf_score_fwd(const dccf_dims* dims, const float* E_user, const 
     prm.drop_scale = (rng->p_drop < 1.0f) ? 1.0f / (1.0f - rng->p_drop) : 0.0f;
     prm.rng.seed = rng->seed; prm.rng.offset = rng->offset; prm.rng.offset_dev = rng->offset_dev;
 
-    const unsigned grid = (unsigned)((n_rows + FWD_BM - 1) / FWD_BM);
-    switch (rng->noise_mode) {
-        case 0: k_row_scores<0><<<grid, FWD_NT, 0, stream>>>(prm); break;
-        case 1: k_row_scores<1><<<grid, FWD_NT, 0, stream>>>(prm); break;
-        default: k_row_scores<2><<<grid, FWD_NT, 0, stream>>>(prm); break;
+    // few rows (a training step): 32-row CTAs with K split over the warps fill the 148 SMs;
+    // many rows (an evaluation batch): 128-row CTAs reuse each staged W chunk four times more
+    const unsigned grid_big = (unsigned)((n_rows + FWD_BM - 1) / FWD_BM);
+    if (grid_big < 2 * 148) {
+        const unsigned grid = (unsigned)((n_rows + SK_BM - 1) / SK_BM);
+        switch (rng->noise_mode) {
+            case 0: k_row_scores_splitk<0><<<grid, SK_NT, 0, stream>>>(prm); break;
+            case 1: k_row_scores_splitk<1><<<grid, SK_NT, 0, stream>>>(prm); break;
+            default: k_row_scores_splitk<2><<<grid, SK_NT, 0, stream>>>(prm); break;
+        }
+        DCCF_CHECK_LAUNCH("k_row_scores_splitk");
+    } else {
+        switch (rng->noise_mode) {
+            case 0: k_row_scores<0><<<grid_big, FWD_NT, 0, stream>>>(prm); break;
+            case 1: k_row_scores<1><<<grid_big, FWD_NT, 0, stream>>>(prm); break;
+            default: k_row_scores<2><<<grid_big, FWD_NT, 0, stream>>>(prm); break;
+        }
+        DCCF_CHECK_LAUNCH("k_row_scores");
     }
-    DCCF_CHECK_LAUNCH("k_row_scores");
 
     const int warps_per_cta = 8;
     k_backdoor<<<(unsigned)((n_pairs + warps_per_cta - 1) / warps_per_cta), warps_per_cta * 32, 0, stream>>>(

@@ -6,7 +6,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import Adam, Dims, Expo, Rng, check, ptr, stream_ptr
+from ._lib import Adam, AdamTable, AdamTensor, Dims, Expo, Rng, check, ptr, stream_ptr
 
 D = _lib.DIM
 
@@ -135,6 +135,37 @@ def adam_dense(p, m, v, g_parts, n_parts, part_stride, hp):
     check(lib.dccf_adam_dense(ptr(p), ptr(m), ptr(v), p.numel(), ptr(g_parts), int(n_parts), int(part_stride),
                               ctypes.byref(hp), stream_ptr()), 'dccf_adam_dense')
     LAUNCHES[0] += 1
+
+
+def adam_table(table, m, v, rec_keys, rec_grads, n_seg, seg_len, key_seg_stride, grad_seg_stride, head, nxt):
+    t = AdamTable()
+    t.table, t.m, t.v = ptr(table).value, ptr(m).value, ptr(v).value
+    t.n_rows = table.shape[0]
+    t.rec_keys = ptr(rec_keys).value if rec_keys is not None else None
+    t.rec_grads = ptr(rec_grads).value if rec_grads is not None else None
+    t.n_seg, t.seg_len = int(n_seg), int(seg_len)
+    t.key_seg_stride, t.grad_seg_stride = int(key_seg_stride), int(grad_seg_stride)
+    t.head = ptr(head).value
+    t.next = ptr(nxt).value if nxt is not None else None
+    return t
+
+
+def adam_tensor(p, m, v, g_parts, n_parts, part_stride):
+    t = AdamTensor()
+    t.p, t.m, t.v = ptr(p).value, ptr(m).value, ptr(v).value
+    t.n = p.numel()
+    t.g_parts = ptr(g_parts).value if g_parts is not None else None
+    t.n_parts, t.part_stride = int(n_parts), int(part_stride)
+    return t
+
+
+def adam_step(tables, dense, hp):
+    """l2 + clip + Adam over every tensor of the model in two launches (dccf_adam_step)."""
+    lib = _lib.load()
+    ta = (AdamTable * max(1, len(tables)))(*tables)
+    da = (AdamTensor * max(1, len(dense)))(*dense)
+    check(lib.dccf_adam_step(ta, len(tables), da, len(dense), ctypes.byref(hp), stream_ptr()), 'dccf_adam_step')
+    LAUNCHES[0] += 2 if any(t.n_seg * t.seg_len > 0 for t in tables) else 1
 
 
 def state_advance(step_dev, offset_dev, offset_inc=1):

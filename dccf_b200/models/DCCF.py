@@ -321,13 +321,57 @@ class DCCF(DMF):
         self._check_ready()
         return FusedAdamState(self, lr=lr, l2=l2, weight_decay=l2 if weight_decay is None else weight_decay, **kw)
 
+    def _apply_adam(self, rec, P, opt, hp):
+        """l2 + clip + Adam over both tables, W and b (two launches); under data parallelism preceded by the
+        fold of the row-split partials and ONE all-gather of the packed gradient segment."""
+        Z = self.sample_num + 1
+        W, b = self.mlp[0].weight.data, self.mlp[0].bias.data
+        eu, ei = self.uid_embeddings.weight.data, self.iid_embeddings.weight.data
+        if 'exchange' in rec:
+            ex, v = rec['exchange'], rec['send']
+            kernels.sum_parts(rec['gW_part'], rec['n_splits'], W.numel(), W.numel(), v['gW'])
+            kernels.sum_parts(rec['gb_part'], rec['n_splits'], b.numel(), b.numel(), v['gb'])
+            recv = ex.exchange()
+            world, seg = ex.world, ex.seg
+            tables = [
+                kernels.adam_table(eu, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'], ex.part(recv, 'keys_u'),
+                                   ex.part(recv, 'gu'), world, P, seg, seg, opt.head_u,
+                                   self._buf('next_u', (world * P,), torch.int32)),
+                kernels.adam_table(ei, opt.exp_avg['E_item'], opt.exp_avg_sq['E_item'], ex.part(recv, 'keys_i'),
+                                   ex.part(recv, 'gi'), world, P * Z, seg, seg, opt.head_i,
+                                   self._buf('next_i', (world * P * Z,), torch.int32))]
+            dense = [kernels.adam_tensor(W, opt.exp_avg['W'], opt.exp_avg_sq['W'], ex.part(recv, 'gW'), world, seg),
+                     kernels.adam_tensor(b, opt.exp_avg['b'], opt.exp_avg_sq['b'], ex.part(recv, 'gb'), world, seg)]
+            kernels.adam_step(tables, dense, hp)
+            return ex.total_loss()
+        tables = [
+            kernels.adam_table(eu, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'], rec['keys_u'], rec['gu_rec'], 1, P,
+                               P, P * self.ui_vector_size, opt.head_u, self._buf('next_u', (P,), torch.int32)),
+            kernels.adam_table(ei, opt.exp_avg['E_item'], opt.exp_avg_sq['E_item'], rec['keys_i'], rec['gi_rec'], 1,
+                               P * Z, P * Z, P * Z * self.ui_vector_size, opt.head_i,
+                               self._buf('next_i', (P * Z,), torch.int32))]
+        dense = [kernels.adam_tensor(W, opt.exp_avg['W'], opt.exp_avg_sq['W'], rec['gW_part'], rec['n_splits'],
+                                     W.numel()),
+                 kernels.adam_tensor(b, opt.exp_avg['b'], opt.exp_avg_sq['b'], rec['gb_part'], rec['n_splits'],
+                                     b.numel())]
+        kernels.adam_step(tables, dense, hp)
+        return rec['loss'][0]
+
     def train_step(self, feed_dict, opt=None, stage_events=None):
         """One iteration of BaseRunner.fit (src/runners/BaseRunner.py:175-188): forward, loss, l2 term,
-        backward, clip, Adam — four kernel launches plus the transposition of W, no autograd, no host sync.
-        Returns the reference's out_dict (prediction, check, loss) with detached tensors."""
+        backward, clip, Adam — no autograd, no host sync.  Steps whose random inputs come from the library's
+        own streams are captured once into a CUDA graph per batch shape and replayed (one graph launch instead
+        of six kernel launches; the step counter and the rng call counter then live in device memory).
+        Returns the reference's out_dict (prediction, check, loss); under graph replay the tensors are the
+        graph's static outputs, valid until the next train_step."""
         opt = opt or self.optimizer
         if not isinstance(opt, FusedAdamState):
             raise RuntimeError('train_step needs the fused optimizer state (model.make_fused_optimizer)')
+        if stage_events is None and self.use_cuda_graph and 'noise' not in feed_dict and \
+                'dropout_mask' not in feed_dict:
+            out = self._train_step_graph(feed_dict, opt)
+            if out is not None:
+                return out
         call = self._make_call(feed_dict)
         if stage_events is not None:
             stage_events[0].record()
@@ -335,46 +379,77 @@ class DCCF(DMF):
         if stage_events is not None:
             stage_events[1].record()
         loss_mode = 0 if feed_dict['rank'] == 1 else 1
-        Y = feed_dict.get('Y')
-        if loss_mode == 1:
-            Y = Y.to(pred.device, torch.float32).contiguous()
-        else:
-            Y = None
+        Y = feed_dict['Y'].to(pred.device, torch.float32).contiguous() if loss_mode == 1 else None
         rec = self._launch_bwd(call, loss_mode=loss_mode, Y=Y)
         if stage_events is not None:
             stage_events[2].record()
         opt.step_count += 1
-        hp = opt.hp()
-        P, Z = call['P'], self.sample_num + 1
-        W, b = self.mlp[0].weight.data, self.mlp[0].bias.data
-        if 'exchange' in rec:
-            # fold the row-split partials, then ONE all-gather of the packed segment (records, dW, db, keys, loss)
-            ex, v = rec['exchange'], rec['send']
-            kernels.sum_parts(rec['gW_part'], rec['n_splits'], W.numel(), W.numel(), v['gW'])
-            kernels.sum_parts(rec['gb_part'], rec['n_splits'], b.numel(), b.numel(), v['gb'])
-            recv = ex.exchange()
-            world, seg = ex.world, ex.seg
-            nxt = self._buf('next', (world * P * Z,), torch.int32)
-            kernels.adam_sweep_seg(self.uid_embeddings.weight.data, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'],
-                                   ex.part(recv, 'keys_u'), ex.part(recv, 'gu'), world, P, seg, seg, opt.head_u, nxt,
-                                   hp)
-            kernels.adam_sweep_seg(self.iid_embeddings.weight.data, opt.exp_avg['E_item'], opt.exp_avg_sq['E_item'],
-                                   ex.part(recv, 'keys_i'), ex.part(recv, 'gi'), world, P * Z, seg, seg, opt.head_i,
-                                   nxt, hp)
-            kernels.adam_dense(W, opt.exp_avg['W'], opt.exp_avg_sq['W'], ex.part(recv, 'gW'), world, seg, hp)
-            kernels.adam_dense(b, opt.exp_avg['b'], opt.exp_avg_sq['b'], ex.part(recv, 'gb'), world, seg, hp)
-            if stage_events is not None:
-                stage_events[3].record()
-            loss = ex.total_loss()
-            return {'prediction': pred, 'check': [('prediction', pred)], 'loss': loss}
-        nxt = self._buf('next', (P * Z,), torch.int32)
-        kernels.adam_sweep(self.uid_embeddings.weight.data, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'],
-                           rec['keys_u'], rec['gu_rec'], P, opt.head_u, nxt, hp)
-        kernels.adam_sweep(self.iid_embeddings.weight.data, opt.exp_avg['E_item'], opt.exp_avg_sq['E_item'],
-                           rec['keys_i'], rec['gi_rec'], P * Z, opt.head_i, nxt, hp)
-        kernels.adam_dense(W, opt.exp_avg['W'], opt.exp_avg_sq['W'], rec['gW_part'], rec['n_splits'], W.numel(), hp)
-        kernels.adam_dense(b, opt.exp_avg['b'], opt.exp_avg_sq['b'], rec['gb_part'], rec['n_splits'], b.numel(), hp)
+        loss = self._apply_adam(rec, call['P'], opt, opt.hp())
         if stage_events is not None:
             stage_events[3].record()
-        loss = rec['loss'][0].clone()
-        return {'prediction': pred, 'check': [('prediction', pred)], 'loss': loss}
+        return {'prediction': pred, 'check': [('prediction', pred)], 'loss': loss.clone()}
+
+    # ---- CUDA-graph replay of the fused step -----------------------------------------------------
+    use_cuda_graph = True
+
+    def _train_step_graph(self, feed_dict, opt):
+        self._check_ready()
+        dev = self.uid_embeddings.weight.device
+        X = feed_dict['X']
+        P = X.shape[0]
+        rank_mode = int(feed_dict['rank'])
+        p_drop = float(feed_dict.get('dropout', 0.0))
+        key = (P, rank_mode, p_drop, id(opt))
+        graphs = self.__dict__.setdefault('_graphs', {})
+        g = graphs.get(key)
+        if g is None:
+            # first step of this shape runs eagerly (it also loads every kernel); capture on the second
+            graphs[key] = 'warm'
+            return None
+        S = self.sample_num
+        if g == 'warm':
+            g = {'X': torch.zeros((P, 2), dtype=torch.int64, device=dev),
+                 'si': torch.zeros((P, S), dtype=torch.int64, device=dev),
+                 'Y': torch.zeros(P, dtype=torch.float32, device=dev),
+                 'step_dev': torch.zeros(1, dtype=torch.int32, device=dev),
+                 'offset_dev': torch.zeros(1, dtype=torch.int64, device=dev), 'synced': None}
+            seed = self.random_seed
+            if self._dp is not None:
+                seed = (seed + 0x9E3779B97F4A7C15 * self._dp['rank']) & 0xffffffffffffffff
+            rng = kernels.make_rng(noise_std=self.std, p_drop=p_drop, seed=seed, offset_dev=g['offset_dev'],
+                                   generate_noise=self.std > 0, generate_mask=p_drop > 0)
+            call = {'X': g['X'], 'sample_item': g['si'], 'rng': rng, 'noise': None, 'mask': None, 'P': P,
+                    'N': P * (S + 1) * self.attribute_num}
+            hp = kernels.make_adam(opt.lr, opt.l2, opt.weight_decay, step=1, step_dev=g['step_dev'], beta1=opt.beta1,
+                                   beta2=opt.beta2, eps=opt.eps, clip=opt.clip)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            launches_before = kernels.LAUNCHES[0]
+            with torch.cuda.graph(graph):
+                pred = self._launch_fwd(call, save=True)
+                rec = self._launch_bwd(call, loss_mode=0 if rank_mode == 1 else 1, Y=g['Y'] if rank_mode != 1 else None)
+                loss = self._apply_adam(rec, P, opt, hp).clone()
+                kernels.state_advance(g['step_dev'], g['offset_dev'], 1)
+            g.update({'graph': graph, 'pred': pred, 'loss': loss, 'call': call,
+                      'n_kernels': kernels.LAUNCHES[0] - launches_before})
+            kernels.LAUNCHES[0] = launches_before           # capturing launched nothing
+            graphs[key] = g
+        # inputs into the graph's static buffers (async copies on the current stream)
+        Xs = X if torch.is_tensor(X) else torch.as_tensor(np.asarray(X))
+        g['X'].copy_(Xs[:, :2] if Xs.shape[1] != 2 else Xs, non_blocking=True)
+        si = feed_dict.get('sample_item')
+        if si is None:
+            si = torch.randint(self.item_num, size=(P, S))          # DCCF.py:72, CPU generator
+        g['si'].copy_(si, non_blocking=True)
+        if rank_mode != 1:
+            g['Y'].copy_(feed_dict['Y'], non_blocking=True)
+        self._rng_offset += 1
+        opt.step_count += 1
+        if g['synced'] != (opt.step_count, self._rng_offset):
+            # device counters out of step with the host mirrors (eager steps ran in between)
+            g['step_dev'].fill_(opt.step_count)
+            g['offset_dev'].fill_(self._rng_offset)
+        g['graph'].replay()
+        kernels.LAUNCHES[0] += g['n_kernels']
+        g['synced'] = (opt.step_count + 1, self._rng_offset + 1)
+        return {'prediction': g['pred'], 'check': [('prediction', g['pred'])], 'loss': g['loss']}

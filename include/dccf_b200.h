@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 5
+#define DCCF_ABI_VERSION 6
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -169,6 +169,26 @@ int dccf_sum_parts(const float* parts, int32_t n_parts, int64_t part_stride, int
 /* Dense variant for mlp.0.weight / mlp.0.bias: g = sum over n_parts partial buffers of n floats. */
 int dccf_adam_dense(float* p, float* m, float* v, int64_t n, const float* g_parts,
                     int32_t n_parts, int64_t part_stride, const dccf_adam* hp, void* stream);
+/* The whole optimizer step in two launches (record linking + one sweep over every tensor): up to 4
+ * embedding tables with segmented records and up to 4 dense tensors with partial-sum gradients.  Same
+ * arithmetic and summation order as the per-tensor entry points above. */
+typedef struct dccf_adam_table {
+    float* table; float* m; float* v;
+    int64_t n_rows;
+    const int32_t* rec_keys; const float* rec_grads;
+    int32_t n_seg; int32_t _pad;
+    int64_t seg_len, key_seg_stride, grad_seg_stride;
+    int32_t* head; int32_t* next;      /* next: n_seg*seg_len entries, private to this table */
+} dccf_adam_table;
+typedef struct dccf_adam_tensor {
+    float* p; float* m; float* v;
+    int64_t n;
+    const float* g_parts;
+    int32_t n_parts; int32_t _pad;
+    int64_t part_stride;
+} dccf_adam_tensor;
+int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
+                   int32_t n_dense, const dccf_adam* hp, void* stream);
 /* step_dev[0] += 1 ; offset_dev[0] += offset_inc  (either pointer may be NULL) — the last node
  * of a captured training step, so that a replay sees t+1 and a fresh rng counter. */
 int dccf_state_advance(int32_t* step_dev, uint64_t* offset_dev, uint64_t offset_inc, void* stream);

@@ -423,3 +423,31 @@ def test_confounders_come_from_the_torch_cpu_stream():
     assert np.array_equal(a, b)
     want = O.MT19937(123).torch_randint(40, 32).reshape(8, 4)
     assert np.array_equal(draw.numpy(), want)
+
+
+def test_graph_replay_equals_eager_steps():
+    """The CUDA-graph replay of the fused step (device-resident step / rng counters) is bit-identical to
+    launching the kernels one by one, over several steps and with an evaluation call in between."""
+    U, I, F, P, S, A, std, drop = 200, 300, 768, 64, 10, 2, 0.1, 0.2
+    params, X, si, _, _ = random_problem(8, U, I, F, P, S, A, 0.0, 0.0)
+    rs = np.random.RandomState(3)
+    outs = []
+    for use_graph in (False, True):
+        model = make_model(params, S, A, std)
+        model.use_cuda_graph = use_graph
+        model.optimizer = model.make_fused_optimizer(lr=1e-3, l2=1e-4)
+        losses = []
+        for t in range(6):
+            Xt = np.roll(X, t, axis=0).copy()
+            Xt[P // 2:, 0] = Xt[:P // 2, 0]
+            fd = {'X': torch.from_numpy(Xt).cuda(), 'rank': 1, 'train': True, 'dropout': drop,
+                  'Y': torch.zeros(P).cuda(), 'sample_item': torch.from_numpy(np.roll(si, t, axis=0).copy())}
+            losses.append(float(model.train_step(fd)['loss']))
+            if t == 3:       # an evaluation pass advances the rng call counter between training steps
+                model.predict({'X': torch.from_numpy(X).cuda(), 'rank': 1, 'train': False, 'dropout': 0.0,
+                               'sample_item': torch.from_numpy(si)})
+        outs.append((losses, model_params(model), model.optimizer.step_count))
+    assert outs[0][0] == outs[1][0]
+    assert outs[0][2] == outs[1][2] == 6
+    for k in ('E_user', 'E_item', 'W', 'b'):
+        assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
