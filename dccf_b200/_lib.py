@@ -11,7 +11,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libdccf_b200.so')
-ABI_VERSION = 6
+ABI_VERSION = 8
 DIM = 64
 
 
@@ -68,6 +68,10 @@ _SIGNATURES = {
                                               ctypes.c_uint64, ctypes.c_int64, _P]),
     'dccf_score_fwd': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, _P, _P, _P, ctypes.POINTER(Expo), _P, _P,
                                       ctypes.c_int64, ctypes.POINTER(Rng), _P, _P, _P, _P, _P, _P, _P]),
+    'dccf_tc_operand_floats': (ctypes.c_int64, [ctypes.c_int32]),
+    'dccf_tc_prepare': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'dccf_score_fwd_tc': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, _P, _P, ctypes.POINTER(Expo), _P, _P,
+                                         ctypes.c_int64, ctypes.POINTER(Rng), _P, _P, _P, _P, _P]),
     'dccf_bwd_splits': (ctypes.c_int32, [ctypes.c_int64]),
     'dccf_bpr_bwd': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64,
                                     ctypes.POINTER(Rng), ctypes.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -81,6 +85,8 @@ _SIGNATURES = {
     'dccf_adam_step': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(AdamTensor),
                                       ctypes.c_int32, ctypes.POINTER(Adam), _P]),
     'dccf_state_advance': (ctypes.c_int, [_P, _P, ctypes.c_uint64, _P]),
+    'dccf_sample_negatives': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
+                                             ctypes.c_int64, _P, _P, _P, _P, _P]),
     'dccf_rank_eval': (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, _P, _P]),
 }
 

@@ -417,6 +417,19 @@ __global__ void __launch_bounds__(256) k_backdoor(const dccf_expo ex, const int6
     }
 }
 
+void launch_transpose_w(const float* W, float* Wt, int K, cudaStream_t stream) {
+    k_transpose_w<<<dim3((K + 31) / 32, D / 32), dim3(32, 8), 0, stream>>>(W, Wt, K);
+}
+
+void launch_backdoor(const dccf_expo* expo, const int64_t* X, const int64_t* sample_item, int64_t n_pairs,
+                     const dccf_dims* dims, const float* ws_rows, float* out_pred, float* save_w, int32_t* err_flag,
+                     cudaStream_t stream) {
+    const int warps_per_cta = 8;
+    k_backdoor<<<(unsigned)((n_pairs + warps_per_cta - 1) / warps_per_cta), warps_per_cta * 32, 0, stream>>>(
+        *expo, X, sample_item, n_pairs, dims->n_users, dims->n_items, dims->n_samples, dims->n_attr, ws_rows, out_pred,
+        save_w, err_flag);
+}
+
 }  // namespace dccf
 
 using namespace dccf;

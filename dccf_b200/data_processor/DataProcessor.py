@@ -47,6 +47,8 @@ class DataProcessor(object):
             for uid, items in data_loader.vt_user_his.items():
                 self.vt_history_dict[uid] = set(items)
         self.vt_batches_buffer = {}
+        self.use_native_sampler = True      # dccf_sample_negatives (C++, draw-for-draw identical); False = Python loop
+        self._csr = None
 
     # ---- data dicts --------------------------------------------------------------------------
     def get_train_data(self, epoch):
@@ -280,9 +282,60 @@ class DataProcessor(object):
         neg_df[self.data_loader.label] = 0
         return neg_df
 
+    def _history_csr(self):
+        """Per-user sorted item lists of the train and validation/test histories as CSR arrays."""
+        if self._csr is None:
+            n_users = int(self.data_loader.user_num)
+
+            def build(hist):
+                off = np.zeros(n_users + 1, dtype=np.int64)
+                for u, items in hist.items():
+                    if 0 <= u < n_users:
+                        off[u + 1] = len(items)
+                off = np.cumsum(off)
+                flat = np.zeros(max(int(off[-1]), 1), dtype=np.int64)
+                for u, items in hist.items():
+                    if 0 <= u < n_users and items:
+                        flat[off[u]:off[u + 1]] = sorted(items)
+                return off, flat
+
+            self._csr = (n_users,) + build(self.train_history_dict) + build(self.vt_history_dict)
+        return self._csr
+
+    def _sample_neg_native(self, uids, neg_n, train):
+        """dccf_sample_negatives: the same draws from numpy's global MT19937 state, in C++."""
+        import ctypes
+        from .. import _lib
+        lib = _lib.load()
+        n_users, t_off, t_items, v_off, v_items = self._history_csr()
+        uids = np.ascontiguousarray(uids, dtype=np.int64)
+        kind, key, pos, has_gauss, cached = np.random.get_state()
+        assert kind == 'MT19937'
+        key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+        pos_c = ctypes.c_int32(int(pos))
+        out = np.empty(len(uids) * neg_n, dtype=np.int64)
+
+        def p(a):
+            return a.ctypes.data_as(ctypes.c_void_p)
+
+        rc = lib.dccf_sample_negatives(p(key), ctypes.byref(pos_c), p(uids), len(uids), int(neg_n), int(bool(train)),
+                                       int(self.data_loader.item_num), n_users, p(t_off), p(t_items), p(v_off),
+                                       p(v_items), p(out))
+        np.random.set_state((kind, key, int(pos_c.value), has_gauss, cached))
+        if rc != 0:
+            raise AssertionError(lib.dccf_last_error().decode())
+        return out
+
     def _sample_neg_from_uid_list(self, uids, neg_n, train, other_infos=None):
         """The rejection sampler (DataProcessor.py:446-524), draw for draw."""
         other_infos = other_infos or {}
+        if self.use_native_sampler and len(uids) > 0:
+            uid_arr = np.asarray(uids, dtype=np.int64)
+            neg_df = pd.DataFrame({'uid': np.repeat(uid_arr, neg_n),
+                                   'iid_neg': self._sample_neg_native(uid_arr, neg_n, train)})
+            for info, values in other_infos.items():
+                neg_df[info] = np.repeat(np.asarray(values), neg_n)
+            return neg_df
         item_num = self.data_loader.item_num
         randint, choice = np.random.randint, np.random.choice
         train_hist, vt_hist = self.train_history_dict, self.vt_history_dict

@@ -92,6 +92,28 @@ def score_fwd(dims, E_user, E_item, Feat, W, b, expo, X, sample_item, rng, out_p
     return out_pred
 
 
+def tc_operand_floats(feat_dim):
+    return int(_lib.load().dccf_tc_operand_floats(int(feat_dim)))
+
+
+def tc_prepare(dims, E_item, Feat, W, b, ws_wt, PI, PF, gB):
+    """Project the item tables and split W_f for the tensor-core scorer (4 launches)."""
+    lib = _lib.load()
+    check(lib.dccf_tc_prepare(ctypes.byref(dims), ptr(E_item), ptr(Feat), ptr(W), ptr(b), ptr(ws_wt), ptr(PI), ptr(PF),
+                              ptr(gB), stream_ptr()), 'dccf_tc_prepare')
+    LAUNCHES[0] += 4
+
+
+def score_fwd_tc(dims, E_user, PI, PF, gB, expo, X, sample_item, rng, out_pred, ws_rows, dbg_pre=None, err_flag=None):
+    lib = _lib.load()
+    n_pairs = X.shape[0]
+    check(lib.dccf_score_fwd_tc(ctypes.byref(dims), ptr(E_user), ptr(PI), ptr(PF), ptr(gB), ctypes.byref(expo), ptr(X),
+                                ptr(sample_item), n_pairs, ctypes.byref(rng), ptr(out_pred), ptr(ws_rows), ptr(dbg_pre),
+                                ptr(err_flag), stream_ptr()), 'dccf_score_fwd_tc')
+    LAUNCHES[0] += 2 if n_pairs > 0 else 0      # k_row_scores_tc, k_backdoor
+    return out_pred
+
+
 def bwd_splits(n_rows):
     return int(_lib.load().dccf_bwd_splits(int(n_rows)))
 

@@ -110,6 +110,8 @@ class DCCF(DMF):
         self._ws = {}
         self._err_flag = None
         self._dp = None
+        self._param_epoch = 0          # bumped whenever the fused kernels change the parameters in place
+        self._tc_cache = None
 
     # ---- construction ------------------------------------------------------------------------
     @staticmethod
@@ -215,7 +217,32 @@ class DCCF(DMF):
                                offset=self._rng_offset, generate_noise=(noise is None and self.std > 0),
                                generate_mask=(mask is None and p_drop > 0))
         return {'X': X, 'sample_item': sample_item, 'rng': rng, 'noise': noise, 'mask': mask, 'P': P,
-                'N': P * (S + 1) * A}
+                'N': P * (S + 1) * A, 'force_tc': feed_dict.get('force_tc'), 'dbg_pre': feed_dict.get('dbg_pre')}
+
+    # evaluation batches with feature noise go to the tcgen05 scorer (dccf_score_fwd_tc) when they are large
+    # enough to fill the machine; training steps and noise-free scoring use the FP32 SIMT kernels
+    use_tensor_cores = True
+    tc_min_rows = 128 * 148
+
+    def _tc_tables(self):
+        """PI = E_item·W_i^T, PF = Feat·W_f^T + b and the split W_f operand, rebuilt when a parameter changed."""
+        W, b, ei = self.mlp[0].weight, self.mlp[0].bias, self.iid_embeddings.weight
+        key = (self._param_epoch, W._version, b._version, ei._version, W.data_ptr(), ei.data_ptr(),
+               self.feature_embedding.data_ptr())
+        if self._tc_cache is not None and self._tc_cache['key'] == key:
+            return self._tc_cache
+        D, F = self.ui_vector_size, self.feature_embedding.shape[1]
+        dev = W.device
+        c = self._tc_cache or {}
+        if c.get('PI') is None or c['PI'].shape[0] != self.item_num:
+            c = {'PI': torch.empty((self.item_num, D), dtype=torch.float32, device=dev),
+                 'PF': torch.empty((self.item_num, D), dtype=torch.float32, device=dev),
+                 'gB': torch.empty(kernels.tc_operand_floats(F), dtype=torch.float32, device=dev)}
+        kernels.tc_prepare(self._dims(), ei.data, self.feature_embedding, W.data, b.data,
+                           self._buf('ws_wt', ((D + F) * D,), torch.float32), c['PI'], c['PF'], c['gB'])
+        c['key'] = key
+        self._tc_cache = c
+        return c
 
     def _launch_fwd(self, call, save):
         P, N = call['P'], call['N']
@@ -226,6 +253,14 @@ class DCCF(DMF):
         if P == 0:
             return pred
         ws_rows = self._buf('ws_rows', (N,), torch.float32)
+        if not save and self.use_tensor_cores and call['rng'].noise_mode != 0 and \
+                (N >= self.tc_min_rows or call.get('force_tc')):
+            t = self._tc_tables()
+            dbg = call.get('dbg_pre')
+            kernels.score_fwd_tc(self._dims(), self.uid_embeddings.weight.data, t['PI'], t['PF'], t['gB'], self._expo(),
+                                 call['X'], call['sample_item'], call['rng'], pred, ws_rows, dbg, self._err_flag)
+            call['pred'] = pred
+            return pred
         ws_wt = self._buf('ws_wt', (K * D,), torch.float32)
         save_h = save_w = None
         if save:
@@ -384,6 +419,7 @@ class DCCF(DMF):
         if stage_events is not None:
             stage_events[2].record()
         opt.step_count += 1
+        self._param_epoch += 1
         loss = self._apply_adam(rec, call['P'], opt, opt.hp())
         if stage_events is not None:
             stage_events[3].record()
@@ -445,6 +481,7 @@ class DCCF(DMF):
             g['Y'].copy_(feed_dict['Y'], non_blocking=True)
         self._rng_offset += 1
         opt.step_count += 1
+        self._param_epoch += 1
         if g['synced'] != (opt.step_count, self._rng_offset):
             # device counters out of step with the host mirrors (eager steps ran in between)
             g['step_dev'].fill_(opt.step_count)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 6
+#define DCCF_ABI_VERSION 8
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -107,6 +107,21 @@ int dccf_score_fwd(const dccf_dims* dims, const float* E_user, const float* E_it
                    const int64_t* X, const int64_t* sample_item, int64_t n_pairs,
                    const dccf_rng* rng, float* out_pred, float* ws_rows, float* ws_wt,
                    float* save_h, float* save_w, int32_t* err_flag, void* stream);
+
+/* ---- (a)+(b), tensor-core variant for evaluation batches ------------------------------------ */
+/* Same result as dccf_score_fwd (no save_h / save_w: inference only) with the W_f·eps product on the
+ * tcgen05 tensor cores as an error-compensated 3xTF32 product (FP32-level accuracy) and the noise-free terms
+ * taken from two projected tables.  dccf_tc_prepare must be called again whenever E_item, W or b change:
+ *   PI [I,D] = E_item·W_i^T     PF [I,D] = Feat·W_f^T + b     gB [dccf_tc_operand_floats(F)] = split W_f
+ *   dbg_pre [N,D] or NULL: the raw tensor-core accumulator W_f·eps (tests)
+ */
+int64_t dccf_tc_operand_floats(int32_t feat_dim);
+int dccf_tc_prepare(const dccf_dims* dims, const float* E_item, const float* Feat, const float* W,
+                    const float* b, float* ws_wt, float* PI, float* PF, float* gB, void* stream);
+int dccf_score_fwd_tc(const dccf_dims* dims, const float* E_user, const float* PI, const float* PF,
+                      const float* gB, const dccf_expo* expo, const int64_t* X, const int64_t* sample_item,
+                      int64_t n_pairs, const dccf_rng* rng, float* out_pred, float* ws_rows, float* dbg_pre,
+                      int32_t* err_flag, void* stream);
 
 /* ---- (c) part 1: pairwise loss forward + full backward ---------------------------------- */
 /* Replaces DCCF.forward lines 116-125 (src/models/DCCF.py) + autograd backward
@@ -207,6 +222,19 @@ int dccf_rank_eval(const float* scores, const float* labels, const int64_t* iids
                    const int32_t* cand_rows, const int64_t* user_off, int64_t n_users, int32_t k,
                    int64_t* out_topk_iid, int32_t* out_topk_row, double* out_metrics,
                    void* stream);
+
+/* ---- host side: exact replay of the reference's negative sampler ---------------------------- */
+/* Replaces the Python loop of src/data_processor/DataProcessor.py:446-524 draw for draw.  HOST pointers.
+ *   mt_key[624], mt_pos: numpy's legacy MT19937 state (np.random.get_state()[1:3]); advanced in place
+ *   uids [n]: users in sampling order; neg_n negatives each; train != 0: avoid the train history and the
+ *             negatives already drawn for that user in this call; train == 0: avoid train U validation/test
+ *             history, per-row draw memory only
+ *   *_off [n_users+1], *_items: CSR of sorted, de-duplicated per-user item lists
+ *   out_iid [n*neg_n] */
+int dccf_sample_negatives(uint32_t* mt_key, int32_t* mt_pos, const int64_t* uids, int64_t n, int32_t neg_n,
+                          int32_t train, int64_t item_num, int64_t n_users, const int64_t* train_off,
+                          const int64_t* train_items, const int64_t* vt_off, const int64_t* vt_items,
+                          int64_t* out_iid);
 
 #ifdef __cplusplus
 }

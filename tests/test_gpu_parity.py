@@ -451,3 +451,56 @@ def test_graph_replay_equals_eager_steps():
     assert outs[0][2] == outs[1][2] == 6
     for k in ('E_user', 'E_item', 'W', 'b'):
         assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05, 3xTF32) evaluation scorer
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('P,F', [(300, 768), (37, 128), (6, 64)])
+def test_tensor_core_scorer_vs_oracle(P, F):
+    """dccf_score_fwd_tc with the explicit noise tensor: the raw accumulator equals noise·W_f^T to 3xTF32
+    accuracy (~1e-6) and the prediction keeps the 1e-5 bound; ragged tiles included."""
+    U, I, S, A, std = 200, 300, 10, 2, 0.1
+    params, X, si, noise, _ = random_problem(31, U, I, F, P, S, A, std, 0.0)
+    model = make_model(params, S, A, std)
+    N = P * (S + 1) * A
+    dbg = torch.zeros((N, 64), device='cuda')
+    fd = {'X': torch.from_numpy(X).cuda(), 'rank': 1, 'train': False, 'dropout': 0.0,
+          'sample_item': torch.from_numpy(si), 'noise': torch.from_numpy(noise), 'force_tc': True, 'dbg_pre': dbg}
+    got = model.predict(fd)['prediction'].cpu().numpy()
+    want_pre = noise.astype(np.float64) @ params['W'][:, 64:].astype(np.float64).T
+    assert rel_err(dbg.cpu().numpy(), want_pre) < 3e-6
+    ref = O.predict(params, X, si, noise, None, A, dtype=np.float64)
+    assert rel_err(got, ref['pred']) < 1e-5
+    model.check_ids()
+
+
+def test_tensor_core_scorer_equals_simt_scorer_on_library_noise():
+    """Noise generated inside the kernels (mode 2): the tcgen05 path and the FP32 SIMT path see the same
+    Philox stream and agree within the parity bound; with dropout too; tables follow parameter updates."""
+    U, I, F, P, S, A, std = 500, 800, 768, 1024, 10, 2, 0.1
+    params, X, si, _, _ = random_problem(41, U, I, F, P, S, A, 0.0, 0.0)
+    model = make_model(params, S, A, std)
+    for drop in (0.0, 0.3):
+        fd = {'X': torch.from_numpy(X).cuda(), 'rank': 1, 'train': False, 'dropout': drop,
+              'sample_item': torch.from_numpy(si)}
+        model.use_tensor_cores = False
+        model._rng_offset = 10
+        a = model.predict(fd)['prediction'].cpu().numpy()
+        model.use_tensor_cores = True
+        model._rng_offset = 10
+        b = model.predict(dict(fd, force_tc=True))['prediction'].cpu().numpy()
+        assert rel_err(b, a) < 1e-5
+    # a training step changes W / E_item: the projected tables must be rebuilt
+    model.optimizer = model.make_fused_optimizer(lr=1e-2, l2=1e-4)
+    tr = {'X': torch.from_numpy(X[:64]).cuda(), 'rank': 1, 'train': True, 'dropout': 0.2, 'Y': torch.zeros(64).cuda(),
+          'sample_item': torch.from_numpy(si[:64])}
+    model.train_step(tr)
+    fd = {'X': torch.from_numpy(X).cuda(), 'rank': 1, 'train': False, 'dropout': 0.0, 'sample_item': torch.from_numpy(si)}
+    model.use_tensor_cores = False
+    model._rng_offset = 50
+    a = model.predict(fd)['prediction'].cpu().numpy()
+    model.use_tensor_cores = True
+    model._rng_offset = 50
+    b = model.predict(dict(fd, force_tc=True))['prediction'].cpu().numpy()
+    assert rel_err(b, a) < 1e-5

@@ -169,3 +169,41 @@ def test_runner_bookkeeping():
     assert batches[0]['dropout'] == 0.0 and not batches[0]['train']
     r.valid_results = [[0.5]] + [[0.1]] * 21
     assert r.eva_termination(None)            # best result more than 20 evaluations ago
+
+
+def test_native_sampler_equals_python_loop(golden, tmp_path):
+    """dccf_sample_negatives (C++) consumes numpy's MT19937 stream exactly like the Python loop that mirrors
+    src/data_processor/DataProcessor.py:446-524: same negatives, same generator state afterwards — on the
+    golden dataset (both sampler branches) and on a random one."""
+    g = golden('sampler')
+    d = _write_sampler_dataset(g, str(tmp_path))
+    dl = DataLoader(path=str(tmp_path), dataset='s', label='label', sep=',')
+    model = _make_model(d, 's', dl.user_num, dl.item_num)
+    dl.drop_neg()
+    results = []
+    for native in (False, True):
+        np.random.seed(77)
+        dp = DataProcessor(dl, model, rank=1, test_neg_n=int(g['test_neg_n']))
+        dp.use_native_sampler = native
+        te = dp.get_test_data()
+        xs = [te['X'].copy()]
+        for ep in range(3):
+            data = dp.get_train_data(epoch=ep)
+            batches = dp.prepare_batches(data, 16, train=True)
+            xs.append(np.concatenate([b['X'].cpu().numpy() for b in batches]))
+        results.append((xs, np.random.get_state()[1].copy(), np.random.get_state()[2]))
+    for a, b in zip(results[0][0], results[1][0]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(results[0][1], results[1][1]) and results[0][2] == results[1][2]
+
+
+def test_native_sampler_reports_exhausted_user(tmp_path):
+    """The reference asserts `remain_iids_num >= neg_n` (DataProcessor.py:495); so does the native sampler."""
+    from dccf_b200 import synth
+    d = synth.write_dataset(str(tmp_path), 'x', n_users=5, n_items=40, per_user=10, feat_dim=64, seed=3)
+    dl = DataLoader(path=str(tmp_path), dataset='x', label='label', sep=',')
+    model = _make_model(d, 'x', dl.user_num, dl.item_num)
+    dl.drop_neg()
+    dp = DataProcessor(dl, model, rank=1, test_neg_n=35)
+    with pytest.raises(AssertionError):
+        dp.get_test_data()
