@@ -427,8 +427,11 @@ class DCCF(DMF):
 
     # ---- CUDA-graph replay of the fused step -----------------------------------------------------
     use_cuda_graph = True
+    dp_cuda_graph = False      # capture the NCCL all-gather inside the step graph (off until validated on N GPUs)
 
     def _train_step_graph(self, feed_dict, opt):
+        if self._dp is not None and not self.dp_cuda_graph:
+            return None
         self._check_ready()
         dev = self.uid_embeddings.weight.device
         X = feed_dict['X']

@@ -15,6 +15,10 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from test_gpu_parity import make_model, model_params, random_problem  # noqa: E402
 
 
+def say(rank, msg):
+    print('[dp_check rank %d] %s' % (rank, msg), flush=True)
+
+
 def rel(a, b):
     return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / np.abs(b).max())
 
@@ -42,6 +46,7 @@ def main():
               'Y': torch.zeros(len(pairs)).cuda(), 'sample_item': torch.from_numpy(si[pairs]),
               'noise': torch.from_numpy(noise[rows]), 'dropout_mask': torch.from_numpy(mask[rows])}
         out = model.train_step(fd)
+    say(rank, 'dp steps done, loss %.6f' % float(out['loss']))
     got = model_params(model)
     # replicas bit-identical
     for k, v in got.items():
@@ -57,6 +62,7 @@ def main():
               'sample_item': torch.from_numpy(si), 'noise': torch.from_numpy(noise),
               'dropout_mask': torch.from_numpy(mask)}
         out1 = single.train_step(fd)
+    say(rank, 'single-GPU steps done')
     want = model_params(single)
     assert abs(float(out['loss']) - float(out1['loss'])) < 1e-5 * abs(float(out1['loss'])), (float(out['loss']), float(out1['loss']))
     for k in ('E_user', 'E_item', 'b'):
@@ -65,7 +71,9 @@ def main():
     for k in ('E_user', 'E_item', 'W', 'b'):
         assert rel(model.optimizer.exp_avg[k].cpu().numpy(), single.optimizer.exp_avg[k].cpu().numpy()) < 1e-5, k
 
-    # graph-replayed DP steps (library rng) keep the replicas identical too
+    say(rank, 'equality with the single-GPU step ok')
+    # DP steps on the library's own rng streams keep the replicas identical too
+    model.dp_cuda_graph = os.environ.get('DCCF_DP_GRAPH', '0') == '1'
     for t in range(4):
         fd = {'X': torch.from_numpy(X[pairs]).cuda(), 'rank': 1, 'train': True, 'dropout': drop,
               'Y': torch.zeros(len(pairs)).cuda(), 'sample_item': torch.from_numpy(si[pairs])}
@@ -76,6 +84,7 @@ def main():
         dist.broadcast(ref, 0)
         assert torch.equal(t, ref), 'rank %d diverged from rank 0 on %s after graph replay' % (rank, k)
 
+    say(rank, 'library-rng DP steps ok (graph=%s)' % model.dp_cuda_graph)
     # user-sharded evaluation == single-GPU evaluation (same scores -> same metrics)
     from dccf_b200.dist import all_reduce_sum, shard_users
     from dccf_b200.models.BaseModel import BaseModel
