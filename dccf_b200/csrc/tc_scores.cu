@@ -32,7 +32,8 @@ constexpr uint32_t TC_A_BYTES = TC_BM * TC_KC * 4;   // 16 KB (one of hi / lo)
 constexpr uint32_t TC_B_BYTES = D * TC_KC * 4;       //  8 KB (one of hi / lo)
 constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 48 KB
 constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 256;
-constexpr uint32_t TC_TMEM_COLS = 64;
+constexpr int TC_NACC = 4;                 // TMEM accumulators per tile (see the MMA issuer)
+constexpr uint32_t TC_TMEM_COLS = TC_NACC * D;   // 256 of the 512 columns: two CTAs per SM
 constexpr uint32_t TC_LBO = 128;           // K-adjacent core matrices are contiguous
 constexpr uint32_t TC_SBO = 1024;          // 8 core matrices (32 K values) per 8-row group
 
@@ -201,9 +202,15 @@ __global__ void __launch_bounds__(TC_NT, 2) k_row_scores_tc(const TcParams prm) 
                     const uint64_t da_lo = tc::make_smem_desc(a_lo + ko, TC_LBO, TC_SBO);
                     const uint64_t db_hi = tc::make_smem_desc(b_hi + ko, TC_LBO, TC_SBO);
                     const uint64_t db_lo = tc::make_smem_desc(b_lo + ko, TC_LBO, TC_SBO);
-                    tc::umma_tf32(tmem_base, da_lo, db_hi, idesc, (c | j) != 0);   // small terms first
+                    // The tensor core adds into the FP32 accumulator with truncation, a bias of ~2^-24 per
+                    // accumulation that 288 chained MMAs would grow to ~8e-6.  The two correction products
+                    // (2^-11 smaller) share accumulator 0; the main hi·hi product rotates over accumulators
+                    // 1..3 (32 accumulations each); the epilogue adds the four in round-to-nearest FP32.
+                    const int ks = c * (TC_KC / 8) + j;
+                    const uint32_t main_acc = tmem_base + (uint32_t)(1 + ks % (TC_NACC - 1)) * D;
+                    tc::umma_tf32(tmem_base, da_lo, db_hi, idesc, ks != 0);
                     tc::umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
-                    tc::umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
+                    tc::umma_tf32(main_acc, da_hi, db_hi, idesc, ks >= TC_NACC - 1);
                 }
                 tc::umma_commit(&empty_bar[s]);   // frees the stage when these MMAs have read it
             }
@@ -244,18 +251,28 @@ __global__ void __launch_bounds__(TC_NT, 2) k_row_scores_tc(const TcParams prm) 
         const float* eu = prm.E_user + (size_t)u * D;
         const RngKey key_drop = resolve_rng_key(prm.rng, DOMAIN_DROPOUT);
         float dot = 0.f;
+#pragma unroll 1
+        for (int quarter = 0; quarter < 4; ++quarter) {
+            float acc[16], part[16];
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(quarter * 16);
+            tc::tmem_ld_32x16(lane_addr + 1 * D, acc);
+            tc::tmem_ld_32x16(lane_addr + 2 * D, part);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float acc[32];
-            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(half * 32), acc);
+            for (int j = 0; j < 16; ++j) acc[j] += part[j];
+            tc::tmem_ld_32x16(lane_addr + 3 * D, part);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] += part[j];
+            tc::tmem_ld_32x16(lane_addr, part);          // the small correction terms last
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] += part[j];
             if (prm.dbg_pre != nullptr && valid) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    st4(prm.dbg_pre + (size_t)grow * D + half * 32 + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+                for (int j = 0; j < 16; j += 4)
+                    st4(prm.dbg_pre + (size_t)grow * D + quarter * 16 + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
             }
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const int col = half * 32 + j;
+            for (int j = 0; j < 16; j += 4) {
+                const int col = quarter * 16 + j;
                 const float4 a = ldg4(pi + col), f = ldg4(pf + col), e = ldg4(eu + col);
                 float h0 = fmaxf(acc[j] + (a.x + f.x), 0.f), h1 = fmaxf(acc[j + 1] + (a.y + f.y), 0.f);
                 float h2 = fmaxf(acc[j + 2] + (a.z + f.z), 0.f), h3 = fmaxf(acc[j + 3] + (a.w + f.w), 0.f);
