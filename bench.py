@@ -306,7 +306,7 @@ def bench_eval(model, n_users, warm_batches, world, rank, flush):
     for _ in range(3):
         model.predict({'X': X_d[:EVAL_BATCH], 'rank': 1, 'train': False, 'dropout': 0.0,
                             'sample_item': si_d[:EVAL_BATCH]})
-        rank_metrics_device(torch.zeros(rows, device=dev), Y_d, iid_d, cand_d, off_d, 5)
+        rank_metrics_device(torch.zeros(rows, device=dev), Y_d, iid_d, cand_d, off_d, 5).sum(dim=0)
     barrier(world)
     sums, evs = run(False, X_d, True)
     barrier(world)
