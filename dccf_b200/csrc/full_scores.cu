@@ -120,6 +120,9 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) fs_store_split(st, FS_B_IMG, item, khalf * 32 + q * 4, v[q]);
             if (khalf == 0) {
+                // the epilogue of the tile that used this stage two tiles ago still reads its column vectors
+                // until it hands the accumulator back
+                tc::mbar_wait(&acc_empty[s], ph ^ 1u);
                 float* col = reinterpret_cast<float*>(st + FS_B_BYTES);
                 col[item] = prm.col_bias ? __ldg(prm.col_bias + i) : 0.f;
                 col[FS_BN + item] = prm.col_scale ? __ldg(prm.col_scale + i) : 1.f;
@@ -170,6 +173,8 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
 #pragma unroll
         for (int j = 0; j < FS_KMAX; ++j) { best_s[j] = -INFINITY; best_i[j] = -1; }
         const int k = prm.k;
+        float thr_s = -INFINITY;      // score and id of the current k-th entry (kept in registers: the
+        int32_t thr_i = -1;           // arrays are only touched through fully unrolled loops)
         for (int t = t_lo; t < t_hi; ++t) {
             const int n = t - t_lo, s = n & 1;
             const uint32_t ph = (uint32_t)(n >> 1) & 1u;
@@ -183,12 +188,6 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
                 float acc[16], corr[16];
                 tc::tmem_ld_32x16(lane_addr + quarter * 16, acc);
                 tc::tmem_ld_32x16(lane_addr + FS_BN + quarter * 16, corr);
-                if (quarter == 3) {
-                    // all TMEM reads of this accumulator pair are done: hand it back to the MMA warp.
-                    // (the column vectors in the B stage are still needed below, but b_empty for this stage
-                    //  was committed by the MMAs already and the staging warps only overwrite it after
-                    //  acc_empty of the NEXT use... they are copied to registers first)
-                }
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -214,7 +213,7 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
                     for (int j = 0; j < 16; ++j) {
                         const int64_t i = i0 + quarter * 16 + j;
                         float sc = (v[j] != v[j]) ? -INFINITY : v[j];
-                        if (i < prm.n_items && (sc > best_s[k - 1] || best_i[k - 1] < 0)) {
+                        if (i < prm.n_items && (sc > thr_s || thr_i < 0)) {
                             // insert, keeping (score desc, id asc): items arrive in ascending id, so an
                             // equal score never displaces an earlier one
                             int32_t ci = (int32_t)i;
@@ -227,9 +226,11 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
                                     best_i[q] = ci;
                                     sc = ts;
                                     ci = ti;
-                                    if (ci < 0) break;
                                 }
                             }
+#pragma unroll
+                            for (int q = 0; q < FS_KMAX; ++q)
+                                if (q == k - 1) { thr_s = best_s[q]; thr_i = best_i[q]; }
                         }
                     }
                 }

@@ -203,3 +203,24 @@ def rank_eval(scores, labels, iids, cand_rows, user_off, k, out_metrics, out_top
                              ptr(out_topk_iid), ptr(out_topk_row), ptr(out_metrics), stream_ptr()), 'dccf_rank_eval')
     LAUNCHES[0] += 1
     return out_metrics
+
+
+def full_scores(A, B, row_bias=None, col_bias=None, col_scale=None, g=0.0, materialise=True, k=0):
+    """Full-catalogue scoring on the tensor cores (dccf_full_scores).  Returns (matrix [U,I] or None,
+    topk_score [U,k] or None, topk_id [U,k] or None)."""
+    lib = _lib.load()
+    U, I = A.shape[0], B.shape[0]
+    dev = A.device
+    out = torch.empty((U, I), dtype=torch.float32, device=dev) if materialise else None
+    ts = ti = ws = wi = None
+    if k > 0:
+        ts = torch.empty((U, k), dtype=torch.float32, device=dev)
+        ti = torch.empty((U, k), dtype=torch.int64, device=dev)
+        splits = int(lib.dccf_full_scores_splits(U, I))
+        if splits > 1:
+            ws = torch.empty((splits, U, k), dtype=torch.float32, device=dev)
+            wi = torch.empty((splits, U, k), dtype=torch.int64, device=dev)
+    check(lib.dccf_full_scores(U, I, ptr(A), ptr(B), ptr(row_bias), ptr(col_bias), ptr(col_scale), float(g), ptr(out),
+                               int(k), ptr(ts), ptr(ti), ptr(ws), ptr(wi), stream_ptr()), 'dccf_full_scores')
+    LAUNCHES[0] += 2 if ws is not None else 1
+    return out, ts, ti

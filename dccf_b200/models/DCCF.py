@@ -464,7 +464,7 @@ class DCCF(DMF):
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             launches_before = kernels.LAUNCHES[0]
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode='thread_local'):
                 pred = self._launch_fwd(call, save=True)
                 rec = self._launch_bwd(call, loss_mode=0 if rank_mode == 1 else 1, Y=g['Y'] if rank_mode != 1 else None)
                 loss = self._apply_adam(rec, P, opt, hp).clone()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 8
+#define DCCF_ABI_VERSION 9
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -222,6 +222,21 @@ int dccf_rank_eval(const float* scores, const float* labels, const int64_t* iids
                    const int32_t* cand_rows, const int64_t* user_off, int64_t n_users, int32_t k,
                    int64_t* out_topk_iid, int32_t* out_topk_row, double* out_metrics,
                    void* stream);
+
+/* ---- full-catalogue scoring (tcgen05 GEMM) -------------------------------------------------- */
+/* score[u,i] = ( <A[u,:], B[i,:]> + row_bias[u] + col_bias[i] + g ) * col_scale[i],  A [U,D], B [I,D] f32,
+ * 3xTF32 on the tensor cores (FP32-level accuracy).  Replaces IPSBiasedMF.predict over the whole catalogue
+ * (src/models/IPSBiasedMF.py:37-57 with col_scale = 1/max(propensity, M); README.md:27-29: that matrix is
+ * <ds>.ips_expo_prob.npy) and serves deterministic full-catalogue DCCF scoring.  Bias / scale vectors may be
+ * NULL.  Outputs, either or both:
+ *   out        [U,I]  the materialised matrix (or NULL)
+ *   topk_score [U,k] f32, topk_id [U,k] int64 (-1 padded): fused per-user top-k, score descending, ties by
+ *              item id ascending, NaN last; 1 <= k <= 16 (or NULL)
+ *   ws_score / ws_id: [dccf_full_scores_splits(U,I), U, k] workspaces, needed when that count is > 1 */
+int32_t dccf_full_scores_splits(int32_t n_users, int32_t n_items);
+int dccf_full_scores(int32_t n_users, int32_t n_items, const float* A, const float* B, const float* row_bias,
+                     const float* col_bias, const float* col_scale, float g, float* out, int32_t k,
+                     float* topk_score, int64_t* topk_id, float* ws_score, int64_t* ws_id, void* stream);
 
 /* ---- host side: exact replay of the reference's negative sampler ---------------------------- */
 /* Replaces the Python loop of src/data_processor/DataProcessor.py:446-524 draw for draw.  HOST pointers.

@@ -504,3 +504,44 @@ def test_tensor_core_scorer_equals_simt_scorer_on_library_noise():
     model._rng_offset = 50
     b = model.predict(dict(fd, force_tc=True))['prediction'].cpu().numpy()
     assert rel_err(b, a) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------
+# full-catalogue scoring (tcgen05 GEMM + fused top-k)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('U,I', [(300, 1000), (129, 67), (1000, 4096)])
+def test_full_catalogue_ipsmf_scores_and_topk(U, I):
+    """IPSBiasedMF over the whole catalogue (src/models/IPSBiasedMF.py:37-57): matrix vs float64 numpy,
+    fused top-k ids bit-identical to the top-k of the materialised matrix (ties by item id)."""
+    from dccf_b200 import full_catalogue, synth
+    fac = synth.make_ipsmf_factors(U, I, seed=11)
+    dev = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else float(v)) for k, v in fac.items()}
+    got = full_catalogue.ipsmf_exposure(dev)
+    want = O.exposure_values({k: (v.astype(np.float64) if isinstance(v, np.ndarray) else float(v)) for k, v in fac.items()},
+                             np.arange(U), np.tile(np.arange(I), (U, 1)))
+    assert got.shape == (U, I)
+    assert rel_err(got.cpu().numpy(), want) < 3e-6
+    for k in (1, 5, 16):
+        kk = min(k, I)
+        s, ids = full_catalogue.ipsmf_topk(dev, kk)
+        m = got.cpu().numpy()
+        order = np.lexsort((np.tile(np.arange(I), (U, 1)), -m.astype(np.float64)), axis=1)[:, :kk]
+        assert np.array_equal(ids.cpu().numpy(), order)
+        assert np.array_equal(s.cpu().numpy(), np.take_along_axis(m, order, axis=1))
+
+
+def test_full_catalogue_dccf_topk_matches_pairwise_scorer():
+    """Deterministic DCCF (std 0, no confounders): the GEMM scorer ranks the catalogue like the pairwise scorer."""
+    from dccf_b200 import full_catalogue
+    U, I, F = 64, 500, 768
+    params, _, _, _, _ = random_problem(5, U, I, F, 2, 0, 1, 0.0, 0.0)
+    model = make_model(params, 0, 1, 0.0)
+    s, ids = full_catalogue.dccf_catalogue_topk(model, 5)
+    X = np.stack([np.repeat(np.arange(U), I), np.tile(np.arange(I), U)], 1).astype(np.int64)
+    pair = model.predict({'X': torch.from_numpy(X).cuda(), 'rank': 1, 'train': False, 'dropout': 0.0})
+    pair = pair['prediction'].cpu().numpy().reshape(U, I)
+    top_pair = np.take_along_axis(pair, ids.cpu().numpy(), axis=1)
+    assert rel_err(s.cpu().numpy(), top_pair) < 1e-5
+    # the 5th best pairwise score is not beaten by anything outside the returned set (up to rounding)
+    kth = np.sort(pair, axis=1)[:, -5]
+    assert (top_pair.min(axis=1) >= kth - 1e-5 * np.abs(pair).max()).all()
