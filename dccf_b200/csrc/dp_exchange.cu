@@ -1,0 +1,124 @@
+// dp_exchange.cu — the data-parallel gradient exchange as plain kernels over NVLink peer memory.
+//
+// Every rank owns a symmetric buffer [ recv: world x seg floats | arrival flags | consumed flags ] whose
+// address on every peer is known (torch symmetric memory / CUDA IPC mappings).  Per training step:
+//   k_dp_push : wait until every peer has consumed the previous step's data, then store this rank's packed
+//               gradient segment (records, dW, db, keys, loss) straight into slot `rank` of EVERY peer's recv
+//               buffer with 128-bit stores over NVLink (an all-gather written by the producers), fence, and
+//               publish the step number in each peer's arrival flag
+//   k_dp_wait : spin until all world arrival flags show this step (the peers run their own k_dp_push)
+//   ...the Adam kernels read recv...
+//   k_dp_done : tell every peer this rank is done reading, advance the step counter
+// No NCCL call and no host involvement: the whole step, exchange included, is capturable in one CUDA graph.
+#include "common.cuh"
+
+namespace dccf {
+
+constexpr int DP_MAX_WORLD = 8;
+struct DpPeers {
+    float* base[DP_MAX_WORLD];
+};
+
+__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
+    int32_t v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send, int64_t seg, DpPeers peers, int world,
+                                                 int rank, int64_t flag_off, const int32_t* __restrict__ epoch_dev,
+                                                 int32_t* cta_counter) {
+    const int32_t epoch = __ldg(epoch_dev) + 1;
+    if (threadIdx.x < world) {
+        // peers have finished reading what this rank pushed last step
+        const int32_t* consumed = reinterpret_cast<const int32_t*>(peers.base[rank] + flag_off) + DP_MAX_WORLD;
+        while (ld_acquire_sys(consumed + threadIdx.x) < epoch - 1) {
+        }
+    }
+    __syncthreads();
+    const int64_t n4 = seg >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int p = 0; p < world; ++p) {
+        float4* dst = reinterpret_cast<float4*>(peers.base[p] + (int64_t)rank * seg);
+        const float4* src = reinterpret_cast<const float4*>(send);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int32_t prev = atomicAdd(cta_counter, 1);
+        if (prev == (int32_t)gridDim.x - 1) {
+            __threadfence_system();
+            for (int p = 0; p < world; ++p)
+                st_release_sys(reinterpret_cast<int32_t*>(peers.base[p] + flag_off) + rank, epoch);
+            *cta_counter = 0;
+        }
+    }
+}
+
+__global__ void k_dp_wait(const float* my_base, int world, int64_t flag_off, const int32_t* __restrict__ epoch_dev) {
+    const int32_t epoch = __ldg(epoch_dev) + 1;
+    if ((int)threadIdx.x < world) {
+        const int32_t* arrival = reinterpret_cast<const int32_t*>(my_base + flag_off);
+        while (ld_acquire_sys(arrival + threadIdx.x) < epoch) {
+        }
+    }
+}
+
+__global__ void k_dp_done(DpPeers peers, int world, int rank, int64_t flag_off, int32_t* epoch_dev) {
+    const int32_t epoch = *epoch_dev + 1;
+    __syncthreads();
+    if ((int)threadIdx.x < world)
+        st_release_sys(reinterpret_cast<int32_t*>(peers.base[threadIdx.x] + flag_off) + DP_MAX_WORLD + rank, epoch);
+    __syncthreads();
+    if (threadIdx.x == 0) *epoch_dev = epoch;
+}
+
+static int fill_peers(DpPeers* out, const uint64_t* peer_bases, int world, const char* who) {
+    DCCF_CHECK_ARG(peer_bases != nullptr && world >= 1 && world <= DP_MAX_WORLD, "%s: world size must be in [1,%d]", who, DP_MAX_WORLD);
+    for (int p = 0; p < DP_MAX_WORLD; ++p) out->base[p] = p < world ? reinterpret_cast<float*>(peer_bases[p]) : nullptr;
+    for (int p = 0; p < world; ++p) DCCF_CHECK_ARG(out->base[p] != nullptr, "%s: peer %d has a null buffer", who, p);
+    return DCCF_OK;
+}
+
+}  // namespace dccf
+
+using namespace dccf;
+
+// peer_bases: HOST array of `world` device addresses (this rank's own buffer at index `rank`)
+extern "C" int dccf_dp_push(const float* send, int64_t seg_floats, const uint64_t* peer_bases, int32_t world,
+                            int32_t rank, int64_t flag_off, const int32_t* epoch_dev, int32_t* cta_counter,
+                            void* stream_) {
+    DpPeers peers;
+    int rc = fill_peers(&peers, peer_bases, world, "dccf_dp_push");
+    if (rc != DCCF_OK) return rc;
+    DCCF_CHECK_ARG(send && epoch_dev && cta_counter, "dccf_dp_push: null buffer");
+    DCCF_CHECK_ARG(seg_floats > 0 && seg_floats % 4 == 0, "dccf_dp_push: segment length must be a positive multiple of 4 floats");
+    DCCF_CHECK_ARG(rank >= 0 && rank < world, "dccf_dp_push: rank %d outside [0,%d)", rank, world);
+    int64_t ctas = (seg_floats / 4 + 255) / 256;
+    if (ctas > 148) ctas = 148;
+    k_dp_push<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream_>>>(send, seg_floats, peers, world, rank, flag_off, epoch_dev, cta_counter);
+    DCCF_CHECK_LAUNCH("k_dp_push");
+    return DCCF_OK;
+}
+
+extern "C" int dccf_dp_wait(const float* my_base, int32_t world, int64_t flag_off, const int32_t* epoch_dev, void* stream_) {
+    DCCF_CHECK_ARG(my_base && epoch_dev && world >= 1 && world <= DP_MAX_WORLD, "dccf_dp_wait: bad argument");
+    k_dp_wait<<<1, 32, 0, (cudaStream_t)stream_>>>(my_base, world, flag_off, epoch_dev);
+    DCCF_CHECK_LAUNCH("k_dp_wait");
+    return DCCF_OK;
+}
+
+extern "C" int dccf_dp_done(const uint64_t* peer_bases, int32_t world, int32_t rank, int64_t flag_off, int32_t* epoch_dev,
+                            void* stream_) {
+    DpPeers peers;
+    int rc = fill_peers(&peers, peer_bases, world, "dccf_dp_done");
+    if (rc != DCCF_OK) return rc;
+    DCCF_CHECK_ARG(epoch_dev != nullptr && rank >= 0 && rank < world, "dccf_dp_done: bad argument");
+    k_dp_done<<<1, 32, 0, (cudaStream_t)stream_>>>(peers, world, rank, flag_off, epoch_dev);
+    DCCF_CHECK_LAUNCH("k_dp_done");
+    return DCCF_OK;
+}

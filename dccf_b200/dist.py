@@ -26,7 +26,7 @@ class GradExchange(object):
     P pairs per rank and step, Z slots, D embedding width, K = D + F columns of W.  Offsets are in 4-byte
     elements; the key arrays are int32 views of the same float32 buffer."""
 
-    def __init__(self, P, Z, D, K, world, rank, device, group=None):
+    def __init__(self, P, Z, D, K, world, rank, device, group=None, use_p2p=True):
         self.P, self.Z, self.D, self.K = P, Z, D, K
         self.world, self.rank, self.group = world, rank, group
         off = 0
@@ -36,10 +36,37 @@ class GradExchange(object):
             self.off[name] = (off, n)
             off += (n + 3) // 4 * 4                      # keep every part 16-byte aligned
         self.seg = off
-        self.recv = torch.zeros(world * self.seg, dtype=torch.float32, device=device)
-        # the send segment is this rank's slot of the receive buffer when the backend allows in-place
-        # all-gather; kept separate for portability (gloo)
         self.send = torch.zeros(self.seg, dtype=torch.float32, device=device)
+        self.mode = 'collective'
+        self.recv = None
+        if world > 1 and torch.device(device).type == 'cuda' and use_p2p:
+            try:
+                self._init_p2p(device)
+                self.mode = 'p2p'
+            except Exception as e:                      # symmetric memory unavailable: NCCL all-gather instead
+                import logging
+                logging.warning('dccf_b200.dist: peer-memory exchange unavailable (%s); using all_gather' % (e,))
+        if self.recv is None:
+            self.recv = torch.zeros(world * self.seg, dtype=torch.float32, device=device)
+
+    def _init_p2p(self, device):
+        """Symmetric receive buffer mapped on every peer (torch symmetric memory = CUDA VMM/IPC over NVLink):
+        [ recv: world x seg floats | arrival flags int32[8] | consumed flags int32[8] ]."""
+        import torch.distributed._symmetric_memory as symm
+        from . import kernels  # noqa: F401  (fail early if the library is missing)
+        self.flag_off = self.world * self.seg
+        buf = symm.empty(self.flag_off + 16, dtype=torch.float32, device=device)
+        hdl = symm.rendezvous(buf, dist.group.WORLD if self.group is None else self.group)
+        buf.zero_()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)                  # every rank's flags are zero before anyone pushes
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        delta = int(buf.data_ptr()) - ptrs[self.rank]   # offset of `buf` inside the symmetric allocation
+        self.peer_bases = [p + delta for p in ptrs]
+        self.sym, self.hdl = buf, hdl
+        self.recv = buf[:self.flag_off]
+        self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=device)
+        self.cta_counter = torch.zeros(1, dtype=torch.int32, device=device)
 
     def part(self, buf, name, seg_index=0):
         a, n = self.off[name]
@@ -57,12 +84,25 @@ class GradExchange(object):
                 'loss': self.part(self.send, 'loss')}
 
     def exchange(self):
-        """All ranks' segments, rank-major, in self.recv."""
-        if self.world == 1:
+        """All ranks' segments, rank-major, in self.recv.  Peer-memory mode: this rank's kernel stores its
+        segment into every peer's buffer over NVLink and waits for the peers' stores (no NCCL, no host sync,
+        capturable in a CUDA graph); otherwise one all_gather_into_tensor."""
+        if self.mode == 'p2p':
+            from . import kernels
+            kernels.dp_push(self.send, self.seg, self.peer_bases, self.world, self.rank, self.flag_off,
+                            self.epoch_dev, self.cta_counter)
+            kernels.dp_wait(self.sym, self.world, self.flag_off, self.epoch_dev)
+        elif self.world == 1:
             self.recv.copy_(self.send)
         else:
             dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
         return self.recv
+
+    def done(self):
+        """The receive buffer has been consumed (call after the last kernel that reads it)."""
+        if self.mode == 'p2p':
+            from . import kernels
+            kernels.dp_done(self.peer_bases, self.world, self.rank, self.flag_off, self.epoch_dev)
 
     def total_loss(self):
         a, _ = self.off['loss']

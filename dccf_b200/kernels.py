@@ -224,3 +224,25 @@ def full_scores(A, B, row_bias=None, col_bias=None, col_scale=None, g=0.0, mater
                                int(k), ptr(ts), ptr(ti), ptr(ws), ptr(wi), stream_ptr()), 'dccf_full_scores')
     LAUNCHES[0] += 2 if ws is not None else 1
     return out, ts, ti
+
+
+def dp_push(send, seg, peer_bases, world, rank, flag_off, epoch_dev, cta_counter):
+    """Store this rank's gradient segment into every peer's receive buffer (NVLink P2P stores)."""
+    lib = _lib.load()
+    arr = (ctypes.c_uint64 * world)(*[int(b) for b in peer_bases])
+    check(lib.dccf_dp_push(ptr(send), int(seg), arr, int(world), int(rank), int(flag_off), ptr(epoch_dev),
+                           ptr(cta_counter), stream_ptr()), 'dccf_dp_push')
+    LAUNCHES[0] += 1
+
+
+def dp_wait(my_buf, world, flag_off, epoch_dev):
+    lib = _lib.load()
+    check(lib.dccf_dp_wait(ptr(my_buf), int(world), int(flag_off), ptr(epoch_dev), stream_ptr()), 'dccf_dp_wait')
+    LAUNCHES[0] += 1
+
+
+def dp_done(peer_bases, world, rank, flag_off, epoch_dev):
+    lib = _lib.load()
+    arr = (ctypes.c_uint64 * world)(*[int(b) for b in peer_bases])
+    check(lib.dccf_dp_done(arr, int(world), int(rank), int(flag_off), ptr(epoch_dev), stream_ptr()), 'dccf_dp_done')
+    LAUNCHES[0] += 1

@@ -334,11 +334,13 @@ class DCCF(DMF):
         return out_dict
 
     # ---- data parallel ----------------------------------------------------------------------
-    def enable_data_parallel(self, group=None):
-        """Replicated parameters, per-rank batches, gradients exchanged with one all-gather per step
-        (dccf_b200/dist.py).  Requires an initialised torch.distributed process group."""
+    def enable_data_parallel(self, group=None, p2p=True):
+        """Replicated parameters, per-rank batches, gradients exchanged once per step (dccf_b200/dist.py):
+        by this rank's own kernels over NVLink peer memory (p2p=True, default) or by an NCCL all-gather.
+        Requires an initialised torch.distributed process group."""
         import torch.distributed as dist
-        self._dp = {'world': dist.get_world_size(group), 'rank': dist.get_rank(group), 'group': group, 'ex': {}}
+        self._dp = {'world': dist.get_world_size(group), 'rank': dist.get_rank(group), 'group': group, 'ex': {},
+                    'p2p': p2p}
         return self
 
     def _exchange_for(self, P):
@@ -347,7 +349,8 @@ class DCCF(DMF):
         if ex is None:
             D, Z = self.ui_vector_size, self.sample_num + 1
             ex = GradExchange(P, Z, D, D + self.feature_embedding.shape[1], self._dp['world'], self._dp['rank'],
-                              self.uid_embeddings.weight.device, group=self._dp['group'])
+                              self.uid_embeddings.weight.device, group=self._dp['group'],
+                              use_p2p=self._dp.get('p2p', True))
             self._dp['ex'][P] = ex
         return ex
 
@@ -378,7 +381,9 @@ class DCCF(DMF):
             dense = [kernels.adam_tensor(W, opt.exp_avg['W'], opt.exp_avg_sq['W'], ex.part(recv, 'gW'), world, seg),
                      kernels.adam_tensor(b, opt.exp_avg['b'], opt.exp_avg_sq['b'], ex.part(recv, 'gb'), world, seg)]
             kernels.adam_step(tables, dense, hp)
-            return ex.total_loss()
+            loss = ex.total_loss()
+            ex.done()
+            return loss
         tables = [
             kernels.adam_table(eu, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'], rec['keys_u'], rec['gu_rec'], 1, P,
                                P, P * self.ui_vector_size, opt.head_u, self._buf('next_u', (P,), torch.int32)),
@@ -427,11 +432,13 @@ class DCCF(DMF):
 
     # ---- CUDA-graph replay of the fused step -----------------------------------------------------
     use_cuda_graph = True
-    dp_cuda_graph = False      # capture the NCCL all-gather inside the step graph (off until validated on N GPUs)
-
     def _train_step_graph(self, feed_dict, opt):
-        if self._dp is not None and not self.dp_cuda_graph:
-            return None
+        if self._dp is not None:
+            # graph capture needs the exchange to be plain kernels (peer-memory mode); an NCCL all-gather
+            # inside the captured step deadlocked on 2 x B200 with torch 2.11 / NCCL 2.28
+            ex = self._exchange_for(feed_dict['X'].shape[0])
+            if ex.mode != 'p2p':
+                return None
         self._check_ready()
         dev = self.uid_embeddings.weight.device
         X = feed_dict['X']

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 9
+#define DCCF_ABI_VERSION 10
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -222,6 +222,21 @@ int dccf_rank_eval(const float* scores, const float* labels, const int64_t* iids
                    const int32_t* cand_rows, const int64_t* user_off, int64_t n_users, int32_t k,
                    int64_t* out_topk_iid, int32_t* out_topk_row, double* out_metrics,
                    void* stream);
+
+/* ---- data-parallel gradient exchange over NVLink peer memory (new: the reference is single-GPU) ----- */
+/* Every rank owns a symmetric buffer of floats: [ recv: world*seg | arrival flags int32[8] | consumed flags
+ * int32[8] ] mapped on all peers; peer_bases is a HOST array with its device address on each rank.
+ *   dccf_dp_push: waits for the peers to have consumed the previous step, stores `send` (seg floats) into slot
+ *                 `rank` of every peer's recv region with 128-bit stores, publishes the step in their arrival flags
+ *   dccf_dp_wait: spins until all `world` arrival flags of this rank show the current step
+ *   dccf_dp_done: marks this rank's recv region as consumed on every peer and advances epoch_dev (device int32,
+ *                 the number of completed exchanges; starts at 0)
+ * flag_off: offset of the flag area in floats (>= world*seg, multiple of 4).  cta_counter: device int32, zero. */
+int dccf_dp_push(const float* send, int64_t seg_floats, const uint64_t* peer_bases, int32_t world, int32_t rank,
+                 int64_t flag_off, const int32_t* epoch_dev, int32_t* cta_counter, void* stream);
+int dccf_dp_wait(const float* my_base, int32_t world, int64_t flag_off, const int32_t* epoch_dev, void* stream);
+int dccf_dp_done(const uint64_t* peer_bases, int32_t world, int32_t rank, int64_t flag_off, int32_t* epoch_dev,
+                 void* stream);
 
 /* ---- full-catalogue scoring (tcgen05 GEMM) -------------------------------------------------- */
 /* score[u,i] = ( <A[u,:], B[i,:]> + row_bias[u] + col_bias[i] + g ) * col_scale[i],  A [U,D], B [I,D] f32,

@@ -38,7 +38,7 @@ def main():
     pairs = np.concatenate([pos, b + pos])
     rows = (pairs[:, None] * R + np.arange(R)[None, :]).reshape(-1)
     model = make_model(params, S, A, std)
-    model.enable_data_parallel()
+    model.enable_data_parallel(p2p=os.environ.get('DCCF_DP_P2P', '1') == '1')
     model.optimizer = model.make_fused_optimizer(lr=1e-3, l2=1e-4)
     steps = 2
     for t in range(steps):
@@ -46,7 +46,7 @@ def main():
               'Y': torch.zeros(len(pairs)).cuda(), 'sample_item': torch.from_numpy(si[pairs]),
               'noise': torch.from_numpy(noise[rows]), 'dropout_mask': torch.from_numpy(mask[rows])}
         out = model.train_step(fd)
-    say(rank, 'dp steps done, loss %.6f' % float(out['loss']))
+    say(rank, 'dp steps done (exchange=%s), loss %.6f' % (model._exchange_for(len(pairs)).mode, float(out['loss'])))
     got = model_params(model)
     # replicas bit-identical
     for k, v in got.items():
@@ -73,7 +73,6 @@ def main():
 
     say(rank, 'equality with the single-GPU step ok')
     # DP steps on the library's own rng streams keep the replicas identical too
-    model.dp_cuda_graph = os.environ.get('DCCF_DP_GRAPH', '0') == '1'
     for t in range(4):
         fd = {'X': torch.from_numpy(X[pairs]).cuda(), 'rank': 1, 'train': True, 'dropout': drop,
               'Y': torch.zeros(len(pairs)).cuda(), 'sample_item': torch.from_numpy(si[pairs])}
@@ -84,7 +83,7 @@ def main():
         dist.broadcast(ref, 0)
         assert torch.equal(t, ref), 'rank %d diverged from rank 0 on %s after graph replay' % (rank, k)
 
-    say(rank, 'library-rng DP steps ok (graph=%s)' % model.dp_cuda_graph)
+    say(rank, 'library-rng DP steps ok (exchange=%s, graphs=%d)' % (model._exchange_for(len(pairs)).mode, len(getattr(model, '_graphs', {}))))
     # user-sharded evaluation == single-GPU evaluation (same scores -> same metrics)
     from dccf_b200.dist import all_reduce_sum, shard_users
     from dccf_b200.models.BaseModel import BaseModel
