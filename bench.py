@@ -48,12 +48,13 @@ FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 
 
 def measured_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s burst, source)."""
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
         with open(path) as f:
             d = json.load(f)
-        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
-    return 6650.0, 'fallback (B200_PROFILING.md)'
+        return float(d['hbm_gbs']), float(d.get('bf16_tflops', 1590.0)), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 1590.0, 'fallback (B200_PROFILING.md)'
 
 
 # ------------------------------------------------------------------------------------------------
@@ -279,28 +280,36 @@ def bench_eval(model, n_users, warm_batches, world, rank, flush):
     si_d = torch.randint(I, size=(rows, S)).to(dev)
     model.eval()
 
-    def run(from_host, X_src, timed):
-        preds = []
-        ev_pairs = []
-        for bi, (a, b) in enumerate(bounds):
-            flush()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            if from_host:
-                fd = {'X': X_src[a:b].to(dev, non_blocking=True), 'rank': 1, 'train': False, 'dropout': 0.0}
-            else:
-                fd = {'X': X_src[a:b], 'rank': 1, 'train': False, 'dropout': 0.0, 'sample_item': si_d[a:b]}
-            preds.append(model.predict(fd)['prediction'])
-            e1.record()
-            ev_pairs.append((e0, e1))
-        pred = torch.cat(preds)
+    def rank_and_sum(pred):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         m = rank_metrics_device(pred, Y_d, iid_d, cand_d, off_d, 5)
         sums = m.sum(dim=0)
         e1.record()
-        ev_pairs.append((e0, e1))
-        return sums, ev_pairs
+        return sums, (e0, e1)
+
+    def run_resident():
+        """ids and confounder draws already in HBM; one CUDA-event pair per batch, L2 flushed in between"""
+        preds, ev_pairs = [], []
+        for a, b in bounds:
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            preds.append(model.predict({'X': X_d[a:b], 'rank': 1, 'train': False, 'dropout': 0.0,
+                                        'sample_item': si_d[a:b]})['prediction'])
+            e1.record()
+            ev_pairs.append((e0, e1))
+        sums, ev = rank_and_sum(torch.cat(preds))
+        return sums, ev_pairs + [ev]
+
+    def run_from_host(X_pin):
+        """public API: ids from pinned host memory, confounders drawn on the torch CPU generator per batch
+        (src/models/DCCF.py:72) by predict_many's worker thread, metric sums read back"""
+        fds = [{'X': X_pin[a:b].to(dev, non_blocking=True), 'rank': 1, 'train': False, 'dropout': 0.0}
+               for a, b in bounds]
+        preds = model.predict_many(fds)
+        sums, _ = rank_and_sum(torch.cat(preds))
+        return sums.cpu().numpy()
 
     # warm-up (also loads the ranker's module: CUDA loads kernels lazily on first launch)
     for _ in range(3):
@@ -308,7 +317,7 @@ def bench_eval(model, n_users, warm_batches, world, rank, flush):
                             'sample_item': si_d[:EVAL_BATCH]})
         rank_metrics_device(torch.zeros(rows, device=dev), Y_d, iid_d, cand_d, off_d, 5).sum(dim=0)
     barrier(world)
-    sums, evs = run(False, X_d, True)
+    sums, evs = run_resident()
     barrier(world)
     score_ms = sum(a.elapsed_time(b) for a, b in evs[:-1])
     rank_ms = evs[-1][0].elapsed_time(evs[-1][1])
@@ -318,9 +327,10 @@ def bench_eval(model, n_users, warm_batches, world, rank, flush):
     # metric sums read back at the end
     X_pin = torch.from_numpy(X).pin_memory()
     barrier(world)
+    run_from_host(X_pin)                       # warm the pinned-buffer cache
+    barrier(world)
     t0 = time.perf_counter()
-    sums, _ = run(True, X_pin, True)
-    host_sums = sums.cpu().numpy()
+    host_sums = run_from_host(X_pin)
     t1 = time.perf_counter()
     e2e_s = dist_max(t1 - t0, world)
     flush_s = 0.0
@@ -382,7 +392,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--preset', default='electronics', choices=sorted(PRESETS))
-    ap.add_argument('--eval-users', type=int, default=256)
+    ap.add_argument('--eval-users', type=int, default=1024)
     ap.add_argument('--cpu-budget', type=float, default=12.0, help='seconds of CPU work for the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
@@ -435,7 +445,8 @@ def main():
         evl = bench_eval(model, args.eval_users, 3, world, rank, flush)
     clk = clocks.summary()
 
-    hbm_peak, peak_src = measured_peaks()
+    hbm_peak, bf16_peak, peak_src = measured_peaks()
+    tf32_peak = bf16_peak / 2.0          # kind::tf32 runs at half the bf16 rate
     ms_per_step = tr['total_ms'] / args.steps
     value = world * BATCH * args.steps / (tr['total_ms'] / 1e3)
     e2e_value = world * BATCH * args.steps / tr['e2e_s']
@@ -456,21 +467,40 @@ def main():
             'frac': stages[dom]['gbs'] / hbm_peak, 'traffic': None, 'peak_source': peak_src,
             'fp32_simt': {'achieved': stages[dom]['tflops'], 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s',
                           'frac': stages[dom]['tflops'] / FP32_PEAK_TFLOPS},
+            'stages_note': 'per-stage CUDA events of the same step launched kernel by kernel (includes launch gaps; the '
+                           'timed value replays the step as one CUDA graph)',
             'stages': stages}
     eval_pairs = evl['rows']
     eval_users_s = world * args.eval_users / (evl['dev_ms'] / 1e3)
     eval_tflops = eval_pairs * FLOP_FWD_PAIR / 1e12 / (evl['score_ms'] / 1e3)
+    used_tc = bool(getattr(model, 'use_tensor_cores', False)) and eval_pairs * R >= model.tc_min_rows
+    noise_tflop = 3 * eval_pairs * R * 2.0 * F * D / 1e12          # the three TF32 products actually issued
+    if used_tc:
+        eval_roof = {'kernel': 'k_row_scores_tc (tcgen05 3xTF32)', 'bound': 'tensor',
+                     'achieved': noise_tflop / (evl['score_ms'] / 1e3), 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                     'frac': noise_tflop / (evl['score_ms'] / 1e3) / tf32_peak, 'traffic': None,
+                     'peak_source': peak_src + ': bf16 burst / 2 for kind::tf32',
+                     'limiter': 'Gaussian noise generation (Philox4x32-10 + Box-Muller, 16.9 M normals per user) on '
+                                'the SIMT ALU/XU pipes, not the tensor pipe',
+                     'fp32_equivalent': {'achieved': eval_tflops, 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+                                         'frac': eval_tflops / FP32_PEAK_TFLOPS,
+                                         'note': 'algorithmic FP32 flops of the reference formulation / time, against '
+                                                 'the FP32 SIMT peak a non-tensor-core kernel is bounded by'},
+                     'hbm': {'achieved': eval_pairs * BYTES_PAIR / 1e9 / (evl['score_ms'] / 1e3), 'peak': hbm_peak,
+                             'unit': 'GB/s', 'frac': eval_pairs * BYTES_PAIR / 1e9 / (evl['score_ms'] / 1e3) / hbm_peak}}
+    else:
+        eval_roof = {'kernel': 'k_row_scores', 'bound': 'hbm',
+                     'achieved': eval_pairs * BYTES_PAIR / 1e9 / (evl['score_ms'] / 1e3), 'peak': hbm_peak,
+                     'unit': 'GB/s', 'frac': eval_pairs * BYTES_PAIR / 1e9 / (evl['score_ms'] / 1e3) / hbm_peak,
+                     'traffic': None,
+                     'fp32_simt': {'achieved': eval_tflops, 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+                                   'frac': eval_tflops / FP32_PEAK_TFLOPS}}
     eval_obj = {'metric': 'eval_users_per_s', 'value': eval_users_s, 'unit': 'users/s',
                 'users': world * args.eval_users, 'candidates_per_user': 1 + TEST_NEG_N,
                 'ms_per_batch': evl['score_ms'] / evl['n_batches'], 'rank_ms': evl['rank_ms'],
                 'e2e': {'value': world * args.eval_users / evl['e2e_s'], 'unit': 'users/s',
                         'h2d_bytes': evl['h2d'], 'd2h_bytes': evl['d2h']},
-                'roofline': {'kernel': 'k_row_scores', 'bound': 'hbm',
-                             'achieved': eval_pairs * BYTES_PAIR / 1e9 / (evl['score_ms'] / 1e3), 'peak': hbm_peak,
-                             'unit': 'GB/s', 'frac': eval_pairs * BYTES_PAIR / 1e9 / (evl['score_ms'] / 1e3) / hbm_peak,
-                             'traffic': None,
-                             'fp32_simt': {'achieved': eval_tflops, 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s',
-                                           'frac': eval_tflops / FP32_PEAK_TFLOPS}},
+                'roofline': eval_roof,
                 'ndcg@5': evl['ndcg@5'], 'recall@5': evl['recall@5'], 'precision@5': evl['precision@5']}
     line = {'metric': 'train_samples_per_s', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',

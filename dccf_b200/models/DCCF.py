@@ -320,6 +320,45 @@ class DCCF(DMF):
             prediction = self._launch_fwd(call, save=False)
         return {'prediction': prediction, 'check': [('prediction', prediction)]}
 
+    def predict_many(self, feed_dicts, depth=2):
+        """Predictions for a list of feed dicts (an evaluation pass).  Identical to calling `predict` on each
+        in turn — including the order in which the torch CPU generator is consumed (DCCF.py:72) — but the
+        confounder draw of batch k+1 is made by a worker thread into pinned memory while batch k runs on the
+        GPU, so the host generator no longer serialises with the device."""
+        import queue
+        import threading
+        S = self.sample_num
+        pin = torch.cuda.is_available()
+        q = queue.Queue(maxsize=max(1, depth))
+
+        def produce():
+            try:
+                for fd in feed_dicts:
+                    if 'sample_item' in fd or S == 0:
+                        q.put(None)
+                        continue
+                    buf = torch.empty((fd['X'].shape[0], S), dtype=torch.int64, pin_memory=pin)
+                    torch.randint(self.item_num, (fd['X'].shape[0], S), out=buf)
+                    q.put(buf)
+            except BaseException as e:      # surface the failure in the consumer
+                q.put(e)
+
+        worker = threading.Thread(target=produce, daemon=True)
+        worker.start()
+        outs = []
+        try:
+            for fd in feed_dicts:
+                draw = q.get()
+                if isinstance(draw, BaseException):
+                    raise draw
+                if draw is not None:
+                    fd = dict(fd)
+                    fd['sample_item'] = draw
+                outs.append(self.predict(fd)['prediction'])
+        finally:
+            worker.join()
+        return outs
+
     def forward(self, feed_dict):
         """predict + BPR (rank 1; first half positives, second half their negatives) or MSE loss
         (DCCF.py:109-127)."""

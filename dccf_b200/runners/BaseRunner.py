@@ -106,10 +106,11 @@ class BaseRunner(object):
         batches = data_processor.prepare_batches(data, self.eval_batch_size, train=False)
         batches = self.batches_add_control(batches, train=False)
         model.eval()
-        outs = []
         with torch.no_grad():
-            for batch in self._bar(batches, desc='Predict'):
-                outs.append(model.predict(batch)['prediction'].detach())
+            if hasattr(model, 'predict_many'):
+                outs = [o.detach() for o in model.predict_many(batches)]
+            else:
+                outs = [model.predict(batch)['prediction'].detach() for batch in self._bar(batches, desc='Predict')]
         pred = torch.cat(outs) if len(outs) > 1 else outs[0]
         sample_ids = np.concatenate([b[global_p.K_SAMPLE_ID] for b in batches])
         want = np.asarray(data[global_p.K_SAMPLE_ID])
@@ -162,10 +163,11 @@ class BaseRunner(object):
                 if data_processor.rank == 1 else data_processor._prepare_batches_rt(shard, self.eval_batch_size, False)
         batches = self.batches_add_control(saved[key], train=False)
         model.eval()
-        outs = []
         with torch.no_grad():
-            for batch in self._bar(batches, desc='Predict'):
-                outs.append(model.predict(batch)['prediction'].detach())
+            if hasattr(model, 'predict_many'):
+                outs = [o.detach() for o in model.predict_many(batches)]
+            else:
+                outs = [model.predict(batch)['prediction'].detach() for batch in self._bar(batches, desc='Predict')]
         return rows, (torch.cat(outs) if len(outs) > 1 else outs[0]), shard
 
     # ---- training ----------------------------------------------------------------------------

@@ -545,3 +545,24 @@ def test_full_catalogue_dccf_topk_matches_pairwise_scorer():
     # the 5th best pairwise score is not beaten by anything outside the returned set (up to rounding)
     kth = np.sort(pair, axis=1)[:, -5]
     assert (top_pair.min(axis=1) >= kth - 1e-5 * np.abs(pair).max()).all()
+
+
+def test_predict_many_equals_sequential_predict():
+    """The evaluation loop with the prefetching worker thread consumes the torch CPU generator in the same
+    order as batch-by-batch predict calls (src/models/DCCF.py:72): identical confounders, identical scores."""
+    U, I, F, S, A, std = 100, 150, 128, 10, 2, 0.1
+    params, X, _, _, _ = random_problem(13, U, I, F, 300, S, A, 0.0, 0.0)
+    bounds = [(0, 128), (128, 256), (256, 300)]
+    outs = []
+    for many in (False, True):
+        model = make_model(params, S, A, std)
+        torch.manual_seed(99)
+        fds = [{'X': torch.from_numpy(X[a:b]).cuda(), 'rank': 1, 'train': False, 'dropout': 0.0} for a, b in bounds]
+        if many:
+            preds = model.predict_many(fds)
+        else:
+            preds = [model.predict(fd)['prediction'] for fd in fds]
+        outs.append(torch.cat(preds).cpu().numpy())
+        after = torch.randint(1000, (4,))
+        outs.append(after.numpy())
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
