@@ -19,6 +19,7 @@ struct AdamScalars {
     float omb2;        // 1 - beta2
     float step_size;   // -(lr / (1 - beta1^t))
     float bc2_sqrt;    // sqrt(1 - beta2^t)
+    float inv_bc2_sqrt;
     float eps;
     float two_l2;      // 2 * l2
     float wd;          // weight decay
@@ -42,6 +43,7 @@ __device__ __forceinline__ AdamScalars resolve_adam(const AdamHost& h) {
     const double bc2 = 1.0 - pow(h.beta2, (double)t);
     s.step_size = (float)(-(h.lr / bc1));
     s.bc2_sqrt = (float)sqrt(bc2);
+    s.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
     s.eps = h.eps;
     s.two_l2 = 2.0f * h.l2;
     s.wd = h.wd;
@@ -57,7 +59,9 @@ __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g_
     m = fmaf(s.w1, __fsub_rn(g, m), m);                          // exp_avg.lerp_(g, 1 - beta1)
     v = __fmul_rn(v, s.beta2);                                   // exp_avg_sq.mul_(beta2)
     v = fmaf(__fmul_rn(s.omb2, g), g, v);                        //   .addcmul_(g, g, value = 1 - beta2)
-    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), s.bc2_sqrt), s.eps);
+    // denom = sqrt(v)/sqrt(bc2) + eps: the division by the per-step constant is a multiplication by its
+    // reciprocal (<= 1 ulp from torch's _foreach_div_), the per-element division stays IEEE
+    const float denom = fmaf(sqrtf(v), s.inv_bc2_sqrt, s.eps);
     p = fmaf(s.step_size, __fdiv_rn(m, denom), p);               // param.addcdiv_(exp_avg, denom, value = step_size)
 }
 
@@ -225,7 +229,7 @@ __device__ __forceinline__ float4 gather_row_grad(const AdamTableArgs& t, int32_
     return g;
 }
 
-__global__ void __launch_bounds__(256) k_adam_all(const AdamAllArgs a) {
+__global__ void __launch_bounds__(256, 4) k_adam_all(const AdamAllArgs a) {
     const AdamScalars s = resolve_adam(a.hp);
     const int bid = (int)blockIdx.x;
     for (int i = 0; i < a.n_tables; ++i) {

@@ -65,10 +65,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
                                                uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(PHILOX_M0, c0);
-        const uint32_t lo0 = PHILOX_M0 * c0;
-        const uint32_t hi1 = __umulhi(PHILOX_M1, c2);
-        const uint32_t lo1 = PHILOX_M1 * c2;
+        // one 32x32->64 multiply (IMAD.WIDE.U32) per product instead of a high and a low multiply
+        uint32_t hi0, lo0, hi1, lo1;
+        asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo0), "=r"(hi0) : "r"(PHILOX_M0), "r"(c0));
+        asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo1), "=r"(hi1) : "r"(PHILOX_M1), "r"(c2));
         c0 = hi1 ^ c1 ^ k0;
         c1 = lo1;
         c2 = hi0 ^ c3 ^ k1;

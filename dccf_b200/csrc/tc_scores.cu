@@ -62,20 +62,59 @@ __global__ void k_prep_wf(const float* __restrict__ W, int F, float* __restrict_
     }
 }
 
-// out[i,:] = X[i,:] · Wt_sub + bias      X [n,Kx] row-major, Wt_sub = rows of the k-major W copy ([Kx,64])
-__global__ void __launch_bounds__(256) k_table_gemm(const float* __restrict__ X, int64_t n, int Kx,
-                                                    const float* __restrict__ Wt_sub, const float* __restrict__ bias,
-                                                    float* __restrict__ out) {
+// Which table row feeds output row i:  0 = row i itself (whole-table projection);
+// 1 = the item in slot (p, z) of the batch, i = p*Z + z;  2 = the true item of pair i.
+struct RowSource {
+    int32_t mode;
+    int32_t Z, S, n_items;
+    const int64_t* X;
+    const int64_t* sample_item;
+};
+__device__ __forceinline__ int64_t source_row(const RowSource& rs, int64_t i) {
+    if (rs.mode == 0) return i;
+    if (rs.mode == 2) return checked_id(rs.X[2 * i + 1], rs.n_items, nullptr);
+    const int64_t p = i / rs.Z;
+    const int z = (int)(i - p * rs.Z);
+    return checked_id(z == 0 ? rs.X[2 * p + 1] : rs.sample_item[p * rs.S + (z - 1)], rs.n_items, nullptr);
+}
+
+// out[i,:] = X[src(i),:] · Wt_sub + bias      X [*,Kx] row-major, Wt_sub = rows of the k-major W copy ([Kx,64])
+struct TableJob {
+    const float* X;
+    int64_t n;
+    int32_t Kx;
+    const float* Wt_sub;
+    const float* bias;
+    float* out;
+    RowSource src;
+    int32_t block_lo, block_n;
+};
+struct TableJobs {
+    TableJob job[2];
+    int32_t n_jobs;
+};
+
+__global__ void __launch_bounds__(256) k_table_gemm(const TableJobs jobs) {
     __shared__ __align__(16) float Xs[16][64 + 4];
     __shared__ __align__(16) float Ws[16][D];
+    int ji = 0;
+    if (jobs.n_jobs > 1 && (int)blockIdx.x >= jobs.job[1].block_lo) ji = 1;
+    const TableJob& jb = jobs.job[ji];
+    const float* __restrict__ X = jb.X;
+    const float* __restrict__ Wt_sub = jb.Wt_sub;
+    const float* __restrict__ bias = jb.bias;
+    float* __restrict__ out = jb.out;
+    const int64_t n = jb.n;
+    const int Kx = jb.Kx;
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;          // 4 cols x 4 rows per thread
-    const int64_t row0 = (int64_t)blockIdx.x * 64;
+    const int64_t row0 = (int64_t)((int)blockIdx.x - jb.block_lo) * 64;
+    const int64_t my_src = source_row(jb.src, min(row0 + (tid >> 2), n - 1));
     float acc[4][4] = {};
     for (int k0 = 0; k0 < Kx; k0 += 16) {
         {   // stage X: 64 rows x 16 k  (thread: row = tid>>2, 4 k)
             const int r = tid >> 2, q = tid & 3;
-            const int64_t gr = min(row0 + r, n - 1);
+            const int64_t gr = my_src;
             const float4 v = ldg4(X + (size_t)gr * Kx + k0 + q * 4);
             Xs[q * 4 + 0][r] = v.x; Xs[q * 4 + 1][r] = v.y; Xs[q * 4 + 2][r] = v.z; Xs[q * 4 + 3][r] = v.w;
             st4(&Ws[tid >> 4][(tid & 15) * 4], ldg4(Wt_sub + (size_t)(k0 + (tid >> 4)) * D + (tid & 15) * 4));
@@ -112,6 +151,8 @@ struct TcParams {
     const float* noise;  // mode 1
     const float* mask;   // mode 1
     float* ws_rows;
+    float* save_h;       // optional [N,64]: post-dropout activations (training)
+    int32_t batch_tables;  // 0: PI/PF are [I,64] tables indexed by item id; 1: PI is [P*Z,64] (slot order), PF [P,64]
     float* dbg_pre;      // optional [N,64]: raw accumulator (W_f·eps), for tests
     int32_t* err_flag;
     int64_t n_rows;
@@ -246,8 +287,8 @@ __global__ void __launch_bounds__(TC_NT, 2) k_row_scores_tc(const TcParams prm) 
         const int32_t u = checked_id(prm.X[2 * p], prm.n_users, prm.err_flag);
         const int32_t fi = checked_id(prm.X[2 * p + 1], prm.n_items, prm.err_flag);
         const int32_t it = (z == 0) ? fi : checked_id(prm.sample_item[p * prm.S + (z - 1)], prm.n_items, prm.err_flag);
-        const float* pi = prm.PI + (size_t)it * D;
-        const float* pf = prm.PF + (size_t)fi * D;
+        const float* pi = prm.PI + (size_t)(prm.batch_tables ? (p * (prm.S + 1) + z) : (int64_t)it) * D;
+        const float* pf = prm.PF + (size_t)(prm.batch_tables ? p : (int64_t)fi) * D;
         const float* eu = prm.E_user + (size_t)u * D;
         const RngKey key_drop = resolve_rng_key(prm.rng, DOMAIN_DROPOUT);
         float dot = 0.f;
@@ -283,6 +324,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_row_scores_tc(const TcParams prm) 
                     const float4 m = dropout_quad(key_drop, (uint32_t)grow, (uint32_t)(col >> 2), prm.keep_prob, prm.drop_scale);
                     h0 *= m.x; h1 *= m.y; h2 *= m.z; h3 *= m.w;
                 }
+                if (prm.save_h != nullptr && valid) st4(prm.save_h + (size_t)grow * D + col, make_float4(h0, h1, h2, h3));
                 dot = fmaf(h0, e.x, dot);
                 dot = fmaf(h1, e.y, dot);
                 dot = fmaf(h2, e.z, dot);
@@ -311,6 +353,14 @@ extern "C" int64_t dccf_tc_operand_floats(int32_t feat_dim) {
     return (int64_t)(feat_dim / TC_KC) * (2 * TC_B_BYTES / 4);
 }
 
+static void fill_job(TableJob& j, const float* X, int64_t n, int Kx, const float* Wt_sub, const float* bias, float* out,
+                     int mode, const dccf_dims* dims, const int64_t* Xids, const int64_t* sample_item, int32_t& blocks) {
+    j.X = X; j.n = n; j.Kx = Kx; j.Wt_sub = Wt_sub; j.bias = bias; j.out = out;
+    j.src.mode = mode; j.src.Z = dims->n_samples + 1; j.src.S = dims->n_samples; j.src.n_items = dims->n_items;
+    j.src.X = Xids; j.src.sample_item = sample_item;
+    j.block_lo = blocks; j.block_n = (int32_t)((n + 63) / 64); blocks += j.block_n;
+}
+
 extern "C" int dccf_tc_prepare(const dccf_dims* dims, const float* E_item, const float* Feat, const float* W,
                                const float* b, float* ws_wt, float* PI, float* PF, float* gB, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -320,25 +370,68 @@ extern "C" int dccf_tc_prepare(const dccf_dims* dims, const float* E_item, const
     const int F = dims->feat_dim, K = D + F;
     launch_transpose_w(W, ws_wt, K, stream);
     DCCF_CHECK_LAUNCH("k_transpose_w");
-    const unsigned grid = (unsigned)((dims->n_items + 63) / 64);
-    k_table_gemm<<<grid, 256, 0, stream>>>(E_item, dims->n_items, D, ws_wt, nullptr, PI);
-    DCCF_CHECK_LAUNCH("k_table_gemm(PI)");
-    k_table_gemm<<<grid, 256, 0, stream>>>(Feat, dims->n_items, F, ws_wt + (size_t)D * D, b, PF);
-    DCCF_CHECK_LAUNCH("k_table_gemm(PF)");
+    TableJobs jobs;
+    int32_t blocks = 0;
+    fill_job(jobs.job[0], E_item, dims->n_items, D, ws_wt, nullptr, PI, 0, dims, nullptr, nullptr, blocks);
+    fill_job(jobs.job[1], Feat, dims->n_items, F, ws_wt + (size_t)D * D, b, PF, 0, dims, nullptr, nullptr, blocks);
+    jobs.n_jobs = 2;
+    k_table_gemm<<<(unsigned)blocks, 256, 0, stream>>>(jobs);
+    DCCF_CHECK_LAUNCH("k_table_gemm");
     k_prep_wf<<<96, 256, 0, stream>>>(W, F, gB);
     DCCF_CHECK_LAUNCH("k_prep_wf");
     return DCCF_OK;
+}
+
+static int tc_launch(const dccf_dims* dims, const float* E_user, const float* PI, const float* PF, const float* gB,
+                     int batch_tables, const dccf_expo* expo, const int64_t* X, const int64_t* sample_item,
+                     int64_t n_pairs, const dccf_rng* rng, float* out_pred, float* ws_rows, float* save_h, float* save_w,
+                     float* dbg_pre, int32_t* err_flag, cudaStream_t stream);
+
+extern "C" int dccf_score_fwd_tc_train(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
+                                       const float* W, const float* b, const dccf_expo* expo, const int64_t* X,
+                                       const int64_t* sample_item, int64_t n_pairs, const dccf_rng* rng, float* out_pred,
+                                       float* ws_rows, float* ws_wt, float* ws_pi, float* ws_pf, float* ws_gB,
+                                       float* save_h, float* save_w, int32_t* err_flag, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DCCF_CHECK_ARG(dims && expo && rng && E_user && E_item && Feat && W && b && X && out_pred && ws_rows && ws_wt && ws_pi &&
+                       ws_pf && ws_gB, "dccf_score_fwd_tc_train: null argument");
+    DCCF_CHECK_ARG(dims->dim == D, "dccf_score_fwd_tc_train: dim=%d but this build has D=%d", dims->dim, D);
+    DCCF_CHECK_ARG(dims->feat_dim > 0 && dims->feat_dim % 64 == 0, "dccf_score_fwd_tc_train: feat_dim=%d must be a positive multiple of 64", dims->feat_dim);
+    DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item, "dccf_score_fwd_tc_train: sample_item is null");
+    if (n_pairs <= 0) return DCCF_OK;
+    const int F = dims->feat_dim, K = D + F, Z = dims->n_samples + 1;
+    launch_transpose_w(W, ws_wt, K, stream);
+    DCCF_CHECK_LAUNCH("k_transpose_w");
+    // the noise-free terms only for the rows of this batch: PI per (pair, slot), PF per pair
+    TableJobs jobs;
+    int32_t blocks = 0;
+    fill_job(jobs.job[0], E_item, n_pairs * Z, D, ws_wt, nullptr, ws_pi, 1, dims, X, sample_item, blocks);
+    fill_job(jobs.job[1], Feat, n_pairs, F, ws_wt + (size_t)D * D, b, ws_pf, 2, dims, X, sample_item, blocks);
+    jobs.n_jobs = 2;
+    k_table_gemm<<<(unsigned)blocks, 256, 0, stream>>>(jobs);
+    DCCF_CHECK_LAUNCH("k_table_gemm");
+    k_prep_wf<<<96, 256, 0, stream>>>(W, F, ws_gB);
+    DCCF_CHECK_LAUNCH("k_prep_wf");
+    return tc_launch(dims, E_user, ws_pi, ws_pf, ws_gB, 1, expo, X, sample_item, n_pairs, rng, out_pred, ws_rows, save_h,
+                     save_w, nullptr, err_flag, stream);
 }
 
 extern "C" int dccf_score_fwd_tc(const dccf_dims* dims, const float* E_user, const float* PI, const float* PF,
                                  const float* gB, const dccf_expo* expo, const int64_t* X, const int64_t* sample_item,
                                  int64_t n_pairs, const dccf_rng* rng, float* out_pred, float* ws_rows, float* dbg_pre,
                                  int32_t* err_flag, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
     DCCF_CHECK_ARG(dims && expo && rng, "dccf_score_fwd_tc: null struct argument");
+    DCCF_CHECK_ARG(E_user && PI && PF && gB && X && out_pred && ws_rows, "dccf_score_fwd_tc: null buffer");
+    return tc_launch(dims, E_user, PI, PF, gB, 0, expo, X, sample_item, n_pairs, rng, out_pred, ws_rows, nullptr, nullptr,
+                     dbg_pre, err_flag, (cudaStream_t)stream_);
+}
+
+static int tc_launch(const dccf_dims* dims, const float* E_user, const float* PI, const float* PF, const float* gB,
+                     int batch_tables, const dccf_expo* expo, const int64_t* X, const int64_t* sample_item,
+                     int64_t n_pairs, const dccf_rng* rng, float* out_pred, float* ws_rows, float* save_h, float* save_w,
+                     float* dbg_pre, int32_t* err_flag, cudaStream_t stream) {
     DCCF_CHECK_ARG(dims->dim == D, "dccf_score_fwd_tc: dim=%d but this build has D=%d", dims->dim, D);
     DCCF_CHECK_ARG(dims->feat_dim > 0 && dims->feat_dim % 64 == 0, "dccf_score_fwd_tc: feat_dim=%d must be a positive multiple of 64", dims->feat_dim);
-    DCCF_CHECK_ARG(E_user && PI && PF && gB && X && out_pred && ws_rows, "dccf_score_fwd_tc: null buffer");
     DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item, "dccf_score_fwd_tc: sample_item is null");
     DCCF_CHECK_ARG(rng->noise_mode == 1 || rng->noise_mode == 2, "dccf_score_fwd_tc: needs feature noise (mode 1 or 2); without noise use dccf_score_fwd");
     DCCF_CHECK_ARG(rng->noise_mode != 1 || rng->noise, "dccf_score_fwd_tc: noise_mode 1 needs a noise tensor");
@@ -350,7 +443,8 @@ extern "C" int dccf_score_fwd_tc(const dccf_dims* dims, const float* E_user, con
 
     TcParams prm;
     prm.E_user = E_user; prm.PI = PI; prm.PF = PF; prm.gB = gB; prm.X = X; prm.sample_item = sample_item;
-    prm.noise = rng->noise; prm.mask = rng->mask; prm.ws_rows = ws_rows; prm.dbg_pre = dbg_pre; prm.err_flag = err_flag;
+    prm.noise = rng->noise; prm.mask = rng->mask; prm.ws_rows = ws_rows; prm.save_h = save_h; prm.batch_tables = batch_tables;
+    prm.dbg_pre = dbg_pre; prm.err_flag = err_flag;
     prm.n_rows = n_rows; prm.n_users = dims->n_users; prm.n_items = dims->n_items; prm.F = dims->feat_dim;
     prm.S = dims->n_samples; prm.A = dims->n_attr; prm.R = R; prm.mask_mode = rng->mask_mode;
     prm.noise_std = rng->noise_std; prm.keep_prob = 1.0f - rng->p_drop;
@@ -372,7 +466,7 @@ extern "C" int dccf_score_fwd_tc(const dccf_dims* dims, const float* E_user, con
     if (rng->noise_mode == 1) k_row_scores_tc<1><<<grid, TC_NT, TC_SMEM_BYTES, stream>>>(prm);
     else k_row_scores_tc<2><<<grid, TC_NT, TC_SMEM_BYTES, stream>>>(prm);
     DCCF_CHECK_LAUNCH("k_row_scores_tc");
-    launch_backdoor(expo, X, sample_item, n_pairs, dims, ws_rows, out_pred, nullptr, err_flag, stream);
+    launch_backdoor(expo, X, sample_item, n_pairs, dims, ws_rows, out_pred, save_w, err_flag, stream);
     DCCF_CHECK_LAUNCH("k_backdoor");
     return DCCF_OK;
 }

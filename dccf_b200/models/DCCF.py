@@ -222,6 +222,7 @@ class DCCF(DMF):
     # evaluation batches with feature noise go to the tcgen05 scorer (dccf_score_fwd_tc) when they are large
     # enough to fill the machine; training steps and noise-free scoring use the FP32 SIMT kernels
     use_tensor_cores = True
+    use_tensor_cores_train = True      # the forward of a training step too (batch-local projections)
     tc_min_rows = 128 * 148
 
     def _tc_tables(self):
@@ -266,6 +267,16 @@ class DCCF(DMF):
         if save:
             call['save_h'] = save_h = torch.empty((N, D), dtype=torch.float32, device=dev)
             call['save_w'] = save_w = torch.empty((P, Z), dtype=torch.float32, device=dev)
+            if self.use_tensor_cores and self.use_tensor_cores_train and call['rng'].noise_mode != 0:
+                kernels.score_fwd_tc_train(
+                    self._dims(), self.uid_embeddings.weight.data, self.iid_embeddings.weight.data,
+                    self.feature_embedding, self.mlp[0].weight.data, self.mlp[0].bias.data, self._expo(), call['X'],
+                    call['sample_item'], call['rng'], pred, ws_rows, ws_wt,
+                    self._buf('ws_pi', (P * Z, D), torch.float32), self._buf('ws_pf', (P, D), torch.float32),
+                    self._buf('ws_gB', (kernels.tc_operand_floats(K - D),), torch.float32), save_h, save_w,
+                    self._err_flag)
+                call['pred'] = pred
+                return pred
         kernels.score_fwd(self._dims(), self.uid_embeddings.weight.data, self.iid_embeddings.weight.data,
                           self.feature_embedding, self.mlp[0].weight.data, self.mlp[0].bias.data, self._expo(),
                           call['X'], call['sample_item'], call['rng'], pred, ws_rows, ws_wt, save_h, save_w,
@@ -319,6 +330,16 @@ class DCCF(DMF):
         else:
             prediction = self._launch_fwd(call, save=False)
         return {'prediction': prediction, 'check': [('prediction', prediction)]}
+
+    def draw_confounders(self, n_pairs):
+        """The confounder draw of one predict call — `torch.randint(item_num, (P, S))` on the torch CPU generator
+        exactly as src/models/DCCF.py:72 — into pinned memory.  A caller that knows its next batch (the runner's
+        fit loop) draws it right after launching the current step, so the host generator overlaps the device;
+        the generator is consumed in the same order as without the prefetch."""
+        buf = torch.empty((n_pairs, self.sample_num), dtype=torch.int64, pin_memory=torch.cuda.is_available())
+        if self.sample_num > 0 and n_pairs > 0:
+            torch.randint(self.item_num, (n_pairs, self.sample_num), out=buf)
+        return buf
 
     def predict_many(self, feed_dicts, depth=2):
         """Predictions for a list of feed dicts (an evaluation pass).  Identical to calling `predict` on each

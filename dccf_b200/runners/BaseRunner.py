@@ -182,10 +182,20 @@ class BaseRunner(object):
         fused = hasattr(model, 'train_step') and not isinstance(model.optimizer, torch.optim.Optimizer)
         accumulate_size = 0
         output_dict = None
+        if fused and hasattr(model, 'draw_confounders') and batches:
+            # forward + (loss + l2) backward + clip + step in one go: the reference steps on every batch
+            # (accumulate_size >= batch_size always holds for its batch layout, BaseRunner.py:176,186-188).
+            # The confounder draw of batch k+1 (torch CPU generator, DCCF.py:72) is made while batch k runs.
+            draw = model.draw_confounders(batches[0]['X'].shape[0])
+            for k, batch in enumerate(self._bar(batches, desc='Epoch %5d' % (epoch + 1))):
+                fd = dict(batch)
+                fd['sample_item'] = draw
+                output_dict = model.train_step(fd)
+                if k + 1 < len(batches):
+                    draw = model.draw_confounders(batches[k + 1]['X'].shape[0])
+            batches = []
         for batch in self._bar(batches, desc='Epoch %5d' % (epoch + 1)):
             if fused:
-                # forward + (loss + l2) backward + clip + step in one go: the reference steps on every batch
-                # (accumulate_size >= batch_size always holds for its batch layout, BaseRunner.py:176,186-188)
                 output_dict = model.train_step(batch)
                 continue
             accumulate_size += len(batch['Y'])
