@@ -14,7 +14,7 @@
 // the N rows) and write a partial 64x64 tile of gW (no atomics — the Adam kernel sums the splits
 // in a fixed order); CTAs [n_gw, n_gw+n_rec) produce the per-pair embedding-gradient records
 // with warp-shuffle reductions; the last CTA computes the scalar loss.
-#include "bwd_common.cuh"
+#include "common.cuh"
 
 namespace dccf {
 
@@ -22,6 +22,53 @@ constexpr int BWD_NT = 128;     // threads per CTA
 constexpr int BWD_RC = 16;      // rows per staged chunk
 constexpr int BWD_CW = 64;      // W columns per CTA
 constexpr int BWD_WARPS = BWD_NT / 32;
+
+struct BwdParams {
+    const float* E_user;
+    const float* E_item;
+    const float* Feat;
+    const float* W;  // [D, D+F] row-major
+    const int64_t* X;
+    const int64_t* sample_item;
+    const float* Y;
+    const float* noise;  // mode 1
+    const float* mask;   // mode 1
+    const float* pred;
+    const float* save_h;
+    const float* save_w;
+    float* out_loss;
+    float* gW_part;
+    float* gb_part;
+    float* gu_rec;
+    float* gi_rec;
+    int32_t* rec_keys_u;
+    int32_t* rec_keys_i;
+    int64_t n_pairs, n_rows;
+    int32_t n_users, n_items, F, S, A, Z, R;
+    int32_t noise_mode, mask_mode, loss_mode;
+    int32_t n_chunks;        // (D+F)/64
+    int32_t n_splits;        // row splits
+    int32_t rows_per_split;  // multiple of BWD_RC
+    int32_t n_gw, n_rec_ctas;
+    float noise_std, drop_scale, inv_A;
+    RngSpec rng;
+};
+
+// d loss / d pred[p]   (DCCF.py:116-125)
+__device__ __forceinline__ float dpred_of(const BwdParams& prm, int64_t p) {
+    if (prm.loss_mode == 0) {
+        const int64_t b = prm.n_pairs >> 1;
+        if (p >= 2 * b) return 0.f;  // odd tail never enters the loss
+        const bool is_pos = p < b;
+        const float d = is_pos ? (__ldg(prm.pred + p) - __ldg(prm.pred + p + b))
+                               : (__ldg(prm.pred + p - b) - __ldg(prm.pred + p));
+        const float sg = 1.f / (1.f + expf(-d));
+        const float g = -(1.f - sg);
+        return is_pos ? g : -g;
+    }
+    if (prm.loss_mode == 2) return __ldg(prm.Y + p);  // upstream gradient supplied by the caller (autograd)
+    return 2.f * (__ldg(prm.pred + p) - __ldg(prm.Y + p)) / (float)prm.n_pairs;
+}
 
 // ---------------------------------------------------------------------------------------------
 // role 1: partial gW tile.  CTA (chunk c, split s): acc[j][col] = sum_{r in split} dpre[r][j] * x[r][c*64+col]
@@ -252,7 +299,7 @@ __device__ void bwd_loss_role(const BwdParams& prm) {
 __global__ void __launch_bounds__(BWD_NT) k_bpr_bwd(const BwdParams prm) {
     const int b = blockIdx.x;
     if (b < prm.n_gw) {
-        bwd_gw_role(prm, b % prm.n_simt_chunks, b / prm.n_simt_chunks);
+        bwd_gw_role(prm, b % prm.n_chunks, b / prm.n_chunks);
     } else if (b < prm.n_gw + prm.n_rec_ctas) {
         bwd_record_role(prm, b - prm.n_gw);
     } else {
@@ -280,16 +327,11 @@ extern "C" int32_t dccf_bwd_splits(int64_t n_rows) {
     return bwd_splits_for(n_rows, 13);
 }
 
-namespace dccf {
-int launch_bwd_gw_tc(const BwdParams& prm, cudaStream_t stream);   // tc_bwd.cu
-}
-
-static int bpr_bwd_impl(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
-                        const float* W, const int64_t* X, const int64_t* sample_item, const float* Y,
-                        int64_t n_pairs, const dccf_rng* rng, int32_t loss_mode, const float* pred,
-                        const float* save_h, const float* save_w, float* out_loss, float* gW_part, float* gb_part,
-                        float* gu_rec, float* gi_rec, int32_t* rec_keys_u, int32_t* rec_keys_i, void* stream_,
-                        bool use_tc) {
+extern "C" int dccf_bpr_bwd(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
+                            const float* W, const int64_t* X, const int64_t* sample_item, const float* Y,
+                            int64_t n_pairs, const dccf_rng* rng, int32_t loss_mode, const float* pred,
+                            const float* save_h, const float* save_w, float* out_loss, float* gW_part, float* gb_part,
+                            float* gu_rec, float* gi_rec, int32_t* rec_keys_u, int32_t* rec_keys_i, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     DCCF_CHECK_ARG(dims && rng, "dccf_bpr_bwd: null struct argument");
     DCCF_CHECK_ARG(dims->dim == D, "dccf_bpr_bwd: dim=%d but this build has D=%d", dims->dim, D);
@@ -323,10 +365,7 @@ static int bpr_bwd_impl(const dccf_dims* dims, const float* E_user, const float*
     prm.n_splits = dccf_bwd_splits(prm.n_rows);
     const int64_t rps = (prm.n_rows + prm.n_splits - 1) / prm.n_splits;
     prm.rows_per_split = (int32_t)(((rps + BWD_RC - 1) / BWD_RC) * BWD_RC);
-    // tensor-core variant: the 768 feature columns of dW go to k_bwd_gw_tc, this kernel keeps the item chunk
-    use_tc = use_tc && (prm.F % 128 == 0);
-    prm.n_simt_chunks = use_tc ? 1 : prm.n_chunks;
-    prm.n_gw = prm.n_simt_chunks * prm.n_splits;
+    prm.n_gw = prm.n_chunks * prm.n_splits;
     prm.n_rec_ctas = (int32_t)((n_pairs + BWD_WARPS - 1) / BWD_WARPS);
     prm.noise_std = rng->noise_std;
     prm.drop_scale = (rng->p_drop < 1.0f) ? 1.0f / (1.0f - rng->p_drop) : 0.0f;
@@ -336,29 +375,5 @@ static int bpr_bwd_impl(const dccf_dims* dims, const float* E_user, const float*
     const unsigned grid = (unsigned)(prm.n_gw + prm.n_rec_ctas + 1);
     k_bpr_bwd<<<grid, BWD_NT, 0, stream>>>(prm);
     DCCF_CHECK_LAUNCH("k_bpr_bwd");
-    if (use_tc) {
-        int rc = launch_bwd_gw_tc(prm, stream);
-        if (rc != DCCF_OK) return rc;
-        DCCF_CHECK_LAUNCH("k_bwd_gw_tc");
-    }
     return DCCF_OK;
-}
-
-extern "C" int dccf_bpr_bwd(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
-                            const float* W, const int64_t* X, const int64_t* sample_item, const float* Y,
-                            int64_t n_pairs, const dccf_rng* rng, int32_t loss_mode, const float* pred,
-                            const float* save_h, const float* save_w, float* out_loss, float* gW_part, float* gb_part,
-                            float* gu_rec, float* gi_rec, int32_t* rec_keys_u, int32_t* rec_keys_i, void* stream_) {
-    return bpr_bwd_impl(dims, E_user, E_item, Feat, W, X, sample_item, Y, n_pairs, rng, loss_mode, pred, save_h, save_w,
-                        out_loss, gW_part, gb_part, gu_rec, gi_rec, rec_keys_u, rec_keys_i, stream_, false);
-}
-
-extern "C" int dccf_bpr_bwd_tc(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
-                               const float* W, const int64_t* X, const int64_t* sample_item, const float* Y,
-                               int64_t n_pairs, const dccf_rng* rng, int32_t loss_mode, const float* pred,
-                               const float* save_h, const float* save_w, float* out_loss, float* gW_part,
-                               float* gb_part, float* gu_rec, float* gi_rec, int32_t* rec_keys_u, int32_t* rec_keys_i,
-                               void* stream_) {
-    return bpr_bwd_impl(dims, E_user, E_item, Feat, W, X, sample_item, Y, n_pairs, rng, loss_mode, pred, save_h, save_w,
-                        out_loss, gW_part, gb_part, gu_rec, gi_rec, rec_keys_u, rec_keys_i, stream_, true);
 }

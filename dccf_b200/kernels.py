@@ -133,15 +133,14 @@ def bwd_splits(n_rows):
 
 
 def bpr_bwd(dims, E_user, E_item, Feat, W, X, sample_item, Y, rng, loss_mode, pred, save_h, save_w, out_loss, gW_part,
-            gb_part, gu_rec, gi_rec, rec_keys_u, rec_keys_i, tensor_cores=False):
+            gb_part, gu_rec, gi_rec, rec_keys_u, rec_keys_i):
     lib = _lib.load()
     n_pairs = X.shape[0]
-    fn = lib.dccf_bpr_bwd_tc if tensor_cores else lib.dccf_bpr_bwd
-    check(fn(ctypes.byref(dims), ptr(E_user), ptr(E_item), ptr(Feat), ptr(W), ptr(X), ptr(sample_item),
+    check(lib.dccf_bpr_bwd(ctypes.byref(dims), ptr(E_user), ptr(E_item), ptr(Feat), ptr(W), ptr(X), ptr(sample_item),
                            ptr(Y), n_pairs, ctypes.byref(rng), int(loss_mode), ptr(pred), ptr(save_h), ptr(save_w),
                            ptr(out_loss), ptr(gW_part), ptr(gb_part), ptr(gu_rec), ptr(gi_rec), ptr(rec_keys_u),
                            ptr(rec_keys_i), stream_ptr()), 'dccf_bpr_bwd')
-    LAUNCHES[0] += (2 if tensor_cores else 1) if n_pairs > 0 else 0
+    LAUNCHES[0] += 1 if n_pairs > 0 else 0
 
 
 def adam_sweep(table, m, v, rec_keys, rec_grads, n_rec, head, nxt, hp):

@@ -222,11 +222,7 @@ class DCCF(DMF):
     # evaluation batches with feature noise go to the tcgen05 scorer (dccf_score_fwd_tc) when they are large
     # enough to fill the machine; training steps and noise-free scoring use the FP32 SIMT kernels
     use_tensor_cores = True
-    # forward of a training step on the tensor cores: correct, but a 256-pair step is only 44 row tiles and the
-    # per-tile noise generation then runs on 44 of the 148 SMs — measured slower (0.186 ms/step) than the FP32
-    # split-K kernel that spreads over all SMs (0.138 ms/step); kept off
-    use_tensor_cores_train = False
-    use_tensor_cores_bwd = True        # d loss/d W_f: (feature block) x (row split) CTAs cover the machine
+    use_tensor_cores_train = True      # the forward of a training step too (batch-local projections)
     tc_min_rows = 128 * 148
 
     def _tc_tables(self):
@@ -312,8 +308,7 @@ class DCCF(DMF):
         kernels.bpr_bwd(self._dims(), self.uid_embeddings.weight.data, self.iid_embeddings.weight.data,
                         self.feature_embedding, self.mlp[0].weight.data, call['X'], call['sample_item'], Y,
                         call['rng'], loss_mode, call['pred'], call['save_h'], call['save_w'], rec['loss'],
-                        rec['gW_part'], rec['gb_part'], rec['gu_rec'], rec['gi_rec'], rec['keys_u'], rec['keys_i'],
-                        tensor_cores=self.use_tensor_cores and self.use_tensor_cores_bwd)
+                        rec['gW_part'], rec['gb_part'], rec['gu_rec'], rec['gi_rec'], rec['keys_u'], rec['keys_i'])
         return rec
 
     def check_ids(self):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 12
+#define DCCF_ABI_VERSION 11
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -155,16 +155,6 @@ int dccf_bpr_bwd(const dccf_dims* dims, const float* E_user, const float* E_item
                  const float* pred, const float* save_h, const float* save_w, float* out_loss,
                  float* gW_part, float* gb_part, float* gu_rec, float* gi_rec,
                  int32_t* rec_keys_u, int32_t* rec_keys_i, void* stream);
-
-/* Same contract; the 768 feature columns of d loss/d W are computed on the tcgen05 tensor cores (3xTF32,
- * reduction over the predictor rows as the MMA K dimension), the rest as in dccf_bpr_bwd.  Two launches.
- * Falls back to the single-kernel path when feat_dim is not a multiple of 128. */
-int dccf_bpr_bwd_tc(const dccf_dims* dims, const float* E_user, const float* E_item,
-                    const float* Feat, const float* W, const int64_t* X, const int64_t* sample_item,
-                    const float* Y, int64_t n_pairs, const dccf_rng* rng, int32_t loss_mode,
-                    const float* pred, const float* save_h, const float* save_w, float* out_loss,
-                    float* gW_part, float* gb_part, float* gu_rec, float* gi_rec,
-                    int32_t* rec_keys_u, int32_t* rec_keys_i, void* stream);
 
 /* ---- (c) part 2: l2 + clip + Adam, dense over every row --------------------------------- */
 /* Replaces model.l2()*l2 (BaseRunner.py:181, BaseModel.py:179-187), clip_grad_value_
