@@ -222,7 +222,10 @@ class DCCF(DMF):
     # evaluation batches with feature noise go to the tcgen05 scorer (dccf_score_fwd_tc) when they are large
     # enough to fill the machine; training steps and noise-free scoring use the FP32 SIMT kernels
     use_tensor_cores = True
-    use_tensor_cores_train = True      # the forward of a training step too (batch-local projections)
+    # forward of a training step on the tensor cores (dccf_score_fwd_tc_train): correct (tested), but a 256-pair
+    # step is only 44 row tiles, so the per-tile noise generation runs on 44 of the 148 SMs — measured slower
+    # (0.186 ms/step) than the FP32 split-K kernel that spreads over all SMs (0.138 ms/step).  Off by default.
+    use_tensor_cores_train = False
     tc_min_rows = 128 * 148
 
     def _tc_tables(self):
