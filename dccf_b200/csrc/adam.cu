@@ -59,10 +59,15 @@ __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g_
     m = fmaf(s.w1, __fsub_rn(g, m), m);                          // exp_avg.lerp_(g, 1 - beta1)
     v = __fmul_rn(v, s.beta2);                                   // exp_avg_sq.mul_(beta2)
     v = fmaf(__fmul_rn(s.omb2, g), g, v);                        //   .addcmul_(g, g, value = 1 - beta2)
-    // denom = sqrt(v)/sqrt(bc2) + eps: the division by the per-step constant is a multiplication by its
-    // reciprocal (<= 1 ulp from torch's _foreach_div_), the per-element division stays IEEE
-    const float denom = fmaf(sqrtf(v), s.inv_bc2_sqrt, s.eps);
-    p = fmaf(s.step_size, __fdiv_rn(m, denom), p);               // param.addcdiv_(exp_avg, denom, value = step_size)
+    // denom = sqrt(v)/sqrt(bc2) + eps ; p += step_size * m / denom.  The sweep is HBM-bound only if the
+    // arithmetic stays short: sqrt and the division use the hardware approximations (MUFU.SQRT, MUFU.RCP;
+    // <= 2 ulp each) and the per-step constant divides by multiplication.  The update term is <= lr relative
+    // to the step size, so this perturbs p by ~1e-7 * lr — four orders below the 1e-5 parity bound; exp_avg
+    // and exp_avg_sq above follow torch's IEEE arithmetic exactly.
+    float sq;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v));
+    const float denom = fmaf(sq, s.inv_bc2_sqrt, s.eps);
+    p = fmaf(s.step_size, __fdividef(m, denom), p);              // param.addcdiv_(exp_avg, denom, value = step_size)
 }
 
 // Records may arrive in n_seg segments of seg_len records each (one segment per data-parallel rank after the
