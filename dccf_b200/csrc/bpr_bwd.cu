@@ -307,11 +307,12 @@ __global__ void __launch_bounds__(BWD_NT) k_bpr_bwd(const BwdParams prm) {
     }
 }
 
-// number of row splits for N rows: enough CTAs to put about four on each of the 148 SMs, at least 64 rows each
+// number of row splits for N rows: enough CTAs to cover the 148 SMs about twice, at least 64 rows each
+// (four per SM was measured: no faster, and the Adam kernel then reads twice the partial sums)
 static int32_t bwd_splits_for(int64_t n_rows, int n_chunks) {
     if (n_rows <= 0) return 1;
     const int64_t max_by_rows = (n_rows + 63) / 64;
-    int64_t want = (4 * 148 + n_chunks - 1) / n_chunks;   // ~4 CTAs of 4 warps per SM hide the staging latency
+    int64_t want = (2 * 148 + n_chunks - 1) / n_chunks;
     if (want > max_by_rows) want = max_by_rows;
     if (want < 1) want = 1;
     return (int32_t)want;
