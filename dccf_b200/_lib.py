@@ -11,7 +11,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libdccf_b200.so')
-ABI_VERSION = 11
+ABI_VERSION = 12
 DIM = 64
 
 
@@ -87,6 +87,7 @@ _SIGNATURES = {
                                        ctypes.POINTER(Adam), _P]),
     'dccf_adam_step': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(AdamTensor),
                                       ctypes.c_int32, ctypes.POINTER(Adam), _P]),
+    'dccf_stage_batch': (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, _P]),
     'dccf_state_advance': (ctypes.c_int, [_P, _P, ctypes.c_uint64, _P]),
     'dccf_dp_push': (ctypes.c_int, [_P, ctypes.c_int64, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, _P, _P, _P]),
     'dccf_dp_wait': (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int64, _P, _P]),

@@ -300,6 +300,21 @@ __global__ void k_state_advance(int32_t* step_dev, uint64_t* offset_dev, uint64_
     }
 }
 
+// Copy batch number *cursor of a device-resident epoch ([n_batches, P, 2] ids and [n_batches, P, S] confounder
+// draws, base addresses read from device memory) into the step graph's static input buffers, then advance
+// the cursor: a replayed graph walks through the epoch without any host-side copy.
+__global__ void __launch_bounds__(256) k_stage_batch(const uint64_t* __restrict__ epoch_ptrs, int64_t* cursor,
+                                                     int64_t n_x, int64_t n_s, int64_t* __restrict__ X_out,
+                                                     int64_t* __restrict__ si_out) {
+    const int64_t b = *cursor;
+    const int64_t* X_src = reinterpret_cast<const int64_t*>(epoch_ptrs[0]) + b * n_x;
+    const int64_t* s_src = reinterpret_cast<const int64_t*>(epoch_ptrs[1]) + b * n_s;
+    for (int64_t i = threadIdx.x; i < n_x; i += blockDim.x) X_out[i] = X_src[i];
+    for (int64_t i = threadIdx.x; i < n_s; i += blockDim.x) si_out[i] = s_src[i];
+    __syncthreads();
+    if (threadIdx.x == 0) *cursor = b + 1;
+}
+
 static int check_hp(const dccf_adam* hp, AdamHost* out, const char* who) {
     DCCF_CHECK_ARG(hp != nullptr, "%s: null hyper-parameter struct", who);
     DCCF_CHECK_ARG(hp->step_dev != nullptr || hp->step >= 1, "%s: step must be >= 1 (got %d)", who, hp->step);
@@ -445,5 +460,16 @@ extern "C" int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, c
         k_adam_all<<<(unsigned)blocks, 256, 0, stream>>>(a);
         DCCF_CHECK_LAUNCH("k_adam_all");
     }
+    return DCCF_OK;
+}
+
+extern "C" int dccf_stage_batch(const uint64_t* epoch_ptrs_dev, int64_t* cursor_dev, int64_t n_pairs, int32_t n_samples,
+                                int64_t* X_out, int64_t* sample_item_out, void* stream_) {
+    DCCF_CHECK_ARG(epoch_ptrs_dev && cursor_dev && X_out && (n_samples == 0 || sample_item_out), "dccf_stage_batch: null argument");
+    DCCF_CHECK_ARG(n_pairs >= 0 && n_samples >= 0, "dccf_stage_batch: negative size");
+    if (n_pairs == 0) return DCCF_OK;
+    k_stage_batch<<<1, 256, 0, (cudaStream_t)stream_>>>(epoch_ptrs_dev, cursor_dev, n_pairs * 2, n_pairs * n_samples, X_out,
+                                                         sample_item_out);
+    DCCF_CHECK_LAUNCH("k_stage_batch");
     return DCCF_OK;
 }

@@ -204,6 +204,13 @@ def adam_step(tables, dense, hp):
     LAUNCHES[0] += 2 if any(t.n_seg * t.seg_len > 0 for t in tables) else 1
 
 
+def stage_batch(epoch_ptrs_dev, cursor_dev, n_pairs, n_samples, X_out, si_out):
+    lib = _lib.load()
+    check(lib.dccf_stage_batch(ptr(epoch_ptrs_dev), ptr(cursor_dev), int(n_pairs), int(n_samples), ptr(X_out), ptr(si_out),
+                               stream_ptr()), 'dccf_stage_batch')
+    LAUNCHES[0] += 1
+
+
 def state_advance(step_dev, offset_dev, offset_inc=1):
     lib = _lib.load()
     check(lib.dccf_state_advance(ptr(step_dev), ptr(offset_dev), int(offset_inc), stream_ptr()), 'dccf_state_advance')

@@ -495,20 +495,72 @@ class DCCF(DMF):
 
     # ---- CUDA-graph replay of the fused step -----------------------------------------------------
     use_cuda_graph = True
-    def _train_step_graph(self, feed_dict, opt):
+    def _build_step_graph(self, P, rank_mode, p_drop, opt, staged):
+        """Capture forward + backward + (exchange) + Adam + counter advance for a batch of P pairs.  `staged`:
+        the graph's first node copies the batch from a device-resident epoch (dccf_stage_batch)."""
+        dev = self.uid_embeddings.weight.device
+        S = self.sample_num
+        g = {'X': torch.zeros((P, 2), dtype=torch.int64, device=dev),
+             'si': torch.zeros((P, S), dtype=torch.int64, device=dev),
+             'Y': torch.zeros(P, dtype=torch.float32, device=dev),
+             'step_dev': torch.zeros(1, dtype=torch.int32, device=dev),
+             'offset_dev': torch.zeros(1, dtype=torch.int64, device=dev), 'synced': None}
+        if staged:
+            g['epoch_ptrs'] = torch.zeros(2, dtype=torch.int64, device=dev)
+            g['cursor'] = torch.zeros(1, dtype=torch.int64, device=dev)
+        seed = self.random_seed
+        if self._dp is not None:
+            seed = (seed + 0x9E3779B97F4A7C15 * self._dp['rank']) & 0xffffffffffffffff
+        rng = kernels.make_rng(noise_std=self.std, p_drop=p_drop, seed=seed, offset_dev=g['offset_dev'],
+                               generate_noise=self.std > 0, generate_mask=p_drop > 0)
+        call = {'X': g['X'], 'sample_item': g['si'], 'rng': rng, 'noise': None, 'mask': None, 'P': P,
+                'N': P * (S + 1) * self.attribute_num}
+        hp = kernels.make_adam(opt.lr, opt.l2, opt.weight_decay, step=1, step_dev=g['step_dev'], beta1=opt.beta1,
+                               beta2=opt.beta2, eps=opt.eps, clip=opt.clip)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        launches_before = kernels.LAUNCHES[0]
+        with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+            if staged:
+                kernels.stage_batch(g['epoch_ptrs'], g['cursor'], P, S, g['X'], g['si'])
+            pred = self._launch_fwd(call, save=True)
+            rec = self._launch_bwd(call, loss_mode=0 if rank_mode == 1 else 1, Y=g['Y'] if rank_mode != 1 else None)
+            loss = self._apply_adam(rec, P, opt, hp).clone()
+            kernels.state_advance(g['step_dev'], g['offset_dev'], 1)
+        g.update({'graph': graph, 'pred': pred, 'loss': loss, 'call': call,
+                  'n_kernels': kernels.LAUNCHES[0] - launches_before})
+        kernels.LAUNCHES[0] = launches_before           # capturing launched nothing
+        return g
+
+    def _replay(self, g, opt):
+        self._rng_offset += 1
+        opt.step_count += 1
+        self._param_epoch += 1
+        if g['synced'] != (opt.step_count, self._rng_offset):
+            # device counters out of step with the host mirrors (eager steps or predict calls ran in between)
+            g['step_dev'].fill_(opt.step_count)
+            g['offset_dev'].fill_(self._rng_offset)
+        g['graph'].replay()
+        kernels.LAUNCHES[0] += g['n_kernels']
+        g['synced'] = (opt.step_count + 1, self._rng_offset + 1)
+        return {'prediction': g['pred'], 'check': [('prediction', g['pred'])], 'loss': g['loss']}
+
+    def _graph_allowed(self, P):
         if self._dp is not None:
             # graph capture needs the exchange to be plain kernels (peer-memory mode); an NCCL all-gather
             # inside the captured step deadlocked on 2 x B200 with torch 2.11 / NCCL 2.28
-            ex = self._exchange_for(feed_dict['X'].shape[0])
-            if ex.mode != 'p2p':
-                return None
-        self._check_ready()
-        dev = self.uid_embeddings.weight.device
+            return self._exchange_for(P).mode == 'p2p'
+        return True
+
+    def _train_step_graph(self, feed_dict, opt):
         X = feed_dict['X']
         P = X.shape[0]
+        if not self._graph_allowed(P):
+            return None
+        self._check_ready()
         rank_mode = int(feed_dict['rank'])
         p_drop = float(feed_dict.get('dropout', 0.0))
-        key = (P, rank_mode, p_drop, id(opt))
+        key = (P, rank_mode, p_drop, id(opt), False)
         graphs = self.__dict__.setdefault('_graphs', {})
         g = graphs.get(key)
         if g is None:
@@ -517,32 +569,7 @@ class DCCF(DMF):
             return None
         S = self.sample_num
         if g == 'warm':
-            g = {'X': torch.zeros((P, 2), dtype=torch.int64, device=dev),
-                 'si': torch.zeros((P, S), dtype=torch.int64, device=dev),
-                 'Y': torch.zeros(P, dtype=torch.float32, device=dev),
-                 'step_dev': torch.zeros(1, dtype=torch.int32, device=dev),
-                 'offset_dev': torch.zeros(1, dtype=torch.int64, device=dev), 'synced': None}
-            seed = self.random_seed
-            if self._dp is not None:
-                seed = (seed + 0x9E3779B97F4A7C15 * self._dp['rank']) & 0xffffffffffffffff
-            rng = kernels.make_rng(noise_std=self.std, p_drop=p_drop, seed=seed, offset_dev=g['offset_dev'],
-                                   generate_noise=self.std > 0, generate_mask=p_drop > 0)
-            call = {'X': g['X'], 'sample_item': g['si'], 'rng': rng, 'noise': None, 'mask': None, 'P': P,
-                    'N': P * (S + 1) * self.attribute_num}
-            hp = kernels.make_adam(opt.lr, opt.l2, opt.weight_decay, step=1, step_dev=g['step_dev'], beta1=opt.beta1,
-                                   beta2=opt.beta2, eps=opt.eps, clip=opt.clip)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            launches_before = kernels.LAUNCHES[0]
-            with torch.cuda.graph(graph, capture_error_mode='thread_local'):
-                pred = self._launch_fwd(call, save=True)
-                rec = self._launch_bwd(call, loss_mode=0 if rank_mode == 1 else 1, Y=g['Y'] if rank_mode != 1 else None)
-                loss = self._apply_adam(rec, P, opt, hp).clone()
-                kernels.state_advance(g['step_dev'], g['offset_dev'], 1)
-            g.update({'graph': graph, 'pred': pred, 'loss': loss, 'call': call,
-                      'n_kernels': kernels.LAUNCHES[0] - launches_before})
-            kernels.LAUNCHES[0] = launches_before           # capturing launched nothing
-            graphs[key] = g
+            g = graphs[key] = self._build_step_graph(P, rank_mode, p_drop, opt, staged=False)
         # inputs into the graph's static buffers (async copies on the current stream)
         Xs = X if torch.is_tensor(X) else torch.as_tensor(np.asarray(X))
         g['X'].copy_(Xs[:, :2] if Xs.shape[1] != 2 else Xs, non_blocking=True)
@@ -552,14 +579,48 @@ class DCCF(DMF):
         g['si'].copy_(si, non_blocking=True)
         if rank_mode != 1:
             g['Y'].copy_(feed_dict['Y'], non_blocking=True)
-        self._rng_offset += 1
-        opt.step_count += 1
-        self._param_epoch += 1
-        if g['synced'] != (opt.step_count, self._rng_offset):
-            # device counters out of step with the host mirrors (eager steps ran in between)
-            g['step_dev'].fill_(opt.step_count)
-            g['offset_dev'].fill_(self._rng_offset)
-        g['graph'].replay()
-        kernels.LAUNCHES[0] += g['n_kernels']
-        g['synced'] = (opt.step_count + 1, self._rng_offset + 1)
-        return {'prediction': g['pred'], 'check': [('prediction', g['pred'])], 'loss': g['loss']}
+        return self._replay(g, opt)
+
+    def begin_resident_epoch(self, X_epoch, sample_epoch, dropout, opt=None):
+        """Training over a device-resident epoch: X_epoch [n, P, 2] and sample_epoch [n, P, S] int64 CUDA tensors
+        (all batches of P pairs; the confounder block is ONE torch.randint(item_num, (n*P, S)) call, which yields
+        the same numbers as n per-batch calls on the same generator).  Returns a callable: each call runs the next
+        batch as one CUDA-graph launch — the batch is fetched by a kernel through a device-side cursor, so the
+        host does nothing per step but launch.  BPR (rank 1) only.  Returns None when graphs cannot be used."""
+        opt = opt or self.optimizer
+        if not isinstance(opt, FusedAdamState) or not self.use_cuda_graph:
+            return None
+        self._check_ready()
+        n, P = X_epoch.shape[0], X_epoch.shape[1]
+        if not self._graph_allowed(P) or n == 0:
+            return None
+        p_drop = float(dropout)
+        key = (P, 1, p_drop, id(opt), True)
+        graphs = self.__dict__.setdefault('_graphs', {})
+        state = {'next': 0}
+        if key not in graphs:
+            # the very first step runs kernel by kernel (loads every kernel before capture)
+            saved = self.use_cuda_graph
+            self.use_cuda_graph = False
+            try:
+                first = self.train_step({'X': X_epoch[0], 'rank': 1, 'train': True, 'dropout': p_drop,
+                                         'sample_item': sample_epoch[0]}, opt)
+            finally:
+                self.use_cuda_graph = saved
+            state['next'] = 1
+            state['first'] = first
+            graphs[key] = self._build_step_graph(P, 1, p_drop, opt, staged=True)
+        g = graphs[key]
+        g['epoch_ptrs'].copy_(torch.tensor([X_epoch.data_ptr(), sample_epoch.data_ptr()], dtype=torch.int64))
+        g['cursor'].fill_(state['next'])
+        g['keep'] = (X_epoch, sample_epoch)                 # the graph reads these buffers: keep them alive
+
+        def step():
+            if state['next'] >= n:
+                raise StopIteration('resident epoch exhausted')
+            state['next'] += 1
+            return self._replay(g, opt)
+
+        step.remaining = lambda: n - state['next']
+        step.first = state.get('first')
+        return step

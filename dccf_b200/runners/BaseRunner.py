@@ -182,6 +182,34 @@ class BaseRunner(object):
         fused = hasattr(model, 'train_step') and not isinstance(model.optimizer, torch.optim.Optimizer)
         accumulate_size = 0
         output_dict = None
+        if fused and hasattr(model, 'begin_resident_epoch') and len(batches) > 2 and data_processor.rank == 1 \
+                and batches[0]['X'].is_cuda:
+            # Equal-size batches run from a device-resident epoch: the confounder draws of all of them are ONE
+            # torch.randint call (same CPU-generator stream as the reference's per-batch calls, DCCF.py:72) and
+            # each step is a single CUDA-graph launch that fetches its batch through a device-side cursor.
+            P0 = batches[0]['X'].shape[0]
+            n_full = 0
+            while n_full < len(batches) and batches[n_full]['X'].shape[0] == P0:
+                n_full += 1
+            chunk = 1024
+            done = 0
+            while done < n_full:
+                m = min(chunk, n_full - done)
+                X_epoch = torch.stack([b['X'] for b in batches[done:done + m]])
+                draws = model.draw_confounders(m * P0).view(m, P0, model.sample_num)
+                step = model.begin_resident_epoch(X_epoch, draws.to(X_epoch.device, non_blocking=True), self.dropout)
+                if step is None:
+                    break
+                if step.first is not None:
+                    output_dict = step.first
+                while step.remaining() > 0:
+                    output_dict = step()
+                done += m
+            if done > 0:
+                output_dict = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in output_dict.items()
+                               if k != 'check'}
+                output_dict['check'] = [('prediction', output_dict['prediction'])]
+            batches = batches[done:]
         if fused and hasattr(model, 'draw_confounders') and batches:
             # forward + (loss + l2) backward + clip + step in one go: the reference steps on every batch
             # (accumulate_size >= batch_size always holds for its batch layout, BaseRunner.py:176,186-188).

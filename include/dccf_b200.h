@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 11
+#define DCCF_ABI_VERSION 12
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -213,6 +213,11 @@ typedef struct dccf_adam_tensor {
 } dccf_adam_tensor;
 int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
                    int32_t n_dense, const dccf_adam* hp, void* stream);
+/* First node of a captured training step that reads its inputs from a device-resident epoch:
+ * epoch_ptrs_dev = device array {address of X_epoch [n_batches,P,2], address of sample_epoch [n_batches,P,S]},
+ * cursor_dev = device int64 batch counter (copied batch *cursor, then incremented). */
+int dccf_stage_batch(const uint64_t* epoch_ptrs_dev, int64_t* cursor_dev, int64_t n_pairs, int32_t n_samples,
+                     int64_t* X_out, int64_t* sample_item_out, void* stream);
 /* step_dev[0] += 1 ; offset_dev[0] += offset_inc  (either pointer may be NULL) — the last node
  * of a captured training step, so that a replay sees t+1 and a fresh rng counter. */
 int dccf_state_advance(int32_t* step_dev, uint64_t* offset_dev, uint64_t offset_inc, void* stream);

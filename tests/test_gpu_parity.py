@@ -566,3 +566,35 @@ def test_predict_many_equals_sequential_predict():
         after = torch.randint(1000, (4,))
         outs.append(after.numpy())
     assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
+
+
+def test_resident_epoch_equals_step_by_step():
+    """The epoch-resident path (device-side batch cursor, one graph launch per step, one confounder draw for
+    the whole epoch) is bit-identical to feeding the same batches one by one."""
+    U, I, F, P, S, A, std, drop = 200, 300, 768, 64, 10, 2, 0.1, 0.2
+    params, X, _, _, _ = random_problem(8, U, I, F, P, S, A, 0.0, 0.0)
+    n = 5
+    Xs = np.stack([np.roll(X, t, axis=0) for t in range(n)])
+    Xs[:, P // 2:, 0] = Xs[:, :P // 2, 0]
+    outs = []
+    for resident in (False, True):
+        model = make_model(params, S, A, std)
+        model.optimizer = model.make_fused_optimizer(lr=1e-3, l2=1e-4)
+        torch.manual_seed(4242)
+        losses = []
+        if resident:
+            draws = model.draw_confounders(n * P).view(n, P, S)
+            step = model.begin_resident_epoch(torch.from_numpy(Xs).cuda(), draws.cuda(), drop)
+            losses.append(float(step.first['loss']))
+            while step.remaining() > 0:
+                losses.append(float(step()['loss']))
+        else:
+            for t in range(n):
+                fd = {'X': torch.from_numpy(Xs[t]).cuda(), 'rank': 1, 'train': True, 'dropout': drop,
+                      'Y': torch.zeros(P).cuda()}
+                losses.append(float(model.train_step(fd)['loss']))
+        outs.append((losses, model_params(model), torch.randint(1000, (3,)).numpy()))
+    assert outs[0][0] == outs[1][0]
+    assert np.array_equal(outs[0][2], outs[1][2])           # the CPU generator ends in the same state
+    for k in ('E_user', 'E_item', 'W', 'b'):
+        assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
