@@ -268,8 +268,8 @@ def bench_train(model, X_all, steps, warmup, world, flush):
         if i == warmup:
             barrier(world)
         t0 = time.perf_counter()
-        fd = {'X': X_pin[i].to(dev, non_blocking=True), 'Y': Y, 'rank': 1, 'train': True, 'dropout': DROPOUT,
-              'sample_item': draw}
+        fd = {'X': X_pin[i], 'Y': Y, 'rank': 1, 'train': True, 'dropout': DROPOUT,     # pinned host ids: the step
+              'sample_item': draw}                                                   # copies them in (H2D)
         out = model.train_step(fd)
         draw = model.draw_confounders(2 * BATCH)                        # next step's draw overlaps this step
         loss = float(out['loss'].item())                                # D2H + sync
