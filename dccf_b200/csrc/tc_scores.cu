@@ -12,11 +12,11 @@
 // FP32 accumulation in TMEM), which keeps the 1e-5 parity bound of the FP32 reference.
 //
 // CTA = one 128-row tile, 10 warps:
-//   warps 0-7  producers: generate eps (Philox4x32-10 + Box-Muller, the library's stream — bit-identical to
+//   warps 0-15 producers: generate eps (Philox4x32-10 + Box-Muller, the library's stream — bit-identical to
 //              the SIMT kernels) or read the explicit noise tensor, split hi/lo, store the K-major
 //              core-matrix layout the UMMA descriptors describe, fence.proxy.async, arrive on `full`
-//   warp  8    one thread issues tcgen05.mma.kind::tf32 (M=128, N=64, K=8), tcgen05.commit frees the stage
-//   warp  9    one thread streams the pre-split W_f chunks with cp.async.bulk (TMA engine) into the stage
+//   warp  16   one thread issues tcgen05.mma.kind::tf32 (M=128, N=64, K=8), tcgen05.commit frees the stage
+//   warp  17   one thread streams the pre-split W_f chunks with cp.async.bulk (TMA engine) into the stage
 //   warps 0-3  epilogue: tcgen05.ld the accumulator (lane = row), + PI + PF, ReLU, dropout, dot with E_user
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -26,7 +26,7 @@ namespace dccf {
 constexpr int TC_BM = 128;                 // rows per tile
 constexpr int TC_KC = 32;                  // K per stage (8 core-matrix columns of 4 tf32)
 constexpr int TC_STAGES = 2;
-constexpr int TC_PRODUCERS = 256;          // 8 warps
+constexpr int TC_PRODUCERS = 512;          // 16 warps: enough independent Philox chains per SM to fill the issue slots
 constexpr int TC_NT = TC_PRODUCERS + 64;   // + MMA warp + TMA warp
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_KC * 4;   // 16 KB (one of hi / lo)
 constexpr uint32_t TC_B_BYTES = D * TC_KC * 4;       //  8 KB (one of hi / lo)
@@ -182,36 +182,36 @@ __global__ void __launch_bounds__(TC_NT, 2) k_row_scores_tc(const TcParams prm) 
         tc::mbar_init(accum_bar, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 8) tc::tmem_alloc(tmem_slot, TC_TMEM_COLS);
+    if (warp == TC_PRODUCERS / 32) tc::tmem_alloc(tmem_slot, TC_TMEM_COLS);
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 8) {
-        // ===== producers =====
-        const int row = tid & (TC_BM - 1), khalf = tid >> 7;
+    if (warp < TC_PRODUCERS / 32) {
+        // ===== producers: thread = (row, quarter of the 32-wide K chunk) =====
+        const int row = tid & (TC_BM - 1), kq = tid >> 7;
         const int64_t grow = min(row_base + row, prm.n_rows - 1);
         const RngKey key_noise = resolve_rng_key(prm.rng, DOMAIN_NOISE);
-        const float* nptr = (NOISE_MODE == 1) ? prm.noise + (size_t)grow * prm.F + khalf * 16 : nullptr;
+        const float* nptr = (NOISE_MODE == 1) ? prm.noise + (size_t)grow * prm.F + kq * 8 : nullptr;
         for (int c = 0; c < n_chunks; ++c) {
             const int s = c % TC_STAGES;
             const uint32_t ph = (uint32_t)(c / TC_STAGES) & 1u;
-            float4 e[4];
+            float4 e[2];
             if (NOISE_MODE == 1) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) e[q] = ldg4(nptr + c * TC_KC + 4 * q);
+                for (int q = 0; q < 2; ++q) e[q] = ldg4(nptr + c * TC_KC + 4 * q);
             } else {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    e[q] = noise_quad(key_noise, (uint32_t)grow, (uint32_t)(c * 8 + khalf * 4 + q), prm.noise_std);
+                for (int q = 0; q < 2; ++q)
+                    e[q] = noise_quad(key_noise, (uint32_t)grow, (uint32_t)(c * 8 + kq * 2 + q), prm.noise_std);
             }
             tc::mbar_wait(&empty_bar[s], ph ^ 1u);   // the MMAs that read this stage have completed
             uint8_t* a_hi = smem + s * TC_STAGE_BYTES;
             uint8_t* a_lo = a_hi + TC_A_BYTES;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t off = core_offset(row, khalf * 16 + 4 * q);
+            for (int q = 0; q < 2; ++q) {
+                const uint32_t off = core_offset(row, kq * 8 + 4 * q);
                 float4 hi, lo;
                 hi.x = tf32_hi(e[q].x); hi.y = tf32_hi(e[q].y); hi.z = tf32_hi(e[q].z); hi.w = tf32_hi(e[q].w);
                 lo.x = __fsub_rn(e[q].x, hi.x); lo.y = __fsub_rn(e[q].y, hi.y);
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_row_scores_tc(const TcParams prm) 
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&full_bar[s]);
         }
-    } else if (warp == 8) {
+    } else if (warp == TC_PRODUCERS / 32) {
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = tc::make_idesc_tf32(TC_BM, D);
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_row_scores_tc(const TcParams prm) 
 
     tc::tc_fence_before_sync();
     __syncthreads();
-    if (warp == 8) tc::tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    if (warp == TC_PRODUCERS / 32) tc::tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
 // defined in score_fwd.cu
