@@ -91,28 +91,30 @@ __device__ __forceinline__ RngKey resolve_rng_key(const RngSpec& s, uint32_t dom
     return make_rng_key(s.seed, off, domain);
 }
 
-// Box-Muller on two 32-bit words -> two standard normals.
-__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
-    // u in (0,1]: (a + 0.5) * 2^-32  (rounds to 1.0f at the very top, never 0)
+// Box-Muller on two 32-bit words -> two normals of standard deviation `std` (std folded into the radius).
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float std, float& n0, float& n1) {
+    // u in (0,1]: (a + 0.5) * 2^-32  (rounds to 1.0f at the very top, never 0), so -2 ln u >= 0
     const float u = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     // theta in [-pi, pi)
     const float theta = (float)(int32_t)b * 1.4629180792671596e-9f;  // pi * 2^-31
     const float t = -1.3862943611198906f * __log2f(u);               // -2 ln u = -2 ln2 log2 u
-    const float rad = sqrtf(fmaxf(t, 0.0f));
+    float rad;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(rad) : "f"(t));
+    rad = __fmul_rn(rad, std);
     float s, c;
     __sincosf(theta, &s, &c);
-    n0 = rad * c;
-    n1 = rad * s;
+    n0 = __fmul_rn(rad, c);
+    n1 = __fmul_rn(rad, s);
 }
 
-// eps for columns 4*quad .. 4*quad+3 of `row`: std * N(0,1).  __fmul_rn keeps the product
-// un-contracted so the fused kernels and the materialiser agree bit for bit.
+// eps for columns 4*quad .. 4*quad+3 of `row`: N(0, std^2).  Every kernel and the materialiser go through this
+// one function (explicit round-to-nearest multiplies, no contraction), so they agree bit for bit.
 __device__ __forceinline__ float4 noise_quad(const RngKey& key, uint32_t row, uint32_t quad, float std) {
     const uint4 x = philox4x32_10(quad, row, key.c2, key.c3, key.k0, key.k1);
     float n0, n1, n2, n3;
-    box_muller(x.x, x.y, n0, n1);
-    box_muller(x.z, x.w, n2, n3);
-    return make_float4(__fmul_rn(std, n0), __fmul_rn(std, n1), __fmul_rn(std, n2), __fmul_rn(std, n3));
+    box_muller(x.x, x.y, std, n0, n1);
+    box_muller(x.z, x.w, std, n2, n3);
+    return make_float4(n0, n1, n2, n3);
 }
 
 // dropout multipliers for columns 4*quad..4*quad+3 of `row`: keep with prob 1-p, scaled 1/(1-p).
