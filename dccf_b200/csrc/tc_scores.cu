@@ -24,20 +24,20 @@
 namespace dccf {
 
 constexpr int TC_BM = 128;                 // rows per tile
-constexpr int TC_KC = 16;                  // K per stage (4 core-matrix columns of 4 tf32, two MMA k-steps)
-constexpr int TC_STAGES = 4;               // 24 KB each: a deeper ring decouples the producers from the MMA issuer
+constexpr int TC_KC = 32;                  // K per stage (8 core-matrix columns of 4 tf32)
+constexpr int TC_STAGES = 2;
 constexpr int TC_PRODUCERS = 512;          // 16 warps: enough independent Philox chains per SM to fill the issue slots
 constexpr int TC_NT = TC_PRODUCERS + 64;   // + MMA warp + TMA warp
-constexpr uint32_t TC_A_BYTES = TC_BM * TC_KC * 4;   // 8 KB (one of hi / lo)
-constexpr uint32_t TC_B_BYTES = D * TC_KC * 4;       // 4 KB (one of hi / lo)
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_KC * 4;   // 16 KB (one of hi / lo)
+constexpr uint32_t TC_B_BYTES = D * TC_KC * 4;       //  8 KB (one of hi / lo)
 constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 48 KB
 constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 256;
 constexpr int TC_NACC = 4;                 // TMEM accumulators per tile (see the MMA issuer)
 constexpr uint32_t TC_TMEM_COLS = TC_NACC * D;   // 256 of the 512 columns: two CTAs per SM
 constexpr uint32_t TC_LBO = 128;           // K-adjacent core matrices are contiguous
-constexpr uint32_t TC_SBO = (TC_KC / 4) * 128;   // core matrices of one 8-row group are contiguous
+constexpr uint32_t TC_SBO = 1024;          // 8 core matrices (32 K values) per 8-row group
 
-// byte offset of element (row r, k) inside a [rows x TC_KC] K-major no-swizzle operand tile
+// byte offset of element (row r, k) inside a [rows x 32] K-major no-swizzle operand tile
 __host__ __device__ __forceinline__ uint32_t core_offset(int r, int k) {
     return (uint32_t)((r >> 3) * TC_SBO + (k >> 2) * TC_LBO + (r & 7) * 16 + (k & 3) * 4);
 }
@@ -189,23 +189,29 @@ __global__ void __launch_bounds__(TC_NT, 2) k_row_scores_tc(const TcParams prm) 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < TC_PRODUCERS / 32) {
-        // ===== producers: thread = (row, one 4-wide quad of the 16-wide K chunk) =====
+        // ===== producers: thread = (row, quarter of the 32-wide K chunk) =====
         const int row = tid & (TC_BM - 1), kq = tid >> 7;
         const int64_t grow = min(row_base + row, prm.n_rows - 1);
         const RngKey key_noise = resolve_rng_key(prm.rng, DOMAIN_NOISE);
-        const float* nptr = (NOISE_MODE == 1) ? prm.noise + (size_t)grow * prm.F + kq * 4 : nullptr;
+        const float* nptr = (NOISE_MODE == 1) ? prm.noise + (size_t)grow * prm.F + kq * 8 : nullptr;
         for (int c = 0; c < n_chunks; ++c) {
             const int s = c % TC_STAGES;
             const uint32_t ph = (uint32_t)(c / TC_STAGES) & 1u;
-            float4 e[1];                       // 512 producers x 4 values = the 128 x 16 chunk
-            if (NOISE_MODE == 1) e[0] = ldg4(nptr + c * TC_KC);
-            else e[0] = noise_quad(key_noise, (uint32_t)grow, (uint32_t)(c * (TC_KC / 4) + kq), prm.noise_std);
+            float4 e[2];
+            if (NOISE_MODE == 1) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) e[q] = ldg4(nptr + c * TC_KC + 4 * q);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    e[q] = noise_quad(key_noise, (uint32_t)grow, (uint32_t)(c * 8 + kq * 2 + q), prm.noise_std);
+            }
             tc::mbar_wait(&empty_bar[s], ph ^ 1u);   // the MMAs that read this stage have completed
             uint8_t* a_hi = smem + s * TC_STAGE_BYTES;
             uint8_t* a_lo = a_hi + TC_A_BYTES;
 #pragma unroll
-            for (int q = 0; q < 1; ++q) {
-                const uint32_t off = core_offset(row, kq * 4);
+            for (int q = 0; q < 2; ++q) {
+                const uint32_t off = core_offset(row, kq * 8 + 4 * q);
                 float4 hi, lo;
                 hi.x = tf32_hi(e[q].x); hi.y = tf32_hi(e[q].y); hi.z = tf32_hi(e[q].z); hi.w = tf32_hi(e[q].w);
                 lo.x = __fsub_rn(e[q].x, hi.x); lo.y = __fsub_rn(e[q].y, hi.y);
