@@ -25,19 +25,24 @@ namespace dccf {
 constexpr int FS_BM = 128, FS_BN = 64;
 constexpr int FS_NT = 288;
 constexpr int FS_KMAX = 16;                              // largest fused top-k
-constexpr uint32_t FS_A_IMG = FS_BM * 32 * 4;            // one [128 x 32] chunk image, 16 KB
-constexpr uint32_t FS_B_IMG = FS_BN * 32 * 4;            // one [64 x 32] chunk image, 8 KB
-constexpr uint32_t FS_A_BYTES = 4 * FS_A_IMG;            // hi k0-31, hi k32-63, lo k0-31, lo k32-63
-constexpr uint32_t FS_B_BYTES = 4 * FS_B_IMG;            // same for the item tile, 32 KB per stage
-constexpr uint32_t FS_COL_BYTES = 2 * FS_BN * 4;         // col_bias + col_scale of the tile
-constexpr uint32_t FS_STAGE = FS_B_BYTES + FS_COL_BYTES;
-constexpr uint32_t FS_SMEM = FS_A_BYTES + 2 * FS_STAGE + 256;
+// The biases and the column scale ride inside the GEMM: K is augmented from 64 to 72,
+//   A'[u] = [ A[u,:], row_bias[u] + g, 1, 0.. ]      B'[i] = cs_i * [ B[i,:], 1, col_bias[i], 0.. ]
+// so that <A'[u], B'[i]> = cs_i * (<A[u],B[i]> + row_bias[u] + g + col_bias[i]) and the epilogue is a bare
+// accumulator read.  Operand images ([rows x 32] / [rows x 8], K-major core matrices, hi and lo parts):
+constexpr uint32_t FS_A_IMG = FS_BM * 32 * 4;            // 16 KB: one [128 x 32] image
+constexpr uint32_t FS_A_AUG = FS_BM * 8 * 4;             //  4 KB: the [128 x 8] augmentation image
+constexpr uint32_t FS_B_IMG = FS_BN * 32 * 4;            //  8 KB
+constexpr uint32_t FS_B_AUG = FS_BN * 8 * 4;             //  2 KB
+constexpr uint32_t FS_A_HALF = 2 * FS_A_IMG + FS_A_AUG;  // hi (or lo) part of the user tile
+constexpr uint32_t FS_A_BYTES = 2 * FS_A_HALF;           // 72 KB
+constexpr uint32_t FS_B_HALF = 2 * FS_B_IMG + FS_B_AUG;
+constexpr uint32_t FS_STAGE = 2 * FS_B_HALF;             // 36 KB per item-tile stage
+constexpr int FS_OUT_LD = FS_BN + 4;                     // padded row of the store-staging tile
+constexpr uint32_t FS_OUT_BYTES = 4 * 32 * FS_OUT_LD * 4;   // one 32 x 64 tile per epilogue warp
+constexpr uint32_t FS_SMEM = FS_A_BYTES + 2 * FS_STAGE + FS_OUT_BYTES + 256;
 constexpr uint32_t FS_TMEM_COLS = 256;                   // 2 buffers x (main + correction) x 64 columns
-constexpr uint32_t FS_LBO = 128, FS_SBO = 1024;
+constexpr uint32_t FS_LBO = 128, FS_SBO = 1024, FS_SBO_AUG = 256;
 
-__device__ __forceinline__ uint32_t fs_core_offset(int r, int k) {   // inside a [rows x 32] image
-    return (uint32_t)((r >> 3) * FS_SBO + (k >> 2) * FS_LBO + (r & 7) * 16 + (k & 3) * 4);
-}
 __device__ __forceinline__ float fs_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 struct FsParams {
@@ -54,22 +59,25 @@ struct FsParams {
     int32_t tiles_per_split, n_tiles;
 };
 
-// store a 4-float group of one row (split hi / lo into the chunk images at `base`)
-__device__ __forceinline__ void fs_store_split(uint8_t* base, uint32_t img_bytes, int r, int k, const float4& v) {
-    const int chunk = k >> 5, kk = k & 31;
-    const uint32_t off = fs_core_offset(r, kk);
+// store 4 consecutive k values of row r into the hi / lo images (k < 64: main images, k >= 64: augmentation)
+__device__ __forceinline__ void fs_store_split(uint8_t* hi_base, uint8_t* lo_base, uint32_t img_bytes, int r, int k,
+                                               const float4& v) {
+    uint32_t off;
+    if (k < 64) off = (uint32_t)(k >> 5) * img_bytes + (uint32_t)((r >> 3) * FS_SBO + ((k & 31) >> 2) * FS_LBO + (r & 7) * 16);
+    else off = 2 * img_bytes + (uint32_t)((r >> 3) * FS_SBO_AUG + ((k - 64) >> 2) * FS_LBO + (r & 7) * 16);
     float4 hi, lo;
     hi.x = fs_hi(v.x); hi.y = fs_hi(v.y); hi.z = fs_hi(v.z); hi.w = fs_hi(v.w);
     lo.x = __fsub_rn(v.x, hi.x); lo.y = __fsub_rn(v.y, hi.y); lo.z = __fsub_rn(v.z, hi.z); lo.w = __fsub_rn(v.w, hi.w);
-    *reinterpret_cast<float4*>(base + chunk * img_bytes + off) = hi;
-    *reinterpret_cast<float4*>(base + (2 + chunk) * img_bytes + off) = lo;
+    *reinterpret_cast<float4*>(hi_base + off) = hi;
+    *reinterpret_cast<float4*>(lo_base + off) = lo;
 }
 
 __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* a_s = smem;
     uint8_t* stage0 = smem + FS_A_BYTES;
-    uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + FS_A_BYTES + 2 * FS_STAGE);
+    float* out_s = reinterpret_cast<float*>(smem + FS_A_BYTES + 2 * FS_STAGE);
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + FS_A_BYTES + 2 * FS_STAGE + FS_OUT_BYTES);
     uint64_t* b_empty = b_full + 2;
     uint64_t* acc_full = b_empty + 2;
     uint64_t* acc_empty = acc_full + 2;
@@ -92,11 +100,15 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
     }
     if (warp == 8) tc::tmem_alloc(tmem_slot, FS_TMEM_COLS);
 
-    // user tile: 128 rows x 64 factors, split once (all threads)
-    for (int i = tid; i < FS_BM * 16; i += FS_NT) {
-        const int r = i >> 4, q = i & 15;
+    // user tile: 128 rows x (64 factors + augmentation), split once (all threads)
+    for (int i = tid; i < FS_BM * 18; i += FS_NT) {
+        const int r = i / 18, q = i - r * 18;
         const int64_t u = min(u0 + r, (int64_t)prm.n_users - 1);
-        fs_store_split(a_s, FS_A_IMG, r, q * 4, ldg4(prm.A + (size_t)u * D + q * 4));
+        float4 v;
+        if (q < 16) v = ldg4(prm.A + (size_t)u * D + q * 4);
+        else if (q == 16) v = make_float4((prm.row_bias ? __ldg(prm.row_bias + u) : 0.f) + prm.g, 1.f, 0.f, 0.f);
+        else v = make_float4(0.f, 0.f, 0.f, 0.f);
+        fs_store_split(a_s, a_s + FS_A_HALF, FS_A_IMG, r, q * 4, v);
     }
     tc::fence_proxy_async_smem();
     tc::tc_fence_before_sync();
@@ -105,27 +117,30 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp >= 4 && warp < 8) {
-        // ===== item-tile staging =====
+        // ===== item-tile staging: thread = (item, half of K) =====
         const int t128 = tid - 128;
         const int item = t128 & 63, khalf = t128 >> 6;
         for (int t = t_lo; t < t_hi; ++t) {
             const int n = t - t_lo, s = n & 1;
             const uint32_t ph = (uint32_t)(n >> 1) & 1u;
-            const int64_t i = min((int64_t)t * FS_BN + item, (int64_t)prm.n_items - 1);
+            const int64_t i_raw = (int64_t)t * FS_BN + item;
+            const bool live = i_raw < prm.n_items;
+            const int64_t i = live ? i_raw : (int64_t)prm.n_items - 1;
+            const float cs = live ? (prm.col_scale ? __ldg(prm.col_scale + i) : 1.f) : 0.f;   // dead columns score 0
             float4 v[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = ldg4(prm.B + (size_t)i * D + khalf * 32 + q * 4);
+            for (int q = 0; q < 8; ++q) {
+                v[q] = ldg4(prm.B + (size_t)i * D + khalf * 32 + q * 4);
+                v[q].x *= cs; v[q].y *= cs; v[q].z *= cs; v[q].w *= cs;
+            }
             tc::mbar_wait(&b_empty[s], ph ^ 1u);
             uint8_t* st = stage0 + s * FS_STAGE;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) fs_store_split(st, FS_B_IMG, item, khalf * 32 + q * 4, v[q]);
-            if (khalf == 0) {
-                // the epilogue of the tile that used this stage two tiles ago still reads its column vectors
-                // until it hands the accumulator back
-                tc::mbar_wait(&acc_empty[s], ph ^ 1u);
-                float* col = reinterpret_cast<float*>(st + FS_B_BYTES);
-                col[item] = prm.col_bias ? __ldg(prm.col_bias + i) : 0.f;
-                col[FS_BN + item] = prm.col_scale ? __ldg(prm.col_scale + i) : 1.f;
+            for (int q = 0; q < 8; ++q) fs_store_split(st, st + FS_B_HALF, FS_B_IMG, item, khalf * 32 + q * 4, v[q]);
+            {   // augmentation columns: khalf 0 writes k 64..67, khalf 1 writes k 68..71
+                const float cb = (live && prm.col_bias) ? __ldg(prm.col_bias + i) : 0.f;
+                const float4 aug = (khalf == 0) ? make_float4(cs, cs * cb, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+                fs_store_split(st, st + FS_B_HALF, FS_B_IMG, item, 64 + khalf * 4, aug);
             }
             tc::fence_proxy_async_smem();
             __syncwarp();
@@ -135,23 +150,26 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = tc::make_idesc_tf32(FS_BM, FS_BN);
-            const uint32_t a_base = tc::smem_u32(a_s);
+            const uint32_t a_hi0 = tc::smem_u32(a_s), a_lo0 = a_hi0 + FS_A_HALF;
             for (int t = t_lo; t < t_hi; ++t) {
                 const int n = t - t_lo, s = n & 1;
                 const uint32_t ph = (uint32_t)(n >> 1) & 1u;
                 tc::mbar_wait(&b_full[s], ph);
                 tc::mbar_wait(&acc_empty[s], ph ^ 1u);     // the epilogue has drained this accumulator pair
                 tc::tc_fence_after_sync();
-                const uint32_t b_base = tc::smem_u32(stage0 + s * FS_STAGE);
+                const uint32_t b_hi0 = tc::smem_u32(stage0 + s * FS_STAGE), b_lo0 = b_hi0 + FS_B_HALF;
                 const uint32_t d_main = tmem_base + (uint32_t)(s * 2) * FS_BN;
                 const uint32_t d_corr = d_main + FS_BN;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const uint32_t chunk = ks >> 2, ko = (uint32_t)(ks & 3) * 2 * FS_LBO;
-                    const uint64_t a_hi = tc::make_smem_desc(a_base + chunk * FS_A_IMG + ko, FS_LBO, FS_SBO);
-                    const uint64_t a_lo = tc::make_smem_desc(a_base + (2 + chunk) * FS_A_IMG + ko, FS_LBO, FS_SBO);
-                    const uint64_t b_hi = tc::make_smem_desc(b_base + chunk * FS_B_IMG + ko, FS_LBO, FS_SBO);
-                    const uint64_t b_lo = tc::make_smem_desc(b_base + (2 + chunk) * FS_B_IMG + ko, FS_LBO, FS_SBO);
+                for (int ks = 0; ks < 9; ++ks) {
+                    // k-steps 0..7: the two [rows x 32] images; k-step 8: the [rows x 8] augmentation image
+                    const uint32_t a_off = ks < 8 ? (uint32_t)(ks >> 2) * FS_A_IMG + (uint32_t)(ks & 3) * 2 * FS_LBO : 2 * FS_A_IMG;
+                    const uint32_t b_off = ks < 8 ? (uint32_t)(ks >> 2) * FS_B_IMG + (uint32_t)(ks & 3) * 2 * FS_LBO : 2 * FS_B_IMG;
+                    const uint32_t sbo = ks < 8 ? FS_SBO : FS_SBO_AUG;
+                    const uint64_t a_hi = tc::make_smem_desc(a_hi0 + a_off, FS_LBO, sbo);
+                    const uint64_t a_lo = tc::make_smem_desc(a_lo0 + a_off, FS_LBO, sbo);
+                    const uint64_t b_hi = tc::make_smem_desc(b_hi0 + b_off, FS_LBO, sbo);
+                    const uint64_t b_lo = tc::make_smem_desc(b_lo0 + b_off, FS_LBO, sbo);
                     tc::umma_tf32(d_corr, a_lo, b_hi, idesc, ks != 0);
                     tc::umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
                     tc::umma_tf32(d_main, a_hi, b_hi, idesc, ks != 0);
@@ -163,63 +181,49 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
         __syncwarp();
     } else {
         // ===== epilogue: thread = user row =====
-        const int row = tid;
-        const int64_t u = u0 + row;
+        const int64_t u = u0 + tid;
         const bool valid = u < prm.n_users;
-        const float rb = (valid && prm.row_bias) ? __ldg(prm.row_bias + u) : 0.f;
-        const float add = rb + prm.g;
         float best_s[FS_KMAX];
         int32_t best_i[FS_KMAX];
 #pragma unroll
         for (int j = 0; j < FS_KMAX; ++j) { best_s[j] = -INFINITY; best_i[j] = -1; }
         const int k = prm.k;
-        float thr_s = -INFINITY;      // score and id of the current k-th entry (kept in registers: the
-        int32_t thr_i = -1;           // arrays are only touched through fully unrolled loops)
+        float thr = -INFINITY;      // score of the current k-th entry; an item enters only when it beats it
+        int filled = 0;
+        float* my_out = out_s + warp * 32 * FS_OUT_LD;
         for (int t = t_lo; t < t_hi; ++t) {
             const int n = t - t_lo, s = n & 1;
             const uint32_t ph = (uint32_t)(n >> 1) & 1u;
             tc::mbar_wait(&acc_full[s], ph);
             tc::tc_fence_after_sync();
-            const float* col = reinterpret_cast<const float*>(stage0 + s * FS_STAGE + FS_B_BYTES);
             const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * 2) * FS_BN;
             const int64_t i0 = (int64_t)t * FS_BN;
+            const bool last_tile = i0 + FS_BN > prm.n_items;      // warp-uniform: only this tile has dead columns
 #pragma unroll 1
             for (int quarter = 0; quarter < 4; ++quarter) {
-                float acc[16], corr[16];
-                tc::tmem_ld_32x16(lane_addr + quarter * 16, acc);
+                float v[16], corr[16];
+                tc::tmem_ld_32x16(lane_addr + quarter * 16, v);
                 tc::tmem_ld_32x16(lane_addr + FS_BN + quarter * 16, corr);
-                float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int c = quarter * 16 + j;
-                    v[j] = ((acc[j] + corr[j]) + (add + col[c])) * col[FS_BN + c];
-                }
-                if (prm.out != nullptr && valid) {
+                for (int j = 0; j < 16; ++j) v[j] += corr[j];
+                if (prm.out != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        const int64_t i = i0 + quarter * 16 + j;
-                        float* dst = prm.out + (size_t)u * prm.n_items + i;
-                        if (i + 3 < prm.n_items && ((prm.n_items & 3) == 0)) {
-                            st4(dst, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (i + e < prm.n_items) dst[e] = v[j + e];
-                        }
-                    }
+                    for (int j = 0; j < 16; j += 4)
+                        st4(my_out + lane * FS_OUT_LD + quarter * 16 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
                 }
                 if (prm.topk_score != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int64_t i = i0 + quarter * 16 + j;
-                        float sc = (v[j] != v[j]) ? -INFINITY : v[j];
-                        if (i < prm.n_items && (sc > thr_s || thr_i < 0)) {
-                            // insert, keeping (score desc, id asc): items arrive in ascending id, so an
-                            // equal score never displaces an earlier one
-                            int32_t ci = (int32_t)i;
+                        const int32_t ci0 = (int32_t)(i0 + quarter * 16 + j);
+                        float sc = v[j];
+                        if (last_tile && ci0 >= prm.n_items) sc = -INFINITY;
+                        // items arrive in ascending id, so an equal score never displaces an earlier one; NaN never
+                        // compares greater and is left out (ranked last)
+                        if (sc > thr || (filled < k && sc == sc && !(last_tile && ci0 >= prm.n_items))) {
+                            int32_t ci = ci0;
 #pragma unroll
                             for (int q = 0; q < FS_KMAX; ++q) {
-                                if (q < k && (sc > best_s[q] || best_i[q] < 0)) {
+                                if (q < k && (best_i[q] < 0 || sc > best_s[q])) {
                                     const float ts = best_s[q];
                                     const int32_t ti = best_i[q];
                                     best_s[q] = sc;
@@ -228,16 +232,43 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
                                     ci = ti;
                                 }
                             }
+                            filled = min(filled + 1, k);
 #pragma unroll
                             for (int q = 0; q < FS_KMAX; ++q)
-                                if (q == k - 1) { thr_s = best_s[q]; thr_i = best_i[q]; }
+                                if (q == k - 1 && filled == k) thr = best_s[q];
                         }
                     }
                 }
             }
+            // every TMEM read of this accumulator pair is done: hand it back to the MMA warp
             tc::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&acc_empty[s]);
+            if (prm.out != nullptr) {
+                // coalesced write-out of this warp's 32 x 64 tile: two rows (2 x 256 B) per instruction
+                __syncwarp();
+                const int half = lane >> 4, c4 = (lane & 15) * 4;
+                const bool vec_ok = ((prm.n_items & 3) == 0);
+#pragma unroll 4
+                for (int rr = 0; rr < 32; rr += 2) {
+                    const int r = rr + half;
+                    const int64_t uu = u0 + warp * 32 + r;
+                    const int64_t i = i0 + c4;
+                    if (uu < prm.n_users) {
+                        const float4 w = ld4(my_out + r * FS_OUT_LD + c4);
+                        float* dst = prm.out + (size_t)uu * prm.n_items + i;
+                        if (vec_ok && i + 3 < prm.n_items) {
+                            st4(dst, w);
+                        } else {
+                            const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (i + e < prm.n_items) dst[e] = wv[e];
+                        }
+                    }
+                }
+                __syncwarp();
+            }
         }
         if (prm.topk_score != nullptr && valid) {
             float* ds = prm.topk_score + ((size_t)split * prm.n_users + u) * k;
