@@ -206,37 +206,46 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
                 tc::tmem_ld_32x16(lane_addr + FS_BN + quarter * 16, corr);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] += corr[j];
-                if (prm.out != nullptr) {
+                // this row's 16 scores go to the warp's staging tile (write-out and dynamic re-reads below)
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        st4(my_out + lane * FS_OUT_LD + quarter * 16 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-                }
+                for (int j = 0; j < 16; j += 4)
+                    st4(my_out + lane * FS_OUT_LD + quarter * 16 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
                 if (prm.topk_score != nullptr) {
+                    // cheap, fully unrolled filter: which of the 16 beat the current k-th score (or fill an empty
+                    // slot)?  NaN never compares greater and is left out (ranked last).
+                    uint32_t hits = 0;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int32_t ci0 = (int32_t)(i0 + quarter * 16 + j);
-                        float sc = v[j];
-                        if (last_tile && ci0 >= prm.n_items) sc = -INFINITY;
-                        // items arrive in ascending id, so an equal score never displaces an earlier one; NaN never
-                        // compares greater and is left out (ranked last)
-                        if (sc > thr || (filled < k && sc == sc && !(last_tile && ci0 >= prm.n_items))) {
-                            int32_t ci = ci0;
+                        const bool take = (filled < k) ? (v[j] == v[j]) : (v[j] > thr);
+                        hits |= take ? (1u << j) : 0u;
+                    }
+                    if (last_tile) {
+                        const int64_t live = (int64_t)prm.n_items - (i0 + quarter * 16);      // columns that exist
+                        hits &= live >= 16 ? 0xffffu : (live <= 0 ? 0u : ((1u << live) - 1u));
+                    }
+                    // rare path, ONE copy of the insertion code: items arrive in ascending id, so an equal score
+                    // never displaces an earlier one
+                    while (hits) {
+                        const int j = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        float sc = my_out[lane * FS_OUT_LD + quarter * 16 + j];
+                        if (!(filled < k || sc > thr)) continue;        // the threshold moved since the filter
+                        int32_t ci = (int32_t)(i0 + quarter * 16 + j);
 #pragma unroll
-                            for (int q = 0; q < FS_KMAX; ++q) {
-                                if (q < k && (best_i[q] < 0 || sc > best_s[q])) {
-                                    const float ts = best_s[q];
-                                    const int32_t ti = best_i[q];
-                                    best_s[q] = sc;
-                                    best_i[q] = ci;
-                                    sc = ts;
-                                    ci = ti;
-                                }
+                        for (int q = 0; q < FS_KMAX; ++q) {
+                            if (q < k && (best_i[q] < 0 || sc > best_s[q])) {
+                                const float ts = best_s[q];
+                                const int32_t ti = best_i[q];
+                                best_s[q] = sc;
+                                best_i[q] = ci;
+                                sc = ts;
+                                ci = ti;
                             }
-                            filled = min(filled + 1, k);
-#pragma unroll
-                            for (int q = 0; q < FS_KMAX; ++q)
-                                if (q == k - 1 && filled == k) thr = best_s[q];
                         }
+                        filled = min(filled + 1, k);
+#pragma unroll
+                        for (int q = 0; q < FS_KMAX; ++q)
+                            if (q == k - 1 && filled == k) thr = best_s[q];
                     }
                 }
             }
