@@ -200,37 +200,46 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
             const int64_t i0 = (int64_t)t * FS_BN;
             const bool last_tile = i0 + FS_BN > prm.n_items;      // warp-uniform: only this tile has dead columns
 #pragma unroll 1
-            for (int quarter = 0; quarter < 4; ++quarter) {
-                float v[16], corr[16];
-                tc::tmem_ld_32x16(lane_addr + quarter * 16, v);
-                tc::tmem_ld_32x16(lane_addr + FS_BN + quarter * 16, corr);
+            for (int half = 0; half < 2; ++half) {
+                // main and correction accumulators of 32 columns: two TMEM loads in flight, one wait
+                uint32_t rm[32], rc[32];
+                tc::tmem_ld_32x32_issue(lane_addr + half * 32, rm);
+                tc::tmem_ld_32x32_issue(lane_addr + FS_BN + half * 32, rc);
+                tc::tmem_wait_ld();
+                if (half == 1) {
+                    // every TMEM read of this accumulator pair is done: hand it back to the MMA warp
+                    tc::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&acc_empty[s]);
+                }
+                float v[32];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += corr[j];
-                // this row's 16 scores go to the warp's staging tile (write-out and dynamic re-reads below)
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rm[j]) + __uint_as_float(rc[j]);
+                // this row's scores go to the warp's staging tile (write-out and dynamic re-reads below)
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    st4(my_out + lane * FS_OUT_LD + quarter * 16 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                for (int j = 0; j < 32; j += 4)
+                    st4(my_out + lane * FS_OUT_LD + half * 32 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
                 if (prm.topk_score != nullptr) {
-                    // cheap, fully unrolled filter: which of the 16 beat the current k-th score (or fill an empty
+                    // cheap, fully unrolled filter: which of the 32 beat the current k-th score (or fill an empty
                     // slot)?  NaN never compares greater and is left out (ranked last).
                     uint32_t hits = 0;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < 32; ++j) {
                         const bool take = (filled < k) ? (v[j] == v[j]) : (v[j] > thr);
                         hits |= take ? (1u << j) : 0u;
                     }
                     if (last_tile) {
-                        const int64_t live = (int64_t)prm.n_items - (i0 + quarter * 16);      // columns that exist
-                        hits &= live >= 16 ? 0xffffu : (live <= 0 ? 0u : ((1u << live) - 1u));
+                        const int64_t live = (int64_t)prm.n_items - (i0 + half * 32);      // columns that exist
+                        hits &= live >= 32 ? 0xffffffffu : (live <= 0 ? 0u : ((1u << live) - 1u));
                     }
                     // rare path, ONE copy of the insertion code: items arrive in ascending id, so an equal score
                     // never displaces an earlier one
                     while (hits) {
                         const int j = __ffs(hits) - 1;
                         hits &= hits - 1;
-                        float sc = my_out[lane * FS_OUT_LD + quarter * 16 + j];
+                        float sc = my_out[lane * FS_OUT_LD + half * 32 + j];
                         if (!(filled < k || sc > thr)) continue;        // the threshold moved since the filter
-                        int32_t ci = (int32_t)(i0 + quarter * 16 + j);
+                        int32_t ci = (int32_t)(i0 + half * 32 + j);
 #pragma unroll
                         for (int q = 0; q < FS_KMAX; ++q) {
                             if (q < k && (best_i[q] < 0 || sc > best_s[q])) {
@@ -249,10 +258,6 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
                     }
                 }
             }
-            // every TMEM read of this accumulator pair is done: hand it back to the MMA warp
-            tc::tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&acc_empty[s]);
             if (prm.out != nullptr) {
                 // coalesced write-out of this warp's 32 x 64 tile: two rows (2 x 256 B) per instruction
                 __syncwarp();
