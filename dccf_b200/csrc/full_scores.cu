@@ -33,14 +33,16 @@ constexpr uint32_t FS_A_IMG = FS_BM * 32 * 4;            // 16 KB: one [128 x 32
 constexpr uint32_t FS_A_AUG = FS_BM * 8 * 4;             //  4 KB: the [128 x 8] augmentation image
 constexpr uint32_t FS_B_IMG = FS_BN * 32 * 4;            //  8 KB
 constexpr uint32_t FS_B_AUG = FS_BN * 8 * 4;             //  2 KB
-constexpr uint32_t FS_A_HALF = 2 * FS_A_IMG + FS_A_AUG;  // hi (or lo) part of the user tile
-constexpr uint32_t FS_A_BYTES = 2 * FS_A_HALF;           // 72 KB
+constexpr uint32_t FS_A_HALF = 2 * FS_A_IMG + FS_A_AUG;  // (unused: the user tile lives in tensor memory)
+constexpr uint32_t FS_A_BYTES = 0;
+constexpr int FS_KAUG = 72;                              // augmented K
+constexpr uint32_t FS_TM_AHI = 256, FS_TM_ALO = 384;     // TMEM columns of the user tile (hi / lo), 72 each
 constexpr uint32_t FS_B_HALF = 2 * FS_B_IMG + FS_B_AUG;
 constexpr uint32_t FS_STAGE = 2 * FS_B_HALF;             // 36 KB per item-tile stage
 constexpr int FS_OUT_LD = FS_BN + 4;                     // padded row of the store-staging tile
 constexpr uint32_t FS_OUT_BYTES = 4 * 32 * FS_OUT_LD * 4;   // one 32 x 64 tile per epilogue warp
 constexpr uint32_t FS_SMEM = FS_A_BYTES + 2 * FS_STAGE + FS_OUT_BYTES + 256;
-constexpr uint32_t FS_TMEM_COLS = 256;                   // 2 buffers x (main + correction) x 64 columns
+constexpr uint32_t FS_TMEM_COLS = 512;                   // accumulators: 2 buffers x (main + correction) x 64; A: 2 x 72
 constexpr uint32_t FS_LBO = 128, FS_SBO = 1024, FS_SBO_AUG = 256;
 
 __device__ __forceinline__ float fs_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
@@ -74,7 +76,6 @@ __device__ __forceinline__ void fs_store_split(uint8_t* hi_base, uint8_t* lo_bas
 
 __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* a_s = smem;
     uint8_t* stage0 = smem + FS_A_BYTES;
     float* out_s = reinterpret_cast<float*>(smem + FS_A_BYTES + 2 * FS_STAGE);
     uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + FS_A_BYTES + 2 * FS_STAGE + FS_OUT_BYTES);
@@ -100,21 +101,42 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
     }
     if (warp == 8) tc::tmem_alloc(tmem_slot, FS_TMEM_COLS);
 
-    // user tile: 128 rows x (64 factors + augmentation), split once (all threads)
-    for (int i = tid; i < FS_BM * 18; i += FS_NT) {
-        const int r = i / 18, q = i - r * 18;
-        const int64_t u = min(u0 + r, (int64_t)prm.n_users - 1);
-        float4 v;
-        if (q < 16) v = ldg4(prm.A + (size_t)u * D + q * 4);
-        else if (q == 16) v = make_float4((prm.row_bias ? __ldg(prm.row_bias + u) : 0.f) + prm.g, 1.f, 0.f, 0.f);
-        else v = make_float4(0.f, 0.f, 0.f, 0.f);
-        fs_store_split(a_s, a_s + FS_A_HALF, FS_A_IMG, r, q * 4, v);
-    }
-    tc::fence_proxy_async_smem();
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+
+    // user tile -> tensor memory, once: A'[u] = [A[u,:], row_bias[u] + g, 1, 0..] as 72 columns of lane u;
+    // warps 0-3 write the hi parts, warps 4-7 the lo parts (a warp reaches the 32 lanes of its quarter)
+    if (warp < 8) {
+        const int r = (warp & 3) * 32 + lane;
+        const bool lo_part = warp >= 4;
+        const int64_t u = min(u0 + r, (int64_t)prm.n_users - 1);
+        const uint32_t col0 = lo_part ? FS_TM_ALO : FS_TM_AHI;
+#pragma unroll
+        for (int c8 = 0; c8 < FS_KAUG / 8; ++c8) {
+            float v[8];
+            if (c8 < 8) {
+                const float4 x0 = ldg4(prm.A + (size_t)u * D + c8 * 8), x1 = ldg4(prm.A + (size_t)u * D + c8 * 8 + 4);
+                v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+            } else {
+                v[0] = (prm.row_bias ? __ldg(prm.row_bias + u) : 0.f) + prm.g;
+                v[1] = 1.f;
+                v[2] = v[3] = v[4] = v[5] = v[6] = v[7] = 0.f;
+            }
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float hi = fs_hi(v[j]);
+                w[j] = __float_as_uint(lo_part ? __fsub_rn(v[j], hi) : hi);
+            }
+            tc::tmem_st_32x8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + col0 + c8 * 8, w);
+        }
+        tc::tmem_wait_st();
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
 
     if (warp >= 4 && warp < 8) {
         // ===== item-tile staging: thread = (item, half of K) =====
@@ -150,7 +172,6 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = tc::make_idesc_tf32(FS_BM, FS_BN);
-            const uint32_t a_hi0 = tc::smem_u32(a_s), a_lo0 = a_hi0 + FS_A_HALF;
             for (int t = t_lo; t < t_hi; ++t) {
                 const int n = t - t_lo, s = n & 1;
                 const uint32_t ph = (uint32_t)(n >> 1) & 1u;
@@ -163,16 +184,15 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
 #pragma unroll
                 for (int ks = 0; ks < 9; ++ks) {
                     // k-steps 0..7: the two [rows x 32] images; k-step 8: the [rows x 8] augmentation image
-                    const uint32_t a_off = ks < 8 ? (uint32_t)(ks >> 2) * FS_A_IMG + (uint32_t)(ks & 3) * 2 * FS_LBO : 2 * FS_A_IMG;
                     const uint32_t b_off = ks < 8 ? (uint32_t)(ks >> 2) * FS_B_IMG + (uint32_t)(ks & 3) * 2 * FS_LBO : 2 * FS_B_IMG;
                     const uint32_t sbo = ks < 8 ? FS_SBO : FS_SBO_AUG;
-                    const uint64_t a_hi = tc::make_smem_desc(a_hi0 + a_off, FS_LBO, sbo);
-                    const uint64_t a_lo = tc::make_smem_desc(a_lo0 + a_off, FS_LBO, sbo);
+                    const uint32_t a_hi = tmem_base + FS_TM_AHI + (uint32_t)ks * 8;     // 8 K columns per MMA
+                    const uint32_t a_lo = tmem_base + FS_TM_ALO + (uint32_t)ks * 8;
                     const uint64_t b_hi = tc::make_smem_desc(b_hi0 + b_off, FS_LBO, sbo);
                     const uint64_t b_lo = tc::make_smem_desc(b_lo0 + b_off, FS_LBO, sbo);
-                    tc::umma_tf32(d_corr, a_lo, b_hi, idesc, ks != 0);
-                    tc::umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
-                    tc::umma_tf32(d_main, a_hi, b_hi, idesc, ks != 0);
+                    tc::umma_tf32_ts(d_corr, a_lo, b_hi, idesc, ks != 0);
+                    tc::umma_tf32_ts(d_corr, a_hi, b_lo, idesc, 1u);
+                    tc::umma_tf32_ts(d_main, a_hi, b_hi, idesc, ks != 0);
                 }
                 tc::umma_commit(&b_empty[s]);
                 tc::umma_commit(&acc_full[s]);
