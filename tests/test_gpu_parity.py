@@ -598,3 +598,45 @@ def test_resident_epoch_equals_step_by_step():
     assert np.array_equal(outs[0][2], outs[1][2])           # the CPU generator ends in the same state
     for k in ('E_user', 'E_item', 'W', 'b'):
         assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
+
+
+def test_fused_adam_step_record_lists():
+    """dccf_adam_step (the kernel the training step uses): rows with 1, 2, 50 (ranked in shared memory) and 300
+    (longer than the list buffer: repeated walks) records, two tables + two dense tensors in one launch; result
+    identical to the per-tensor entry points and to the oracle."""
+    from dccf_b200 import kernels
+    rs = np.random.RandomState(12)
+    rows, n_rec = 700, 900
+    keys = rs.randint(0, rows, size=n_rec).astype(np.int32)
+    keys[:300] = 17
+    keys[300:350] = 99
+    keys = keys[rs.permutation(n_rec)]
+    grads = (rs.standard_normal((n_rec, 64)) * 0.01).astype(np.float32)
+    table = (rs.standard_normal((rows, 64)) * 0.05).astype(np.float32)
+    dense = np.zeros((rows, 64), dtype=np.float32)
+    for r in range(n_rec):
+        dense[keys[r]] += grads[r]
+    want_p, want_m, want_v = O.adam_step(table, dense, np.zeros_like(table), np.zeros_like(table), 3)
+    Wd = (rs.standard_normal(5000) * 0.05).astype(np.float32)
+    gparts = (rs.standard_normal((4, 5000)) * 0.01).astype(np.float32)
+    want_W, _, _ = O.adam_step(Wd, gparts.sum(0), np.zeros_like(Wd), np.zeros_like(Wd), 3)
+    hp = kernels.make_adam(1e-3, 1e-4, 1e-4, step=3)
+    res = []
+    for fused in (True, False):
+        t = torch.from_numpy(table).cuda(); m = torch.zeros_like(t); v = torch.zeros_like(t)
+        w = torch.from_numpy(Wd).cuda(); wm = torch.zeros_like(w); wv = torch.zeros_like(w)
+        head = torch.full((rows,), -1, dtype=torch.int32, device='cuda')
+        nxt = torch.empty(n_rec, dtype=torch.int32, device='cuda')
+        k_d, g_d, gp_d = torch.from_numpy(keys).cuda(), torch.from_numpy(grads).cuda(), torch.from_numpy(gparts).cuda()
+        if fused:
+            kernels.adam_step([kernels.adam_table(t, m, v, k_d, g_d, 1, n_rec, n_rec, n_rec * 64, head, nxt)],
+                              [kernels.adam_tensor(w, wm, wv, gp_d, 4, 5000)], hp)
+        else:
+            kernels.adam_sweep(t, m, v, k_d, g_d, n_rec, head, nxt, hp)
+            kernels.adam_dense(w, wm, wv, gp_d, 4, 5000, hp)
+        assert int((head != -1).sum()) == 0
+        res.append((t.cpu().numpy(), m.cpu().numpy(), v.cpu().numpy(), w.cpu().numpy()))
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+    assert rel_err(res[0][1], want_m) < 1e-6 and rel_err(res[0][2], want_v) < 1e-6
+    assert rel_err(res[0][0], want_p) < 1e-5 and rel_err(res[0][3], want_W) < 1e-5
