@@ -11,7 +11,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libdccf_b200.so')
-ABI_VERSION = 12
+ABI_VERSION = 13
 DIM = 64
 
 
@@ -21,7 +21,8 @@ class DccfError(RuntimeError):
 
 class Dims(ctypes.Structure):
     _fields_ = [('n_users', ctypes.c_int32), ('n_items', ctypes.c_int32), ('dim', ctypes.c_int32),
-                ('feat_dim', ctypes.c_int32), ('n_samples', ctypes.c_int32), ('n_attr', ctypes.c_int32)]
+                ('feat_dim', ctypes.c_int32), ('n_samples', ctypes.c_int32), ('n_attr', ctypes.c_int32),
+                ('user_base', ctypes.c_int32), ('_pad', ctypes.c_int32)]
 
 
 class Expo(ctypes.Structure):

@@ -45,6 +45,7 @@ struct BwdParams {
     int32_t* rec_keys_i;
     int64_t n_pairs, n_rows;
     int32_t n_users, n_items, F, S, A, Z, R;
+    int32_t user_base;
     int32_t noise_mode, mask_mode, loss_mode;
     int32_t n_chunks;        // (D+F)/64
     int32_t n_splits;        // row splits
@@ -110,7 +111,7 @@ __device__ void bwd_gw_role(const BwdParams& prm, int chunk, int split) {
         const int64_t p = r / prm.R;
         const int rem = (int)(r - p * prm.R);
         const int z = rem / prm.A;
-        const int32_t u = checked_id(prm.X[2 * p], prm.n_users, nullptr);
+        const int32_t u = checked_id(prm.X[2 * p] - prm.user_base, prm.n_users, nullptr);
         const int32_t fi = checked_id(prm.X[2 * p + 1], prm.n_items, nullptr);
         w.ds = dpred_of(prm, p) * __ldg(prm.save_w + p * prm.Z + z) * prm.inv_A;
         w.h0 = ldg4(prm.save_h + (size_t)r * D + fc);
@@ -220,7 +221,7 @@ __device__ void bwd_record_role(const BwdParams& prm, int cta) {
 
     const int64_t p = (int64_t)cta * BWD_WARPS + warp;
     if (p >= prm.n_pairs) return;
-    const int32_t u = checked_id(prm.X[2 * p], prm.n_users, nullptr);
+    const int32_t u = checked_id(prm.X[2 * p] - prm.user_base, prm.n_users, nullptr);
     const int32_t fi = checked_id(prm.X[2 * p + 1], prm.n_items, nullptr);
     const float dp = dpred_of(prm, p);
     const int c = lane * 2;  // this lane's two columns
@@ -357,7 +358,7 @@ extern "C" int dccf_bpr_bwd(const dccf_dims* dims, const float* E_user, const fl
     prm.out_loss = out_loss; prm.gW_part = gW_part; prm.gb_part = gb_part; prm.gu_rec = gu_rec; prm.gi_rec = gi_rec;
     prm.rec_keys_u = rec_keys_u; prm.rec_keys_i = rec_keys_i;
     prm.n_pairs = n_pairs;
-    prm.n_users = dims->n_users; prm.n_items = dims->n_items; prm.F = dims->feat_dim; prm.S = dims->n_samples;
+    prm.n_users = dims->n_users; prm.user_base = dims->user_base; prm.n_items = dims->n_items; prm.F = dims->feat_dim; prm.S = dims->n_samples;
     prm.A = dims->n_attr; prm.Z = dims->n_samples + 1; prm.R = prm.Z * prm.A;
     prm.n_rows = n_pairs * prm.R;
     DCCF_CHECK_ARG(prm.n_rows < (int64_t)1 << 31, "dccf_bpr_bwd: %lld rows in one call (max 2^31-1)", (long long)prm.n_rows);

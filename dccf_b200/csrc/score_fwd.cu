@@ -44,6 +44,7 @@ struct FwdParams {
     int32_t* err_flag;
     int64_t n_rows;
     int32_t n_users, n_items, F, S, A, R;
+    int32_t user_base;
     int32_t mask_mode;
     float noise_std, keep_prob, drop_scale;
     RngSpec rng;
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(FWD_NT) k_row_scores(const FwdParams prm) {
         const int64_t p = my_row / prm.R;
         const int rem = (int)(my_row - p * prm.R);
         const int z = rem / prm.A;
-        const int32_t u = checked_id(prm.X[2 * p], prm.n_users, prm.err_flag);
+        const int32_t u = checked_id(prm.X[2 * p] - prm.user_base, prm.n_users, prm.err_flag);
         const int32_t fi = checked_id(prm.X[2 * p + 1], prm.n_items, prm.err_flag);
         const int32_t it = (z == 0) ? fi : checked_id(prm.sample_item[p * prm.S + (z - 1)], prm.n_items, prm.err_flag);
         u_row_s[tid] = u;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(SK_NT) k_row_scores_splitk(const FwdParams prm
         const int64_t p = my_row / prm.R;
         const int rem = (int)(my_row - p * prm.R);
         const int z = rem / prm.A;
-        const int32_t u = checked_id(prm.X[2 * p], prm.n_users, prm.err_flag);
+        const int32_t u = checked_id(prm.X[2 * p] - prm.user_base, prm.n_users, prm.err_flag);
         const int32_t fi = checked_id(prm.X[2 * p + 1], prm.n_items, prm.err_flag);
         const int32_t it = (z == 0) ? fi : checked_id(prm.sample_item[p * prm.S + (z - 1)], prm.n_items, prm.err_flag);
         if (warp == 0) u_row_s[lane] = u;
@@ -378,14 +379,14 @@ __device__ __forceinline__ float expo_value(const dccf_expo& ex, int32_t u, int3
 // pred[p] = (1/A) sum_z softmax_z(expo[u, item_z]) sum_a s[p,z,a]   — one warp per pair, shuffle reductions.
 __global__ void __launch_bounds__(256) k_backdoor(const dccf_expo ex, const int64_t* __restrict__ X,
                                                   const int64_t* __restrict__ sample_item, int64_t n_pairs,
-                                                  int32_t n_users, int32_t n_items, int32_t S, int32_t A,
+                                                  int32_t n_users, int32_t user_base, int32_t n_items, int32_t S, int32_t A,
                                                   const float* __restrict__ ws_rows, float* __restrict__ out_pred,
                                                   float* __restrict__ save_w, int32_t* err_flag) {
     const int lane = threadIdx.x & 31;
     const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (p >= n_pairs) return;  // warp-uniform
     const int Z = S + 1, R = Z * A;
-    const int32_t u = checked_id(X[2 * p], n_users, err_flag);
+    const int32_t u = checked_id(X[2 * p] - user_base, n_users, err_flag);
 
     float mx = -INFINITY;
     for (int l = lane; l < R; l += 32) {
@@ -426,7 +427,7 @@ void launch_backdoor(const dccf_expo* expo, const int64_t* X, const int64_t* sam
                      cudaStream_t stream) {
     const int warps_per_cta = 8;
     k_backdoor<<<(unsigned)((n_pairs + warps_per_cta - 1) / warps_per_cta), warps_per_cta * 32, 0, stream>>>(
-        *expo, X, sample_item, n_pairs, dims->n_users, dims->n_items, dims->n_samples, dims->n_attr, ws_rows, out_pred,
+        *expo, X, sample_item, n_pairs, dims->n_users, dims->user_base, dims->n_items, dims->n_samples, dims->n_attr, ws_rows, out_pred,
         save_w, err_flag);
 }
 
@@ -465,7 +466,7 @@ extern "C" int dccf_score_fwd(const dccf_dims* dims, const float* E_user, const 
     prm.E_user = E_user; prm.E_item = E_item; prm.Feat = Feat; prm.Wt = ws_wt; prm.bias = b;
     prm.X = X; prm.sample_item = sample_item; prm.noise = rng->noise; prm.mask = rng->mask;
     prm.ws_rows = ws_rows; prm.save_h = save_h; prm.err_flag = err_flag; prm.n_rows = n_rows;
-    prm.n_users = dims->n_users; prm.n_items = dims->n_items; prm.F = dims->feat_dim;
+    prm.n_users = dims->n_users; prm.user_base = dims->user_base; prm.n_items = dims->n_items; prm.F = dims->feat_dim;
     prm.S = dims->n_samples; prm.A = dims->n_attr; prm.R = R;
     prm.mask_mode = rng->mask_mode;
     prm.noise_std = rng->noise_std;
@@ -495,7 +496,7 @@ extern "C" int dccf_score_fwd(const dccf_dims* dims, const float* E_user, const 
 
     const int warps_per_cta = 8;
     k_backdoor<<<(unsigned)((n_pairs + warps_per_cta - 1) / warps_per_cta), warps_per_cta * 32, 0, stream>>>(
-        *expo, X, sample_item, n_pairs, dims->n_users, dims->n_items, dims->n_samples, dims->n_attr, ws_rows, out_pred,
+        *expo, X, sample_item, n_pairs, dims->n_users, dims->user_base, dims->n_items, dims->n_samples, dims->n_attr, ws_rows, out_pred,
         save_w, err_flag);
     DCCF_CHECK_LAUNCH("k_backdoor");
     return DCCF_OK;

@@ -157,6 +157,7 @@ struct TcParams {
     int32_t* err_flag;
     int64_t n_rows;
     int32_t n_users, n_items, F, S, A, R;
+    int32_t user_base;
     int32_t mask_mode;
     float noise_std, keep_prob, drop_scale;
     RngSpec rng;
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_row_scores_tc(const TcParams prm) 
         const int64_t p = grow / prm.R;
         const int rem = (int)(grow - p * prm.R);
         const int z = rem / prm.A;
-        const int32_t u = checked_id(prm.X[2 * p], prm.n_users, prm.err_flag);
+        const int32_t u = checked_id(prm.X[2 * p] - prm.user_base, prm.n_users, prm.err_flag);
         const int32_t fi = checked_id(prm.X[2 * p + 1], prm.n_items, prm.err_flag);
         const int32_t it = (z == 0) ? fi : checked_id(prm.sample_item[p * prm.S + (z - 1)], prm.n_items, prm.err_flag);
         const float* pi = prm.PI + (size_t)(prm.batch_tables ? (p * (prm.S + 1) + z) : (int64_t)it) * D;
@@ -445,7 +446,7 @@ static int tc_launch(const dccf_dims* dims, const float* E_user, const float* PI
     prm.E_user = E_user; prm.PI = PI; prm.PF = PF; prm.gB = gB; prm.X = X; prm.sample_item = sample_item;
     prm.noise = rng->noise; prm.mask = rng->mask; prm.ws_rows = ws_rows; prm.save_h = save_h; prm.batch_tables = batch_tables;
     prm.dbg_pre = dbg_pre; prm.err_flag = err_flag;
-    prm.n_rows = n_rows; prm.n_users = dims->n_users; prm.n_items = dims->n_items; prm.F = dims->feat_dim;
+    prm.n_rows = n_rows; prm.n_users = dims->n_users; prm.user_base = dims->user_base; prm.n_items = dims->n_items; prm.F = dims->feat_dim;
     prm.S = dims->n_samples; prm.A = dims->n_attr; prm.R = R; prm.mask_mode = rng->mask_mode;
     prm.noise_std = rng->noise_std; prm.keep_prob = 1.0f - rng->p_drop;
     prm.drop_scale = (rng->p_drop < 1.0f) ? 1.0f / (1.0f - rng->p_drop) : 0.0f;

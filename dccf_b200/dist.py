@@ -26,12 +26,16 @@ class GradExchange(object):
     P pairs per rank and step, Z slots, D embedding width, K = D + F columns of W.  Offsets are in 4-byte
     elements; the key arrays are int32 views of the same float32 buffer."""
 
-    def __init__(self, P, Z, D, K, world, rank, device, group=None, use_p2p=True):
+    def __init__(self, P, Z, D, K, world, rank, device, group=None, use_p2p=True, user_records=True):
         self.P, self.Z, self.D, self.K = P, Z, D, K
         self.world, self.rank, self.group = world, rank, group
+        # user_records=False: the user table is row-sharded and each rank only trains its own users, so the
+        # user-row gradients never leave the rank (SURVEY.md §8e, scaled config)
+        self.user_records = user_records
+        Pu = P if user_records else 0
         off = 0
         self.off = {}
-        for name, n in (('gu', P * D), ('gi', P * Z * D), ('gW', D * K), ('gb', D), ('keys_u', P),
+        for name, n in (('gu', Pu * D), ('gi', P * Z * D), ('gW', D * K), ('gb', D), ('keys_u', Pu),
                         ('keys_i', P * Z), ('loss', 1)):
             self.off[name] = (off, n)
             off += (n + 3) // 4 * 4                      # keep every part 16-byte aligned
@@ -77,7 +81,7 @@ class GradExchange(object):
 
     def send_views(self):
         D = self.D
-        return {'gu_rec': self.part(self.send, 'gu').view(self.P, D),
+        return {'gu_rec': self.part(self.send, 'gu').view(-1, D),
                 'gi_rec': self.part(self.send, 'gi').view(self.P * self.Z, D),
                 'gW': self.part(self.send, 'gW').view(D, self.K), 'gb': self.part(self.send, 'gb'),
                 'keys_u': self.part(self.send, 'keys_u'), 'keys_i': self.part(self.send, 'keys_i'),

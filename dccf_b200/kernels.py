@@ -14,8 +14,9 @@ D = _lib.DIM
 LAUNCHES = [0]
 
 
-def make_dims(n_users, n_items, feat_dim, n_samples, n_attr, dim=D):
-    return Dims(int(n_users), int(n_items), int(dim), int(feat_dim), int(n_samples), int(n_attr))
+def make_dims(n_users, n_items, feat_dim, n_samples, n_attr, dim=D, user_base=0):
+    """n_users = rows of the (local) user table; user_base = first global uid it holds (row-sharded tables)."""
+    return Dims(int(n_users), int(n_items), int(dim), int(feat_dim), int(n_samples), int(n_attr), int(user_base), 0)
 
 
 def make_expo(dense=None, ipsmf=None):

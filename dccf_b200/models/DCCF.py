@@ -42,7 +42,7 @@ class FusedAdamState(object):
         self.exp_avg = {k: torch.zeros_like(p.data) for k, p in self.params.items()}
         self.exp_avg_sq = {k: torch.zeros_like(p.data) for k, p in self.params.items()}
         dev = model.uid_embeddings.weight.device
-        self.head_u = torch.full((model.user_num,), -1, dtype=torch.int32, device=dev)
+        self.head_u = torch.full((model.uid_embeddings.weight.shape[0],), -1, dtype=torch.int32, device=dev)
         self.head_i = torch.full((model.item_num,), -1, dtype=torch.int32, device=dev)
 
     def hp(self, step=None):
@@ -92,7 +92,7 @@ class DCCF(DMF):
 
     def __init__(self, path, dataset, sentence_model, sample_num, attribute_num, std, label_min, label_max,
                  feature_num, user_num, item_num, u_vector_size, i_vector_size, n_layers, random_seed, model_path,
-                 feature_embedding=None, expo_prob=None, expo_factors=None):
+                 feature_embedding=None, expo_prob=None, expo_factors=None, user_shard=None):
         """Reference constructor arguments (src/main.py:137-145).  The three trailing keyword arguments
         are additions: in-memory tables instead of the .npy files, and IPSBiasedMF factors for
         on-the-fly exposure (scaled config) instead of the dense user x item matrix."""
@@ -103,6 +103,10 @@ class DCCF(DMF):
         self.attribute_num = attribute_num
         self.std = std
         self._given = (feature_embedding, expo_prob, expo_factors)
+        # row-sharded user table (scaled config): this rank owns global users [lo, hi); the
+        # embedding, its Adam state, the exposure rows / IPS-MF user factors hold only those rows and every
+        # batch it is given must contain only those users
+        self.user_shard = None if user_shard is None else (int(user_shard[0]), int(user_shard[1]))
         DMF.__init__(self, label_min=label_min, label_max=label_max, feature_num=feature_num, user_num=user_num,
                      item_num=item_num, u_vector_size=u_vector_size, i_vector_size=i_vector_size, n_layers=n_layers,
                      random_seed=random_seed, model_path=model_path)
@@ -123,7 +127,8 @@ class DCCF(DMF):
         identically and `apply(init_paras)` yields the reference's initial weights for a given seed."""
         feature_embedding, expo_prob, expo_factors = self._given
         dev = self._table_device()
-        self.uid_embeddings = torch.nn.Embedding(self.user_num, self.ui_vector_size)
+        lo, hi = self.user_shard if self.user_shard is not None else (0, self.user_num)
+        self.uid_embeddings = torch.nn.Embedding(hi - lo, self.ui_vector_size)
         self.iid_embeddings = torch.nn.Embedding(self.item_num, self.ui_vector_size)
         if feature_embedding is None:
             feature_embedding = np.load(os.path.join(self.path, self.dataset + '_' + self.sentence_model + '.npy'))
@@ -135,19 +140,29 @@ class DCCF(DMF):
             self.mlp.append(torch.nn.Linear(self.ui_vector_size, self.ui_vector_size))
         self.expo_factors = None
         self.expo_prob = None
+        def local_rows(t):      # a per-user array given for ALL users is cut down to this rank's rows
+            return t[lo:hi] if (self.user_shard is not None and t.shape[0] == self.user_num) else t
+
         if expo_factors is not None:
-            self.expo_factors = {k: (torch.as_tensor(v, dtype=torch.float32).to(dev).contiguous()
-                                     if k not in ('mf_global_bias', 'mf_min_propensity') else float(v))
-                                 for k, v in expo_factors.items()}
+            self.expo_factors = {}
+            for k, v in expo_factors.items():
+                if k in ('mf_global_bias', 'mf_min_propensity'):
+                    self.expo_factors[k] = float(v)
+                else:
+                    v = torch.as_tensor(v, dtype=torch.float32)
+                    if k in ('mf_user', 'mf_user_bias'):
+                        v = local_rows(v)
+                    self.expo_factors[k] = v.to(dev).contiguous()
         else:
             if expo_prob is None:
-                expo_prob = np.load(os.path.join(self.path, self.dataset + '.ips_expo_prob.npy'))
-            self.expo_prob = torch.as_tensor(expo_prob, dtype=torch.float32).to(dev).contiguous()
+                expo_prob = np.load(os.path.join(self.path, self.dataset + '.ips_expo_prob.npy'), mmap_mode='r')
+            self.expo_prob = torch.as_tensor(np.asarray(local_rows(expo_prob)), dtype=torch.float32).to(dev).contiguous()
 
     # ---- kernel plumbing ---------------------------------------------------------------------
     def _dims(self):
-        return kernels.make_dims(self.user_num, self.item_num, self.feature_embedding.shape[1], self.sample_num,
-                                 self.attribute_num, dim=self.ui_vector_size)
+        lo = self.user_shard[0] if self.user_shard is not None else 0
+        return kernels.make_dims(self.uid_embeddings.weight.shape[0], self.item_num, self.feature_embedding.shape[1],
+                                 self.sample_num, self.attribute_num, dim=self.ui_vector_size, user_base=lo)
 
     def _expo(self):
         if self.expo_factors is not None:
@@ -302,6 +317,9 @@ class DCCF(DMF):
             v = ex.send_views()
             rec.update({'gu_rec': v['gu_rec'], 'gi_rec': v['gi_rec'], 'keys_u': v['keys_u'], 'keys_i': v['keys_i'],
                         'loss': v['loss'], 'exchange': ex, 'send': v})
+            if not ex.user_records:      # row-sharded user table: user-row gradients stay on this rank
+                rec['gu_rec'] = self._buf('gu_rec', (P, D), torch.float32)
+                rec['keys_u'] = self._buf('keys_u', (P,), torch.int32)
         else:
             rec.update({'gu_rec': self._buf('gu_rec', (P, D), torch.float32),
                         'gi_rec': self._buf('gi_rec', (P * Z, D), torch.float32),
@@ -413,7 +431,7 @@ class DCCF(DMF):
             D, Z = self.ui_vector_size, self.sample_num + 1
             ex = GradExchange(P, Z, D, D + self.feature_embedding.shape[1], self._dp['world'], self._dp['rank'],
                               self.uid_embeddings.weight.device, group=self._dp['group'],
-                              use_p2p=self._dp.get('p2p', True))
+                              use_p2p=self._dp.get('p2p', True), user_records=self.user_shard is None)
             self._dp['ex'][P] = ex
         return ex
 
@@ -434,10 +452,16 @@ class DCCF(DMF):
             kernels.sum_parts(rec['gb_part'], rec['n_splits'], b.numel(), b.numel(), v['gb'])
             recv = ex.exchange()
             world, seg = ex.world, ex.seg
+            if ex.user_records:
+                user_table = kernels.adam_table(eu, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'],
+                                                ex.part(recv, 'keys_u'), ex.part(recv, 'gu'), world, P, seg, seg,
+                                                opt.head_u, self._buf('next_u', (world * P,), torch.int32))
+            else:
+                user_table = kernels.adam_table(eu, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'], rec['keys_u'],
+                                                rec['gu_rec'], 1, P, P, P * self.ui_vector_size, opt.head_u,
+                                                self._buf('next_u', (P,), torch.int32))
             tables = [
-                kernels.adam_table(eu, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'], ex.part(recv, 'keys_u'),
-                                   ex.part(recv, 'gu'), world, P, seg, seg, opt.head_u,
-                                   self._buf('next_u', (world * P,), torch.int32)),
+                user_table,
                 kernels.adam_table(ei, opt.exp_avg['E_item'], opt.exp_avg_sq['E_item'], ex.part(recv, 'keys_i'),
                                    ex.part(recv, 'gi'), world, P * Z, seg, seg, opt.head_i,
                                    self._buf('next_i', (world * P * Z,), torch.int32))]

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 12
+#define DCCF_ABI_VERSION 13
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -43,6 +43,10 @@ typedef struct dccf_dims {
     int32_t feat_dim;  /* F, multiple of 64 */
     int32_t n_samples; /* S  (--sample-num) */
     int32_t n_attr;    /* A  (--attribute-num) */
+    int32_t user_base; /* row-sharded user table: this rank owns global users [user_base, user_base + n_users);
+                          E_user, the dense expo rows / IPS-MF user factors and the user gradient records are
+                          indexed by uid - user_base.  0 when the table is not sharded. */
+    int32_t _pad;
 } dccf_dims;
 
 /* Exposure source for softmax_z(expo_prob[u, item_z])  (src/models/DCCF.py:64,98). */
