@@ -11,7 +11,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libdccf_b200.so')
-ABI_VERSION = 13
+ABI_VERSION = 14
 DIM = 64
 
 
@@ -79,6 +79,14 @@ _SIGNATURES = {
     'dccf_bwd_splits': (ctypes.c_int32, [ctypes.c_int64]),
     'dccf_bpr_bwd': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64,
                                     ctypes.POINTER(Rng), ctypes.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'dccf_train_w_image_floats': (ctypes.c_int64, [ctypes.c_int32]),
+    'dccf_train_fwd_ksplits': (ctypes.c_int32, [ctypes.c_int64, ctypes.c_int32]),
+    'dccf_train_bwd_splits': (ctypes.c_int32, [ctypes.c_int64, ctypes.c_int32]),
+    'dccf_train_fwd_tc': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, _P, _P, _P, ctypes.POINTER(Expo), _P, _P,
+                                         ctypes.c_int64, ctypes.POINTER(Rng), _P, _P, _P, _P, _P, _P, _P, _P]),
+    'dccf_train_bwd_tc': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64,
+                                         ctypes.POINTER(Rng), ctypes.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                         _P, _P]),
     'dccf_adam_sweep': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int64, _P, _P,
                                        ctypes.POINTER(Adam), _P]),
     'dccf_adam_sweep_seg': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int32, ctypes.c_int64,

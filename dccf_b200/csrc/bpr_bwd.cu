@@ -43,6 +43,7 @@ struct BwdParams {
     float* gi_rec;
     int32_t* rec_keys_u;
     int32_t* rec_keys_i;
+    float* dpre_rows;        // optional [N, D]: d loss / d pre-activation of every row (operand of the tensor-core dW kernel)
     int64_t n_pairs, n_rows;
     int32_t n_users, n_items, F, S, A, Z, R;
     int32_t user_base;
@@ -246,8 +247,10 @@ __device__ void bwd_record_role(const BwdParams& prm, int cta) {
                 gx = h.x > 0.f ? s : 0.f;
                 gy = h.y > 0.f ? s : 0.f;
             }
-            dsum.x += ds * eu.x * gx;
-            dsum.y += ds * eu.y * gy;
+            const float dx = ds * eu.x * gx, dy = ds * eu.y * gy;
+            dsum.x += dx;
+            dsum.y += dy;
+            if (prm.dpre_rows != nullptr) *reinterpret_cast<float2*>(prm.dpre_rows + (size_t)r * D + c) = make_float2(dx, dy);
         }
         // gi[k] = sum_j W[j][k] * dsum[j]
         float2 gi = make_float2(0.f, 0.f);
@@ -310,6 +313,12 @@ __global__ void __launch_bounds__(BWD_NT) k_bpr_bwd(const BwdParams prm) {
 
 // number of row splits for N rows: enough CTAs to cover the 148 SMs about twice, at least 64 rows each
 // (four per SM was measured: no faster, and the Adam kernel then reads twice the partial sums)
+int bpr_bwd_launch(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat, const float* W,
+                   const int64_t* X, const int64_t* sample_item, const float* Y, int64_t n_pairs, const dccf_rng* rng,
+                   int32_t loss_mode, const float* pred, const float* save_h, const float* save_w, float* out_loss,
+                   float* gW_part, float* gb_part, float* gu_rec, float* gi_rec, int32_t* rec_keys_u, int32_t* rec_keys_i,
+                   float* dpre_rows, bool with_gw, cudaStream_t stream);
+
 static int32_t bwd_splits_for(int64_t n_rows, int n_chunks) {
     if (n_rows <= 0) return 1;
     const int64_t max_by_rows = (n_rows + 63) / 64;
@@ -329,19 +338,21 @@ extern "C" int32_t dccf_bwd_splits(int64_t n_rows) {
     return bwd_splits_for(n_rows, 13);
 }
 
-extern "C" int dccf_bpr_bwd(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
-                            const float* W, const int64_t* X, const int64_t* sample_item, const float* Y,
-                            int64_t n_pairs, const dccf_rng* rng, int32_t loss_mode, const float* pred,
-                            const float* save_h, const float* save_w, float* out_loss, float* gW_part, float* gb_part,
-                            float* gu_rec, float* gi_rec, int32_t* rec_keys_u, int32_t* rec_keys_i, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+// with_gw = false: only the record and loss roles run (the tensor-core path computes dW / db itself from
+// dpre_rows, see tc_train.cu); gW_part / gb_part may then be null.
+int dccf::bpr_bwd_launch(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
+                         const float* W, const int64_t* X, const int64_t* sample_item, const float* Y,
+                         int64_t n_pairs, const dccf_rng* rng, int32_t loss_mode, const float* pred,
+                         const float* save_h, const float* save_w, float* out_loss, float* gW_part, float* gb_part,
+                         float* gu_rec, float* gi_rec, int32_t* rec_keys_u, int32_t* rec_keys_i, float* dpre_rows,
+                         bool with_gw, cudaStream_t stream) {
     DCCF_CHECK_ARG(dims && rng, "dccf_bpr_bwd: null struct argument");
     DCCF_CHECK_ARG(dims->dim == D, "dccf_bpr_bwd: dim=%d but this build has D=%d", dims->dim, D);
     DCCF_CHECK_ARG(dims->feat_dim > 0 && dims->feat_dim % 64 == 0, "dccf_bpr_bwd: feat_dim=%d must be a positive multiple of 64", dims->feat_dim);
     DCCF_CHECK_ARG(dims->n_samples >= 0 && dims->n_attr >= 1, "dccf_bpr_bwd: bad n_samples/n_attr");
     DCCF_CHECK_ARG(loss_mode >= 0 && loss_mode <= 2, "dccf_bpr_bwd: loss_mode must be 0 (BPR), 1 (MSE) or 2 (external d loss/d pred in Y)");
-    DCCF_CHECK_ARG(E_user && E_item && Feat && W && X && pred && save_h && save_w && gW_part && gb_part &&
-                       gu_rec && gi_rec && rec_keys_u && rec_keys_i,
+    DCCF_CHECK_ARG(E_user && E_item && Feat && W && X && pred && save_h && save_w && gu_rec && gi_rec && rec_keys_u &&
+                       rec_keys_i && (!with_gw || (gW_part && gb_part)),
                    "dccf_bpr_bwd: null buffer");
     DCCF_CHECK_ARG(loss_mode == 2 || out_loss, "dccf_bpr_bwd: out_loss is null");
     DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item, "dccf_bpr_bwd: sample_item is null");
@@ -356,7 +367,7 @@ extern "C" int dccf_bpr_bwd(const dccf_dims* dims, const float* E_user, const fl
     prm.E_user = E_user; prm.E_item = E_item; prm.Feat = Feat; prm.W = W; prm.X = X; prm.sample_item = sample_item;
     prm.Y = Y; prm.noise = rng->noise; prm.mask = rng->mask; prm.pred = pred; prm.save_h = save_h; prm.save_w = save_w;
     prm.out_loss = out_loss; prm.gW_part = gW_part; prm.gb_part = gb_part; prm.gu_rec = gu_rec; prm.gi_rec = gi_rec;
-    prm.rec_keys_u = rec_keys_u; prm.rec_keys_i = rec_keys_i;
+    prm.rec_keys_u = rec_keys_u; prm.rec_keys_i = rec_keys_i; prm.dpre_rows = dpre_rows;
     prm.n_pairs = n_pairs;
     prm.n_users = dims->n_users; prm.user_base = dims->user_base; prm.n_items = dims->n_items; prm.F = dims->feat_dim; prm.S = dims->n_samples;
     prm.A = dims->n_attr; prm.Z = dims->n_samples + 1; prm.R = prm.Z * prm.A;
@@ -367,7 +378,7 @@ extern "C" int dccf_bpr_bwd(const dccf_dims* dims, const float* E_user, const fl
     prm.n_splits = dccf_bwd_splits(prm.n_rows);
     const int64_t rps = (prm.n_rows + prm.n_splits - 1) / prm.n_splits;
     prm.rows_per_split = (int32_t)(((rps + BWD_RC - 1) / BWD_RC) * BWD_RC);
-    prm.n_gw = prm.n_chunks * prm.n_splits;
+    prm.n_gw = with_gw ? prm.n_chunks * prm.n_splits : 0;
     prm.n_rec_ctas = (int32_t)((n_pairs + BWD_WARPS - 1) / BWD_WARPS);
     prm.noise_std = rng->noise_std;
     prm.drop_scale = (rng->p_drop < 1.0f) ? 1.0f / (1.0f - rng->p_drop) : 0.0f;
@@ -378,4 +389,14 @@ extern "C" int dccf_bpr_bwd(const dccf_dims* dims, const float* E_user, const fl
     k_bpr_bwd<<<grid, BWD_NT, 0, stream>>>(prm);
     DCCF_CHECK_LAUNCH("k_bpr_bwd");
     return DCCF_OK;
+}
+
+extern "C" int dccf_bpr_bwd(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
+                            const float* W, const int64_t* X, const int64_t* sample_item, const float* Y,
+                            int64_t n_pairs, const dccf_rng* rng, int32_t loss_mode, const float* pred,
+                            const float* save_h, const float* save_w, float* out_loss, float* gW_part, float* gb_part,
+                            float* gu_rec, float* gi_rec, int32_t* rec_keys_u, int32_t* rec_keys_i, void* stream_) {
+    return bpr_bwd_launch(dims, E_user, E_item, Feat, W, X, sample_item, Y, n_pairs, rng, loss_mode, pred, save_h, save_w,
+                          out_loss, gW_part, gb_part, gu_rec, gi_rec, rec_keys_u, rec_keys_i, nullptr, true,
+                          (cudaStream_t)stream_);
 }

@@ -6,6 +6,7 @@
 // their [E_item[item_z] | Feat[i] + eps] tile chunk by chunk in shared memory (noise generated in
 // registers when rng mode 2) and keeps the 128x64 pre-activations in registers.
 #include "common.cuh"
+#include "backdoor.cuh"
 
 namespace dccf {
 
@@ -355,28 +356,8 @@ __global__ void __launch_bounds__(SK_NT) k_row_scores_splitk(const FwdParams prm
     }
 }
 
-// ----------------------------------------------------------------------------------------------
-// exposure value of (user u, item it):  expo_prob[u, it]  or the IPSBiasedMF formula
-// (src/models/DCCF.py:98 lookup; src/models/IPSBiasedMF.py:42-53 on the fly)
-// ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ float expo_value(const dccf_expo& ex, int32_t u, int32_t it, int32_t n_items) {
-    if (ex.mode == 0) return __ldg(ex.dense + (size_t)u * n_items + it);
-    const float* pu = ex.mf_user + (size_t)u * D;
-    const float* qi = ex.mf_item + (size_t)it * D;
-    float dot = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < D; k += 4) {
-        const float4 a = ldg4(pu + k), b = ldg4(qi + k);
-        dot = fmaf(a.x, b.x, dot);
-        dot = fmaf(a.y, b.y, dot);
-        dot = fmaf(a.z, b.z, dot);
-        dot = fmaf(a.w, b.w, dot);
-    }
-    const float pred = dot + __ldg(ex.mf_user_bias + u) + __ldg(ex.mf_item_bias + it) + ex.mf_global_bias;
-    return pred / fmaxf(__ldg(ex.propensity + it), ex.mf_min_propensity);
-}
-
-// pred[p] = (1/A) sum_z softmax_z(expo[u, item_z]) sum_a s[p,z,a]   — one warp per pair, shuffle reductions.
+// pred[p] = (1/A) sum_z softmax_z(expo[u, item_z]) sum_a s[p,z,a]   — one warp per pair, shuffle reductions
+// (body in backdoor.cuh, shared with the fused epilogue of the tensor-core training forward).
 __global__ void __launch_bounds__(256) k_backdoor(const dccf_expo ex, const int64_t* __restrict__ X,
                                                   const int64_t* __restrict__ sample_item, int64_t n_pairs,
                                                   int32_t n_users, int32_t user_base, int32_t n_items, int32_t S, int32_t A,
@@ -385,37 +366,7 @@ __global__ void __launch_bounds__(256) k_backdoor(const dccf_expo ex, const int6
     const int lane = threadIdx.x & 31;
     const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (p >= n_pairs) return;  // warp-uniform
-    const int Z = S + 1, R = Z * A;
-    const int32_t u = checked_id(X[2 * p] - user_base, n_users, err_flag);
-
-    float mx = -INFINITY;
-    for (int l = lane; l < R; l += 32) {
-        const int z = l / A;
-        const int32_t it = checked_id(slot_item(X, sample_item, p, z, S), n_items, err_flag);
-        mx = fmaxf(mx, expo_value(ex, u, it, n_items));
-    }
-    mx = warp_max(mx);
-    float num = 0.f, den = 0.f;
-    for (int l = lane; l < R; l += 32) {
-        const int z = l / A;
-        const int32_t it = checked_id(slot_item(X, sample_item, p, z, S), n_items, err_flag);
-        const float e = expf(expo_value(ex, u, it, n_items) - mx);
-        num = fmaf(e, ws_rows[p * R + l], num);
-        den += e;
-    }
-    num = warp_sum(num);
-    den = warp_sum(den);  // = A * sum_z exp(.)
-    if (lane == 0) out_pred[p] = num / den;
-    if (save_w != nullptr) {
-        for (int l = lane; l < R; l += 32) {
-            if (l % A == 0) {
-                const int z = l / A;
-                const int32_t it = checked_id(slot_item(X, sample_item, p, z, S), n_items, err_flag);
-                const float e = expf(expo_value(ex, u, it, n_items) - mx);
-                save_w[p * Z + z] = e * (float)A / den;
-            }
-        }
-    }
+    backdoor_pair(ex, X, sample_item, p, lane, n_users, user_base, n_items, S, A, ws_rows, out_pred, save_w, err_flag);
 }
 
 void launch_transpose_w(const float* W, float* Wt, int K, cudaStream_t stream) {

@@ -1,0 +1,674 @@
+// tc_train.cu — the two large contractions of a TRAINING step on the tensor cores (tcgen05 / TMEM), spread over
+// every SM although a step has few rows (256 pairs = 5 632 predictor rows = 44 row tiles for 148 SMs).
+//
+// Forward (replaces src/models/DCCF.py:84-96 for the step's rows):
+//   pre[r,:] = W · [E_item[item_r] | Feat[i_r] + eps_r] + b
+//   grid = (row tiles of 128) x (K splits): CTA (t, ks) multiplies its 128 rows by the K range of split ks
+//   (32-wide chunks of the 832 columns) as an error-compensated 3xTF32 product and writes a PARTIAL
+//   pre-activation tile; k_train_fwd_finish (one CTA per pair) adds the partials and the bias, applies
+//   ReLU + dropout, saves h, dots with the user row and runs the backdoor-adjusted softmax sum of the pair.
+//
+// Backward (replaces the addmm backward of autograd, src/runners/BaseRunner.py:183):
+//   gW[c, k] = sum_r dpre[r, c] · x[r, k]          gb[c] = sum_r dpre[r, c]
+//   grid = (tiles of 128 columns of [x | 1]) x (row splits): the contraction index is the ROW, so the
+//   producers regenerate x (same Philox stream as the forward) and store it TRANSPOSED — a 4x4 register
+//   transpose across four lanes turns "4 columns of one row" into "4 rows of one column", which is one
+//   16-byte store into the same K-major core-matrix layout the forward uses (no MN-major descriptors).
+//   dpre comes from the record role of k_bpr_bwd (bpr_bwd.cu), which also produces the embedding-gradient
+//   records and the loss.  The bias gradient falls out of the same GEMM through a column of ones at k = K.
+#include <stdlib.h>
+
+#include "backdoor.cuh"
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_layout.cuh"
+
+namespace dccf {
+
+// ---------------------------------------------------------------------------------------------
+// W [D, K] -> per-chunk operand images [chunk][ hi 8 KB | lo 8 KB ], all K = D + F columns
+// ---------------------------------------------------------------------------------------------
+__global__ void k_prep_w_image(const float* __restrict__ W, int K, float* __restrict__ img) {
+    const int total = D * K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n = i / K, k = i - n * K;
+        const float w = __ldg(W + i);
+        const float hi = tf32_hi(w);
+        const int c = k / TC_KC, kk = k - c * TC_KC;
+        float* base = img + (size_t)c * (2 * TC_B_BYTES / 4);
+        const uint32_t off = core_offset(n, kk) / 4;
+        base[off] = hi;
+        base[TC_B_BYTES / 4 + off] = __fsub_rn(w, hi);
+    }
+}
+
+// store a float4 as its TF32 hi part and the exact remainder
+__device__ __forceinline__ void store_hi_lo(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, const float4& v) {
+    float4 hi, lo;
+    hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
+    lo.x = __fsub_rn(v.x, hi.x); lo.y = __fsub_rn(v.y, hi.y);
+    lo.z = __fsub_rn(v.z, hi.z); lo.w = __fsub_rn(v.w, hi.w);
+    *reinterpret_cast<float4*>(hi_base + off) = hi;
+    *reinterpret_cast<float4*>(lo_base + off) = lo;
+}
+
+// issue the 3xTF32 MMAs of one 32-wide stage (see tc_scores.cu for the accumulator rotation)
+__device__ __forceinline__ void issue_stage_mmas(uint32_t stage_addr, uint32_t tmem_base, int stage_index) {
+    constexpr uint32_t idesc = tc::make_idesc_tf32(TC_BM, D);
+    const uint32_t a_hi = stage_addr;
+    const uint32_t a_lo = a_hi + TC_A_BYTES;
+    const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
+    const uint32_t b_lo = b_hi + TC_B_BYTES;
+#pragma unroll
+    for (int j = 0; j < TC_KC / 8; ++j) {
+        const uint32_t ko = (uint32_t)j * 2 * TC_LBO;   // two core matrices per K=8 step
+        const uint64_t da_hi = tc::make_smem_desc(a_hi + ko, TC_LBO, TC_SBO);
+        const uint64_t da_lo = tc::make_smem_desc(a_lo + ko, TC_LBO, TC_SBO);
+        const uint64_t db_hi = tc::make_smem_desc(b_hi + ko, TC_LBO, TC_SBO);
+        const uint64_t db_lo = tc::make_smem_desc(b_lo + ko, TC_LBO, TC_SBO);
+        const int ks = stage_index * (TC_KC / 8) + j;
+        const uint32_t main_acc = tmem_base + (uint32_t)(1 + ks % (TC_NACC - 1)) * D;
+        tc::umma_tf32(tmem_base, da_lo, db_hi, idesc, ks != 0);
+        tc::umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
+        tc::umma_tf32(main_acc, da_hi, db_hi, idesc, ks >= TC_NACC - 1);
+    }
+}
+
+// accumulator columns [16*quarter, 16*quarter + 16) of this thread's TMEM lane: three main accumulators,
+// then the small correction terms, added in round-to-nearest FP32
+__device__ __forceinline__ void load_acc_quarter(uint32_t tmem_base, int warp, int quarter, float (&acc)[16]) {
+    float part[16];
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(quarter * 16);
+    tc::tmem_ld_32x16(lane_addr + 1 * D, acc);
+    tc::tmem_ld_32x16(lane_addr + 2 * D, part);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] += part[j];
+    tc::tmem_ld_32x16(lane_addr + 3 * D, part);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] += part[j];
+    tc::tmem_ld_32x16(lane_addr, part);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] += part[j];
+}
+
+// =============================================================================================
+// forward
+// =============================================================================================
+struct TrainFwdParams {
+    const float* E_item;
+    const float* Feat;
+    const float* gWimg;          // operand images of W, one per 32-wide chunk of K
+    const int64_t* X;
+    const int64_t* sample_item;
+    const float* noise;          // mode 1
+    float* pre_part;             // [n_ksplits][N][D]
+    int32_t* err_flag;
+    int64_t n_rows;
+    int32_t n_items, F, S, A, R;
+    int32_t n_chunks;            // (D + F) / 32
+    float noise_std;
+    RngSpec rng;
+};
+
+template <int NOISE_MODE>
+__global__ void __launch_bounds__(TC_NT, 1) k_train_fwd_tc(const TrainFwdParams prm) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + TC_STAGES;
+    uint64_t* accum_bar = empty_bar + TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t row_base = (int64_t)blockIdx.x * TC_BM;
+    const int ks = (int)blockIdx.y, n_ks = (int)gridDim.y;
+    const int c_lo = (int)(((int64_t)ks * prm.n_chunks) / n_ks);
+    const int c_hi = (int)(((int64_t)(ks + 1) * prm.n_chunks) / n_ks);
+    const int n_local = c_hi - c_lo;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            tc::mbar_init(&full_bar[s], TC_PRODUCERS / 32 + 1);   // producer warps + the expect_tx arrival
+            tc::mbar_init(&empty_bar[s], 1);                      // one tcgen05.commit
+        }
+        tc::mbar_init(accum_bar, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == TC_PRODUCERS / 32) tc::tmem_alloc(tmem_slot, TC_TMEM_COLS);
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < TC_PRODUCERS / 32) {
+        // ===== producers: thread = (row, quarter of the 32-wide K chunk) =====
+        const int row = tid & (TC_BM - 1), kq = tid >> 7;
+        const int64_t grow = min(row_base + row, prm.n_rows - 1);
+        const uint32_t p = (uint32_t)grow / (uint32_t)prm.R;
+        const int z = (int)((uint32_t)grow - p * (uint32_t)prm.R) / prm.A;
+        const int32_t fi = checked_id(prm.X[2 * (int64_t)p + 1], prm.n_items, prm.err_flag);
+        const int32_t it = (z == 0) ? fi : checked_id(prm.sample_item[(int64_t)p * prm.S + (z - 1)], prm.n_items, prm.err_flag);
+        const float* item_ptr = prm.E_item + (size_t)it * D + kq * 8;
+        const float* feat_ptr = prm.Feat + (size_t)fi * prm.F + kq * 8;
+        const float* nptr = (NOISE_MODE == 1) ? prm.noise + (size_t)grow * prm.F + kq * 8 : nullptr;
+        RngKey key_noise = make_rng_key(0, 0, DOMAIN_NOISE);
+        if (NOISE_MODE == 2) key_noise = resolve_rng_key(prm.rng, DOMAIN_NOISE);
+        for (int i = 0; i < n_local; ++i) {
+            const int c = c_lo + i;
+            const int s = i % TC_STAGES;
+            const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+            const int k0 = c * TC_KC;                 // first column of the chunk in [E_item | Feat]
+            float4 v[2];
+            if (k0 < D) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) v[q] = ldg4(item_ptr + k0 + 4 * q);
+            } else {
+                const int f0 = k0 - D;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) v[q] = ldg4(feat_ptr + f0 + 4 * q);
+                if (NOISE_MODE != 0) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        float4 e;
+                        if (NOISE_MODE == 1) e = ldg4(nptr + f0 + 4 * q);
+                        else e = noise_quad(key_noise, (uint32_t)grow, (uint32_t)(f0 / 4 + kq * 2 + q), prm.noise_std);
+                        v[q].x = __fadd_rn(v[q].x, e.x); v[q].y = __fadd_rn(v[q].y, e.y);
+                        v[q].z = __fadd_rn(v[q].z, e.z); v[q].w = __fadd_rn(v[q].w, e.w);
+                    }
+                }
+            }
+            tc::mbar_wait(&empty_bar[s], ph ^ 1u);   // the MMAs that read this stage have completed
+            uint8_t* a_hi = smem + s * TC_STAGE_BYTES;
+            uint8_t* a_lo = a_hi + TC_A_BYTES;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) store_hi_lo(a_hi, a_lo, core_offset(row, kq * 8 + 4 * q), v[q]);
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&full_bar[s]);
+        }
+    } else if (warp == TC_PRODUCERS / 32) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            for (int i = 0; i < n_local; ++i) {
+                const int s = i % TC_STAGES;
+                const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+                tc::mbar_wait(&full_bar[s], ph);
+                tc::tc_fence_after_sync();
+                issue_stage_mmas(tc::smem_u32(smem + s * TC_STAGE_BYTES), tmem_base, i);
+                tc::umma_commit(&empty_bar[s]);   // frees the stage when these MMAs have read it
+            }
+            tc::umma_commit(accum_bar);           // accumulators complete
+        }
+        __syncwarp();
+    } else {
+        // ===== W streamer (TMA engine bulk copies) =====
+        if (lane == 0) {
+            for (int i = 0; i < n_local; ++i) {
+                const int c = c_lo + i;
+                const int s = i % TC_STAGES;
+                const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+                tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+                tc::mbar_arrive_expect_tx(&full_bar[s], 2 * TC_B_BYTES);
+                tc::bulk_g2s(smem + s * TC_STAGE_BYTES + 2 * TC_A_BYTES, prm.gWimg + (size_t)c * (2 * TC_B_BYTES / 4),
+                             2 * TC_B_BYTES, &full_bar[s]);
+            }
+        }
+        __syncwarp();
+    }
+
+    // ===== epilogue: warps 0-3, thread = row = TMEM lane: the partial pre-activations of this K split =====
+    if (warp < 4) {
+        const int64_t grow = row_base + tid;
+        const bool valid = grow < prm.n_rows;
+        float* out = prm.pre_part + ((size_t)ks * (size_t)prm.n_rows + (size_t)(valid ? grow : 0)) * D;
+        if (n_local > 0) {
+            tc::mbar_wait(accum_bar, 0u);
+            tc::tc_fence_after_sync();
+        }
+#pragma unroll 1
+        for (int quarter = 0; quarter < 4; ++quarter) {
+            float acc[16];
+            if (n_local > 0) {
+                load_acc_quarter(tmem_base, warp, quarter, acc);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+            }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    st4(out + quarter * 16 + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+            }
+        }
+    }
+
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == TC_PRODUCERS / 32) tc::tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+// One CTA per pair: 8 half-warps take the pair's R rows (lane = 4 columns), then warp 0 runs the backdoor sum.
+struct TrainFinishParams {
+    dccf_expo ex;
+    const float* E_user;
+    const float* bias;
+    const int64_t* X;
+    const int64_t* sample_item;
+    const float* mask;           // mode 1
+    const float* pre_part;
+    float* ws_rows;
+    float* save_h;
+    float* save_w;
+    float* out_pred;
+    int32_t* err_flag;
+    int64_t n_pairs, n_rows;
+    int32_t n_users, user_base, n_items, S, A, R;
+    int32_t n_ksplits, mask_mode;
+    float keep_prob, drop_scale;
+    RngSpec rng;
+};
+
+__global__ void __launch_bounds__(128) k_train_fwd_finish(const TrainFinishParams prm) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int hw = tid >> 4, sub = tid & 15;
+    const int64_t p = blockIdx.x;
+    const int32_t u = checked_id(prm.X[2 * p] - prm.user_base, prm.n_users, prm.err_flag);
+    const float4 e = ldg4(prm.E_user + (size_t)u * D + sub * 4);
+    const float4 b = ldg4(prm.bias + sub * 4);
+    RngKey key_drop = make_rng_key(0, 0, DOMAIN_DROPOUT);
+    if (prm.mask_mode == 2) key_drop = resolve_rng_key(prm.rng, DOMAIN_DROPOUT);
+    const uint32_t half_mask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;
+    const size_t part_stride = (size_t)prm.n_rows * D;
+
+    for (int l = hw; l < prm.R; l += 8) {
+        const int64_t r = p * prm.R + l;
+        const float* src = prm.pre_part + (size_t)r * D + sub * 4;
+        float4 acc = ldg4(src);
+        for (int k = 1; k < prm.n_ksplits; ++k) {
+            const float4 t = ldg4(src + (size_t)k * part_stride);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        float4 h = make_float4(fmaxf(acc.x + b.x, 0.f), fmaxf(acc.y + b.y, 0.f), fmaxf(acc.z + b.z, 0.f),
+                               fmaxf(acc.w + b.w, 0.f));
+        if (prm.mask_mode == 1) {
+            const float4 m = ldg4(prm.mask + (size_t)r * D + sub * 4);
+            h.x *= m.x; h.y *= m.y; h.z *= m.z; h.w *= m.w;
+        } else if (prm.mask_mode == 2) {
+            const float4 m = dropout_quad(key_drop, (uint32_t)r, (uint32_t)sub, prm.keep_prob, prm.drop_scale);
+            h.x *= m.x; h.y *= m.y; h.z *= m.z; h.w *= m.w;
+        }
+        if (prm.save_h != nullptr) st4(prm.save_h + (size_t)r * D + sub * 4, h);
+        float dot = h.x * e.x;
+        dot = fmaf(h.y, e.y, dot);
+        dot = fmaf(h.z, e.z, dot);
+        dot = fmaf(h.w, e.w, dot);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(half_mask, dot, o);
+        if (sub == 0) prm.ws_rows[r] = dot;
+    }
+    __syncthreads();   // the pair's row scores (global memory, written by this CTA) are visible to warp 0
+    if (tid < 32)
+        backdoor_pair(prm.ex, prm.X, prm.sample_item, p, lane, prm.n_users, prm.user_base, prm.n_items, prm.S, prm.A,
+                      prm.ws_rows, prm.out_pred, prm.save_w, prm.err_flag);
+}
+
+// =============================================================================================
+// backward: gW / gb partial tiles
+// =============================================================================================
+constexpr int TB_NT = TC_PRODUCERS + 32;   // 16 producer warps + the MMA warp
+
+struct TrainBwdParams {
+    const float* E_item;
+    const float* Feat;
+    const int64_t* X;
+    const int64_t* sample_item;
+    const float* noise;          // mode 1
+    const float* dpre_rows;      // [N, D]
+    float* gW_part;              // [n_splits][D][K]
+    float* gb_part;              // [n_splits][D]
+    int64_t n_rows;
+    int32_t n_items, F, S, A, R, K;
+    int32_t rows_per_split;      // multiple of 32
+    float noise_std;
+    RngSpec rng;
+};
+
+// 4x4 transpose across the four lanes of a quad: in: lane j holds a[0..3] = M[j][0..3]; out: lane j holds M[0..3][j]
+__device__ __forceinline__ void quad_transpose(float4& a, int j) {
+    const bool odd = (j & 1) != 0, up = (j & 2) != 0;
+    float s0 = odd ? a.x : a.y, s1 = odd ? a.z : a.w;
+    s0 = __shfl_xor_sync(0xffffffffu, s0, 1);
+    s1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    if (odd) { a.x = s0; a.z = s1; } else { a.y = s0; a.w = s1; }
+    float t0 = up ? a.x : a.z, t1 = up ? a.y : a.w;
+    t0 = __shfl_xor_sync(0xffffffffu, t0, 2);
+    t1 = __shfl_xor_sync(0xffffffffu, t1, 2);
+    if (up) { a.x = t0; a.y = t1; } else { a.z = t0; a.w = t1; }
+}
+
+template <int NOISE_MODE>
+__global__ void __launch_bounds__(TB_NT, 1) k_train_bwd_tc(const TrainBwdParams prm) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + TC_STAGES;
+    uint64_t* accum_bar = empty_bar + TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mt = (int)blockIdx.x, sp = (int)blockIdx.y;
+    const int64_t row_lo = (int64_t)sp * prm.rows_per_split;
+    const int64_t row_hi = min(row_lo + prm.rows_per_split, prm.n_rows);
+    const int n_st = row_hi > row_lo ? (int)((row_hi - row_lo + TC_KC - 1) / TC_KC) : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            tc::mbar_init(&full_bar[s], TC_PRODUCERS / 32);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        tc::mbar_init(accum_bar, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == TC_PRODUCERS / 32) tc::tmem_alloc(tmem_slot, TC_TMEM_COLS);
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < TC_PRODUCERS / 32) {
+        // ===== producers =====
+        // x tile (the A operand, M = column of [x | 1], K = row): a quad of lanes owns 4 rows x 4 columns
+        const int j = lane & 3, g = lane >> 2;
+        const int rq = warp & 7;            // which 4 of the stage's 32 rows
+        const int cb0 = warp >> 3;          // 32-column blocks cb0 and cb0 + 2 of the 128-column tile
+        // dpre tile (the B operand, N = output channel, K = row): thread owns channel bc, rows 4*brq .. 4*brq+3
+        const int bc = tid & 63, brq = tid >> 6;
+        RngKey key_noise = make_rng_key(0, 0, DOMAIN_NOISE);
+        if (NOISE_MODE == 2) key_noise = resolve_rng_key(prm.rng, DOMAIN_NOISE);
+
+        for (int st = 0; st < n_st; ++st) {
+            const int s = st % TC_STAGES;
+            const uint32_t ph = (uint32_t)(st / TC_STAGES) & 1u;
+            const int64_t rb = row_lo + (int64_t)st * TC_KC;
+
+            // dpre values first: their loads are in flight while the noise is generated
+            float4 dv;
+            {
+                const int64_t r0 = rb + brq * 4;
+                const float* src = prm.dpre_rows + (size_t)r0 * D + bc;
+                dv.x = (r0 + 0 < row_hi) ? __ldg(src) : 0.f;
+                dv.y = (r0 + 1 < row_hi) ? __ldg(src + D) : 0.f;
+                dv.z = (r0 + 2 < row_hi) ? __ldg(src + 2 * D) : 0.f;
+                dv.w = (r0 + 3 < row_hi) ? __ldg(src + 3 * D) : 0.f;
+            }
+
+            const int64_t r = rb + rq * 4 + j;
+            const bool live = r < row_hi;
+            int32_t fi = 0, it = 0;
+            if (live) {
+                const uint32_t p = (uint32_t)r / (uint32_t)prm.R;
+                fi = checked_id(prm.X[2 * (int64_t)p + 1], prm.n_items, nullptr);
+                if (mt == 0) {
+                    const int z = (int)((uint32_t)r - p * (uint32_t)prm.R) / prm.A;
+                    it = (z == 0) ? fi : checked_id(prm.sample_item[(int64_t)p * prm.S + (z - 1)], prm.n_items, nullptr);
+                }
+            }
+            float4 v[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int col = mt * TC_BM + (cb0 + 2 * t) * 32 + g * 4;   // first of this lane's 4 columns of [x | 1]
+                v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live) {
+                    if (col < D) {
+                        v[t] = ldg4(prm.E_item + (size_t)it * D + col);
+                    } else if (col < prm.K) {
+                        const int f = col - D;
+                        v[t] = ldg4(prm.Feat + (size_t)fi * prm.F + f);
+                        if (NOISE_MODE != 0) {
+                            float4 e;
+                            if (NOISE_MODE == 1) e = ldg4(prm.noise + (size_t)r * prm.F + f);
+                            else e = noise_quad(key_noise, (uint32_t)r, (uint32_t)(f / 4), prm.noise_std);
+                            v[t].x = __fadd_rn(v[t].x, e.x); v[t].y = __fadd_rn(v[t].y, e.y);
+                            v[t].z = __fadd_rn(v[t].z, e.z); v[t].w = __fadd_rn(v[t].w, e.w);
+                        }
+                    } else if (col == prm.K) {
+                        v[t].x = 1.f;                 // the column of ones: its output row is the bias gradient
+                    }
+                }
+            }
+            quad_transpose(v[0], j);
+            quad_transpose(v[1], j);
+
+            tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+            uint8_t* a_hi = smem + s * TC_STAGE_BYTES;
+            uint8_t* a_lo = a_hi + TC_A_BYTES;
+            uint8_t* b_hi = a_hi + 2 * TC_A_BYTES;
+            uint8_t* b_lo = b_hi + TC_B_BYTES;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int m = (cb0 + 2 * t) * 32 + g * 4 + j;      // after the transpose this lane holds column m,
+                store_hi_lo(a_hi, a_lo, core_offset(m, rq * 4), v[t]);   // rows 4*rq .. 4*rq+3 of the stage
+            }
+            store_hi_lo(b_hi, b_lo, core_offset(bc, brq * 4), dv);
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&full_bar[s]);
+        }
+    } else {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            for (int st = 0; st < n_st; ++st) {
+                const int s = st % TC_STAGES;
+                const uint32_t ph = (uint32_t)(st / TC_STAGES) & 1u;
+                tc::mbar_wait(&full_bar[s], ph);
+                tc::tc_fence_after_sync();
+                issue_stage_mmas(tc::smem_u32(smem + s * TC_STAGE_BYTES), tmem_base, st);
+                tc::umma_commit(&empty_bar[s]);
+            }
+            tc::umma_commit(accum_bar);
+        }
+        __syncwarp();
+    }
+
+    // ===== epilogue: warps 0-3, thread = TMEM lane = column m of the tile; lanes of a warp are 32 consecutive
+    // columns of gW, so every store below is one coalesced 128-byte line =====
+    if (warp < 4) {
+        const int col = mt * TC_BM + tid;
+        if (n_st > 0) {
+            tc::mbar_wait(accum_bar, 0u);
+            tc::tc_fence_after_sync();
+        }
+        float* gw = prm.gW_part + (size_t)sp * D * prm.K;
+        float* gb = prm.gb_part + (size_t)sp * D;
+#pragma unroll 1
+        for (int quarter = 0; quarter < 4; ++quarter) {
+            float acc[16];
+            if (n_st > 0) {
+                load_acc_quarter(tmem_base, warp, quarter, acc);
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.f;
+            }
+            if (col < prm.K) {
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) gw[(size_t)(quarter * 16 + jj) * prm.K + col] = acc[jj];
+            } else if (col == prm.K) {
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) gb[quarter * 16 + jj] = acc[jj];
+            }
+        }
+    }
+
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == TC_PRODUCERS / 32) tc::tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+// defined in bpr_bwd.cu
+int bpr_bwd_launch(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat, const float* W,
+                   const int64_t* X, const int64_t* sample_item, const float* Y, int64_t n_pairs, const dccf_rng* rng,
+                   int32_t loss_mode, const float* pred, const float* save_h, const float* save_w, float* out_loss,
+                   float* gW_part, float* gb_part, float* gu_rec, float* gi_rec, int32_t* rec_keys_u, int32_t* rec_keys_i,
+                   float* dpre_rows, bool with_gw, cudaStream_t stream);
+
+static int env_int(const char* name) {
+    const char* v = getenv(name);
+    return (v != nullptr && v[0] != '\0') ? atoi(v) : 0;
+}
+
+static int32_t fwd_ksplits_for(int64_t n_rows, int n_chunks) {
+    if (n_rows <= 0) return 1;
+    const int64_t tiles = (n_rows + TC_BM - 1) / TC_BM;
+    int64_t ks = env_int("DCCF_TC_KSPLITS");
+    if (ks <= 0) ks = 148 / tiles;                 // about one CTA per SM
+    if (ks > 8) ks = 8;
+    if (ks > n_chunks) ks = n_chunks;
+    if (ks < 1) ks = 1;
+    return (int32_t)ks;
+}
+
+static void bwd_geometry(int64_t n_rows, int K, int32_t* n_mtiles, int32_t* n_splits, int32_t* rows_per_split) {
+    const int mt = (K + 1 + TC_BM - 1) / TC_BM;    // columns of [x | 1]
+    int64_t want = env_int("DCCF_TC_BWD_SPLITS");
+    if (want <= 0) want = 148 / mt;
+    if (want < 1) want = 1;
+    int64_t rps = (n_rows + want - 1) / want;
+    rps = ((rps + TC_KC - 1) / TC_KC) * TC_KC;
+    if (rps < TC_KC) rps = TC_KC;
+    *n_mtiles = mt;
+    *rows_per_split = (int32_t)rps;
+    *n_splits = (int32_t)((n_rows + rps - 1) / rps);
+    if (*n_splits < 1) *n_splits = 1;
+}
+
+template <typename Kern>
+static int opt_in_smem(Kern k, const char* name) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    if (e != cudaSuccess) {
+        set_error("%s: cannot opt in to %u bytes of shared memory: %s", name, TC_SMEM_BYTES, cudaGetErrorString(e));
+        return DCCF_ERR_CUDA;
+    }
+    return DCCF_OK;
+}
+
+}  // namespace dccf
+
+using namespace dccf;
+
+extern "C" int64_t dccf_train_w_image_floats(int32_t feat_dim) {
+    return (int64_t)((D + feat_dim) / TC_KC) * (2 * TC_B_BYTES / 4);
+}
+
+extern "C" int32_t dccf_train_fwd_ksplits(int64_t n_rows, int32_t feat_dim) {
+    return fwd_ksplits_for(n_rows, (D + feat_dim) / TC_KC);
+}
+
+extern "C" int32_t dccf_train_bwd_splits(int64_t n_rows, int32_t feat_dim) {
+    int32_t mt, ns, rps;
+    bwd_geometry(n_rows, D + feat_dim, &mt, &ns, &rps);
+    return ns;
+}
+
+extern "C" int dccf_train_fwd_tc(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
+                                 const float* W, const float* b, const dccf_expo* expo, const int64_t* X,
+                                 const int64_t* sample_item, int64_t n_pairs, const dccf_rng* rng, float* out_pred,
+                                 float* ws_rows, float* ws_wimg, float* ws_pre_part, float* save_h, float* save_w,
+                                 int32_t* err_flag, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DCCF_CHECK_ARG(dims && expo && rng, "dccf_train_fwd_tc: null struct argument");
+    DCCF_CHECK_ARG(dims->dim == D, "dccf_train_fwd_tc: dim=%d but this build has D=%d", dims->dim, D);
+    DCCF_CHECK_ARG(dims->feat_dim > 0 && dims->feat_dim % 64 == 0, "dccf_train_fwd_tc: feat_dim=%d must be a positive multiple of 64", dims->feat_dim);
+    DCCF_CHECK_ARG(dims->n_samples >= 0 && dims->n_attr >= 1, "dccf_train_fwd_tc: bad n_samples/n_attr");
+    DCCF_CHECK_ARG(E_user && E_item && Feat && W && b && X && out_pred && ws_rows && ws_wimg && ws_pre_part, "dccf_train_fwd_tc: null buffer");
+    DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item, "dccf_train_fwd_tc: sample_item is null");
+    DCCF_CHECK_ARG(rng->noise_mode >= 0 && rng->noise_mode <= 2 && rng->mask_mode >= 0 && rng->mask_mode <= 2, "dccf_train_fwd_tc: bad rng mode");
+    DCCF_CHECK_ARG(rng->noise_mode != 1 || rng->noise, "dccf_train_fwd_tc: noise_mode 1 needs a noise tensor");
+    DCCF_CHECK_ARG(rng->mask_mode != 1 || rng->mask, "dccf_train_fwd_tc: mask_mode 1 needs a mask tensor");
+    DCCF_CHECK_ARG(expo->mode == 0 ? expo->dense != nullptr
+                                   : (expo->mode == 1 && expo->mf_user && expo->mf_item && expo->mf_user_bias && expo->mf_item_bias && expo->propensity),
+                   "dccf_train_fwd_tc: exposure source incomplete (mode %d)", expo->mode);
+    if (n_pairs <= 0) return DCCF_OK;
+    const int F = dims->feat_dim, K = D + F, Z = dims->n_samples + 1, R = Z * dims->n_attr;
+    const int64_t n_rows = n_pairs * R;
+    DCCF_CHECK_ARG(n_rows < (int64_t)1 << 31, "dccf_train_fwd_tc: %lld rows in one call (max 2^31-1)", (long long)n_rows);
+    DCCF_CHECK_ARG(n_pairs < (int64_t)1 << 31, "dccf_train_fwd_tc: too many pairs");
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        int rc = opt_in_smem(k_train_fwd_tc<0>, "dccf_train_fwd_tc");
+        if (rc == DCCF_OK) rc = opt_in_smem(k_train_fwd_tc<1>, "dccf_train_fwd_tc");
+        if (rc == DCCF_OK) rc = opt_in_smem(k_train_fwd_tc<2>, "dccf_train_fwd_tc");
+        if (rc != DCCF_OK) return rc;
+        attr_set = true;
+    }
+
+    k_prep_w_image<<<104, 256, 0, stream>>>(W, K, ws_wimg);
+    DCCF_CHECK_LAUNCH("k_prep_w_image");
+
+    TrainFwdParams prm;
+    prm.E_item = E_item; prm.Feat = Feat; prm.gWimg = ws_wimg; prm.X = X; prm.sample_item = sample_item;
+    prm.noise = rng->noise; prm.pre_part = ws_pre_part; prm.err_flag = err_flag; prm.n_rows = n_rows;
+    prm.n_items = dims->n_items; prm.F = F; prm.S = dims->n_samples; prm.A = dims->n_attr; prm.R = R;
+    prm.n_chunks = K / TC_KC; prm.noise_std = rng->noise_std;
+    prm.rng.seed = rng->seed; prm.rng.offset = rng->offset; prm.rng.offset_dev = rng->offset_dev;
+    const int32_t n_ks = fwd_ksplits_for(n_rows, prm.n_chunks);
+    const dim3 grid((unsigned)((n_rows + TC_BM - 1) / TC_BM), (unsigned)n_ks);
+    switch (rng->noise_mode) {
+        case 0: k_train_fwd_tc<0><<<grid, TC_NT, TC_SMEM_BYTES, stream>>>(prm); break;
+        case 1: k_train_fwd_tc<1><<<grid, TC_NT, TC_SMEM_BYTES, stream>>>(prm); break;
+        default: k_train_fwd_tc<2><<<grid, TC_NT, TC_SMEM_BYTES, stream>>>(prm); break;
+    }
+    DCCF_CHECK_LAUNCH("k_train_fwd_tc");
+
+    TrainFinishParams fin;
+    fin.ex = *expo; fin.E_user = E_user; fin.bias = b; fin.X = X; fin.sample_item = sample_item; fin.mask = rng->mask;
+    fin.pre_part = ws_pre_part; fin.ws_rows = ws_rows; fin.save_h = save_h; fin.save_w = save_w; fin.out_pred = out_pred;
+    fin.err_flag = err_flag; fin.n_pairs = n_pairs; fin.n_rows = n_rows; fin.n_users = dims->n_users;
+    fin.user_base = dims->user_base; fin.n_items = dims->n_items; fin.S = dims->n_samples; fin.A = dims->n_attr; fin.R = R;
+    fin.n_ksplits = n_ks; fin.mask_mode = rng->mask_mode; fin.keep_prob = 1.0f - rng->p_drop;
+    fin.drop_scale = (rng->p_drop < 1.0f) ? 1.0f / (1.0f - rng->p_drop) : 0.0f;
+    fin.rng = prm.rng;
+    k_train_fwd_finish<<<(unsigned)n_pairs, 128, 0, stream>>>(fin);
+    DCCF_CHECK_LAUNCH("k_train_fwd_finish");
+    return DCCF_OK;
+}
+
+extern "C" int dccf_train_bwd_tc(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
+                                 const float* W, const int64_t* X, const int64_t* sample_item, const float* Y,
+                                 int64_t n_pairs, const dccf_rng* rng, int32_t loss_mode, const float* pred,
+                                 const float* save_h, const float* save_w, float* out_loss, float* gW_part,
+                                 float* gb_part, float* gu_rec, float* gi_rec, int32_t* rec_keys_u, int32_t* rec_keys_i,
+                                 float* ws_dpre, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DCCF_CHECK_ARG(dims && rng, "dccf_train_bwd_tc: null struct argument");
+    DCCF_CHECK_ARG(gW_part && gb_part && ws_dpre, "dccf_train_bwd_tc: null buffer");
+    // records (embedding gradients), loss and the dpre rows: the record / loss roles of k_bpr_bwd (validates the rest)
+    int rc = bpr_bwd_launch(dims, E_user, E_item, Feat, W, X, sample_item, Y, n_pairs, rng, loss_mode, pred, save_h,
+                            save_w, out_loss, nullptr, nullptr, gu_rec, gi_rec, rec_keys_u, rec_keys_i, ws_dpre, false,
+                            stream);
+    if (rc != DCCF_OK || n_pairs <= 0) return rc;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        rc = opt_in_smem(k_train_bwd_tc<0>, "dccf_train_bwd_tc");
+        if (rc == DCCF_OK) rc = opt_in_smem(k_train_bwd_tc<1>, "dccf_train_bwd_tc");
+        if (rc == DCCF_OK) rc = opt_in_smem(k_train_bwd_tc<2>, "dccf_train_bwd_tc");
+        if (rc != DCCF_OK) return rc;
+        attr_set = true;
+    }
+    const int F = dims->feat_dim, K = D + F, Z = dims->n_samples + 1, R = Z * dims->n_attr;
+    TrainBwdParams prm;
+    prm.E_item = E_item; prm.Feat = Feat; prm.X = X; prm.sample_item = sample_item; prm.noise = rng->noise;
+    prm.dpre_rows = ws_dpre; prm.gW_part = gW_part; prm.gb_part = gb_part; prm.n_rows = n_pairs * R;
+    prm.n_items = dims->n_items; prm.F = F; prm.S = dims->n_samples; prm.A = dims->n_attr; prm.R = R; prm.K = K;
+    prm.noise_std = rng->noise_std;
+    prm.rng.seed = rng->seed; prm.rng.offset = rng->offset; prm.rng.offset_dev = rng->offset_dev;
+    int32_t n_mtiles, n_splits;
+    bwd_geometry(prm.n_rows, K, &n_mtiles, &n_splits, &prm.rows_per_split);
+    const dim3 grid((unsigned)n_mtiles, (unsigned)n_splits);
+    switch (rng->noise_mode) {
+        case 0: k_train_bwd_tc<0><<<grid, TB_NT, TC_SMEM_BYTES, stream>>>(prm); break;
+        case 1: k_train_bwd_tc<1><<<grid, TB_NT, TC_SMEM_BYTES, stream>>>(prm); break;
+        default: k_train_bwd_tc<2><<<grid, TB_NT, TC_SMEM_BYTES, stream>>>(prm); break;
+    }
+    DCCF_CHECK_LAUNCH("k_train_bwd_tc");
+    return DCCF_OK;
+}

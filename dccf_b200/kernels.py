@@ -144,6 +144,45 @@ def bpr_bwd(dims, E_user, E_item, Feat, W, X, sample_item, Y, rng, loss_mode, pr
     LAUNCHES[0] += 1 if n_pairs > 0 else 0
 
 
+def train_w_image_floats(feat_dim):
+    return int(_lib.load().dccf_train_w_image_floats(int(feat_dim)))
+
+
+def train_fwd_ksplits(n_rows, feat_dim):
+    return int(_lib.load().dccf_train_fwd_ksplits(int(n_rows), int(feat_dim)))
+
+
+def train_bwd_splits(n_rows, feat_dim):
+    return int(_lib.load().dccf_train_bwd_splits(int(n_rows), int(feat_dim)))
+
+
+def train_fwd_tc(dims, E_user, E_item, Feat, W, b, expo, X, sample_item, rng, out_pred, ws_rows, ws_wimg, ws_pre_part,
+                 save_h, save_w, err_flag=None):
+    """Forward of a training step on the tensor cores (3 launches: W operand images, partial products per
+    (row tile, K split), per-pair epilogue + backdoor sum)."""
+    lib = _lib.load()
+    n_pairs = X.shape[0]
+    check(lib.dccf_train_fwd_tc(ctypes.byref(dims), ptr(E_user), ptr(E_item), ptr(Feat), ptr(W), ptr(b),
+                                ctypes.byref(expo), ptr(X), ptr(sample_item), n_pairs, ctypes.byref(rng), ptr(out_pred),
+                                ptr(ws_rows), ptr(ws_wimg), ptr(ws_pre_part), ptr(save_h), ptr(save_w), ptr(err_flag),
+                                stream_ptr()), 'dccf_train_fwd_tc')
+    LAUNCHES[0] += 3 if n_pairs > 0 else 0
+    return out_pred
+
+
+def train_bwd_tc(dims, E_user, E_item, Feat, W, X, sample_item, Y, rng, loss_mode, pred, save_h, save_w, out_loss,
+                 gW_part, gb_part, gu_rec, gi_rec, rec_keys_u, rec_keys_i, ws_dpre):
+    """Loss + backward of a training step, dW / db on the tensor cores (2 launches)."""
+    lib = _lib.load()
+    n_pairs = X.shape[0]
+    check(lib.dccf_train_bwd_tc(ctypes.byref(dims), ptr(E_user), ptr(E_item), ptr(Feat), ptr(W), ptr(X),
+                                ptr(sample_item), ptr(Y), n_pairs, ctypes.byref(rng), int(loss_mode), ptr(pred),
+                                ptr(save_h), ptr(save_w), ptr(out_loss), ptr(gW_part), ptr(gb_part), ptr(gu_rec),
+                                ptr(gi_rec), ptr(rec_keys_u), ptr(rec_keys_i), ptr(ws_dpre), stream_ptr()),
+          'dccf_train_bwd_tc')
+    LAUNCHES[0] += 2 if n_pairs > 0 else 0
+
+
 def adam_sweep(table, m, v, rec_keys, rec_grads, n_rec, head, nxt, hp):
     lib = _lib.load()
     check(lib.dccf_adam_sweep(ptr(table), ptr(m), ptr(v), table.shape[0], ptr(rec_keys), ptr(rec_grads), int(n_rec),

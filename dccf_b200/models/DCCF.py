@@ -237,10 +237,10 @@ class DCCF(DMF):
     # evaluation batches with feature noise go to the tcgen05 scorer (dccf_score_fwd_tc) when they are large
     # enough to fill the machine; training steps and noise-free scoring use the FP32 SIMT kernels
     use_tensor_cores = True
-    # forward of a training step on the tensor cores (dccf_score_fwd_tc_train): correct (tested), but a 256-pair
-    # step is only 44 row tiles, so the per-tile noise generation runs on 44 of the 148 SMs — measured slower
-    # (0.186 ms/step) than the FP32 split-K kernel that spreads over all SMs (0.138 ms/step).  Off by default.
-    use_tensor_cores_train = False
+    # training steps: both large contractions (forward W·x, backward dW = dpre^T·x) on the tensor cores, spread over
+    # all SMs by (row tile, K split) / (column tile, row split) — dccf_train_fwd_tc / dccf_train_bwd_tc.  False:
+    # the FP32 SIMT kernels (k_row_scores_splitk, k_bpr_bwd), kept as the cross-check of the tensor-core path.
+    use_tensor_cores_train = True
     tc_min_rows = 128 * 148
 
     def _tc_tables(self):
@@ -285,15 +285,17 @@ class DCCF(DMF):
         if save:
             call['save_h'] = save_h = torch.empty((N, D), dtype=torch.float32, device=dev)
             call['save_w'] = save_w = torch.empty((P, Z), dtype=torch.float32, device=dev)
-            if self.use_tensor_cores and self.use_tensor_cores_train and call['rng'].noise_mode != 0:
-                kernels.score_fwd_tc_train(
+            if self.use_tensor_cores and self.use_tensor_cores_train:
+                F = K - D
+                n_ks = kernels.train_fwd_ksplits(N, F)
+                kernels.train_fwd_tc(
                     self._dims(), self.uid_embeddings.weight.data, self.iid_embeddings.weight.data,
                     self.feature_embedding, self.mlp[0].weight.data, self.mlp[0].bias.data, self._expo(), call['X'],
-                    call['sample_item'], call['rng'], pred, ws_rows, ws_wt,
-                    self._buf('ws_pi', (P * Z, D), torch.float32), self._buf('ws_pf', (P, D), torch.float32),
-                    self._buf('ws_gB', (kernels.tc_operand_floats(K - D),), torch.float32), save_h, save_w,
-                    self._err_flag)
+                    call['sample_item'], call['rng'], pred, ws_rows,
+                    self._buf('ws_wimg', (kernels.train_w_image_floats(F),), torch.float32),
+                    self._buf('ws_pre_part', (n_ks, N, D), torch.float32), save_h, save_w, self._err_flag)
                 call['pred'] = pred
+                call['tc_train'] = True
                 return pred
         kernels.score_fwd(self._dims(), self.uid_embeddings.weight.data, self.iid_embeddings.weight.data,
                           self.feature_embedding, self.mlp[0].weight.data, self.mlp[0].bias.data, self._expo(),
@@ -306,7 +308,8 @@ class DCCF(DMF):
         P, N = call['P'], call['N']
         D, Z = self.ui_vector_size, self.sample_num + 1
         K = D + self.feature_embedding.shape[1]
-        n_splits = kernels.bwd_splits(N)
+        tc = bool(call.get('tc_train'))
+        n_splits = kernels.train_bwd_splits(N, K - D) if tc else kernels.bwd_splits(N)
         rec = {
             'gW_part': self._buf('gW_part', (n_splits, D, K), torch.float32),
             'gb_part': self._buf('gb_part', (n_splits, D), torch.float32),
@@ -326,10 +329,14 @@ class DCCF(DMF):
                         'keys_u': self._buf('keys_u', (P,), torch.int32),
                         'keys_i': self._buf('keys_i', (P * Z,), torch.int32),
                         'loss': self._buf('loss', (1,), torch.float32)})
-        kernels.bpr_bwd(self._dims(), self.uid_embeddings.weight.data, self.iid_embeddings.weight.data,
-                        self.feature_embedding, self.mlp[0].weight.data, call['X'], call['sample_item'], Y,
-                        call['rng'], loss_mode, call['pred'], call['save_h'], call['save_w'], rec['loss'],
-                        rec['gW_part'], rec['gb_part'], rec['gu_rec'], rec['gi_rec'], rec['keys_u'], rec['keys_i'])
+        args = (self._dims(), self.uid_embeddings.weight.data, self.iid_embeddings.weight.data,
+                self.feature_embedding, self.mlp[0].weight.data, call['X'], call['sample_item'], Y,
+                call['rng'], loss_mode, call['pred'], call['save_h'], call['save_w'], rec['loss'],
+                rec['gW_part'], rec['gb_part'], rec['gu_rec'], rec['gi_rec'], rec['keys_u'], rec['keys_i'])
+        if tc:
+            kernels.train_bwd_tc(*args, self._buf('ws_dpre', (N, D), torch.float32))
+        else:
+            kernels.bpr_bwd(*args)
         return rec
 
     def check_ids(self):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 13
+#define DCCF_ABI_VERSION 14
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -159,6 +159,31 @@ int dccf_bpr_bwd(const dccf_dims* dims, const float* E_user, const float* E_item
                  const float* pred, const float* save_h, const float* save_w, float* out_loss,
                  float* gW_part, float* gb_part, float* gu_rec, float* gi_rec,
                  int32_t* rec_keys_u, int32_t* rec_keys_i, void* stream);
+
+/* ---- training step on the tensor cores (tcgen05, 3xTF32) --------------------------------- */
+/* Same results as dccf_score_fwd (with save_h / save_w) and dccf_bpr_bwd, for the rows of ONE training step
+ * (src/runners/BaseRunner.py:175-188), with both large contractions on the tensor cores and spread over all
+ * SMs: the forward as (128-row tiles) x (K splits) partial products, the backward dW / db as (128-column
+ * tiles of [x | 1]) x (row splits) with the row as the contraction index.
+ *   ws_wimg      [dccf_train_w_image_floats(F)] workspace: hi/lo operand images of W (rebuilt per call)
+ *   ws_pre_part  [dccf_train_fwd_ksplits(N, F), N, D] workspace: partial pre-activations
+ *   gW_part      [dccf_train_bwd_splits(N, F), D, D+F], gb_part [same, D]
+ *   ws_dpre      [N, D] workspace: d loss / d pre-activation rows
+ * All other arguments as in dccf_score_fwd / dccf_bpr_bwd; both calls must use the SAME rng. */
+int64_t dccf_train_w_image_floats(int32_t feat_dim);
+int32_t dccf_train_fwd_ksplits(int64_t n_rows, int32_t feat_dim);
+int32_t dccf_train_bwd_splits(int64_t n_rows, int32_t feat_dim);
+int dccf_train_fwd_tc(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
+                      const float* W, const float* b, const dccf_expo* expo, const int64_t* X,
+                      const int64_t* sample_item, int64_t n_pairs, const dccf_rng* rng, float* out_pred,
+                      float* ws_rows, float* ws_wimg, float* ws_pre_part, float* save_h, float* save_w,
+                      int32_t* err_flag, void* stream);
+int dccf_train_bwd_tc(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
+                      const float* W, const int64_t* X, const int64_t* sample_item, const float* Y,
+                      int64_t n_pairs, const dccf_rng* rng, int32_t loss_mode, const float* pred,
+                      const float* save_h, const float* save_w, float* out_loss, float* gW_part,
+                      float* gb_part, float* gu_rec, float* gi_rec, int32_t* rec_keys_u, int32_t* rec_keys_i,
+                      float* ws_dpre, void* stream);
 
 /* ---- (c) part 2: l2 + clip + Adam, dense over every row --------------------------------- */
 /* Replaces model.l2()*l2 (BaseRunner.py:181, BaseModel.py:179-187), clip_grad_value_

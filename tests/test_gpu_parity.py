@@ -506,6 +506,44 @@ def test_tensor_core_scorer_equals_simt_scorer_on_library_noise():
     assert rel_err(b, a) < 1e-5
 
 
+@pytest.mark.parametrize('U,I,F,P,S,A', [(300, 500, 768, 256, 10, 2), (50, 70, 128, 38, 3, 1), (20, 30, 64, 2, 0, 1),
+                                         (64, 64, 256, 130, 5, 3)])
+def test_tensor_core_training_step_equals_simt_step(U, I, F, P, S, A):
+    """Three fused training steps (library noise + dropout, mode 2) with the contractions on the tensor cores
+    (dccf_train_fwd_tc / dccf_train_bwd_tc) against the same steps on the FP32 SIMT kernels: same Philox streams,
+    predictions / loss / Adam moments / updated tables within the parity bounds."""
+    params, X, si, _, _ = random_problem(23, U, I, F, P, S, A, 0.0, 0.0)
+    X[P // 2:, 0] = X[:P // 2, 0]
+    outs = []
+    for tc in (False, True):
+        model = make_model(params, S, A, 0.1)
+        model.use_tensor_cores_train = tc
+        model.use_cuda_graph = False
+        model.optimizer = model.make_fused_optimizer(lr=1e-3, l2=1e-4)
+        preds, losses = [], []
+        for t in range(3):
+            fd = {'X': torch.from_numpy(np.roll(X, t, axis=0).copy()).cuda(), 'rank': 1, 'train': True, 'dropout': 0.2,
+                  'Y': torch.zeros(P).cuda(), 'sample_item': torch.from_numpy(np.roll(si, t, axis=0).copy())}
+            fd['X'][P // 2:, 0] = fd['X'][:P // 2, 0]
+            o = model.train_step(fd)
+            preds.append(o['prediction'].cpu().numpy().copy())
+            losses.append(float(o['loss']))
+        opt = model.optimizer
+        outs.append((preds, losses, model_params(model), {k: v.cpu().numpy() for k, v in opt.exp_avg.items()},
+                     {k: v.cpu().numpy() for k, v in opt.exp_avg_sq.items()}))
+        model.check_ids()
+    a, b = outs
+    for t in range(3):
+        assert rel_err(b[0][t], a[0][t]) < 1e-5
+        assert abs(b[1][t] - a[1][t]) < 1e-5 * abs(a[1][t])
+    for k in ('E_user', 'E_item', 'W', 'b'):
+        assert rel_err(b[3][k], a[3][k]) < 2e-5, k          # exp_avg
+        assert rel_err(b[4][k], a[4][k]) < 2e-5, k          # exp_avg_sq
+    for k in ('E_user', 'E_item'):
+        assert rel_err(b[2][k], a[2][k]) < 1e-5, k
+    assert rel_err(b[2]['W'], a[2]['W']) < 5e-4              # see DESIGN.md §4 (lr/eps sensitivity where |g| << eps)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # full-catalogue scoring (tcgen05 GEMM + fused top-k)
 # ---------------------------------------------------------------------------------------------------------
