@@ -334,6 +334,169 @@ __global__ void __launch_bounds__(256, 4) k_adam_all(const AdamAllArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same step split around the backward pass, so that the HBM-bound sweep of the rows a step does NOT touch
+// (99 % of both tables) runs concurrently with the FMA/tensor-bound forward and backward on another stream:
+//   k_link_ids       the record lists of the step built from the ids alone (record p = user row of pair p, record
+//                    p*Z + z = item row of slot z), before any gradient exists: head[row] >= 0 marks a touched row
+//   k_adam_untouched rows with head == -1: gradient = l2 / weight-decay terms only
+//   k_adam_touched   after the backward: the record that ended up as the HEAD of its row's list processes the row
+//                    (records summed in ascending index as always); + W, b; the last CTA advances the step counters
+// Every row is updated exactly once per step and with the same arithmetic as k_adam_all.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_link_ids(const int64_t* __restrict__ X, const int64_t* __restrict__ sample_item,
+                                                  int64_t n_pairs, int32_t S, int32_t user_base, int32_t n_users,
+                                                  int32_t n_items, int32_t* __restrict__ head_u, int32_t* __restrict__ next_u,
+                                                  int32_t* __restrict__ head_i, int32_t* __restrict__ next_i) {
+    const int Z = S + 1;
+    tl_begin(0);
+    tl_end(0);      // (a single short wave: start and end of the kernel are indistinguishable at this resolution)
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs * (Z + 1)) return;
+    const int64_t p = i / (Z + 1);
+    const int slot = (int)(i - p * (Z + 1));   // 0 = the user record of pair p, 1 + z = its item record of slot z
+    if (slot == 0) {
+        const int32_t u = checked_id(X[2 * p] - user_base, n_users, nullptr);
+        next_u[p] = atomicExch(&head_u[u], (int32_t)p);
+    } else {
+        const int z = slot - 1;
+        const int32_t it = checked_id(slot_item(X, sample_item, p, z, S), n_items, nullptr);
+        const int32_t r = (int32_t)(p * Z + z);
+        next_i[r] = atomicExch(&head_i[it], r);
+    }
+}
+
+constexpr int ADAM_SIDE_SMEM = 120 * 1024;
+
+__global__ void __launch_bounds__(256, 1) k_adam_untouched(const AdamAllArgs a) {
+    tl_begin(1);
+    const AdamScalars s = resolve_adam(a.hp);
+    const int bid = (int)blockIdx.x;
+    for (int i = 0; i < a.n_tables; ++i) {
+        const AdamTableArgs& t = a.t[i];
+        const int b = bid - t.block_lo;
+        if (b < 0 || b >= t.block_n) continue;
+        const int sub = threadIdx.x & 15;
+        const int half = (threadIdx.x >> 4) & 1;
+        const int64_t warp = ((int64_t)b * blockDim.x + threadIdx.x) >> 5;
+        const int64_t n_warps = ((int64_t)t.block_n * blockDim.x) >> 5;
+        for (int64_t w = warp; 4 * w < t.n_rows; w += n_warps) {
+            const int64_t r0 = 4 * w + half, r1 = r0 + 2;
+            const bool v0 = r0 < t.n_rows && t.head[r0] == -1;
+            const bool v1 = r1 < t.n_rows && t.head[r1] == -1;
+            const size_t o0 = (size_t)(v0 ? r0 : 0) * D + sub * 4, o1 = (size_t)(v1 ? r1 : 0) * D + sub * 4;
+            float4 p0, m0, q0, p1, m1, q1;
+            if (v0) { p0 = ld4(t.table + o0); m0 = ld4(t.m + o0); q0 = ld4(t.v + o0); }
+            if (v1) { p1 = ld4(t.table + o1); m1 = ld4(t.m + o1); q1 = ld4(t.v + o1); }
+            if (v0) {
+                adam_elem(p0.x, m0.x, q0.x, 0.f, s); adam_elem(p0.y, m0.y, q0.y, 0.f, s);
+                adam_elem(p0.z, m0.z, q0.z, 0.f, s); adam_elem(p0.w, m0.w, q0.w, 0.f, s);
+                st4(t.table + o0, p0); st4(t.m + o0, m0); st4(t.v + o0, q0);
+            }
+            if (v1) {
+                adam_elem(p1.x, m1.x, q1.x, 0.f, s); adam_elem(p1.y, m1.y, q1.y, 0.f, s);
+                adam_elem(p1.z, m1.z, q1.z, 0.f, s); adam_elem(p1.w, m1.w, q1.w, 0.f, s);
+                st4(t.table + o1, p1); st4(t.m + o1, m1); st4(t.v + o1, q1);
+            }
+        }
+        __syncthreads();
+        tl_end(1);
+        return;
+    }
+}
+
+struct WImageArgs {
+    float* img;          // operand images of W for the tensor-core forward of the NEXT step (tc_train.cu), or null
+    int32_t tensor;      // index of W among the dense tensors
+    int32_t K;           // row length of W
+    // optional: the last CTA to finish advances the graph's device counters (replaces dccf_state_advance)
+    int32_t* cta_counter;    // zero on entry, zero again on exit
+    int32_t* step_dev;
+    uint64_t* offset_dev;
+};
+
+__device__ __forceinline__ void touched_cta_done(const WImageArgs& wi) {
+    __syncthreads();
+    tl_end(5);
+    if (wi.cta_counter == nullptr) return;                       // every thread of this CTA has read the counters it needs and stored its rows
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(wi.cta_counter, 1) == (int32_t)gridDim.x - 1) {
+            if (wi.step_dev) wi.step_dev[0] += 1;
+            if (wi.offset_dev) wi.offset_dev[0] += 1;
+            *wi.cta_counter = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_adam_touched(const AdamAllArgs a, const WImageArgs wi) {
+    __shared__ int32_t list_s[16][2][ADAM_LIST_CAP];
+    tl_begin(5);
+    const AdamScalars s = resolve_adam(a.hp);
+    const int bid = (int)blockIdx.x;
+    for (int i = 0; i < a.n_tables; ++i) {
+        const AdamTableArgs& t = a.t[i];
+        const int b = bid - t.block_lo;
+        if (b < 0 || b >= t.block_n) continue;
+        // half-warp per record; the record that is the head of its row's list owns the row
+        const int sub = threadIdx.x & 15;
+        const int64_t r = ((int64_t)b * blockDim.x + threadIdx.x) >> 4;
+        int32_t row = -1;
+        if (r < t.n_rec) {
+            row = t.keys[rec_key_index(t.L, r)];
+            if (row < 0 || row >= t.n_rows || t.head[row] != (int32_t)r) row = -1;
+        }
+        if (row >= 0) {
+            const uint32_t half_mask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
+            __syncwarp(half_mask);   // every lane of the half-warp has read the head before lane 0 resets it
+            const size_t o = (size_t)row * D + sub * 4;
+            float4 p = ld4(t.table + o), m = ld4(t.m + o), q = ld4(t.v + o);
+            const float4 g = gather_row_grad(t, (int32_t)r, sub, half_mask, list_s[threadIdx.x >> 4][0], list_s[threadIdx.x >> 4][1]);
+            if (sub == 0) t.head[row] = -1;
+            adam_elem(p.x, m.x, q.x, g.x, s); adam_elem(p.y, m.y, q.y, g.y, s);
+            adam_elem(p.z, m.z, q.z, g.z, s); adam_elem(p.w, m.w, q.w, g.w, s);
+            st4(t.table + o, p); st4(t.m + o, m); st4(t.v + o, q);
+        }
+        touched_cta_done(wi);
+        return;
+    }
+    for (int i = 0; i < a.n_dense; ++i) {
+        const AdamDenseArgs& d = a.d[i];
+        const int b = bid - d.block_lo;
+        if (b < 0 || b >= d.block_n) continue;
+        const int64_t stride = (int64_t)d.block_n * blockDim.x;
+        const bool image = wi.img != nullptr && wi.tensor == i;
+        for (int64_t e = (int64_t)b * blockDim.x + threadIdx.x; e < d.n; e += stride) {
+            float p = d.p[e], m = d.m[e], v = d.v[e];
+            // partials in ascending order, eight loads in flight at a time
+            float g = 0.f;
+            int32_t k = 0;
+            for (; k + 8 <= d.n_parts; k += 8) {
+                float t8[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) t8[q] = __ldg(d.g_parts + (size_t)(k + q) * d.part_stride + e);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) g += t8[q];
+            }
+            for (; k < d.n_parts; ++k) g += __ldg(d.g_parts + (size_t)k * d.part_stride + e);
+            adam_elem(p, m, v, g, s);
+            d.p[e] = p; d.m[e] = m; d.v[e] = v;
+            if (image) {
+                // same layout as k_prep_w_image (tc_train.cu): 32-wide K chunks of [hi 8 KB | lo 8 KB], 8x4 core matrices
+                const int n = (int)(e / wi.K), k = (int)(e - (int64_t)n * wi.K);
+                const int c = k >> 5, kk = k & 31;
+                const float hi = __uint_as_float(__float_as_uint(p) & 0xFFFFE000u);
+                float* base = wi.img + (size_t)c * 4096;
+                const int off = (n >> 3) * 256 + (kk >> 2) * 32 + (n & 7) * 4 + (kk & 3);
+                base[off] = hi;
+                base[2048 + off] = __fsub_rn(p, hi);
+            }
+        }
+        touched_cta_done(wi);
+        return;
+    }
+}
+
 __global__ void k_state_advance(int32_t* step_dev, uint64_t* offset_dev, uint64_t inc) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         if (step_dev) step_dev[0] += 1;
@@ -347,6 +510,8 @@ __global__ void k_state_advance(int32_t* step_dev, uint64_t* offset_dev, uint64_
 __global__ void __launch_bounds__(256) k_stage_batch(const uint64_t* __restrict__ epoch_ptrs, int64_t* cursor,
                                                      int64_t n_x, int64_t n_s, int64_t* __restrict__ X_out,
                                                      int64_t* __restrict__ si_out) {
+    tl_begin(6);
+    tl_end(6);
     const int64_t b = *cursor;
     const int64_t* X_src = reinterpret_cast<const int64_t*>(epoch_ptrs[0]) + b * n_x;
     const int64_t* s_src = reinterpret_cast<const int64_t*>(epoch_ptrs[1]) + b * n_s;
@@ -447,45 +612,52 @@ extern "C" int dccf_state_advance(int32_t* step_dev, uint64_t* offset_dev, uint6
     return DCCF_OK;
 }
 
-extern "C" int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
-                              int32_t n_dense, const dccf_adam* hp, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    AdamAllArgs a;
-    int rc = check_hp(hp, &a.hp, "dccf_adam_step");
+// Validate and marshal the table / tensor descriptors.  mode 0: k_adam_all (sweep blocks over all rows);
+// 1: k_adam_untouched (sweep blocks, at most one 256-thread CTA per SM so that a tensor-core CTA of the forward /
+// backward fits beside it); 2: k_adam_touched (one half-warp per record).
+static int marshal_adam(const char* who, const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
+                        int32_t n_dense, const dccf_adam* hp, int mode, AdamAllArgs& a, int32_t* blocks_out,
+                        int32_t* link_blocks_out) {
+    int rc = check_hp(hp, &a.hp, who);
     if (rc != DCCF_OK) return rc;
     DCCF_CHECK_ARG(n_tables >= 0 && n_tables <= ADAM_MAX_T && n_dense >= 0 && n_dense <= ADAM_MAX_T,
-                   "dccf_adam_step: at most %d tables and %d dense tensors per call", ADAM_MAX_T, ADAM_MAX_T);
-    DCCF_CHECK_ARG((n_tables == 0 || tables) && (n_dense == 0 || dense), "dccf_adam_step: null descriptor array");
+                   "%s: at most %d tables and %d dense tensors per call", who, ADAM_MAX_T, ADAM_MAX_T);
+    DCCF_CHECK_ARG((n_tables == 0 || tables) && (n_dense == 0 || dense), "%s: null descriptor array", who);
     a.n_tables = n_tables;
     a.n_dense = n_dense;
     int64_t total_rows = 0;
     for (int i = 0; i < n_tables; ++i) total_rows += tables[i].n_rows > 0 ? tables[i].n_rows : 0;
     int32_t blocks = 0, link_blocks = 0;
-    const int64_t budget = 148 * 8;   // CTAs for the table sweeps, shared in proportion to the row counts
+    const int64_t budget = (mode == 1) ? 148 : 148 * 8;   // CTAs for the table sweeps, shared in proportion to the row counts
     for (int i = 0; i < n_tables; ++i) {
         const dccf_adam_table& t = tables[i];
-        DCCF_CHECK_ARG(t.table && t.m && t.v && t.head, "dccf_adam_step: table %d has a null buffer", i);
+        DCCF_CHECK_ARG(t.table && t.m && t.v && t.head, "%s: table %d has a null buffer", who, i);
         const int64_t n_rec = (int64_t)t.n_seg * t.seg_len;
-        DCCF_CHECK_ARG(t.n_seg >= 0 && t.seg_len >= 0, "dccf_adam_step: table %d has a negative record layout", i);
-        DCCF_CHECK_ARG(n_rec == 0 || (t.rec_keys && t.rec_grads && t.next), "dccf_adam_step: table %d has records but a null record buffer", i);
-        DCCF_CHECK_ARG(n_rec < ((int64_t)1 << 31) && t.n_rows < ((int64_t)1 << 31), "dccf_adam_step: table %d exceeds int32 indexing", i);
-        DCCF_CHECK_ARG(t.n_seg <= 1 || (t.key_seg_stride >= t.seg_len && t.grad_seg_stride >= t.seg_len * D), "dccf_adam_step: table %d segment strides overlap", i);
+        DCCF_CHECK_ARG(t.n_seg >= 0 && t.seg_len >= 0, "%s: table %d has a negative record layout", who, i);
+        DCCF_CHECK_ARG(n_rec == 0 || (t.rec_keys && t.rec_grads && t.next), "%s: table %d has records but a null record buffer", who, i);
+        DCCF_CHECK_ARG(n_rec < ((int64_t)1 << 31) && t.n_rows < ((int64_t)1 << 31), "%s: table %d exceeds int32 indexing", who, i);
+        DCCF_CHECK_ARG(t.n_seg <= 1 || (t.key_seg_stride >= t.seg_len && t.grad_seg_stride >= t.seg_len * D), "%s: table %d segment strides overlap", who, i);
         AdamTableArgs& o = a.t[i];
         o.table = t.table; o.m = t.m; o.v = t.v; o.n_rows = t.n_rows > 0 ? t.n_rows : 0;
         o.keys = t.rec_keys; o.grads = t.rec_grads; o.n_rec = n_rec;
         o.L.seg_len = t.seg_len > 0 ? t.seg_len : 1; o.L.key_seg_stride = t.key_seg_stride; o.L.grad_seg_stride = t.grad_seg_stride;
         o.head = t.head; o.next = t.next;
-        int64_t want = (o.n_rows + 31) / 32;                       // 32 rows per 256-thread CTA per trip
-        int64_t share = total_rows > 0 ? (budget * o.n_rows + total_rows - 1) / total_rows : 0;
-        if (want > share) want = share;
-        if (want < 1 && o.n_rows > 0) want = 1;
+        int64_t want;
+        if (mode == 2) {
+            want = (n_rec + 15) / 16;                              // 16 records (half-warps) per 256-thread CTA
+        } else {
+            want = (o.n_rows + 31) / 32;                           // 32 rows per 256-thread CTA per trip
+            int64_t share = total_rows > 0 ? (budget * o.n_rows + total_rows - 1) / total_rows : 0;
+            if (want > share) want = share;
+            if (want < 1 && o.n_rows > 0) want = 1;
+        }
         o.block_lo = blocks; o.block_n = (int32_t)want; blocks += (int32_t)want;
         o.link_lo = link_blocks; o.link_n = (int32_t)((n_rec + 255) / 256); link_blocks += o.link_n;
     }
     for (int i = 0; i < n_dense; ++i) {
         const dccf_adam_tensor& d = dense[i];
-        DCCF_CHECK_ARG(d.p && d.m && d.v, "dccf_adam_step: dense tensor %d has a null buffer", i);
-        DCCF_CHECK_ARG(d.n_parts == 0 || d.g_parts, "dccf_adam_step: dense tensor %d has a null gradient", i);
+        DCCF_CHECK_ARG(d.p && d.m && d.v, "%s: dense tensor %d has a null buffer", who, i);
+        DCCF_CHECK_ARG(d.n_parts == 0 || d.g_parts, "%s: dense tensor %d has a null gradient", who, i);
         AdamDenseArgs& o = a.d[i];
         o.p = d.p; o.m = d.m; o.v = d.v; o.n = d.n > 0 ? d.n : 0; o.g_parts = d.g_parts; o.n_parts = d.n_parts;
         o.part_stride = d.part_stride;
@@ -493,6 +665,18 @@ extern "C" int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, c
         if (want > 148) want = 148;
         o.block_lo = blocks; o.block_n = (int32_t)want; blocks += (int32_t)want;
     }
+    *blocks_out = blocks;
+    *link_blocks_out = link_blocks;
+    return DCCF_OK;
+}
+
+extern "C" int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
+                              int32_t n_dense, const dccf_adam* hp, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AdamAllArgs a;
+    int32_t blocks = 0, link_blocks = 0;
+    int rc = marshal_adam("dccf_adam_step", tables, n_tables, dense, n_dense, hp, 0, a, &blocks, &link_blocks);
+    if (rc != DCCF_OK) return rc;
     if (link_blocks > 0) {
         k_link_all<<<(unsigned)link_blocks, 256, 0, stream>>>(a);
         DCCF_CHECK_LAUNCH("k_link_all");
@@ -500,6 +684,90 @@ extern "C" int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, c
     if (blocks > 0) {
         k_adam_all<<<(unsigned)blocks, 256, 0, stream>>>(a);
         DCCF_CHECK_LAUNCH("k_adam_all");
+    }
+    return DCCF_OK;
+}
+
+extern "C" int dccf_debug_timeline_adam(unsigned long long* slots) {
+    cudaError_t e = cudaMemcpyToSymbol(g_timeline, &slots, sizeof(slots));
+    if (e != cudaSuccess) {
+        set_error("dccf_debug_timeline: %s", cudaGetErrorString(e));
+        return DCCF_ERR_CUDA;
+    }
+    return DCCF_OK;
+}
+
+extern "C" int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const int64_t* sample_item, int64_t n_pairs,
+                                  int32_t* head_user, int32_t* next_user, int32_t* head_item, int32_t* next_item,
+                                  void* stream_) {
+    DCCF_CHECK_ARG(dims && X && head_user && next_user && head_item && next_item, "dccf_adam_link_ids: null argument");
+    DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item, "dccf_adam_link_ids: sample_item is null");
+    DCCF_CHECK_ARG(n_pairs * (dims->n_samples + 1) < ((int64_t)1 << 31), "dccf_adam_link_ids: too many records");
+    if (n_pairs <= 0) return DCCF_OK;
+    const int64_t n = n_pairs * (dims->n_samples + 2);
+    k_link_ids<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+        X, sample_item, n_pairs, dims->n_samples, dims->user_base, dims->n_users, dims->n_items, head_user, next_user,
+        head_item, next_item);
+    DCCF_CHECK_LAUNCH("k_link_ids");
+    return DCCF_OK;
+}
+
+extern "C" int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam* hp, void* stream_) {
+    AdamAllArgs a;
+    int32_t blocks = 0, link_blocks = 0;
+    // record buffers are not read by this kernel: strip them so the validation does not demand them
+    dccf_adam_table local[ADAM_MAX_T];
+    DCCF_CHECK_ARG(n_tables >= 0 && n_tables <= ADAM_MAX_T && (n_tables == 0 || tables), "dccf_adam_untouched: bad table array");
+    for (int i = 0; i < n_tables; ++i) {
+        local[i] = tables[i];
+        local[i].n_seg = 0; local[i].seg_len = 0;
+    }
+    int rc = marshal_adam("dccf_adam_untouched", local, n_tables, nullptr, 0, hp, 1, a, &blocks, &link_blocks);
+    if (rc != DCCF_OK) return rc;
+    if (blocks > 0) {
+        // Occupancy limiter: the sweep runs beside the tensor-core kernels of the forward / backward (96 KB of shared
+        // memory, ~48 K registers per CTA).  Two sweep CTAs on one SM would leave no room for such a CTA and push it
+        // into a second wave, so every sweep CTA reserves (and never touches) 120 KB of dynamic shared memory:
+        // at most one per SM, and 120 + 96 KB still fit the 227 KB of an SM.
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(k_adam_untouched, cudaFuncAttributeMaxDynamicSharedMemorySize, ADAM_SIDE_SMEM);
+            if (e != cudaSuccess) {
+                set_error("dccf_adam_untouched: cannot opt in to %d bytes of shared memory: %s", ADAM_SIDE_SMEM, cudaGetErrorString(e));
+                return DCCF_ERR_CUDA;
+            }
+            attr_set = true;
+        }
+        k_adam_untouched<<<(unsigned)blocks, 256, ADAM_SIDE_SMEM, (cudaStream_t)stream_>>>(a);
+        DCCF_CHECK_LAUNCH("k_adam_untouched");
+    }
+    return DCCF_OK;
+}
+
+extern "C" int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
+                                 int32_t n_dense, const dccf_adam* hp, int32_t already_linked, float* w_image,
+                                 int32_t w_image_tensor, int32_t w_image_K, int32_t* cta_counter, int32_t* advance_step_dev,
+                                 uint64_t* advance_offset_dev, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AdamAllArgs a;
+    int32_t blocks = 0, link_blocks = 0;
+    int rc = marshal_adam("dccf_adam_touched", tables, n_tables, dense, n_dense, hp, 2, a, &blocks, &link_blocks);
+    if (rc != DCCF_OK) return rc;
+    DCCF_CHECK_ARG(w_image == nullptr || (w_image_tensor >= 0 && w_image_tensor < n_dense && w_image_K > 0 && w_image_K % 32 == 0 &&
+                                          dense[w_image_tensor].n == (int64_t)D * w_image_K),
+                   "dccf_adam_touched: the W image needs the index of W [D, K] among the dense tensors and K %% 32 == 0");
+    WImageArgs wi;
+    wi.img = w_image; wi.tensor = w_image_tensor; wi.K = w_image_K;
+    wi.cta_counter = cta_counter; wi.step_dev = advance_step_dev; wi.offset_dev = advance_offset_dev;
+    DCCF_CHECK_ARG(cta_counter != nullptr || (advance_step_dev == nullptr && advance_offset_dev == nullptr),
+                   "dccf_adam_touched: advancing the counters needs cta_counter");
+    if (link_blocks > 0 && !already_linked) {
+        k_link_all<<<(unsigned)link_blocks, 256, 0, stream>>>(a);
+        DCCF_CHECK_LAUNCH("k_link_all");
+    }
+    if (blocks > 0) {
+        k_adam_touched<<<(unsigned)blocks, 256, 0, stream>>>(a, wi);
+        DCCF_CHECK_LAUNCH("k_adam_touched");
     }
     return DCCF_OK;
 }

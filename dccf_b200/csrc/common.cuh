@@ -131,6 +131,24 @@ __device__ __forceinline__ float4 dropout_quad(const RngKey& key, uint32_t row, 
 }
 
 // ------------------------------------------------------------------------------------------
+// debug timeline: when a buffer is installed (dccf_debug_timeline), thread 0 of every CTA of an instrumented
+// kernel records the earliest start / latest end of its kernel in nanoseconds of %globaltimer:
+// slot s -> {min start, max end}.  A null pointer (the default) costs one uniform load per CTA.
+// ------------------------------------------------------------------------------------------
+static __device__ unsigned long long* g_timeline = nullptr;
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void tl_begin(int slot) {
+    if (threadIdx.x == 0 && g_timeline != nullptr) atomicMin(g_timeline + 2 * slot, global_ns());
+}
+__device__ __forceinline__ void tl_end(int slot) {
+    if (threadIdx.x == 0 && g_timeline != nullptr) atomicMax(g_timeline + 2 * slot + 1, global_ns());
+}
+
+// ------------------------------------------------------------------------------------------
 // small utilities
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(256) k_backdoor(const dccf_expo ex, const int6
     const int lane = threadIdx.x & 31;
     const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (p >= n_pairs) return;  // warp-uniform
-    backdoor_pair(ex, X, sample_item, p, lane, n_users, user_base, n_items, S, A, ws_rows, out_pred, save_w, err_flag);
+    backdoor_pair(ex, X, sample_item, p, lane, n_users, user_base, n_items, S, A, ws_rows + p * ((S + 1) * A), out_pred + p,
+                  save_w != nullptr ? save_w + p * (S + 1) : nullptr, err_flag);
 }
 
 void launch_transpose_w(const float* W, float* Wt, int K, cudaStream_t stream) {

@@ -102,6 +102,7 @@ struct TrainFwdParams {
     const int64_t* sample_item;
     const float* noise;          // mode 1
     float* pre_part;             // [n_ksplits][N][D]
+    float* x_save;               // optional [N][F]: Feat[i_r] + eps_r as multiplied, for the dW kernel of the same step
     int32_t* err_flag;
     int64_t n_rows;
     int32_t n_items, F, S, A, R;
@@ -111,7 +112,7 @@ struct TrainFwdParams {
 };
 
 template <int NOISE_MODE>
-__global__ void __launch_bounds__(TC_NT, 1) k_train_fwd_tc(const TrainFwdParams prm) {
+__global__ void __launch_bounds__(TC_NT, 2) k_train_fwd_tc(const TrainFwdParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + TC_STAGES;
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(TC_NT, 1) k_train_fwd_tc(const TrainFwdParams 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    tl_begin(2);
     const int64_t row_base = (int64_t)blockIdx.x * TC_BM;
     const int ks = (int)blockIdx.y, n_ks = (int)gridDim.y;
     const int c_lo = (int)(((int64_t)ks * prm.n_chunks) / n_ks);
@@ -174,6 +176,10 @@ __global__ void __launch_bounds__(TC_NT, 1) k_train_fwd_tc(const TrainFwdParams 
                         v[q].x = __fadd_rn(v[q].x, e.x); v[q].y = __fadd_rn(v[q].y, e.y);
                         v[q].z = __fadd_rn(v[q].z, e.z); v[q].w = __fadd_rn(v[q].w, e.w);
                     }
+                }
+                if (prm.x_save != nullptr && row_base + row < prm.n_rows) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) st4(prm.x_save + (size_t)grow * prm.F + kq * 8 + f0 + 4 * q, v[q]);
                 }
             }
             tc::mbar_wait(&empty_bar[s], ph ^ 1u);   // the MMAs that read this stage have completed
@@ -243,6 +249,7 @@ __global__ void __launch_bounds__(TC_NT, 1) k_train_fwd_tc(const TrainFwdParams 
 
     tc::tc_fence_before_sync();
     __syncthreads();
+    tl_end(2);
     if (warp == TC_PRODUCERS / 32) tc::tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
@@ -308,7 +315,219 @@ __global__ void __launch_bounds__(128) k_train_fwd_finish(const TrainFinishParam
     __syncthreads();   // the pair's row scores (global memory, written by this CTA) are visible to warp 0
     if (tid < 32)
         backdoor_pair(prm.ex, prm.X, prm.sample_item, p, lane, prm.n_users, prm.user_base, prm.n_items, prm.S, prm.A,
-                      prm.ws_rows, prm.out_pred, prm.save_w, prm.err_flag);
+                      prm.ws_rows + p * prm.R, prm.out_pred + p,
+                      prm.save_w != nullptr ? prm.save_w + p * (prm.S + 1) : nullptr, prm.err_flag);
+}
+
+// =============================================================================================
+// fused middle of the step (BPR / MSE loss): per-pair forward epilogue, backdoor sum, loss term, d loss / d pred,
+// dpre rows and the embedding-gradient records in ONE kernel.  A CTA owns one loss term: with BPR the positive
+// pair j and its negative j + b (src/models/DCCF.py:116-120), so d loss / d pred needs no second pass over
+// global memory and the activations h never leave shared memory.
+// =============================================================================================
+constexpr int TM_NT = 256;
+
+struct TrainMidParams {
+    dccf_expo ex;
+    const float* E_user;
+    const float* W;
+    const float* bias;
+    const int64_t* X;
+    const int64_t* sample_item;
+    const float* Y;
+    const float* mask;           // mode 1
+    const float* pre_part;
+    float* out_pred;
+    float* loss_terms;
+    float* dpre_rows;
+    float* gu_rec;
+    float* gi_rec;
+    int32_t* rec_keys_u;
+    int32_t* rec_keys_i;
+    float* save_h;               // optional
+    float* save_w;               // optional
+    int32_t* err_flag;
+    int64_t n_pairs, n_rows;
+    int32_t n_users, user_base, n_items, S, A, R, Z, K;
+    int32_t n_ksplits, mask_mode, loss_mode;
+    float keep_prob, drop_scale, inv_A;
+    RngSpec rng;
+};
+
+__host__ __device__ inline size_t train_mid_smem_floats(int R, int Z, int npc) {
+    return (size_t)D * D + (size_t)npc * R * D + (size_t)npc * Z * D + (size_t)npc * R + (size_t)npc * Z + 8;
+}
+
+__global__ void __launch_bounds__(TM_NT) k_train_mid(const TrainMidParams prm) {
+    extern __shared__ __align__(16) float sm[];
+    const int R = prm.R, Z = prm.Z, A = prm.A;
+    const int npc = (prm.loss_mode == 0) ? 2 : 1;   // pairs per CTA
+    float* Wi_s = sm;                               // [D][D]   Wi_s[j*D + k] = W[j][k], k < D
+    float* h_s = Wi_s + D * D;                      // [npc*R][D] post-dropout activations
+    float* dsum_s = h_s + (size_t)npc * R * D;      // [npc*Z][D] sum_a dpre
+    float* score_s = dsum_s + (size_t)npc * Z * D;  // [npc*R]
+    float* w_s = score_s + npc * R;                 // [npc*Z]  softmax exposure weights
+    float* pred_s = w_s + npc * Z;                  // [2]
+    float* dpred_s = pred_s + 2;                    // [2]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    tl_begin(3);
+    const int hw = tid >> 4, sub = tid & 15;
+    const int64_t jt = blockIdx.x;
+    const int64_t b = prm.n_pairs >> 1;
+    const int64_t p_second = (prm.loss_mode == 0) ? jt + b : jt;
+    auto pair_of = [&](int q) { return q == 0 ? jt : p_second; };
+    const uint32_t half_mask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;
+
+    for (int i = tid; i < D * D / 4; i += TM_NT) {
+        const int j = i / (D / 4), q4 = i % (D / 4);
+        st4(&Wi_s[j * D + q4 * 4], ldg4(prm.W + (size_t)j * prm.K + q4 * 4));
+    }
+    const float4 bia = ldg4(prm.bias + sub * 4);
+    // the user rows of the CTA's (at most two) pairs, columns 4*sub .. 4*sub+3
+    const int32_t u0 = checked_id(prm.X[2 * jt] - prm.user_base, prm.n_users, prm.err_flag);
+    const int32_t u1 = checked_id(prm.X[2 * p_second] - prm.user_base, prm.n_users, prm.err_flag);
+    const float4 eu0 = ldg4(prm.E_user + (size_t)u0 * D + sub * 4);
+    const float4 eu1 = ldg4(prm.E_user + (size_t)u1 * D + sub * 4);
+    RngKey key_drop = make_rng_key(0, 0, DOMAIN_DROPOUT);
+    if (prm.mask_mode == 2) key_drop = resolve_rng_key(prm.rng, DOMAIN_DROPOUT);
+    const size_t part_stride = (size_t)prm.n_rows * D;
+
+    // ---- A: rows of the CTA's pairs: partial sums + bias, ReLU, dropout, dot with the user row -------------
+    for (int rr = hw; rr < npc * R; rr += TM_NT / 16) {
+        const int q = rr / R, l = rr - q * R;
+        const int64_t p = pair_of(q);
+        const int64_t r = p * R + l;
+        const float4 e = q == 0 ? eu0 : eu1;
+        const float* src = prm.pre_part + (size_t)r * D + sub * 4;
+        float4 acc = ldg4(src);
+        for (int k = 1; k < prm.n_ksplits; ++k) {
+            const float4 t = ldg4(src + (size_t)k * part_stride);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        float4 h = make_float4(fmaxf(acc.x + bia.x, 0.f), fmaxf(acc.y + bia.y, 0.f), fmaxf(acc.z + bia.z, 0.f),
+                               fmaxf(acc.w + bia.w, 0.f));
+        if (prm.mask_mode == 1) {
+            const float4 m = ldg4(prm.mask + (size_t)r * D + sub * 4);
+            h.x *= m.x; h.y *= m.y; h.z *= m.z; h.w *= m.w;
+        } else if (prm.mask_mode == 2) {
+            const float4 m = dropout_quad(key_drop, (uint32_t)r, (uint32_t)sub, prm.keep_prob, prm.drop_scale);
+            h.x *= m.x; h.y *= m.y; h.z *= m.z; h.w *= m.w;
+        }
+        if (prm.save_h != nullptr) st4(prm.save_h + (size_t)r * D + sub * 4, h);
+        st4(h_s + (size_t)rr * D + sub * 4, h);
+        float dot = h.x * e.x;
+        dot = fmaf(h.y, e.y, dot);
+        dot = fmaf(h.z, e.z, dot);
+        dot = fmaf(h.w, e.w, dot);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(half_mask, dot, o);
+        if (sub == 0) score_s[rr] = dot;
+    }
+    __syncthreads();
+
+    // ---- B: backdoor-adjusted sum of each pair (one warp per pair), then the loss term and d loss / d pred ----
+    if (warp < npc) {
+        const int64_t p = pair_of(warp);
+        backdoor_pair(prm.ex, prm.X, prm.sample_item, p, lane, prm.n_users, prm.user_base, prm.n_items, prm.S, A,
+                      score_s + warp * R, pred_s + warp, w_s + warp * Z, prm.err_flag);
+        __syncwarp();
+        if (lane == 0) prm.out_pred[p] = pred_s[warp];
+        if (prm.save_w != nullptr)
+            for (int z = lane; z < Z; z += 32) prm.save_w[p * Z + z] = w_s[warp * Z + z];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (prm.loss_mode == 0) {
+            const float d = pred_s[0] - pred_s[1];
+            const float sg = 1.f / (1.f + expf(-d));
+            const float g = -(1.f - sg);
+            dpred_s[0] = g;
+            dpred_s[1] = -g;
+            // -log(sigmoid(d)) = softplus(-d), evaluated the stable way
+            prm.loss_terms[jt] = (d > 0.f) ? log1pf(expf(-d)) : (-d + log1pf(expf(d)));
+        } else {
+            const float d = pred_s[0] - __ldg(prm.Y + jt);
+            dpred_s[0] = 2.f * d / (float)prm.n_pairs;
+            prm.loss_terms[jt] = d * d;
+        }
+    }
+    __syncthreads();
+
+    // ---- C1: dpre rows (to global memory for the dW kernel) and their sum over the attribute copies ---------
+    for (int qz = hw; qz < npc * Z; qz += TM_NT / 16) {
+        const int q = qz / Z, z = qz - q * Z;
+        const int64_t p = pair_of(q);
+        const float4 e = q == 0 ? eu0 : eu1;
+        const float ds = dpred_s[q] * w_s[qz] * prm.inv_A;
+        float4 dsum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int a = 0; a < A; ++a) {
+            const int l = z * A + a;
+            const int64_t r = p * R + l;
+            const float4 h = ld4(h_s + (size_t)(q * R + l) * D + sub * 4);
+            float4 g;
+            if (prm.mask_mode == 1) {
+                const float4 m = ldg4(prm.mask + (size_t)r * D + sub * 4);
+                g = make_float4(h.x > 0.f ? m.x : 0.f, h.y > 0.f ? m.y : 0.f, h.z > 0.f ? m.z : 0.f, h.w > 0.f ? m.w : 0.f);
+            } else {
+                const float sc = (prm.mask_mode == 2) ? prm.drop_scale : 1.f;
+                g = make_float4(h.x > 0.f ? sc : 0.f, h.y > 0.f ? sc : 0.f, h.z > 0.f ? sc : 0.f, h.w > 0.f ? sc : 0.f);
+            }
+            const float4 dv = make_float4(ds * e.x * g.x, ds * e.y * g.y, ds * e.z * g.z, ds * e.w * g.w);
+            st4(prm.dpre_rows + (size_t)r * D + sub * 4, dv);
+            dsum.x += dv.x; dsum.y += dv.y; dsum.z += dv.z; dsum.w += dv.w;
+        }
+        st4(dsum_s + (size_t)qz * D + sub * 4, dsum);
+    }
+    // user-row record: gu[c] = sum_{z,a} ds * h[.,c], rows in ascending order (thread = column)
+    if (tid < npc * D) {
+        const int q = tid >> 6, c = tid & (D - 1);
+        const int64_t p = pair_of(q);
+        float gu = 0.f;
+        for (int l = 0; l < R; ++l) {
+            const float ds = dpred_s[q] * w_s[q * Z + l / A] * prm.inv_A;
+            gu = fmaf(ds, h_s[(size_t)(q * R + l) * D + c], gu);
+        }
+        prm.gu_rec[(size_t)p * D + c] = gu;
+        if (c == 0) prm.rec_keys_u[p] = q == 0 ? u0 : u1;
+    }
+    __syncthreads();
+
+    // ---- C2: item-row records gi[k] = sum_j W[j][k] * dsum[j]  (thread = column k, ascending j; four records
+    // per thread at a time so that four independent FMA chains share each W value) ------------------------------
+    {
+        const int k = tid & (D - 1);
+        const int n_qz = npc * Z;
+        for (int base = (tid >> 6) * 4; base < n_qz; base += (TM_NT / D) * 4) {
+            const float* d0 = dsum_s + (size_t)min(base + 0, n_qz - 1) * D;
+            const float* d1 = dsum_s + (size_t)min(base + 1, n_qz - 1) * D;
+            const float* d2 = dsum_s + (size_t)min(base + 2, n_qz - 1) * D;
+            const float* d3 = dsum_s + (size_t)min(base + 3, n_qz - 1) * D;
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < D; ++j) {
+                const float w = Wi_s[j * D + k];
+                g0 = fmaf(w, d0[j], g0);
+                g1 = fmaf(w, d1[j], g1);
+                g2 = fmaf(w, d2[j], g2);
+                g3 = fmaf(w, d3[j], g3);
+            }
+            const float gv[4] = {g0, g1, g2, g3};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int qz = base + i;
+                if (qz < n_qz) {
+                    const int q = qz / Z, z = qz - q * Z;
+                    const int64_t rec = pair_of(q) * Z + z;
+                    prm.gi_rec[(size_t)rec * D + k] = gv[i];
+                    if (k == 0)
+                        prm.rec_keys_i[rec] = checked_id(slot_item(prm.X, prm.sample_item, pair_of(q), z, prm.S), prm.n_items, nullptr);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    tl_end(3);
 }
 
 // =============================================================================================
@@ -323,8 +542,13 @@ struct TrainBwdParams {
     const int64_t* sample_item;
     const float* noise;          // mode 1
     const float* dpre_rows;      // [N, D]
+    const float* x_rows;         // optional [N, F]: the forward's Feat + eps rows (else regenerated here)
     float* gW_part;              // [n_splits][D][K]
     float* gb_part;              // [n_splits][D]
+    const float* loss_terms;     // optional [n_loss_terms]: summed into out_loss by CTA (0,0) (fused step)
+    float* out_loss;
+    int64_t n_loss_terms;
+    float loss_scale;
     int64_t n_rows;
     int32_t n_items, F, S, A, R, K;
     int32_t rows_per_split;      // multiple of 32
@@ -346,7 +570,7 @@ __device__ __forceinline__ void quad_transpose(float4& a, int j) {
 }
 
 template <int NOISE_MODE>
-__global__ void __launch_bounds__(TB_NT, 1) k_train_bwd_tc(const TrainBwdParams prm) {
+__global__ void __launch_bounds__(TB_NT, 2) k_train_bwd_tc(const TrainBwdParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + TC_STAGES;
@@ -354,6 +578,7 @@ __global__ void __launch_bounds__(TB_NT, 1) k_train_bwd_tc(const TrainBwdParams 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    tl_begin(4);
     const int mt = (int)blockIdx.x, sp = (int)blockIdx.y;
     const int64_t row_lo = (int64_t)sp * prm.rows_per_split;
     const int64_t row_hi = min(row_lo + prm.rows_per_split, prm.n_rows);
@@ -384,13 +609,9 @@ __global__ void __launch_bounds__(TB_NT, 1) k_train_bwd_tc(const TrainBwdParams 
         RngKey key_noise = make_rng_key(0, 0, DOMAIN_NOISE);
         if (NOISE_MODE == 2) key_noise = resolve_rng_key(prm.rng, DOMAIN_NOISE);
 
-        for (int st = 0; st < n_st; ++st) {
-            const int s = st % TC_STAGES;
-            const uint32_t ph = (uint32_t)(st / TC_STAGES) & 1u;
+        // operands of stage st: dpre values (B) and this lane's 4 columns of x for its row (A, before the transpose)
+        auto fetch = [&](int st, float4 (&v)[2], float4& dv) {
             const int64_t rb = row_lo + (int64_t)st * TC_KC;
-
-            // dpre values first: their loads are in flight while the noise is generated
-            float4 dv;
             {
                 const int64_t r0 = rb + brq * 4;
                 const float* src = prm.dpre_rows + (size_t)r0 * D + bc;
@@ -399,11 +620,11 @@ __global__ void __launch_bounds__(TB_NT, 1) k_train_bwd_tc(const TrainBwdParams 
                 dv.z = (r0 + 2 < row_hi) ? __ldg(src + 2 * D) : 0.f;
                 dv.w = (r0 + 3 < row_hi) ? __ldg(src + 3 * D) : 0.f;
             }
-
             const int64_t r = rb + rq * 4 + j;
             const bool live = r < row_hi;
+            const bool need_ids = live && (prm.x_rows == nullptr || mt == 0);
             int32_t fi = 0, it = 0;
-            if (live) {
+            if (need_ids) {
                 const uint32_t p = (uint32_t)r / (uint32_t)prm.R;
                 fi = checked_id(prm.X[2 * (int64_t)p + 1], prm.n_items, nullptr);
                 if (mt == 0) {
@@ -411,7 +632,6 @@ __global__ void __launch_bounds__(TB_NT, 1) k_train_bwd_tc(const TrainBwdParams 
                     it = (z == 0) ? fi : checked_id(prm.sample_item[(int64_t)p * prm.S + (z - 1)], prm.n_items, nullptr);
                 }
             }
-            float4 v[2];
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
                 const int col = mt * TC_BM + (cb0 + 2 * t) * 32 + g * 4;   // first of this lane's 4 columns of [x | 1]
@@ -421,19 +641,33 @@ __global__ void __launch_bounds__(TB_NT, 1) k_train_bwd_tc(const TrainBwdParams 
                         v[t] = ldg4(prm.E_item + (size_t)it * D + col);
                     } else if (col < prm.K) {
                         const int f = col - D;
-                        v[t] = ldg4(prm.Feat + (size_t)fi * prm.F + f);
-                        if (NOISE_MODE != 0) {
-                            float4 e;
-                            if (NOISE_MODE == 1) e = ldg4(prm.noise + (size_t)r * prm.F + f);
-                            else e = noise_quad(key_noise, (uint32_t)r, (uint32_t)(f / 4), prm.noise_std);
-                            v[t].x = __fadd_rn(v[t].x, e.x); v[t].y = __fadd_rn(v[t].y, e.y);
-                            v[t].z = __fadd_rn(v[t].z, e.z); v[t].w = __fadd_rn(v[t].w, e.w);
+                        if (prm.x_rows != nullptr) {
+                            v[t] = ldg4(prm.x_rows + (size_t)r * prm.F + f);
+                        } else {
+                            v[t] = ldg4(prm.Feat + (size_t)fi * prm.F + f);
+                            if (NOISE_MODE != 0) {
+                                float4 e;
+                                if (NOISE_MODE == 1) e = ldg4(prm.noise + (size_t)r * prm.F + f);
+                                else e = noise_quad(key_noise, (uint32_t)r, (uint32_t)(f / 4), prm.noise_std);
+                                v[t].x = __fadd_rn(v[t].x, e.x); v[t].y = __fadd_rn(v[t].y, e.y);
+                                v[t].z = __fadd_rn(v[t].z, e.z); v[t].w = __fadd_rn(v[t].w, e.w);
+                            }
                         }
                     } else if (col == prm.K) {
                         v[t].x = 1.f;                 // the column of ones: its output row is the bias gradient
                     }
                 }
             }
+        };
+
+        float4 v[2], dv;
+        if (n_st > 0) fetch(0, v, dv);
+        for (int st = 0; st < n_st; ++st) {
+            const int s = st % TC_STAGES;
+            const uint32_t ph = (uint32_t)(st / TC_STAGES) & 1u;
+            // the next stage's operands are in flight while this one is transposed, stored and multiplied
+            float4 vn[2], dvn;
+            if (st + 1 < n_st) fetch(st + 1, vn, dvn);
             quad_transpose(v[0], j);
             quad_transpose(v[1], j);
 
@@ -451,6 +685,17 @@ __global__ void __launch_bounds__(TB_NT, 1) k_train_bwd_tc(const TrainBwdParams 
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&full_bar[s]);
+            if (st + 1 < n_st) {
+                v[0] = vn[0]; v[1] = vn[1]; dv = dvn;
+            }
+        }
+        // the scalar loss of the fused step: per-term values summed in a fixed order (lane-strided, then a shuffle
+        // tree) by one warp that is idle during the epilogue
+        if (warp == 4 && mt == 0 && sp == 0 && prm.loss_terms != nullptr) {
+            float acc = 0.f;
+            for (int64_t i = lane; i < prm.n_loss_terms; i += 32) acc += __ldg(prm.loss_terms + i);
+            acc = warp_sum(acc);
+            if (lane == 0) prm.out_loss[0] = acc * prm.loss_scale;
         }
     } else {
         // ===== MMA issuer =====
@@ -499,6 +744,7 @@ __global__ void __launch_bounds__(TB_NT, 1) k_train_bwd_tc(const TrainBwdParams 
 
     tc::tc_fence_before_sync();
     __syncthreads();
+    tl_end(4);
     if (warp == TC_PRODUCERS / 32) tc::tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
@@ -557,6 +803,22 @@ extern "C" int64_t dccf_train_w_image_floats(int32_t feat_dim) {
     return (int64_t)((D + feat_dim) / TC_KC) * (2 * TC_B_BYTES / 4);
 }
 
+extern "C" int dccf_debug_timeline_train(unsigned long long* slots) {
+    cudaError_t e = cudaMemcpyToSymbol(g_timeline, &slots, sizeof(slots));
+    if (e != cudaSuccess) {
+        set_error("dccf_debug_timeline: %s", cudaGetErrorString(e));
+        return DCCF_ERR_CUDA;
+    }
+    return DCCF_OK;
+}
+
+extern "C" int dccf_train_prep_w_image(const float* W, int32_t feat_dim, float* w_image, void* stream_) {
+    DCCF_CHECK_ARG(W && w_image && feat_dim > 0 && feat_dim % 64 == 0, "dccf_train_prep_w_image: bad argument");
+    k_prep_w_image<<<104, 256, 0, (cudaStream_t)stream_>>>(W, D + feat_dim, w_image);
+    DCCF_CHECK_LAUNCH("k_prep_w_image");
+    return DCCF_OK;
+}
+
 extern "C" int32_t dccf_train_fwd_ksplits(int64_t n_rows, int32_t feat_dim) {
     return fwd_ksplits_for(n_rows, (D + feat_dim) / TC_KC);
 }
@@ -567,30 +829,13 @@ extern "C" int32_t dccf_train_bwd_splits(int64_t n_rows, int32_t feat_dim) {
     return ns;
 }
 
-extern "C" int dccf_train_fwd_tc(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
-                                 const float* W, const float* b, const dccf_expo* expo, const int64_t* X,
-                                 const int64_t* sample_item, int64_t n_pairs, const dccf_rng* rng, float* out_pred,
-                                 float* ws_rows, float* ws_wimg, float* ws_pre_part, float* save_h, float* save_w,
-                                 int32_t* err_flag, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    DCCF_CHECK_ARG(dims && expo && rng, "dccf_train_fwd_tc: null struct argument");
-    DCCF_CHECK_ARG(dims->dim == D, "dccf_train_fwd_tc: dim=%d but this build has D=%d", dims->dim, D);
-    DCCF_CHECK_ARG(dims->feat_dim > 0 && dims->feat_dim % 64 == 0, "dccf_train_fwd_tc: feat_dim=%d must be a positive multiple of 64", dims->feat_dim);
-    DCCF_CHECK_ARG(dims->n_samples >= 0 && dims->n_attr >= 1, "dccf_train_fwd_tc: bad n_samples/n_attr");
-    DCCF_CHECK_ARG(E_user && E_item && Feat && W && b && X && out_pred && ws_rows && ws_wimg && ws_pre_part, "dccf_train_fwd_tc: null buffer");
-    DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item, "dccf_train_fwd_tc: sample_item is null");
-    DCCF_CHECK_ARG(rng->noise_mode >= 0 && rng->noise_mode <= 2 && rng->mask_mode >= 0 && rng->mask_mode <= 2, "dccf_train_fwd_tc: bad rng mode");
-    DCCF_CHECK_ARG(rng->noise_mode != 1 || rng->noise, "dccf_train_fwd_tc: noise_mode 1 needs a noise tensor");
-    DCCF_CHECK_ARG(rng->mask_mode != 1 || rng->mask, "dccf_train_fwd_tc: mask_mode 1 needs a mask tensor");
-    DCCF_CHECK_ARG(expo->mode == 0 ? expo->dense != nullptr
-                                   : (expo->mode == 1 && expo->mf_user && expo->mf_item && expo->mf_user_bias && expo->mf_item_bias && expo->propensity),
-                   "dccf_train_fwd_tc: exposure source incomplete (mode %d)", expo->mode);
-    if (n_pairs <= 0) return DCCF_OK;
+// W images + partial products of every (row tile, K split)
+static int launch_fwd_tc(const dccf_dims* dims, const float* E_item, const float* Feat, const float* W, const int64_t* X,
+                         const int64_t* sample_item, int64_t n_pairs, const dccf_rng* rng, float* ws_wimg,
+                         bool w_image_valid, float* ws_pre_part, float* x_save, int32_t* err_flag, int32_t* n_ks_out,
+                         cudaStream_t stream) {
     const int F = dims->feat_dim, K = D + F, Z = dims->n_samples + 1, R = Z * dims->n_attr;
     const int64_t n_rows = n_pairs * R;
-    DCCF_CHECK_ARG(n_rows < (int64_t)1 << 31, "dccf_train_fwd_tc: %lld rows in one call (max 2^31-1)", (long long)n_rows);
-    DCCF_CHECK_ARG(n_pairs < (int64_t)1 << 31, "dccf_train_fwd_tc: too many pairs");
-
     static bool attr_set = false;
     if (!attr_set) {
         int rc = opt_in_smem(k_train_fwd_tc<0>, "dccf_train_fwd_tc");
@@ -599,17 +844,18 @@ extern "C" int dccf_train_fwd_tc(const dccf_dims* dims, const float* E_user, con
         if (rc != DCCF_OK) return rc;
         attr_set = true;
     }
-
-    k_prep_w_image<<<104, 256, 0, stream>>>(W, K, ws_wimg);
-    DCCF_CHECK_LAUNCH("k_prep_w_image");
-
+    if (!w_image_valid) {
+        k_prep_w_image<<<104, 256, 0, stream>>>(W, K, ws_wimg);
+        DCCF_CHECK_LAUNCH("k_prep_w_image");
+    }
     TrainFwdParams prm;
     prm.E_item = E_item; prm.Feat = Feat; prm.gWimg = ws_wimg; prm.X = X; prm.sample_item = sample_item;
-    prm.noise = rng->noise; prm.pre_part = ws_pre_part; prm.err_flag = err_flag; prm.n_rows = n_rows;
+    prm.noise = rng->noise; prm.pre_part = ws_pre_part; prm.x_save = x_save; prm.err_flag = err_flag; prm.n_rows = n_rows;
     prm.n_items = dims->n_items; prm.F = F; prm.S = dims->n_samples; prm.A = dims->n_attr; prm.R = R;
     prm.n_chunks = K / TC_KC; prm.noise_std = rng->noise_std;
     prm.rng.seed = rng->seed; prm.rng.offset = rng->offset; prm.rng.offset_dev = rng->offset_dev;
     const int32_t n_ks = fwd_ksplits_for(n_rows, prm.n_chunks);
+    *n_ks_out = n_ks;
     const dim3 grid((unsigned)((n_rows + TC_BM - 1) / TC_BM), (unsigned)n_ks);
     switch (rng->noise_mode) {
         case 0: k_train_fwd_tc<0><<<grid, TC_NT, TC_SMEM_BYTES, stream>>>(prm); break;
@@ -617,15 +863,84 @@ extern "C" int dccf_train_fwd_tc(const dccf_dims* dims, const float* E_user, con
         default: k_train_fwd_tc<2><<<grid, TC_NT, TC_SMEM_BYTES, stream>>>(prm); break;
     }
     DCCF_CHECK_LAUNCH("k_train_fwd_tc");
+    return DCCF_OK;
+}
+
+// gW / gb partial tiles from the dpre rows (+ the scalar loss of the fused step)
+static int launch_bwd_tc(const dccf_dims* dims, const float* E_item, const float* Feat, const int64_t* X,
+                         const int64_t* sample_item, int64_t n_pairs, const dccf_rng* rng, const float* ws_dpre,
+                         const float* x_rows, float* gW_part, float* gb_part, const float* loss_terms, int64_t n_loss_terms,
+                         float loss_scale, float* out_loss, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        int rc = opt_in_smem(k_train_bwd_tc<0>, "dccf_train_bwd_tc");
+        if (rc == DCCF_OK) rc = opt_in_smem(k_train_bwd_tc<1>, "dccf_train_bwd_tc");
+        if (rc == DCCF_OK) rc = opt_in_smem(k_train_bwd_tc<2>, "dccf_train_bwd_tc");
+        if (rc != DCCF_OK) return rc;
+        attr_set = true;
+    }
+    const int F = dims->feat_dim, K = D + F, Z = dims->n_samples + 1, R = Z * dims->n_attr;
+    TrainBwdParams prm;
+    prm.E_item = E_item; prm.Feat = Feat; prm.X = X; prm.sample_item = sample_item; prm.noise = rng->noise;
+    prm.dpre_rows = ws_dpre; prm.x_rows = x_rows; prm.gW_part = gW_part; prm.gb_part = gb_part; prm.n_rows = n_pairs * R;
+    prm.loss_terms = loss_terms; prm.out_loss = out_loss; prm.n_loss_terms = n_loss_terms; prm.loss_scale = loss_scale;
+    prm.n_items = dims->n_items; prm.F = F; prm.S = dims->n_samples; prm.A = dims->n_attr; prm.R = R; prm.K = K;
+    prm.noise_std = rng->noise_std;
+    prm.rng.seed = rng->seed; prm.rng.offset = rng->offset; prm.rng.offset_dev = rng->offset_dev;
+    int32_t n_mtiles, n_splits;
+    bwd_geometry(prm.n_rows, K, &n_mtiles, &n_splits, &prm.rows_per_split);
+    const dim3 grid((unsigned)n_mtiles, (unsigned)n_splits);
+    switch (rng->noise_mode) {
+        case 0: k_train_bwd_tc<0><<<grid, TB_NT, TC_SMEM_BYTES, stream>>>(prm); break;
+        case 1: k_train_bwd_tc<1><<<grid, TB_NT, TC_SMEM_BYTES, stream>>>(prm); break;
+        default: k_train_bwd_tc<2><<<grid, TB_NT, TC_SMEM_BYTES, stream>>>(prm); break;
+    }
+    DCCF_CHECK_LAUNCH("k_train_bwd_tc");
+    return DCCF_OK;
+}
+
+static int check_fwd_args(const char* who, const dccf_dims* dims, const dccf_expo* expo, const dccf_rng* rng,
+                          const int64_t* sample_item, int64_t n_pairs) {
+    DCCF_CHECK_ARG(dims && expo && rng, "%s: null struct argument", who);
+    DCCF_CHECK_ARG(dims->dim == D, "%s: dim=%d but this build has D=%d", who, dims->dim, D);
+    DCCF_CHECK_ARG(dims->feat_dim > 0 && dims->feat_dim % 64 == 0, "%s: feat_dim=%d must be a positive multiple of 64", who, dims->feat_dim);
+    DCCF_CHECK_ARG(dims->n_samples >= 0 && dims->n_attr >= 1, "%s: bad n_samples/n_attr", who);
+    DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item, "%s: sample_item is null", who);
+    DCCF_CHECK_ARG(rng->noise_mode >= 0 && rng->noise_mode <= 2 && rng->mask_mode >= 0 && rng->mask_mode <= 2, "%s: bad rng mode", who);
+    DCCF_CHECK_ARG(rng->noise_mode != 1 || rng->noise, "%s: noise_mode 1 needs a noise tensor", who);
+    DCCF_CHECK_ARG(rng->mask_mode != 1 || rng->mask, "%s: mask_mode 1 needs a mask tensor", who);
+    DCCF_CHECK_ARG(expo->mode == 0 ? expo->dense != nullptr
+                                   : (expo->mode == 1 && expo->mf_user && expo->mf_item && expo->mf_user_bias && expo->mf_item_bias && expo->propensity),
+                   "%s: exposure source incomplete (mode %d)", who, expo->mode);
+    const int64_t R = (int64_t)(dims->n_samples + 1) * dims->n_attr;
+    DCCF_CHECK_ARG(n_pairs * R < (int64_t)1 << 31, "%s: %lld rows in one call (max 2^31-1)", who, (long long)(n_pairs * R));
+    return DCCF_OK;
+}
+
+extern "C" int dccf_train_fwd_tc(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
+                                 const float* W, const float* b, const dccf_expo* expo, const int64_t* X,
+                                 const int64_t* sample_item, int64_t n_pairs, const dccf_rng* rng, float* out_pred,
+                                 float* ws_rows, float* ws_wimg, float* ws_pre_part, float* save_h, float* save_w,
+                                 int32_t* err_flag, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_fwd_args("dccf_train_fwd_tc", dims, expo, rng, sample_item, n_pairs);
+    if (rc != DCCF_OK) return rc;
+    DCCF_CHECK_ARG(E_user && E_item && Feat && W && b && X && out_pred && ws_rows && ws_wimg && ws_pre_part, "dccf_train_fwd_tc: null buffer");
+    if (n_pairs <= 0) return DCCF_OK;
+    const int Z = dims->n_samples + 1, R = Z * dims->n_attr;
+    int32_t n_ks = 1;
+    rc = launch_fwd_tc(dims, E_item, Feat, W, X, sample_item, n_pairs, rng, ws_wimg, false, ws_pre_part, nullptr, err_flag,
+                       &n_ks, stream);
+    if (rc != DCCF_OK) return rc;
 
     TrainFinishParams fin;
     fin.ex = *expo; fin.E_user = E_user; fin.bias = b; fin.X = X; fin.sample_item = sample_item; fin.mask = rng->mask;
     fin.pre_part = ws_pre_part; fin.ws_rows = ws_rows; fin.save_h = save_h; fin.save_w = save_w; fin.out_pred = out_pred;
-    fin.err_flag = err_flag; fin.n_pairs = n_pairs; fin.n_rows = n_rows; fin.n_users = dims->n_users;
+    fin.err_flag = err_flag; fin.n_pairs = n_pairs; fin.n_rows = n_pairs * R; fin.n_users = dims->n_users;
     fin.user_base = dims->user_base; fin.n_items = dims->n_items; fin.S = dims->n_samples; fin.A = dims->n_attr; fin.R = R;
     fin.n_ksplits = n_ks; fin.mask_mode = rng->mask_mode; fin.keep_prob = 1.0f - rng->p_drop;
     fin.drop_scale = (rng->p_drop < 1.0f) ? 1.0f / (1.0f - rng->p_drop) : 0.0f;
-    fin.rng = prm.rng;
+    fin.rng.seed = rng->seed; fin.rng.offset = rng->offset; fin.rng.offset_dev = rng->offset_dev;
     k_train_fwd_finish<<<(unsigned)n_pairs, 128, 0, stream>>>(fin);
     DCCF_CHECK_LAUNCH("k_train_fwd_finish");
     return DCCF_OK;
@@ -645,30 +960,64 @@ extern "C" int dccf_train_bwd_tc(const dccf_dims* dims, const float* E_user, con
                             save_w, out_loss, nullptr, nullptr, gu_rec, gi_rec, rec_keys_u, rec_keys_i, ws_dpre, false,
                             stream);
     if (rc != DCCF_OK || n_pairs <= 0) return rc;
+    return launch_bwd_tc(dims, E_item, Feat, X, sample_item, n_pairs, rng, ws_dpre, nullptr, gW_part, gb_part, nullptr, 0,
+                         1.f, nullptr, stream);
+}
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        rc = opt_in_smem(k_train_bwd_tc<0>, "dccf_train_bwd_tc");
-        if (rc == DCCF_OK) rc = opt_in_smem(k_train_bwd_tc<1>, "dccf_train_bwd_tc");
-        if (rc == DCCF_OK) rc = opt_in_smem(k_train_bwd_tc<2>, "dccf_train_bwd_tc");
-        if (rc != DCCF_OK) return rc;
-        attr_set = true;
+extern "C" int64_t dccf_train_fused_smem_bytes(int32_t n_samples, int32_t n_attr, int32_t loss_mode) {
+    const int Z = n_samples + 1, R = Z * n_attr;
+    return (int64_t)(train_mid_smem_floats(R, Z, loss_mode == 0 ? 2 : 1) * sizeof(float));
+}
+
+extern "C" int dccf_train_fwd_bwd_tc(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
+                                     const float* W, const float* b, const dccf_expo* expo, const int64_t* X,
+                                     const int64_t* sample_item, const float* Y, int64_t n_pairs, const dccf_rng* rng,
+                                     int32_t loss_mode, float* out_pred, float* out_loss, float* ws_wimg,
+                                     int32_t w_image_valid, float* ws_pre_part, float* ws_dpre, float* ws_x, float* ws_loss_terms,
+                                     float* gW_part, float* gb_part, float* gu_rec, float* gi_rec, int32_t* rec_keys_u,
+                                     int32_t* rec_keys_i, float* save_h, float* save_w, int32_t* err_flag, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_fwd_args("dccf_train_fwd_bwd_tc", dims, expo, rng, sample_item, n_pairs);
+    if (rc != DCCF_OK) return rc;
+    DCCF_CHECK_ARG(loss_mode == 0 || loss_mode == 1, "dccf_train_fwd_bwd_tc: loss_mode must be 0 (BPR) or 1 (MSE)");
+    DCCF_CHECK_ARG(E_user && E_item && Feat && W && b && X && out_pred && out_loss && ws_wimg && ws_pre_part && ws_dpre &&
+                       ws_loss_terms && gW_part && gb_part && gu_rec && gi_rec && rec_keys_u && rec_keys_i,
+                   "dccf_train_fwd_bwd_tc: null buffer");
+    DCCF_CHECK_ARG(loss_mode != 1 || Y, "dccf_train_fwd_bwd_tc: MSE needs Y");
+    DCCF_CHECK_ARG(loss_mode != 0 || n_pairs % 2 == 0, "dccf_train_fwd_bwd_tc: BPR needs an even number of pairs, got %lld", (long long)n_pairs);
+    if (n_pairs <= 0) return DCCF_OK;
+    const int Z = dims->n_samples + 1, R = Z * dims->n_attr, K = D + dims->feat_dim;
+    const size_t smem = train_mid_smem_floats(R, Z, loss_mode == 0 ? 2 : 1) * sizeof(float);
+    DCCF_CHECK_ARG(smem <= 200 * 1024, "dccf_train_fwd_bwd_tc: S=%d A=%d need %zu bytes of shared memory per CTA; use dccf_train_fwd_tc + dccf_train_bwd_tc", dims->n_samples, dims->n_attr, smem);
+    static size_t smem_opted = 48 * 1024;
+    if (smem > smem_opted) {
+        cudaError_t e = cudaFuncSetAttribute(k_train_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("dccf_train_fwd_bwd_tc: cannot opt in to %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+            return DCCF_ERR_CUDA;
+        }
+        smem_opted = smem;
     }
-    const int F = dims->feat_dim, K = D + F, Z = dims->n_samples + 1, R = Z * dims->n_attr;
-    TrainBwdParams prm;
-    prm.E_item = E_item; prm.Feat = Feat; prm.X = X; prm.sample_item = sample_item; prm.noise = rng->noise;
-    prm.dpre_rows = ws_dpre; prm.gW_part = gW_part; prm.gb_part = gb_part; prm.n_rows = n_pairs * R;
-    prm.n_items = dims->n_items; prm.F = F; prm.S = dims->n_samples; prm.A = dims->n_attr; prm.R = R; prm.K = K;
-    prm.noise_std = rng->noise_std;
-    prm.rng.seed = rng->seed; prm.rng.offset = rng->offset; prm.rng.offset_dev = rng->offset_dev;
-    int32_t n_mtiles, n_splits;
-    bwd_geometry(prm.n_rows, K, &n_mtiles, &n_splits, &prm.rows_per_split);
-    const dim3 grid((unsigned)n_mtiles, (unsigned)n_splits);
-    switch (rng->noise_mode) {
-        case 0: k_train_bwd_tc<0><<<grid, TB_NT, TC_SMEM_BYTES, stream>>>(prm); break;
-        case 1: k_train_bwd_tc<1><<<grid, TB_NT, TC_SMEM_BYTES, stream>>>(prm); break;
-        default: k_train_bwd_tc<2><<<grid, TB_NT, TC_SMEM_BYTES, stream>>>(prm); break;
-    }
-    DCCF_CHECK_LAUNCH("k_train_bwd_tc");
-    return DCCF_OK;
+    int32_t n_ks = 1;
+    rc = launch_fwd_tc(dims, E_item, Feat, W, X, sample_item, n_pairs, rng, ws_wimg, w_image_valid != 0, ws_pre_part, ws_x,
+                       err_flag, &n_ks, stream);
+    if (rc != DCCF_OK) return rc;
+
+    TrainMidParams mid;
+    mid.ex = *expo; mid.E_user = E_user; mid.W = W; mid.bias = b; mid.X = X; mid.sample_item = sample_item; mid.Y = Y;
+    mid.mask = rng->mask; mid.pre_part = ws_pre_part; mid.out_pred = out_pred; mid.loss_terms = ws_loss_terms;
+    mid.dpre_rows = ws_dpre; mid.gu_rec = gu_rec; mid.gi_rec = gi_rec; mid.rec_keys_u = rec_keys_u; mid.rec_keys_i = rec_keys_i;
+    mid.save_h = save_h; mid.save_w = save_w; mid.err_flag = err_flag; mid.n_pairs = n_pairs; mid.n_rows = n_pairs * R;
+    mid.n_users = dims->n_users; mid.user_base = dims->user_base; mid.n_items = dims->n_items; mid.S = dims->n_samples;
+    mid.A = dims->n_attr; mid.R = R; mid.Z = Z; mid.K = K; mid.n_ksplits = n_ks; mid.mask_mode = rng->mask_mode;
+    mid.loss_mode = loss_mode; mid.keep_prob = 1.0f - rng->p_drop;
+    mid.drop_scale = (rng->p_drop < 1.0f) ? 1.0f / (1.0f - rng->p_drop) : 0.0f;
+    mid.inv_A = 1.0f / (float)dims->n_attr;
+    mid.rng.seed = rng->seed; mid.rng.offset = rng->offset; mid.rng.offset_dev = rng->offset_dev;
+    const int64_t n_terms = (loss_mode == 0) ? n_pairs / 2 : n_pairs;
+    k_train_mid<<<(unsigned)n_terms, TM_NT, smem, stream>>>(mid);
+    DCCF_CHECK_LAUNCH("k_train_mid");
+
+    return launch_bwd_tc(dims, E_item, Feat, X, sample_item, n_pairs, rng, ws_dpre, ws_x, gW_part, gb_part, ws_loss_terms,
+                         n_terms, loss_mode == 0 ? 1.f : 1.f / (float)n_pairs, out_loss, stream);
 }

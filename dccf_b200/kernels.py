@@ -183,6 +183,26 @@ def train_bwd_tc(dims, E_user, E_item, Feat, W, X, sample_item, Y, rng, loss_mod
     LAUNCHES[0] += 2 if n_pairs > 0 else 0
 
 
+def train_fused_supported(n_samples, n_attr, loss_mode):
+    return int(_lib.load().dccf_train_fused_smem_bytes(int(n_samples), int(n_attr), int(loss_mode))) <= 200 * 1024
+
+
+def train_fwd_bwd_tc(dims, E_user, E_item, Feat, W, b, expo, X, sample_item, Y, rng, loss_mode, out_pred, out_loss,
+                     ws_wimg, w_image_valid, ws_pre_part, ws_dpre, ws_x, ws_loss_terms, gW_part, gb_part, gu_rec, gi_rec,
+                     rec_keys_u, rec_keys_i, save_h=None, save_w=None, err_flag=None):
+    """Forward + BPR/MSE loss + backward of a training step: partial products, fused per-loss-term middle kernel,
+    dW / db tiles (3 launches, 4 when the W operand images must be rebuilt)."""
+    lib = _lib.load()
+    n_pairs = X.shape[0]
+    check(lib.dccf_train_fwd_bwd_tc(ctypes.byref(dims), ptr(E_user), ptr(E_item), ptr(Feat), ptr(W), ptr(b),
+                                    ctypes.byref(expo), ptr(X), ptr(sample_item), ptr(Y), n_pairs, ctypes.byref(rng),
+                                    int(loss_mode), ptr(out_pred), ptr(out_loss), ptr(ws_wimg), int(bool(w_image_valid)),
+                                    ptr(ws_pre_part), ptr(ws_dpre), ptr(ws_x), ptr(ws_loss_terms), ptr(gW_part), ptr(gb_part),
+                                    ptr(gu_rec), ptr(gi_rec), ptr(rec_keys_u), ptr(rec_keys_i), ptr(save_h), ptr(save_w),
+                                    ptr(err_flag), stream_ptr()), 'dccf_train_fwd_bwd_tc')
+    LAUNCHES[0] += (3 if w_image_valid else 4) if n_pairs > 0 else 0
+
+
 def adam_sweep(table, m, v, rec_keys, rec_grads, n_rec, head, nxt, hp):
     lib = _lib.load()
     check(lib.dccf_adam_sweep(ptr(table), ptr(m), ptr(v), table.shape[0], ptr(rec_keys), ptr(rec_grads), int(n_rec),
@@ -242,6 +262,40 @@ def adam_step(tables, dense, hp):
     da = (AdamTensor * max(1, len(dense)))(*dense)
     check(lib.dccf_adam_step(ta, len(tables), da, len(dense), ctypes.byref(hp), stream_ptr()), 'dccf_adam_step')
     LAUNCHES[0] += 2 if any(t.n_seg * t.seg_len > 0 for t in tables) else 1
+
+
+def adam_link_ids(dims, X, sample_item, head_user, next_user, head_item, next_item):
+    """Record lists of the step from the ids alone (before any gradient exists)."""
+    lib = _lib.load()
+    check(lib.dccf_adam_link_ids(ctypes.byref(dims), ptr(X), ptr(sample_item), X.shape[0], ptr(head_user),
+                                 ptr(next_user), ptr(head_item), ptr(next_item), stream_ptr()), 'dccf_adam_link_ids')
+    LAUNCHES[0] += 1 if X.shape[0] > 0 else 0
+
+
+def adam_untouched(tables, hp):
+    """l2 + clip + Adam over the rows no record of this step refers to (head == -1): one launch, <= 148 CTAs."""
+    lib = _lib.load()
+    ta = (AdamTable * max(1, len(tables)))(*tables)
+    check(lib.dccf_adam_untouched(ta, len(tables), ctypes.byref(hp), stream_ptr()), 'dccf_adam_untouched')
+    LAUNCHES[0] += 1
+
+
+def adam_touched(tables, dense, hp, already_linked=False, w_image=None, w_image_tensor=0, w_image_K=0, cta_counter=None,
+                 advance_step_dev=None, advance_offset_dev=None):
+    """Adam over the touched rows and the dense tensors (one launch, two when the records still need linking)."""
+    lib = _lib.load()
+    ta = (AdamTable * max(1, len(tables)))(*tables)
+    da = (AdamTensor * max(1, len(dense)))(*dense)
+    check(lib.dccf_adam_touched(ta, len(tables), da, len(dense), ctypes.byref(hp), int(bool(already_linked)),
+                                ptr(w_image), int(w_image_tensor), int(w_image_K), ptr(cta_counter),
+                                ptr(advance_step_dev), ptr(advance_offset_dev), stream_ptr()), 'dccf_adam_touched')
+    LAUNCHES[0] += 1 if already_linked or not any(t.n_seg * t.seg_len > 0 for t in tables) else 2
+
+
+def train_prep_w_image(W, feat_dim, w_image):
+    lib = _lib.load()
+    check(lib.dccf_train_prep_w_image(ptr(W), int(feat_dim), ptr(w_image), stream_ptr()), 'dccf_train_prep_w_image')
+    LAUNCHES[0] += 1
 
 
 def stage_batch(epoch_ptrs_dev, cursor_dev, n_pairs, n_samples, X_out, si_out):

@@ -156,7 +156,10 @@ class DCCF(DMF):
         else:
             if expo_prob is None:
                 expo_prob = np.load(os.path.join(self.path, self.dataset + '.ips_expo_prob.npy'), mmap_mode='r')
-            self.expo_prob = torch.as_tensor(np.asarray(local_rows(expo_prob)), dtype=torch.float32).to(dev).contiguous()
+            expo_prob = local_rows(expo_prob)
+            if not torch.is_tensor(expo_prob):
+                expo_prob = torch.from_numpy(np.ascontiguousarray(expo_prob, dtype=np.float32))
+            self.expo_prob = expo_prob.to(dev, torch.float32).contiguous()
 
     # ---- kernel plumbing ---------------------------------------------------------------------
     def _dims(self):
@@ -241,6 +244,12 @@ class DCCF(DMF):
     # all SMs by (row tile, K split) / (column tile, row split) — dccf_train_fwd_tc / dccf_train_bwd_tc.  False:
     # the FP32 SIMT kernels (k_row_scores_splitk, k_bpr_bwd), kept as the cross-check of the tensor-core path.
     use_tensor_cores_train = True
+    # forward + loss + backward as dccf_train_fwd_bwd_tc (one fused kernel between the two contractions)
+    use_fused_step = True
+    # True: the forward stores the rows Feat + eps it multiplied and the dW kernel reads them back instead of
+    # regenerating the noise.  Measured slower (the strided 16-byte stores cost the forward 6 us, the dW kernel is
+    # not bound by the noise generation): off.
+    reuse_noise_rows = False
     tc_min_rows = 128 * 148
 
     def _tc_tables(self):
@@ -304,12 +313,12 @@ class DCCF(DMF):
         call['pred'] = pred
         return pred
 
-    def _launch_bwd(self, call, loss_mode, Y):
-        P, N = call['P'], call['N']
+    def _rec_buffers(self, call, loss_mode, n_splits):
+        """Outputs of the backward: row-split partials of dW / db, gradient records + keys, loss.  Under data
+        parallelism the records, keys and loss live directly in the rank's send segment."""
+        P = call['P']
         D, Z = self.ui_vector_size, self.sample_num + 1
         K = D + self.feature_embedding.shape[1]
-        tc = bool(call.get('tc_train'))
-        n_splits = kernels.train_bwd_splits(N, K - D) if tc else kernels.bwd_splits(N)
         rec = {
             'gW_part': self._buf('gW_part', (n_splits, D, K), torch.float32),
             'gb_part': self._buf('gb_part', (n_splits, D), torch.float32),
@@ -329,6 +338,14 @@ class DCCF(DMF):
                         'keys_u': self._buf('keys_u', (P,), torch.int32),
                         'keys_i': self._buf('keys_i', (P * Z,), torch.int32),
                         'loss': self._buf('loss', (1,), torch.float32)})
+        return rec
+
+    def _launch_bwd(self, call, loss_mode, Y):
+        N = call['N']
+        D = self.ui_vector_size
+        F = self.feature_embedding.shape[1]
+        tc = bool(call.get('tc_train'))
+        rec = self._rec_buffers(call, loss_mode, kernels.train_bwd_splits(N, F) if tc else kernels.bwd_splits(N))
         args = (self._dims(), self.uid_embeddings.weight.data, self.iid_embeddings.weight.data,
                 self.feature_embedding, self.mlp[0].weight.data, call['X'], call['sample_item'], Y,
                 call['rng'], loss_mode, call['pred'], call['save_h'], call['save_w'], rec['loss'],
@@ -338,6 +355,35 @@ class DCCF(DMF):
         else:
             kernels.bpr_bwd(*args)
         return rec
+
+    def _fused_step_ok(self, loss_mode):
+        return self.use_tensor_cores and self.use_tensor_cores_train and self.use_fused_step and \
+            loss_mode in (0, 1) and kernels.train_fused_supported(self.sample_num, self.attribute_num, loss_mode)
+
+    def _launch_fwd_bwd(self, call, loss_mode, Y, rec=None, w_image_valid=False):
+        """Forward + loss + backward of one step through dccf_train_fwd_bwd_tc (three launches; the activations
+        never leave shared memory).  Returns (prediction, gradient buffers)."""
+        P, N = call['P'], call['N']
+        D = self.ui_vector_size
+        F = self.feature_embedding.shape[1]
+        dev = self.uid_embeddings.weight.device
+        pred = torch.empty(P, dtype=torch.float32, device=dev)
+        if rec is None:
+            rec = self._rec_buffers(call, loss_mode, kernels.train_bwd_splits(N, F))
+        if P == 0:
+            rec['loss'].zero_()
+            return pred, rec
+        n_ks = kernels.train_fwd_ksplits(N, F)
+        kernels.train_fwd_bwd_tc(
+            self._dims(), self.uid_embeddings.weight.data, self.iid_embeddings.weight.data, self.feature_embedding,
+            self.mlp[0].weight.data, self.mlp[0].bias.data, self._expo(), call['X'], call['sample_item'], Y, call['rng'],
+            loss_mode, pred, rec['loss'], self._buf('ws_wimg', (kernels.train_w_image_floats(F),), torch.float32),
+            w_image_valid, self._buf('ws_pre_part', (n_ks, N, D), torch.float32), self._buf('ws_dpre', (N, D), torch.float32),
+            self._buf('ws_x', (N, F), torch.float32) if self.reuse_noise_rows else None,
+            self._buf('ws_loss_terms', (P,), torch.float32), rec['gW_part'], rec['gb_part'], rec['gu_rec'],
+            rec['gi_rec'], rec['keys_u'], rec['keys_i'], None, None, self._err_flag)
+        call['pred'] = pred
+        return pred, rec
 
     def check_ids(self):
         """Raise if any kernel since the last check met a user/item id outside the tables (the kernels clamp
@@ -491,6 +537,73 @@ class DCCF(DMF):
         kernels.adam_step(tables, dense, hp)
         return rec['loss'][0]
 
+    # single-GPU fused step: the Adam sweep of the rows the batch does not touch runs on a second stream while the
+    # forward and backward run (dccf_adam_mark_touched / _untouched / _touched)
+    use_split_adam = os.environ.get('DCCF_SPLIT_ADAM', '1') != '0'
+    overlap_split_adam = os.environ.get('DCCF_SPLIT_OVERLAP', '1') != '0'
+
+    def _local_tables(self, rec, P, opt):
+        Z = self.sample_num + 1
+        W, b = self.mlp[0].weight.data, self.mlp[0].bias.data
+        eu, ei = self.uid_embeddings.weight.data, self.iid_embeddings.weight.data
+        tables = [
+            kernels.adam_table(eu, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'], rec['keys_u'], rec['gu_rec'], 1, P,
+                               P, P * self.ui_vector_size, opt.head_u, self._buf('next_u', (P,), torch.int32)),
+            kernels.adam_table(ei, opt.exp_avg['E_item'], opt.exp_avg_sq['E_item'], rec['keys_i'], rec['gi_rec'], 1,
+                               P * Z, P * Z, P * Z * self.ui_vector_size, opt.head_i,
+                               self._buf('next_i', (P * Z,), torch.int32))]
+        dense = [kernels.adam_tensor(W, opt.exp_avg['W'], opt.exp_avg_sq['W'], rec['gW_part'], rec['n_splits'],
+                                     W.numel()),
+                 kernels.adam_tensor(b, opt.exp_avg['b'], opt.exp_avg_sq['b'], rec['gb_part'], rec['n_splits'],
+                                     b.numel())]
+        return tables, dense
+
+    def _wimg_key(self):
+        W = self.mlp[0].weight
+        return (W._version, W.data_ptr(), self._param_epoch)
+
+    def _split_step_ok(self, loss_mode):
+        return self._dp is None and self.use_split_adam and self._fused_step_ok(loss_mode)
+
+    def _fused_split_step(self, call, loss_mode, Y, opt, hp, w_image_valid, overlap, counters=None):
+        """Forward + loss + backward + optimizer with the optimizer split around the backward.  overlap=True: the
+        record linking and the sweep of the untouched rows go to a side stream (forked from / joined to the current
+        stream with events, so it is also legal under CUDA-graph capture).  counters = (step_dev, offset_dev): the
+        last CTA of the step advances them.  Returns (prediction, loss)."""
+        P, N = call['P'], call['N']
+        D, F = self.ui_vector_size, self.feature_embedding.shape[1]
+        rec = self._rec_buffers(call, loss_mode, kernels.train_bwd_splits(N, F))
+        tables, dense = self._local_tables(rec, P, opt)
+        next_u, next_i = self._buf('next_u', (P,), torch.int32), self._buf('next_i', (P * (self.sample_num + 1),), torch.int32)
+        wimg = self._buf('ws_wimg', (kernels.train_w_image_floats(F),), torch.float32)
+        if opt.__dict__.get('cta_counter') is None:
+            opt.cta_counter = torch.zeros(1, dtype=torch.int32, device=self.uid_embeddings.weight.device)
+        main = torch.cuda.current_stream()
+        overlap = overlap and self.overlap_split_adam
+
+        def early():
+            kernels.adam_link_ids(self._dims(), call['X'], call['sample_item'], opt.head_u, next_u, opt.head_i, next_i)
+            kernels.adam_untouched(tables, hp)
+
+        if overlap:
+            if self.__dict__.get('_side_stream') is None:
+                self.__dict__['_side_stream'] = torch.cuda.Stream(device=main.device)
+            side = self.__dict__['_side_stream']
+            fork, done = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                early()
+                done.record(side)
+        else:
+            early()
+        pred, rec = self._launch_fwd_bwd(call, loss_mode, Y, rec=rec, w_image_valid=w_image_valid)
+        if overlap:
+            main.wait_event(done)
+        step_dev, offset_dev = counters if counters is not None else (None, None)
+        kernels.adam_touched(tables, dense, hp, True, wimg, 0, D + F, opt.cta_counter, step_dev, offset_dev)
+        return pred, rec['loss'][0]
+
     def train_step(self, feed_dict, opt=None, stage_events=None):
         """One iteration of BaseRunner.fit (src/runners/BaseRunner.py:175-188): forward, loss, l2 term,
         backward, clip, Adam — no autograd, no host sync.  Steps whose random inputs come from the library's
@@ -507,14 +620,24 @@ class DCCF(DMF):
             if out is not None:
                 return out
         call = self._make_call(feed_dict)
+        loss_mode = 0 if feed_dict['rank'] == 1 else 1
+        Y = feed_dict['Y'].to(call['X'].device, torch.float32).contiguous() if loss_mode == 1 else None
+        if stage_events is None and call['P'] > 0 and self._split_step_ok(loss_mode):
+            valid = self.__dict__.get('_wimg_valid_key') == self._wimg_key()
+            opt.step_count += 1
+            self._param_epoch += 1
+            pred, loss = self._fused_split_step(call, loss_mode, Y, opt, opt.hp(), valid, overlap=False)
+            self.__dict__['_wimg_valid_key'] = self._wimg_key()
+            return {'prediction': pred, 'check': [('prediction', pred)], 'loss': loss.clone()}
         if stage_events is not None:
             stage_events[0].record()
-        pred = self._launch_fwd(call, save=True)
-        if stage_events is not None:
-            stage_events[1].record()
-        loss_mode = 0 if feed_dict['rank'] == 1 else 1
-        Y = feed_dict['Y'].to(pred.device, torch.float32).contiguous() if loss_mode == 1 else None
-        rec = self._launch_bwd(call, loss_mode=loss_mode, Y=Y)
+        if stage_events is None and self._fused_step_ok(loss_mode):
+            pred, rec = self._launch_fwd_bwd(call, loss_mode, Y)
+        else:
+            pred = self._launch_fwd(call, save=True)
+            if stage_events is not None:
+                stage_events[1].record()
+            rec = self._launch_bwd(call, loss_mode=loss_mode, Y=Y)
         if stage_events is not None:
             stage_events[2].record()
         opt.step_count += 1
@@ -554,16 +677,32 @@ class DCCF(DMF):
         with torch.cuda.graph(graph, capture_error_mode='thread_local'):
             if staged:
                 kernels.stage_batch(g['epoch_ptrs'], g['cursor'], P, S, g['X'], g['si'])
-            pred = self._launch_fwd(call, save=True)
-            rec = self._launch_bwd(call, loss_mode=0 if rank_mode == 1 else 1, Y=g['Y'] if rank_mode != 1 else None)
-            loss = self._apply_adam(rec, P, opt, hp).clone()
-            kernels.state_advance(g['step_dev'], g['offset_dev'], 1)
+            loss_mode = 0 if rank_mode == 1 else 1
+            Yg = g['Y'] if rank_mode != 1 else None
+            if self._split_step_ok(loss_mode):
+                # the W operand images are kept current by dccf_adam_touched (checked before every replay)
+                pred, loss = self._fused_split_step(call, loss_mode, Yg, opt, hp, True, overlap=True,
+                                                    counters=(g['step_dev'], g['offset_dev']))
+                g['w_image'] = True     # loss: the step's own output buffer (valid until the next train_step)
+            else:
+                if self._fused_step_ok(loss_mode):
+                    pred, rec = self._launch_fwd_bwd(call, loss_mode, Yg)
+                else:
+                    pred = self._launch_fwd(call, save=True)
+                    rec = self._launch_bwd(call, loss_mode=loss_mode, Y=Yg)
+                loss = self._apply_adam(rec, P, opt, hp).clone()
+                kernels.state_advance(g['step_dev'], g['offset_dev'], 1)
         g.update({'graph': graph, 'pred': pred, 'loss': loss, 'call': call,
                   'n_kernels': kernels.LAUNCHES[0] - launches_before})
         kernels.LAUNCHES[0] = launches_before           # capturing launched nothing
         return g
 
     def _replay(self, g, opt):
+        if g.get('w_image') and self.__dict__.get('_wimg_valid_key') != self._wimg_key():
+            # W changed outside the fused steps (or this is the first one): rebuild its operand images
+            F = self.feature_embedding.shape[1]
+            kernels.train_prep_w_image(self.mlp[0].weight.data, F,
+                                       self._buf('ws_wimg', (kernels.train_w_image_floats(F),), torch.float32))
         self._rng_offset += 1
         opt.step_count += 1
         self._param_epoch += 1
@@ -572,6 +711,8 @@ class DCCF(DMF):
             g['step_dev'].fill_(opt.step_count)
             g['offset_dev'].fill_(self._rng_offset)
         g['graph'].replay()
+        if g.get('w_image'):
+            self.__dict__['_wimg_valid_key'] = self._wimg_key()
         kernels.LAUNCHES[0] += g['n_kernels']
         g['synced'] = (opt.step_count + 1, self._rng_offset + 1)
         return {'prediction': g['pred'], 'check': [('prediction', g['pred'])], 'loss': g['loss']}

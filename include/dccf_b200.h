@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 14
+#define DCCF_ABI_VERSION 19
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -185,6 +185,25 @@ int dccf_train_bwd_tc(const dccf_dims* dims, const float* E_user, const float* E
                       float* gb_part, float* gu_rec, float* gi_rec, int32_t* rec_keys_u, int32_t* rec_keys_i,
                       float* ws_dpre, void* stream);
 
+/* Forward + loss + backward of one training step in three launches (BPR loss_mode 0 or MSE loss_mode 1): the
+ * partial products, then ONE fused kernel per loss term (forward epilogue, backdoor sum, loss term,
+ * d loss / d pred, dpre rows, embedding-gradient records — with BPR a CTA owns the positive pair j and its
+ * negative j + P/2), then the dW / db tiles (whose CTA (0,0) also sums the loss terms in a fixed order).
+ *   w_image_valid != 0: ws_wimg already holds the operand images of the current W (dccf_adam_step wrote them)
+ *   ws_x [N, F] optional workspace: the forward stores the rows Feat[i] + eps it multiplied and the dW kernel
+ *        reads them back (L2-resident) instead of regenerating the noise; NULL: regenerated
+ *   ws_loss_terms [P/2] (BPR) or [P] (MSE) workspace;  save_h / save_w optional (NULL: not written)
+ * Needs dccf_train_fused_smem_bytes(S, A, loss_mode) <= 200 KB of shared memory per CTA (else use the two calls
+ * above). */
+int64_t dccf_train_fused_smem_bytes(int32_t n_samples, int32_t n_attr, int32_t loss_mode);
+int dccf_train_fwd_bwd_tc(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
+                          const float* W, const float* b, const dccf_expo* expo, const int64_t* X,
+                          const int64_t* sample_item, const float* Y, int64_t n_pairs, const dccf_rng* rng,
+                          int32_t loss_mode, float* out_pred, float* out_loss, float* ws_wimg,
+                          int32_t w_image_valid, float* ws_pre_part, float* ws_dpre, float* ws_x, float* ws_loss_terms,
+                          float* gW_part, float* gb_part, float* gu_rec, float* gi_rec, int32_t* rec_keys_u,
+                          int32_t* rec_keys_i, float* save_h, float* save_w, int32_t* err_flag, void* stream);
+
 /* ---- (c) part 2: l2 + clip + Adam, dense over every row --------------------------------- */
 /* Replaces model.l2()*l2 (BaseRunner.py:181, BaseModel.py:179-187), clip_grad_value_
  * (BaseRunner.py:185) and torch.optim.Adam(weight_decay=l2).step (BaseRunner.py:100,187):
@@ -242,6 +261,30 @@ typedef struct dccf_adam_tensor {
 } dccf_adam_tensor;
 int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
                    int32_t n_dense, const dccf_adam* hp, void* stream);
+/* The same optimizer step split around the backward pass: the rows a step does not touch (99 % of both
+ * embedding tables; their gradient is the l2 / weight-decay term only) are swept by dccf_adam_untouched on a
+ * second stream WHILE the forward and backward run; the touched rows, W and b follow the backward.
+ *   dccf_adam_link_ids      builds the record lists of the step from the ids alone (record p = user row of pair
+ *                           p, record p*Z + z = item row of slot z; out-of-range ids are clamped to row 0 exactly as
+ *                           the kernels that write the records do): afterwards head[row] >= 0 marks a touched row
+ *   dccf_adam_untouched     rows whose head is -1; at most 148 CTAs so that a tensor-core CTA fits beside each
+ *   dccf_adam_touched       the head record of each list updates its row (records summed in ascending index) and
+ *                           resets head to -1; dense tensors as in dccf_adam_step.  already_linked = 0: links the
+ *                           records first (dccf_adam_link_ids was not used).  w_image (optional): operand images
+ *                           of the UPDATED W [D, w_image_K] = dense[w_image_tensor] for the next step's
+ *                           dccf_train_fwd_bwd_tc(w_image_valid = 1); dccf_train_prep_w_image builds them from
+ *                           scratch.  cta_counter (optional, int32 zero on entry / exit): the last CTA to finish does
+ *                           advance_step_dev[0] += 1 and advance_offset_dev[0] += 1 (replaces dccf_state_advance in a
+ *                           captured step; every other reader of the counters must have completed).
+ * Every row is updated exactly once, with the arithmetic of dccf_adam_step. */
+int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const int64_t* sample_item, int64_t n_pairs,
+                       int32_t* head_user, int32_t* next_user, int32_t* head_item, int32_t* next_item, void* stream);
+int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam* hp, void* stream);
+int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
+                      int32_t n_dense, const dccf_adam* hp, int32_t already_linked, float* w_image,
+                      int32_t w_image_tensor, int32_t w_image_K, int32_t* cta_counter, int32_t* advance_step_dev,
+                      uint64_t* advance_offset_dev, void* stream);
+int dccf_train_prep_w_image(const float* W, int32_t feat_dim, float* w_image, void* stream);
 /* First node of a captured training step that reads its inputs from a device-resident epoch:
  * epoch_ptrs_dev = device array {address of X_epoch [n_batches,P,2], address of sample_epoch [n_batches,P,S]},
  * cursor_dev = device int64 batch counter (copied batch *cursor, then incremented). */
@@ -250,6 +293,15 @@ int dccf_stage_batch(const uint64_t* epoch_ptrs_dev, int64_t* cursor_dev, int64_
 /* step_dev[0] += 1 ; offset_dev[0] += offset_inc  (either pointer may be NULL) — the last node
  * of a captured training step, so that a replay sees t+1 and a fresh rng counter. */
 int dccf_state_advance(int32_t* step_dev, uint64_t* offset_dev, uint64_t offset_inc, void* stream);
+
+/* ---- debug ------------------------------------------------------------------------------- */
+/* Install (or remove, with NULL) a device buffer of 2 x 8 uint64 slots in which the kernels of the fused training
+ * step record {earliest CTA start, latest CTA end} in nanoseconds of %globaltimer: slot 0 k_link_ids,
+ * 1 k_adam_untouched, 2 k_train_fwd_tc, 3 k_train_mid, 4 k_train_bwd_tc, 5 k_adam_touched, 6 k_stage_batch.
+ * The caller initialises every slot to {UINT64_MAX, 0} (tools/step_timeline.py).  One entry point per
+ * translation unit that owns instrumented kernels. */
+int dccf_debug_timeline_train(unsigned long long* slots);
+int dccf_debug_timeline_adam(unsigned long long* slots);
 
 /* ---- (d): evaluation ranker -------------------------------------------------------------- */
 /* Replaces BaseModel.evaluate_method ranking branch (src/models/BaseModel.py:82-126) and

@@ -61,6 +61,30 @@ def run(path, t, X, si, F, S, A, rng, time_it=0):
         fwd = lambda: kernels.train_fwd_tc(dims, t['E_user'], t['E_item'], t['Feat'], t['W'], t['b'], expo, X, si, rng,
                                            pred, ws_rows, wimg, pre_part, save_h, save_w, None)
     gW_part, gb_part = torch.zeros(ns, D, K, **f32), torch.zeros(ns, D, **f32)
+    if path == 'fused':
+        terms = torch.zeros(P, **f32)
+        xs = torch.zeros(N, F, **f32)
+
+        def step():
+            kernels.train_fwd_bwd_tc(dims, t['E_user'], t['E_item'], t['Feat'], t['W'], t['b'], expo, X, si, None, rng, 0,
+                                     pred, loss, wimg, False, pre_part, dpre, xs, terms, gW_part, gb_part, gu, gi, ku, ki,
+                                     save_h, save_w, None)
+        step()
+        torch.cuda.synchronize()
+        out = {'pred': pred, 'ws_rows': None, 'save_h': save_h, 'save_w': save_w, 'loss': loss, 'gW': gW_part.sum(0),
+               'gb': gb_part.sum(0), 'gu': gu, 'gi': gi, 'ku': ku, 'ki': ki, 'splits': ns}
+        if time_it:
+            for _ in range(5):
+                step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(time_it):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            out['us_fwd'] = e0.elapsed_time(e1) * 1000.0 / time_it
+            out['us_bwd'] = 0.0
+        return out
     args = (dims, t['E_user'], t['E_item'], t['Feat'], t['W'], X, si, None, rng, 0, pred, save_h, save_w, loss, gW_part,
             gb_part, gu, gi, ku, ki)
     bwd = (lambda: kernels.bpr_bwd(*args)) if path == 'simt' else (lambda: kernels.train_bwd_tc(*args, dpre))
@@ -87,6 +111,8 @@ def compare(tag, a, b, tol):
     bad = []
     line = []
     for k in ('pred', 'ws_rows', 'save_h', 'save_w', 'loss', 'gW', 'gb', 'gu', 'gi'):
+        if a[k] is None or b[k] is None:
+            continue
         e = rel(b[k], a[k])
         line.append('%s %.2e' % (k, e))
         if not (e < tol.get(k, 2e-5)):
@@ -119,11 +145,13 @@ def main():
             a = run('simt', t, X, si, F, S, A, rng)
             b = run('tc', t, X, si, F, S, A, rng)
             ok &= compare('U%d I%d F%d P%d S%d A%d %s' % (U, I, F, P, S, A, mode), a, b, {})
+            c = run('fused', t, X, si, F, S, A, rng)
+            ok &= compare('    fused', a, c, {})
     if time_it:
         U, I, F, P, S, A = 48000, 16000, 768, 256, 10, 2
         t, X, si = problem(7, U, I, F, P, S, A)
         rng = kernels.make_rng(noise_std=0.1, p_drop=0.2, seed=2019, offset=3, generate_noise=True, generate_mask=True)
-        for path in ('simt', 'tc'):
+        for path in ('simt', 'tc', 'fused'):
             o = run(path, t, X, si, F, S, A, rng, time_it=time_it)
             print('timing %-5s fwd %.1f us  bwd %.1f us  (back to back, no L2 flush; fwd incl. W prep + epilogue; '
                   'splits %d)' % (path, o['us_fwd'], o['us_bwd'], o['splits']), flush=True)
