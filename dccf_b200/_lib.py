@@ -11,7 +11,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libdccf_b200.so')
-ABI_VERSION = 19
+ABI_VERSION = 21
 DIM = 64
 
 
@@ -90,7 +90,8 @@ _SIGNATURES = {
     'dccf_train_fused_smem_bytes': (ctypes.c_int64, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
     'dccf_train_fwd_bwd_tc': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, _P, _P, _P, ctypes.POINTER(Expo), _P, _P, _P,
                                              ctypes.c_int64, ctypes.POINTER(Rng), ctypes.c_int32, _P, _P, _P,
-                                             ctypes.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+                                             ctypes.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                             ctypes.c_int32, _P, _P]),
     'dccf_adam_sweep': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int64, _P, _P,
                                        ctypes.POINTER(Adam), _P]),
     'dccf_adam_sweep_seg': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int32, ctypes.c_int64,
@@ -100,7 +101,8 @@ _SIGNATURES = {
                                        ctypes.POINTER(Adam), _P]),
     'dccf_adam_step': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(AdamTensor),
                                       ctypes.c_int32, ctypes.POINTER(Adam), _P]),
-    'dccf_adam_link_ids': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, ctypes.c_int64, _P, _P, _P, _P, _P]),
+    'dccf_adam_link_ids': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, ctypes.c_int64, _P, _P, _P, _P,
+                                          ctypes.POINTER(Expo), _P, _P, _P]),
     'dccf_adam_untouched': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(Adam), _P]),
     'dccf_adam_touched': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(AdamTensor),
                                          ctypes.c_int32, ctypes.POINTER(Adam), ctypes.c_int32, _P, ctypes.c_int32,

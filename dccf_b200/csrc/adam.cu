@@ -9,7 +9,10 @@
 // update is a full streaming sweep (24 B/param: read p,m,v, write p,m,v).  The sparse part of the
 // gradient arrives as records (row id + 64 floats) linked per row through head/next; records of one
 // row are summed in ascending record order so the result does not depend on atomics timing.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "backdoor.cuh"
 
 namespace dccf {
 
@@ -344,29 +347,54 @@ __global__ void __launch_bounds__(256, 4) k_adam_all(const AdamAllArgs a) {
 //                    (records summed in ascending index as always); + W, b; the last CTA advances the step counters
 // Every row is updated exactly once per step and with the same arithmetic as k_adam_all.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_link_ids(const int64_t* __restrict__ X, const int64_t* __restrict__ sample_item,
-                                                  int64_t n_pairs, int32_t S, int32_t user_base, int32_t n_users,
-                                                  int32_t n_items, int32_t* __restrict__ head_u, int32_t* __restrict__ next_u,
-                                                  int32_t* __restrict__ head_i, int32_t* __restrict__ next_i) {
-    const int Z = S + 1;
+struct LinkIdsArgs {
+    const int64_t* X;
+    const int64_t* sample_item;
+    int64_t n_pairs;
+    int32_t S, A, user_base, n_users, n_items;
+    int32_t* head_u;
+    int32_t* next_u;
+    int32_t* head_i;
+    int32_t* next_i;
+    int32_t link_blocks;     // blocks [0, link_blocks) link; the rest evaluate the exposure softmax (warp per pair)
+    dccf_expo ex;
+    float* expo_e;           // [P, Z]
+    float* expo_den;         // [P]
+};
+
+__global__ void __launch_bounds__(256) k_link_ids(const LinkIdsArgs a) {
     tl_begin(0);
-    tl_end(0);      // (a single short wave: start and end of the kernel are indistinguishable at this resolution)
+    tl_end(0);      // (short single wave: start and end are indistinguishable at the timer's resolution)
+    if ((int)blockIdx.x >= a.link_blocks) {
+        // exposure softmax of every pair: depends on the ids only, so it is taken off the critical path here
+        const int64_t p = (int64_t)((int)blockIdx.x - a.link_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        if (p >= a.n_pairs) return;   // warp-uniform
+        backdoor_weights(a.ex, a.X, a.sample_item, p, threadIdx.x & 31, a.n_users, a.user_base, a.n_items, a.S, a.A,
+                         a.expo_e + p * (a.S + 1), a.expo_den + p, nullptr);
+        return;
+    }
+    const int Z = a.S + 1;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pairs * (Z + 1)) return;
+    if (i >= a.n_pairs * (Z + 1)) return;
     const int64_t p = i / (Z + 1);
     const int slot = (int)(i - p * (Z + 1));   // 0 = the user record of pair p, 1 + z = its item record of slot z
     if (slot == 0) {
-        const int32_t u = checked_id(X[2 * p] - user_base, n_users, nullptr);
-        next_u[p] = atomicExch(&head_u[u], (int32_t)p);
+        const int32_t u = checked_id(a.X[2 * p] - a.user_base, a.n_users, nullptr);
+        a.next_u[p] = atomicExch(&a.head_u[u], (int32_t)p);
     } else {
         const int z = slot - 1;
-        const int32_t it = checked_id(slot_item(X, sample_item, p, z, S), n_items, nullptr);
+        const int32_t it = checked_id(slot_item(a.X, a.sample_item, p, z, a.S), a.n_items, nullptr);
         const int32_t r = (int32_t)(p * Z + z);
-        next_i[r] = atomicExch(&head_i[it], r);
+        a.next_i[r] = atomicExch(&a.head_i[it], r);
     }
 }
 
 constexpr int ADAM_SIDE_SMEM = 120 * 1024;
+
+// L2-only loads / stores: the sweep streams 100 MB past SMs whose L1 holds the feature rows of the concurrent
+// forward — it must not evict them
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stcg4(float* p, const float4& v) { __stcg(reinterpret_cast<float4*>(p), v); }
 
 __global__ void __launch_bounds__(256, 1) k_adam_untouched(const AdamAllArgs a) {
     tl_begin(1);
@@ -378,7 +406,7 @@ __global__ void __launch_bounds__(256, 1) k_adam_untouched(const AdamAllArgs a) 
         if (b < 0 || b >= t.block_n) continue;
         const int sub = threadIdx.x & 15;
         const int half = (threadIdx.x >> 4) & 1;
-        const int64_t warp = ((int64_t)b * blockDim.x + threadIdx.x) >> 5;
+        const int64_t warp = ((int64_t)b * blockDim.x + threadIdx.x) >> 5;   // (block size: see dccf_adam_untouched)
         const int64_t n_warps = ((int64_t)t.block_n * blockDim.x) >> 5;
         for (int64_t w = warp; 4 * w < t.n_rows; w += n_warps) {
             const int64_t r0 = 4 * w + half, r1 = r0 + 2;
@@ -386,17 +414,17 @@ __global__ void __launch_bounds__(256, 1) k_adam_untouched(const AdamAllArgs a) 
             const bool v1 = r1 < t.n_rows && t.head[r1] == -1;
             const size_t o0 = (size_t)(v0 ? r0 : 0) * D + sub * 4, o1 = (size_t)(v1 ? r1 : 0) * D + sub * 4;
             float4 p0, m0, q0, p1, m1, q1;
-            if (v0) { p0 = ld4(t.table + o0); m0 = ld4(t.m + o0); q0 = ld4(t.v + o0); }
-            if (v1) { p1 = ld4(t.table + o1); m1 = ld4(t.m + o1); q1 = ld4(t.v + o1); }
+            if (v0) { p0 = ldcg4(t.table + o0); m0 = ldcg4(t.m + o0); q0 = ldcg4(t.v + o0); }
+            if (v1) { p1 = ldcg4(t.table + o1); m1 = ldcg4(t.m + o1); q1 = ldcg4(t.v + o1); }
             if (v0) {
                 adam_elem(p0.x, m0.x, q0.x, 0.f, s); adam_elem(p0.y, m0.y, q0.y, 0.f, s);
                 adam_elem(p0.z, m0.z, q0.z, 0.f, s); adam_elem(p0.w, m0.w, q0.w, 0.f, s);
-                st4(t.table + o0, p0); st4(t.m + o0, m0); st4(t.v + o0, q0);
+                stcg4(t.table + o0, p0); stcg4(t.m + o0, m0); stcg4(t.v + o0, q0);
             }
             if (v1) {
                 adam_elem(p1.x, m1.x, q1.x, 0.f, s); adam_elem(p1.y, m1.y, q1.y, 0.f, s);
                 adam_elem(p1.z, m1.z, q1.z, 0.f, s); adam_elem(p1.w, m1.w, q1.w, 0.f, s);
-                st4(t.table + o1, p1); st4(t.m + o1, m1); st4(t.v + o1, q1);
+                stcg4(t.table + o1, p1); stcg4(t.m + o1, m1); stcg4(t.v + o1, q1);
             }
         }
         __syncthreads();
@@ -507,16 +535,40 @@ __global__ void k_state_advance(int32_t* step_dev, uint64_t* offset_dev, uint64_
 // Copy batch number *cursor of a device-resident epoch ([n_batches, P, 2] ids and [n_batches, P, S] confounder
 // draws, base addresses read from device memory) into the step graph's static input buffers, then advance
 // the cursor: a replayed graph walks through the epoch without any host-side copy.
-__global__ void __launch_bounds__(256) k_stage_batch(const uint64_t* __restrict__ epoch_ptrs, int64_t* cursor,
-                                                     int64_t n_x, int64_t n_s, int64_t* __restrict__ X_out,
-                                                     int64_t* __restrict__ si_out) {
+__global__ void __launch_bounds__(1024) k_stage_batch(const uint64_t* __restrict__ epoch_ptrs, int64_t* cursor,
+                                                      int64_t n_x, int64_t n_s, int64_t* __restrict__ X_out,
+                                                      int64_t* __restrict__ si_out) {
     tl_begin(6);
     tl_end(6);
     const int64_t b = *cursor;
     const int64_t* X_src = reinterpret_cast<const int64_t*>(epoch_ptrs[0]) + b * n_x;
     const int64_t* s_src = reinterpret_cast<const int64_t*>(epoch_ptrs[1]) + b * n_s;
-    for (int64_t i = threadIdx.x; i < n_x; i += blockDim.x) X_out[i] = X_src[i];
-    for (int64_t i = threadIdx.x; i < n_s; i += blockDim.x) si_out[i] = s_src[i];
+    // 16-byte copies when the batch slices are 16-byte aligned (they are: n_x and n_s are even), all loads of a
+    // thread issued before its first store
+    const int64_t n2x = n_x >> 1, n2s = n_s >> 1;
+    const longlong2* X2 = reinterpret_cast<const longlong2*>(X_src);
+    const longlong2* S2 = reinterpret_cast<const longlong2*>(s_src);
+    if (((n_x | n_s) & 1) == 0 && (reinterpret_cast<uintptr_t>(X_src) & 15) == 0 && (reinterpret_cast<uintptr_t>(s_src) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(X_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(si_out) & 15) == 0) {
+        for (int64_t i0 = 0; i0 < n2x + n2s; i0 += 4 * blockDim.x) {
+            longlong2 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t i = i0 + q * blockDim.x + threadIdx.x;
+                if (i < n2x) v[q] = X2[i];
+                else if (i < n2x + n2s) v[q] = S2[i - n2x];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t i = i0 + q * blockDim.x + threadIdx.x;
+                if (i < n2x) reinterpret_cast<longlong2*>(X_out)[i] = v[q];
+                else if (i < n2x + n2s) reinterpret_cast<longlong2*>(si_out)[i - n2x] = v[q];
+            }
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < n_x; i += blockDim.x) X_out[i] = X_src[i];
+        for (int64_t i = threadIdx.x; i < n_s; i += blockDim.x) si_out[i] = s_src[i];
+    }
     __syncthreads();
     if (threadIdx.x == 0) *cursor = b + 1;
 }
@@ -699,15 +751,27 @@ extern "C" int dccf_debug_timeline_adam(unsigned long long* slots) {
 
 extern "C" int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const int64_t* sample_item, int64_t n_pairs,
                                   int32_t* head_user, int32_t* next_user, int32_t* head_item, int32_t* next_item,
-                                  void* stream_) {
+                                  const dccf_expo* expo, float* expo_e, float* expo_den, void* stream_) {
     DCCF_CHECK_ARG(dims && X && head_user && next_user && head_item && next_item, "dccf_adam_link_ids: null argument");
     DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item, "dccf_adam_link_ids: sample_item is null");
     DCCF_CHECK_ARG(n_pairs * (dims->n_samples + 1) < ((int64_t)1 << 31), "dccf_adam_link_ids: too many records");
+    DCCF_CHECK_ARG(expo == nullptr || (expo_e && expo_den), "dccf_adam_link_ids: expo needs expo_e and expo_den");
     if (n_pairs <= 0) return DCCF_OK;
+    LinkIdsArgs a;
+    a.X = X; a.sample_item = sample_item; a.n_pairs = n_pairs; a.S = dims->n_samples; a.A = dims->n_attr;
+    a.user_base = dims->user_base; a.n_users = dims->n_users; a.n_items = dims->n_items;
+    a.head_u = head_user; a.next_u = next_user; a.head_i = head_item; a.next_i = next_item;
     const int64_t n = n_pairs * (dims->n_samples + 2);
-    k_link_ids<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
-        X, sample_item, n_pairs, dims->n_samples, dims->user_base, dims->n_users, dims->n_items, head_user, next_user,
-        head_item, next_item);
+    a.link_blocks = (int32_t)((n + 255) / 256);
+    int64_t blocks = a.link_blocks;
+    a.expo_e = expo_e; a.expo_den = expo_den;
+    if (expo != nullptr) {
+        a.ex = *expo;
+        blocks += (n_pairs + 7) / 8;
+    } else {
+        a.ex.mode = 0; a.ex.dense = nullptr;
+    }
+    k_link_ids<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(a);
     DCCF_CHECK_LAUNCH("k_link_ids");
     return DCCF_OK;
 }
@@ -732,13 +796,28 @@ extern "C" int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tabl
         static bool attr_set = false;
         if (!attr_set) {
             cudaError_t e = cudaFuncSetAttribute(k_adam_untouched, cudaFuncAttributeMaxDynamicSharedMemorySize, ADAM_SIDE_SMEM);
+            if (e == cudaSuccess && getenv("DCCF_NO_CARVEOUT") == nullptr) e = cudaFuncSetAttribute(k_adam_untouched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) {
                 set_error("dccf_adam_untouched: cannot opt in to %d bytes of shared memory: %s", ADAM_SIDE_SMEM, cudaGetErrorString(e));
                 return DCCF_ERR_CUDA;
             }
             attr_set = true;
         }
-        k_adam_untouched<<<(unsigned)blocks, 256, ADAM_SIDE_SMEM, (cudaStream_t)stream_>>>(a);
+        // 256 threads per CTA unless DCCF_SIDE_THREADS says otherwise (tuning knob: fewer threads = less L2 pressure on
+        // the concurrent forward, longer sweep)
+        static int side_threads = 0;
+        if (side_threads == 0) {
+            const char* v = getenv("DCCF_SIDE_THREADS");
+            side_threads = (v != nullptr && atoi(v) >= 32 && atoi(v) <= 256) ? (atoi(v) / 32) * 32 : 256;
+        }
+        if (getenv("DCCF_DEBUG_SKIP_UNTOUCHED") != nullptr) return DCCF_OK;   // timing experiments only: wrong results
+        static int side_smem = -1;
+        if (side_smem < 0) {
+            const char* v = getenv("DCCF_SIDE_SMEM_KB");
+            side_smem = (v != nullptr && v[0] != '\0') ? atoi(v) * 1024 : ADAM_SIDE_SMEM;
+            if (side_smem > ADAM_SIDE_SMEM) side_smem = ADAM_SIDE_SMEM;
+        }
+        k_adam_untouched<<<(unsigned)blocks, side_threads, side_smem, (cudaStream_t)stream_>>>(a);
         DCCF_CHECK_LAUNCH("k_adam_untouched");
     }
     return DCCF_OK;
@@ -777,7 +856,7 @@ extern "C" int dccf_stage_batch(const uint64_t* epoch_ptrs_dev, int64_t* cursor_
     DCCF_CHECK_ARG(epoch_ptrs_dev && cursor_dev && X_out && (n_samples == 0 || sample_item_out), "dccf_stage_batch: null argument");
     DCCF_CHECK_ARG(n_pairs >= 0 && n_samples >= 0, "dccf_stage_batch: negative size");
     if (n_pairs == 0) return DCCF_OK;
-    k_stage_batch<<<1, 256, 0, (cudaStream_t)stream_>>>(epoch_ptrs_dev, cursor_dev, n_pairs * 2, n_pairs * n_samples, X_out,
+    k_stage_batch<<<1, 1024, 0, (cudaStream_t)stream_>>>(epoch_ptrs_dev, cursor_dev, n_pairs * 2, n_pairs * n_samples, X_out,
                                                          sample_item_out);
     DCCF_CHECK_LAUNCH("k_stage_batch");
     return DCCF_OK;

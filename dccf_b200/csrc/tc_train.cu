@@ -76,9 +76,9 @@ __device__ __forceinline__ void issue_stage_mmas(uint32_t stage_addr, uint32_t t
 
 // accumulator columns [16*quarter, 16*quarter + 16) of this thread's TMEM lane: three main accumulators,
 // then the small correction terms, added in round-to-nearest FP32
-__device__ __forceinline__ void load_acc_quarter(uint32_t tmem_base, int warp, int quarter, float (&acc)[16]) {
+__device__ __forceinline__ void load_acc_quarter(uint32_t tmem_base, int lane_quarter, int quarter, float (&acc)[16]) {
     float part[16];
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(quarter * 16);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_quarter * 32) << 16) + (uint32_t)(quarter * 16);
     tc::tmem_ld_32x16(lane_addr + 1 * D, acc);
     tc::tmem_ld_32x16(lane_addr + 2 * D, part);
 #pragma unroll
@@ -121,11 +121,23 @@ __global__ void __launch_bounds__(TC_NT, 2) k_train_fwd_tc(const TrainFwdParams 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     tl_begin(2);
+    tl_end(7);        // slot 7, "end" field: the LATEST CTA start of this kernel
     const int64_t row_base = (int64_t)blockIdx.x * TC_BM;
     const int ks = (int)blockIdx.y, n_ks = (int)gridDim.y;
     const int c_lo = (int)(((int64_t)ks * prm.n_chunks) / n_ks);
     const int c_hi = (int)(((int64_t)(ks + 1) * prm.n_chunks) / n_ks);
     const int n_local = c_hi - c_lo;
+
+    // producers: thread = (row, quarter of the 32-wide K chunk); the id lookups overlap the barrier / TMEM set-up
+    const int row = tid & (TC_BM - 1), kq = (tid >> 7) & 3;
+    const int64_t grow = min(row_base + row, prm.n_rows - 1);
+    int32_t fi = 0, it = 0;
+    if (warp < TC_PRODUCERS / 32) {
+        const uint32_t p = (uint32_t)grow / (uint32_t)prm.R;
+        const int z = (int)((uint32_t)grow - p * (uint32_t)prm.R) / prm.A;
+        fi = checked_id(prm.X[2 * (int64_t)p + 1], prm.n_items, prm.err_flag);
+        it = (z == 0) ? fi : checked_id(prm.sample_item[(int64_t)p * prm.S + (z - 1)], prm.n_items, prm.err_flag);
+    }
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -142,13 +154,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_train_fwd_tc(const TrainFwdParams 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < TC_PRODUCERS / 32) {
-        // ===== producers: thread = (row, quarter of the 32-wide K chunk) =====
-        const int row = tid & (TC_BM - 1), kq = tid >> 7;
-        const int64_t grow = min(row_base + row, prm.n_rows - 1);
-        const uint32_t p = (uint32_t)grow / (uint32_t)prm.R;
-        const int z = (int)((uint32_t)grow - p * (uint32_t)prm.R) / prm.A;
-        const int32_t fi = checked_id(prm.X[2 * (int64_t)p + 1], prm.n_items, prm.err_flag);
-        const int32_t it = (z == 0) ? fi : checked_id(prm.sample_item[(int64_t)p * prm.S + (z - 1)], prm.n_items, prm.err_flag);
+        // ===== producers =====
         const float* item_ptr = prm.E_item + (size_t)it * D + kq * 8;
         const float* feat_ptr = prm.Feat + (size_t)fi * prm.F + kq * 8;
         const float* nptr = (NOISE_MODE == 1) ? prm.noise + (size_t)grow * prm.F + kq * 8 : nullptr;
@@ -221,29 +227,25 @@ __global__ void __launch_bounds__(TC_NT, 2) k_train_fwd_tc(const TrainFwdParams 
         __syncwarp();
     }
 
-    // ===== epilogue: warps 0-3, thread = row = TMEM lane: the partial pre-activations of this K split =====
-    if (warp < 4) {
-        const int64_t grow = row_base + tid;
-        const bool valid = grow < prm.n_rows;
-        float* out = prm.pre_part + ((size_t)ks * (size_t)prm.n_rows + (size_t)(valid ? grow : 0)) * D;
+    // ===== epilogue: the 16 producer warps; warp w reads TMEM lanes 32*(w%4).. (the only ones it may touch) and
+    // columns 16*(w/4)..: one 16-column slice of 32 rows of the partial pre-activations of this K split =====
+    if (warp < TC_PRODUCERS / 32) {
+        const int lq = warp & 3, cq = warp >> 2;
+        const int64_t orow = row_base + lq * 32 + lane;
+        const bool valid = orow < prm.n_rows;
+        float* out = prm.pre_part + ((size_t)ks * (size_t)prm.n_rows + (size_t)(valid ? orow : 0)) * D + cq * 16;
+        float acc[16];
         if (n_local > 0) {
             tc::mbar_wait(accum_bar, 0u);
             tc::tc_fence_after_sync();
+            load_acc_quarter(tmem_base, lq, cq, acc);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
         }
-#pragma unroll 1
-        for (int quarter = 0; quarter < 4; ++quarter) {
-            float acc[16];
-            if (n_local > 0) {
-                load_acc_quarter(tmem_base, warp, quarter, acc);
-            } else {
+        if (valid) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-            }
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    st4(out + quarter * 16 + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
-            }
+            for (int j = 0; j < 16; j += 4) st4(out + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
         }
     }
 
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(128) k_train_fwd_finish(const TrainFinishParam
 // pair j and its negative j + b (src/models/DCCF.py:116-120), so d loss / d pred needs no second pass over
 // global memory and the activations h never leave shared memory.
 // =============================================================================================
-constexpr int TM_NT = 256;
+constexpr int TM_NT = 768;   // 48 half-warps: every phase below is a single pass at the reference shapes (2 x 22 rows)
 
 struct TrainMidParams {
     dccf_expo ex;
@@ -337,6 +339,8 @@ struct TrainMidParams {
     const float* Y;
     const float* mask;           // mode 1
     const float* pre_part;
+    const float* expo_e;         // optional [P, Z] + expo_den [P]: the exposure softmax of every pair, precomputed from
+    const float* expo_den;       // the ids on another stream (dccf_adam_link_ids); null: evaluated here
     float* out_pred;
     float* loss_terms;
     float* dpre_rows;
@@ -358,7 +362,9 @@ __host__ __device__ inline size_t train_mid_smem_floats(int R, int Z, int npc) {
     return (size_t)D * D + (size_t)npc * R * D + (size_t)npc * Z * D + (size_t)npc * R + (size_t)npc * Z + 8;
 }
 
-__global__ void __launch_bounds__(TM_NT) k_train_mid(const TrainMidParams prm) {
+// (no launch bound: the default 1024-thread bound caps the kernel at 64 registers, so that a 256-thread CTA of the
+// side-stream Adam sweep still fits beside its 768 threads)
+__global__ void k_train_mid(const TrainMidParams prm) {
     extern __shared__ __align__(16) float sm[];
     const int R = prm.R, Z = prm.Z, A = prm.A;
     const int npc = (prm.loss_mode == 0) ? 2 : 1;   // pairs per CTA
@@ -368,7 +374,6 @@ __global__ void __launch_bounds__(TM_NT) k_train_mid(const TrainMidParams prm) {
     float* score_s = dsum_s + (size_t)npc * Z * D;  // [npc*R]
     float* w_s = score_s + npc * R;                 // [npc*Z]  softmax exposure weights
     float* pred_s = w_s + npc * Z;                  // [2]
-    float* dpred_s = pred_s + 2;                    // [2]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     tl_begin(3);
@@ -379,9 +384,12 @@ __global__ void __launch_bounds__(TM_NT) k_train_mid(const TrainMidParams prm) {
     auto pair_of = [&](int q) { return q == 0 ? jt : p_second; };
     const uint32_t half_mask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;
 
-    for (int i = tid; i < D * D / 4; i += TM_NT) {
-        const int j = i / (D / 4), q4 = i % (D / 4);
-        st4(&Wi_s[j * D + q4 * 4], ldg4(prm.W + (size_t)j * prm.K + q4 * 4));
+    // W_i: loaded now, parked in registers, stored to shared memory after the first phase (only the last one reads it)
+    float4 wreg[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int i = tid + t * TM_NT;
+        if (i < D * D / 4) wreg[t] = ldg4(prm.W + (size_t)(i / (D / 4)) * prm.K + (i % (D / 4)) * 4);
     }
     const float4 bia = ldg4(prm.bias + sub * 4);
     // the user rows of the CTA's (at most two) pairs, columns 4*sub .. 4*sub+3
@@ -424,42 +432,52 @@ __global__ void __launch_bounds__(TM_NT) k_train_mid(const TrainMidParams prm) {
         for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(half_mask, dot, o);
         if (sub == 0) score_s[rr] = dot;
     }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int i = tid + t * TM_NT;
+        if (i < D * D / 4) st4(&Wi_s[(i / (D / 4)) * D + (i % (D / 4)) * 4], wreg[t]);
+    }
     __syncthreads();
 
-    // ---- B: backdoor-adjusted sum of each pair (one warp per pair), then the loss term and d loss / d pred ----
+    // ---- B: backdoor-adjusted sum of each pair (one warp per pair) ------------------------------------------
     if (warp < npc) {
         const int64_t p = pair_of(warp);
-        backdoor_pair(prm.ex, prm.X, prm.sample_item, p, lane, prm.n_users, prm.user_base, prm.n_items, prm.S, A,
-                      score_s + warp * R, pred_s + warp, w_s + warp * Z, prm.err_flag);
+        if (prm.expo_e != nullptr) {
+            backdoor_apply(prm.expo_e + p * Z, __ldg(prm.expo_den + p), lane, prm.S, A, score_s + warp * R, pred_s + warp,
+                           w_s + warp * Z);
+        } else {
+            backdoor_pair(prm.ex, prm.X, prm.sample_item, p, lane, prm.n_users, prm.user_base, prm.n_items, prm.S, A,
+                          score_s + warp * R, pred_s + warp, w_s + warp * Z, prm.err_flag);
+        }
         __syncwarp();
         if (lane == 0) prm.out_pred[p] = pred_s[warp];
         if (prm.save_w != nullptr)
             for (int z = lane; z < Z; z += 32) prm.save_w[p * Z + z] = w_s[warp * Z + z];
     }
     __syncthreads();
-    if (tid == 0) {
-        if (prm.loss_mode == 0) {
-            const float d = pred_s[0] - pred_s[1];
-            const float sg = 1.f / (1.f + expf(-d));
-            const float g = -(1.f - sg);
-            dpred_s[0] = g;
-            dpred_s[1] = -g;
-            // -log(sigmoid(d)) = softplus(-d), evaluated the stable way
-            prm.loss_terms[jt] = (d > 0.f) ? log1pf(expf(-d)) : (-d + log1pf(expf(d)));
-        } else {
-            const float d = pred_s[0] - __ldg(prm.Y + jt);
-            dpred_s[0] = 2.f * d / (float)prm.n_pairs;
-            prm.loss_terms[jt] = d * d;
-        }
+
+    // loss term and d loss / d pred of the CTA's pairs (every thread evaluates the two scalars it needs itself)
+    float dp0, dp1 = 0.f;
+    if (prm.loss_mode == 0) {
+        const float d = pred_s[0] - pred_s[1];
+        const float sg = 1.f / (1.f + expf(-d));
+        const float g = -(1.f - sg);
+        dp0 = g;
+        dp1 = -g;
+        // -log(sigmoid(d)) = softplus(-d), evaluated the stable way
+        if (tid == 0) prm.loss_terms[jt] = (d > 0.f) ? log1pf(expf(-d)) : (-d + log1pf(expf(d)));
+    } else {
+        const float d = pred_s[0] - __ldg(prm.Y + jt);
+        dp0 = 2.f * d / (float)prm.n_pairs;
+        if (tid == 0) prm.loss_terms[jt] = d * d;
     }
-    __syncthreads();
 
     // ---- C1: dpre rows (to global memory for the dW kernel) and their sum over the attribute copies ---------
     for (int qz = hw; qz < npc * Z; qz += TM_NT / 16) {
         const int q = qz / Z, z = qz - q * Z;
         const int64_t p = pair_of(q);
         const float4 e = q == 0 ? eu0 : eu1;
-        const float ds = dpred_s[q] * w_s[qz] * prm.inv_A;
+        const float ds = (q == 0 ? dp0 : dp1) * w_s[qz] * prm.inv_A;
         float4 dsum = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int a = 0; a < A; ++a) {
             const int l = z * A + a;
@@ -479,13 +497,16 @@ __global__ void __launch_bounds__(TM_NT) k_train_mid(const TrainMidParams prm) {
         }
         st4(dsum_s + (size_t)qz * D + sub * 4, dsum);
     }
-    // user-row record: gu[c] = sum_{z,a} ds * h[.,c], rows in ascending order (thread = column)
-    if (tid < npc * D) {
-        const int q = tid >> 6, c = tid & (D - 1);
+    // user-row record: gu[c] = sum_{z,a} ds * h[.,c], rows in ascending order (thread = column; the warps at the
+    // top of the CTA, which have no C1 work at the reference shapes)
+    if (tid >= TM_NT - npc * D) {
+        const int t2 = tid - (TM_NT - npc * D);
+        const int q = t2 >> 6, c = t2 & (D - 1);
         const int64_t p = pair_of(q);
+        const float dpq = q == 0 ? dp0 : dp1;
         float gu = 0.f;
         for (int l = 0; l < R; ++l) {
-            const float ds = dpred_s[q] * w_s[q * Z + l / A] * prm.inv_A;
+            const float ds = dpq * w_s[q * Z + l / A] * prm.inv_A;
             gu = fmaf(ds, h_s[(size_t)(q * R + l) * D + c], gu);
         }
         prm.gu_rec[(size_t)p * D + c] = gu;
@@ -713,32 +734,29 @@ __global__ void __launch_bounds__(TB_NT, 2) k_train_bwd_tc(const TrainBwdParams 
         __syncwarp();
     }
 
-    // ===== epilogue: warps 0-3, thread = TMEM lane = column m of the tile; lanes of a warp are 32 consecutive
-    // columns of gW, so every store below is one coalesced 128-byte line =====
-    if (warp < 4) {
-        const int col = mt * TC_BM + tid;
+    // ===== epilogue: the 16 producer warps; warp w owns TMEM lanes 32*(w%4).. = 32 consecutive columns m of the
+    // tile and the output channels 16*(w/4)..; lanes of a warp are consecutive columns of gW, so every store below
+    // is one coalesced 128-byte line =====
+    if (warp < TC_PRODUCERS / 32) {
+        const int lq = warp & 3, cq = warp >> 2;
+        const int col = mt * TC_BM + lq * 32 + lane;
+        float acc[16];
         if (n_st > 0) {
             tc::mbar_wait(accum_bar, 0u);
             tc::tc_fence_after_sync();
+            load_acc_quarter(tmem_base, lq, cq, acc);
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.f;
         }
         float* gw = prm.gW_part + (size_t)sp * D * prm.K;
         float* gb = prm.gb_part + (size_t)sp * D;
-#pragma unroll 1
-        for (int quarter = 0; quarter < 4; ++quarter) {
-            float acc[16];
-            if (n_st > 0) {
-                load_acc_quarter(tmem_base, warp, quarter, acc);
-            } else {
+        if (col < prm.K) {
 #pragma unroll
-                for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.f;
-            }
-            if (col < prm.K) {
+            for (int jj = 0; jj < 16; ++jj) gw[(size_t)(cq * 16 + jj) * prm.K + col] = acc[jj];
+        } else if (col == prm.K) {
 #pragma unroll
-                for (int jj = 0; jj < 16; ++jj) gw[(size_t)(quarter * 16 + jj) * prm.K + col] = acc[jj];
-            } else if (col == prm.K) {
-#pragma unroll
-                for (int jj = 0; jj < 16; ++jj) gb[quarter * 16 + jj] = acc[jj];
-            }
+            for (int jj = 0; jj < 16; ++jj) gb[cq * 16 + jj] = acc[jj];
         }
     }
 
@@ -788,6 +806,9 @@ static void bwd_geometry(int64_t n_rows, int K, int32_t* n_mtiles, int32_t* n_sp
 template <typename Kern>
 static int opt_in_smem(Kern k, const char* name) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    // always the largest shared-memory carveout: a CTA of the side-stream Adam sweep (120 KB) and a tensor-core CTA
+    // (96 KB) share an SM only if neither launch shrinks the carveout under the other
+    if (e == cudaSuccess && getenv("DCCF_NO_CARVEOUT") == nullptr) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) {
         set_error("%s: cannot opt in to %u bytes of shared memory: %s", name, TC_SMEM_BYTES, cudaGetErrorString(e));
         return DCCF_ERR_CUDA;
@@ -975,9 +996,12 @@ extern "C" int dccf_train_fwd_bwd_tc(const dccf_dims* dims, const float* E_user,
                                      int32_t loss_mode, float* out_pred, float* out_loss, float* ws_wimg,
                                      int32_t w_image_valid, float* ws_pre_part, float* ws_dpre, float* ws_x, float* ws_loss_terms,
                                      float* gW_part, float* gb_part, float* gu_rec, float* gi_rec, int32_t* rec_keys_u,
-                                     int32_t* rec_keys_i, float* save_h, float* save_w, int32_t* err_flag, void* stream_) {
+                                     int32_t* rec_keys_i, float* save_h, float* save_w, const float* expo_e,
+                                     const float* expo_den, int32_t phases, int32_t* err_flag, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = check_fwd_args("dccf_train_fwd_bwd_tc", dims, expo, rng, sample_item, n_pairs);
+    DCCF_CHECK_ARG(phases >= 1 && phases <= 3, "dccf_train_fwd_bwd_tc: phases must be 1 (partial products), 2 (the rest) or 3 (both)");
+    DCCF_CHECK_ARG((expo_e == nullptr) == (expo_den == nullptr), "dccf_train_fwd_bwd_tc: expo_e and expo_den go together");
     if (rc != DCCF_OK) return rc;
     DCCF_CHECK_ARG(loss_mode == 0 || loss_mode == 1, "dccf_train_fwd_bwd_tc: loss_mode must be 0 (BPR) or 1 (MSE)");
     DCCF_CHECK_ARG(E_user && E_item && Feat && W && b && X && out_pred && out_loss && ws_wimg && ws_pre_part && ws_dpre &&
@@ -989,7 +1013,11 @@ extern "C" int dccf_train_fwd_bwd_tc(const dccf_dims* dims, const float* E_user,
     const int Z = dims->n_samples + 1, R = Z * dims->n_attr, K = D + dims->feat_dim;
     const size_t smem = train_mid_smem_floats(R, Z, loss_mode == 0 ? 2 : 1) * sizeof(float);
     DCCF_CHECK_ARG(smem <= 200 * 1024, "dccf_train_fwd_bwd_tc: S=%d A=%d need %zu bytes of shared memory per CTA; use dccf_train_fwd_tc + dccf_train_bwd_tc", dims->n_samples, dims->n_attr, smem);
-    static size_t smem_opted = 48 * 1024;
+    static size_t smem_opted = 0;
+    if (smem_opted == 0) {
+        if (getenv("DCCF_NO_CARVEOUT") == nullptr) cudaFuncSetAttribute(k_train_mid, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        smem_opted = 48 * 1024;
+    }
     if (smem > smem_opted) {
         cudaError_t e = cudaFuncSetAttribute(k_train_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
@@ -998,14 +1026,18 @@ extern "C" int dccf_train_fwd_bwd_tc(const dccf_dims* dims, const float* E_user,
         }
         smem_opted = smem;
     }
-    int32_t n_ks = 1;
-    rc = launch_fwd_tc(dims, E_item, Feat, W, X, sample_item, n_pairs, rng, ws_wimg, w_image_valid != 0, ws_pre_part, ws_x,
-                       err_flag, &n_ks, stream);
-    if (rc != DCCF_OK) return rc;
+    int32_t n_ks = fwd_ksplits_for(n_pairs * R, K / TC_KC);
+    if (phases & 1) {
+        rc = launch_fwd_tc(dims, E_item, Feat, W, X, sample_item, n_pairs, rng, ws_wimg, w_image_valid != 0, ws_pre_part, ws_x,
+                           err_flag, &n_ks, stream);
+        if (rc != DCCF_OK) return rc;
+    }
+    if (!(phases & 2)) return DCCF_OK;
 
     TrainMidParams mid;
     mid.ex = *expo; mid.E_user = E_user; mid.W = W; mid.bias = b; mid.X = X; mid.sample_item = sample_item; mid.Y = Y;
-    mid.mask = rng->mask; mid.pre_part = ws_pre_part; mid.out_pred = out_pred; mid.loss_terms = ws_loss_terms;
+    mid.mask = rng->mask; mid.pre_part = ws_pre_part; mid.expo_e = expo_e; mid.expo_den = expo_den;
+    mid.out_pred = out_pred; mid.loss_terms = ws_loss_terms;
     mid.dpre_rows = ws_dpre; mid.gu_rec = gu_rec; mid.gi_rec = gi_rec; mid.rec_keys_u = rec_keys_u; mid.rec_keys_i = rec_keys_i;
     mid.save_h = save_h; mid.save_w = save_w; mid.err_flag = err_flag; mid.n_pairs = n_pairs; mid.n_rows = n_pairs * R;
     mid.n_users = dims->n_users; mid.user_base = dims->user_base; mid.n_items = dims->n_items; mid.S = dims->n_samples;

@@ -189,7 +189,7 @@ def train_fused_supported(n_samples, n_attr, loss_mode):
 
 def train_fwd_bwd_tc(dims, E_user, E_item, Feat, W, b, expo, X, sample_item, Y, rng, loss_mode, out_pred, out_loss,
                      ws_wimg, w_image_valid, ws_pre_part, ws_dpre, ws_x, ws_loss_terms, gW_part, gb_part, gu_rec, gi_rec,
-                     rec_keys_u, rec_keys_i, save_h=None, save_w=None, err_flag=None):
+                     rec_keys_u, rec_keys_i, save_h=None, save_w=None, expo_e=None, expo_den=None, err_flag=None, phases=3):
     """Forward + BPR/MSE loss + backward of a training step: partial products, fused per-loss-term middle kernel,
     dW / db tiles (3 launches, 4 when the W operand images must be rebuilt)."""
     lib = _lib.load()
@@ -199,8 +199,10 @@ def train_fwd_bwd_tc(dims, E_user, E_item, Feat, W, b, expo, X, sample_item, Y, 
                                     int(loss_mode), ptr(out_pred), ptr(out_loss), ptr(ws_wimg), int(bool(w_image_valid)),
                                     ptr(ws_pre_part), ptr(ws_dpre), ptr(ws_x), ptr(ws_loss_terms), ptr(gW_part), ptr(gb_part),
                                     ptr(gu_rec), ptr(gi_rec), ptr(rec_keys_u), ptr(rec_keys_i), ptr(save_h), ptr(save_w),
-                                    ptr(err_flag), stream_ptr()), 'dccf_train_fwd_bwd_tc')
-    LAUNCHES[0] += (3 if w_image_valid else 4) if n_pairs > 0 else 0
+                                    ptr(expo_e), ptr(expo_den), int(phases), ptr(err_flag), stream_ptr()),
+          'dccf_train_fwd_bwd_tc')
+    if n_pairs > 0:
+        LAUNCHES[0] += ((1 if w_image_valid else 2) if phases & 1 else 0) + (2 if phases & 2 else 0)
 
 
 def adam_sweep(table, m, v, rec_keys, rec_grads, n_rec, head, nxt, hp):
@@ -264,11 +266,15 @@ def adam_step(tables, dense, hp):
     LAUNCHES[0] += 2 if any(t.n_seg * t.seg_len > 0 for t in tables) else 1
 
 
-def adam_link_ids(dims, X, sample_item, head_user, next_user, head_item, next_item):
-    """Record lists of the step from the ids alone (before any gradient exists)."""
+def adam_link_ids(dims, X, sample_item, head_user, next_user, head_item, next_item, expo=None, expo_e=None,
+                  expo_den=None):
+    """Record lists of the step from the ids alone (before any gradient exists); with `expo` also the exposure
+    softmax of every pair (expo_e [P, Z], expo_den [P])."""
     lib = _lib.load()
     check(lib.dccf_adam_link_ids(ctypes.byref(dims), ptr(X), ptr(sample_item), X.shape[0], ptr(head_user),
-                                 ptr(next_user), ptr(head_item), ptr(next_item), stream_ptr()), 'dccf_adam_link_ids')
+                                 ptr(next_user), ptr(head_item), ptr(next_item),
+                                 ctypes.byref(expo) if expo is not None else None, ptr(expo_e), ptr(expo_den),
+                                 stream_ptr()), 'dccf_adam_link_ids')
     LAUNCHES[0] += 1 if X.shape[0] > 0 else 0
 
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 19
+#define DCCF_ABI_VERSION 21
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -193,6 +193,9 @@ int dccf_train_bwd_tc(const dccf_dims* dims, const float* E_user, const float* E
  *   ws_x [N, F] optional workspace: the forward stores the rows Feat[i] + eps it multiplied and the dW kernel
  *        reads them back (L2-resident) instead of regenerating the noise; NULL: regenerated
  *   ws_loss_terms [P/2] (BPR) or [P] (MSE) workspace;  save_h / save_w optional (NULL: not written)
+ *   expo_e [P, Z] / expo_den [P] optional: the exposure softmax precomputed by dccf_adam_link_ids
+ *   phases: 3 = everything; 1 = only the partial products, 2 = only the rest (same arguments both times) — lets
+ *        the caller wait for another stream (the one that produced expo_e) between the two
  * Needs dccf_train_fused_smem_bytes(S, A, loss_mode) <= 200 KB of shared memory per CTA (else use the two calls
  * above). */
 int64_t dccf_train_fused_smem_bytes(int32_t n_samples, int32_t n_attr, int32_t loss_mode);
@@ -202,7 +205,8 @@ int dccf_train_fwd_bwd_tc(const dccf_dims* dims, const float* E_user, const floa
                           int32_t loss_mode, float* out_pred, float* out_loss, float* ws_wimg,
                           int32_t w_image_valid, float* ws_pre_part, float* ws_dpre, float* ws_x, float* ws_loss_terms,
                           float* gW_part, float* gb_part, float* gu_rec, float* gi_rec, int32_t* rec_keys_u,
-                          int32_t* rec_keys_i, float* save_h, float* save_w, int32_t* err_flag, void* stream);
+                          int32_t* rec_keys_i, float* save_h, float* save_w, const float* expo_e,
+                          const float* expo_den, int32_t phases, int32_t* err_flag, void* stream);
 
 /* ---- (c) part 2: l2 + clip + Adam, dense over every row --------------------------------- */
 /* Replaces model.l2()*l2 (BaseRunner.py:181, BaseModel.py:179-187), clip_grad_value_
@@ -267,6 +271,9 @@ int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, const dccf_a
  *   dccf_adam_link_ids      builds the record lists of the step from the ids alone (record p = user row of pair
  *                           p, record p*Z + z = item row of slot z; out-of-range ids are clamped to row 0 exactly as
  *                           the kernels that write the records do): afterwards head[row] >= 0 marks a touched row
+ *                           expo (optional): the same launch also evaluates the exposure softmax of every pair
+ *                           (src/models/DCCF.py:98, a function of the ids only): expo_e [P, Z] = exp(expo - max),
+ *                           expo_den [P] = A * sum_z, consumed by dccf_train_fwd_bwd_tc
  *   dccf_adam_untouched     rows whose head is -1; at most 148 CTAs so that a tensor-core CTA fits beside each
  *   dccf_adam_touched       the head record of each list updates its row (records summed in ascending index) and
  *                           resets head to -1; dense tensors as in dccf_adam_step.  already_linked = 0: links the
@@ -278,7 +285,8 @@ int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, const dccf_a
  *                           captured step; every other reader of the counters must have completed).
  * Every row is updated exactly once, with the arithmetic of dccf_adam_step. */
 int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const int64_t* sample_item, int64_t n_pairs,
-                       int32_t* head_user, int32_t* next_user, int32_t* head_item, int32_t* next_item, void* stream);
+                       int32_t* head_user, int32_t* next_user, int32_t* head_item, int32_t* next_item,
+                       const dccf_expo* expo, float* expo_e, float* expo_den, void* stream);
 int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam* hp, void* stream);
 int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
                       int32_t n_dense, const dccf_adam* hp, int32_t already_linked, float* w_image,
