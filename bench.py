@@ -41,6 +41,11 @@ LR, L2, DROPOUT, STD = 1e-3, 1e-4, 0.2, 0.1
 SEED = 2019
 
 # algorithmic work per scored pair
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the step's kernels at the electronics shape, from ONE
+# `ncu --set full --clock-control none` capture (cold cache before every kernel), see profiles/
+NCU_TRAFFIC_SOURCE = 'profiles/r1e_ncu_full_train_summary.csv (ncu --set full, per launch, cold cache)'
+NCU_TRAFFIC_BYTES = {'k_train_fwd_tc': 1.89e6, 'k_train_mid': 4.47e6, 'k_train_bwd_tc': 2.92e6, 'k_adam_touched': 7.91e6,
+                     'k_adam_untouched': 47.35e6 + 0.81e6}
 FLOP_FWD_PAIR = R * (2 * (D + F) * D + 4 * D)
 FLOP_BWD_PAIR = R * (2 * (D + F) * D + 2 * D * D + 2 * D)
 BYTES_PAIR = 16 + 4 * D + 4 * D * Z + 4 * F + 4 * Z
@@ -242,19 +247,40 @@ def bench_train(model, X_all, steps, warmup, world, flush):
     barrier(world)
     b2b_ms = dist_max(e0.elapsed_time(e1) / max(1, n_b2b), world)
 
-    # ---- stage breakdown: the same step launched kernel by kernel with events between the stages ------
-    n_s = min(n, warmup + 50)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_s)]
-    stage_ms = np.zeros(3)
-    for i in range(n_s):
-        flush()
-        fd = {'X': X_dev[i], 'Y': Y, 'rank': 1, 'train': True, 'dropout': DROPOUT, 'sample_item': si_dev[i]}
-        model.train_step(fd, stage_events=evs[i])
-    barrier(world)
-    for i in range(warmup, n_s):
-        for st in range(3):
-            stage_ms[st] += evs[i][st].elapsed_time(evs[i][st + 1])
-    stage_ms /= max(1, n_s - warmup)
+    # ---- per-kernel times of the SAME captured step (extra replays of the same graph, L2 flushed before each
+    # measured step exactly as in the timed loop): the kernels' own CTAs stamp %globaltimer at start / end
+    # (dccf_b200/debug.py) — CUDA events cannot bracket the nodes of a graph.  Data-parallel runs (a different,
+    # unfused step) fall back to CUDA events between the stages of a kernel-by-kernel step. --------------------
+    kernels_us, timeline_step_us, stage_ms = {}, 0.0, None
+    if world == 1 and model._split_step_ok(0):
+        from dccf_b200.debug import StepTimeline
+        n_t = 30
+        torch.manual_seed(SEED + 15)
+        si_t = torch.randint(I, size=(3 * n_t, 2 * BATCH, S)).to(dev)
+        X_t = X_dev[torch.arange(3 * n_t, device=dev) % n].contiguous()
+        step3 = model.begin_resident_epoch(X_t, si_t, DROPOUT)
+        with StepTimeline(dev) as tl:
+            while step3.remaining() >= 3:
+                step3()
+                step3()                 # no host synchronisation before the measured step: it starts on a busy GPU
+                flush()
+                tl.arm()
+                step3()
+                tl.collect()
+            kernels_us, timeline_step_us = tl.summary()
+    else:
+        n_s = min(n, warmup + 50)
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_s)]
+        stage_ms = np.zeros(3)
+        for i in range(n_s):
+            flush()
+            fd = {'X': X_dev[i], 'Y': Y, 'rank': 1, 'train': True, 'dropout': DROPOUT, 'sample_item': si_dev[i]}
+            model.train_step(fd, stage_events=evs[i])
+        barrier(world)
+        for i in range(warmup, n_s):
+            for st in range(3):
+                stage_ms[st] += evs[i][st].elapsed_time(evs[i][st + 1])
+        stage_ms /= max(1, n_s - warmup)
 
     # ---- e2e: public API from pinned host memory, loss read back every step ---------------------
     X_pin = torch.from_numpy(X_all[:n]).pin_memory()
@@ -278,7 +304,8 @@ def bench_train(model, X_all, steps, warmup, world, flush):
             e2e_s += t1 - t0
     assert np.isfinite(loss)
     e2e_s = dist_max(e2e_s, world)
-    return {'total_ms': total_ms, 'stage_ms': stage_ms, 'launches': launches, 'e2e_s': e2e_s, 'b2b_ms': b2b_ms,
+    return {'total_ms': total_ms, 'stage_ms': stage_ms, 'kernels_us': kernels_us, 'timeline_step_us': timeline_step_us,
+            'launches': launches, 'e2e_s': e2e_s, 'b2b_ms': b2b_ms,
             'h2d': 2 * BATCH * 2 * 8 + 2 * BATCH * S * 8, 'd2h': 4, 'last_loss': loss}
 
 
@@ -469,25 +496,83 @@ def main():
     value = world * BATCH * args.steps / (tr['total_ms'] / 1e3)
     e2e_value = world * BATCH * args.steps / tr['e2e_s']
     n_params = (U + I) * D + D * (D + F) + D
-    stage = tr['stage_ms']                                   # fwd, bwd, adam  (ms per step)
     pairs = 2 * BATCH
-    stages = {
-        'score_fwd': {'ms': float(stage[0]), 'gflop': pairs * FLOP_FWD_PAIR / 1e9, 'mbytes': pairs * BYTES_PAIR / 1e6},
-        'bpr_bwd': {'ms': float(stage[1]), 'gflop': pairs * FLOP_BWD_PAIR / 1e9,
-                    'mbytes': pairs * (BYTES_PAIR + 4 * D * (1 + Z)) / 1e6},
-        'adam_sweep': {'ms': float(stage[2]), 'gflop': 0.0, 'mbytes': 24.0 * n_params / 1e6},
-    }
-    for s in stages.values():
-        s['gbs'] = s['mbytes'] / 1e3 / (s['ms'] / 1e3) if s['ms'] > 0 else 0.0
-        s['tflops'] = s['gflop'] / 1e3 / (s['ms'] / 1e3) if s['ms'] > 0 else 0.0
-    dom = max(stages, key=lambda k: stages[k]['ms'])
-    roof = {'kernel': dom, 'bound': 'hbm', 'achieved': stages[dom]['gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
-            'frac': stages[dom]['gbs'] / hbm_peak, 'traffic': None, 'peak_source': peak_src,
-            'fp32_simt': {'achieved': stages[dom]['tflops'], 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s',
-                          'frac': stages[dom]['tflops'] / FP32_PEAK_TFLOPS},
-            'stages_note': 'per-stage CUDA events of the same step launched kernel by kernel (includes launch gaps; the '
-                           'timed value replays the step as one CUDA graph)',
-            'stages': stages}
+    n_rows = pairs * R
+    if tr['kernels_us']:
+        # per-kernel roofline of the captured step.  Algorithmic work: forward 2.349 MFLOP and backward
+        # 2.526 MFLOP per pair; the two contractions are issued as 3 TF32 products each (error-compensated) on the
+        # tensor cores; the sweep streams 24 B per parameter.
+        ku = tr['kernels_us']
+        n_touched = pairs * (1 + Z)                      # upper bound of the rows the step touches
+        work = {
+            'k_train_fwd_tc': {'tensor_gflop': 3 * 2.0 * n_rows * (D + F) * D / 1e9, 'gflop': pairs * FLOP_FWD_PAIR / 1e9,
+                               'mbytes': pairs * BYTES_PAIR / 1e6},
+            'k_train_bwd_tc': {'tensor_gflop': 3 * 2.0 * n_rows * (D + F + 1) * D / 1e9, 'gflop': pairs * FLOP_BWD_PAIR / 1e9,
+                               'mbytes': (pairs * BYTES_PAIR + 4.0 * n_rows * D) / 1e6},
+            'k_adam_untouched': {'mbytes': 24.0 * ((U + I) * D - n_touched * D) / 1e6},
+            'k_adam_touched': {'mbytes': 24.0 * (n_touched * D + D * (D + F) + D) / 1e6},
+            'k_train_mid': {'mbytes': (4.0 * 3 * n_rows * D + 4.0 * n_rows * D) / 1e6},
+        }
+        kernels_obj = {}
+        for name, k in ku.items():
+            o = {'us': k['us'], 'start_us': k['start_us'], 'end_us': k['end_us']}
+            w = work.get(name, {})
+            if 'mbytes' in w:
+                o['mbytes'] = w['mbytes']
+                o['gbs'] = w['mbytes'] / 1e3 / (k['us'] / 1e6) if k['us'] > 0 else 0.0
+            if 'gflop' in w:
+                o['gflop'] = w['gflop']
+                o['fp32_equivalent_tflops'] = w['gflop'] / 1e3 / (k['us'] / 1e6)
+                o['tensor_tflops'] = w['tensor_gflop'] / 1e3 / (k['us'] / 1e6)
+            kernels_obj[name] = o
+        for name, tb in NCU_TRAFFIC_BYTES.items():
+            if name in kernels_obj:
+                kernels_obj[name]['dram_traffic_mbytes'] = tb / 1e6
+        crit = [n_ for n_ in ('k_train_fwd_tc', 'k_train_mid', 'k_train_bwd_tc', 'k_adam_touched') if n_ in ku]
+        dom = max(crit, key=lambda n_: ku[n_]['us'])
+        d = kernels_obj[dom]
+        if 'tensor_tflops' in d:
+            roof = {'kernel': dom + ' (tcgen05 3xTF32)', 'bound': 'tensor', 'achieved': d['tensor_tflops'],
+                    'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': d['tensor_tflops'] / tf32_peak,
+                    'traffic': NCU_TRAFFIC_BYTES.get(dom), 'traffic_source': NCU_TRAFFIC_SOURCE,
+                    'peak_source': peak_src + ': bf16 burst / 2 for kind::tf32',
+                    'limiter': 'the operand tile is generated, not loaded: Philox4x32-10 + Box-Muller for 4.3 M normals '
+                               'per step in each of the two contractions, on 16 producer warps per SM (instruction '
+                               'latency, not the tensor pipe or HBM)',
+                    'fp32_equivalent': {'achieved': d['fp32_equivalent_tflops'], 'peak': FP32_PEAK_TFLOPS,
+                                        'unit': 'TFLOP/s', 'frac': d['fp32_equivalent_tflops'] / FP32_PEAK_TFLOPS}}
+        else:
+            roof = {'kernel': dom, 'bound': 'hbm', 'achieved': d.get('gbs', 0.0), 'peak': hbm_peak, 'unit': 'GB/s',
+                    'frac': d.get('gbs', 0.0) / hbm_peak, 'traffic': NCU_TRAFFIC_BYTES.get(dom),
+                    'traffic_source': NCU_TRAFFIC_SOURCE, 'peak_source': peak_src}
+        sweep = kernels_obj.get('k_adam_untouched')
+        if sweep is not None:
+            roof['side_stream_sweep'] = {'kernel': 'k_adam_untouched', 'bound': 'hbm', 'achieved': sweep['gbs'],
+                                         'peak': hbm_peak, 'unit': 'GB/s', 'frac': sweep['gbs'] / hbm_peak,
+                                         'note': 'l2 + clip + Adam over the untouched rows, 128 threads on each SM '
+                                                 'beside the tensor-core kernels; off the critical path'}
+        roof['kernels_note'] = ('per-kernel %%globaltimer stamps inside extra replays of the captured step, L2 flushed '
+                                'before each measured step; step length by the same stamps: %.1f us' % tr['timeline_step_us'])
+        roof['kernels'] = kernels_obj
+    else:
+        stage = tr['stage_ms']                               # fwd, bwd, adam  (ms per step)
+        stages = {
+            'score_fwd': {'ms': float(stage[0]), 'gflop': pairs * FLOP_FWD_PAIR / 1e9, 'mbytes': pairs * BYTES_PAIR / 1e6},
+            'bpr_bwd': {'ms': float(stage[1]), 'gflop': pairs * FLOP_BWD_PAIR / 1e9,
+                        'mbytes': pairs * (BYTES_PAIR + 4 * D * (1 + Z)) / 1e6},
+            'adam_sweep': {'ms': float(stage[2]), 'gflop': 0.0, 'mbytes': 24.0 * n_params / 1e6},
+        }
+        for st in stages.values():
+            st['gbs'] = st['mbytes'] / 1e3 / (st['ms'] / 1e3) if st['ms'] > 0 else 0.0
+            st['tflops'] = st['gflop'] / 1e3 / (st['ms'] / 1e3) if st['ms'] > 0 else 0.0
+        dom = max(stages, key=lambda k: stages[k]['ms'])
+        roof = {'kernel': dom, 'bound': 'hbm', 'achieved': stages[dom]['gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': stages[dom]['gbs'] / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                'fp32_simt': {'achieved': stages[dom]['tflops'], 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+                              'frac': stages[dom]['tflops'] / FP32_PEAK_TFLOPS},
+                'stages_note': 'per-stage CUDA events of the same step launched kernel by kernel (includes launch gaps; '
+                               'the timed value replays the step as one CUDA graph)',
+                'stages': stages}
     eval_pairs = evl['rows']
     eval_users_s = world * args.eval_users / (evl['dev_ms'] / 1e3)
     eval_tflops = eval_pairs * FLOP_FWD_PAIR / 1e12 / (evl['score_ms'] / 1e3)

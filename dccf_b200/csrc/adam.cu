@@ -803,12 +803,14 @@ extern "C" int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tabl
             }
             attr_set = true;
         }
-        // 256 threads per CTA unless DCCF_SIDE_THREADS says otherwise (tuning knob: fewer threads = less L2 pressure on
-        // the concurrent forward, longer sweep)
+        // 128 threads per CTA unless DCCF_SIDE_THREADS says otherwise.  Measured (tools/step_timeline.py, electronics
+        // shape): 256 threads finish the sweep in 29 us but slow the concurrent forward / middle kernels by 4 / 6 us
+        // (L2 bandwidth); 128 threads take 45 us — still hidden behind the 50 us of forward + backward — and cost 2 us;
+        // 64 threads (82 us) no longer fit.
         static int side_threads = 0;
         if (side_threads == 0) {
             const char* v = getenv("DCCF_SIDE_THREADS");
-            side_threads = (v != nullptr && atoi(v) >= 32 && atoi(v) <= 256) ? (atoi(v) / 32) * 32 : 256;
+            side_threads = (v != nullptr && atoi(v) >= 32 && atoi(v) <= 256) ? (atoi(v) / 32) * 32 : 128;
         }
         if (getenv("DCCF_DEBUG_SKIP_UNTOUCHED") != nullptr) return DCCF_OK;   // timing experiments only: wrong results
         static int side_smem = -1;

@@ -102,7 +102,7 @@ struct TrainFwdParams {
     const int64_t* sample_item;
     const float* noise;          // mode 1
     float* pre_part;             // [n_ksplits][N][D]
-    float* x_save;               // optional [N][F]: Feat[i_r] + eps_r as multiplied, for the dW kernel of the same step
+    float* x_save;               // optional [ceil(N/128)*128 * F], tile-major: Feat[i_r] + eps_r as multiplied, for the dW kernel
     int32_t* err_flag;
     int64_t n_rows;
     int32_t n_items, F, S, A, R;
@@ -183,9 +183,12 @@ __global__ void __launch_bounds__(TC_NT, 2) k_train_fwd_tc(const TrainFwdParams 
                         v[q].z = __fadd_rn(v[q].z, e.z); v[q].w = __fadd_rn(v[q].w, e.w);
                     }
                 }
-                if (prm.x_save != nullptr && row_base + row < prm.n_rows) {
+                if (prm.x_save != nullptr) {
+                    // tile-major copy of what is multiplied: [row tile][feature chunk][kq][row][8 floats] — a warp
+                    // (32 consecutive rows, one kq) stores 1 KB contiguous
+                    float* dst = prm.x_save + ((((size_t)blockIdx.x * (prm.F / TC_KC) + (size_t)(f0 / TC_KC)) * 4 + kq) * TC_BM + row) * 8;
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) st4(prm.x_save + (size_t)grow * prm.F + kq * 8 + f0 + 4 * q, v[q]);
+                    for (int q = 0; q < 2; ++q) st4(dst + 4 * q, v[q]);
                 }
             }
             tc::mbar_wait(&empty_bar[s], ph ^ 1u);   // the MMAs that read this stage have completed
@@ -563,7 +566,7 @@ struct TrainBwdParams {
     const int64_t* sample_item;
     const float* noise;          // mode 1
     const float* dpre_rows;      // [N, D]
-    const float* x_rows;         // optional [N, F]: the forward's Feat + eps rows (else regenerated here)
+    const float* x_rows;         // optional: the forward's tile-major Feat + eps copy (else regenerated here)
     float* gW_part;              // [n_splits][D][K]
     float* gb_part;              // [n_splits][D]
     const float* loss_terms;     // optional [n_loss_terms]: summed into out_loss by CTA (0,0) (fused step)
@@ -663,7 +666,9 @@ __global__ void __launch_bounds__(TB_NT, 2) k_train_bwd_tc(const TrainBwdParams 
                     } else if (col < prm.K) {
                         const int f = col - D;
                         if (prm.x_rows != nullptr) {
-                            v[t] = ldg4(prm.x_rows + (size_t)r * prm.F + f);
+                            // the forward's tile-major copy (see k_train_fwd_tc)
+                            const size_t tile = (size_t)(r >> 7);
+                            v[t] = ldg4(prm.x_rows + (((tile * (prm.F / TC_KC) + (size_t)(f >> 5)) * 4 + ((f >> 3) & 3)) * TC_BM + (size_t)(r & 127)) * 8 + (f & 7));
                         } else {
                             v[t] = ldg4(prm.Feat + (size_t)fi * prm.F + f);
                             if (NOISE_MODE != 0) {

@@ -246,10 +246,10 @@ class DCCF(DMF):
     use_tensor_cores_train = True
     # forward + loss + backward as dccf_train_fwd_bwd_tc (one fused kernel between the two contractions)
     use_fused_step = True
-    # True: the forward stores the rows Feat + eps it multiplied and the dW kernel reads them back instead of
-    # regenerating the noise.  Measured slower (the strided 16-byte stores cost the forward 6 us, the dW kernel is
-    # not bound by the noise generation): off.
-    reuse_noise_rows = False
+    # True: the forward stores the rows Feat + eps it multiplied (tile-major, coalesced) and the dW kernel reads
+    # them back instead of regenerating the noise.  Measured: the dW kernel gains 1 us (it is not bound by the
+    # generation), the forward loses 3 us to the 17 MB of extra stores beside the Adam sweep: off.
+    reuse_noise_rows = os.environ.get('DCCF_REUSE_X', '0') != '0'
     tc_min_rows = 128 * 148
 
     def _tc_tables(self):
@@ -380,7 +380,7 @@ class DCCF(DMF):
             self.mlp[0].weight.data, self.mlp[0].bias.data, self._expo(), call['X'], call['sample_item'], Y, call['rng'],
             loss_mode, pred, rec['loss'], self._buf('ws_wimg', (kernels.train_w_image_floats(F),), torch.float32),
             w_image_valid, self._buf('ws_pre_part', (n_ks, N, D), torch.float32), self._buf('ws_dpre', (N, D), torch.float32),
-            self._buf('ws_x', (N, F), torch.float32) if self.reuse_noise_rows else None,
+            self._buf('ws_x', ((N + 127) // 128 * 128, F), torch.float32) if self.reuse_noise_rows else None,
             self._buf('ws_loss_terms', (P,), torch.float32), rec['gW_part'], rec['gb_part'], rec['gu_rec'],
             rec['gi_rec'], rec['keys_u'], rec['keys_i'], None, None, expo_e, expo_den, self._err_flag)
         if between is None:

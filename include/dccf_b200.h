@@ -190,8 +190,8 @@ int dccf_train_bwd_tc(const dccf_dims* dims, const float* E_user, const float* E
  * d loss / d pred, dpre rows, embedding-gradient records — with BPR a CTA owns the positive pair j and its
  * negative j + P/2), then the dW / db tiles (whose CTA (0,0) also sums the loss terms in a fixed order).
  *   w_image_valid != 0: ws_wimg already holds the operand images of the current W (dccf_adam_step wrote them)
- *   ws_x [N, F] optional workspace: the forward stores the rows Feat[i] + eps it multiplied and the dW kernel
- *        reads them back (L2-resident) instead of regenerating the noise; NULL: regenerated
+ *   ws_x [ceil(N/128)*128 * F] optional workspace: the forward stores the rows Feat[i] + eps it multiplied (tile-major)
+ *        and the dW kernel reads them back (L2-resident) instead of regenerating the noise; NULL: regenerated
  *   ws_loss_terms [P/2] (BPR) or [P] (MSE) workspace;  save_h / save_w optional (NULL: not written)
  *   expo_e [P, Z] / expo_den [P] optional: the exposure softmax precomputed by dccf_adam_link_ids
  *   phases: 3 = everything; 1 = only the partial products, 2 = only the rest (same arguments both times) — lets

@@ -63,7 +63,7 @@ def run(path, t, X, si, F, S, A, rng, time_it=0):
     gW_part, gb_part = torch.zeros(ns, D, K, **f32), torch.zeros(ns, D, **f32)
     if path == 'fused':
         terms = torch.zeros(P, **f32)
-        xs = torch.zeros(N, F, **f32)
+        xs = torch.zeros((N + 127) // 128 * 128, F, **f32)
 
         def step():
             kernels.train_fwd_bwd_tc(dims, t['E_user'], t['E_item'], t['Feat'], t['W'], t['b'], expo, X, si, None, rng, 0,
