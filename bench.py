@@ -252,7 +252,7 @@ def bench_train(model, X_all, steps, warmup, world, flush):
     # (dccf_b200/debug.py) — CUDA events cannot bracket the nodes of a graph.  Data-parallel runs (a different,
     # unfused step) fall back to CUDA events between the stages of a kernel-by-kernel step. --------------------
     kernels_us, timeline_step_us, stage_ms = {}, 0.0, None
-    if world == 1 and model._split_step_ok(0):
+    if model._split_step_ok(0, 2 * BATCH):
         from dccf_b200.debug import StepTimeline
         n_t = 30
         torch.manual_seed(SEED + 15)
@@ -478,6 +478,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: ONE JSON line
         torch.distributed.init_process_group('nccl', device_id=dev)
     from dccf_b200 import kernels
     model = build_model(U, I, dev)

@@ -11,7 +11,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libdccf_b200.so')
-ABI_VERSION = 21
+ABI_VERSION = 23
 DIM = 64
 
 
@@ -101,8 +101,8 @@ _SIGNATURES = {
                                        ctypes.POINTER(Adam), _P]),
     'dccf_adam_step': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(AdamTensor),
                                       ctypes.c_int32, ctypes.POINTER(Adam), _P]),
-    'dccf_adam_link_ids': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, ctypes.c_int64, _P, _P, _P, _P,
-                                          ctypes.POINTER(Expo), _P, _P, _P]),
+    'dccf_adam_link_ids': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
+                                          ctypes.c_int32, _P, _P, _P, _P, ctypes.POINTER(Expo), _P, _P, _P, _P, _P]),
     'dccf_adam_untouched': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(Adam), _P]),
     'dccf_adam_touched': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(AdamTensor),
                                          ctypes.c_int32, ctypes.POINTER(Adam), ctypes.c_int32, _P, ctypes.c_int32,
@@ -113,6 +113,9 @@ _SIGNATURES = {
     'dccf_stage_batch': (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, _P]),
     'dccf_state_advance': (ctypes.c_int, [_P, _P, ctypes.c_uint64, _P]),
     'dccf_dp_push': (ctypes.c_int, [_P, ctypes.c_int64, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, _P, _P, _P]),
+    'dccf_dp_push_fold': (ctypes.c_int, [_P, ctypes.c_int64, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, _P, _P,
+                                         _P, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                         _P, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _P]),
     'dccf_dp_wait': (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int64, _P, _P]),
     'dccf_dp_done': (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, _P, _P]),
     'dccf_full_scores_splits': (ctypes.c_int32, [ctypes.c_int32, ctypes.c_int32]),

@@ -348,9 +348,13 @@ __global__ void __launch_bounds__(256, 4) k_adam_all(const AdamAllArgs a) {
 // Every row is updated exactly once per step and with the same arithmetic as k_adam_all.
 // ---------------------------------------------------------------------------------------------
 struct LinkIdsArgs {
-    const int64_t* X;
+    const int64_t* X;            // segment 0; segment s at + s * seg_stride (int64 elements)
     const int64_t* sample_item;
-    int64_t n_pairs;
+    const int64_t* X_local;      // this rank's own batch (exposure softmax)
+    const int64_t* si_local;
+    int64_t n_pairs;             // per segment
+    int64_t seg_stride;
+    int32_t n_seg, user_seg;     // user_seg >= 0: only that segment carries user records (row-sharded user table)
     int32_t S, A, user_base, n_users, n_items;
     int32_t* head_u;
     int32_t* next_u;
@@ -366,25 +370,33 @@ __global__ void __launch_bounds__(256) k_link_ids(const LinkIdsArgs a) {
     tl_begin(0);
     tl_end(0);      // (short single wave: start and end are indistinguishable at the timer's resolution)
     if ((int)blockIdx.x >= a.link_blocks) {
-        // exposure softmax of every pair: depends on the ids only, so it is taken off the critical path here
+        // exposure softmax of every local pair: depends on the ids only, so it is taken off the critical path here
         const int64_t p = (int64_t)((int)blockIdx.x - a.link_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
         if (p >= a.n_pairs) return;   // warp-uniform
-        backdoor_weights(a.ex, a.X, a.sample_item, p, threadIdx.x & 31, a.n_users, a.user_base, a.n_items, a.S, a.A,
+        backdoor_weights(a.ex, a.X_local, a.si_local, p, threadIdx.x & 31, a.n_users, a.user_base, a.n_items, a.S, a.A,
                          a.expo_e + p * (a.S + 1), a.expo_den + p, nullptr);
         return;
     }
+    // record index (the one the gradient records will have): segment-major, as the Adam tables number them
     const int Z = a.S + 1;
+    const int64_t per_seg = a.n_pairs * (Z + 1);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_pairs * (Z + 1)) return;
-    const int64_t p = i / (Z + 1);
-    const int slot = (int)(i - p * (Z + 1));   // 0 = the user record of pair p, 1 + z = its item record of slot z
+    if (i >= per_seg * a.n_seg) return;
+    const int seg = (int)(i / per_seg);
+    const int64_t il = i - (int64_t)seg * per_seg;
+    const int64_t p = il / (Z + 1);
+    const int slot = (int)(il - p * (Z + 1));   // 0 = the user record of pair p, 1 + z = its item record of slot z
+    const int64_t* X = a.X + (int64_t)seg * a.seg_stride;
+    const int64_t* si = a.sample_item + (int64_t)seg * a.seg_stride;
     if (slot == 0) {
-        const int32_t u = checked_id(a.X[2 * p] - a.user_base, a.n_users, nullptr);
-        a.next_u[p] = atomicExch(&a.head_u[u], (int32_t)p);
+        if (a.user_seg >= 0 && seg != a.user_seg) return;
+        const int32_t u = checked_id(X[2 * p] - a.user_base, a.n_users, nullptr);
+        const int32_t r = (int32_t)((a.user_seg >= 0 ? 0 : (int64_t)seg * a.n_pairs) + p);
+        a.next_u[r] = atomicExch(&a.head_u[u], r);
     } else {
         const int z = slot - 1;
-        const int32_t it = checked_id(slot_item(a.X, a.sample_item, p, z, a.S), a.n_items, nullptr);
-        const int32_t r = (int32_t)(p * Z + z);
+        const int32_t it = checked_id(slot_item(X, si, p, z, a.S), a.n_items, nullptr);
+        const int32_t r = (int32_t)(((int64_t)seg * a.n_pairs + p) * Z + z);
         a.next_i[r] = atomicExch(&a.head_i[it], r);
     }
 }
@@ -750,18 +762,23 @@ extern "C" int dccf_debug_timeline_adam(unsigned long long* slots) {
 }
 
 extern "C" int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const int64_t* sample_item, int64_t n_pairs,
-                                  int32_t* head_user, int32_t* next_user, int32_t* head_item, int32_t* next_item,
-                                  const dccf_expo* expo, float* expo_e, float* expo_den, void* stream_) {
+                                  int32_t n_seg, int64_t seg_stride, int32_t user_seg, int32_t* head_user,
+                                  int32_t* next_user, int32_t* head_item, int32_t* next_item, const dccf_expo* expo,
+                                  const int64_t* X_local, const int64_t* sample_item_local, float* expo_e,
+                                  float* expo_den, void* stream_) {
     DCCF_CHECK_ARG(dims && X && head_user && next_user && head_item && next_item, "dccf_adam_link_ids: null argument");
     DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item, "dccf_adam_link_ids: sample_item is null");
-    DCCF_CHECK_ARG(n_pairs * (dims->n_samples + 1) < ((int64_t)1 << 31), "dccf_adam_link_ids: too many records");
+    DCCF_CHECK_ARG(n_seg >= 1 && (n_seg == 1 || seg_stride > 0) && user_seg < n_seg, "dccf_adam_link_ids: bad segment layout");
+    DCCF_CHECK_ARG(n_pairs * n_seg * (dims->n_samples + 1) < ((int64_t)1 << 31), "dccf_adam_link_ids: too many records");
     DCCF_CHECK_ARG(expo == nullptr || (expo_e && expo_den), "dccf_adam_link_ids: expo needs expo_e and expo_den");
     if (n_pairs <= 0) return DCCF_OK;
     LinkIdsArgs a;
     a.X = X; a.sample_item = sample_item; a.n_pairs = n_pairs; a.S = dims->n_samples; a.A = dims->n_attr;
+    a.X_local = X_local ? X_local : X; a.si_local = X_local ? sample_item_local : sample_item;
+    a.n_seg = n_seg; a.seg_stride = seg_stride; a.user_seg = user_seg;
     a.user_base = dims->user_base; a.n_users = dims->n_users; a.n_items = dims->n_items;
     a.head_u = head_user; a.next_u = next_user; a.head_i = head_item; a.next_i = next_item;
-    const int64_t n = n_pairs * (dims->n_samples + 2);
+    const int64_t n = n_pairs * n_seg * (dims->n_samples + 2);
     a.link_blocks = (int32_t)((n + 255) / 256);
     int64_t blocks = a.link_blocks;
     a.expo_e = expo_e; a.expo_den = expo_den;

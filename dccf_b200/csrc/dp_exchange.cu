@@ -28,9 +28,22 @@ __device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Up to two ranges of the segment are not copied from `send` but summed on the fly from row-split partial buffers
+// (the dW / db partials of the backward, ascending split order — the fold dccf_sum_parts would do in two more launches).
+struct DpFold {
+    const float* parts;      // [n_parts][stride]
+    int32_t n_parts;
+    int64_t stride;          // floats between partial buffers
+    int64_t off4, n4;        // range of the segment in float4 units: [off4, off4 + n4)
+};
+struct DpFolds {
+    DpFold f[2];
+    int32_t n;
+};
+
 __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send, int64_t seg, DpPeers peers, int world,
                                                  int rank, int64_t flag_off, const int32_t* __restrict__ epoch_dev,
-                                                 int32_t* cta_counter) {
+                                                 int32_t* cta_counter, const DpFolds folds) {
     const int32_t epoch = __ldg(epoch_dev) + 1;
     if (threadIdx.x < world) {
         // peers have finished reading what this rank pushed last step
@@ -41,10 +54,24 @@ __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send,
     __syncthreads();
     const int64_t n4 = seg >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int p = 0; p < world; ++p) {
-        float4* dst = reinterpret_cast<float4*>(peers.base[p] + (int64_t)rank * seg);
-        const float4* src = reinterpret_cast<const float4*>(send);
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) dst[i] = src[i];
+    const float4* src = reinterpret_cast<const float4*>(send);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v;
+        int which = -1;
+        for (int k = 0; k < folds.n; ++k)
+            if (i >= folds.f[k].off4 && i < folds.f[k].off4 + folds.f[k].n4) which = k;
+        if (which < 0) {
+            v = src[i];
+        } else {
+            const DpFold& f = folds.f[which];
+            const float* pp = f.parts + (i - f.off4) * 4;
+            v = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int32_t q = 0; q < f.n_parts; ++q) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(pp + (size_t)q * f.stride));
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
+        }
+        for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(peers.base[p] + (int64_t)rank * seg)[i] = v;
     }
     __threadfence_system();
     __syncthreads();
@@ -89,9 +116,9 @@ static int fill_peers(DpPeers* out, const uint64_t* peer_bases, int world, const
 using namespace dccf;
 
 // peer_bases: HOST array of `world` device addresses (this rank's own buffer at index `rank`)
-extern "C" int dccf_dp_push(const float* send, int64_t seg_floats, const uint64_t* peer_bases, int32_t world,
-                            int32_t rank, int64_t flag_off, const int32_t* epoch_dev, int32_t* cta_counter,
-                            void* stream_) {
+static int dp_push_impl(const float* send, int64_t seg_floats, const uint64_t* peer_bases, int32_t world, int32_t rank,
+                        int64_t flag_off, const int32_t* epoch_dev, int32_t* cta_counter, const DpFolds& folds,
+                        cudaStream_t stream) {
     DpPeers peers;
     int rc = fill_peers(&peers, peer_bases, world, "dccf_dp_push");
     if (rc != DCCF_OK) return rc;
@@ -100,9 +127,41 @@ extern "C" int dccf_dp_push(const float* send, int64_t seg_floats, const uint64_
     DCCF_CHECK_ARG(rank >= 0 && rank < world, "dccf_dp_push: rank %d outside [0,%d)", rank, world);
     int64_t ctas = (seg_floats / 4 + 255) / 256;
     if (ctas > 148) ctas = 148;
-    k_dp_push<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream_>>>(send, seg_floats, peers, world, rank, flag_off, epoch_dev, cta_counter);
+    k_dp_push<<<(unsigned)ctas, 256, 0, stream>>>(send, seg_floats, peers, world, rank, flag_off, epoch_dev, cta_counter, folds);
     DCCF_CHECK_LAUNCH("k_dp_push");
     return DCCF_OK;
+}
+
+// peer_bases: HOST array of `world` device addresses (this rank's own buffer at index `rank`)
+extern "C" int dccf_dp_push(const float* send, int64_t seg_floats, const uint64_t* peer_bases, int32_t world,
+                            int32_t rank, int64_t flag_off, const int32_t* epoch_dev, int32_t* cta_counter,
+                            void* stream_) {
+    DpFolds folds;
+    folds.n = 0;
+    return dp_push_impl(send, seg_floats, peer_bases, world, rank, flag_off, epoch_dev, cta_counter, folds,
+                        (cudaStream_t)stream_);
+}
+
+extern "C" int dccf_dp_push_fold(const float* send, int64_t seg_floats, const uint64_t* peer_bases, int32_t world,
+                                 int32_t rank, int64_t flag_off, const int32_t* epoch_dev, int32_t* cta_counter,
+                                 const float* parts_a, int32_t n_parts_a, int64_t stride_a, int64_t off_a, int64_t n_a,
+                                 const float* parts_b, int32_t n_parts_b, int64_t stride_b, int64_t off_b, int64_t n_b,
+                                 void* stream_) {
+    DpFolds folds;
+    folds.n = 0;
+    const float* parts[2] = {parts_a, parts_b};
+    const int32_t n_parts[2] = {n_parts_a, n_parts_b};
+    const int64_t stride[2] = {stride_a, stride_b}, off[2] = {off_a, off_b}, n[2] = {n_a, n_b};
+    for (int k = 0; k < 2; ++k) {
+        if (parts[k] == nullptr || n[k] <= 0) continue;
+        DCCF_CHECK_ARG(n_parts[k] >= 1 && off[k] % 4 == 0 && n[k] % 4 == 0 && stride[k] % 4 == 0 && off[k] + n[k] <= seg_floats &&
+                           (reinterpret_cast<uintptr_t>(parts[k]) & 15) == 0,
+                       "dccf_dp_push_fold: range %d must be 16-byte aligned and inside the segment", k);
+        DpFold& f = folds.f[folds.n++];
+        f.parts = parts[k]; f.n_parts = n_parts[k]; f.stride = stride[k]; f.off4 = off[k] / 4; f.n4 = n[k] / 4;
+    }
+    return dp_push_impl(send, seg_floats, peer_bases, world, rank, flag_off, epoch_dev, cta_counter, folds,
+                        (cudaStream_t)stream_);
 }
 
 extern "C" int dccf_dp_wait(const float* my_base, int32_t world, int64_t flag_off, const int32_t* epoch_dev, void* stream_) {

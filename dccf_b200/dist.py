@@ -20,26 +20,15 @@ def is_distributed():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
-class GradExchange(object):
-    """Layout of the per-rank gradient segment and the all-gather of all segments.
+class SegmentExchange(object):
+    """All-gather of one packed float32 segment per rank: `send` [seg] -> `recv` [world, seg] on every rank.
+    Peer-memory mode (default on CUDA): the rank's own kernels store the segment into every peer's symmetric
+    buffer over NVLink and wait on arrival flags (csrc/dp_exchange.cu) — plain kernels, capturable in a CUDA
+    graph, on whatever stream is current.  Otherwise one all_gather_into_tensor."""
 
-    P pairs per rank and step, Z slots, D embedding width, K = D + F columns of W.  Offsets are in 4-byte
-    elements; the key arrays are int32 views of the same float32 buffer."""
-
-    def __init__(self, P, Z, D, K, world, rank, device, group=None, use_p2p=True, user_records=True):
-        self.P, self.Z, self.D, self.K = P, Z, D, K
+    def __init__(self, seg, world, rank, device, group=None, use_p2p=True):
+        self.seg = (int(seg) + 3) // 4 * 4
         self.world, self.rank, self.group = world, rank, group
-        # user_records=False: the user table is row-sharded and each rank only trains its own users, so the
-        # user-row gradients never leave the rank (SURVEY.md §8e, scaled config)
-        self.user_records = user_records
-        Pu = P if user_records else 0
-        off = 0
-        self.off = {}
-        for name, n in (('gu', Pu * D), ('gi', P * Z * D), ('gW', D * K), ('gb', D), ('keys_u', Pu),
-                        ('keys_i', P * Z), ('loss', 1)):
-            self.off[name] = (off, n)
-            off += (n + 3) // 4 * 4                      # keep every part 16-byte aligned
-        self.seg = off
         self.send = torch.zeros(self.seg, dtype=torch.float32, device=device)
         self.mode = 'collective'
         self.recv = None
@@ -72,6 +61,70 @@ class GradExchange(object):
         self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=device)
         self.cta_counter = torch.zeros(1, dtype=torch.int32, device=device)
 
+    def exchange(self, folds=None):
+        """All ranks' segments, rank-major, in self.recv.  folds (peer-memory mode only): ranges of the segment that
+        are summed from partial buffers on the way out instead of being read from `send`:
+        [(parts, n_parts, stride, offset_in_segment, n_floats), ...] (csrc/dp_exchange.cu)."""
+        if self.mode == 'p2p':
+            from . import kernels
+            if folds:
+                kernels.dp_push_fold(self.send, self.seg, self.peer_bases, self.world, self.rank, self.flag_off,
+                                     self.epoch_dev, self.cta_counter, folds)
+            else:
+                kernels.dp_push(self.send, self.seg, self.peer_bases, self.world, self.rank, self.flag_off,
+                                self.epoch_dev, self.cta_counter)
+            kernels.dp_wait(self.sym, self.world, self.flag_off, self.epoch_dev)
+        elif self.world == 1:
+            self.recv.copy_(self.send)
+        else:
+            dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        return self.recv
+
+    def done(self):
+        """The receive buffer has been consumed (call after the last kernel that reads it)."""
+        if self.mode == 'p2p':
+            from . import kernels
+            kernels.dp_done(self.peer_bases, self.world, self.rank, self.flag_off, self.epoch_dev)
+
+
+class IdExchange(SegmentExchange):
+    """The ids of every rank's batch, gathered at the START of a step (24 KB per rank): with them each rank knows
+    which table rows the global step touches before any gradient exists, so the Adam sweep of all other rows can
+    overlap the forward and backward (DCCF._fused_split_step).  Segment = [X int64 [P,2] | sample_item int64 [P,S]];
+    `send_X` / `send_si` are the step's input buffers themselves (no staging copy)."""
+
+    def __init__(self, P, S, world, rank, device, group=None, use_p2p=True):
+        self.P, self.S = P, S
+        SegmentExchange.__init__(self, 2 * (2 * P) + 2 * (P * S), world, rank, device, group, use_p2p)
+        self.send_X = self.send[:4 * P].view(torch.int64).view(P, 2)
+        self.send_si = self.send[4 * P:4 * P + 2 * P * S].view(torch.int64).view(P, S)
+        self.si_off_i64 = 2 * P                          # int64 elements from a segment's X to its sample_item
+        self.seg_i64 = self.seg // 2
+
+    def recv_i64(self):
+        return self.recv.view(torch.int64)
+
+
+class GradExchange(SegmentExchange):
+    """Layout of the per-rank gradient segment and the all-gather of all segments.
+
+    P pairs per rank and step, Z slots, D embedding width, K = D + F columns of W.  Offsets are in 4-byte
+    elements; the key arrays are int32 views of the same float32 buffer."""
+
+    def __init__(self, P, Z, D, K, world, rank, device, group=None, use_p2p=True, user_records=True):
+        self.P, self.Z, self.D, self.K = P, Z, D, K
+        # user_records=False: the user table is row-sharded and each rank only trains its own users, so the
+        # user-row gradients never leave the rank (SURVEY.md §8e, scaled config)
+        self.user_records = user_records
+        Pu = P if user_records else 0
+        off = 0
+        self.off = {}
+        for name, n in (('gu', Pu * D), ('gi', P * Z * D), ('gW', D * K), ('gb', D), ('keys_u', Pu),
+                        ('keys_i', P * Z), ('loss', 1)):
+            self.off[name] = (off, n)
+            off += (n + 3) // 4 * 4                      # keep every part 16-byte aligned
+        SegmentExchange.__init__(self, off, world, rank, device, group, use_p2p)
+
     def part(self, buf, name, seg_index=0):
         a, n = self.off[name]
         t = buf[seg_index * self.seg + a: seg_index * self.seg + a + n]
@@ -86,27 +139,6 @@ class GradExchange(object):
                 'gW': self.part(self.send, 'gW').view(D, self.K), 'gb': self.part(self.send, 'gb'),
                 'keys_u': self.part(self.send, 'keys_u'), 'keys_i': self.part(self.send, 'keys_i'),
                 'loss': self.part(self.send, 'loss')}
-
-    def exchange(self):
-        """All ranks' segments, rank-major, in self.recv.  Peer-memory mode: this rank's kernel stores its
-        segment into every peer's buffer over NVLink and waits for the peers' stores (no NCCL, no host sync,
-        capturable in a CUDA graph); otherwise one all_gather_into_tensor."""
-        if self.mode == 'p2p':
-            from . import kernels
-            kernels.dp_push(self.send, self.seg, self.peer_bases, self.world, self.rank, self.flag_off,
-                            self.epoch_dev, self.cta_counter)
-            kernels.dp_wait(self.sym, self.world, self.flag_off, self.epoch_dev)
-        elif self.world == 1:
-            self.recv.copy_(self.send)
-        else:
-            dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
-        return self.recv
-
-    def done(self):
-        """The receive buffer has been consumed (call after the last kernel that reads it)."""
-        if self.mode == 'p2p':
-            from . import kernels
-            kernels.dp_done(self.peer_bases, self.world, self.rank, self.flag_off, self.epoch_dev)
 
     def total_loss(self):
         a, _ = self.off['loss']

@@ -267,15 +267,17 @@ def adam_step(tables, dense, hp):
 
 
 def adam_link_ids(dims, X, sample_item, head_user, next_user, head_item, next_item, expo=None, expo_e=None,
-                  expo_den=None):
+                  expo_den=None, n_pairs=None, n_seg=1, seg_stride=0, user_seg=-1, X_local=None, si_local=None):
     """Record lists of the step from the ids alone (before any gradient exists); with `expo` also the exposure
-    softmax of every pair (expo_e [P, Z], expo_den [P])."""
+    softmax of every local pair (expo_e [P, Z], expo_den [P]).  Data parallel: X / sample_item point at segment 0
+    of the gathered ids, n_seg segments seg_stride int64 apart."""
     lib = _lib.load()
-    check(lib.dccf_adam_link_ids(ctypes.byref(dims), ptr(X), ptr(sample_item), X.shape[0], ptr(head_user),
-                                 ptr(next_user), ptr(head_item), ptr(next_item),
-                                 ctypes.byref(expo) if expo is not None else None, ptr(expo_e), ptr(expo_den),
-                                 stream_ptr()), 'dccf_adam_link_ids')
-    LAUNCHES[0] += 1 if X.shape[0] > 0 else 0
+    n_pairs = X.shape[0] if n_pairs is None else int(n_pairs)
+    check(lib.dccf_adam_link_ids(ctypes.byref(dims), ptr(X), ptr(sample_item), n_pairs, int(n_seg), int(seg_stride),
+                                 int(user_seg), ptr(head_user), ptr(next_user), ptr(head_item), ptr(next_item),
+                                 ctypes.byref(expo) if expo is not None else None, ptr(X_local), ptr(si_local),
+                                 ptr(expo_e), ptr(expo_den), stream_ptr()), 'dccf_adam_link_ids')
+    LAUNCHES[0] += 1 if n_pairs > 0 else 0
 
 
 def adam_untouched(tables, hp):
@@ -353,6 +355,19 @@ def dp_push(send, seg, peer_bases, world, rank, flag_off, epoch_dev, cta_counter
     arr = (ctypes.c_uint64 * world)(*[int(b) for b in peer_bases])
     check(lib.dccf_dp_push(ptr(send), int(seg), arr, int(world), int(rank), int(flag_off), ptr(epoch_dev),
                            ptr(cta_counter), stream_ptr()), 'dccf_dp_push')
+    LAUNCHES[0] += 1
+
+
+def dp_push_fold(send, seg, peer_bases, world, rank, flag_off, epoch_dev, cta_counter, folds):
+    """dp_push with up to two ranges of the segment summed on the fly from partial buffers:
+    folds = [(parts, n_parts, stride, offset, n), ...]."""
+    lib = _lib.load()
+    arr = (ctypes.c_uint64 * world)(*[int(b) for b in peer_bases])
+    f = list(folds) + [(None, 0, 0, 0, 0)] * (2 - len(folds))
+    check(lib.dccf_dp_push_fold(ptr(send), int(seg), arr, int(world), int(rank), int(flag_off), ptr(epoch_dev),
+                                ptr(cta_counter), ptr(f[0][0]), int(f[0][1]), int(f[0][2]), int(f[0][3]), int(f[0][4]),
+                                ptr(f[1][0]), int(f[1][1]), int(f[1][2]), int(f[1][3]), int(f[1][4]), stream_ptr()),
+          'dccf_dp_push_fold')
     LAUNCHES[0] += 1
 
 

@@ -500,119 +500,164 @@ class DCCF(DMF):
         self._check_ready()
         return FusedAdamState(self, lr=lr, l2=l2, weight_decay=l2 if weight_decay is None else weight_decay, **kw)
 
+    def _step_tables(self, rec, P, opt):
+        """Descriptors of the optimizer step's tensors: the two embedding tables with their gradient records and W, b
+        with their partial sums.  Data parallel: records / dW / db of every rank, read from the receive buffer of the
+        gradient exchange (static addresses, so the descriptors can be built before the exchange runs)."""
+        Z, D = self.sample_num + 1, self.ui_vector_size
+        W, b = self.mlp[0].weight.data, self.mlp[0].bias.data
+        eu, ei = self.uid_embeddings.weight.data, self.iid_embeddings.weight.data
+        ea, es = opt.exp_avg, opt.exp_avg_sq
+        local_user = kernels.adam_table(eu, ea['E_user'], es['E_user'], rec['keys_u'], rec['gu_rec'], 1, P, P, P * D,
+                                        opt.head_u, self._buf('next_u', (P,), torch.int32))
+        if 'exchange' in rec:
+            ex = rec['exchange']
+            recv, world, seg = ex.recv, ex.world, ex.seg
+            user = local_user if not ex.user_records else \
+                kernels.adam_table(eu, ea['E_user'], es['E_user'], ex.part(recv, 'keys_u'), ex.part(recv, 'gu'), world, P,
+                                   seg, seg, opt.head_u, self._buf('next_u', (world * P,), torch.int32))
+            tables = [user,
+                      kernels.adam_table(ei, ea['E_item'], es['E_item'], ex.part(recv, 'keys_i'), ex.part(recv, 'gi'),
+                                         world, P * Z, seg, seg, opt.head_i,
+                                         self._buf('next_i', (world * P * Z,), torch.int32))]
+            dense = [kernels.adam_tensor(W, ea['W'], es['W'], ex.part(recv, 'gW'), world, seg),
+                     kernels.adam_tensor(b, ea['b'], es['b'], ex.part(recv, 'gb'), world, seg)]
+            return tables, dense
+        tables = [local_user,
+                  kernels.adam_table(ei, ea['E_item'], es['E_item'], rec['keys_i'], rec['gi_rec'], 1, P * Z, P * Z,
+                                     P * Z * D, opt.head_i, self._buf('next_i', (P * Z,), torch.int32))]
+        dense = [kernels.adam_tensor(W, ea['W'], es['W'], rec['gW_part'], rec['n_splits'], W.numel()),
+                 kernels.adam_tensor(b, ea['b'], es['b'], rec['gb_part'], rec['n_splits'], b.numel())]
+        return tables, dense
+
+    def _exchange_grads(self, rec):
+        """Data parallel: all-gather the gradient segments; the row-split partials of dW / db are folded into the
+        segment by the push kernel itself (peer-memory mode) or by two dccf_sum_parts launches."""
+        ex, v = rec['exchange'], rec['send']
+        W, b = self.mlp[0].weight.data, self.mlp[0].bias.data
+        if ex.mode == 'p2p':
+            ex.exchange(folds=[(rec['gW_part'], rec['n_splits'], W.numel(), ex.off['gW'][0], W.numel()),
+                               (rec['gb_part'], rec['n_splits'], b.numel(), ex.off['gb'][0], b.numel())])
+            return
+        kernels.sum_parts(rec['gW_part'], rec['n_splits'], W.numel(), W.numel(), v['gW'])
+        kernels.sum_parts(rec['gb_part'], rec['n_splits'], b.numel(), b.numel(), v['gb'])
+        ex.exchange()
+
     def _apply_adam(self, rec, P, opt, hp):
         """l2 + clip + Adam over both tables, W and b (two launches); under data parallelism preceded by the
         fold of the row-split partials and ONE all-gather of the packed gradient segment."""
-        Z = self.sample_num + 1
-        W, b = self.mlp[0].weight.data, self.mlp[0].bias.data
-        eu, ei = self.uid_embeddings.weight.data, self.iid_embeddings.weight.data
+        tables, dense = self._step_tables(rec, P, opt)
         if 'exchange' in rec:
-            ex, v = rec['exchange'], rec['send']
-            kernels.sum_parts(rec['gW_part'], rec['n_splits'], W.numel(), W.numel(), v['gW'])
-            kernels.sum_parts(rec['gb_part'], rec['n_splits'], b.numel(), b.numel(), v['gb'])
-            recv = ex.exchange()
-            world, seg = ex.world, ex.seg
-            if ex.user_records:
-                user_table = kernels.adam_table(eu, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'],
-                                                ex.part(recv, 'keys_u'), ex.part(recv, 'gu'), world, P, seg, seg,
-                                                opt.head_u, self._buf('next_u', (world * P,), torch.int32))
-            else:
-                user_table = kernels.adam_table(eu, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'], rec['keys_u'],
-                                                rec['gu_rec'], 1, P, P, P * self.ui_vector_size, opt.head_u,
-                                                self._buf('next_u', (P,), torch.int32))
-            tables = [
-                user_table,
-                kernels.adam_table(ei, opt.exp_avg['E_item'], opt.exp_avg_sq['E_item'], ex.part(recv, 'keys_i'),
-                                   ex.part(recv, 'gi'), world, P * Z, seg, seg, opt.head_i,
-                                   self._buf('next_i', (world * P * Z,), torch.int32))]
-            dense = [kernels.adam_tensor(W, opt.exp_avg['W'], opt.exp_avg_sq['W'], ex.part(recv, 'gW'), world, seg),
-                     kernels.adam_tensor(b, opt.exp_avg['b'], opt.exp_avg_sq['b'], ex.part(recv, 'gb'), world, seg)]
+            self._exchange_grads(rec)
             kernels.adam_step(tables, dense, hp)
-            loss = ex.total_loss()
-            ex.done()
+            loss = rec['exchange'].total_loss()
+            rec['exchange'].done()
             return loss
-        tables = [
-            kernels.adam_table(eu, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'], rec['keys_u'], rec['gu_rec'], 1, P,
-                               P, P * self.ui_vector_size, opt.head_u, self._buf('next_u', (P,), torch.int32)),
-            kernels.adam_table(ei, opt.exp_avg['E_item'], opt.exp_avg_sq['E_item'], rec['keys_i'], rec['gi_rec'], 1,
-                               P * Z, P * Z, P * Z * self.ui_vector_size, opt.head_i,
-                               self._buf('next_i', (P * Z,), torch.int32))]
-        dense = [kernels.adam_tensor(W, opt.exp_avg['W'], opt.exp_avg_sq['W'], rec['gW_part'], rec['n_splits'],
-                                     W.numel()),
-                 kernels.adam_tensor(b, opt.exp_avg['b'], opt.exp_avg_sq['b'], rec['gb_part'], rec['n_splits'],
-                                     b.numel())]
         kernels.adam_step(tables, dense, hp)
         return rec['loss'][0]
 
-    # single-GPU fused step: the Adam sweep of the rows the batch does not touch runs on a second stream while the
-    # forward and backward run (dccf_adam_mark_touched / _untouched / _touched)
+    # fused step with the optimizer split around the backward: the Adam sweep of the rows the (global) batch does not
+    # touch runs on a second stream while the forward and backward run (dccf_adam_link_ids / _untouched / _touched)
     use_split_adam = os.environ.get('DCCF_SPLIT_ADAM', '1') != '0'
     overlap_split_adam = os.environ.get('DCCF_SPLIT_OVERLAP', '1') != '0'
-
-    def _local_tables(self, rec, P, opt):
-        Z = self.sample_num + 1
-        W, b = self.mlp[0].weight.data, self.mlp[0].bias.data
-        eu, ei = self.uid_embeddings.weight.data, self.iid_embeddings.weight.data
-        tables = [
-            kernels.adam_table(eu, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user'], rec['keys_u'], rec['gu_rec'], 1, P,
-                               P, P * self.ui_vector_size, opt.head_u, self._buf('next_u', (P,), torch.int32)),
-            kernels.adam_table(ei, opt.exp_avg['E_item'], opt.exp_avg_sq['E_item'], rec['keys_i'], rec['gi_rec'], 1,
-                               P * Z, P * Z, P * Z * self.ui_vector_size, opt.head_i,
-                               self._buf('next_i', (P * Z,), torch.int32))]
-        dense = [kernels.adam_tensor(W, opt.exp_avg['W'], opt.exp_avg_sq['W'], rec['gW_part'], rec['n_splits'],
-                                     W.numel()),
-                 kernels.adam_tensor(b, opt.exp_avg['b'], opt.exp_avg_sq['b'], rec['gb_part'], rec['n_splits'],
-                                     b.numel())]
-        return tables, dense
 
     def _wimg_key(self):
         W = self.mlp[0].weight
         return (W._version, W.data_ptr(), self._param_epoch)
 
-    def _split_step_ok(self, loss_mode):
-        return self._dp is None and self.use_split_adam and self._fused_step_ok(loss_mode)
+    def _split_step_ok(self, loss_mode, P=None):
+        if not (self.use_split_adam and self._fused_step_ok(loss_mode)):
+            return False
+        if self._dp is None:
+            return True
+        # data parallel: needs the ids of every rank at the start of the step, exchanged by plain kernels
+        return P is not None and self._exchange_for(P).mode == 'p2p' and self._id_exchange_for(P).mode == 'p2p'
+
+    def _id_exchange_for(self, P):
+        from ..dist import IdExchange
+        ix = self._dp.setdefault('ids', {}).get(P)
+        if ix is None:
+            ix = IdExchange(P, self.sample_num, self._dp['world'], self._dp['rank'], self.uid_embeddings.weight.device,
+                            group=self._dp['group'], use_p2p=self._dp.get('p2p', True))
+            self._dp['ids'][P] = ix
+        return ix
 
     def _fused_split_step(self, call, loss_mode, Y, opt, hp, w_image_valid, overlap, counters=None):
         """Forward + loss + backward + optimizer with the optimizer split around the backward.  overlap=True: the
-        record linking and the sweep of the untouched rows go to a side stream (forked from / joined to the current
-        stream with events, so it is also legal under CUDA-graph capture).  counters = (step_dev, offset_dev): the
+        sweep of the untouched rows goes to a side stream (forked from / joined to the current stream with events,
+        so it is also legal under CUDA-graph capture).  Data parallel: the ranks first gather each other's ids
+        (call['X'] / call['sample_item'] must then be the send buffers of the id exchange), and the gradients are
+        exchanged between the backward and the sweep of the touched rows.  counters = (step_dev, offset_dev): the
         last CTA of the step advances them.  Returns (prediction, loss)."""
         P, N = call['P'], call['N']
         D, F = self.ui_vector_size, self.feature_embedding.shape[1]
         rec = self._rec_buffers(call, loss_mode, kernels.train_bwd_splits(N, F))
-        tables, dense = self._local_tables(rec, P, opt)
-        next_u, next_i = self._buf('next_u', (P,), torch.int32), self._buf('next_i', (P * (self.sample_num + 1),), torch.int32)
+        tables, dense = self._step_tables(rec, P, opt)
+        world = rec['exchange'].world if 'exchange' in rec else 1
+        next_u = self._buf('next_u', ((world if ('exchange' in rec and rec['exchange'].user_records) else 1) * P,), torch.int32)
+        next_i = self._buf('next_i', (world * P * (self.sample_num + 1),), torch.int32)
         wimg = self._buf('ws_wimg', (kernels.train_w_image_floats(F),), torch.float32)
         if opt.__dict__.get('cta_counter') is None:
             opt.cta_counter = torch.zeros(1, dtype=torch.int32, device=self.uid_embeddings.weight.device)
         main = torch.cuda.current_stream()
         overlap = overlap and self.overlap_split_adam
-
         expo_e = self._buf('ws_expo_e', (P, self.sample_num + 1), torch.float32)
         expo_den = self._buf('ws_expo_den', (P,), torch.float32)
+        dp = 'exchange' in rec
+        if dp:
+            ex, ix = rec['exchange'], self._id_exchange_for(P)
+            assert call['X'].data_ptr() == ix.send_X.data_ptr() and call['sample_item'].data_ptr() == ix.send_si.data_ptr()
 
-        # Record lists + exposure softmax from the ids: first, on the main stream.  (On the side stream it would run
-        # beside the first CTAs of the partial-product kernel — measured: that kernel then takes 22 us instead of 13.)
-        kernels.adam_link_ids(self._dims(), call['X'], call['sample_item'], opt.head_u, next_u, opt.head_i, next_i,
-                              self._expo(), expo_e, expo_den)
+        def link():
+            if dp:
+                ids = ix.exchange().view(torch.int64)
+                kernels.adam_link_ids(self._dims(), ids, ids[ix.si_off_i64:], opt.head_u, next_u, opt.head_i, next_i,
+                                      self._expo(), expo_e, expo_den, n_pairs=P, n_seg=ix.world, seg_stride=ix.seg_i64,
+                                      user_seg=-1 if ex.user_records else ix.rank, X_local=call['X'],
+                                      si_local=call['sample_item'])
+            else:
+                kernels.adam_link_ids(self._dims(), call['X'], call['sample_item'], opt.head_u, next_u, opt.head_i,
+                                      next_i, self._expo(), expo_e, expo_den)
+
+        between = None
+        if not dp:
+            # Record lists + exposure softmax from the ids: first, on the main stream.  (On the side stream it would run
+            # beside the first CTAs of the partial-product kernel — measured: that kernel then takes 22 us instead of 13.)
+            link()
         if overlap:
             if self.__dict__.get('_side_stream') is None:
                 self.__dict__['_side_stream'] = torch.cuda.Stream(device=main.device)
             side = self.__dict__['_side_stream']
-            fork, done = torch.cuda.Event(), torch.cuda.Event()
+            fork, linked, done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
             fork.record(main)
             side.wait_event(fork)
             with torch.cuda.stream(side):
+                if dp:                      # the id exchange waits for the peers: never on the critical path
+                    link()
+                    linked.record(side)
+                    between = lambda: main.wait_event(linked)      # noqa: E731  (the middle kernel reads expo_e)
                 kernels.adam_untouched(tables, hp)
+                if dp:
+                    ix.done()
                 done.record(side)
         else:
+            if dp:
+                link()
             kernels.adam_untouched(tables, hp)
+            if dp:
+                ix.done()
         pred, rec = self._launch_fwd_bwd(call, loss_mode, Y, rec=rec, w_image_valid=w_image_valid, expo_e=expo_e,
-                                         expo_den=expo_den)
+                                         expo_den=expo_den, between=between)
+        if dp:
+            self._exchange_grads(rec)
         if overlap:
             main.wait_event(done)
         step_dev, offset_dev = counters if counters is not None else (None, None)
         kernels.adam_touched(tables, dense, hp, True, wimg, 0, D + F, opt.cta_counter, step_dev, offset_dev)
+        if dp:
+            loss = ex.total_loss()
+            ex.done()
+            return pred, loss
         return pred, rec['loss'][0]
 
     def train_step(self, feed_dict, opt=None, stage_events=None):
@@ -633,7 +678,12 @@ class DCCF(DMF):
         call = self._make_call(feed_dict)
         loss_mode = 0 if feed_dict['rank'] == 1 else 1
         Y = feed_dict['Y'].to(call['X'].device, torch.float32).contiguous() if loss_mode == 1 else None
-        if stage_events is None and call['P'] > 0 and self._split_step_ok(loss_mode):
+        if stage_events is None and call['P'] > 0 and self._split_step_ok(loss_mode, call['P']):
+            if self._dp is not None:        # the ids travel to the peers from the id exchange's send buffers
+                ix = self._id_exchange_for(call['P'])
+                ix.send_X.copy_(call['X'])
+                ix.send_si.copy_(call['sample_item'])
+                call['X'], call['sample_item'] = ix.send_X, ix.send_si
             valid = self.__dict__.get('_wimg_valid_key') == self._wimg_key()
             opt.step_count += 1
             self._param_epoch += 1
@@ -673,6 +723,9 @@ class DCCF(DMF):
         if staged:
             g['epoch_ptrs'] = torch.zeros(2, dtype=torch.int64, device=dev)
             g['cursor'] = torch.zeros(1, dtype=torch.int64, device=dev)
+        if self._dp is not None and self._split_step_ok(0 if rank_mode == 1 else 1, P):
+            ix = self._id_exchange_for(P)       # the step's input buffers ARE the send segment of the id exchange
+            g['X'], g['si'] = ix.send_X, ix.send_si
         seed = self.random_seed
         if self._dp is not None:
             seed = (seed + 0x9E3779B97F4A7C15 * self._dp['rank']) & 0xffffffffffffffff
@@ -690,7 +743,7 @@ class DCCF(DMF):
                 kernels.stage_batch(g['epoch_ptrs'], g['cursor'], P, S, g['X'], g['si'])
             loss_mode = 0 if rank_mode == 1 else 1
             Yg = g['Y'] if rank_mode != 1 else None
-            if self._split_step_ok(loss_mode):
+            if self._split_step_ok(loss_mode, P):
                 # the W operand images are kept current by dccf_adam_touched (checked before every replay)
                 pred, loss = self._fused_split_step(call, loss_mode, Yg, opt, hp, True, overlap=True,
                                                     counters=(g['step_dev'], g['offset_dev']))

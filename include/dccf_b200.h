@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 21
+#define DCCF_ABI_VERSION 23
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -271,7 +271,12 @@ int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, const dccf_a
  *   dccf_adam_link_ids      builds the record lists of the step from the ids alone (record p = user row of pair
  *                           p, record p*Z + z = item row of slot z; out-of-range ids are clamped to row 0 exactly as
  *                           the kernels that write the records do): afterwards head[row] >= 0 marks a touched row
- *                           expo (optional): the same launch also evaluates the exposure softmax of every pair
+ *                           Data parallel: the ids of all n_seg ranks (gathered at the start of the step), segment s
+ *                           at X + s*seg_stride / sample_item + s*seg_stride (int64 elements), records numbered
+ *                           segment-major like the gathered gradient records; user_seg >= 0: only that segment
+ *                           has user records (row-sharded user table), numbered locally.
+ *                           expo (optional): the same launch also evaluates the exposure softmax of every pair of
+ *                           this rank's own batch (X_local / sample_item_local; NULL: segment 0)
  *                           (src/models/DCCF.py:98, a function of the ids only): expo_e [P, Z] = exp(expo - max),
  *                           expo_den [P] = A * sum_z, consumed by dccf_train_fwd_bwd_tc
  *   dccf_adam_untouched     rows whose head is -1; at most 148 CTAs so that a tensor-core CTA fits beside each
@@ -285,8 +290,9 @@ int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, const dccf_a
  *                           captured step; every other reader of the counters must have completed).
  * Every row is updated exactly once, with the arithmetic of dccf_adam_step. */
 int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const int64_t* sample_item, int64_t n_pairs,
-                       int32_t* head_user, int32_t* next_user, int32_t* head_item, int32_t* next_item,
-                       const dccf_expo* expo, float* expo_e, float* expo_den, void* stream);
+                       int32_t n_seg, int64_t seg_stride, int32_t user_seg, int32_t* head_user, int32_t* next_user,
+                       int32_t* head_item, int32_t* next_item, const dccf_expo* expo, const int64_t* X_local,
+                       const int64_t* sample_item_local, float* expo_e, float* expo_den, void* stream);
 int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam* hp, void* stream);
 int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
                       int32_t n_dense, const dccf_adam* hp, int32_t already_linked, float* w_image,
@@ -337,6 +343,15 @@ int dccf_rank_eval(const float* scores, const float* labels, const int64_t* iids
  * flag_off: offset of the flag area in floats (>= world*seg, multiple of 4).  cta_counter: device int32, zero. */
 int dccf_dp_push(const float* send, int64_t seg_floats, const uint64_t* peer_bases, int32_t world, int32_t rank,
                  int64_t flag_off, const int32_t* epoch_dev, int32_t* cta_counter, void* stream);
+/* Same as dccf_dp_push, but up to two ranges [off, off + n) (floats) of the segment are not read from `send`: they
+ * are the sum over n_parts partial buffers parts[q*stride + .], ascending q — the dW / db row-split partials of the
+ * backward folded on the way out (what dccf_sum_parts would do in two extra launches).  Ranges and strides must be
+ * multiples of 4 floats, the partial buffers 16-byte aligned; a NULL `parts` skips that range. */
+int dccf_dp_push_fold(const float* send, int64_t seg_floats, const uint64_t* peer_bases, int32_t world,
+                      int32_t rank, int64_t flag_off, const int32_t* epoch_dev, int32_t* cta_counter,
+                      const float* parts_a, int32_t n_parts_a, int64_t stride_a, int64_t off_a, int64_t n_a,
+                      const float* parts_b, int32_t n_parts_b, int64_t stride_b, int64_t off_b, int64_t n_b,
+                      void* stream);
 int dccf_dp_wait(const float* my_base, int32_t world, int64_t flag_off, const int32_t* epoch_dev, void* stream);
 int dccf_dp_done(const uint64_t* peer_bases, int32_t world, int32_t rank, int64_t flag_off, int32_t* epoch_dev,
                  void* stream);

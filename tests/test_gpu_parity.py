@@ -240,6 +240,62 @@ def test_ipsmf_exposure_vs_oracle():
     assert rel_err(got, ref['pred']) < 1e-5
 
 
+@pytest.mark.parametrize('dense_expo', [False, True])
+def test_row_sharded_user_table_equals_full_table(dense_expo):
+    """Scaled configuration: a rank that owns users [lo, hi) holds only those rows of the user
+    table, of its Adam state and of the exposure source (IPS-MF user factors, or the dense rows), and is fed
+    batches of its own users with GLOBAL ids.  Three fused steps give the same predictions, loss, user rows,
+    item table and W as the unsharded model on the same batches."""
+    from dccf_b200 import synth
+    from dccf_b200.models.DCCF import DCCF
+    U, I, F, P, S, A = 400, 300, 128, 64, 10, 2
+    lo, hi = 150, 270
+    params, X, si, _, _ = random_problem(29, U, I, F, P, S, A, 0.0, 0.0)
+    rs = np.random.RandomState(4)
+    X[:P // 2, 0] = rs.randint(lo, hi, size=P // 2)
+    X[P // 2:, 0] = X[:P // 2, 0]
+    fac = None if dense_expo else synth.make_ipsmf_factors(U, I, seed=3)
+    outs = []
+    for shard in (None, (lo, hi)):
+        model = DCCF(path='', dataset='', sentence_model='', sample_num=S, attribute_num=A, std=0.1, label_min=0,
+                     label_max=1, feature_num=0, user_num=U, item_num=I, u_vector_size=64, i_vector_size=64, n_layers=1,
+                     random_seed=2019, model_path='/tmp/dccf_test_model.pt', feature_embedding=params['Feat'],
+                     expo_prob=params['expo'] if dense_expo else None, expo_factors=fac, user_shard=shard)
+        with torch.no_grad():
+            eu = params['E_user'] if shard is None else params['E_user'][lo:hi]
+            model.uid_embeddings.weight.copy_(torch.from_numpy(eu))
+            model.iid_embeddings.weight.copy_(torch.from_numpy(params['E_item']))
+            model.mlp[0].weight.copy_(torch.from_numpy(params['W']))
+            model.mlp[0].bias.copy_(torch.from_numpy(params['b']))
+        model = model.cuda()
+        assert model.uid_embeddings.weight.shape[0] == (U if shard is None else hi - lo)
+        model.optimizer = model.make_fused_optimizer(lr=1e-3, l2=1e-4)
+        preds, losses = [], []
+        for t in range(3):
+            Xt = np.roll(X, t, axis=0).copy()
+            Xt[P // 2:, 0] = Xt[:P // 2, 0]
+            o = model.train_step({'X': torch.from_numpy(Xt).cuda(), 'rank': 1, 'train': True, 'dropout': 0.2,
+                                  'Y': torch.zeros(P).cuda(), 'sample_item': torch.from_numpy(np.roll(si, t, axis=0).copy())})
+            preds.append(o['prediction'].cpu().numpy().copy())
+            losses.append(float(o['loss']))
+        model.check_ids()
+        outs.append((preds, losses, model_params(model)))
+    full, part = outs
+    for t in range(3):
+        assert np.array_equal(part[0][t], full[0][t])
+        assert part[1][t] == full[1][t]
+    assert np.array_equal(part[2]['E_user'], full[2]['E_user'][lo:hi])
+    for k in ('E_item', 'W', 'b'):
+        assert np.array_equal(part[2][k], full[2][k]), k
+    # a user outside the shard is reported, not silently mapped onto a local row
+    bad = X.copy()
+    bad[0, 0] = bad[P // 2, 0] = lo - 1
+    model.predict({'X': torch.from_numpy(bad).cuda(), 'rank': 1, 'train': False, 'dropout': 0.0,
+                   'sample_item': torch.from_numpy(si)})
+    with pytest.raises(IndexError):
+        model.check_ids()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # the library's own random streams
 # ---------------------------------------------------------------------------------------------------------
