@@ -56,6 +56,14 @@ class FusedAdamState(object):
         return {'step': self.step_count, 'exp_avg': self.exp_avg, 'exp_avg_sq': self.exp_avg_sq,
                 'lr': self.lr, 'l2': self.l2, 'weight_decay': self.weight_decay}
 
+    def load_state_dict(self, sd):
+        """Resume: moments and step count of a saved run (the reference resumes weights only)."""
+        for k in self.exp_avg:
+            self.exp_avg[k].copy_(sd['exp_avg'][k])
+            self.exp_avg_sq[k].copy_(sd['exp_avg_sq'][k])
+        self.step_count = int(sd['step'])
+        self.lr, self.l2, self.weight_decay = sd['lr'], sd['l2'], sd['weight_decay']
+
 
 class _ScoreFn(torch.autograd.Function):
     """pred = DCCF score; backward through dccf_bpr_bwd with the upstream gradient (loss_mode 2)."""
@@ -391,6 +399,30 @@ class DCCF(DMF):
             kernels.train_fwd_bwd_tc(*args, phases=2)
         call['pred'] = pred
         return pred, rec
+
+    def save_training_state(self, path=None):
+        """Weights (the reference's state_dict keys) + fused-optimizer moments / step + the position of the library's
+        noise / dropout streams: everything a run needs to continue bit-identically."""
+        path = path or (self.model_path + '.train_state')
+        dir_path = os.path.dirname(path)
+        if dir_path and not os.path.exists(dir_path):
+            os.makedirs(dir_path)
+        opt = self.optimizer.state_dict() if isinstance(self.optimizer, FusedAdamState) else None
+        torch.save({'model': self.state_dict(), 'optimizer': opt, 'rng_offset': self._rng_offset}, path)
+        return path
+
+    def load_training_state(self, path=None):
+        path = path or (self.model_path + '.train_state')
+        st = torch.load(path, map_location=self.uid_embeddings.weight.device)
+        self.load_state_dict(st['model'])
+        if st['optimizer'] is not None:
+            if not isinstance(self.optimizer, FusedAdamState):
+                self.optimizer = self.make_fused_optimizer(lr=st['optimizer']['lr'], l2=st['optimizer']['l2'],
+                                                           weight_decay=st['optimizer']['weight_decay'])
+            self.optimizer.load_state_dict(st['optimizer'])
+        self._rng_offset = int(st['rng_offset'])
+        self._param_epoch += 1                      # projected tables / operand images of the old weights are stale
+        return self
 
     def check_ids(self):
         """Raise if any kernel since the last check met a user/item id outside the tables (the kernels clamp

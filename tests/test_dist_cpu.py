@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from dccf_b200.dist import GradExchange, all_reduce_sum, shard_users
+from dccf_b200.dist import GradExchange, IdExchange, all_reduce_sum, shard_users
 
 
 def _free_port():
@@ -46,6 +46,18 @@ def _worker(rank, world, port, out_dir):
             assert torch.equal(ex.part(recv, 'keys_i', r), torch.arange(P * Z, dtype=torch.int32) + 5000 * r)
         assert float(ex.total_loss()) == sum(range(1, world + 1))
         assert ex.seg % 4 == 0 and all(a % 4 == 0 for a, _ in ex.off.values())
+        # the ids of every rank's batch, gathered at the start of a step: int64 views of a float32 segment
+        S = 5
+        ix = IdExchange(P, S, world, rank, torch.device('cpu'))
+        ix.send_X.copy_(torch.arange(2 * P, dtype=torch.int64).view(P, 2) + (1 << 40) * (rank + 1))
+        ix.send_si.copy_(torch.arange(P * S, dtype=torch.int64).view(P, S) + 7 * rank)
+        ids = ix.exchange().view(torch.int64)
+        for r in range(world):
+            seg = ids[r * ix.seg_i64:(r + 1) * ix.seg_i64]
+            assert torch.equal(seg[:2 * P].view(P, 2), torch.arange(2 * P, dtype=torch.int64).view(P, 2) + (1 << 40) * (r + 1))
+            assert torch.equal(seg[ix.si_off_i64:ix.si_off_i64 + P * S].view(P, S),
+                               torch.arange(P * S, dtype=torch.int64).view(P, S) + 7 * r)
+        ix.done()
         # evaluation: users partitioned, metric sums reduced
         rs = np.random.RandomState(0)
         uid = rs.randint(0, 37, size=500)

@@ -296,6 +296,38 @@ def test_row_sharded_user_table_equals_full_table(dense_expo):
         model.check_ids()
 
 
+def test_training_state_resume_is_bit_identical(tmp_path):
+    """save_training_state / load_training_state (weights, Adam moments, step, stream position): a run resumed
+    in a fresh model continues exactly like the uninterrupted one."""
+    U, I, F, P, S, A = 120, 150, 128, 32, 10, 2
+    params, X, si, _, _ = random_problem(31, U, I, F, P, S, A, 0.0, 0.0)
+    X[P // 2:, 0] = X[:P // 2, 0]
+
+    def steps(model, t0, t1):
+        out = []
+        for t in range(t0, t1):
+            o = model.train_step({'X': torch.from_numpy(X).cuda(), 'rank': 1, 'train': True, 'dropout': 0.2,
+                                  'Y': torch.zeros(P).cuda(), 'sample_item': torch.from_numpy(np.roll(si, t, axis=0).copy())})
+            out.append(float(o['loss']))
+        return out
+
+    a = make_model(params, S, A, 0.1)
+    a.optimizer = a.make_fused_optimizer(lr=1e-3, l2=1e-4)
+    steps(a, 0, 3)
+    path = a.save_training_state(str(tmp_path / 'run.train_state'))
+    la = steps(a, 3, 6)
+    b = make_model(params, S, A, 0.1)
+    b.load_training_state(path)
+    lb = steps(b, 3, 6)
+    assert la == lb
+    pa, pb = model_params(a), model_params(b)
+    for k in pa:
+        assert np.array_equal(pa[k], pb[k]), k
+    for k in a.optimizer.exp_avg:
+        assert torch.equal(a.optimizer.exp_avg[k], b.optimizer.exp_avg[k])
+        assert torch.equal(a.optimizer.exp_avg_sq[k], b.optimizer.exp_avg_sq[k])
+
+
 # ---------------------------------------------------------------------------------------------------------
 # the library's own random streams
 # ---------------------------------------------------------------------------------------------------------
