@@ -11,7 +11,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libdccf_b200.so')
-ABI_VERSION = 23
+ABI_VERSION = 24
 DIM = 64
 
 
@@ -103,7 +103,8 @@ _SIGNATURES = {
                                       ctypes.c_int32, ctypes.POINTER(Adam), _P]),
     'dccf_adam_link_ids': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
                                           ctypes.c_int32, _P, _P, _P, _P, ctypes.POINTER(Expo), _P, _P, _P, _P, _P]),
-    'dccf_adam_untouched': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(Adam), _P]),
+    'dccf_adam_untouched': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(Adam), ctypes.c_int32,
+                                           _P]),
     'dccf_adam_touched': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(AdamTensor),
                                          ctypes.c_int32, ctypes.POINTER(Adam), ctypes.c_int32, _P, ctypes.c_int32,
                                          ctypes.c_int32, _P, _P, _P, _P]),

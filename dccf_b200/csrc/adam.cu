@@ -768,7 +768,8 @@ extern "C" int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const
                                   float* expo_den, void* stream_) {
     DCCF_CHECK_ARG(dims && X && head_user && next_user && head_item && next_item, "dccf_adam_link_ids: null argument");
     DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item, "dccf_adam_link_ids: sample_item is null");
-    DCCF_CHECK_ARG(n_seg >= 1 && (n_seg == 1 || seg_stride > 0) && user_seg < n_seg, "dccf_adam_link_ids: bad segment layout");
+    DCCF_CHECK_ARG(n_seg >= 0 && (n_seg <= 1 || seg_stride > 0) && (n_seg == 0 || user_seg < n_seg), "dccf_adam_link_ids: bad segment layout");
+    DCCF_CHECK_ARG(n_seg > 0 || expo != nullptr, "dccf_adam_link_ids: nothing to do (n_seg == 0 and no exposure source)");
     DCCF_CHECK_ARG(n_pairs * n_seg * (dims->n_samples + 1) < ((int64_t)1 << 31), "dccf_adam_link_ids: too many records");
     DCCF_CHECK_ARG(expo == nullptr || (expo_e && expo_den), "dccf_adam_link_ids: expo needs expo_e and expo_den");
     if (n_pairs <= 0) return DCCF_OK;
@@ -793,7 +794,8 @@ extern "C" int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const
     return DCCF_OK;
 }
 
-extern "C" int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam* hp, void* stream_) {
+extern "C" int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam* hp,
+                                   int32_t threads_per_cta, void* stream_) {
     AdamAllArgs a;
     int32_t blocks = 0, link_blocks = 0;
     // record buffers are not read by this kernel: strip them so the validation does not demand them
@@ -820,14 +822,15 @@ extern "C" int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tabl
             }
             attr_set = true;
         }
-        // 128 threads per CTA unless DCCF_SIDE_THREADS says otherwise.  Measured (tools/step_timeline.py, electronics
+        // threads_per_cta (0 = default 128; DCCF_SIDE_THREADS overrides).  Measured (tools/step_timeline.py, electronics
         // shape): 256 threads finish the sweep in 29 us but slow the concurrent forward / middle kernels by 4 / 6 us
-        // (L2 bandwidth); 128 threads take 45 us — still hidden behind the 50 us of forward + backward — and cost 2 us;
-        // 64 threads (82 us) no longer fit.
-        static int side_threads = 0;
-        if (side_threads == 0) {
+        // (L2 bandwidth); 128 threads take 45 us — still hidden behind the 50 us of forward + backward on one GPU — and
+        // cost 2 us; 64 threads (82 us) no longer fit.  Data-parallel steps start the sweep later (after the id exchange)
+        // and ask for 256.
+        int side_threads = (threads_per_cta >= 32 && threads_per_cta <= 256) ? (threads_per_cta / 32) * 32 : 128;
+        {
             const char* v = getenv("DCCF_SIDE_THREADS");
-            side_threads = (v != nullptr && atoi(v) >= 32 && atoi(v) <= 256) ? (atoi(v) / 32) * 32 : 128;
+            if (v != nullptr && atoi(v) >= 32 && atoi(v) <= 256) side_threads = (atoi(v) / 32) * 32;
         }
         if (getenv("DCCF_DEBUG_SKIP_UNTOUCHED") != nullptr) return DCCF_OK;   // timing experiments only: wrong results
         static int side_smem = -1;

@@ -1005,7 +1005,7 @@ extern "C" int dccf_train_fwd_bwd_tc(const dccf_dims* dims, const float* E_user,
                                      const float* expo_den, int32_t phases, int32_t* err_flag, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = check_fwd_args("dccf_train_fwd_bwd_tc", dims, expo, rng, sample_item, n_pairs);
-    DCCF_CHECK_ARG(phases >= 1 && phases <= 3, "dccf_train_fwd_bwd_tc: phases must be 1 (partial products), 2 (the rest) or 3 (both)");
+    DCCF_CHECK_ARG(phases >= 1 && phases <= 7, "dccf_train_fwd_bwd_tc: phases is a mask of 1 (partial products), 2 (middle kernel), 4 (dW / db)");
     DCCF_CHECK_ARG((expo_e == nullptr) == (expo_den == nullptr), "dccf_train_fwd_bwd_tc: expo_e and expo_den go together");
     if (rc != DCCF_OK) return rc;
     DCCF_CHECK_ARG(loss_mode == 0 || loss_mode == 1, "dccf_train_fwd_bwd_tc: loss_mode must be 0 (BPR) or 1 (MSE)");
@@ -1037,7 +1037,7 @@ extern "C" int dccf_train_fwd_bwd_tc(const dccf_dims* dims, const float* E_user,
                            err_flag, &n_ks, stream);
         if (rc != DCCF_OK) return rc;
     }
-    if (!(phases & 2)) return DCCF_OK;
+    if (!(phases & 6)) return DCCF_OK;
 
     TrainMidParams mid;
     mid.ex = *expo; mid.E_user = E_user; mid.W = W; mid.bias = b; mid.X = X; mid.sample_item = sample_item; mid.Y = Y;
@@ -1052,8 +1052,11 @@ extern "C" int dccf_train_fwd_bwd_tc(const dccf_dims* dims, const float* E_user,
     mid.inv_A = 1.0f / (float)dims->n_attr;
     mid.rng.seed = rng->seed; mid.rng.offset = rng->offset; mid.rng.offset_dev = rng->offset_dev;
     const int64_t n_terms = (loss_mode == 0) ? n_pairs / 2 : n_pairs;
-    k_train_mid<<<(unsigned)n_terms, TM_NT, smem, stream>>>(mid);
-    DCCF_CHECK_LAUNCH("k_train_mid");
+    if (phases & 2) {
+        k_train_mid<<<(unsigned)n_terms, TM_NT, smem, stream>>>(mid);
+        DCCF_CHECK_LAUNCH("k_train_mid");
+    }
+    if (!(phases & 4)) return DCCF_OK;
 
     return launch_bwd_tc(dims, E_item, Feat, X, sample_item, n_pairs, rng, ws_dpre, ws_x, gW_part, gb_part, ws_loss_terms,
                          n_terms, loss_mode == 0 ? 1.f : 1.f / (float)n_pairs, out_loss, stream);

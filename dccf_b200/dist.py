@@ -2,13 +2,10 @@
 
 One process per GPU, `torch.distributed` (NCCL over NVLink/NVSwitch; gloo in the CPU tests).  Training is
 data parallel with replicated parameters: the BPR loss is a SUM over samples (src/models/DCCF.py:120), so
-gradients add across ranks.  Per step each rank contributes ONE packed segment
-
-    [ user-row gradient records | item-row gradient records | dW | db | user keys | item keys | loss ]
-
-and a single all-gather delivers every rank's segment to every rank; each rank then applies the identical
-dense l2 + clip + Adam sweep over the identical record list (segment-major, fixed order), so replicas stay
-bit-identical without any parameter broadcast.  Evaluation shards users across ranks and needs one small
+gradients add across ranks.  Per step each rank contributes its ids (start of the step), its gradient records
+(after the middle kernel) and its dW / db / loss (after the dW kernel) as packed segments; an all-gather delivers
+every rank's segments to every rank; each rank then applies the identical l2 + clip + Adam update over the
+identical record list (segment-major, fixed order), so replicas stay bit-identical without any parameter broadcast.  Evaluation shards users across ranks and needs one small
 all-reduce of the metric sums.
 """
 import numpy as np
@@ -105,44 +102,78 @@ class IdExchange(SegmentExchange):
         return self.recv.view(torch.int64)
 
 
-class GradExchange(SegmentExchange):
-    """Layout of the per-rank gradient segment and the all-gather of all segments.
+class GradExchange(object):
+    """The per-rank gradient contribution of a step, all-gathered in TWO packed segments:
 
-    P pairs per rank and step, Z slots, D embedding width, K = D + F columns of W.  Offsets are in 4-byte
-    elements; the key arrays are int32 views of the same float32 buffer."""
+        records [ user-row gradient records | item-row gradient records | user keys | item keys ]   (ready after the
+                 middle kernel of the step; shipped on a side stream while the dW kernel runs)
+        dense   [ dW | db | loss ]                                                                  (after the dW kernel)
+
+    P pairs per rank and step, Z slots, D embedding width, K = D + F columns of W.  Offsets are in 4-byte elements
+    inside their segment; the key arrays are int32 views of the same float32 buffer."""
 
     def __init__(self, P, Z, D, K, world, rank, device, group=None, use_p2p=True, user_records=True):
         self.P, self.Z, self.D, self.K = P, Z, D, K
+        self.world, self.rank = world, rank
         # user_records=False: the user table is row-sharded and each rank only trains its own users, so the
         # user-row gradients never leave the rank (SURVEY.md §8e, scaled config)
         self.user_records = user_records
         Pu = P if user_records else 0
-        off = 0
-        self.off = {}
-        for name, n in (('gu', Pu * D), ('gi', P * Z * D), ('gW', D * K), ('gb', D), ('keys_u', Pu),
-                        ('keys_i', P * Z), ('loss', 1)):
-            self.off[name] = (off, n)
-            off += (n + 3) // 4 * 4                      # keep every part 16-byte aligned
-        SegmentExchange.__init__(self, off, world, rank, device, group, use_p2p)
+        self.off, self.where = {}, {}
+        sizes = {}
+        for which, parts in (('rec', (('gu', Pu * D), ('gi', P * Z * D), ('keys_u', Pu), ('keys_i', P * Z))),
+                             ('dense', (('gW', D * K), ('gb', D), ('loss', 1)))):
+            off = 0
+            for name, n in parts:
+                self.off[name] = (off, n)
+                self.where[name] = which
+                off += (n + 3) // 4 * 4                  # keep every part 16-byte aligned
+            sizes[which] = off
+        self.rec = SegmentExchange(sizes['rec'], world, rank, device, group, use_p2p)
+        self.dense = SegmentExchange(sizes['dense'], world, rank, device, group, use_p2p)
+        self.mode = 'p2p' if (self.rec.mode == 'p2p' and self.dense.mode == 'p2p') else 'collective'
 
-    def part(self, buf, name, seg_index=0):
+    def _ex(self, name):
+        return self.rec if self.where[name] == 'rec' else self.dense
+
+    def seg_of(self, name):
+        """segment length (floats) of the exchange that carries `name`"""
+        return self._ex(name).seg
+
+    def send_part(self, name):
         a, n = self.off[name]
-        t = buf[seg_index * self.seg + a: seg_index * self.seg + a + n]
-        if name.startswith('keys'):
-            t = t.view(torch.int32)
-        return t
+        t = self._ex(name).send[a:a + n]
+        return t.view(torch.int32) if name.startswith('keys') else t
+
+    def recv_part(self, name, seg_index=0):
+        """part `name` of rank seg_index's segment in the receive buffer; the parts of consecutive ranks are
+        seg_of(name) elements apart"""
+        a, n = self.off[name]
+        ex = self._ex(name)
+        t = ex.recv[seg_index * ex.seg + a: seg_index * ex.seg + a + n]
+        return t.view(torch.int32) if name.startswith('keys') else t
 
     def send_views(self):
         D = self.D
-        return {'gu_rec': self.part(self.send, 'gu').view(-1, D),
-                'gi_rec': self.part(self.send, 'gi').view(self.P * self.Z, D),
-                'gW': self.part(self.send, 'gW').view(D, self.K), 'gb': self.part(self.send, 'gb'),
-                'keys_u': self.part(self.send, 'keys_u'), 'keys_i': self.part(self.send, 'keys_i'),
-                'loss': self.part(self.send, 'loss')}
+        return {'gu_rec': self.send_part('gu').view(-1, D), 'gi_rec': self.send_part('gi').view(self.P * self.Z, D),
+                'gW': self.send_part('gW').view(D, self.K), 'gb': self.send_part('gb'),
+                'keys_u': self.send_part('keys_u'), 'keys_i': self.send_part('keys_i'), 'loss': self.send_part('loss')}
+
+    def exchange_records(self):
+        return self.rec.exchange()
+
+    def exchange_dense(self, folds=None):
+        if folds and self.dense.mode == 'p2p':
+            return self.dense.exchange(folds=folds)
+        return self.dense.exchange()
+
+    def done(self):
+        self.rec.done()
+        self.dense.done()
 
     def total_loss(self):
         a, _ = self.off['loss']
-        return self.recv.view(self.world, self.seg)[:, a].sum()
+        return self.dense.recv.view(self.world, self.dense.seg)[:, a].sum()
 
 
 def shard_users(uid, rank, world):

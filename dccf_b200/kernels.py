@@ -189,7 +189,7 @@ def train_fused_supported(n_samples, n_attr, loss_mode):
 
 def train_fwd_bwd_tc(dims, E_user, E_item, Feat, W, b, expo, X, sample_item, Y, rng, loss_mode, out_pred, out_loss,
                      ws_wimg, w_image_valid, ws_pre_part, ws_dpre, ws_x, ws_loss_terms, gW_part, gb_part, gu_rec, gi_rec,
-                     rec_keys_u, rec_keys_i, save_h=None, save_w=None, expo_e=None, expo_den=None, err_flag=None, phases=3):
+                     rec_keys_u, rec_keys_i, save_h=None, save_w=None, expo_e=None, expo_den=None, err_flag=None, phases=7):
     """Forward + BPR/MSE loss + backward of a training step: partial products, fused per-loss-term middle kernel,
     dW / db tiles (3 launches, 4 when the W operand images must be rebuilt)."""
     lib = _lib.load()
@@ -202,7 +202,7 @@ def train_fwd_bwd_tc(dims, E_user, E_item, Feat, W, b, expo, X, sample_item, Y, 
                                     ptr(expo_e), ptr(expo_den), int(phases), ptr(err_flag), stream_ptr()),
           'dccf_train_fwd_bwd_tc')
     if n_pairs > 0:
-        LAUNCHES[0] += ((1 if w_image_valid else 2) if phases & 1 else 0) + (2 if phases & 2 else 0)
+        LAUNCHES[0] += ((1 if w_image_valid else 2) if phases & 1 else 0) + (1 if phases & 2 else 0) + (1 if phases & 4 else 0)
 
 
 def adam_sweep(table, m, v, rec_keys, rec_grads, n_rec, head, nxt, hp):
@@ -280,11 +280,12 @@ def adam_link_ids(dims, X, sample_item, head_user, next_user, head_item, next_it
     LAUNCHES[0] += 1 if n_pairs > 0 else 0
 
 
-def adam_untouched(tables, hp):
-    """l2 + clip + Adam over the rows no record of this step refers to (head == -1): one launch, <= 148 CTAs."""
+def adam_untouched(tables, hp, threads=0):
+    """l2 + clip + Adam over the rows no record of this step refers to (head == -1): one launch, <= 148 CTAs of
+    `threads` threads (0 = the library's default)."""
     lib = _lib.load()
     ta = (AdamTable * max(1, len(tables)))(*tables)
-    check(lib.dccf_adam_untouched(ta, len(tables), ctypes.byref(hp), stream_ptr()), 'dccf_adam_untouched')
+    check(lib.dccf_adam_untouched(ta, len(tables), ctypes.byref(hp), int(threads), stream_ptr()), 'dccf_adam_untouched')
     LAUNCHES[0] += 1
 
 

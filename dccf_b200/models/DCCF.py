@@ -393,10 +393,10 @@ class DCCF(DMF):
             rec['gi_rec'], rec['keys_u'], rec['keys_i'], None, None, expo_e, expo_den, self._err_flag)
         if between is None:
             kernels.train_fwd_bwd_tc(*args)
-        else:                       # partial products, then whatever the caller must wait for, then the rest
-            kernels.train_fwd_bwd_tc(*args, phases=1)
-            between()
-            kernels.train_fwd_bwd_tc(*args, phases=2)
+        else:                       # kernel by kernel, with the caller's stream plumbing after each
+            for phase in (1, 2, 4):
+                kernels.train_fwd_bwd_tc(*args, phases=phase)
+                between(phase)
         call['pred'] = pred
         return pred, rec
 
@@ -544,16 +544,16 @@ class DCCF(DMF):
                                         opt.head_u, self._buf('next_u', (P,), torch.int32))
         if 'exchange' in rec:
             ex = rec['exchange']
-            recv, world, seg = ex.recv, ex.world, ex.seg
+            world, rseg, dseg = ex.world, ex.seg_of('gi'), ex.seg_of('gW')
             user = local_user if not ex.user_records else \
-                kernels.adam_table(eu, ea['E_user'], es['E_user'], ex.part(recv, 'keys_u'), ex.part(recv, 'gu'), world, P,
-                                   seg, seg, opt.head_u, self._buf('next_u', (world * P,), torch.int32))
+                kernels.adam_table(eu, ea['E_user'], es['E_user'], ex.recv_part('keys_u'), ex.recv_part('gu'), world, P,
+                                   rseg, rseg, opt.head_u, self._buf('next_u', (world * P,), torch.int32))
             tables = [user,
-                      kernels.adam_table(ei, ea['E_item'], es['E_item'], ex.part(recv, 'keys_i'), ex.part(recv, 'gi'),
-                                         world, P * Z, seg, seg, opt.head_i,
+                      kernels.adam_table(ei, ea['E_item'], es['E_item'], ex.recv_part('keys_i'), ex.recv_part('gi'),
+                                         world, P * Z, rseg, rseg, opt.head_i,
                                          self._buf('next_i', (world * P * Z,), torch.int32))]
-            dense = [kernels.adam_tensor(W, ea['W'], es['W'], ex.part(recv, 'gW'), world, seg),
-                     kernels.adam_tensor(b, ea['b'], es['b'], ex.part(recv, 'gb'), world, seg)]
+            dense = [kernels.adam_tensor(W, ea['W'], es['W'], ex.recv_part('gW'), world, dseg),
+                     kernels.adam_tensor(b, ea['b'], es['b'], ex.recv_part('gb'), world, dseg)]
             return tables, dense
         tables = [local_user,
                   kernels.adam_table(ei, ea['E_item'], es['E_item'], rec['keys_i'], rec['gi_rec'], 1, P * Z, P * Z,
@@ -562,25 +562,26 @@ class DCCF(DMF):
                  kernels.adam_tensor(b, ea['b'], es['b'], rec['gb_part'], rec['n_splits'], b.numel())]
         return tables, dense
 
-    def _exchange_grads(self, rec):
-        """Data parallel: all-gather the gradient segments; the row-split partials of dW / db are folded into the
-        segment by the push kernel itself (peer-memory mode) or by two dccf_sum_parts launches."""
+    def _exchange_dense(self, rec):
+        """Data parallel: all-gather dW / db / loss; the row-split partials of dW / db are folded into the segment by
+        the push kernel itself (peer-memory mode) or by two dccf_sum_parts launches."""
         ex, v = rec['exchange'], rec['send']
         W, b = self.mlp[0].weight.data, self.mlp[0].bias.data
         if ex.mode == 'p2p':
-            ex.exchange(folds=[(rec['gW_part'], rec['n_splits'], W.numel(), ex.off['gW'][0], W.numel()),
-                               (rec['gb_part'], rec['n_splits'], b.numel(), ex.off['gb'][0], b.numel())])
+            ex.exchange_dense(folds=[(rec['gW_part'], rec['n_splits'], W.numel(), ex.off['gW'][0], W.numel()),
+                                     (rec['gb_part'], rec['n_splits'], b.numel(), ex.off['gb'][0], b.numel())])
             return
         kernels.sum_parts(rec['gW_part'], rec['n_splits'], W.numel(), W.numel(), v['gW'])
         kernels.sum_parts(rec['gb_part'], rec['n_splits'], b.numel(), b.numel(), v['gb'])
-        ex.exchange()
+        ex.exchange_dense()
 
     def _apply_adam(self, rec, P, opt, hp):
         """l2 + clip + Adam over both tables, W and b (two launches); under data parallelism preceded by the
         fold of the row-split partials and ONE all-gather of the packed gradient segment."""
         tables, dense = self._step_tables(rec, P, opt)
         if 'exchange' in rec:
-            self._exchange_grads(rec)
+            rec['exchange'].exchange_records()
+            self._exchange_dense(rec)
             kernels.adam_step(tables, dense, hp)
             loss = rec['exchange'].total_loss()
             rec['exchange'].done()
@@ -640,48 +641,60 @@ class DCCF(DMF):
             ex, ix = rec['exchange'], self._id_exchange_for(P)
             assert call['X'].data_ptr() == ix.send_X.data_ptr() and call['sample_item'].data_ptr() == ix.send_si.data_ptr()
 
-        def link():
-            if dp:
-                ids = ix.exchange().view(torch.int64)
-                kernels.adam_link_ids(self._dims(), ids, ids[ix.si_off_i64:], opt.head_u, next_u, opt.head_i, next_i,
-                                      self._expo(), expo_e, expo_den, n_pairs=P, n_seg=ix.world, seg_stride=ix.seg_i64,
-                                      user_seg=-1 if ex.user_records else ix.rank, X_local=call['X'],
-                                      si_local=call['sample_item'])
-            else:
-                kernels.adam_link_ids(self._dims(), call['X'], call['sample_item'], opt.head_u, next_u, opt.head_i,
-                                      next_i, self._expo(), expo_e, expo_den)
+        # The exposure softmax of the local pairs (read by the middle kernel) and, on one GPU, the record lists: first,
+        # on the main stream.  (On the side stream this kernel would run beside the first CTAs of the partial-product
+        # kernel — measured: that kernel then takes 22 us instead of 13.)
+        kernels.adam_link_ids(self._dims(), call['X'], call['sample_item'], opt.head_u, next_u, opt.head_i, next_i,
+                              self._expo(), expo_e, expo_den, n_seg=0 if dp else 1)
+
+        def link_global():
+            # data parallel: every rank's ids, then the record lists of the GLOBAL step
+            ids = ix.exchange().view(torch.int64)
+            kernels.adam_link_ids(self._dims(), ids, ids[ix.si_off_i64:], opt.head_u, next_u, opt.head_i, next_i,
+                                  n_pairs=P, n_seg=ix.world, seg_stride=ix.seg_i64,
+                                  user_seg=-1 if ex.user_records else ix.rank)
 
         between = None
-        if not dp:
-            # Record lists + exposure softmax from the ids: first, on the main stream.  (On the side stream it would run
-            # beside the first CTAs of the partial-product kernel — measured: that kernel then takes 22 us instead of 13.)
-            link()
         if overlap:
-            if self.__dict__.get('_side_stream') is None:
-                self.__dict__['_side_stream'] = torch.cuda.Stream(device=main.device)
-            side = self.__dict__['_side_stream']
-            fork, linked, done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            d = self.__dict__
+            if d.get('_side_stream') is None:
+                d['_side_stream'] = torch.cuda.Stream(device=main.device)
+                d['_ship_stream'] = torch.cuda.Stream(device=main.device)
+            side, ship = d['_side_stream'], d['_ship_stream']
+            fork, done = torch.cuda.Event(), torch.cuda.Event()
             fork.record(main)
             side.wait_event(fork)
             with torch.cuda.stream(side):
                 if dp:                      # the id exchange waits for the peers: never on the critical path
-                    link()
-                    linked.record(side)
-                    between = lambda: main.wait_event(linked)      # noqa: E731  (the middle kernel reads expo_e)
-                kernels.adam_untouched(tables, hp)
+                    link_global()
+                kernels.adam_untouched(tables, hp, 256 if dp else 0)
                 if dp:
                     ix.done()
                 done.record(side)
+            if dp:
+                mid_done, shipped = torch.cuda.Event(), torch.cuda.Event()
+
+                def between(phase):        # noqa: E306  the gradient records leave while the dW kernel runs
+                    if phase == 2:
+                        mid_done.record(main)
+                        ship.wait_event(mid_done)
+                        with torch.cuda.stream(ship):
+                            ex.exchange_records()
+                            shipped.record(ship)
         else:
             if dp:
-                link()
+                link_global()
             kernels.adam_untouched(tables, hp)
             if dp:
                 ix.done()
         pred, rec = self._launch_fwd_bwd(call, loss_mode, Y, rec=rec, w_image_valid=w_image_valid, expo_e=expo_e,
                                          expo_den=expo_den, between=between)
         if dp:
-            self._exchange_grads(rec)
+            if not overlap:
+                ex.exchange_records()
+            self._exchange_dense(rec)
+            if overlap:
+                main.wait_event(shipped)
         if overlap:
             main.wait_event(done)
         step_dev, offset_dev = counters if counters is not None else (None, None)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 23
+#define DCCF_ABI_VERSION 24
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -194,8 +194,9 @@ int dccf_train_bwd_tc(const dccf_dims* dims, const float* E_user, const float* E
  *        and the dW kernel reads them back (L2-resident) instead of regenerating the noise; NULL: regenerated
  *   ws_loss_terms [P/2] (BPR) or [P] (MSE) workspace;  save_h / save_w optional (NULL: not written)
  *   expo_e [P, Z] / expo_den [P] optional: the exposure softmax precomputed by dccf_adam_link_ids
- *   phases: 3 = everything; 1 = only the partial products, 2 = only the rest (same arguments both times) — lets
- *        the caller wait for another stream (the one that produced expo_e) between the two
+ *   phases: mask of 1 = the partial products, 2 = the middle kernel, 4 = the dW / db tiles (7 = everything; same
+ *        arguments every time) — lets the caller wait for / signal other streams between the kernels (the stream
+ *        that produced expo_e before the middle kernel; the stream that ships the gradient records after it)
  * Needs dccf_train_fused_smem_bytes(S, A, loss_mode) <= 200 KB of shared memory per CTA (else use the two calls
  * above). */
 int64_t dccf_train_fused_smem_bytes(int32_t n_samples, int32_t n_attr, int32_t loss_mode);
@@ -274,12 +275,14 @@ int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, const dccf_a
  *                           Data parallel: the ids of all n_seg ranks (gathered at the start of the step), segment s
  *                           at X + s*seg_stride / sample_item + s*seg_stride (int64 elements), records numbered
  *                           segment-major like the gathered gradient records; user_seg >= 0: only that segment
- *                           has user records (row-sharded user table), numbered locally.
+ *                           has user records (row-sharded user table), numbered locally.  n_seg == 0: no linking,
+ *                           only the exposure softmax below.
  *                           expo (optional): the same launch also evaluates the exposure softmax of every pair of
  *                           this rank's own batch (X_local / sample_item_local; NULL: segment 0)
  *                           (src/models/DCCF.py:98, a function of the ids only): expo_e [P, Z] = exp(expo - max),
  *                           expo_den [P] = A * sum_z, consumed by dccf_train_fwd_bwd_tc
- *   dccf_adam_untouched     rows whose head is -1; at most 148 CTAs so that a tensor-core CTA fits beside each
+ *   dccf_adam_untouched     rows whose head is -1; at most 148 CTAs of threads_per_cta threads (0 = 128) so that a
+ *                           tensor-core CTA fits beside each
  *   dccf_adam_touched       the head record of each list updates its row (records summed in ascending index) and
  *                           resets head to -1; dense tensors as in dccf_adam_step.  already_linked = 0: links the
  *                           records first (dccf_adam_link_ids was not used).  w_image (optional): operand images
@@ -293,7 +296,8 @@ int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const int64_t* s
                        int32_t n_seg, int64_t seg_stride, int32_t user_seg, int32_t* head_user, int32_t* next_user,
                        int32_t* head_item, int32_t* next_item, const dccf_expo* expo, const int64_t* X_local,
                        const int64_t* sample_item_local, float* expo_e, float* expo_den, void* stream);
-int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam* hp, void* stream);
+int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam* hp,
+                        int32_t threads_per_cta, void* stream);
 int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
                       int32_t n_dense, const dccf_adam* hp, int32_t already_linked, float* w_image,
                       int32_t w_image_tensor, int32_t w_image_K, int32_t* cta_counter, int32_t* advance_step_dev,

@@ -35,17 +35,19 @@ def _worker(rank, world, port, out_dir):
         v['keys_u'].copy_(torch.arange(P, dtype=torch.int32) + 1000 * rank)
         v['keys_i'].copy_(torch.arange(P * Z, dtype=torch.int32) + 5000 * rank)
         v['loss'].fill_(float(rank + 1))
-        recv = ex.exchange()
+        ex.exchange_records()              # the two segments travel separately (records first, dW / db / loss later)
+        ex.exchange_dense()
         # every rank sees every segment, rank-major, keys intact as int32
         for r in range(world):
             gr = torch.Generator().manual_seed(100 + r)
-            assert torch.equal(ex.part(recv, 'gu', r).view(P, D), torch.randn(P, D, generator=gr))
-            assert torch.equal(ex.part(recv, 'gi', r).view(P * Z, D), torch.randn(P * Z, D, generator=gr))
-            assert torch.equal(ex.part(recv, 'gW', r).view(D, K), torch.randn(D, K, generator=gr))
-            assert torch.equal(ex.part(recv, 'keys_u', r), torch.arange(P, dtype=torch.int32) + 1000 * r)
-            assert torch.equal(ex.part(recv, 'keys_i', r), torch.arange(P * Z, dtype=torch.int32) + 5000 * r)
+            assert torch.equal(ex.recv_part('gu', r).view(P, D), torch.randn(P, D, generator=gr))
+            assert torch.equal(ex.recv_part('gi', r).view(P * Z, D), torch.randn(P * Z, D, generator=gr))
+            assert torch.equal(ex.recv_part('gW', r).view(D, K), torch.randn(D, K, generator=gr))
+            assert torch.equal(ex.recv_part('keys_u', r), torch.arange(P, dtype=torch.int32) + 1000 * r)
+            assert torch.equal(ex.recv_part('keys_i', r), torch.arange(P * Z, dtype=torch.int32) + 5000 * r)
         assert float(ex.total_loss()) == sum(range(1, world + 1))
-        assert ex.seg % 4 == 0 and all(a % 4 == 0 for a, _ in ex.off.values())
+        assert ex.rec.seg % 4 == 0 and ex.dense.seg % 4 == 0 and all(a % 4 == 0 for a, _ in ex.off.values())
+        ex.done()
         # the ids of every rank's batch, gathered at the start of a step: int64 views of a float32 segment
         S = 5
         ix = IdExchange(P, S, world, rank, torch.device('cpu'))
