@@ -11,7 +11,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libdccf_b200.so')
-ABI_VERSION = 24
+ABI_VERSION = 25
 DIM = 64
 
 
@@ -111,6 +111,7 @@ _SIGNATURES = {
     'dccf_train_prep_w_image': (ctypes.c_int, [_P, ctypes.c_int32, _P, _P]),
     'dccf_debug_timeline_train': (ctypes.c_int, [_P]),
     'dccf_debug_timeline_adam': (ctypes.c_int, [_P]),
+    'dccf_debug_timeline_dp': (ctypes.c_int, [_P]),
     'dccf_stage_batch': (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, _P]),
     'dccf_state_advance': (ctypes.c_int, [_P, _P, ctypes.c_uint64, _P]),
     'dccf_dp_push': (ctypes.c_int, [_P, ctypes.c_int64, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, _P, _P, _P]),

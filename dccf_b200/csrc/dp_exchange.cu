@@ -44,6 +44,7 @@ struct DpFolds {
 __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send, int64_t seg, DpPeers peers, int world,
                                                  int rank, int64_t flag_off, const int32_t* __restrict__ epoch_dev,
                                                  int32_t* cta_counter, const DpFolds folds) {
+    tl_begin(8);
     const int32_t epoch = __ldg(epoch_dev) + 1;
     if (threadIdx.x < world) {
         // peers have finished reading what this rank pushed last step
@@ -66,16 +67,26 @@ __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send,
             const DpFold& f = folds.f[which];
             const float* pp = f.parts + (i - f.off4) * 4;
             v = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int32_t q = 0; q < f.n_parts; ++q) {
+            int32_t q = 0;
+            for (; q + 8 <= f.n_parts; q += 8) {       // eight loads in flight, added in ascending order
+                float4 t8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t8[j] = __ldg(reinterpret_cast<const float4*>(pp + (size_t)(q + j) * f.stride));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { v.x += t8[j].x; v.y += t8[j].y; v.z += t8[j].z; v.w += t8[j].w; }
+            }
+            for (; q < f.n_parts; ++q) {
                 const float4 t = __ldg(reinterpret_cast<const float4*>(pp + (size_t)q * f.stride));
                 v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
             }
         }
         for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(peers.base[p] + (int64_t)rank * seg)[i] = v;
     }
-    __threadfence_system();
+    // one system-scope fence per CTA, by the thread that publishes the CTA's arrival, after the CTA barrier has
+    // ordered every thread's stores before it (a fence in each of the 13 K threads made the push take ~17 us)
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const int32_t prev = atomicAdd(cta_counter, 1);
         if (prev == (int32_t)gridDim.x - 1) {
             __threadfence_system();
@@ -84,15 +95,19 @@ __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send,
             *cta_counter = 0;
         }
     }
+    tl_end(8);
 }
 
 __global__ void k_dp_wait(const float* my_base, int world, int64_t flag_off, const int32_t* __restrict__ epoch_dev) {
+    tl_begin(9);
     const int32_t epoch = __ldg(epoch_dev) + 1;
     if ((int)threadIdx.x < world) {
         const int32_t* arrival = reinterpret_cast<const int32_t*>(my_base + flag_off);
         while (ld_acquire_sys(arrival + threadIdx.x) < epoch) {
         }
     }
+    __syncthreads();
+    tl_end(9);
 }
 
 __global__ void k_dp_done(DpPeers peers, int world, int rank, int64_t flag_off, int32_t* epoch_dev) {
@@ -114,6 +129,15 @@ static int fill_peers(DpPeers* out, const uint64_t* peer_bases, int world, const
 }  // namespace dccf
 
 using namespace dccf;
+
+extern "C" int dccf_debug_timeline_dp(unsigned long long* slots) {
+    cudaError_t e = cudaMemcpyToSymbol(g_timeline, &slots, sizeof(slots));
+    if (e != cudaSuccess) {
+        set_error("dccf_debug_timeline: %s", cudaGetErrorString(e));
+        return DCCF_ERR_CUDA;
+    }
+    return DCCF_OK;
+}
 
 // peer_bases: HOST array of `world` device addresses (this rank's own buffer at index `rank`)
 static int dp_push_impl(const float* send, int64_t seg_floats, const uint64_t* peer_bases, int32_t world, int32_t rank,

@@ -11,24 +11,25 @@ import torch
 from . import _lib
 
 SLOT_NAMES = ['k_link_ids', 'k_adam_untouched', 'k_train_fwd_tc', 'k_train_mid', 'k_train_bwd_tc', 'k_adam_touched',
-              'k_stage_batch']
+              'k_stage_batch', 'fwd latest CTA start', 'k_dp_push', 'k_dp_wait']
+N_SLOTS = 12
 
 
 class StepTimeline(object):
     def __init__(self, device):
         self.lib = _lib.load()
-        self.slots = torch.zeros(16, dtype=torch.int64, device=device)
-        self.init = torch.tensor([-1, 0] * 8, dtype=torch.int64, device=device)     # -1 = UINT64_MAX for atomicMin
+        self.slots = torch.zeros(2 * N_SLOTS, dtype=torch.int64, device=device)
+        self.init = torch.tensor([-1, 0] * N_SLOTS, dtype=torch.int64, device=device)     # -1 = UINT64_MAX for atomicMin
         self.rows = []
 
     def __enter__(self):
-        for fn in (self.lib.dccf_debug_timeline_train, self.lib.dccf_debug_timeline_adam):
+        for fn in (self.lib.dccf_debug_timeline_train, self.lib.dccf_debug_timeline_adam, self.lib.dccf_debug_timeline_dp):
             _lib.check(fn(ctypes.c_void_p(self.slots.data_ptr())), 'dccf_debug_timeline')
         return self
 
     def __exit__(self, *a):
         torch.cuda.synchronize()
-        for fn in (self.lib.dccf_debug_timeline_train, self.lib.dccf_debug_timeline_adam):
+        for fn in (self.lib.dccf_debug_timeline_train, self.lib.dccf_debug_timeline_adam, self.lib.dccf_debug_timeline_dp):
             fn(None)
 
     def arm(self):
@@ -37,13 +38,13 @@ class StepTimeline(object):
 
     def collect(self):
         torch.cuda.synchronize()
-        self.rows.append(self.slots.cpu().numpy().astype(np.uint64).reshape(8, 2).copy())
+        self.rows.append(self.slots.cpu().numpy().astype(np.uint64).reshape(N_SLOTS, 2).copy())
 
     def summary(self):
         """{kernel: {'start_us', 'end_us', 'us'}} (medians over the collected steps, relative to the first kernel
         start of the step) and the median step length."""
         rows = np.stack(self.rows)
-        used = [i for i in range(len(SLOT_NAMES)) if rows[0, i, 1] != 0]
+        used = [i for i in range(len(SLOT_NAMES)) if i != 7 and rows[0, i, 1] != 0 and rows[0, i, 0] != np.uint64(2**64 - 1)]
         if not used:
             return {}, 0.0
         t0 = np.array([min(int(r[i, 0]) for i in used) for r in rows], dtype=np.float64)

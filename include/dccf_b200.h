@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 24
+#define DCCF_ABI_VERSION 25
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -313,13 +313,15 @@ int dccf_stage_batch(const uint64_t* epoch_ptrs_dev, int64_t* cursor_dev, int64_
 int dccf_state_advance(int32_t* step_dev, uint64_t* offset_dev, uint64_t offset_inc, void* stream);
 
 /* ---- debug ------------------------------------------------------------------------------- */
-/* Install (or remove, with NULL) a device buffer of 2 x 8 uint64 slots in which the kernels of the fused training
+/* Install (or remove, with NULL) a device buffer of 2 x 12 uint64 slots in which the kernels of the fused training
  * step record {earliest CTA start, latest CTA end} in nanoseconds of %globaltimer: slot 0 k_link_ids,
- * 1 k_adam_untouched, 2 k_train_fwd_tc, 3 k_train_mid, 4 k_train_bwd_tc, 5 k_adam_touched, 6 k_stage_batch.
+ * 1 k_adam_untouched, 2 k_train_fwd_tc, 3 k_train_mid, 4 k_train_bwd_tc, 5 k_adam_touched, 6 k_stage_batch,
+ * 8 k_dp_push, 9 k_dp_wait (first start / last end over the exchanges of the step).
  * The caller initialises every slot to {UINT64_MAX, 0} (tools/step_timeline.py).  One entry point per
  * translation unit that owns instrumented kernels. */
 int dccf_debug_timeline_train(unsigned long long* slots);
 int dccf_debug_timeline_adam(unsigned long long* slots);
+int dccf_debug_timeline_dp(unsigned long long* slots);
 
 /* ---- (d): evaluation ranker -------------------------------------------------------------- */
 /* Replaces BaseModel.evaluate_method ranking branch (src/models/BaseModel.py:82-126) and
