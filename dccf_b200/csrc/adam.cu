@@ -815,7 +815,7 @@ extern "C" int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tabl
         static bool attr_set = false;
         if (!attr_set) {
             cudaError_t e = cudaFuncSetAttribute(k_adam_untouched, cudaFuncAttributeMaxDynamicSharedMemorySize, ADAM_SIDE_SMEM);
-            if (e == cudaSuccess && getenv("DCCF_NO_CARVEOUT") == nullptr) e = cudaFuncSetAttribute(k_adam_untouched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_adam_untouched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) {
                 set_error("dccf_adam_untouched: cannot opt in to %d bytes of shared memory: %s", ADAM_SIDE_SMEM, cudaGetErrorString(e));
                 return DCCF_ERR_CUDA;
@@ -832,14 +832,7 @@ extern "C" int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tabl
             const char* v = getenv("DCCF_SIDE_THREADS");
             if (v != nullptr && atoi(v) >= 32 && atoi(v) <= 256) side_threads = (atoi(v) / 32) * 32;
         }
-        if (getenv("DCCF_DEBUG_SKIP_UNTOUCHED") != nullptr) return DCCF_OK;   // timing experiments only: wrong results
-        static int side_smem = -1;
-        if (side_smem < 0) {
-            const char* v = getenv("DCCF_SIDE_SMEM_KB");
-            side_smem = (v != nullptr && v[0] != '\0') ? atoi(v) * 1024 : ADAM_SIDE_SMEM;
-            if (side_smem > ADAM_SIDE_SMEM) side_smem = ADAM_SIDE_SMEM;
-        }
-        k_adam_untouched<<<(unsigned)blocks, side_threads, side_smem, (cudaStream_t)stream_>>>(a);
+        k_adam_untouched<<<(unsigned)blocks, side_threads, ADAM_SIDE_SMEM, (cudaStream_t)stream_>>>(a);
         DCCF_CHECK_LAUNCH("k_adam_untouched");
     }
     return DCCF_OK;

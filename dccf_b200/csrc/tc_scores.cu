@@ -368,35 +368,6 @@ static int tc_launch(const dccf_dims* dims, const float* E_user, const float* PI
                      int64_t n_pairs, const dccf_rng* rng, float* out_pred, float* ws_rows, float* save_h, float* save_w,
                      float* dbg_pre, int32_t* err_flag, cudaStream_t stream);
 
-extern "C" int dccf_score_fwd_tc_train(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
-                                       const float* W, const float* b, const dccf_expo* expo, const int64_t* X,
-                                       const int64_t* sample_item, int64_t n_pairs, const dccf_rng* rng, float* out_pred,
-                                       float* ws_rows, float* ws_wt, float* ws_pi, float* ws_pf, float* ws_gB,
-                                       float* save_h, float* save_w, int32_t* err_flag, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    DCCF_CHECK_ARG(dims && expo && rng && E_user && E_item && Feat && W && b && X && out_pred && ws_rows && ws_wt && ws_pi &&
-                       ws_pf && ws_gB, "dccf_score_fwd_tc_train: null argument");
-    DCCF_CHECK_ARG(dims->dim == D, "dccf_score_fwd_tc_train: dim=%d but this build has D=%d", dims->dim, D);
-    DCCF_CHECK_ARG(dims->feat_dim > 0 && dims->feat_dim % 64 == 0, "dccf_score_fwd_tc_train: feat_dim=%d must be a positive multiple of 64", dims->feat_dim);
-    DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item, "dccf_score_fwd_tc_train: sample_item is null");
-    if (n_pairs <= 0) return DCCF_OK;
-    const int F = dims->feat_dim, K = D + F, Z = dims->n_samples + 1;
-    launch_transpose_w(W, ws_wt, K, stream);
-    DCCF_CHECK_LAUNCH("k_transpose_w");
-    // the noise-free terms only for the rows of this batch: PI per (pair, slot), PF per pair
-    TableJobs jobs;
-    int32_t blocks = 0;
-    fill_job(jobs.job[0], E_item, n_pairs * Z, D, ws_wt, nullptr, ws_pi, 1, dims, X, sample_item, blocks);
-    fill_job(jobs.job[1], Feat, n_pairs, F, ws_wt + (size_t)D * D, b, ws_pf, 2, dims, X, sample_item, blocks);
-    jobs.n_jobs = 2;
-    k_table_gemm<<<(unsigned)blocks, 256, 0, stream>>>(jobs);
-    DCCF_CHECK_LAUNCH("k_table_gemm");
-    k_prep_wf<<<96, 256, 0, stream>>>(W, F, ws_gB);
-    DCCF_CHECK_LAUNCH("k_prep_wf");
-    return tc_launch(dims, E_user, ws_pi, ws_pf, ws_gB, 1, expo, X, sample_item, n_pairs, rng, out_pred, ws_rows, save_h,
-                     save_w, nullptr, err_flag, stream);
-}
-
 extern "C" int dccf_score_fwd_tc(const dccf_dims* dims, const float* E_user, const float* PI, const float* PF,
                                  const float* gB, const dccf_expo* expo, const int64_t* X, const int64_t* sample_item,
                                  int64_t n_pairs, const dccf_rng* rng, float* out_pred, float* ws_rows, float* dbg_pre,

@@ -813,7 +813,7 @@ static int opt_in_smem(Kern k, const char* name) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
     // always the largest shared-memory carveout: a CTA of the side-stream Adam sweep (120 KB) and a tensor-core CTA
     // (96 KB) share an SM only if neither launch shrinks the carveout under the other
-    if (e == cudaSuccess && getenv("DCCF_NO_CARVEOUT") == nullptr) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) {
         set_error("%s: cannot opt in to %u bytes of shared memory: %s", name, TC_SMEM_BYTES, cudaGetErrorString(e));
         return DCCF_ERR_CUDA;
@@ -1020,7 +1020,7 @@ extern "C" int dccf_train_fwd_bwd_tc(const dccf_dims* dims, const float* E_user,
     DCCF_CHECK_ARG(smem <= 200 * 1024, "dccf_train_fwd_bwd_tc: S=%d A=%d need %zu bytes of shared memory per CTA; use dccf_train_fwd_tc + dccf_train_bwd_tc", dims->n_samples, dims->n_attr, smem);
     static size_t smem_opted = 0;
     if (smem_opted == 0) {
-        if (getenv("DCCF_NO_CARVEOUT") == nullptr) cudaFuncSetAttribute(k_train_mid, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_train_mid, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         smem_opted = 48 * 1024;
     }
     if (smem > smem_opted) {

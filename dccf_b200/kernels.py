@@ -115,20 +115,6 @@ def score_fwd_tc(dims, E_user, PI, PF, gB, expo, X, sample_item, rng, out_pred, 
     return out_pred
 
 
-def score_fwd_tc_train(dims, E_user, E_item, Feat, W, b, expo, X, sample_item, rng, out_pred, ws_rows, ws_wt, ws_pi,
-                       ws_pf, ws_gB, save_h, save_w, err_flag=None):
-    """Tensor-core forward of a training step (5 launches: W transpose, batch projections, W_f split, scorer,
-    backdoor sum)."""
-    lib = _lib.load()
-    n_pairs = X.shape[0]
-    check(lib.dccf_score_fwd_tc_train(ctypes.byref(dims), ptr(E_user), ptr(E_item), ptr(Feat), ptr(W), ptr(b),
-                                      ctypes.byref(expo), ptr(X), ptr(sample_item), n_pairs, ctypes.byref(rng),
-                                      ptr(out_pred), ptr(ws_rows), ptr(ws_wt), ptr(ws_pi), ptr(ws_pf), ptr(ws_gB),
-                                      ptr(save_h), ptr(save_w), ptr(err_flag), stream_ptr()), 'dccf_score_fwd_tc_train')
-    LAUNCHES[0] += 5 if n_pairs > 0 else 0
-    return out_pred
-
-
 def bwd_splits(n_rows):
     return int(_lib.load().dccf_bwd_splits(int(n_rows)))
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 25
+#define DCCF_ABI_VERSION 26
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -126,15 +126,6 @@ int dccf_score_fwd_tc(const dccf_dims* dims, const float* E_user, const float* P
                       const float* gB, const dccf_expo* expo, const int64_t* X, const int64_t* sample_item,
                       int64_t n_pairs, const dccf_rng* rng, float* out_pred, float* ws_rows, float* dbg_pre,
                       int32_t* err_flag, void* stream);
-
-/* Training-step flavour of the tensor-core scorer: the parameters change every step, so the noise-free
- * terms are projected only for the rows of this batch (ws_pi [P*Z,D] per (pair, slot), ws_pf [P,D] per pair),
- * W_f is re-split into ws_gB, and save_h [N,D] / save_w [P,Z] are written for dccf_bpr_bwd. */
-int dccf_score_fwd_tc_train(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
-                            const float* W, const float* b, const dccf_expo* expo, const int64_t* X,
-                            const int64_t* sample_item, int64_t n_pairs, const dccf_rng* rng, float* out_pred,
-                            float* ws_rows, float* ws_wt, float* ws_pi, float* ws_pf, float* ws_gB,
-                            float* save_h, float* save_w, int32_t* err_flag, void* stream);
 
 /* ---- (c) part 1: pairwise loss forward + full backward ---------------------------------- */
 /* Replaces DCCF.forward lines 116-125 (src/models/DCCF.py) + autograd backward
