@@ -2,9 +2,10 @@
 mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l)
 echo "gpus: $N"
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 tools/dp_check.py 2>&1 | grep -v "^\*\|OMP_NUM\|^$" | tail -6
-timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 200 --warmup 10 --eval-users 256 > gpurun_out/bench_r1e_dp$N.json 2> gpurun_out/bench_r1e_dp$N.err
-grep -v "^\*\|OMP_NUM\|^$" gpurun_out/bench_r1e_dp$N.err | tail -8
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 tools/dp_check.py > gpurun_out/dp_check_$N.log 2>&1
+grep -v "^\*\|OMP_NUM\|^$" gpurun_out/dp_check_$N.log | grep -i "error\|assert\|DP CHECK\|Traceback" | head -8
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 100 --warmup 5 --eval-users 128 > gpurun_out/bench_r1e_dp$N.json 2> gpurun_out/bench_r1e_dp$N.err
+grep -v "^\*\|OMP_NUM\|^$" gpurun_out/bench_r1e_dp$N.err | tail -5
 python -c "
 import json,sys
 d=json.loads([l for l in open('gpurun_out/bench_r1e_dp$N.json') if l.startswith('{')][-1])
