@@ -266,7 +266,17 @@ __device__ __forceinline__ float4 gather_row_grad(const AdamTableArgs& t, int32_
         ord_s[rank] = mine;
     }
     __syncwarp(half_mask);
-    for (int q = 0; q < n; ++q) {
+    // records added in ascending index, four loads in flight at a time (a hot item row has tens of records under
+    // data parallelism: one load per add would expose the L2 latency once per record)
+    int q = 0;
+    for (; q + 4 <= n; q += 4) {
+        float4 rg[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rg[j] = ldg4(t.grads + rec_grad_index(t.L, ord_s[q + j]) + sub * 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { g.x += rg[j].x; g.y += rg[j].y; g.z += rg[j].z; g.w += rg[j].w; }
+    }
+    for (; q < n; ++q) {
         const float4 rg = ldg4(t.grads + rec_grad_index(t.L, ord_s[q]) + sub * 4);
         g.x += rg.x; g.y += rg.y; g.z += rg.z; g.w += rg.w;
     }
@@ -478,17 +488,16 @@ __global__ void __launch_bounds__(256) k_adam_touched(const AdamAllArgs a, const
         const AdamTableArgs& t = a.t[i];
         const int b = bid - t.block_lo;
         if (b < 0 || b >= t.block_n) continue;
-        // half-warp per record; the record that is the head of its row's list owns the row
+        // half-warp per record (grid-stride: under data parallelism a step has tens of thousands of records, and one
+        // CTA per 16 of them would queue in several waves); the record that is the head of its row's list owns the row
         const int sub = threadIdx.x & 15;
-        const int64_t r = ((int64_t)b * blockDim.x + threadIdx.x) >> 4;
-        int32_t row = -1;
-        if (r < t.n_rec) {
-            row = t.keys[rec_key_index(t.L, r)];
+        const uint32_t half_mask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
+        const int64_t hw_stride = ((int64_t)t.block_n * blockDim.x) >> 4;
+        for (int64_t r = ((int64_t)b * blockDim.x + threadIdx.x) >> 4; r < t.n_rec; r += hw_stride) {
+            int32_t row = t.keys[rec_key_index(t.L, r)];
             if (row < 0 || row >= t.n_rows || t.head[row] != (int32_t)r) row = -1;
-        }
-        if (row >= 0) {
-            const uint32_t half_mask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
-            __syncwarp(half_mask);   // every lane of the half-warp has read the head before lane 0 resets it
+            if (row < 0) continue;          // (uniform over the half-warp: all 16 lanes read the same key and head)
+            __syncwarp(half_mask);          // every lane of the half-warp has read the head before lane 0 resets it
             const size_t o = (size_t)row * D + sub * 4;
             float4 p = ld4(t.table + o), m = ld4(t.m + o), q = ld4(t.v + o);
             const float4 g = gather_row_grad(t, (int32_t)r, sub, half_mask, list_s[threadIdx.x >> 4][0], list_s[threadIdx.x >> 4][1]);
@@ -708,7 +717,8 @@ static int marshal_adam(const char* who, const dccf_adam_table* tables, int32_t 
         o.head = t.head; o.next = t.next;
         int64_t want;
         if (mode == 2) {
-            want = (n_rec + 15) / 16;                              // 16 records (half-warps) per 256-thread CTA
+            want = (n_rec + 15) / 16;                              // 16 records (half-warps) per 256-thread CTA per trip
+            if (want > 148 * 3) want = 148 * 3;                    // one wave (three 256-thread CTAs fit an SM)
         } else {
             want = (o.n_rows + 31) / 32;                           // 32 rows per 256-thread CTA per trip
             int64_t share = total_rows > 0 ? (budget * o.n_rows + total_rows - 1) / total_rows : 0;
