@@ -551,8 +551,9 @@ def main():
         if sweep is not None:
             roof['side_stream_sweep'] = {'kernel': 'k_adam_untouched', 'bound': 'hbm', 'achieved': sweep['gbs'],
                                          'peak': hbm_peak, 'unit': 'GB/s', 'frac': sweep['gbs'] / hbm_peak,
-                                         'note': 'l2 + clip + Adam over the untouched rows, 128 threads on each SM '
-                                                 'beside the tensor-core kernels; off the critical path'}
+                                         'note': 'l2 + clip + Adam over the untouched rows on a side stream, one small CTA per SM '
+                                                 'beside the tensor-core kernels (128 threads; 256 under data parallelism); '
+                                                 'off the critical path by design, so its rate is a floor, not a target'}
         roof['kernels_note'] = ('per-kernel %%globaltimer stamps inside extra replays of the captured step, L2 flushed '
                                 'before each measured step; step length by the same stamps: %.1f us' % tr['timeline_step_us'])
         roof['kernels'] = kernels_obj
