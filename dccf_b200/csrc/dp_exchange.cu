@@ -24,6 +24,15 @@ __device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Spin until *p >= want.  A peer that died (or never reaches this step) must not leave this GPU spinning for ever:
+// after 60 s — four orders of magnitude beyond any legitimate wait, start-up skew included — the kernel traps, the
+// process sees a CUDA error and the job fails loudly instead of hanging the box.
+__device__ __forceinline__ void spin_until(const int32_t* p, int32_t want) {
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(p) < want) {
+        if (global_ns() - t0 > 60ull * 1000000000ull) __trap();
+    }
+}
 __device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -49,8 +58,7 @@ __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send,
     if (threadIdx.x < world) {
         // peers have finished reading what this rank pushed last step
         const int32_t* consumed = reinterpret_cast<const int32_t*>(peers.base[rank] + flag_off) + DP_MAX_WORLD;
-        while (ld_acquire_sys(consumed + threadIdx.x) < epoch - 1) {
-        }
+        spin_until(consumed + threadIdx.x, epoch - 1);
     }
     __syncthreads();
     const int64_t n4 = seg >> 2;
@@ -103,8 +111,7 @@ __global__ void k_dp_wait(const float* my_base, int world, int64_t flag_off, con
     const int32_t epoch = __ldg(epoch_dev) + 1;
     if ((int)threadIdx.x < world) {
         const int32_t* arrival = reinterpret_cast<const int32_t*>(my_base + flag_off);
-        while (ld_acquire_sys(arrival + threadIdx.x) < epoch) {
-        }
+        spin_until(arrival + threadIdx.x, epoch);
     }
     __syncthreads();
     tl_end(9);
