@@ -119,3 +119,64 @@ def test_torch_port_matches_reference(golden, name):
         assert rel_err(out['prediction'].detach().numpy(), g['pred_%d' % t]) < 1e-6
     assert rel_err(model.uid_embeddings.weight.detach().numpy(), g['final_E_user']) < 1e-6
     assert rel_err(model.mlp[0].weight.detach().numpy(), g['final_W']) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------
+# property tests of the oracle's ranker (the checker of the device ranker): SURVEY.md §4 plan item (4)
+# ---------------------------------------------------------------------------------------------------------
+def _brute_force_user(scores, labels, iids, rows, k):
+    """One user, straight from the definition: candidates in the total order (score desc, item id asc, row asc),
+    NaN scores last; ndcg@k with method-1 DCG and the ideal from the user's own labels
+    (src/utils/rank_metrics.py:159-164,198), hit / precision / recall / f1 as src/models/BaseModel.py:99-126."""
+    import functools
+    import math
+
+    def cmp(a, b):
+        sa, sb = scores[a], scores[b]
+        na, nb = math.isnan(sa), math.isnan(sb)
+        if na != nb:
+            return 1 if na else -1
+        if not na and sa != sb:
+            return -1 if sa > sb else 1
+        if iids[a] != iids[b]:
+            return -1 if iids[a] < iids[b] else 1
+        return -1 if rows[a] < rows[b] else 1
+
+    order = sorted(range(len(scores)), key=functools.cmp_to_key(cmp))
+    rel = [float(labels[i]) for i in order]
+    dcg = sum(r / math.log2(j + 2) for j, r in enumerate(rel[:k]))
+    ideal = sum(r / math.log2(j + 2) for j, r in enumerate(sorted(rel, reverse=True)[:k]))
+    hits = sum(rel[:k])
+    tot = sum(rel)
+    return ([iids[i] for i in order[:k]], [rows[i] for i in order[:k]],
+            [dcg / ideal if ideal else 0.0, 1.0 if hits > 0 else 0.0, sum(1 for r in rel[:k] if r != 0) / k,
+             hits / tot if tot else float('nan'), 2.0 * hits / (k + tot)])
+
+
+def test_rank_users_property_against_brute_force():
+    from hypothesis import given, settings, strategies as st
+
+    # few distinct scores and item ids: ties everywhere; NaN allowed; users of very different sizes
+    cand = st.tuples(st.integers(0, 3), st.sampled_from([0.0, 0.5, 0.5000001, -1.0, 2.0, float('nan')]),
+                     st.integers(0, 5), st.booleans())
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(cand, min_size=1, max_size=40), st.integers(1, 7))
+    def check(cands, k):
+        uid = np.array([c[0] for c in cands], dtype=np.int64)
+        scores = np.array([c[1] for c in cands], dtype=np.float32)
+        iid = np.array([c[2] for c in cands], dtype=np.int64)
+        Y = np.array([1.0 if c[3] else 0.0 for c in cands], dtype=np.float32)
+        users, topk, rows, m = O.rank_users(scores, uid, Y, iid, k)
+        assert list(users) == sorted(set(uid.tolist()))
+        for g, u in enumerate(users):
+            mine = [i for i in range(len(cands)) if uid[i] == u]
+            want_iid, want_row, want_m = _brute_force_user([float(scores[i]) for i in mine], [Y[i] for i in mine],
+                                                           [int(iid[i]) for i in mine], mine, k)
+            n = len(want_iid)
+            assert list(topk[g, :n]) == want_iid and all(topk[g, n:] == -1)
+            assert list(rows[g, :n]) == want_row
+            for a, b in zip(m[g], want_m):
+                assert (np.isnan(a) and np.isnan(b)) or abs(a - b) < 1e-12
+
+    check()
