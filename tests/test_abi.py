@@ -57,3 +57,24 @@ def test_sass_is_sm100a(lib_path):
 def test_missing_library_fails_loudly(tmp_path):
     with pytest.raises(_lib.DccfError, match='no CPU fallback'):
         _lib.load(str(tmp_path / 'nope.so'))
+
+
+def test_training_kernels_use_tcgen05_and_bulk_copies(lib_path):
+    """The two contractions of the training step and the evaluation scorer are tcgen05 kernels: their SASS holds
+    the tensor-core MMA (UTCHMMA), TMEM loads (LDTM), TMEM allocation (UTCATOMSWS), the MMA-completion barrier
+    (UTCBAR); the forward and the scorer also stream their W operand with bulk copies (UBLKCP)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    want = {'k_train_fwd_tc': ('UTCHMMA', 'LDTM', 'UTCATOMSWS', 'UTCBAR', 'UBLKCP'),
+            'k_train_bwd_tc': ('UTCHMMA', 'LDTM', 'UTCATOMSWS', 'UTCBAR'),
+            'k_row_scores_tc': ('UTCHMMA', 'LDTM', 'UTCATOMSWS', 'UTCBAR', 'UBLKCP')}
+    sass = subprocess.run([cuobjdump, '-sass', lib_path], capture_output=True, text=True).stdout
+    chunks = sass.split('Function : ')
+    for kernel, mnemonics in want.items():
+        body = [c for c in chunks if kernel in c.split('\n', 1)[0]]
+        assert body, kernel
+        for m in mnemonics:
+            assert any(m in c for c in body), (kernel, m)
