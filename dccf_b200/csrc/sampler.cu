@@ -54,8 +54,6 @@ struct MT {
     }
 };
 
-static inline bool in_sorted(const int64_t* a, int64_t n, int64_t x) { return std::binary_search(a, a + n, x); }
-
 }  // namespace dccf
 
 using namespace dccf;
@@ -75,27 +73,41 @@ extern "C" int dccf_sample_negatives(uint32_t* mt_key, int32_t* mt_pos, const in
     // negatives already handed to a user during this call (kept across rows when train, DP:477-504,516-517)
     std::vector<std::vector<int64_t>> drawn;
     if (train) drawn.resize((size_t)n_users);
-    std::vector<int64_t> local, taken_vt, pool;
+    std::vector<int64_t> local, pool;
+    // "is item i taken for the current row" in O(1): stamp[i] == the row's stamp.  Each row marks its user's
+    // history and the negatives the user already holds (a few dozen stores into an L2-resident array) instead of
+    // searching them on every draw — with 1000 negatives per evaluation user a search of `mine` per draw is quadratic.
+    std::vector<uint32_t> stamp((size_t)item_num, 0u);
+    uint32_t cur = 0;
     for (int64_t r = 0; r < n; ++r) {
         const int64_t u = uids[r];
         DCCF_CHECK_ARG(u >= 0 && u < n_users, "dccf_sample_negatives: uid %lld outside [0,%lld)", (long long)u, (long long)n_users);
-        const int64_t* th = train_items + train_off[u];
-        const int64_t tn = train_off[u + 1] - train_off[u];
-        const int64_t* vh = nullptr;
-        int64_t vn = 0;
-        int64_t n_taken = tn;
-        if (!train) {
-            vh = vt_items + vt_off[u];
-            vn = vt_off[u + 1] - vt_off[u];
-            for (int64_t k = 0; k < vn; ++k) n_taken += in_sorted(th, tn, vh[k]) ? 0 : 1;   // |train U vt|
+        if (++cur == 0) {                         // stamp wrapped after 2^32 - 1 rows: start over
+            std::fill(stamp.begin(), stamp.end(), 0u);
+            cur = 1;
         }
+        int64_t n_taken = 0;                      // |train U vt U drawn| (ids outside [0, item_num) can never be drawn
+        auto mark = [&](const int64_t* a, int64_t len) {          //  but count, as in the reference's len(set))
+            for (int64_t k = 0; k < len; ++k) {
+                const int64_t i = a[k];
+                if (i < 0 || i >= item_num) {
+                    n_taken += 1;
+                } else if (stamp[(size_t)i] != cur) {
+                    stamp[(size_t)i] = cur;
+                    n_taken += 1;
+                }
+            }
+        };
+        mark(train_items + train_off[u], train_off[u + 1] - train_off[u]);
+        if (!train) mark(vt_items + vt_off[u], vt_off[u + 1] - vt_off[u]);
         std::vector<int64_t>& mine = train ? drawn[(size_t)u] : local;
         if (!train) mine.clear();
-        n_taken += (int64_t)mine.size();          // drawn items are never in the history: disjoint
+        mark(mine.data(), (int64_t)mine.size());
         const int64_t remain = item_num - n_taken;
-        auto is_taken = [&](int64_t i) {
-            return in_sorted(th, tn, i) || (vn > 0 && in_sorted(vh, vn, i)) ||
-                   std::find(mine.begin(), mine.end(), i) != mine.end();
+        auto is_taken = [&](int64_t i) { return stamp[(size_t)i] == cur; };
+        auto take = [&](int64_t i) {
+            stamp[(size_t)i] = cur;
+            mine.push_back(i);
         };
         const bool use_pool = (1.0 * (double)remain / (double)item_num) < 0.2;
         if (use_pool) {
@@ -115,7 +127,7 @@ extern "C" int dccf_sample_negatives(uint32_t* mt_key, int32_t* mt_pos, const in
                 int64_t i = mt.interval((uint32_t)(item_num - 1));
                 while (is_taken(i)) i = mt.interval((uint32_t)(item_num - 1));
                 out[k] = i;
-                mine.push_back(i);
+                take(i);
             }
         } else {
             // np.random.choice(pool, neg_n, replace=False) == pool[permutation(len(pool))[:neg_n]]
@@ -134,7 +146,7 @@ extern "C" int dccf_sample_negatives(uint32_t* mt_key, int32_t* mt_pos, const in
             }
             for (int k = 0; k < neg_n; ++k) {
                 out[k] = pool[(size_t)perm[(size_t)k]];
-                mine.push_back(out[k]);
+                take(out[k]);
             }
         }
     }

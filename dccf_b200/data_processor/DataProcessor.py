@@ -48,6 +48,7 @@ class DataProcessor(object):
                 self.vt_history_dict[uid] = set(items)
         self.vt_batches_buffer = {}
         self.use_native_sampler = True      # dccf_sample_negatives (C++, draw-for-draw identical); False = Python loop
+        self.fast_ids_path = True           # id-only models: data dicts / epochs from arrays; False = DataFrame route
         self._csr = None
 
     # ---- data dicts --------------------------------------------------------------------------
@@ -61,7 +62,36 @@ class DataProcessor(object):
             utils.shuffle_in_unison_scary(self.train_data)
         return self.train_data
 
+    def _ids_only(self, df):
+        """True when format_data_dict's 'X' is exactly [uid, iid] for this model (DCCF: append_id, no id / user / item /
+        context feature columns, RecModel.py:10-13): the data dicts can then be assembled from arrays directly — same
+        contents as the DataFrame route (generate_neg_df + concat + format_data_dict), checked by
+        tests/test_host_parity.py — without a 48 M-row pandas merge for 1000 negatives x 48 k users."""
+        m, l = self.model, self.data_loader
+        return (m.append_id and not m.include_id and not m.include_context_features
+                and not (l.user_df is not None and m.include_user_features)
+                and not (l.item_df is not None and m.include_item_features)
+                and 'uid' in df and 'iid' in df and l.label in df.columns)
+
+    def _negatives(self, uids, neg_n, train):
+        """int64 [len(uids) * neg_n] negatives, user-major — the arrays behind _sample_neg_from_uid_list's frame."""
+        if self.use_native_sampler and len(uids) > 0:
+            return self._sample_neg_native(np.asarray(uids, dtype=np.int64), neg_n, train)
+        return self._sample_neg_from_uid_list(uids=uids, neg_n=neg_n, train=train)['iid_neg'].to_numpy(dtype=np.int64)
+
     def _vt_data(self, df):
+        if self.rank == 1 and self.fast_ids_path and self._ids_only(df):
+            uid = df['uid'].to_numpy(dtype=np.int64)
+            iid = df['iid'].to_numpy(dtype=np.int64)
+            _, first = np.unique(uid, return_index=True)
+            f_u = uid[np.sort(first)]                    # distinct users in first-appearance order (DP:420-430)
+            neg = self._negatives(f_u, self.test_neg_n, train=False)
+            data = {'uid': np.concatenate([uid, np.repeat(f_u, self.test_neg_n)]), 'iid': np.concatenate([iid, neg])}
+            data['Y'] = np.concatenate([np.asarray(df[self.data_loader.label], dtype=np.float32),
+                                        np.zeros(len(neg), dtype=np.float32)])
+            data['X'] = np.stack([data['uid'], data['iid']], axis=1)
+            data[global_p.K_SAMPLE_ID] = np.arange(0, len(data['Y']))
+            return data
         if self.rank == 1:
             neg_df = self.generate_neg_df(uid_list=df['uid'].tolist(), iid_list=df['iid'].tolist(), df=df,
                                           neg_n=self.test_neg_n, train=False)
@@ -174,32 +204,47 @@ class DataProcessor(object):
             for b in batches:
                 b['rank'] = 1
             return batches
-        neg_df = self.generate_neg_df(uid_list=data['uid'], iid_list=data['iid'], df=self.data_loader.train_df,
-                                      neg_n=1, train=True)
-        neg_X = self.format_data_dict(neg_df)['X']
         pos_X = np.asarray(data['X'])
+        if self.fast_ids_path and self._ids_only(self.data_loader.train_df) and pos_X.shape[1] == 2:
+            neg_X = np.stack([data['uid'], self._negatives(data['uid'], 1, train=True)], axis=1).astype(pos_X.dtype)
+        else:
+            neg_df = self.generate_neg_df(uid_list=data['uid'], iid_list=data['iid'], df=self.data_loader.train_df,
+                                          neg_n=1, train=True)
+            neg_X = self.format_data_dict(neg_df)['X']
+        # epoch layout: batch k = [its positives ; their negatives] (DP:160-207), all batches back to back
         total = (n + batch_size - 1) // batch_size
-        rows_X = np.empty((2 * n, pos_X.shape[1]), dtype=pos_X.dtype)
-        rows_Y = np.empty(2 * n, dtype=np.float32)
-        bounds, spans = [], []
-        for k in range(total):
-            a, b = k * batch_size, min(n, (k + 1) * batch_size)
-            real = b - a
-            rows_X[2 * a:2 * a + real] = pos_X[a:b]
-            rows_X[2 * a + real:2 * b] = neg_X[a:b]
-            rows_Y[2 * a:2 * a + real] = 1.0
-            rows_Y[2 * a + real:2 * b] = 0.0
-            bounds.append((2 * a, 2 * b))
-            spans.append((a, b))
-        views = self._epoch_views(rows_X, rows_Y, bounds)
+        n_full = n // batch_size
+        w = pos_X.shape[1]
         n_train = len(self.train_data['Y'])
-        batches = []
-        for (a, b), (xv, yv) in zip(spans, views):
-            sid = data[global_p.K_SAMPLE_ID][a:b]
-            batches.append({'train': train, 'rank': 1, 'Y': yv, 'X': xv,
-                            global_p.K_SAMPLE_ID: np.concatenate([sid, sid + n_train]),
-                            global_p.REAL_BATCH_SIZE: b - a, global_p.TOTAL_BATCH_SIZE: 2 * (b - a)})
-        return batches
+        sid = np.asarray(data[global_p.K_SAMPLE_ID])
+        rows_X = np.empty((2 * n, w), dtype=pos_X.dtype)
+        rows_Y = np.empty(2 * n, dtype=np.float32)
+        rows_sid = np.empty(2 * n, dtype=sid.dtype)
+        m = n_full * batch_size
+        if n_full:
+            vx = rows_X[:2 * m].reshape(n_full, 2, batch_size, w)
+            vx[:, 0] = pos_X[:m].reshape(n_full, batch_size, w)
+            vx[:, 1] = neg_X[:m].reshape(n_full, batch_size, w)
+            vy = rows_Y[:2 * m].reshape(n_full, 2, batch_size)
+            vy[:, 0] = 1.0
+            vy[:, 1] = 0.0
+            vs = rows_sid[:2 * m].reshape(n_full, 2, batch_size)
+            vs[:, 0] = sid[:m].reshape(n_full, batch_size)
+            vs[:, 1] = vs[:, 0] + n_train
+        if m < n:                                       # ragged last batch
+            real = n - m
+            rows_X[2 * m:2 * m + real] = pos_X[m:]
+            rows_X[2 * m + real:] = neg_X[m:]
+            rows_Y[2 * m:2 * m + real] = 1.0
+            rows_Y[2 * m + real:] = 0.0
+            rows_sid[2 * m:2 * m + real] = sid[m:]
+            rows_sid[2 * m + real:] = sid[m:] + n_train
+        spans = [(k * batch_size, min(n, (k + 1) * batch_size)) for k in range(total)]
+        bounds = [(2 * a, 2 * b) for a, b in spans]
+        views = self._epoch_views(rows_X, rows_Y, bounds)
+        return [{'train': train, 'rank': 1, 'Y': yv, 'X': xv, global_p.K_SAMPLE_ID: rows_sid[2 * a:2 * b],
+                 global_p.REAL_BATCH_SIZE: b - a, global_p.TOTAL_BATCH_SIZE: 2 * (b - a)}
+                for (a, b), (xv, yv) in zip(spans, views)]
 
     def prepare_batches(self, data, batch_size, train):
         """All batches of a data dict; validation/test lists are cached (DataProcessor.py:252-275)."""

@@ -35,10 +35,25 @@ def format_metric(metric):
 def shuffle_in_unison_scary(data):
     """Shuffle every array of the dict with the SAME permutation by replaying one numpy RNG state per
     array; the global stream advances by one shuffle (src/utils/utils.py:82-92)."""
+    arrays = [data[key] for key in data]
+    lengths = {len(a) for a in arrays}
+    distinct = all(not np.may_share_memory(a, b) for k, a in enumerate(arrays) for b in arrays[k + 1:]
+                   if isinstance(a, np.ndarray) and isinstance(b, np.ndarray))
+    if len(lengths) == 1 and distinct and all(isinstance(a, np.ndarray) for a in arrays):
+        # Same result, one Fisher-Yates pass instead of one per array: np.random.shuffle draws j in [0, i] for
+        # i = n-1 .. 1 whatever the array holds (1-D or 2-D), so shuffling arange(n) from the current state yields the
+        # permutation every array would undergo and leaves the generator exactly where the last replay would have.
+        # Arrays are overwritten in place (their identity is part of the reference's behaviour: the train dict handed
+        # out by get_train_data(-1) is the one later epochs shuffle).
+        perm = np.arange(lengths.pop())
+        np.random.shuffle(perm)
+        for a in arrays:
+            a[...] = a[perm]
+        return data
     state = np.random.get_state()
-    for key in data:
+    for a in arrays:
         np.random.set_state(state)
-        np.random.shuffle(data[key])
+        np.random.shuffle(a)
     return data
 
 

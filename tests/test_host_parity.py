@@ -207,3 +207,71 @@ def test_native_sampler_reports_exhausted_user(tmp_path):
     dp = DataProcessor(dl, model, rank=1, test_neg_n=35)
     with pytest.raises(AssertionError):
         dp.get_test_data()
+
+
+def test_array_route_equals_dataframe_route(golden, tmp_path):
+    """The id-only shortcut of DataProcessor (data dicts and epochs assembled from arrays) yields exactly what the
+    reference-shaped DataFrame route (generate_neg_df -> concat -> format_data_dict, DP:73-111,227-250,292-356,
+    408-444) yields: every key, dtype and value of the test / validation dicts, every batch of three epochs
+    including a ragged last batch, and the numpy generator afterwards."""
+    g = golden('sampler')
+    d = _write_sampler_dataset(g, str(tmp_path))
+    dl = DataLoader(path=str(tmp_path), dataset='s', label='label', sep=',')
+    model = _make_model(d, 's', dl.user_num, dl.item_num)
+    dl.drop_neg()
+    runs = []
+    for fast in (False, True):
+        np.random.seed(5)
+        dp = DataProcessor(dl, model, rank=1, test_neg_n=int(g['test_neg_n']))
+        dp.fast_ids_path = fast
+        te, va = dp.get_test_data(), dp.get_validation_data()
+        epochs = []
+        for ep in range(3):
+            data = dp.get_train_data(epoch=ep)
+            assert len(data['Y']) % 13 != 0                              # the last batch is ragged
+            epochs.append(dp.prepare_batches(data, 13, train=True))
+        runs.append((te, va, epochs, np.random.get_state()))
+    slow, fast = runs
+    for a, b in ((slow[0], fast[0]), (slow[1], fast[1])):
+        assert sorted(a.keys()) == sorted(b.keys())
+        for k in a:
+            assert np.asarray(a[k]).dtype == np.asarray(b[k]).dtype and np.array_equal(a[k], b[k]), k
+    for ea, eb in zip(slow[2], fast[2]):
+        assert len(ea) == len(eb)
+        for ba, bb in zip(ea, eb):
+            assert sorted(ba.keys()) == sorted(bb.keys())
+            for k in ba:
+                if torch.is_tensor(ba[k]):
+                    assert ba[k].dtype == bb[k].dtype and torch.equal(ba[k], bb[k]), k
+                else:
+                    assert np.array_equal(ba[k], bb[k]), k
+    assert np.array_equal(slow[3][1], fast[3][1]) and slow[3][2] == fast[3][2]
+
+
+@pytest.mark.parametrize('n', [1, 2, 257, 5000])
+def test_one_pass_shuffle_equals_replayed_shuffle(n):
+    """shuffle_in_unison_scary applies ONE permutation; the reference replays the generator state per array
+    (src/utils/utils.py:82-92).  Same arrays, same identity (in place), same generator state afterwards."""
+    rs = np.random.RandomState(n)
+    base = {'uid': rs.randint(0, 50, n), 'Y': rs.rand(n).astype(np.float32),
+            'X': rs.randint(0, 99, (n, 2)), 'sample_id': np.arange(n)}
+    ref = {k: v.copy() for k, v in base.items()}
+    np.random.seed(11)
+    state = np.random.get_state()
+    for k in ref:                                   # the reference's loop, literally
+        np.random.set_state(state)
+        np.random.shuffle(ref[k])
+    ref_state = np.random.get_state()
+    ours = {k: v.copy() for k, v in base.items()}
+    ids = {k: id(v) for k, v in ours.items()}
+    np.random.seed(11)
+    utils.shuffle_in_unison_scary(ours)
+    for k in ref:
+        assert np.array_equal(ref[k], ours[k]) and id(ours[k]) == ids[k], k
+    st = np.random.get_state()
+    assert np.array_equal(st[1], ref_state[1]) and st[2] == ref_state[2]
+    # arrays that alias each other or differ in length take the literal replay
+    np.random.seed(11)
+    x = np.arange(10)
+    odd = {'a': x, 'b': x[::-1], 'c': np.arange(4)}
+    utils.shuffle_in_unison_scary(odd)
