@@ -275,3 +275,32 @@ def test_one_pass_shuffle_equals_replayed_shuffle(n):
     x = np.arange(10)
     odd = {'a': x, 'b': x[::-1], 'c': np.arange(4)}
     utils.shuffle_in_unison_scary(odd)
+
+
+def test_history_grouping_equals_groupby_loop():
+    """group_user_interactions_df (src/utils/mining.py:18-29): same frame as the reference's per-group loop —
+    ascending uid, items in file order, non-positive labels dropped, users without positives absent."""
+    import pandas as pd
+    from dccf_b200.utils.mining import group_user_interactions_df
+    rs = np.random.RandomState(4)
+    df = pd.DataFrame({'uid': rs.randint(0, 40, 500), 'iid': rs.randint(0, 90, 500), 'label': rs.randint(0, 2, 500),
+                       'time': np.arange(500)})
+    uids, inters = [], []
+    for uid, group in df[df['label'] > 0].groupby('uid'):          # the reference's loop
+        uids.append(uid)
+        inters.append(','.join(str(i) for i in group['iid'].tolist()))
+    got = group_user_interactions_df(df, label='label', seq_sep=',')
+    assert got['uid'].tolist() == uids and got['iids'].tolist() == inters
+    assert list(got.columns) == ['uid', 'iids']
+    empty = group_user_interactions_df(df[df['label'] > 5], label='label')
+    assert len(empty) == 0 and list(empty.columns) == ['uid', 'iids']
+
+
+def test_data_order_is_recognised_from_addresses():
+    want = np.arange(100)
+    slices = [{'sample_id': want[a:a + 30]} for a in range(0, 100, 30)]
+    assert BaseRunner._slices_of(slices, want)
+    assert not BaseRunner._slices_of(slices[:-1], want)                       # incomplete
+    assert not BaseRunner._slices_of(slices[::-1], want)                      # out of order
+    assert not BaseRunner._slices_of([{'sample_id': want.copy()}], want)      # equal values, other memory
+    assert not BaseRunner._slices_of([{'sample_id': want[::2]}, {'sample_id': want[1::2]}], want)
