@@ -24,7 +24,7 @@ import os
 import numpy as np
 import torch
 
-from .. import kernels
+from .. import host_rng, kernels
 from .DMF import DMF
 
 
@@ -451,7 +451,7 @@ class DCCF(DMF):
         the generator is consumed in the same order as without the prefetch."""
         buf = torch.empty((n_pairs, self.sample_num), dtype=torch.int64, pin_memory=torch.cuda.is_available())
         if self.sample_num > 0 and n_pairs > 0:
-            torch.randint(self.item_num, (n_pairs, self.sample_num), out=buf)
+            host_rng.randint(self.item_num, (n_pairs, self.sample_num), out=buf)
         return buf
 
     def predict_many(self, feed_dicts, depth=2):
@@ -472,7 +472,7 @@ class DCCF(DMF):
                         q.put(None)
                         continue
                     buf = torch.empty((fd['X'].shape[0], S), dtype=torch.int64, pin_memory=pin)
-                    torch.randint(self.item_num, (fd['X'].shape[0], S), out=buf)
+                    host_rng.randint(self.item_num, (fd['X'].shape[0], S), out=buf)
                     q.put(buf)
             except BaseException as e:      # surface the failure in the consumer
                 q.put(e)

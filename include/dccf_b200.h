@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 26
+#define DCCF_ABI_VERSION 27
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -380,6 +380,16 @@ int dccf_sample_negatives(uint32_t* mt_key, int32_t* mt_pos, const int64_t* uids
                           int32_t train, int64_t item_num, int64_t n_users, const int64_t* train_off,
                           const int64_t* train_items, const int64_t* vt_off, const int64_t* vt_items,
                           int64_t* out_iid);
+
+/* ---- host side: exact replay of the confounder draw ------------------------------------------- */
+/* Replaces `torch.randint(item_num, size=(P, S))` of src/models/DCCF.py:72 (torch CPU generator, at::mt19937):
+ * out[k] = next_u32 % high for k = 0..n-1, the generator advanced in place exactly as torch would.  HOST pointers.
+ *   mt_state[624], *mt_left: words and `left_` counter of at::mt19937 as serialised by torch.get_rng_state()
+ *                            (CPUGeneratorImplStateLegacy: `state` at byte 24, one word per uint64; `left` at byte 8)
+ *   *mt_next:                receives the matching `next_` index (byte 16 of the same blob)
+ *   0 < high < 2^32; torch 2.11 itself takes this 32-bit path only for high < 2^28 (64-bit words above), which is
+ *   the range the Python binding routes here (dccf_b200/host_rng.py) */
+int dccf_confounder_draw(uint32_t* mt_state, int32_t* mt_left, int32_t* mt_next, int64_t high, int64_t n, int64_t* out);
 
 #ifdef __cplusplus
 }

@@ -304,3 +304,49 @@ def test_data_order_is_recognised_from_addresses():
     assert not BaseRunner._slices_of(slices[::-1], want)                      # out of order
     assert not BaseRunner._slices_of([{'sample_id': want.copy()}], want)      # equal values, other memory
     assert not BaseRunner._slices_of([{'sample_id': want[::2]}, {'sample_id': want[1::2]}], want)
+
+
+@pytest.mark.parametrize('item_num', [1, 2, 16000, 999983, (1 << 28) - 1])
+def test_confounder_draw_equals_torch_randint(item_num):
+    """dccf_confounder_draw replays `torch.randint(item_num, size=(P, S))` (src/models/DCCF.py:72) on the torch CPU
+    generator: the same ids AND the same generator afterwards (other consumers continue unchanged) — from a freshly
+    seeded generator, from mid-generation positions, across generation boundaries, interleaved with torch's own draws."""
+    from dccf_b200 import host_rng
+    assert host_rng.available()
+    torch.manual_seed(2019)
+    want = [torch.randint(item_num, (256, 10)), torch.randint(item_num, (16384, 10)), torch.rand(7),
+            torch.randint(item_num, (37, 10)), torch.randint(item_num, (1, 1)), torch.randn(5),
+            torch.randint(item_num, (624 * 3,))]
+    state_want = torch.get_rng_state()
+    torch.manual_seed(2019)
+    got = [host_rng.randint(item_num, (256, 10), min_draws=0), host_rng.randint(item_num, (16384, 10)), torch.rand(7),
+           host_rng.randint(item_num, (37, 10), min_draws=0), host_rng.randint(item_num, (1, 1), min_draws=0),
+           torch.randn(5), host_rng.randint(item_num, (624 * 3,), min_draws=0)]
+    for a, b in zip(want, got):
+        assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b)
+    assert torch.equal(state_want, torch.get_rng_state())
+
+
+def test_confounder_draw_leaves_other_cases_to_torch():
+    """Ranges where torch draws 64-bit words (>= 2^28), small draws and private generators still give torch's numbers."""
+    from dccf_b200 import host_rng
+    g1, g2 = torch.Generator(), torch.Generator()
+    g1.manual_seed(9)
+    g2.manual_seed(9)
+    for high, n in ((1 << 28, 20000), ((1 << 31) + 5, 20000), (16000, 50000), (16000, 3)):
+        assert torch.equal(torch.randint(high, (n,), generator=g1), host_rng.randint(high, (n,), generator=g2))
+    assert torch.equal(g1.get_state(), g2.get_state())
+
+
+def test_model_draws_confounders_like_the_reference(golden, tmp_path):
+    """DCCF.draw_confounders == the torch.randint call of DCCF.py:72, for a training batch and an evaluation batch."""
+    g = golden('train_f64')
+    d = str(tmp_path)
+    np.save(os.path.join(d, 'g_%s.npy' % SENT), g['feat'])
+    np.save(os.path.join(d, 'g.ips_expo_prob.npy'), g['expo'])
+    model = _make_model(d, 'g', 40, 50)
+    torch.manual_seed(4)
+    want = [torch.randint(50, (256, 10)), torch.randint(50, (16384, 10))]
+    torch.manual_seed(4)
+    got = [model.draw_confounders(256), model.draw_confounders(16384)]
+    assert all(torch.equal(a, b) for a, b in zip(want, got))
