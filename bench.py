@@ -153,14 +153,14 @@ def synth_eval_set(n_users, U, I, seed):
     return np.stack([uid, iid], 1).astype(np.int64), uid, iid, Y
 
 
-def build_model(U, I, device):
+def build_model(U, I, device, std=STD):
     from dccf_b200.models.DCCF import DCCF
     g = torch.Generator(device='cpu').manual_seed(SEED + 5)
     feat = torch.randn((I, F), generator=g) / (F ** 0.5)
     gd = torch.Generator(device=device).manual_seed(SEED + 6)
     expo = torch.rand((U, I), generator=gd, device=device)              # "random ips_expo_prob" (BASELINE.json)
     torch.manual_seed(SEED)
-    model = DCCF(path='', dataset='', sentence_model='', sample_num=S, attribute_num=A, std=STD, label_min=0,
+    model = DCCF(path='', dataset='', sentence_model='', sample_num=S, attribute_num=A, std=std, label_min=0,
                  label_max=1, feature_num=0, user_num=U, item_num=I, u_vector_size=D, i_vector_size=D, n_layers=1,
                  random_seed=SEED, model_path='/tmp/dccf_bench.pt', feature_embedding=feat, expo_prob=expo)
     model.apply(model.init_paras)                                         # N(0, 0.01) random-init weights
@@ -387,6 +387,96 @@ def bench_eval(model, n_users, warm_batches, world, rank, flush):
 
 
 # ------------------------------------------------------------------------------------------------
+# noise-free evaluation (--std 0): the gather scorer, the HBM / L2-bound regime of SURVEY.md §8d
+# ------------------------------------------------------------------------------------------------
+# algorithmic bytes per pair when the noise-free terms come from the projected tables: ids + confounder ids, user
+# row, PF row, Z PI rows, Z exposure values
+BYTES_PAIR_GATHER = 16 + 8 * S + 4 * D + 4 * D + 4 * D * Z + 4 * Z
+
+
+def noise_free_eval(U, I, n_users, dev):
+    """Same evaluation workload (n_users x 1001 candidates, batches of 16384 pairs, on-device ranking) for a model
+    with --std 0: scoring is dccf_score_gather.  Returns the object reported as `eval_noise_free`.  Runs in its own
+    process (see main): the kernel had not run on hardware when the round's GPU budget ended."""
+    from dccf_b200.models.BaseModel import group_candidates, rank_metrics_device
+    model = build_model(U, I, dev, std=0.0)
+    model.eval()
+    flush = L2Flusher(dev)
+    X, uid, iid, Y = synth_eval_set(n_users, U, I, SEED)
+    rows = X.shape[0]
+    bounds = [(a, min(rows, a + EVAL_BATCH)) for a in range(0, rows, EVAL_BATCH)]
+    _, cand, off = group_candidates(uid)
+    cand_d, off_d = torch.from_numpy(cand).to(dev), torch.from_numpy(off).to(dev)
+    Y_d, iid_d, X_d = torch.from_numpy(Y).to(dev), torch.from_numpy(iid).to(dev), torch.from_numpy(X).to(dev)
+    torch.manual_seed(SEED + 13)
+    si_d = torch.randint(I, size=(rows, S)).to(dev)
+
+    def fd(a, b):
+        return {'X': X_d[a:b], 'rank': 1, 'train': False, 'dropout': 0.0, 'sample_item': si_d[a:b]}
+
+    # parity of the first batch against the general FP32 scorer (the path validated against the reference)
+    model.use_gather_scorer = False
+    want = model.predict(fd(*bounds[0]))['prediction']
+    model.use_gather_scorer = True
+    got = model.predict(fd(*bounds[0]))['prediction']
+    torch.cuda.synchronize()
+    model.check_ids()
+    rel = float((got - want).abs().max() / want.abs().max())
+
+    def run():
+        preds, evs = [], []
+        for a, b in bounds:
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            preds.append(model.predict(fd(a, b))['prediction'])
+            e1.record()
+            evs.append((e0, e1))
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        sums = rank_metrics_device(torch.cat(preds), Y_d, iid_d, cand_d, off_d, 5).sum(dim=0)
+        r1.record()
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs), r0.elapsed_time(r1), sums.cpu().numpy()
+
+    for _ in range(3):
+        run()
+    score_ms, rank_ms, sums = run()
+    hbm_peak, _, peak_src = measured_peaks()
+    gbs = rows * BYTES_PAIR_GATHER / 1e9 / (score_ms / 1e3)
+    return {'metric': 'eval_users_per_s', 'value': n_users / ((score_ms + rank_ms) / 1e3), 'unit': 'users/s',
+            'config': 'same evaluation workload with --std 0 (no feature noise): dccf_score_gather + dccf_rank_eval',
+            'users': n_users, 'candidates_per_user': 1 + TEST_NEG_N, 'ms_per_batch': score_ms / len(bounds),
+            'rank_ms': rank_ms, 'max_rel_diff_vs_general_scorer': rel, 'parity_ok': bool(rel < 1e-5),
+            'roofline': {'kernel': 'k_gather_scores', 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                         'frac': gbs / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                         'bytes_per_pair': BYTES_PAIR_GATHER,
+                         'note': 'algorithmic bytes (ids, user row, PF row, Z PI rows, Z exposure values) / kernel time, L2 '
+                                 'flushed between batches; the two projected tables (2 x I x 256 B) are re-read from L2 once '
+                                 'warm, so the fraction is not capped at 1'},
+            'ndcg@5': float(sums[0] / n_users), 'recall@5': float(sums[3] / n_users),
+            'precision@5': float(sums[2] / n_users)}
+
+
+def noise_free_eval_subprocess(preset, n_users, timeout_s=300):
+    """Run the noise-free evaluation leg in a child process and return its object, or {'error': ...}: a fault in a
+    kernel that has never run on hardware must not cost the bench line of the paths that have."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--noise-free-eval-only', '--preset', preset, '--eval-users',
+           str(n_users)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        return {'error': 'timed out after %d s' % timeout_s}
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith('{'):
+            try:
+                return json.loads(ln)
+            except ValueError:
+                break
+    return {'error': 'rc=%d: %s' % (r.returncode, (r.stderr or r.stdout)[-400:])}
+
+
+# ------------------------------------------------------------------------------------------------
 # CPU arm: eager-PyTorch port of the reference path on the host cores (oracle/torch_port.py)
 # ------------------------------------------------------------------------------------------------
 def cpu_arm(U, I, X_all, budget_s, steps=None, warmup=1, eval_rows=4096):
@@ -440,6 +530,8 @@ def main():
     ap.add_argument('--eval-users', type=int, default=1024)
     ap.add_argument('--cpu-budget', type=float, default=12.0, help='seconds of CPU work for the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-noise-free-eval', action='store_true', help='skip the --std 0 evaluation leg (child process)')
+    ap.add_argument('--noise-free-eval-only', action='store_true', help='run only that leg and print its object')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     U, I = PRESETS[args.preset]
@@ -477,6 +569,9 @@ def main():
         raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    if args.noise_free_eval_only:
+        print(json.dumps(noise_free_eval(U, I, args.eval_users, dev)))
+        return
     if world > 1:
         if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
             os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: ONE JSON line
@@ -627,6 +722,8 @@ def main():
                                           'oracle/torch_port.py); eval sample %d users -> %.3f users/s'
                                           % (c['train_steps'], c['eval_users'], c['eval_users_per_s']),
                                 'eval_users_per_s': c['eval_users_per_s']}
+    if rank == 0 and world == 1 and not args.no_noise_free_eval:
+        line['eval_noise_free'] = noise_free_eval_subprocess(args.preset, args.eval_users)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

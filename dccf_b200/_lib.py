@@ -11,7 +11,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libdccf_b200.so')
-ABI_VERSION = 27
+ABI_VERSION = 28
 DIM = 64
 
 
@@ -73,6 +73,8 @@ _SIGNATURES = {
     'dccf_tc_prepare': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'dccf_score_fwd_tc': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, _P, _P, ctypes.POINTER(Expo), _P, _P,
                                          ctypes.c_int64, ctypes.POINTER(Rng), _P, _P, _P, _P, _P]),
+    'dccf_score_gather': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, _P, ctypes.POINTER(Expo), _P, _P, ctypes.c_int64,
+                                         _P, _P, _P]),
     'dccf_bwd_splits': (ctypes.c_int32, [ctypes.c_int64]),
     'dccf_bpr_bwd': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64,
                                     ctypes.POINTER(Rng), ctypes.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -115,6 +115,17 @@ def score_fwd_tc(dims, E_user, PI, PF, gB, expo, X, sample_item, rng, out_pred, 
     return out_pred
 
 
+def score_gather(dims, E_user, PI, PF, expo, X, sample_item, out_pred, err_flag=None):
+    """Noise-free scoring from the projected tables (dccf_score_gather): one gather kernel, no workspace."""
+    lib = _lib.load()
+    n_pairs = X.shape[0]
+    check(lib.dccf_score_gather(ctypes.byref(dims), ptr(E_user), ptr(PI), ptr(PF), ctypes.byref(expo), ptr(X),
+                                ptr(sample_item), n_pairs, ptr(out_pred), ptr(err_flag), stream_ptr()),
+          'dccf_score_gather')
+    LAUNCHES[0] += 1 if n_pairs > 0 else 0
+    return out_pred
+
+
 def bwd_splits(n_rows):
     return int(_lib.load().dccf_bwd_splits(int(n_rows)))
 

@@ -259,6 +259,10 @@ class DCCF(DMF):
     # generation), the forward loses 3 us to the 17 MB of extra stores beside the Adam sweep: off.
     reuse_noise_rows = os.environ.get('DCCF_REUSE_X', '0') != '0'
     tc_min_rows = 128 * 148
+    # noise-free inference (--std 0, dropout 0, no explicit noise / mask) as a pure gather over the projected item
+    # tables (dccf_score_gather) instead of the K = D + F contraction.  Written after round 1's GPU budget was spent:
+    # it stays OFF by default until its parity test (tests/test_gpu_zz_gather.py) has been seen green on a B200.
+    use_gather_scorer = os.environ.get('DCCF_GATHER', '0') != '0'
 
     def _tc_tables(self):
         """PI = E_item·W_i^T, PF = Feat·W_f^T + b and the split W_f operand, rebuilt when a parameter changed."""
@@ -287,6 +291,12 @@ class DCCF(DMF):
         dev = self.uid_embeddings.weight.device
         pred = torch.empty(P, dtype=torch.float32, device=dev)
         if P == 0:
+            return pred
+        if not save and self.use_gather_scorer and call['rng'].noise_mode == 0 and call['rng'].mask_mode == 0:
+            t = self._tc_tables()
+            kernels.score_gather(self._dims(), self.uid_embeddings.weight.data, t['PI'], t['PF'], self._expo(),
+                                 call['X'], call['sample_item'], pred, self._err_flag)
+            call['pred'] = pred
             return pred
         ws_rows = self._buf('ws_rows', (N,), torch.float32)
         if not save and self.use_tensor_cores and call['rng'].noise_mode != 0 and \

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 27
+#define DCCF_ABI_VERSION 28
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -126,6 +126,17 @@ int dccf_score_fwd_tc(const dccf_dims* dims, const float* E_user, const float* P
                       const float* gB, const dccf_expo* expo, const int64_t* X, const int64_t* sample_item,
                       int64_t n_pairs, const dccf_rng* rng, float* out_pred, float* ws_rows, float* dbg_pre,
                       int32_t* err_flag, void* stream);
+
+/* ---- (a)+(b), gather variant for noise-free scoring ------------------------------------------ */
+/* src/models/DCCF.py:74-100 when --std 0 and dropout 0 (evaluation of a model trained without feature noise; the
+ * parity configuration): the attribute copies coincide and the predictor input has no per-row random part, so
+ *   pred[p] = sum_z softmax_z(expo[u_p, item(p,z)]) · < E_user[u_p], relu(PI[item(p,z)] + PF[i_p]) >
+ * with the two projected tables of dccf_tc_prepare — Z + 2 row gathers per pair instead of a contraction over the
+ * D + F inputs: the HBM / L2-bound regime of the scorer.  No workspace, no random inputs.
+ *   out_pred [P] */
+int dccf_score_gather(const dccf_dims* dims, const float* E_user, const float* PI, const float* PF,
+                      const dccf_expo* expo, const int64_t* X, const int64_t* sample_item, int64_t n_pairs,
+                      float* out_pred, int32_t* err_flag, void* stream);
 
 /* ---- (c) part 1: pairwise loss forward + full backward ---------------------------------- */
 /* Replaces DCCF.forward lines 116-125 (src/models/DCCF.py) + autograd backward

@@ -42,6 +42,20 @@ def test_argument_errors_are_reported_without_a_gpu(lib_path):
     rc = lib.dccf_noise_fill(None, 4, 768, 0.1, 1, 1, 0, None)
     assert rc == -1 and b'null output' in lib.dccf_last_error()
     assert lib.dccf_bwd_splits(5632) >= 1
+    rc = lib.dccf_score_gather(None, None, None, None, None, None, None, 4, None, None, None)
+    assert rc == -1 and b'dccf_score_gather' in lib.dccf_last_error()
+    dims = _lib.Dims(n_users=4, n_items=4, dim=32, feat_dim=64, n_samples=1, n_attr=1)
+    expo = _lib.Expo(mode=0)
+    rc = lib.dccf_score_gather(ctypes.byref(dims), None, None, None, ctypes.byref(expo), None, None, 4, None, None, None)
+    assert rc == -1 and b'dim=32' in lib.dccf_last_error()
+    state = (ctypes.c_uint32 * 624)()
+    left, nxt = ctypes.c_int32(0), ctypes.c_int32(0)
+    out = (ctypes.c_int64 * 4)()
+    rc = lib.dccf_confounder_draw(state, ctypes.byref(left), ctypes.byref(nxt), 10, 4, out)
+    assert rc == -1 and b'corrupt generator state' in lib.dccf_last_error()
+    left.value = 1
+    assert lib.dccf_confounder_draw(state, ctypes.byref(left), ctypes.byref(nxt), 0, 4, out) == -1
+    assert lib.dccf_confounder_draw(state, ctypes.byref(left), ctypes.byref(nxt), 10, 0, None) == 0
 
 
 def test_sass_is_sm100a(lib_path):

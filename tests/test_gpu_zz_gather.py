@@ -1,0 +1,148 @@
+"""Parity of the noise-free gather scorer (dccf_score_gather, csrc/gather_scores.cu) with the reference fixture, the
+oracle and the general FP32 scorer.  Needs a GPU.
+
+The kernel was written after round 1's GPU budget was spent, so its first execution on a B200 is the round-end run of
+this file.  Two precautions follow from that: the cases run in a CHILD process (a faulting kernel poisons the CUDA
+context of the process that launched it — it must not take the rest of the suite down with it), and they are
+`xfail(strict=False)`: XPASS in the summary = seen green on hardware, after which the marker goes and
+`DCCF.use_gather_scorer` becomes the default for noise-free inference.  The product default is OFF until then."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+CASES = ['reference_fixture', 'oracle_default_shape', 'oracle_ragged_many_slots', 'oracle_no_confounders',
+         'oracle_ipsmf_exposure', 'equals_general_scorer_eval_batch', 'out_of_range_ids']
+
+
+@pytest.fixture(scope='module')
+def worker_output():
+    """All cases in ONE child process (one torch import, one CUDA context); each prints `GATHER_OK <case>` or
+    `GATHER_FAIL <case>: <why>`.  A hard fault ends the child: the cases after it then report 'not reached'."""
+    r = subprocess.run([sys.executable, os.path.abspath(__file__)] + CASES, capture_output=True, text=True, timeout=900,
+                       cwd=ROOT)
+    return r.returncode, r.stdout, r.stderr
+
+
+@pytest.mark.xfail(strict=False, reason='first executed on a GPU by the round-end run (written after the GPU budget '
+                                        'of round 1 was spent); XPASS = verified')
+@pytest.mark.parametrize('case', CASES)
+def test_gather_scorer(worker_output, case):
+    rc, out, err = worker_output
+    failed = [ln for ln in out.splitlines() if ln.startswith('GATHER_FAIL ' + case)]
+    assert not failed, failed[0]
+    assert 'GATHER_OK ' + case in out, 'not reached (child rc=%d): %s' % (rc, (err or out)[-2000:])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# worker side (python tests/test_gpu_zz_gather.py <case>)
+# ---------------------------------------------------------------------------------------------------------
+def _run(case):
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from conftest import golden_params, rel_err, GOLDEN
+    from oracle import dccf_oracle as O
+    from test_gpu_parity import make_model, random_problem
+
+    def fd_of(X, si):
+        return {'X': torch.from_numpy(X).cuda(), 'rank': 1, 'train': False, 'dropout': 0.0,
+                'sample_item': torch.from_numpy(si)}
+
+    def gather_predict(model, X, si):
+        from dccf_b200 import kernels
+        model.use_gather_scorer = True
+        calls, orig = [], kernels.score_gather
+        kernels.score_gather = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+        try:
+            out = model.predict(fd_of(X, si))['prediction']
+        finally:
+            kernels.score_gather = orig
+        torch.cuda.synchronize()
+        model.check_ids()
+        assert len(calls) == (1 if len(X) else 0)          # the gather kernel scored the batch, not the general scorer
+        return out.cpu().numpy()
+
+    if case == 'reference_fixture':
+        # the reference's own predictions with --std 0 --dropout 0 and A = 3 (tests/golden/train_nodrop.npz)
+        g = np.load(os.path.join(GOLDEN, 'train_nodrop.npz'), allow_pickle=False)
+        assert float(g['std']) == 0.0
+        model = make_model(golden_params(g, 'final_'), int(g['S']), int(g['A']), 0.0)
+        got = gather_predict(model, g['eval_X'], g['eval_sample_item'])               # ragged: 37 pairs
+        assert rel_err(got, g['eval_pred']) < 1e-5
+        model = make_model(golden_params(g), int(g['S']), int(g['A']), 0.0)
+        got = gather_predict(model, g['X_0'], g['sample_item_0'])
+        assert rel_err(got, g['pred_0']) < 1e-5
+    elif case in ('oracle_default_shape', 'oracle_ragged_many_slots', 'oracle_no_confounders'):
+        U, I, F, P, S, A = {'oracle_default_shape': (300, 500, 768, 1001, 10, 2),
+                            'oracle_ragged_many_slots': (50, 70, 128, 37, 40, 1),      # Z = 41: three slot chunks
+                            'oracle_no_confounders': (20, 30, 64, 3, 0, 2)}[case]
+        params, X, si, _, _ = random_problem(21, U, I, F, P, S, A, 0.0, 0.0)
+        model = make_model(params, S, A, 0.0)
+        ref = O.predict(params, X, si, None, None, A, dtype=np.float64)
+        got = gather_predict(model, X, si)
+        assert got.shape == (P,) and rel_err(got, ref['pred']) < 1e-5
+        one = gather_predict(model, X[:1], si[:1])                                      # a single pair
+        assert rel_err(one, ref['pred'][:1]) < 1e-5
+    elif case == 'oracle_ipsmf_exposure':
+        from dccf_b200 import synth
+        U, I, F, P, S, A = 80, 120, 64, 64, 10, 2
+        params, X, si, _, _ = random_problem(7, U, I, F, P, S, A, 0.0, 0.0)
+        fac = synth.make_ipsmf_factors(U, I, seed=3)
+        model = make_model(params, S, A, 0.0, expo_factors=fac)
+        ref = O.predict(params, X, si, None, None, A, dtype=np.float64, expo=fac)
+        assert rel_err(gather_predict(model, X, si), ref['pred']) < 1e-5
+    elif case == 'equals_general_scorer_eval_batch':
+        # a full evaluation batch (16 384 pairs, 1 001 candidates per user) against the general FP32 kernel
+        U, I, F, S, A = 500, 3000, 768, 10, 2
+        params, _, _, _, _ = random_problem(3, U, I, F, 2, S, A, 0.0, 0.0)
+        rs = np.random.RandomState(8)
+        P = 16384
+        X = np.stack([np.repeat(np.arange(U), 1001)[:P], rs.randint(0, I, P)], 1).astype(np.int64)
+        si = rs.randint(0, I, (P, S)).astype(np.int64)
+        model = make_model(params, S, A, 0.0)
+        model.use_gather_scorer = False
+        want = model.predict(fd_of(X, si))['prediction'].cpu().numpy()
+        got = gather_predict(model, X, si)
+        assert rel_err(got, want) < 1e-5
+        # after a parameter update the tables are rebuilt
+        with torch.no_grad():
+            model.mlp[0].weight.mul_(1.5)
+            model.iid_embeddings.weight.add_(0.01)
+        model.use_gather_scorer = False
+        want2 = model.predict(fd_of(X, si))['prediction'].cpu().numpy()
+        got2 = gather_predict(model, X, si)
+        assert rel_err(got2, want2) < 1e-5 and rel_err(got2, want) > 1e-3
+    elif case == 'out_of_range_ids':
+        params, X, si, _, _ = random_problem(4, 40, 60, 64, 10, 3, 1, 0.0, 0.0)
+        model = make_model(params, 3, 1, 0.0)
+        model.use_gather_scorer = True
+        bad = si.copy()
+        bad[2, 1] = 60
+        model.predict(fd_of(X, bad))
+        try:
+            model.check_ids()
+        except IndexError:
+            pass
+        else:
+            raise AssertionError('an item id outside the table must raise')
+        assert gather_predict(model, X[:0], si[:0]).shape == (0,)                       # empty batch
+    else:
+        raise SystemExit('unknown case ' + case)
+    print('GATHER_OK ' + case)
+
+
+if __name__ == '__main__':
+    import traceback
+    sys.path.insert(0, ROOT)
+    for name in sys.argv[1:]:
+        try:
+            _run(name)
+        except Exception as exc:        # noqa: BLE001 — reported per case; a sticky CUDA error fails the later ones too
+            traceback.print_exc()
+            print('GATHER_FAIL %s: %s' % (name, str(exc).splitlines()[0][:300] if str(exc) else type(exc).__name__))
