@@ -1,5 +1,7 @@
-"""Parity of the noise-free gather scorer (dccf_score_gather, csrc/gather_scores.cu) with the reference fixture, the
-oracle and the general FP32 scorer.  Needs a GPU.
+"""Parity of the two inference paths added after round 1's GPU work: the noise-free gather scorer (dccf_score_gather,
+csrc/gather_scores.cu) against the reference fixture, the oracle and the general FP32 scorer; and evaluation noise
+drawn in the 64-d image of W_f (DCCF.eval_noise = 'projected') against the reference formula on the equivalent 768-d
+noise tensor.  Needs a GPU.
 
 The kernel was written after round 1's GPU budget was spent, so its first execution on a B200 is the round-end run of
 this file.  Two precautions follow from that: the cases run in a CHILD process (a faulting kernel poisons the CUDA
@@ -18,7 +20,8 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 CASES = ['reference_fixture', 'oracle_default_shape', 'oracle_ragged_many_slots', 'oracle_no_confounders',
-         'oracle_ipsmf_exposure', 'equals_general_scorer_eval_batch', 'out_of_range_ids']
+         'oracle_ipsmf_exposure', 'equals_general_scorer_eval_batch', 'out_of_range_ids',
+         'projected_noise_equals_reference_formula', 'projected_noise_same_distribution']
 
 
 @pytest.fixture(scope='module')
@@ -132,6 +135,54 @@ def _run(case):
         else:
             raise AssertionError('an item id outside the table must raise')
         assert gather_predict(model, X[:0], si[:0]).shape == (0,)                       # empty batch
+    elif case == 'projected_noise_equals_reference_formula':
+        # eval_noise = 'projected' draws g ~ N(0, std^2 I_64) per row (the library's Philox stream, materialised here by
+        # dccf_noise_fill for the same seed / offset) and adds M·g to the pre-activation, M·M^T = W_f·W_f^T.  The same
+        # prediction must come out of the REFERENCE formula (oracle, float64) fed the 768-d noise tensor
+        # eps = W_f^+ · M · g  (W_f^+ the pseudo-inverse, so that W_f·eps = M·g).
+        from dccf_b200 import kernels
+        U, I, F, P, S, A, std = 200, 300, 768, 300, 10, 2, 0.1
+        params, X, si, _, _ = random_problem(31, U, I, F, P, S, A, 0.0, 0.0)
+        model = make_model(params, S, A, std, seed=77)
+        model.eval_noise = 'projected'
+        N = P * (S + 1) * A
+        model._rng_offset = 10                                  # the call below uses offset 11
+        got = model.predict(dict(fd_of(X, si), force_tc=True))['prediction'].cpu().numpy()
+        model.check_ids()
+        g = torch.empty((N, 64), device='cuda')
+        kernels.noise_fill(g, std, 77, 11)
+        g = g.cpu().numpy().astype(np.float64)
+        Wf = params['W'][:, 64:].astype(np.float64)
+        M = model.projection_factor().numpy()
+        assert np.abs(M @ M.T - Wf @ Wf.T).max() < 1e-12 * np.abs(Wf @ Wf.T).max() + 1e-18
+        pinv = Wf.T @ np.linalg.inv(Wf @ Wf.T)                  # [768, 64]
+        eps = g @ M.T @ pinv.T                                  # [N, 768]:  W_f · eps_r = M · g_r
+        ref = O.predict(params, X, si, eps, None, A, dtype=np.float64)
+        assert rel_err(got, ref['pred']) < 1e-5
+        # explicit noise tensors keep the exact formulation whatever eval_noise says
+        noise = (np.random.RandomState(1).standard_normal((N, F)) * std).astype(np.float32)
+        fd = dict(fd_of(X, si), force_tc=True, noise=torch.from_numpy(noise))
+        ref = O.predict(params, X, si, noise, None, A, dtype=np.float64)
+        assert rel_err(model.predict(fd)['prediction'].cpu().numpy(), ref['pred']) < 1e-5
+    elif case == 'projected_noise_same_distribution':
+        # exact and projected draws are different random numbers with the same law: per-pair mean and variance of the
+        # prediction over 64 independent calls agree within sampling error (averaged over 2 048 pairs)
+        U, I, F, P, S, A, std = 300, 500, 768, 2048, 10, 2, 0.3
+        params, X, si, _, _ = random_problem(9, U, I, F, P, S, A, 0.0, 0.0)
+        params['W'] = (params['W'] * 4).astype(np.float32)       # make the noise term matter
+        model = make_model(params, S, A, std)
+        stats = {}
+        for mode in ('exact', 'projected'):
+            model.eval_noise = mode
+            draws = torch.stack([model.predict(dict(fd_of(X, si), force_tc=True))['prediction'] for _ in range(64)])
+            stats[mode] = (draws.mean(0).double().cpu().numpy(), draws.var(0).double().cpu().numpy())
+        mean_e, var_e = stats['exact']
+        mean_p, var_p = stats['projected']
+        assert var_e.mean() > 0 and var_p.mean() > 0
+        assert abs(var_p.mean() / var_e.mean() - 1.0) < 0.05                       # 64 x 2048 samples: ~1 % noise
+        # per-pair means differ by sampling noise only: |diff| ~ sqrt(2 var / 64)
+        zscore = (mean_e - mean_p) / np.sqrt((var_e + var_p) / 64 + 1e-30)
+        assert abs(zscore.mean()) < 0.2 and 0.8 < zscore.std() < 1.2
     else:
         raise SystemExit('unknown case ' + case)
     print('GATHER_OK ' + case)

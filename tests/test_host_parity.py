@@ -350,3 +350,28 @@ def test_model_draws_confounders_like_the_reference(golden, tmp_path):
     torch.manual_seed(4)
     got = [model.draw_confounders(256), model.draw_confounders(16384)]
     assert all(torch.equal(a, b) for a, b in zip(want, got))
+
+
+@pytest.mark.parametrize('F,degenerate', [(768, False), (64, False), (128, True)])
+def test_projection_factor_reproduces_the_noise_covariance(golden, tmp_path, F, degenerate):
+    """DCCF.projection_factor: M with M·M^T = W_f·W_f^T, so that M·g (g ~ N(0, std^2 I_64)) is distributed like the
+    reference's W_f·eps (eps ~ N(0, std^2 I_F), src/models/DCCF.py:87-92) — also when W_f has deficient rank."""
+    d = str(tmp_path)
+    rs = np.random.RandomState(F)
+    np.save(os.path.join(d, 'g_%s.npy' % SENT), rs.standard_normal((50, F)).astype(np.float32))
+    np.save(os.path.join(d, 'g.ips_expo_prob.npy'), rs.random_sample((40, 50)).astype(np.float32))
+    model = _make_model(d, 'g', 40, 50)
+    with torch.no_grad():
+        model.mlp[0].weight.copy_(torch.from_numpy(rs.standard_normal((64, 64 + F)).astype(np.float32)))
+        if degenerate:
+            model.mlp[0].weight[5] = model.mlp[0].weight[3]           # two equal rows: rank 63
+            model.mlp[0].weight[9, 64:] = 0.0                         # a row of W_f that is zero
+    Wf = model.mlp[0].weight.detach()[:, 64:].double().numpy()
+    M = model.projection_factor().numpy()
+    cov = Wf @ Wf.T
+    assert M.shape == (64, 64) and np.isfinite(M).all()
+    assert np.abs(M @ M.T - cov).max() < 1e-10 * np.abs(cov).max()
+    # sampled check of the law itself: cov(M g) == cov(W_f eps) == std^2 W_f W_f^T
+    g = rs.standard_normal((200000, 64)) * 0.1
+    emp = (g @ M.T).T @ (g @ M.T) / len(g)
+    assert np.abs(emp - 0.01 * cov).max() < 0.02 * 0.01 * np.abs(cov).max()
