@@ -555,6 +555,28 @@ def projected_noise_eval(U, I, n_users, dev):
     stats = {'mean_exact': float(pred_e.mean()), 'mean_projected': float(pred_p.mean()),
              'std_exact': float(pred_e.std()), 'std_projected': float(pred_p.std()),
              'rowwise_diff_std': float((pred_e - pred_p).std())}
+    # end to end through the public API (predict_many from pinned host ids, metric sums read back): with the host
+    # draw of the confounders (torch CPU generator replayed by dccf_confounder_draw, shipped per batch) and with the
+    # generator continued on the device (DCCF.device_confounders)
+    X_pin = torch.from_numpy(X).pin_memory()
+
+    def from_host():
+        fds = [{'X': X_pin[a:b].to(dev, non_blocking=True), 'rank': 1, 'train': False, 'dropout': 0.0} for a, b in bounds]
+        pred = torch.cat(model.predict_many(fds))
+        return rank_metrics_device(pred, Y_d, iid_d, cand_d, off_d, 5).sum(dim=0).cpu().numpy()
+
+    e2e = {}
+    for name, flag in (('host_draw', False), ('device_draw', True)):
+        try:
+            model.device_confounders = flag
+            from_host()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            from_host()
+            e2e[name] = {'value': n_users / (time.perf_counter() - t0), 'unit': 'users/s'}
+        except Exception as exc:        # noqa: BLE001
+            e2e[name] = {'error': '%s: %s' % (type(exc).__name__, str(exc)[:200])}
+    model.device_confounders = False
     _, bf16_peak, peak_src = measured_peaks()
     tf32_peak = bf16_peak / 2.0
     tflop = 3 * rows * R * 2.0 * D * D / 1e12
@@ -565,7 +587,7 @@ def projected_noise_eval(U, I, n_users, dev):
                        if graph_total_ms is not None else 'eager loop, CUDA events per batch, L2 flushed between batches'),
             'users': n_users, 'candidates_per_user': 1 + TEST_NEG_N, 'ms_per_batch': score_ms / len(bounds),
             'eager_ms_per_batch': eager_score_ms / len(bounds), 'pass_ms': total_ms,
-            'rank_ms': rank_ms, 'prediction_stats': stats,
+            'rank_ms': rank_ms, 'prediction_stats': stats, 'e2e': e2e,
             'roofline': {'kernel': 'k_row_scores_tc (64-wide operand)', 'bound': 'tensor',
                          'achieved': tflop / (score_ms / 1e3), 'peak': tf32_peak, 'unit': 'TFLOP/s',
                          'frac': tflop / (score_ms / 1e3) / tf32_peak, 'traffic': None,

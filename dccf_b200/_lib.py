@@ -11,7 +11,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libdccf_b200.so')
-ABI_VERSION = 28
+ABI_VERSION = 29
 DIM = 64
 
 
@@ -125,6 +125,7 @@ _SIGNATURES = {
     'dccf_sample_negatives': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                              ctypes.c_int64, _P, _P, _P, _P, _P]),
     'dccf_confounder_draw': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, ctypes.c_int64, _P]),
+    'dccf_confounder_draw_dev': (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int64, _P, _P]),
     'dccf_rank_eval': (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, _P, _P]),
 }
 

@@ -95,3 +95,55 @@ def randint(high, shape, out=None, generator=None, min_draws=None):
     if generator is not None:
         return torch.randint(high, shape, out=out, generator=generator)
     return torch.randint(high, shape, out=out)
+
+
+class DeviceStream(object):
+    """torch's CPU generator continued on the device for the length of an evaluation pass (dccf_confounder_draw_dev):
+    the generator's words are uploaded once, every `draw` is one kernel that writes the ids straight into device memory
+    (same numbers torch.randint would have produced on the host, in the same order), and `finish` puts the advanced
+    state back into the torch generator.  Between construction and `finish` nothing else may draw from that generator."""
+
+    def __init__(self, device, generator=None):
+        self.generator = generator
+        self.blob = generator.get_state() if generator is not None else torch.get_rng_state()
+        if self.blob.numel() != _STATE_BYTES:
+            raise RuntimeError('unexpected torch CPU generator state (%d bytes)' % self.blob.numel())
+        raw = self.blob.numpy()
+        left = int(raw[_OFF_LEFT:_OFF_LEFT + 4].view(np.int32)[0])
+        if not 1 <= left <= _N_WORDS:
+            raise RuntimeError('unexpected torch CPU generator state (left = %d)' % left)
+        host = np.empty(_N_WORDS + 1, dtype=np.uint32)
+        host[:_N_WORDS] = raw[_OFF_WORDS:_OFF_WORDS + 8 * _N_WORDS].view(np.uint64)
+        host[_N_WORDS] = _N_WORDS + 1 - left              # index of the next unread word
+        self.state = torch.from_numpy(host.view(np.int32)).to(device)
+        self.open = True
+
+    def draw(self, high, shape):
+        """int64 CUDA tensor == torch.randint(high, shape) on the host generator (0 < high < 2^28)."""
+        from . import _lib
+        if not self.open:
+            raise RuntimeError('DeviceStream used after finish()')
+        if not 0 < high < _MAX_HIGH:
+            raise ValueError('device confounder draw needs 0 < high < 2^28 (torch draws 64-bit words above)')
+        out = torch.empty(tuple(int(x) for x in shape), dtype=torch.int64, device=self.state.device)
+        if out.numel():
+            lib = _lib.load()
+            _lib.check(lib.dccf_confounder_draw_dev(_lib.ptr(self.state), int(high), out.numel(), _lib.ptr(out),
+                                                    _lib.stream_ptr()), 'dccf_confounder_draw_dev')
+        return out
+
+    def finish(self):
+        """Write the advanced state back into the torch generator (one small device->host copy, synchronising)."""
+        if not self.open:
+            return
+        self.open = False
+        host = self.state.cpu().numpy().view(np.uint32)
+        pos = int(host[_N_WORDS])
+        raw = self.blob.numpy()
+        raw[_OFF_WORDS:_OFF_WORDS + 8 * _N_WORDS].view(np.uint64)[:] = host[:_N_WORDS]
+        raw[_OFF_LEFT:_OFF_LEFT + 4].view(np.int32)[0] = _N_WORDS + 1 - pos
+        raw[_OFF_NEXT:_OFF_NEXT + 8].view(np.uint64)[0] = pos
+        if self.generator is not None:
+            self.generator.set_state(self.blob)
+        else:
+            torch.set_rng_state(self.blob)

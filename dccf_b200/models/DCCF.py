@@ -272,6 +272,9 @@ class DCCF(DMF):
     # Explicit noise tensors (the parity path) always take the exact formulation.  Default 'exact'; 'projected' is
     # opt-in (also: DCCF_EVAL_NOISE=projected) and was first run on hardware by the round-end run of round 1.
     eval_noise = os.environ.get('DCCF_EVAL_NOISE', 'exact')
+    # predict_many: draw the confounders of an evaluation pass on the device (k_confounder_draw continues torch's CPU
+    # generator there; bit-identical ids, no per-batch host draw or host->device copy).  Opt-in until seen on hardware.
+    device_confounders = os.environ.get('DCCF_DEVICE_DRAW', '0') != '0'
 
     def _tc_tables(self):
         """PI = E_item·W_i^T, PF = Feat·W_f^T + b and the split W_f operand, rebuilt when a parameter changed."""
@@ -512,6 +515,22 @@ class DCCF(DMF):
         import queue
         import threading
         S = self.sample_num
+        if self.device_confounders and S > 0 and self.item_num < (1 << 28) and host_rng.available() and \
+                any('sample_item' not in fd for fd in feed_dicts):
+            # the torch CPU generator continued on the device for the length of the pass: every batch's draw is one
+            # kernel writing straight into device memory (host_rng.DeviceStream), same ids in the same order
+            self._check_ready()
+            stream = host_rng.DeviceStream(self.uid_embeddings.weight.device)
+            outs = []
+            try:
+                for fd in feed_dicts:
+                    if 'sample_item' not in fd:
+                        fd = dict(fd)
+                        fd['sample_item'] = stream.draw(self.item_num, (fd['X'].shape[0], S))
+                    outs.append(self.predict(fd)['prediction'])
+            finally:
+                stream.finish()
+            return outs
         pin = torch.cuda.is_available()
         q = queue.Queue(maxsize=max(1, depth))
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 28
+#define DCCF_ABI_VERSION 29
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -401,6 +401,11 @@ int dccf_sample_negatives(uint32_t* mt_key, int32_t* mt_pos, const int64_t* uids
  *   0 < high < 2^32; torch 2.11 itself takes this 32-bit path only for high < 2^28 (64-bit words above), which is
  *   the range the Python binding routes here (dccf_b200/host_rng.py) */
 int dccf_confounder_draw(uint32_t* mt_state, int32_t* mt_left, int32_t* mt_next, int64_t high, int64_t n, int64_t* out);
+/* The same stream continued on the device: state_dev = uint32[625] in DEVICE memory (the 624 words + the index of the
+ * next unread word, 624 = regenerate first; i.e. 625 - left), advanced in place by one single-CTA kernel per call
+ * (three barriers per generation of 624 words); out_dev [n] int64 in device memory — the scorer's sample_item buffer.
+ * An evaluation pass uploads torch's generator once and reads it back once. */
+int dccf_confounder_draw_dev(uint32_t* state_dev, int64_t high, int64_t n, int64_t* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,8 @@ pytestmark = pytest.mark.gpu
 
 CASES = ['reference_fixture', 'oracle_default_shape', 'oracle_ragged_many_slots', 'oracle_no_confounders',
          'oracle_ipsmf_exposure', 'equals_general_scorer_eval_batch', 'out_of_range_ids',
-         'projected_noise_equals_reference_formula', 'projected_noise_same_distribution']
+         'projected_noise_equals_reference_formula', 'projected_noise_same_distribution',
+         'device_confounder_draw_equals_torch_randint', 'predict_many_with_device_confounders']
 
 
 @pytest.fixture(scope='module')
@@ -183,6 +184,46 @@ def _run(case):
         # per-pair means differ by sampling noise only: |diff| ~ sqrt(2 var / 64)
         zscore = (mean_e - mean_p) / np.sqrt((var_e + var_p) / 64 + 1e-30)
         assert abs(zscore.mean()) < 0.2 and 0.8 < zscore.std() < 1.2
+    elif case == 'device_confounder_draw_equals_torch_randint':
+        # k_confounder_draw continues torch's CPU generator on the device: the ids torch.randint would have produced,
+        # bit for bit, across calls of awkward sizes, and torch continues correctly from the state written back
+        from dccf_b200 import host_rng
+        for seed, high in ((2019, 16000), (3, 1), (11, 999983), (5, (1 << 28) - 1)):
+            a, b = torch.Generator(), torch.Generator()
+            a.manual_seed(seed)
+            b.manual_seed(seed)
+            if seed == 11:                                   # start in the middle of a generation
+                torch.randint(10, (100,), generator=a)
+                torch.randint(10, (100,), generator=b)
+            stream = host_rng.DeviceStream(torch.device('cuda'), generator=b)
+            for shape in ((7,), (16384, 10), (0, 10), (3, 1), (624,), (1, 623), (37, 10)):
+                want = torch.randint(high, shape, generator=a)
+                got = stream.draw(high, shape)
+                assert got.dtype == torch.int64 and tuple(got.shape) == tuple(shape)
+                assert torch.equal(got.cpu(), want), (seed, high, shape)
+            stream.finish()
+            assert torch.equal(torch.randint(1 << 20, (1000,), generator=a), torch.randint(1 << 20, (1000,), generator=b))
+            assert torch.equal(torch.randn(4, generator=a), torch.randn(4, generator=b))
+    elif case == 'predict_many_with_device_confounders':
+        # an evaluation pass with the confounders drawn on the device == the same pass with host draws: identical
+        # predictions (same ids, same noise offsets) and an identical torch generator afterwards
+        U, I, F, S, A, std = 200, 300, 128, 10, 2, 0.1
+        params, _, _, _, _ = random_problem(13, U, I, F, 2, S, A, 0.0, 0.0)
+        rs = np.random.RandomState(2)
+        sizes = [4096, 4096, 333]
+        Xs = [np.stack([rs.randint(0, U, n), rs.randint(0, I, n)], 1).astype(np.int64) for n in sizes]
+        results = []
+        for device_draw in (False, True):
+            model = make_model(params, S, A, std)
+            model.device_confounders = device_draw
+            torch.manual_seed(99)
+            fds = [{'X': torch.from_numpy(x).cuda(), 'rank': 1, 'train': False, 'dropout': 0.0} for x in Xs]
+            outs = [o.cpu().numpy() for o in model.predict_many(fds)]
+            model.check_ids()
+            results.append((outs, torch.get_rng_state().clone(), torch.randint(1 << 20, (50,))))
+        for a, b in zip(results[0][0], results[1][0]):
+            assert np.array_equal(a, b)
+        assert torch.equal(results[0][2], results[1][2])
     else:
         raise SystemExit('unknown case ' + case)
     print('GATHER_OK ' + case)

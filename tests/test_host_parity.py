@@ -375,3 +375,38 @@ def test_projection_factor_reproduces_the_noise_covariance(golden, tmp_path, F, 
     g = rs.standard_normal((200000, 64)) * 0.1
     emp = (g @ M.T).T @ (g @ M.T) / len(g)
     assert np.abs(emp - 0.01 * cov).max() < 0.02 * 0.01 * np.abs(cov).max()
+
+
+def test_device_confounder_schedule_emulated(tmp_path):
+    """k_confounder_draw (MT19937 continued on the device, three barrier-separated phases per generation) cannot run
+    here, but its per-phase functions are plain C++ (dccf_b200/csrc/mt19937.cuh): tests/mt_emulate.cpp executes them
+    for every thread of the CTA in forward, backward and shuffled order and compares ids, final words and position with
+    the textbook sequential generator over 400 random states / positions / counts / ranges."""
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    gxx = shutil.which('g++')
+    if gxx is None:
+        pytest.skip('g++ not available')
+    exe = str(tmp_path / 'mt_emulate')
+    subprocess.run([gxx, '-O2', '-std=c++17', '-o', exe, os.path.join(ROOT, 'tests', 'mt_emulate.cpp')], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and 'MT_EMULATION_OK' in r.stdout, r.stdout + r.stderr
+
+
+def test_device_stream_state_round_trip_without_draws():
+    """host_rng.DeviceStream packs torch's generator as [624 words | next unread index] and restores it: with no draw in
+    between the generator is exactly where it was (checked on a CPU 'device'; the kernel itself needs a GPU)."""
+    from dccf_b200 import host_rng
+    for prep in (lambda g: None, lambda g: torch.randint(50, (1000,), generator=g), lambda g: torch.randn(3, generator=g)):
+        g1, g2 = torch.Generator(), torch.Generator()
+        g1.manual_seed(5)
+        g2.manual_seed(5)
+        prep(g1)
+        prep(g2)
+        s = host_rng.DeviceStream('cpu', generator=g2)
+        packed = s.state.numpy().view(np.uint32)
+        assert packed.shape == (625,) and 0 <= int(packed[624]) <= 624
+        s.finish()
+        assert torch.equal(torch.randint(1 << 20, (700,), generator=g1), torch.randint(1 << 20, (700,), generator=g2))
+        assert torch.equal(torch.randn(5, generator=g1), torch.randn(5, generator=g2))
