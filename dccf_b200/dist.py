@@ -176,6 +176,45 @@ class GradExchange(object):
         return self.dense.recv.view(self.world, self.dense.seg)[:, a].sum()
 
 
+def step_partition(n_full, world, rank):
+    """Which of an epoch's `n_full` equal-size batches a rank trains on (src/main.py under torchrun; --batch_size is
+    then PER RANK: the global step k is made of the batches k*world .. k*world + world - 1, one per rank — weak scaling,
+    SURVEY.md §8e (ii)).  Returns (mine, tail): `mine[k]` = index of this rank's batch in global step k; `tail` = the
+    full batches that do not fill a last global step — every rank runs those (and the ragged last batch) itself,
+    replicated, so no sample of the epoch is dropped."""
+    n_steps = n_full // world
+    return [k * world + rank for k in range(n_steps)], list(range(n_steps * world, n_full))
+
+
+def rank_slice_of_draws(draws, world, rank):
+    """draws [m * world, P, S] = the confounder draws of m global steps in batch order (ONE generator stream, consumed
+    identically on every rank so the ranks' generators stay in step) -> [m, P, S], this rank's batches."""
+    return draws.view(-1, world, draws.shape[1], draws.shape[2])[:, rank]
+
+
+def sync_host_rng(model, src=0):
+    """Put every rank's torch CPU generator and the model's noise / dropout call counter where rank `src` has them.
+    Sharded evaluation consumes both by different amounts on different ranks; training needs them in step (every rank
+    draws the global step's confounders and keeps its slice; replicated steps must be bit-identical)."""
+    if not is_distributed():
+        return
+    box = [torch.get_rng_state(), int(model._rng_offset)] if dist.get_rank() == src else [None, None]
+    dist.broadcast_object_list(box, src=src)
+    torch.set_rng_state(box[0])
+    model._rng_offset = int(box[1])
+
+
+def init_from_env():
+    """(rank, local_rank, world) from torchrun's environment; initialises NCCL and selects the GPU when world > 1."""
+    import os
+    rank, local = int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world > 1 and not (dist.is_available() and dist.is_initialized()):
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    return rank, local, world
+
+
 def shard_users(uid, rank, world):
     """Row indices of the contiguous block of (sorted) users owned by `rank`, balanced by row count; all
     candidates of a user stay on one rank."""

@@ -199,14 +199,20 @@ class BaseModel(torch.nn.Module):
     def save_model(self, model_path=None):
         """state_dict only, same keys as the reference so .pt files interchange (BaseModel.py:224-236)."""
         model_path = model_path or self.model_path
-        dir_path = os.path.dirname(model_path)
-        if dir_path and not os.path.exists(dir_path):
-            os.makedirs(dir_path)
-        torch.save(self.state_dict(), model_path)
+        multi = torch.distributed.is_available() and torch.distributed.is_initialized()
+        if not multi or torch.distributed.get_rank() == 0:     # replicas are identical: rank 0 writes for all
+            dir_path = os.path.dirname(model_path)
+            if dir_path and not os.path.exists(dir_path):
+                os.makedirs(dir_path)
+            torch.save(self.state_dict(), model_path)
+        if multi:
+            torch.distributed.barrier()
         logging.info('Save model to ' + model_path)
 
     def load_model(self, model_path=None):
         model_path = model_path or self.model_path
-        self.load_state_dict(torch.load(model_path))
+        multi = torch.distributed.is_available() and torch.distributed.is_initialized()
+        # (under torchrun the file was written from rank 0's GPU: stage through the host instead of that device)
+        self.load_state_dict(torch.load(model_path, map_location='cpu') if multi else torch.load(model_path))
         self.eval()
         logging.info('Load model from ' + model_path)

@@ -585,6 +585,20 @@ class DCCF(DMF):
                     'p2p': p2p}
         return self
 
+    def data_parallel_suspended(self):
+        """Context manager: steps inside run as on one GPU (no exchange; every rank must then feed the SAME batch and
+        random inputs, so the replicas remain bit-identical) — the tail of an epoch that does not fill a global step."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            saved, self._dp = self._dp, None
+            try:
+                yield self
+            finally:
+                self._dp = saved
+        return cm()
+
     def _exchange_for(self, P):
         from ..dist import GradExchange
         ex = self._dp['ex'].get(P)
@@ -910,7 +924,7 @@ class DCCF(DMF):
         self._check_ready()
         rank_mode = int(feed_dict['rank'])
         p_drop = float(feed_dict.get('dropout', 0.0))
-        key = (P, rank_mode, p_drop, id(opt), False)
+        key = (P, rank_mode, p_drop, id(opt), False, self._dp is not None)
         graphs = self.__dict__.setdefault('_graphs', {})
         g = graphs.get(key)
         if g is None:
@@ -945,7 +959,7 @@ class DCCF(DMF):
         if not self._graph_allowed(P) or n == 0:
             return None
         p_drop = float(dropout)
-        key = (P, 1, p_drop, id(opt), True)
+        key = (P, 1, p_drop, id(opt), True, self._dp is not None)
         graphs = self.__dict__.setdefault('_graphs', {})
         state = {'next': 0}
         if key not in graphs:

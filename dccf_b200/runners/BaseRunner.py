@@ -200,23 +200,38 @@ class BaseRunner(object):
         fused = hasattr(model, 'train_step') and not isinstance(model.optimizer, torch.optim.Optimizer)
         accumulate_size = 0
         output_dict = None
-        if fused and hasattr(model, 'begin_resident_epoch') and len(batches) > 2 and data_processor.rank == 1 \
-                and batches[0]['X'].is_cuda:
+        world = self._world(model)
+        suspended = None
+        if world > 1:
+            if not (fused and hasattr(model, 'begin_resident_epoch') and data_processor.rank == 1):
+                raise RuntimeError('data-parallel training (torchrun) needs the fused Adam step of DCCF with --rank 1')
+            from ..dist import sync_host_rng
+            sync_host_rng(model)            # sharded evaluation left the ranks' generators at different positions
+        if fused and hasattr(model, 'begin_resident_epoch') and (len(batches) > 2 or world > 1) \
+                and data_processor.rank == 1 and batches[0]['X'].is_cuda:
             # Equal-size batches run from a device-resident epoch: the confounder draws of all of them are ONE
             # torch.randint call (same CPU-generator stream as the reference's per-batch calls, DCCF.py:72) and
             # each step is a single CUDA-graph launch that fetches its batch through a device-side cursor.
+            # Data parallel (world > 1): global step k = batches k*world .. k*world + world - 1, one per rank; every
+            # rank draws the confounders of all of them (generators stay in step) and keeps its own slice.
+            from ..dist import rank_slice_of_draws, step_partition
+            rank = model._dp['rank'] if world > 1 else 0
             P0 = batches[0]['X'].shape[0]
             n_full = 0
             while n_full < len(batches) and batches[n_full]['X'].shape[0] == P0:
                 n_full += 1
+            mine, _ = step_partition(n_full, world, rank)
             chunk = 1024
-            done = 0
-            while done < n_full:
-                m = min(chunk, n_full - done)
-                X_epoch = torch.stack([b['X'] for b in batches[done:done + m]])
-                draws = model.draw_confounders(m * P0).view(m, P0, model.sample_num)
+            done = 0                                    # global steps run so far
+            while done < len(mine):
+                m = min(chunk, len(mine) - done)
+                X_epoch = torch.stack([batches[i]['X'] for i in mine[done:done + m]])
+                draws = model.draw_confounders(m * world * P0).view(m * world, P0, model.sample_num)
+                draws = rank_slice_of_draws(draws, world, rank) if world > 1 else draws
                 step = model.begin_resident_epoch(X_epoch, draws.to(X_epoch.device, non_blocking=True), self.dropout)
                 if step is None:
+                    if world > 1:
+                        raise RuntimeError('data-parallel training needs the CUDA-graph step (peer-memory exchange)')
                     break
                 if step.first is not None:
                     output_dict = step.first
@@ -227,7 +242,25 @@ class BaseRunner(object):
                 output_dict = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in output_dict.items()
                                if k != 'check'}
                 output_dict['check'] = [('prediction', output_dict['prediction'])]
-            batches = batches[done:]
+            batches = batches[done * world:]
+            if world > 1 and batches:
+                # what does not fill a global step (< world full batches + the ragged last one): every rank runs these
+                # steps itself, un-exchanged, on identical inputs — replicas stay bit-identical, no sample is dropped
+                suspended = model.data_parallel_suspended()
+                suspended.__enter__()
+        try:
+            output_dict = self._fit_remaining(model, batches, fused, batch_size, epoch, output_dict)
+        finally:
+            if suspended is not None:
+                suspended.__exit__(None, None, None)
+        model.eval()
+        if hasattr(model, 'check_ids'):
+            model.check_ids()
+        return output_dict
+
+    def _fit_remaining(self, model, batches, fused, batch_size, epoch, output_dict):
+        """Batches that did not go through the device-resident epoch: step by step."""
+        accumulate_size = 0
         if fused and hasattr(model, 'draw_confounders') and batches:
             # forward + (loss + l2) backward + clip + step in one go: the reference steps on every batch
             # (accumulate_size >= batch_size always holds for its batch layout, BaseRunner.py:176,186-188).
@@ -253,9 +286,6 @@ class BaseRunner(object):
             if accumulate_size >= batch_size or batch is batches[-1]:
                 model.optimizer.step()
                 accumulate_size = 0
-        model.eval()
-        if hasattr(model, 'check_ids'):
-            model.check_ids()
         return output_dict
 
     def eva_termination(self, model):
@@ -346,7 +376,7 @@ class BaseRunner(object):
             return [float(np.sqrt(tot[i] / tot[n + i])) if metrics[i] == 'rmse' else float(tot[i] / tot[n + i])
                     for i in range(n)]
         pred = self._predict_device(model, data, data_processor)
-        if write_rank:
+        if write_rank and (self._world(model) == 1 or model._dp['rank'] == 0):
             df = pd.DataFrame()
             df['uid'] = data['uid']
             df['iid'] = data['iid']

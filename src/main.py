@@ -16,14 +16,24 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def _gpu_list_ok(value):
+    """Under torchrun (LOCAL_WORLD_SIZE ranks on this node) `--gpu` must name at least one device per local rank to be
+    applied as CUDA_VISIBLE_DEVICES; the reference's default `--gpu 0` would pin every rank to the same GPU."""
+    local_world = int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1')))
+    return local_world <= 1 or len([d for d in value.split(',') if d.strip() != '']) >= local_world
+
+
 def _early_gpu_env(argv):
     """CUDA_VISIBLE_DEVICES must be set before CUDA initialises; the reference sets it after parsing
     (main.py:106), which only works because nothing touched CUDA yet.  Same effect, done first."""
     for i, a in enumerate(argv):
+        value = None
         if a == '--gpu' and i + 1 < len(argv):
-            os.environ['CUDA_VISIBLE_DEVICES'] = argv[i + 1]
+            value = argv[i + 1]
         elif a.startswith('--gpu='):
-            os.environ['CUDA_VISIBLE_DEVICES'] = a.split('=', 1)[1]
+            value = a.split('=', 1)[1]
+        if value is not None and _gpu_list_ok(value):
+            os.environ['CUDA_VISIBLE_DEVICES'] = value
 
 
 _early_gpu_env(sys.argv[1:])
@@ -50,6 +60,12 @@ def _resolve(name):
 
 
 def main(argv=None):
+    # Data parallel (new: the reference is single-process): launched with
+    #   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 main.py <same flags>
+    # every rank runs this same program on its own GPU; --batch_size is then per rank (global step = N batches), rank 0
+    # owns the log file, the checkpoint, rank.csv and the result file.
+    from dccf_b200 import dist as dp
+    rank, local_rank, world = dp.init_from_env() if int(os.environ.get('WORLD_SIZE', '1')) > 1 else (0, 0, 1)
     init_parser = argparse.ArgumentParser(description='Model')
     init_parser.add_argument('--rank', type=int, default=1, help='1=ranking, 0=rating/click')
     init_parser.add_argument('--data_loader', type=str, default='DataLoader', help='Choose data_loader')
@@ -93,8 +109,11 @@ def main(argv=None):
 
     for handler in logging.root.handlers[:]:
         logging.root.removeHandler(handler)
-    logging.basicConfig(filename=args.log_file, level=args.verbose)
-    logging.getLogger().addHandler(logging.StreamHandler(sys.stdout))
+    if rank == 0:
+        logging.basicConfig(filename=args.log_file, level=args.verbose)
+        logging.getLogger().addHandler(logging.StreamHandler(sys.stdout))
+    else:                                       # one log: rank 0's
+        logging.basicConfig(handlers=[logging.NullHandler()], level=logging.ERROR)
     logging.info(vars(init_args))
     logging.info(vars(args))
     logging.info('DataLoader: ' + init_args.data_loader)
@@ -107,8 +126,11 @@ def main(argv=None):
     if torch.cuda.is_available():
         torch.cuda.manual_seed(args.random_seed)
     np.random.seed(args.random_seed)
-    os.environ['CUDA_VISIBLE_DEVICES'] = args.gpu
+    if _gpu_list_ok(args.gpu):
+        os.environ['CUDA_VISIBLE_DEVICES'] = args.gpu
     logging.info('# cuda devices: %d' % torch.cuda.device_count())
+    if world > 1:
+        logging.info('data parallel: %d ranks, --batch_size %d per rank' % (world, args.batch_size))
 
     data_loader = data_loader_name(path=args.path, dataset=args.dataset, label=args.label, sep=args.sep)
     features, feature_dims, feature_min, feature_max = data_loader.feature_info(
@@ -136,6 +158,10 @@ def main(argv=None):
     model.apply(model.init_paras)
     if torch.cuda.device_count() > 0:
         model = model.cuda()
+    if world > 1:
+        if not hasattr(model, 'enable_data_parallel'):
+            raise SystemExit('data-parallel runs need --model_name DCCF')
+        model.enable_data_parallel()
 
     if init_args.rank == 1:
         data_loader.drop_neg()
@@ -154,8 +180,20 @@ def main(argv=None):
     logging.info('Test After Training = ' + utils.format_metric(
         runner.evaluate(model, data_processor.get_test_data(), data_processor, write_rank=True))
                  + ' ' + ','.join(runner.metrics))
-    np.save(args.result_file, runner.predict(model, data_processor.get_test_data(), data_processor))
+    result = runner.predict(model, data_processor.get_test_data(), data_processor)
+    if rank == 0:
+        np.save(args.result_file, result)
     logging.info('Save Test Results to ' + args.result_file)
+    if world > 1:
+        # the design invariant of the data-parallel step: replicas stay bit-identical without any parameter broadcast
+        sums = torch.stack([p.detach().view(torch.int32).to(torch.int64).sum() for p in model.parameters()])
+        every = [torch.empty_like(sums) for _ in range(world)]
+        torch.distributed.all_gather(every, sums)
+        if not all(torch.equal(every[0], e) for e in every):
+            raise SystemExit('data-parallel replicas diverged (parameter checksums differ between ranks)')
+        logging.info('data parallel: parameter checksums identical on all %d ranks' % world)
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from dccf_b200.dist import GradExchange, IdExchange, all_reduce_sum, shard_users
+from dccf_b200.dist import (GradExchange, IdExchange, all_reduce_sum, rank_slice_of_draws, shard_users,
+                            step_partition, sync_host_rng)
 
 
 def _free_port():
@@ -67,6 +68,16 @@ def _worker(rank, world, port, out_dir):
         sums = all_reduce_sum([float(len(mine)), float(len(set(uid[mine].tolist())))])
         assert sums[0] == 500 and sums[1] == len(set(uid.tolist()))
         np.save(os.path.join(out_dir, 'rows_%d.npy' % rank), mine)
+        # host generators drift apart during sharded evaluation and are put back in step before training
+        class _M(object):
+            _rng_offset = 0
+        m = _M()
+        torch.manual_seed(5)
+        torch.randint(10, (100 * (rank + 1),))          # ranks consume different amounts
+        m._rng_offset = 40 + rank
+        sync_host_rng(m)
+        torch.save({'draw': torch.randint(1 << 20, (8,)), 'offset': m._rng_offset},
+                   os.path.join(out_dir, 'rng_%d.pt' % rank))
     finally:
         dist.destroy_process_group()
 
@@ -81,6 +92,33 @@ def test_gloo_world2_exchange_and_sharding(tmp_path):
     assert len(rows[0]) + len(rows[1]) == 500
     # a user's candidates never straddle two ranks
     assert len(set(uid[rows[0]].tolist()) & set(uid[rows[1]].tolist())) == 0
+
+
+    a, b = (torch.load(os.path.join(str(tmp_path), 'rng_%d.pt' % r)) for r in range(2))
+    assert torch.equal(a['draw'], b['draw']) and a['offset'] == b['offset'] == 40
+
+
+def test_step_partition_covers_every_batch_once():
+    """src/main.py under torchrun: the global step k = batches k*world .. k*world+world-1, the leftover full batches
+    form the replicated tail; ranks' confounder slices re-assemble the single generator stream."""
+    for n_full, world in ((6750, 8), (13, 4), (3, 4), (8, 2), (0, 2)):
+        seen = []
+        tails = set()
+        for r in range(world):
+            mine, tail = step_partition(n_full, world, r)
+            assert len(mine) == n_full // world
+            seen += mine
+            tails.add(tuple(tail))
+        assert len(tails) == 1                                       # every rank agrees on the tail
+        tail = list(tails.pop())
+        assert sorted(seen + tail) == list(range(n_full)) and len(tail) < world
+    g = torch.Generator().manual_seed(3)
+    m, world, P, S = 5, 4, 6, 10
+    draws = torch.randint(1000, (m * world, P, S), generator=g)
+    parts = [rank_slice_of_draws(draws, world, r) for r in range(world)]
+    for k in range(m):
+        for r in range(world):
+            assert torch.equal(parts[r][k], draws[k * world + r])
 
 
 def test_shard_users_single_rank_and_balance():

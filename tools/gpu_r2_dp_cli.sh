@@ -1,0 +1,15 @@
+#!/bin/bash
+# Round 2, N GPUs (gpurun --gpus 2 ...): first hardware run of src/main.py under torchrun (data-parallel training through
+# the reference CLI: --batch_size per rank, sharded evaluation, rank 0 owns the files; ends with a replica checksum).
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'bash tools/gpu_r2_dp_cli.sh 2'
+N=${1:-2}
+mkdir -p gpurun_out /tmp/dpcli
+python -m dccf_b200.synth --path /tmp/dpcli/datasets/ --dataset toy --preset tiny > /dev/null
+cd src
+timeout 800 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+    main.py --rank 1 --model_name DCCF --optimizer Adam --lr 0.001 --dataset toy --path /tmp/dpcli/datasets/ \
+    --metric ndcg@5,recall@5,precision@5 --epoch 3 --test_neg_n 100 --log_file /tmp/dpcli/log.txt \
+    --result_file /tmp/dpcli/result.npy --model_path /tmp/dpcli/model/m.pt > ../gpurun_out/dp_cli_$N.log 2>&1
+echo "rc=$?"
+cd ..
+grep -E "data parallel|Epoch|Test (Before|After)|Best Iter|diverged|Error|error" gpurun_out/dp_cli_$N.log | tail -20
