@@ -10,7 +10,8 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libdccf_b200.so')
+_VARIANT = os.environ.get('DCCF_LIB_VARIANT', '')          # A/B build variants, see dccf_b200/build.py
+LIB_PATH = os.path.join(HERE, 'libdccf_b200%s.so' % (('_' + _VARIANT) if _VARIANT else ''))
 ABI_VERSION = 29
 DIM = 64
 

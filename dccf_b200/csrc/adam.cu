@@ -411,7 +411,10 @@ __global__ void __launch_bounds__(256) k_link_ids(const LinkIdsArgs a) {
     }
 }
 
-constexpr int ADAM_SIDE_SMEM = 120 * 1024;
+#ifndef DCCF_ADAM_SIDE_SMEM_KB
+#define DCCF_ADAM_SIDE_SMEM_KB 120          // build-time knob, see DCCF_TRAIN_STAGES in tc_train.cu
+#endif
+constexpr int ADAM_SIDE_SMEM = DCCF_ADAM_SIDE_SMEM_KB * 1024;
 
 // L2-only loads / stores: the sweep streams 100 MB past SMs whose L1 holds the feature rows of the concurrent
 // forward — it must not evict them

@@ -25,6 +25,17 @@
 
 namespace dccf {
 
+// Ring depth of the two training contractions.  Build-time knob (python -m dccf_b200.build with
+// DCCF_BUILD_DEFS="-DDCCF_TRAIN_STAGES=3 -DDCCF_ADAM_SIDE_SMEM_KB=80" DCCF_LIB_VARIANT=s3): a third stage decouples the 16
+// producer warps from the MMA issuer but needs 144 KB, so the side-stream sweep's shared-memory
+// occupancy limiter has to shrink with it.  Default: the evaluation scorer's depth.
+#ifndef DCCF_TRAIN_STAGES
+#define DCCF_TRAIN_STAGES TC_STAGES
+#endif
+constexpr int TT_STAGES = DCCF_TRAIN_STAGES;
+constexpr uint32_t TT_SMEM_BYTES = TT_STAGES * TC_STAGE_BYTES + 256;
+static_assert(TT_SMEM_BYTES <= 227 * 1024, "training ring does not fit the shared memory of an SM");
+
 // ---------------------------------------------------------------------------------------------
 // W [D, K] -> per-chunk operand images [chunk][ hi 8 KB | lo 8 KB ], all K = D + F columns
 // ---------------------------------------------------------------------------------------------
@@ -114,9 +125,9 @@ struct TrainFwdParams {
 template <int NOISE_MODE>
 __global__ void __launch_bounds__(TC_NT, 2) k_train_fwd_tc(const TrainFwdParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + TC_STAGES;
-    uint64_t* accum_bar = empty_bar + TC_STAGES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TT_STAGES * TC_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + TT_STAGES;
+    uint64_t* accum_bar = empty_bar + TT_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -140,7 +151,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_train_fwd_tc(const TrainFwdParams 
     }
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < TT_STAGES; ++s) {
             tc::mbar_init(&full_bar[s], TC_PRODUCERS / 32 + 1);   // producer warps + the expect_tx arrival
             tc::mbar_init(&empty_bar[s], 1);                      // one tcgen05.commit
         }
@@ -162,8 +173,8 @@ __global__ void __launch_bounds__(TC_NT, 2) k_train_fwd_tc(const TrainFwdParams 
         if (NOISE_MODE == 2) key_noise = resolve_rng_key(prm.rng, DOMAIN_NOISE);
         for (int i = 0; i < n_local; ++i) {
             const int c = c_lo + i;
-            const int s = i % TC_STAGES;
-            const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+            const int s = i % TT_STAGES;
+            const uint32_t ph = (uint32_t)(i / TT_STAGES) & 1u;
             const int k0 = c * TC_KC;                 // first column of the chunk in [E_item | Feat]
             float4 v[2];
             if (k0 < D) {
@@ -204,8 +215,8 @@ __global__ void __launch_bounds__(TC_NT, 2) k_train_fwd_tc(const TrainFwdParams 
         // ===== MMA issuer =====
         if (lane == 0) {
             for (int i = 0; i < n_local; ++i) {
-                const int s = i % TC_STAGES;
-                const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+                const int s = i % TT_STAGES;
+                const uint32_t ph = (uint32_t)(i / TT_STAGES) & 1u;
                 tc::mbar_wait(&full_bar[s], ph);
                 tc::tc_fence_after_sync();
                 issue_stage_mmas(tc::smem_u32(smem + s * TC_STAGE_BYTES), tmem_base, i);
@@ -219,8 +230,8 @@ __global__ void __launch_bounds__(TC_NT, 2) k_train_fwd_tc(const TrainFwdParams 
         if (lane == 0) {
             for (int i = 0; i < n_local; ++i) {
                 const int c = c_lo + i;
-                const int s = i % TC_STAGES;
-                const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+                const int s = i % TT_STAGES;
+                const uint32_t ph = (uint32_t)(i / TT_STAGES) & 1u;
                 tc::mbar_wait(&empty_bar[s], ph ^ 1u);
                 tc::mbar_arrive_expect_tx(&full_bar[s], 2 * TC_B_BYTES);
                 tc::bulk_g2s(smem + s * TC_STAGE_BYTES + 2 * TC_A_BYTES, prm.gWimg + (size_t)c * (2 * TC_B_BYTES / 4),
@@ -596,9 +607,9 @@ __device__ __forceinline__ void quad_transpose(float4& a, int j) {
 template <int NOISE_MODE>
 __global__ void __launch_bounds__(TB_NT, 2) k_train_bwd_tc(const TrainBwdParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + TC_STAGES;
-    uint64_t* accum_bar = empty_bar + TC_STAGES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TT_STAGES * TC_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + TT_STAGES;
+    uint64_t* accum_bar = empty_bar + TT_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -609,7 +620,7 @@ __global__ void __launch_bounds__(TB_NT, 2) k_train_bwd_tc(const TrainBwdParams 
     const int n_st = row_hi > row_lo ? (int)((row_hi - row_lo + TC_KC - 1) / TC_KC) : 0;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < TT_STAGES; ++s) {
             tc::mbar_init(&full_bar[s], TC_PRODUCERS / 32);
             tc::mbar_init(&empty_bar[s], 1);
         }
@@ -689,8 +700,8 @@ __global__ void __launch_bounds__(TB_NT, 2) k_train_bwd_tc(const TrainBwdParams 
         float4 v[2], dv;
         if (n_st > 0) fetch(0, v, dv);
         for (int st = 0; st < n_st; ++st) {
-            const int s = st % TC_STAGES;
-            const uint32_t ph = (uint32_t)(st / TC_STAGES) & 1u;
+            const int s = st % TT_STAGES;
+            const uint32_t ph = (uint32_t)(st / TT_STAGES) & 1u;
             // the next stage's operands are in flight while this one is transposed, stored and multiplied
             float4 vn[2], dvn;
             if (st + 1 < n_st) fetch(st + 1, vn, dvn);
@@ -727,8 +738,8 @@ __global__ void __launch_bounds__(TB_NT, 2) k_train_bwd_tc(const TrainBwdParams 
         // ===== MMA issuer =====
         if (lane == 0) {
             for (int st = 0; st < n_st; ++st) {
-                const int s = st % TC_STAGES;
-                const uint32_t ph = (uint32_t)(st / TC_STAGES) & 1u;
+                const int s = st % TT_STAGES;
+                const uint32_t ph = (uint32_t)(st / TT_STAGES) & 1u;
                 tc::mbar_wait(&full_bar[s], ph);
                 tc::tc_fence_after_sync();
                 issue_stage_mmas(tc::smem_u32(smem + s * TC_STAGE_BYTES), tmem_base, st);
@@ -810,12 +821,12 @@ static void bwd_geometry(int64_t n_rows, int K, int32_t* n_mtiles, int32_t* n_sp
 
 template <typename Kern>
 static int opt_in_smem(Kern k, const char* name) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TT_SMEM_BYTES);
     // always the largest shared-memory carveout: a CTA of the side-stream Adam sweep (120 KB) and a tensor-core CTA
     // (96 KB) share an SM only if neither launch shrinks the carveout under the other
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) {
-        set_error("%s: cannot opt in to %u bytes of shared memory: %s", name, TC_SMEM_BYTES, cudaGetErrorString(e));
+        set_error("%s: cannot opt in to %u bytes of shared memory: %s", name, TT_SMEM_BYTES, cudaGetErrorString(e));
         return DCCF_ERR_CUDA;
     }
     return DCCF_OK;
@@ -884,9 +895,9 @@ static int launch_fwd_tc(const dccf_dims* dims, const float* E_item, const float
     *n_ks_out = n_ks;
     const dim3 grid((unsigned)((n_rows + TC_BM - 1) / TC_BM), (unsigned)n_ks);
     switch (rng->noise_mode) {
-        case 0: k_train_fwd_tc<0><<<grid, TC_NT, TC_SMEM_BYTES, stream>>>(prm); break;
-        case 1: k_train_fwd_tc<1><<<grid, TC_NT, TC_SMEM_BYTES, stream>>>(prm); break;
-        default: k_train_fwd_tc<2><<<grid, TC_NT, TC_SMEM_BYTES, stream>>>(prm); break;
+        case 0: k_train_fwd_tc<0><<<grid, TC_NT, TT_SMEM_BYTES, stream>>>(prm); break;
+        case 1: k_train_fwd_tc<1><<<grid, TC_NT, TT_SMEM_BYTES, stream>>>(prm); break;
+        default: k_train_fwd_tc<2><<<grid, TC_NT, TT_SMEM_BYTES, stream>>>(prm); break;
     }
     DCCF_CHECK_LAUNCH("k_train_fwd_tc");
     return DCCF_OK;
@@ -917,9 +928,9 @@ static int launch_bwd_tc(const dccf_dims* dims, const float* E_item, const float
     bwd_geometry(prm.n_rows, K, &n_mtiles, &n_splits, &prm.rows_per_split);
     const dim3 grid((unsigned)n_mtiles, (unsigned)n_splits);
     switch (rng->noise_mode) {
-        case 0: k_train_bwd_tc<0><<<grid, TB_NT, TC_SMEM_BYTES, stream>>>(prm); break;
-        case 1: k_train_bwd_tc<1><<<grid, TB_NT, TC_SMEM_BYTES, stream>>>(prm); break;
-        default: k_train_bwd_tc<2><<<grid, TB_NT, TC_SMEM_BYTES, stream>>>(prm); break;
+        case 0: k_train_bwd_tc<0><<<grid, TB_NT, TT_SMEM_BYTES, stream>>>(prm); break;
+        case 1: k_train_bwd_tc<1><<<grid, TB_NT, TT_SMEM_BYTES, stream>>>(prm); break;
+        default: k_train_bwd_tc<2><<<grid, TB_NT, TT_SMEM_BYTES, stream>>>(prm); break;
     }
     DCCF_CHECK_LAUNCH("k_train_bwd_tc");
     return DCCF_OK;

@@ -32,3 +32,18 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --
 timeout 300 $LEGS > gpurun_out/plain_legs2.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_gather_scores|k_confounder_draw|k_row_scores_tc|k_rank_eval' --launch-skip 8 -c 8 -f -o gpurun_out/prof_r2a_legs $LEGS > gpurun_out/ncu_legs2.log 2>&1
 tail -2 gpurun_out/ncu_legs2.log | cut -c1-200
+# 5. A/B: three-stage ring in the two training contractions (+ 80 KB occupancy limiter of the side-stream sweep), built as
+#    a variant library here or in the build container:
+#    DCCF_LIB_VARIANT=s3 DCCF_BUILD_DEFS="-DDCCF_TRAIN_STAGES=3 -DDCCF_ADAM_SIDE_SMEM_KB=80" python -m dccf_b200.build
+export DCCF_BUILD_DEFS="-DDCCF_TRAIN_STAGES=3 -DDCCF_ADAM_SIDE_SMEM_KB=80"
+DCCF_LIB_VARIANT=s3 python -m dccf_b200.build > /dev/null
+DCCF_LIB_VARIANT=s3 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "training or fused or graph or resident" 2>&1 | tail -3
+for v in "" s3; do
+  DCCF_LIB_VARIANT=$v timeout 600 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --no-extra-legs > gpurun_out/bench_r2a_ab_${v:-base}.json 2>/dev/null
+  python - <<P
+import json
+d = json.loads(open('gpurun_out/bench_r2a_ab_${v:-base}.json').read().strip().splitlines()[-1])
+k = d['roofline'].get('kernels', {})
+print('${v:-base}', 'ms/step', round(d['ms_per_step'], 5), 'b2b', round(d['back_to_back']['ms_per_step'], 5), {n: round(o['us'], 1) for n, o in k.items()})
+P
+done
