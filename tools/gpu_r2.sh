@@ -47,3 +47,12 @@ k = d['roofline'].get('kernels', {})
 print('${v:-base}', 'ms/step', round(d['ms_per_step'], 5), 'b2b', round(d['back_to_back']['ms_per_step'], 5), {n: round(o['us'], 1) for n, o in k.items()})
 P
 done
+# 6. what the generator costs: the same bench with 7 Philox rounds (measurement only, not a product configuration)
+DCCF_LIB_VARIANT=p7 DCCF_BUILD_DEFS="-DDCCF_PHILOX_ROUNDS=7" python -m dccf_b200.build > /dev/null
+DCCF_LIB_VARIANT=p7 timeout 600 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --no-extra-legs > gpurun_out/bench_r2a_ab_p7.json 2>/dev/null
+python - <<P
+import json
+d = json.loads(open('gpurun_out/bench_r2a_ab_p7.json').read().strip().splitlines()[-1])
+k = d['roofline'].get('kernels', {})
+print('p7', 'ms/step', round(d['ms_per_step'], 5), 'eval ms/batch', round(d['eval']['ms_per_batch'], 4), {n: round(o['us'], 1) for n, o in k.items()})
+P
