@@ -12,3 +12,9 @@ timeout 1500 compute-sanitizer --tool "$TOOL" --error-exitcode 3 \
     > gpurun_out/sanitize_"$TOOL".log 2>&1
 echo "compute-sanitizer $TOOL rc=$?"
 tail -5 gpurun_out/sanitize_"$TOOL".log
+# the kernels of round 1 that were written without hardware (gather scorer, device confounder draw): small cases only
+timeout 900 compute-sanitizer --tool "$TOOL" --error-exitcode 3 \
+    python tests/test_gpu_zz_gather.py oracle_ragged_many_slots oracle_no_confounders out_of_range_ids \
+    device_confounder_draw_equals_torch_randint > gpurun_out/sanitize_"$TOOL"_blind.log 2>&1
+echo "compute-sanitizer $TOOL (blind kernels) rc=$?"
+grep -E "GATHER_(OK|FAIL)|ERROR SUMMARY" gpurun_out/sanitize_"$TOOL"_blind.log | tail -8
