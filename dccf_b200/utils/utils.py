@@ -105,4 +105,4 @@ def check_dir_and_mkdir(path):
         dirname = os.path.dirname(path)
     if dirname and not os.path.exists(dirname):
         print('make dirs:', dirname)
-        os.makedirs(dirname)
+        os.makedirs(dirname, exist_ok=True)         # (several ranks may get here at once under torchrun)

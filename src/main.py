@@ -132,7 +132,11 @@ def main(argv=None):
     if world > 1:
         logging.info('data parallel: %d ranks, --batch_size %d per rank' % (world, args.batch_size))
 
+    if world > 1 and rank != 0:
+        torch.distributed.barrier()             # rank 0 writes the files a first run generates (.info.json, history csv)
     data_loader = data_loader_name(path=args.path, dataset=args.dataset, label=args.label, sep=args.sep)
+    if world > 1 and rank == 0:
+        torch.distributed.barrier()
     features, feature_dims, feature_min, feature_max = data_loader.feature_info(
         include_id=model_name.include_id, include_item_features=model_name.include_item_features,
         include_user_features=model_name.include_user_features)
