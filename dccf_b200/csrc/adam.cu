@@ -825,15 +825,15 @@ extern "C" int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tabl
         // memory, ~48 K registers per CTA).  Two sweep CTAs on one SM would leave no room for such a CTA and push it
         // into a second wave, so every sweep CTA reserves (and never touches) 120 KB of dynamic shared memory:
         // at most one per SM, and 120 + 96 KB still fit the 227 KB of an SM.
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceOnce attr_once;
+        if (attr_once.need()) {
             cudaError_t e = cudaFuncSetAttribute(k_adam_untouched, cudaFuncAttributeMaxDynamicSharedMemorySize, ADAM_SIDE_SMEM);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_adam_untouched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) {
                 set_error("dccf_adam_untouched: cannot opt in to %d bytes of shared memory: %s", ADAM_SIDE_SMEM, cudaGetErrorString(e));
                 return DCCF_ERR_CUDA;
             }
-            attr_set = true;
+            attr_once.mark();
         }
         // threads_per_cta (0 = default 128; DCCF_SIDE_THREADS overrides).  Measured (tools/step_timeline.py, electronics
         // shape): 256 threads finish the sweep in 29 us but slow the concurrent forward / middle kernels by 4 / 6 us

@@ -31,6 +31,21 @@ void set_error(const char* fmt, ...);
         }                                                                              \
     } while (0)
 
+// cudaFuncSetAttribute is PER DEVICE: one-time kernel configuration (shared-memory opt-in) is remembered per call site
+// and device, so a process that drives several GPUs configures each of them (one process per GPU is the normal mode).
+//     static PerDeviceOnce once;  if (once.need()) { ...configure...; once.mark(); }
+struct PerDeviceOnce {
+    bool done[64] = {};
+    int cur = 0;
+    bool need() {
+        int d = 0;
+        cudaGetDevice(&d);
+        cur = d & 63;
+        return !done[cur];
+    }
+    void mark() { done[cur] = true; }
+};
+
 // ------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based generator (Salmon et al., SC'11).  Counter layout of this
 // library (identical in the fused kernels and in the materialisers):

@@ -376,14 +376,14 @@ extern "C" int dccf_full_scores(int32_t n_users, int32_t n_items, const float* A
     prm.tiles_per_split = (prm.n_tiles + splits - 1) / splits;
     prm.topk_score = topk_score ? (splits == 1 ? topk_score : ws_score) : nullptr;
     prm.topk_id = topk_score ? (splits == 1 ? topk_id : ws_id) : nullptr;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_full_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM);
         if (e != cudaSuccess) {
             set_error("dccf_full_scores: cannot opt in to %u bytes of shared memory: %s", FS_SMEM, cudaGetErrorString(e));
             return DCCF_ERR_CUDA;
         }
-        attr_set = true;
+        attr_once.mark();
     }
     dim3 grid((unsigned)((n_users + FS_BM - 1) / FS_BM), (unsigned)splits);
     k_full_scores<<<grid, FS_NT, FS_SMEM, stream>>>(prm);

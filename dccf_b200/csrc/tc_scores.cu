@@ -403,8 +403,8 @@ static int tc_launch(const dccf_dims* dims, const float* E_user, const float* PI
     prm.drop_scale = (rng->p_drop < 1.0f) ? 1.0f / (1.0f - rng->p_drop) : 0.0f;
     prm.rng.seed = rng->seed; prm.rng.offset = rng->offset; prm.rng.offset_dev = rng->offset_dev;
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
         cudaError_t e1 = cudaFuncSetAttribute(k_row_scores_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
         cudaError_t e2 = cudaFuncSetAttribute(k_row_scores_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
         if (e1 != cudaSuccess || e2 != cudaSuccess) {
@@ -412,7 +412,7 @@ static int tc_launch(const dccf_dims* dims, const float* E_user, const float* PI
                       cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
             return DCCF_ERR_CUDA;
         }
-        attr_set = true;
+        attr_once.mark();
     }
     const unsigned grid = (unsigned)((n_rows + TC_BM - 1) / TC_BM);
     if (rng->noise_mode == 1) k_row_scores_tc<1><<<grid, TC_NT, TC_SMEM_BYTES, stream>>>(prm);

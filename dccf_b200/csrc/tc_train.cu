@@ -873,13 +873,13 @@ static int launch_fwd_tc(const dccf_dims* dims, const float* E_item, const float
                          cudaStream_t stream) {
     const int F = dims->feat_dim, K = D + F, Z = dims->n_samples + 1, R = Z * dims->n_attr;
     const int64_t n_rows = n_pairs * R;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
         int rc = opt_in_smem(k_train_fwd_tc<0>, "dccf_train_fwd_tc");
         if (rc == DCCF_OK) rc = opt_in_smem(k_train_fwd_tc<1>, "dccf_train_fwd_tc");
         if (rc == DCCF_OK) rc = opt_in_smem(k_train_fwd_tc<2>, "dccf_train_fwd_tc");
         if (rc != DCCF_OK) return rc;
-        attr_set = true;
+        attr_once.mark();
     }
     if (!w_image_valid) {
         k_prep_w_image<<<104, 256, 0, stream>>>(W, K, ws_wimg);
@@ -908,13 +908,13 @@ static int launch_bwd_tc(const dccf_dims* dims, const float* E_item, const float
                          const int64_t* sample_item, int64_t n_pairs, const dccf_rng* rng, const float* ws_dpre,
                          const float* x_rows, float* gW_part, float* gb_part, const float* loss_terms, int64_t n_loss_terms,
                          float loss_scale, float* out_loss, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
         int rc = opt_in_smem(k_train_bwd_tc<0>, "dccf_train_bwd_tc");
         if (rc == DCCF_OK) rc = opt_in_smem(k_train_bwd_tc<1>, "dccf_train_bwd_tc");
         if (rc == DCCF_OK) rc = opt_in_smem(k_train_bwd_tc<2>, "dccf_train_bwd_tc");
         if (rc != DCCF_OK) return rc;
-        attr_set = true;
+        attr_once.mark();
     }
     const int F = dims->feat_dim, K = D + F, Z = dims->n_samples + 1, R = Z * dims->n_attr;
     TrainBwdParams prm;
