@@ -196,6 +196,10 @@ class DCCF(DMF):
         if not w.is_cuda:
             raise RuntimeError('DCCF (dccf_b200) runs on CUDA only: move the model with .cuda() on a B200; there is no '
                                'CPU fallback')
+        if w.device.index is not None and w.device.index != torch.cuda.current_device():
+            # launches go to the current device's stream (dccf_b200/_lib.py: stream_ptr)
+            raise RuntimeError('the model lives on %s but the current CUDA device is %d: call torch.cuda.set_device(%d) '
+                               '(one process per GPU)' % (w.device, torch.cuda.current_device(), w.device.index))
         if self.n_layers != 1:
             raise NotImplementedError('the fused kernels implement the default --n_layers 1 (one Linear(D+F -> D))')
         if self.ui_vector_size != kernels.D:
