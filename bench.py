@@ -44,6 +44,9 @@ SEED = 2019
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the step's kernels at the electronics shape, from ONE
 # `ncu --set full --clock-control none` capture (cold cache before every kernel), see profiles/
 NCU_TRAFFIC_SOURCE = 'profiles/r1e_ncu_full_train_summary.csv (ncu --set full, per launch, cold cache)'
+NCU_EVAL_TRAFFIC_BYTES = 8.783616e6        # k_row_scores_tc<2>, one 16384-pair batch: dram read (0 written), r1c capture
+NCU_EVAL_TRAFFIC_SOURCE = ('profiles/r1c_ncu_full_tc_summary.csv (ncu --set full, per launch of one 16384-pair batch, cold '
+                           'cache; the later tuning of the kernel did not change what it reads)')
 NCU_TRAFFIC_BYTES = {'k_train_fwd_tc': 1.89e6, 'k_train_mid': 4.47e6, 'k_train_bwd_tc': 2.92e6, 'k_adam_touched': 7.91e6,
                      'k_adam_untouched': 47.35e6 + 0.81e6}
 FLOP_FWD_PAIR = R * (2 * (D + F) * D + 4 * D)
@@ -835,7 +838,9 @@ def main():
     if used_tc:
         eval_roof = {'kernel': 'k_row_scores_tc (tcgen05 3xTF32)', 'bound': 'tensor',
                      'achieved': noise_tflop / (evl['score_ms'] / 1e3), 'peak': tf32_peak, 'unit': 'TFLOP/s',
-                     'frac': noise_tflop / (evl['score_ms'] / 1e3) / tf32_peak, 'traffic': None,
+                     'frac': noise_tflop / (evl['score_ms'] / 1e3) / tf32_peak,
+                     'traffic': NCU_EVAL_TRAFFIC_BYTES if EVAL_BATCH == 16384 else None,
+                     'traffic_source': NCU_EVAL_TRAFFIC_SOURCE,
                      'peak_source': peak_src + ': bf16 burst / 2 for kind::tf32',
                      'limiter': 'Gaussian noise generation (Philox4x32-10 + Box-Muller, 16.9 M normals per user) on '
                                 'the SIMT ALU/XU pipes, not the tensor pipe',
