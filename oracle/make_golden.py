@@ -182,6 +182,63 @@ def make_sampler_fixture(name='sampler', U=30, I=40, seed=2019, test_neg_n=5, ep
         shutil.rmtree(tmp)
 
 
+def array_digest(a):
+    """sha256 over dtype, shape and bytes of an array (what tests/golden/config0_digest.json stores)."""
+    import hashlib
+    a = np.ascontiguousarray(a)
+    h = hashlib.sha256()
+    h.update(str(a.dtype).encode() + b'|' + str(a.shape).encode() + b'|')
+    h.update(a.tobytes())
+    return h.hexdigest()
+
+
+def make_config0_digest(name='config0_digest', seed=2019, epochs=2, test_neg_n=1000, batch_size=128):
+    """BASELINE.json configs[0] — the reference's own CPU-runnable case: synthetic Electronics-shaped data with 2 000
+    users x 5 000 items x 768-d features, test_neg_n = 1000 — through the UNMODIFIED reference's DataLoader /
+    DataProcessor (src/data_loaders/DataLoader.py, src/data_processor/DataProcessor.py).  The arrays are too large to
+    commit (2 M negatives per evaluation set), so the fixture holds their sha256 digests: every id the host side of
+    the path produces at this scale must match bit for bit (tests/test_host_parity.py::test_config0_host_pipeline_digest)."""
+    import json
+    from dccf_b200 import synth
+    ref = rh.load_reference()
+    tmp = tempfile.mkdtemp()
+    try:
+        U, I, per = synth.PRESETS['tiny']
+        d = synth.write_dataset(tmp, 'tiny', U, I, per, feat_dim=768, seed=seed)
+        out = {'preset': 'tiny', 'users': U, 'items': I, 'per_user': per, 'feat_dim': 768, 'seed': seed, 'epochs': epochs,
+               'test_neg_n': test_neg_n, 'batch_size': batch_size, 'digests': {}, 'rows': {}}
+        with rh.cpu_shims():
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+            dl = ref.DataLoader(path=tmp, dataset='tiny', label='label', sep=',')
+            model = rh.build_reference_model(ref, d, 'tiny', SENT, dl.user_num, dl.item_num, random_seed=seed,
+                                             model_path=os.path.join(tmp, 'm.pt'))
+            dl.drop_neg()
+            dp = ref.DataProcessor(dl, model, rank=1, test_neg_n=test_neg_n)
+            out['user_num'], out['item_num'] = int(dl.user_num), int(dl.item_num)
+            te = dp.get_test_data()
+            va = dp.get_validation_data()
+            for nm, dd in (('test', te), ('validation', va)):
+                out['rows'][nm] = int(len(dd['Y']))
+                for k in ('uid', 'iid', 'Y', 'X', 'sample_id'):
+                    out['digests']['%s_%s' % (nm, k)] = array_digest(np.asarray(dd[k]))
+            dp.get_train_data(epoch=-1)
+            for ep in range(epochs):
+                data = dp.get_train_data(epoch=ep)
+                batches = dp.prepare_batches(data, batch_size, train=True)
+                out['rows']['train_ep%d_batches' % ep] = len(batches)
+                out['digests']['train_ep%d_X' % ep] = array_digest(np.concatenate([b['X'].numpy() for b in batches]))
+                out['digests']['train_ep%d_Y' % ep] = array_digest(np.concatenate([b['Y'].numpy() for b in batches]))
+                out['digests']['train_ep%d_sample_id' % ep] = array_digest(
+                    np.concatenate([np.asarray(b['sample_id']) for b in batches]).astype(np.int64))
+            out['np_state_after'] = [int(x) for x in np.random.get_state()[1][:8]]
+        with open(os.path.join(GOLDEN, name + '.json'), 'w') as f:
+            json.dump(out, f, indent=1, sort_keys=True)
+        print(name, out['rows'])
+    finally:
+        shutil.rmtree(tmp)
+
+
 def make_metrics_fixture(name='metrics', seed=5):
     ref = rh.load_reference()
     rs = np.random.RandomState(seed)
@@ -220,4 +277,5 @@ if __name__ == '__main__':
       make_train_fixture('train_f768', U=24, I=30, F=768, P=8, steps=2)
       make_train_fixture('train_nodrop', U=40, I=50, F=64, P=12, steps=2, dropout=0.0, std=0.0, S=4, A=3)
     make_sampler_fixture()
+    make_config0_digest()
     make_metrics_fixture()

@@ -410,3 +410,48 @@ def test_device_stream_state_round_trip_without_draws():
         s.finish()
         assert torch.equal(torch.randint(1 << 20, (700,), generator=g1), torch.randint(1 << 20, (700,), generator=g2))
         assert torch.equal(torch.randn(5, generator=g1), torch.randn(5, generator=g2))
+
+
+def test_config0_host_pipeline_digest(tmp_path):
+    """BASELINE.json configs[0] — 2 000 users x 5 000 items x 768-d, test_neg_n = 1000, batch 128 — the host side of the
+    path against the UNMODIFIED reference at full size: the reference's own DataLoader / DataProcessor produced
+    tests/golden/config0_digest.json (oracle/make_golden.py::make_config0_digest; 2 M negatives per evaluation set, so
+    sha256 digests instead of the arrays).  Every id, label and sample id of the test / validation sets and of two
+    shuffled training epochs, and the numpy generator afterwards, must match bit for bit."""
+    import hashlib
+    import json
+    from conftest import GOLDEN
+    want = json.load(open(os.path.join(GOLDEN, 'config0_digest.json')))
+
+    def digest(a):
+        a = np.ascontiguousarray(a)
+        h = hashlib.sha256()
+        h.update(str(a.dtype).encode() + b'|' + str(a.shape).encode() + b'|')
+        h.update(a.tobytes())
+        return h.hexdigest()
+
+    d = synth.write_dataset(str(tmp_path), 'tiny', want['users'], want['items'], want['per_user'],
+                            feat_dim=64, seed=want['seed'])       # the feature width does not enter the host pipeline
+    seed = want['seed']
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    dl = DataLoader(path=str(tmp_path), dataset='tiny', label='label', sep=',')
+    assert (int(dl.user_num), int(dl.item_num)) == (want['user_num'], want['item_num'])
+    model = _make_model(d, 'tiny', dl.user_num, dl.item_num, seed=seed)
+    dl.drop_neg()
+    dp = DataProcessor(dl, model, rank=1, test_neg_n=want['test_neg_n'])
+    te, va = dp.get_test_data(), dp.get_validation_data()
+    for nm, dd in (('test', te), ('validation', va)):
+        assert len(dd['Y']) == want['rows'][nm]
+        for k in ('uid', 'iid', 'Y', 'X', 'sample_id'):
+            assert digest(np.asarray(dd[k])) == want['digests']['%s_%s' % (nm, k)], (nm, k)
+    dp.get_train_data(epoch=-1)
+    for ep in range(want['epochs']):
+        data = dp.get_train_data(epoch=ep)
+        batches = dp.prepare_batches(data, want['batch_size'], train=True)
+        assert len(batches) == want['rows']['train_ep%d_batches' % ep]
+        assert digest(np.concatenate([b['X'].cpu().numpy() for b in batches])) == want['digests']['train_ep%d_X' % ep]
+        assert digest(np.concatenate([b['Y'].cpu().numpy() for b in batches])) == want['digests']['train_ep%d_Y' % ep]
+        sid = np.concatenate([np.asarray(b['sample_id']) for b in batches]).astype(np.int64)
+        assert digest(sid) == want['digests']['train_ep%d_sample_id' % ep]
+    assert [int(x) for x in np.random.get_state()[1][:8]] == want['np_state_after']
