@@ -239,6 +239,59 @@ def make_config0_digest(name='config0_digest', seed=2019, epochs=2, test_neg_n=1
         shutil.rmtree(tmp)
 
 
+def make_config0_train(name='config0_train', seed=2019, steps=24, batch_size=128, lr=1e-3, l2=1e-4, dropout=0.2):
+    """BASELINE.json configs[0] again, now the device math: the first `steps` training steps of epoch 0 of the UNMODIFIED
+    reference (its DataLoader -> DataProcessor -> DCCF -> BaseRunner.fit with Adam) at full size — 256 pairs = 5 632
+    predictor rows x 832 inputs per step.  The random inputs are NOT stored (17 MB of noise per step): the torch CPU
+    generator is re-seeded with seed + 1 right before fit, and a test re-draws them with the same three calls per step
+    (torch.randint, normal_, bernoulli_ — oracle/ref_harness.py) on the same torch build.  Stored: every step's loss,
+    the predictions of the first and last step, the final bias, the final rows of the users / items of the last batch,
+    a slice of W, and the norms of all four final tensors."""
+    ref = rh.load_reference()
+    tmp = tempfile.mkdtemp()
+    try:
+        U, I, per = synth.PRESETS['tiny']
+        d = synth.write_dataset(tmp, 'tiny', U, I, per, feat_dim=768, seed=seed)
+        with rh.cpu_shims():
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+            dl = ref.DataLoader(path=tmp, dataset='tiny', label='label', sep=',')
+            model = rh.build_reference_model(ref, d, 'tiny', SENT, dl.user_num, dl.item_num, random_seed=seed,
+                                             model_path=os.path.join(tmp, 'm.pt'))
+            dl.drop_neg()
+            dp = ref.DataProcessor(dl, model, rank=1, test_neg_n=1000)
+            dp.get_test_data()                       # the numpy stream is consumed in main.py's order
+            dp.get_validation_data()
+            dp.get_train_data(epoch=-1)
+            data = dp.get_train_data(epoch=0)
+            batches = dp.prepare_batches(data, batch_size, train=True)[:steps]
+            outs = []
+            model.register_forward_hook(lambda m, i, o: outs.append(
+                (o['prediction'].detach().numpy().copy(), float(o['loss'].detach()))))
+            runner = ref.BaseRunner(optimizer='Adam', learning_rate=lr, epoch=1, batch_size=batch_size,
+                                    eval_batch_size=16384, dropout=dropout, l2=l2, metrics='ndcg@5', check_epoch=1,
+                                    early_stop=1)
+            rh.reset_tape()
+            torch.manual_seed(seed + 1)              # the replay point of the test
+            runner.fit(model, None, _StubDP(batches), epoch=0)
+            final = _params_of(model)
+            X_last = batches[-1]['X'].numpy()
+            users, items = np.unique(X_last[:, 0]), np.unique(X_last[:, 1])
+            out = {'seed': seed, 'steps': steps, 'batch_size': batch_size, 'lr': lr, 'l2': l2, 'dropout': dropout,
+                   'std': 0.1, 'S': 10, 'A': 2, 'torch_version': np.array(torch.__version__),
+                   'loss': np.array([o[1] for o in outs], dtype=np.float64), 'pred_first': outs[0][0],
+                   'pred_last': outs[-1][0], 'X_first': batches[0]['X'].numpy(), 'X_last': X_last,
+                   'sample_item_first': rh.tape().calls[0]['sample_item'].numpy(),
+                   'final_b': final['b'], 'users_last': users, 'items_last': items,
+                   'final_E_user_rows': final['E_user'][users], 'final_E_item_rows': final['E_item'][items],
+                   'final_W_rows': final['W'][::8], 'norms': np.array([np.linalg.norm(final[k].astype(np.float64))
+                                                                       for k in ('E_user', 'E_item', 'W', 'b')])}
+        np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), **out)
+        print(name, 'losses', out['loss'][:3], '...', out['loss'][-1])
+    finally:
+        shutil.rmtree(tmp)
+
+
 def make_metrics_fixture(name='metrics', seed=5):
     ref = rh.load_reference()
     rs = np.random.RandomState(seed)
@@ -278,4 +331,5 @@ if __name__ == '__main__':
       make_train_fixture('train_nodrop', U=40, I=50, F=64, P=12, steps=2, dropout=0.0, std=0.0, S=4, A=3)
     make_sampler_fixture()
     make_config0_digest()
+    make_config0_train()
     make_metrics_fixture()

@@ -766,3 +766,40 @@ def test_fused_adam_step_record_lists():
         assert np.array_equal(a, b)
     assert rel_err(res[0][1], want_m) < 1e-6 and rel_err(res[0][2], want_v) < 1e-6
     assert rel_err(res[0][0], want_p) < 1e-5 and rel_err(res[0][3], want_W) < 1e-5
+
+
+@pytest.mark.xfail(strict=False, reason='written after the GPU budget of round 1 was spent: first hardware run at round '
+                                        'end; XPASS = verified (the kernels it drives are the validated ones)')
+def test_fused_training_follows_the_reference_at_config0(tmp_path):
+    """BASELINE.json configs[0] at full size on the GPU: the first 24 training steps of the UNMODIFIED reference
+    (tests/golden/config0_train.npz) replayed through model.train_step — 256 pairs = 5 632 predictor rows x 832 inputs
+    per step, Adam over 2 000 + 5 000 embedding rows — from seeds alone: dataset, initial weights, batches and
+    negatives from the host pipeline, confounders / noise / dropout masks re-drawn from the torch CPU generator call
+    for call.  Loss of every step within 1e-5; final parameters within the drift the float64 oracle itself shows
+    against the fp32 reference after 24 Adam steps (tests/test_oracle_golden.py::test_oracle_follows_the_reference_at_config0)."""
+    from conftest import config0_draws, config0_problem
+    steps = 24
+    g, model, feat, expo, Xs = config0_problem(str(tmp_path), steps)
+    if str(g['torch_version']) != torch.__version__:
+        pytest.skip('random inputs are re-drawn from the torch CPU generator: needs torch %s' % g['torch_version'])
+    assert np.array_equal(Xs[0], g['X_first']) and np.array_equal(Xs[-1], g['X_last'])
+    model = model.cuda()
+    model.optimizer = model.make_fused_optimizer(lr=float(g['lr']), l2=float(g['l2']))
+    drop = float(g['dropout'])
+    b = Xs[0].shape[0] // 2
+    Y = torch.cat([torch.ones(b), torch.zeros(b)]).cuda()
+    for t, (si, noise, mask) in enumerate(config0_draws(g, model.item_num, steps)):
+        out = model.train_step({'X': torch.from_numpy(Xs[t]).cuda(), 'Y': Y, 'rank': 1, 'train': True, 'dropout': drop,
+                                'sample_item': si, 'noise': noise, 'dropout_mask': mask})
+        assert abs(float(out['loss']) - g['loss'][t]) < 1e-5 * abs(g['loss'][t]), t
+        if t == 0:
+            assert rel_err(out['prediction'].cpu().numpy(), g['pred_first']) < 1e-5
+    assert rel_err(out['prediction'].cpu().numpy(), g['pred_last']) < 2e-4
+    got = model_params(model)
+    assert rel_err(got['W'][::8], g['final_W_rows']) < 2e-4
+    assert rel_err(got['E_user'][g['users_last']], g['final_E_user_rows']) < 4e-4
+    assert rel_err(got['E_item'][g['items_last']], g['final_E_item_rows']) < 4e-4
+    assert rel_err(got['b'], g['final_b']) < 1e-3
+    norms = [np.linalg.norm(got[k].astype(np.float64)) for k in ('E_user', 'E_item', 'W', 'b')]
+    assert np.abs(np.array(norms) / g['norms'] - 1).max() < 1e-5
+    model.check_ids()

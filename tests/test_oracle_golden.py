@@ -180,3 +180,40 @@ def test_rank_users_property_against_brute_force():
                 assert (np.isnan(a) and np.isnan(b)) or abs(a - b) < 1e-12
 
     check()
+
+
+def test_oracle_follows_the_reference_at_config0(tmp_path):
+    """BASELINE.json configs[0] at full size (2 000 users x 5 000 items x 768-d, 256 pairs = 5 632 predictor rows per
+    step): 24 training steps of the UNMODIFIED reference (tests/golden/config0_train.npz, oracle/make_golden.py::
+    make_config0_train) replayed by the oracle from seeds alone — dataset, initial weights, batches and negatives (host
+    pipeline), confounders, noise and dropout masks (the torch CPU generator re-drawn call for call).  Per step the loss
+    agrees to 1e-6; parameters drift apart at Adam's lr/eps conditioning (float64 gradients here, fp32 there)."""
+    import torch
+    from conftest import config0_draws, config0_problem
+    steps = 24
+    g, model, feat, expo, Xs = config0_problem(str(tmp_path), steps)
+    if str(g['torch_version']) != torch.__version__:
+        pytest.skip('random inputs are re-drawn from the torch CPU generator: needs torch %s' % g['torch_version'])
+    assert np.array_equal(Xs[0], g['X_first']) and np.array_equal(Xs[-1], g['X_last'])     # batches + negatives
+    params = {'E_user': model.uid_embeddings.weight.detach().numpy().copy(),
+              'E_item': model.iid_embeddings.weight.detach().numpy().copy(),
+              'W': model.mlp[0].weight.detach().numpy().copy(), 'b': model.mlp[0].bias.detach().numpy().copy(),
+              'Feat': feat, 'expo': expo}
+    state = {k: {'m': np.zeros_like(params[k]), 'v': np.zeros_like(params[k])} for k in ('E_user', 'E_item', 'W', 'b')}
+    hp = dict(lr=float(g['lr']), l2=float(g['l2']), weight_decay=float(g['l2']))
+    for t, (si, noise, mask) in enumerate(config0_draws(g, params['E_item'].shape[0], steps)):
+        if t == 0:
+            assert np.array_equal(si.numpy(), g['sample_item_first'])                       # confounders bit-exact
+        p2, state, loss, pred = O.train_step(params, state, t + 1, Xs[t], si.numpy(), noise.numpy(), mask.numpy(),
+                                             int(g['A']), hp)
+        params = dict(p2, Feat=feat, expo=expo)
+        assert abs(loss - g['loss'][t]) < 1e-6 * abs(g['loss'][t]), t
+        if t == 0:
+            assert rel_err(pred, g['pred_first']) < 1e-5
+    assert rel_err(pred, g['pred_last']) < 2e-4
+    assert rel_err(params['W'][::8], g['final_W_rows']) < 1e-4
+    assert rel_err(params['E_user'][g['users_last']], g['final_E_user_rows']) < 2e-4
+    assert rel_err(params['E_item'][g['items_last']], g['final_E_item_rows']) < 2e-4
+    assert rel_err(params['b'], g['final_b']) < 5e-4
+    norms = [np.linalg.norm(params[k].astype(np.float64)) for k in ('E_user', 'E_item', 'W', 'b')]
+    assert np.abs(np.array(norms) / g['norms'] - 1).max() < 1e-5
