@@ -292,6 +292,52 @@ def make_config0_train(name='config0_train', seed=2019, steps=24, batch_size=128
         shutil.rmtree(tmp)
 
 
+def make_config0_eval(name='config0_eval', seed=2019, n_users=100, eval_batch_size=16384):
+    """BASELINE.json configs[0], the evaluation half: the first `n_users` test users of the configs[0] test set (each
+    with its positives + 1000 sampled negatives) scored by the UNMODIFIED reference (BaseRunner.predict ->
+    DCCF.predict, batches of 16 384 pairs = 360 448 predictor rows) and ranked by its evaluate_method
+    (ndcg@5 / recall@5 / precision@5).  As in make_config0_train the random inputs are re-drawable (torch CPU
+    generator seeded with seed + 2 right before predict: per batch randint -> normal_), only outputs are stored."""
+    ref = rh.load_reference()
+    tmp = tempfile.mkdtemp()
+    try:
+        U, I, per = synth.PRESETS['tiny']
+        d = synth.write_dataset(tmp, 'tiny', U, I, per, feat_dim=768, seed=seed)
+        with rh.cpu_shims():
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+            dl = ref.DataLoader(path=tmp, dataset='tiny', label='label', sep=',')
+            model = rh.build_reference_model(ref, d, 'tiny', SENT, dl.user_num, dl.item_num, random_seed=seed,
+                                             model_path=os.path.join(tmp, 'm.pt'))
+            dl.drop_neg()
+            dp = ref.DataProcessor(dl, model, rank=1, test_neg_n=1000)
+            te = dp.get_test_data()
+            uid = np.asarray(te['uid'])
+            _, first = np.unique(uid, return_index=True)
+            users = uid[np.sort(first)][:n_users]
+            rows = np.nonzero(np.isin(uid, users))[0]
+            sub = {k: np.asarray(te[k])[rows] for k in ('uid', 'iid', 'Y', 'X')}
+            sub['sample_id'] = np.arange(len(rows))
+            runner = ref.BaseRunner(optimizer='Adam', learning_rate=1e-3, epoch=1, batch_size=128,
+                                    eval_batch_size=eval_batch_size, dropout=0.2, l2=1e-4,
+                                    metrics='ndcg@5,recall@5,precision@5', check_epoch=1, early_stop=1)
+            rh.reset_tape()
+            torch.manual_seed(seed + 2)              # the replay point of the test
+            pred = runner.predict(model, sub, dp)
+            metrics = ['ndcg@5', 'recall@5', 'precision@5']
+            vals = model.evaluate_method(pred, sub, metrics=metrics)
+            out = {'seed': seed, 'n_users': n_users, 'eval_batch_size': eval_batch_size, 'users': users,
+                   'n_rows': len(rows),
+                   'torch_version': np.array(torch.__version__), 'std': 0.1, 'S': 10, 'A': 2,
+                   'X_digest': np.array(array_digest(sub['X'])), 'pred': np.asarray(pred, dtype=np.float32),
+                   'sample_item_first_digest': np.array(array_digest(rh.tape().calls[0]['sample_item'].numpy())),
+                   'metrics': np.array(metrics), 'values': np.array([float(v) for v in vals], dtype=np.float64)}
+        np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), **out)
+        print(name, len(rows), 'rows', dict(zip(metrics, vals)))
+    finally:
+        shutil.rmtree(tmp)
+
+
 def make_metrics_fixture(name='metrics', seed=5):
     ref = rh.load_reference()
     rs = np.random.RandomState(seed)
@@ -332,4 +378,5 @@ if __name__ == '__main__':
     make_sampler_fixture()
     make_config0_digest()
     make_config0_train()
+    make_config0_eval()
     make_metrics_fixture()

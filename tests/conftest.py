@@ -84,3 +84,48 @@ def config0_draws(g, n_items, steps):
         noise = torch.empty((N, 768), dtype=torch.float32).normal_(mean=0.0, std=std)
         mask = torch.empty((N, 64), dtype=torch.float32).bernoulli_(1.0 - drop).div_(1.0 - drop)
         yield si, noise, mask
+
+
+def config0_eval_problem(root):
+    """The evaluation fixture of BASELINE.json configs[0] rebuilt from seeds (tests/golden/config0_eval.npz holds the
+    reference's predictions and metrics): the first n_users users of the configs[0] test set, positives + 1000 negatives
+    each.  Returns (g, model, feat, expo, data dict of those rows)."""
+    import torch
+    from dccf_b200 import synth
+    from dccf_b200.data_loaders.DataLoader import DataLoader
+    from dccf_b200.data_processor.DataProcessor import DataProcessor
+    from dccf_b200.models.DCCF import DCCF
+    g = np.load(os.path.join(GOLDEN, 'config0_eval.npz'), allow_pickle=False)
+    seed = int(g['seed'])
+    U, I, per = synth.PRESETS['tiny']
+    d = synth.write_dataset(root, 'tiny', U, I, per, feat_dim=768, seed=seed)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    dl = DataLoader(path=root, dataset='tiny', label='label', sep=',')
+    model = DCCF(path=d, dataset='tiny', sentence_model=synth.DEFAULT_SENTENCE_MODEL, sample_num=int(g['S']),
+                 attribute_num=int(g['A']), std=float(g['std']), label_min=0, label_max=1, feature_num=0,
+                 user_num=dl.user_num, item_num=dl.item_num, u_vector_size=64, i_vector_size=64, n_layers=1,
+                 random_seed=seed, model_path=os.path.join(root, 'm.pt'))
+    model.apply(model.init_paras)
+    dl.drop_neg()
+    dp = DataProcessor(dl, model, rank=1, test_neg_n=1000)
+    te = dp.get_test_data()
+    rows = np.nonzero(np.isin(te['uid'], g['users']))[0]
+    sub = {k: np.asarray(te[k])[rows] for k in ('uid', 'iid', 'Y', 'X')}
+    sub['sample_id'] = np.arange(len(rows))
+    feat = np.load(os.path.join(d, 'tiny_%s.npy' % synth.DEFAULT_SENTENCE_MODEL))
+    expo = np.load(os.path.join(d, 'tiny.ips_expo_prob.npy'))
+    return g, model, feat, expo, sub
+
+
+def config0_eval_draws(g, n_items, n_rows):
+    """Per evaluation batch (sample_item, noise) as the reference harness drew them: generator seeded with seed + 2, per
+    batch randint -> normal_ (dropout is off during evaluation: no mask is drawn)."""
+    import torch
+    S, A, std, B = int(g['S']), int(g['A']), float(g['std']), int(g['eval_batch_size'])
+    torch.manual_seed(int(g['seed']) + 2)
+    for a in range(0, n_rows, B):
+        P = min(B, n_rows - a)
+        si = torch.randint(n_items, size=(P, S))
+        noise = torch.empty((P * (S + 1) * A, 768), dtype=torch.float32).normal_(mean=0.0, std=std)
+        yield a, a + P, si, noise

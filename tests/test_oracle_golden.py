@@ -217,3 +217,33 @@ def test_oracle_follows_the_reference_at_config0(tmp_path):
     assert rel_err(params['b'], g['final_b']) < 5e-4
     norms = [np.linalg.norm(params[k].astype(np.float64)) for k in ('E_user', 'E_item', 'W', 'b')]
     assert np.abs(np.array(norms) / g['norms'] - 1).max() < 1e-5
+
+
+def test_oracle_follows_the_reference_evaluation_at_config0(tmp_path):
+    """BASELINE.json configs[0], evaluation: 100 test users x (positives + 1000 negatives) scored by the UNMODIFIED
+    reference in batches of 16 384 pairs (tests/golden/config0_eval.npz, oracle/make_golden.py::make_config0_eval).
+    The oracle ranker reproduces the reference's ndcg@5 / recall@5 / precision@5 from the reference's predictions, and
+    the oracle scorer reproduces the predictions of the first two batches (32 768 pairs = 720 896 predictor rows) from
+    seeds alone — ids from the host pipeline, confounders and noise re-drawn from the torch CPU generator."""
+    import hashlib
+    import torch
+    from conftest import config0_eval_draws, config0_eval_problem
+    g, model, feat, expo, sub = config0_eval_problem(str(tmp_path))
+    if str(g['torch_version']) != torch.__version__:
+        pytest.skip('random inputs are re-drawn from the torch CPU generator: needs torch %s' % g['torch_version'])
+    assert len(sub['Y']) == int(g['n_rows'])
+    X = np.ascontiguousarray(sub['X'])
+    h = hashlib.sha256()
+    h.update(str(X.dtype).encode() + b'|' + str(X.shape).encode() + b'|')
+    h.update(X.tobytes())
+    assert h.hexdigest() == str(g['X_digest'])                                   # the evaluation set itself
+    vals = O.evaluate_method(g['pred'], sub, [str(m) for m in g['metrics']])
+    assert np.abs(np.array(vals) - g['values']).max() < 1e-6                     # ranking metrics to 1e-6
+    params = {'E_user': model.uid_embeddings.weight.detach().numpy(), 'E_item': model.iid_embeddings.weight.detach().numpy(),
+              'W': model.mlp[0].weight.detach().numpy(), 'b': model.mlp[0].bias.detach().numpy(), 'Feat': feat,
+              'expo': expo}
+    for k, (a, b, si, noise) in enumerate(config0_eval_draws(g, params['E_item'].shape[0], len(sub['Y']))):
+        pred = O.predict(params, sub['X'][a:b], si.numpy(), noise.numpy(), None, int(g['A']))['pred']
+        assert rel_err(pred, g['pred'][a:b]) < 1e-5
+        if k == 1:
+            break
