@@ -338,6 +338,40 @@ def make_config0_eval(name='config0_eval', seed=2019, n_users=100, eval_batch_si
         shutil.rmtree(tmp)
 
 
+def make_ipsmf_fixture(name='ipsmf', U=70, I=110, seed=2019, M=0.1):
+    """IPSBiasedMF.predict of the UNMODIFIED reference (src/models/IPSBiasedMF.py:37-57) over the whole U x I grid:
+    the exposure source of the scaled configuration and the producer of ips_expo_prob.npy (README.md:27-29)."""
+    ref = rh.load_reference()
+    tmp = tempfile.mkdtemp()
+    try:
+        d = os.path.join(tmp, 'p')
+        os.makedirs(d)
+        rs = np.random.RandomState(seed + 3)
+        prop = rs.random_sample(I).astype(np.float32)
+        prop[:5] = [0.0, 0.05, 0.1, 0.1000001, 0.5]            # below, at and above the clamp M
+        np.save(os.path.join(d, 'p' + ref.global_p.PROPENSITY_SUFFIX), prop)
+        with rh.cpu_shims():
+            torch.manual_seed(seed)
+            model = ref.IPSBiasedMF(path=d, dataset='p', M=M, label_min=0, label_max=1, feature_num=0, user_num=U,
+                                    item_num=I, u_vector_size=64, i_vector_size=64, random_seed=seed,
+                                    model_path=os.path.join(tmp, 'm.pt'))
+            with torch.no_grad():                              # biases away from their init so that every term counts
+                for p_ in model.parameters():
+                    p_.copy_(torch.from_numpy(np.asarray(rs.standard_normal(tuple(p_.shape)) * 0.3, dtype=np.float32)))
+            uu, ii = np.meshgrid(np.arange(U), np.arange(I), indexing='ij')
+            X = torch.from_numpy(np.stack([uu.reshape(-1), ii.reshape(-1)], 1).astype(np.int64))
+            pred = model.predict({'X': X})['prediction'].detach().numpy().reshape(U, I)
+            out = {'mf_user': model.uid_embeddings.weight.detach().numpy(), 'mf_item': model.iid_embeddings.weight.detach().numpy(),
+                   'mf_user_bias': model.user_bias.weight.detach().numpy().reshape(-1),
+                   'mf_item_bias': model.item_bias.weight.detach().numpy().reshape(-1),
+                   'mf_global_bias': np.float32(model.global_bias.detach().numpy()), 'propensity': prop,
+                   'mf_min_propensity': np.float32(M), 'pred': pred.astype(np.float32)}
+        np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), **out)
+        print(name, pred.shape, float(np.abs(pred).max()))
+    finally:
+        shutil.rmtree(tmp)
+
+
 def make_metrics_fixture(name='metrics', seed=5):
     ref = rh.load_reference()
     rs = np.random.RandomState(seed)
@@ -379,4 +413,5 @@ if __name__ == '__main__':
     make_config0_digest()
     make_config0_train()
     make_config0_eval()
+    make_ipsmf_fixture()
     make_metrics_fixture()

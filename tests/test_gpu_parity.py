@@ -829,3 +829,28 @@ def test_evaluation_follows_the_reference_at_config0(tmp_path):
     assert rel_err(pred.cpu().numpy(), g['pred']) < 1e-5
     vals = BaseModel.evaluate_method(pred, sub, [str(m) for m in g['metrics']])
     assert np.abs(np.array(vals) - g['values']).max() < 1e-6
+
+
+@pytest.mark.xfail(strict=False, reason='written after the GPU budget of round 1 was spent: first hardware run at round '
+                                        'end; XPASS = verified (the kernels it drives are the validated ones)')
+def test_ipsmf_exposure_matches_reference(golden):
+    """The reference's IPSBiasedMF.predict over a whole U x I grid (tests/golden/ipsmf.npz, src/models/IPSBiasedMF.py:
+    37-57) against the full-catalogue tcgen05 GEMM (the ips_expo_prob.npy producer) and against the on-the-fly
+    exposure of the pairwise scorer (exposure mode 1): a DCCF model fed those factors equals a DCCF model fed the
+    reference's dense matrix."""
+    from dccf_b200 import full_catalogue
+    g = golden('ipsmf')
+    fac = {k: (g[k] if g[k].ndim else float(g[k])) for k in ('mf_user', 'mf_item', 'mf_user_bias', 'mf_item_bias',
+                                                              'mf_global_bias', 'propensity', 'mf_min_propensity')}
+    dev = {k: (torch.from_numpy(np.ascontiguousarray(v)).cuda() if isinstance(v, np.ndarray) else v) for k, v in fac.items()}
+    got = full_catalogue.ipsmf_exposure(dev)
+    assert rel_err(got.cpu().numpy(), g['pred']) < 3e-6
+    U, I = g['pred'].shape
+    F, P, S, A = 64, 48, 10, 2
+    params, X, si, noise, _ = random_problem(5, U, I, F, P, S, A, 0.1, 0.0)
+    fd = {'X': torch.from_numpy(X).cuda(), 'rank': 1, 'train': False, 'dropout': 0.0,
+          'sample_item': torch.from_numpy(si), 'noise': torch.from_numpy(noise)}
+    a = make_model(params, S, A, 0.1, expo_factors=fac).predict(fd)['prediction'].cpu().numpy()
+    b = make_model(dict(params, expo=g['pred']), S, A, 0.1).predict(fd)['prediction'].cpu().numpy()
+    # exposure values reach |29| here (propensity clamp 0.1): an fp32 ulp of the logit moves a softmax weight by ~3e-6
+    assert rel_err(a, b) < 3e-5

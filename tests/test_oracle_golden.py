@@ -247,3 +247,16 @@ def test_oracle_follows_the_reference_evaluation_at_config0(tmp_path):
         assert rel_err(pred, g['pred'][a:b]) < 1e-5
         if k == 1:
             break
+
+
+def test_ipsmf_exposure_matches_reference(golden):
+    """oracle.exposure_values (dict form) == IPSBiasedMF.predict of the unmodified reference over a whole U x I grid
+    (src/models/IPSBiasedMF.py:37-57), including propensities below, at and above the clamp M."""
+    g = golden('ipsmf')
+    fac = {k: (g[k] if g[k].ndim else float(g[k])) for k in ('mf_user', 'mf_item', 'mf_user_bias', 'mf_item_bias',
+                                                              'mf_global_bias', 'propensity', 'mf_min_propensity')}
+    U, I = g['pred'].shape
+    got = O.exposure_values(fac, np.arange(U), np.tile(np.arange(I), (U, 1)))
+    assert rel_err(got, g['pred']) < 1e-6
+    fac64 = {k: (v.astype(np.float64) if isinstance(v, np.ndarray) else v) for k, v in fac.items()}
+    assert rel_err(O.exposure_values(fac64, np.arange(U), np.tile(np.arange(I), (U, 1))), g['pred']) < 1e-6
