@@ -13,3 +13,9 @@ timeout 800 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 echo "rc=$?"
 cd ..
 grep -E "data parallel|Epoch|Test (Before|After)|Best Iter|diverged|Error|error" gpurun_out/dp_cli_$N.log | tail -20
+# the scaled configuration (row-sharded users + on-the-fly IPS-MF exposure + data parallel): equality with one GPU at a
+# small shape, then ms / step at 10 M users x 1 M items split over the N ranks
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 \
+    tools/scaled_check.py > gpurun_out/scaled_check_$N.log 2>&1
+echo "scaled rc=$?"
+grep -E "scaled|SCALED|Error|error" gpurun_out/scaled_check_$N.log | tail -8
