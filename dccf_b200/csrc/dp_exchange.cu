@@ -93,6 +93,27 @@ __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send,
     // one system-scope fence per CTA, by the thread that publishes the CTA's arrival, after the CTA barrier has
     // ordered every thread's stores before it (a fence in each of the 13 K threads made the push take ~17 us)
     __syncthreads();
+#ifdef DCCF_DP_PARALLEL_FLAGS
+    // Build variant (round-2 experiment, python -m dccf_b200.build with DCCF_BUILD_DEFS=-DDCCF_DP_PARALLEL_FLAGS): the
+    // last CTA publishes the arrival to the peers with one release store per LANE instead of `world` release stores in
+    // sequence by one thread — each st.release.sys waits for the NVLink round trip of what precedes it, and eight of
+    // them back to back are the likely bulk of the ~14 us a push costs whatever its size.  Ordering: every CTA's data
+    // stores -> its barrier -> thread 0's system fence -> counter increment; the last CTA's thread 0 observes all
+    // increments, fences, and the CTA barrier below orders the publishing lanes after it (release is cumulative).
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const int32_t prev = atomicAdd(cta_counter, 1);
+        s_last = (prev == (int32_t)gridDim.x - 1) ? 1 : 0;
+        if (s_last) {
+            __threadfence_system();
+            *cta_counter = 0;
+        }
+    }
+    __syncthreads();
+    if (s_last && (int)threadIdx.x < world)
+        st_release_sys(reinterpret_cast<int32_t*>(peers.base[threadIdx.x] + flag_off) + rank, epoch);
+#else
     if (threadIdx.x == 0) {
         __threadfence_system();
         const int32_t prev = atomicAdd(cta_counter, 1);
@@ -103,6 +124,7 @@ __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send,
             *cta_counter = 0;
         }
     }
+#endif
     tl_end(8);
 }
 

@@ -19,3 +19,17 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
     tools/scaled_check.py > gpurun_out/scaled_check_$N.log 2>&1
 echo "scaled rc=$?"
 grep -E "scaled|SCALED|Error|error" gpurun_out/scaled_check_$N.log | tail -8
+# A/B of the data-parallel push: arrival flags published by one release store per lane (variant pf) against the sequence of
+# `world` release stores by one thread (default); dp_check first (correctness), then the bench at N ranks
+DCCF_LIB_VARIANT=pf DCCF_BUILD_DEFS="-DDCCF_DP_PARALLEL_FLAGS" python -m dccf_b200.build > /dev/null
+for v in "" pf; do
+  DCCF_LIB_VARIANT=$v timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+      --master-port 29515 tools/dp_check.py 2>&1 | grep -E "DP CHECK|Error|assert" | tail -2
+  DCCF_LIB_VARIANT=$v timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+      --master-port 29516 bench.py --gpus $N --steps 200 --warmup 10 > gpurun_out/bench_r2a_dp${N}_${v:-base}.json 2>/dev/null
+  python - <<P
+import json
+d = json.loads(open('gpurun_out/bench_r2a_dp${N}_${v:-base}.json').read().strip().splitlines()[-1])
+print('dp$N ${v:-base}', 'value', round(d['value']), 'ms/step', round(d['ms_per_step'], 5), 'b2b', round(d['back_to_back']['ms_per_step'], 5))
+P
+done
