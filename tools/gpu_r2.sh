@@ -56,3 +56,12 @@ d = json.loads(open('gpurun_out/bench_r2a_ab_p7.json').read().strip().splitlines
 k = d['roofline'].get('kernels', {})
 print('p7', 'ms/step', round(d['ms_per_step'], 5), 'eval ms/batch', round(d['eval']['ms_per_batch'], 4), {n: round(o['us'], 1) for n, o in k.items()})
 P
+# 7. the whole command line at the electronics shape: wall time of an epoch (host pipeline + training + the three
+#    evaluations) from the log of src/main.py — the number a user of the reference's CLI sees
+python -m dccf_b200.synth --path /tmp/e2e/datasets/ --dataset electronics --preset electronics > /dev/null
+(cd src && timeout 1200 python main.py --rank 1 --model_name DCCF --optimizer Adam --lr 0.001 --dataset electronics \
+    --path /tmp/e2e/datasets/ --metric ndcg@5,recall@5,precision@5 --gpu 0 --epoch 2 --test_neg_n 1000 \
+    --log_file /tmp/e2e/log.txt --result_file /tmp/e2e/result.npy --model_path /tmp/e2e/model/m.pt > ../gpurun_out/cli_electronics.log 2>&1)
+grep -E "Epoch +[0-9]+ \[|Test (Before|After)|Init:" /tmp/e2e/log.txt | cut -c1-200 | tee gpurun_out/cli_electronics_epochs.log
+# ncu exports -> profiles tables: ncu -i gpurun_out/prof_r2a_legs.ncu-rep --page raw --csv > gpurun_out/prof_r2a_legs_raw.csv
+#                                 python tools/ncu_summary.py gpurun_out/prof_r2a_legs_raw.csv --mean > profiles/r2a_ncu_legs_summary.csv
