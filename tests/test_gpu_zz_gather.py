@@ -1,7 +1,8 @@
 """Parity of the two inference paths added after round 1's GPU work: the noise-free gather scorer (dccf_score_gather,
 csrc/gather_scores.cu) against the reference fixture, the oracle and the general FP32 scorer; and evaluation noise
 drawn in the 64-d image of W_f (DCCF.eval_noise = 'projected') against the reference formula on the equivalent 768-d
-noise tensor.  Needs a GPU.
+noise tensor; and torch's CPU generator continued on the device (k_confounder_draw, host_rng.DeviceStream,
+DCCF.device_confounders) against torch.randint itself.  Needs a GPU.
 
 The kernel was written after round 1's GPU budget was spent, so its first execution on a B200 is the round-end run of
 this file.  Two precautions follow from that: the cases run in a CHILD process (a faulting kernel poisons the CUDA
