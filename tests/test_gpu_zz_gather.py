@@ -30,8 +30,12 @@ CASES = ['reference_fixture', 'oracle_default_shape', 'oracle_ragged_many_slots'
 def worker_output():
     """All cases in ONE child process (one torch import, one CUDA context); each prints `GATHER_OK <case>` or
     `GATHER_FAIL <case>: <why>`.  A hard fault ends the child: the cases after it then report 'not reached'."""
-    r = subprocess.run([sys.executable, os.path.abspath(__file__)] + CASES, capture_output=True, text=True, timeout=900,
-                       cwd=ROOT)
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__)] + CASES, capture_output=True, text=True,
+                           timeout=900, cwd=ROOT)
+    except subprocess.TimeoutExpired as e:
+        out = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or '')
+        return -9, out, 'child timed out after 900 s'
     return r.returncode, r.stdout, r.stderr
 
 
