@@ -10,6 +10,9 @@ samples/s with the batches already in HBM, `e2e` the same through the public API
 buffers (confounder draw on the CPU generator, H2D of ids, D2H of the loss every step).  The `eval`
 object holds the evaluation half of the metric: users/s for ranking each test user's positive against
 test_neg_n = 1000 sampled negatives (scoring + on-device top-k/ndcg/recall/precision@5).
+`eval_noise_free` (a --std 0 model scored by the gather kernel) and `eval_projected_noise` (the reference defaults with
+the feature noise drawn in the 64-d image of W_f, opt-in) are measured by a child process on rank 0 at N = 1 and
+reported next to it (--no-extra-legs skips them); the headline objects keep the reference's formulation.
 """
 import argparse
 import json
