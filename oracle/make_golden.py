@@ -372,6 +372,52 @@ def make_ipsmf_fixture(name='ipsmf', U=70, I=110, seed=2019, M=0.1):
         shutil.rmtree(tmp)
 
 
+def make_run_fixture(name='run_recmodel', seed=2019, epochs=3, n_users=120, n_items=150, per_user=10, test_neg_n=5,
+                     batch_size=64, lr=0.01, l2=1e-4):
+    """A WHOLE RUN of the unmodified reference, src/main.py's sequence (main.py:101-192) with its own DataLoader,
+    DataProcessor, RecModel and BaseRunner on CPU: seeds -> load -> model + init_paras -> drop_neg -> "Test Before
+    Training" -> runner.train (fit / evaluate / model selection / load best) -> "Test After Training" -> predictions.
+    RecModel (plain matrix factorisation, src/models/RecModel.py) needs no CUDA, so every number is reproducible on CPU:
+    the host mirror (loader, processor, runner, BaseModel/RecModel, rmse / mae) has to reproduce all of it."""
+    ref = rh.load_reference()
+    RefRecModel = sys.modules['models.RecModel'].RecModel
+    tmp = tempfile.mkdtemp()
+    try:
+        synth.write_dataset(tmp, 'toy', n_users, n_items, per_user, feat_dim=64, seed=seed + 5)
+        model_path = os.path.join(tmp, 'model', 'm.pt')
+        os.makedirs(os.path.dirname(model_path))
+        with rh.cpu_shims():
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+            dl = ref.DataLoader(path=tmp, dataset='toy', label='label', sep=',')
+            model = RefRecModel(label_min=dl.label_min, label_max=dl.label_max, feature_num=0, user_num=dl.user_num,
+                                item_num=dl.item_num, u_vector_size=64, i_vector_size=64, random_seed=seed,
+                                model_path=model_path)
+            model.apply(model.init_paras)
+            dl.drop_neg()
+            dp = ref.DataProcessor(dl, model, rank=1, test_neg_n=test_neg_n)
+            runner = ref.BaseRunner(optimizer='Adam', learning_rate=lr, epoch=epochs, batch_size=batch_size,
+                                    eval_batch_size=16384, dropout=0.2, l2=l2, metrics='rmse,mae', check_epoch=1,
+                                    early_stop=1)
+            before = runner.evaluate(model, dp.get_test_data(), dp)
+            runner.train(model, dp, skip_eval=0)
+            after = runner.evaluate(model, dp.get_test_data(), dp)
+            pred = runner.predict(model, dp.get_test_data(), dp)
+            sd = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+        out = {'seed': seed, 'epochs': epochs, 'n_users': n_users, 'n_items': n_items, 'per_user': per_user,
+               'test_neg_n': test_neg_n, 'batch_size': batch_size, 'lr': lr, 'l2': l2,
+               'before': np.array(before, dtype=np.float64), 'after': np.array(after, dtype=np.float64),
+               'train_results': np.array(runner.train_results, dtype=np.float64),
+               'valid_results': np.array(runner.valid_results, dtype=np.float64),
+               'test_results': np.array(runner.test_results, dtype=np.float64), 'pred': np.asarray(pred, np.float32)}
+        for k, v in sd.items():
+            out['sd_' + k] = v
+        np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), **out)
+        print(name, 'before', before, 'valid', runner.valid_results, 'after', after)
+    finally:
+        shutil.rmtree(tmp)
+
+
 def make_metrics_fixture(name='metrics', seed=5):
     ref = rh.load_reference()
     rs = np.random.RandomState(seed)
@@ -414,4 +460,5 @@ if __name__ == '__main__':
     make_config0_train()
     make_config0_eval()
     make_ipsmf_fixture()
+    make_run_fixture()
     make_metrics_fixture()

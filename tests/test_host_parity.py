@@ -455,3 +455,43 @@ def test_config0_host_pipeline_digest(tmp_path):
         sid = np.concatenate([np.asarray(b['sample_id']) for b in batches]).astype(np.int64)
         assert digest(sid) == want['digests']['train_ep%d_sample_id' % ep]
     assert [int(x) for x in np.random.get_state()[1][:8]] == want['np_state_after']
+
+
+def test_whole_run_equals_reference_run(golden, tmp_path):
+    """src/main.py's whole sequence with the mirrored classes == the same sequence of the UNMODIFIED reference
+    (tests/golden/run_recmodel.npz, oracle/make_golden.py::make_run_fixture; RecModel on CPU so that every number is
+    reproducible): "Test Before Training", the per-epoch train / validation / test metric lists of runner.train (i.e.
+    shuffles, negatives, Adam steps with l2 + clip, evaluation, model selection and the reload of the best epoch),
+    "Test After Training", the final predictions and the checkpointed parameters."""
+    from dccf_b200.models.RecModel import RecModel
+    g = golden('run_recmodel')
+    seed = int(g['seed'])
+    synth.write_dataset(str(tmp_path), 'toy', int(g['n_users']), int(g['n_items']), int(g['per_user']), feat_dim=64,
+                        seed=seed + 5)
+    model_path = str(tmp_path / 'model' / 'm.pt')
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    dl = DataLoader(path=str(tmp_path), dataset='toy', label='label', sep=',')
+    model = RecModel(label_min=dl.label_min, label_max=dl.label_max, feature_num=0, user_num=dl.user_num,
+                     item_num=dl.item_num, u_vector_size=64, i_vector_size=64, random_seed=seed, model_path=model_path)
+    model.apply(model.init_paras)
+    dl.drop_neg()
+    dp = DataProcessor(dl, model, rank=1, test_neg_n=int(g['test_neg_n']))
+    runner = BaseRunner(optimizer='Adam', learning_rate=float(g['lr']), epoch=int(g['epochs']),
+                        batch_size=int(g['batch_size']), eval_batch_size=16384, dropout=0.2, l2=float(g['l2']),
+                        metrics='rmse,mae', check_epoch=1, early_stop=1)
+    runner.show_progress = False
+    before = runner.evaluate(model, dp.get_test_data(), dp)
+    runner.train(model, dp, skip_eval=0)
+    after = runner.evaluate(model, dp.get_test_data(), dp)
+    pred = runner.predict(model, dp.get_test_data(), dp)
+    assert np.allclose(before, g['before'], rtol=1e-6, atol=0)
+    for ours, name in ((runner.train_results, 'train_results'), (runner.valid_results, 'valid_results'),
+                       (runner.test_results, 'test_results')):
+        assert np.asarray(ours).shape == g[name].shape and np.allclose(ours, g[name], rtol=1e-6, atol=0), name
+    assert np.allclose(after, g['after'], rtol=1e-6, atol=0)
+    assert np.abs(pred - g['pred']).max() <= 1e-6 * np.abs(g['pred']).max()
+    sd = model.state_dict()
+    assert sorted('sd_' + k for k in sd) == sorted(k for k in g.files if k.startswith('sd_'))
+    for k, v in sd.items():
+        assert np.abs(v.numpy() - g['sd_' + k]).max() <= 1e-6 * np.abs(g['sd_' + k]).max(), k
