@@ -372,7 +372,7 @@ def make_ipsmf_fixture(name='ipsmf', U=70, I=110, seed=2019, M=0.1):
         shutil.rmtree(tmp)
 
 
-def make_run_fixture(name='run_recmodel', seed=2019, epochs=3, n_users=120, n_items=150, per_user=10, test_neg_n=5,
+def make_run_fixture(name='run_recmodel', rank=1, seed=2019, epochs=3, n_users=120, n_items=150, per_user=10, test_neg_n=5,
                      batch_size=64, lr=0.01, l2=1e-4):
     """A WHOLE RUN of the unmodified reference, src/main.py's sequence (main.py:101-192) with its own DataLoader,
     DataProcessor, RecModel and BaseRunner on CPU: seeds -> load -> model + init_paras -> drop_neg -> "Test Before
@@ -394,8 +394,9 @@ def make_run_fixture(name='run_recmodel', seed=2019, epochs=3, n_users=120, n_it
                                 item_num=dl.item_num, u_vector_size=64, i_vector_size=64, random_seed=seed,
                                 model_path=model_path)
             model.apply(model.init_paras)
-            dl.drop_neg()
-            dp = ref.DataProcessor(dl, model, rank=1, test_neg_n=test_neg_n)
+            if rank == 1:                           # main.py:157-158
+                dl.drop_neg()
+            dp = ref.DataProcessor(dl, model, rank=rank, test_neg_n=test_neg_n)
             runner = ref.BaseRunner(optimizer='Adam', learning_rate=lr, epoch=epochs, batch_size=batch_size,
                                     eval_batch_size=16384, dropout=0.2, l2=l2, metrics='rmse,mae', check_epoch=1,
                                     early_stop=1)
@@ -404,7 +405,7 @@ def make_run_fixture(name='run_recmodel', seed=2019, epochs=3, n_users=120, n_it
             after = runner.evaluate(model, dp.get_test_data(), dp)
             pred = runner.predict(model, dp.get_test_data(), dp)
             sd = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
-        out = {'seed': seed, 'epochs': epochs, 'n_users': n_users, 'n_items': n_items, 'per_user': per_user,
+        out = {'seed': seed, 'rank': rank, 'epochs': epochs, 'n_users': n_users, 'n_items': n_items, 'per_user': per_user,
                'test_neg_n': test_neg_n, 'batch_size': batch_size, 'lr': lr, 'l2': l2,
                'before': np.array(before, dtype=np.float64), 'after': np.array(after, dtype=np.float64),
                'train_results': np.array(runner.train_results, dtype=np.float64),
@@ -461,4 +462,5 @@ if __name__ == '__main__':
     make_config0_eval()
     make_ipsmf_fixture()
     make_run_fixture()
+    make_run_fixture(name='run_recmodel_rank0', rank=0)
     make_metrics_fixture()

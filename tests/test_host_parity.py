@@ -457,15 +457,16 @@ def test_config0_host_pipeline_digest(tmp_path):
     assert [int(x) for x in np.random.get_state()[1][:8]] == want['np_state_after']
 
 
-def test_whole_run_equals_reference_run(golden, tmp_path):
+@pytest.mark.parametrize('fixture', ['run_recmodel', 'run_recmodel_rank0'])
+def test_whole_run_equals_reference_run(golden, tmp_path, fixture):
     """src/main.py's whole sequence with the mirrored classes == the same sequence of the UNMODIFIED reference
     (tests/golden/run_recmodel.npz, oracle/make_golden.py::make_run_fixture; RecModel on CPU so that every number is
     reproducible): "Test Before Training", the per-epoch train / validation / test metric lists of runner.train (i.e.
     shuffles, negatives, Adam steps with l2 + clip, evaluation, model selection and the reload of the best epoch),
     "Test After Training", the final predictions and the checkpointed parameters."""
     from dccf_b200.models.RecModel import RecModel
-    g = golden('run_recmodel')
-    seed = int(g['seed'])
+    g = golden(fixture)           # rank 1: top-n recommendation (BPR, sampled negatives); rank 0: rating prediction (MSE)
+    seed, rank = int(g['seed']), int(g['rank'])
     synth.write_dataset(str(tmp_path), 'toy', int(g['n_users']), int(g['n_items']), int(g['per_user']), feat_dim=64,
                         seed=seed + 5)
     model_path = str(tmp_path / 'model' / 'm.pt')
@@ -475,8 +476,9 @@ def test_whole_run_equals_reference_run(golden, tmp_path):
     model = RecModel(label_min=dl.label_min, label_max=dl.label_max, feature_num=0, user_num=dl.user_num,
                      item_num=dl.item_num, u_vector_size=64, i_vector_size=64, random_seed=seed, model_path=model_path)
     model.apply(model.init_paras)
-    dl.drop_neg()
-    dp = DataProcessor(dl, model, rank=1, test_neg_n=int(g['test_neg_n']))
+    if rank == 1:
+        dl.drop_neg()
+    dp = DataProcessor(dl, model, rank=rank, test_neg_n=int(g['test_neg_n']))
     runner = BaseRunner(optimizer='Adam', learning_rate=float(g['lr']), epoch=int(g['epochs']),
                         batch_size=int(g['batch_size']), eval_batch_size=16384, dropout=0.2, l2=float(g['l2']),
                         metrics='rmse,mae', check_epoch=1, early_stop=1)
