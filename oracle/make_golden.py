@@ -419,6 +419,54 @@ def make_run_fixture(name='run_recmodel', rank=1, seed=2019, epochs=3, n_users=1
         shutil.rmtree(tmp)
 
 
+def make_run_fixture_dccf(name='run_dccf', seed=2019, epochs=2, n_users=120, n_items=150, per_user=10, test_neg_n=20,
+                          batch_size=64, lr=1e-3, l2=1e-4):
+    """A whole run of the unmodified reference with DCCF itself, in the deterministic configuration --std 0 --dropout 0
+    (no feature noise, no dropout: the only random inputs are the shuffles / negatives on the numpy generator and the
+    confounder draws on the torch CPU generator, both reproducible).  The harness draws the (zero) noise from a
+    private generator, as a GPU run of the reference would from the CUDA generator, so the CPU generator sees exactly
+    the confounder draws (ref_harness.use_device_rng).  Sequence of src/main.py:101-192 with ndcg@5 / recall@5 /
+    precision@5: before, per epoch (train rmse/mae, validation, test), after, predictions, checkpoint."""
+    ref = rh.load_reference()
+    tmp = tempfile.mkdtemp()
+    try:
+        d = synth.write_dataset(tmp, 'toy', n_users, n_items, per_user, feat_dim=64, seed=seed + 5)
+        model_path = os.path.join(tmp, 'model', 'm.pt')
+        os.makedirs(os.path.dirname(model_path))
+        rh.use_device_rng(torch.Generator().manual_seed(12345))
+        try:
+            with rh.cpu_shims():
+                torch.manual_seed(seed)
+                np.random.seed(seed)
+                dl = ref.DataLoader(path=tmp, dataset='toy', label='label', sep=',')
+                model = rh.build_reference_model(ref, d, 'toy', SENT, dl.user_num, dl.item_num, std=0.0,
+                                                 random_seed=seed, model_path=model_path)
+                dl.drop_neg()
+                dp = ref.DataProcessor(dl, model, rank=1, test_neg_n=test_neg_n)
+                runner = ref.BaseRunner(optimizer='Adam', learning_rate=lr, epoch=epochs, batch_size=batch_size,
+                                        eval_batch_size=16384, dropout=0.0, l2=l2,
+                                        metrics='ndcg@5,recall@5,precision@5', check_epoch=1, early_stop=1)
+                before = runner.evaluate(model, dp.get_test_data(), dp)
+                runner.train(model, dp, skip_eval=0)
+                after = runner.evaluate(model, dp.get_test_data(), dp)
+                pred = runner.predict(model, dp.get_test_data(), dp)
+                sd = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+        finally:
+            rh.use_device_rng(None)
+        out = {'seed': seed, 'epochs': epochs, 'n_users': n_users, 'n_items': n_items, 'per_user': per_user,
+               'test_neg_n': test_neg_n, 'batch_size': batch_size, 'lr': lr, 'l2': l2,
+               'before': np.array(before, dtype=np.float64), 'after': np.array(after, dtype=np.float64),
+               'train_results': np.array(runner.train_results, dtype=np.float64),
+               'valid_results': np.array(runner.valid_results, dtype=np.float64),
+               'test_results': np.array(runner.test_results, dtype=np.float64), 'pred': np.asarray(pred, np.float32)}
+        for k, v in sd.items():
+            out['sd_' + k] = v
+        np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), **out)
+        print(name, 'before', before, 'valid', runner.valid_results, 'after', after)
+    finally:
+        shutil.rmtree(tmp)
+
+
 def make_metrics_fixture(name='metrics', seed=5):
     ref = rh.load_reference()
     rs = np.random.RandomState(seed)
@@ -463,4 +511,5 @@ if __name__ == '__main__':
     make_ipsmf_fixture()
     make_run_fixture()
     make_run_fixture(name='run_recmodel_rank0', rank=0)
+    make_run_fixture_dccf()
     make_metrics_fixture()

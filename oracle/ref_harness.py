@@ -59,7 +59,15 @@ class RngTape:
 
 
 _TAPE = RngTape()
-_STATE = {'loaded': None}
+_STATE = {'loaded': None, 'device_rng': None}
+
+
+def use_device_rng(generator):
+    """On a GPU the reference draws the feature noise (DCCF.py:87) and the dropout masks (DCCF.py:94) from the CUDA
+    generator: the torch CPU generator only sees the confounder draws (DCCF.py:72).  With a private `generator` here the
+    CPU harness consumes the CPU generator the way a GPU run of the reference does; None (default) = everything on the
+    CPU generator, as a literal `--gpu ''` run would."""
+    _STATE['device_rng'] = generator
 
 
 def tape():
@@ -83,7 +91,7 @@ class _NoiseBuffer:
         if inj is not None:
             out = inj.clone()
         else:
-            out = torch.empty(self.shape, dtype=torch.float32).normal_(mean=mean, std=std)
+            out = torch.empty(self.shape, dtype=torch.float32).normal_(mean=mean, std=std, generator=_STATE['device_rng'])
         if _TAPE._cur is not None:
             _TAPE._cur['noise'] = out.clone()
         return out
@@ -106,7 +114,7 @@ class _TapedDropout(torch.nn.Module):
         if inj is not None:
             mask = inj.clone()
         else:
-            mask = torch.empty_like(x).bernoulli_(1.0 - self.p).div_(1.0 - self.p)
+            mask = torch.empty_like(x).bernoulli_(1.0 - self.p, generator=_STATE['device_rng']).div_(1.0 - self.p)
         if cur is not None:
             cur['masks'].append(mask.clone())
         return x * mask

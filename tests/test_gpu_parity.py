@@ -854,3 +854,55 @@ def test_ipsmf_exposure_matches_reference(golden):
     b = make_model(dict(params, expo=g['pred']), S, A, 0.1).predict(fd)['prediction'].cpu().numpy()
     # exposure values reach |29| here (propensity clamp 0.1): an fp32 ulp of the logit moves a softmax weight by ~3e-6
     assert rel_err(a, b) < 3e-5
+
+
+@pytest.mark.xfail(strict=False, reason='written after the GPU budget of round 1 was spent: first hardware run at round '
+                                        'end; XPASS = verified (the kernels it drives are the validated ones)')
+def test_whole_dccf_run_equals_reference_run(golden, tmp_path):
+    """src/main.py's whole sequence with DCCF on the GPU == the same sequence of the UNMODIFIED reference in the
+    deterministic configuration --std 0 --dropout 0 (tests/golden/run_dccf.npz, oracle/make_golden.py::
+    make_run_fixture_dccf): same shuffles and negatives (numpy generator), same confounder draws (torch CPU generator,
+    consumed in the same order by evaluation passes and training steps), hence the same "Test Before Training"
+    ndcg@5 / recall@5 / precision@5 to 1e-6, the same per-epoch train rmse / mae, and validation / test metrics,
+    final predictions and checkpoint within the drift of 28 fp32 Adam steps (a near-tie in a 21-candidate ranking may
+    flip: 1/600 per flip)."""
+    from dccf_b200 import synth
+    from dccf_b200.data_loaders.DataLoader import DataLoader
+    from dccf_b200.data_processor.DataProcessor import DataProcessor
+    from dccf_b200.models.DCCF import DCCF
+    from dccf_b200.runners.BaseRunner import BaseRunner
+    g = golden('run_dccf')
+    seed = int(g['seed'])
+    d = synth.write_dataset(str(tmp_path), 'toy', int(g['n_users']), int(g['n_items']), int(g['per_user']), feat_dim=64,
+                            seed=seed + 5)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    dl = DataLoader(path=str(tmp_path), dataset='toy', label='label', sep=',')
+    model = DCCF(path=d, dataset='toy', sentence_model=synth.DEFAULT_SENTENCE_MODEL, sample_num=10, attribute_num=2,
+                 std=0.0, label_min=dl.label_min, label_max=dl.label_max, feature_num=0, user_num=dl.user_num,
+                 item_num=dl.item_num, u_vector_size=64, i_vector_size=64, n_layers=1, random_seed=seed,
+                 model_path=str(tmp_path / 'model' / 'm.pt'))
+    model.apply(model.init_paras)
+    model = model.cuda()
+    dl.drop_neg()
+    dp = DataProcessor(dl, model, rank=1, test_neg_n=int(g['test_neg_n']))
+    runner = BaseRunner(optimizer='Adam', learning_rate=float(g['lr']), epoch=int(g['epochs']),
+                        batch_size=int(g['batch_size']), eval_batch_size=16384, dropout=0.0, l2=float(g['l2']),
+                        metrics='ndcg@5,recall@5,precision@5', check_epoch=1, early_stop=1)
+    runner.show_progress = False
+    before = runner.evaluate(model, dp.get_test_data(), dp)
+    runner.train(model, dp, skip_eval=0)
+    after = runner.evaluate(model, dp.get_test_data(), dp)
+    pred = runner.predict(model, dp.get_test_data(), dp)
+    model.check_ids()
+    assert np.abs(np.array(before) - g['before']).max() < 1e-6
+    assert np.asarray(runner.train_results).shape == g['train_results'].shape
+    assert np.abs(np.array(runner.train_results) - g['train_results']).max() < 1e-4
+    assert np.abs(np.array(runner.valid_results) - g['valid_results']).max() < 0.01
+    assert np.abs(np.array(runner.test_results) - g['test_results']).max() < 0.01
+    assert np.abs(np.array(after) - g['after']).max() < 0.01
+    assert rel_err(pred, g['pred']) < 2e-3
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    assert sorted('sd_' + k for k in sd) == sorted(k for k in g.files if k.startswith('sd_'))
+    for k, v in sd.items():
+        assert rel_err(v, g['sd_' + k]) < 2e-3, k
