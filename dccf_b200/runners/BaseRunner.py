@@ -393,7 +393,7 @@ class BaseRunner(object):
         (BaseRunner.py:334-355)."""
         logging.info(os.linesep)
         for name, t in out_dict['check']:
-            d = np.array(t.detach().cpu())
+            d = t.detach().cpu().numpy()
             logging.info(os.linesep.join([name + '\t' + str(d.shape), np.array2string(d, threshold=20)]) + os.linesep)
         loss = out_dict['loss'].detach()
         with torch.no_grad():

@@ -497,3 +497,71 @@ def test_whole_run_equals_reference_run(golden, tmp_path, fixture):
     assert sorted('sd_' + k for k in sd) == sorted(k for k in g.files if k.startswith('sd_'))
     for k, v in sd.items():
         assert np.abs(v.numpy() - g['sd_' + k]).max() <= 1e-6 * np.abs(g['sd_' + k]).max(), k
+
+
+def test_whole_dccf_run_orchestration_on_cpu(golden, tmp_path):
+    """tests/golden/run_dccf.npz (a whole DCCF run of the unmodified reference, --std 0 --dropout 0) replayed on CPU
+    with the MIRRORED loader, processor and runner around a stand-in for the device math (oracle/torch_port.py, the
+    eager-torch port): every shuffle, negative, confounder draw, evaluation pass, Adam step, model selection and reload
+    happens in the reference's order — "before", per-epoch and "after" metrics, predictions and checkpoint agree to 1e-5.
+    (The GPU path replays the same fixture in tests/test_gpu_parity.py::test_whole_dccf_run_equals_reference_run.)"""
+    from oracle import dccf_oracle as O
+    from oracle import torch_port
+
+    class PortModel(torch_port.DCCFPort):
+        append_id, include_id = True, False
+        include_user_features = include_item_features = include_context_features = False
+        optimizer = None
+
+        def predict(self, feed_dict):
+            fd = dict(feed_dict)
+            fd['noise'] = 0.0               # --std 0: the reference's zero noise comes off the CUDA generator, not this one
+            return torch_port.DCCFPort.predict(self, fd)
+
+        def save_model(self, model_path=None):
+            os.makedirs(os.path.dirname(self.model_path), exist_ok=True)
+            torch.save(self.state_dict(), self.model_path)
+
+        def load_model(self, model_path=None):
+            self.load_state_dict(torch.load(self.model_path))
+            self.eval()
+
+        @staticmethod
+        def evaluate_method(p, data, metrics):
+            p = p.detach().numpy() if torch.is_tensor(p) else np.asarray(p)
+            out = []
+            for m in metrics:
+                d = np.asarray(data['Y'], np.float64) - p.astype(np.float64)
+                out.append(float(np.sqrt(np.mean(d * d))) if m == 'rmse' else float(np.mean(np.abs(d))) if m == 'mae'
+                           else O.evaluate_method(p, data, [m])[0])
+            return out
+
+    g = golden('run_dccf')
+    seed = int(g['seed'])
+    d = synth.write_dataset(str(tmp_path), 'toy', int(g['n_users']), int(g['n_items']), int(g['per_user']), feat_dim=64,
+                            seed=seed + 5)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    dl = DataLoader(path=str(tmp_path), dataset='toy', label='label', sep=',')
+    feat = np.load(os.path.join(d, 'toy_%s.npy' % SENT))
+    expo = np.load(os.path.join(d, 'toy.ips_expo_prob.npy'))
+    model = PortModel(dl.user_num, dl.item_num, feat, expo, sample_num=10, attribute_num=2, std=0.0, seed=seed)
+    model.model_path = str(tmp_path / 'model' / 'm.pt')
+    dl.drop_neg()
+    dp = DataProcessor(dl, model, rank=1, test_neg_n=int(g['test_neg_n']))
+    runner = BaseRunner(optimizer='Adam', learning_rate=float(g['lr']), epoch=int(g['epochs']),
+                        batch_size=int(g['batch_size']), eval_batch_size=16384, dropout=0.0, l2=float(g['l2']),
+                        metrics='ndcg@5,recall@5,precision@5', check_epoch=1, early_stop=1)
+    runner.show_progress = False
+    before = runner.evaluate(model, dp.get_test_data(), dp)
+    runner.train(model, dp, skip_eval=0)
+    after = runner.evaluate(model, dp.get_test_data(), dp)
+    pred = runner.predict(model, dp.get_test_data(), dp)
+    assert np.abs(np.array(before) - g['before']).max() < 1e-6
+    for ours, name in ((runner.train_results, 'train_results'), (runner.valid_results, 'valid_results'),
+                       (runner.test_results, 'test_results')):
+        assert np.asarray(ours).shape == g[name].shape and np.abs(np.asarray(ours) - g[name]).max() < 1e-6, name
+    assert np.abs(np.array(after) - g['after']).max() < 1e-6
+    assert np.abs(pred - g['pred']).max() <= 1e-5 * np.abs(g['pred']).max()
+    for k, v in model.state_dict().items():
+        assert np.abs(v.numpy() - g['sd_' + k]).max() <= 1e-5 * np.abs(g['sd_' + k]).max(), k
