@@ -565,3 +565,112 @@ def test_whole_dccf_run_orchestration_on_cpu(golden, tmp_path):
     assert np.abs(pred - g['pred']).max() <= 1e-5 * np.abs(g['pred']).max()
     for k, v in model.state_dict().items():
         assert np.abs(v.numpy() - g['sd_' + k]).max() <= 1e-5 * np.abs(g['sd_' + k]).max(), k
+
+
+def test_whole_dccf_run_fused_orchestration_on_cpu(golden, tmp_path):
+    """The same fixture through the branches of BaseRunner / DataProcessor that only the CUDA model takes — the
+    device-resident epoch of `fit` (one confounder draw per chunk of batches, ragged tail step by step), `train_step`,
+    `predict_many` (DCCF's own method, worker-thread draws through dccf_confounder_draw) — with the device math replaced
+    by the eager-torch port and the batches merely claiming to live on the GPU.  Same metrics, predictions and checkpoint
+    as the reference run: the orchestration the GPU test relies on is exact."""
+    from oracle import dccf_oracle as O
+    from oracle import torch_port
+    from dccf_b200 import host_rng
+
+    class OnDevice(torch.Tensor):
+        is_cuda = property(lambda self: True)
+
+    class FusedState(object):                       # what make_fused_optimizer hands the runner: not a torch Optimizer
+        def __init__(self, model, lr, l2, weight_decay):
+            self.l2 = l2
+            self.adam = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
+
+    class PortModel(torch_port.DCCFPort):
+        append_id, include_id = True, False
+        include_user_features = include_item_features = include_context_features = False
+        optimizer = None
+        device_confounders = False
+        predict_many = DCCF.predict_many            # the product method itself
+
+        def predict(self, feed_dict):
+            fd = dict(feed_dict)
+            fd['noise'] = 0.0
+            fd['X'] = torch.Tensor(fd['X']).long() if isinstance(fd['X'], OnDevice) else fd['X']
+            return torch_port.DCCFPort.predict(self, fd)
+
+        def make_fused_optimizer(self, lr, l2, weight_decay=None):
+            return FusedState(self, lr, l2, l2 if weight_decay is None else weight_decay)
+
+        def draw_confounders(self, n_pairs):
+            return host_rng.randint(self.item_num, (n_pairs, self.sample_num), min_draws=0)
+
+        def train_step(self, fd):
+            fd = dict(fd)
+            fd['Y'] = torch.cat([torch.ones(fd['X'].shape[0] // 2), torch.zeros(fd['X'].shape[0] // 2)])
+            return torch_port.fit_step(self, self.optimizer.adam, fd, self.optimizer.l2)
+
+        def begin_resident_epoch(self, X_epoch, sample_epoch, dropout):
+            state = {'k': 0}
+            n = X_epoch.shape[0]
+
+            def step():
+                k = state['k']
+                state['k'] += 1
+                return self.train_step({'X': X_epoch[k], 'sample_item': sample_epoch[k], 'dropout': dropout})
+            step.remaining = lambda: n - state['k']
+            step.first = None
+            return step
+
+        def save_model(self, model_path=None):
+            os.makedirs(os.path.dirname(self.model_path), exist_ok=True)
+            torch.save(self.state_dict(), self.model_path)
+
+        def load_model(self, model_path=None):
+            self.load_state_dict(torch.load(self.model_path))
+            self.eval()
+
+        @staticmethod
+        def evaluate_method(p, data, metrics):
+            p = p.detach().numpy() if torch.is_tensor(p) else np.asarray(p)
+            out = []
+            for m in metrics:
+                d = np.asarray(data['Y'], np.float64) - p.astype(np.float64)
+                out.append(float(np.sqrt(np.mean(d * d))) if m == 'rmse' else float(np.mean(np.abs(d))) if m == 'mae'
+                           else O.evaluate_method(p, data, [m])[0])
+            return out
+
+    class DeviceDP(DataProcessor):
+        def _epoch_views(self, rows_X, rows_Y, bounds):
+            X = torch.Tensor._make_subclass(OnDevice, torch.from_numpy(np.ascontiguousarray(rows_X)))
+            Y = torch.from_numpy(np.ascontiguousarray(rows_Y))
+            return [(X[a:b], Y[a:b]) for a, b in bounds]
+
+    g = golden('run_dccf')
+    seed = int(g['seed'])
+    d = synth.write_dataset(str(tmp_path), 'toy', int(g['n_users']), int(g['n_items']), int(g['per_user']), feat_dim=64,
+                            seed=seed + 5)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    dl = DataLoader(path=str(tmp_path), dataset='toy', label='label', sep=',')
+    model = PortModel(dl.user_num, dl.item_num, np.load(os.path.join(d, 'toy_%s.npy' % SENT)),
+                      np.load(os.path.join(d, 'toy.ips_expo_prob.npy')), sample_num=10, attribute_num=2, std=0.0, seed=seed)
+    model.model_path = str(tmp_path / 'model' / 'm.pt')
+    dl.drop_neg()
+    dp = DeviceDP(dl, model, rank=1, test_neg_n=int(g['test_neg_n']))
+    runner = BaseRunner(optimizer='Adam', learning_rate=float(g['lr']), epoch=int(g['epochs']),
+                        batch_size=int(g['batch_size']), eval_batch_size=16384, dropout=0.0, l2=float(g['l2']),
+                        metrics='ndcg@5,recall@5,precision@5', check_epoch=1, early_stop=1)
+    runner.show_progress = False
+    before = runner.evaluate(model, dp.get_test_data(), dp)
+    runner.train(model, dp, skip_eval=0)
+    after = runner.evaluate(model, dp.get_test_data(), dp)
+    pred = runner.predict(model, dp.get_test_data(), dp)
+    assert not isinstance(model.optimizer, torch.optim.Optimizer)          # the fused branch was taken
+    assert np.abs(np.array(before) - g['before']).max() < 1e-6
+    for ours, name in ((runner.train_results, 'train_results'), (runner.valid_results, 'valid_results'),
+                       (runner.test_results, 'test_results')):
+        assert np.asarray(ours).shape == g[name].shape and np.abs(np.asarray(ours) - g[name]).max() < 1e-6, name
+    assert np.abs(np.array(after) - g['after']).max() < 1e-6
+    assert np.abs(pred - g['pred']).max() <= 1e-5 * np.abs(g['pred']).max()
+    for k, v in model.state_dict().items():
+        assert np.abs(v.numpy() - g['sd_' + k]).max() <= 1e-5 * np.abs(g['sd_' + k]).max(), k
