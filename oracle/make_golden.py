@@ -402,10 +402,13 @@ def make_run_fixture(name='run_recmodel', rank=1, seed=2019, epochs=3, n_users=1
                                     early_stop=1)
             before = runner.evaluate(model, dp.get_test_data(), dp)
             runner.train(model, dp, skip_eval=0)
-            after = runner.evaluate(model, dp.get_test_data(), dp)
+            after = runner.evaluate(model, dp.get_test_data(), dp, write_rank=True)      # main.py:188-190
+            rank_text = open(os.path.join(dl.path, ref.global_p.RANK_FILE_NAME)).read()
             pred = runner.predict(model, dp.get_test_data(), dp)
             sd = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
-        out = {'seed': seed, 'rank': rank, 'epochs': epochs, 'n_users': n_users, 'n_items': n_items, 'per_user': per_user,
+        rank_lines = rank_text.strip().split(chr(10))
+        rank_rows = np.array([[float(x) for x in ln.split(chr(9))] for ln in rank_lines[1:]])
+        out = {'rank_header': np.array(rank_lines[0]), 'rank_rows': rank_rows, 'seed': seed, 'rank': rank, 'epochs': epochs, 'n_users': n_users, 'n_items': n_items, 'per_user': per_user,
                'test_neg_n': test_neg_n, 'batch_size': batch_size, 'lr': lr, 'l2': l2,
                'before': np.array(before, dtype=np.float64), 'after': np.array(after, dtype=np.float64),
                'train_results': np.array(runner.train_results, dtype=np.float64),

@@ -485,8 +485,15 @@ def test_whole_run_equals_reference_run(golden, tmp_path, fixture):
     runner.show_progress = False
     before = runner.evaluate(model, dp.get_test_data(), dp)
     runner.train(model, dp, skip_eval=0)
-    after = runner.evaluate(model, dp.get_test_data(), dp)
+    after = runner.evaluate(model, dp.get_test_data(), dp, write_rank=True)
     pred = runner.predict(model, dp.get_test_data(), dp)
+    # rank.csv (BaseRunner.py:315-323): tab separated uid / iid / score / label, sorted by uid
+    lines = open(os.path.join(dl.path, 'rank.csv')).read().strip().split(chr(10))
+    assert lines[0] == str(g['rank_header'])
+    rows = np.array([[float(x) for x in ln.split(chr(9))] for ln in lines[1:]])
+    assert rows.shape == g['rank_rows'].shape
+    assert np.array_equal(rows[:, [0, 1, 3]], g['rank_rows'][:, [0, 1, 3]])
+    assert np.abs(rows[:, 2] - g['rank_rows'][:, 2]).max() <= 1e-6 * np.abs(g['rank_rows'][:, 2]).max()
     assert np.allclose(before, g['before'], rtol=1e-6, atol=0)
     for ours, name in ((runner.train_results, 'train_results'), (runner.valid_results, 'valid_results'),
                        (runner.test_results, 'test_results')):
