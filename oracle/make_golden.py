@@ -232,6 +232,10 @@ def make_config0_digest(name='config0_digest', seed=2019, epochs=2, test_neg_n=1
                 out['digests']['train_ep%d_sample_id' % ep] = array_digest(
                     np.concatenate([np.asarray(b['sample_id']) for b in batches]).astype(np.int64))
             out['np_state_after'] = [int(x) for x in np.random.get_state()[1][:8]]
+        # the files a first run of DataLoader generates next to the dataset (DataLoader.py:113-129, 169-177): bytes
+        import hashlib
+        out['files'] = {f: hashlib.sha256(open(os.path.join(d, f), 'rb').read()).hexdigest()
+                        for f in ('tiny.info.json', 'tiny.train_group.csv', 'tiny.vt_group.csv')}
         with open(os.path.join(GOLDEN, name + '.json'), 'w') as f:
             json.dump(out, f, indent=1, sort_keys=True)
         print(name, out['rows'])

@@ -437,6 +437,8 @@ def test_config0_host_pipeline_digest(tmp_path):
     np.random.seed(seed)
     dl = DataLoader(path=str(tmp_path), dataset='tiny', label='label', sep=',')
     assert (int(dl.user_num), int(dl.item_num)) == (want['user_num'], want['item_num'])
+    for fname, sha in want['files'].items():         # .info.json and the two history files: byte for byte
+        assert hashlib.sha256(open(os.path.join(d, fname), 'rb').read()).hexdigest() == sha, fname
     model = _make_model(d, 'tiny', dl.user_num, dl.item_num, seed=seed)
     dl.drop_neg()
     dp = DataProcessor(dl, model, rank=1, test_neg_n=want['test_neg_n'])
