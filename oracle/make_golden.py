@@ -458,6 +458,8 @@ def make_run_fixture_dccf(name='run_dccf', seed=2019, epochs=2, n_users=120, n_i
                 after = runner.evaluate(model, dp.get_test_data(), dp)
                 pred = runner.predict(model, dp.get_test_data(), dp)
                 sd = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+                model.save_model()                   # the reference's own checkpoint writer (BaseModel.py:224-236)
+                shutil.copy(model_path, os.path.join(GOLDEN, name + '_checkpoint.pt'))
         finally:
             rh.use_device_rng(None)
         out = {'seed': seed, 'epochs': epochs, 'n_users': n_users, 'n_items': n_items, 'per_user': per_user,

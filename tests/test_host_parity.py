@@ -683,3 +683,23 @@ def test_whole_dccf_run_fused_orchestration_on_cpu(golden, tmp_path):
     assert np.abs(pred - g['pred']).max() <= 1e-5 * np.abs(g['pred']).max()
     for k, v in model.state_dict().items():
         assert np.abs(v.numpy() - g['sd_' + k]).max() <= 1e-5 * np.abs(g['sd_' + k]).max(), k
+
+
+def test_reference_checkpoint_loads(golden, tmp_path):
+    """A .pt file written by the reference's own save_model (src/models/BaseModel.py:224-236; the checkpoint of the
+    run behind tests/golden/run_dccf.npz) loads into the mirrored DCCF through load_model — same keys, same tensors —
+    and a checkpoint written here has the reference's keys: the files interchange."""
+    g = golden('run_dccf')
+    d = synth.write_dataset(str(tmp_path), 'toy', int(g['n_users']), int(g['n_items']), int(g['per_user']), feat_dim=64,
+                            seed=int(g['seed']) + 5)
+    U, I = g['sd_uid_embeddings.weight'].shape[0], g['sd_iid_embeddings.weight'].shape[0]
+    model = _make_model(d, 'toy', U, I, std=0.0)
+    from conftest import GOLDEN
+    model.load_model(os.path.join(GOLDEN, 'run_dccf_checkpoint.pt'))
+    sd = model.state_dict()
+    assert sorted(sd) == sorted(k[3:] for k in g.files if k.startswith('sd_'))
+    for k, v in sd.items():
+        assert np.array_equal(v.numpy(), g['sd_' + k]), k
+    model.save_model(str(tmp_path / 'again.pt'))
+    again = torch.load(str(tmp_path / 'again.pt'))
+    assert sorted(again) == sorted(sd) and all(torch.equal(again[k], sd[k]) for k in sd)
