@@ -476,6 +476,36 @@ def make_run_fixture_dccf(name='run_dccf', seed=2019, epochs=2, n_users=120, n_i
         shutil.rmtree(tmp)
 
 
+def make_termination_fixture(name='termination', seed=11, n=300):
+    """BaseRunner.eva_termination (src/runners/BaseRunner.py:193-210) and utils.best_result / format_metric
+    (src/utils/utils.py:62-106) of the unmodified reference on random validation histories."""
+    import json
+    ref = rh.load_reference()
+    rs = np.random.RandomState(seed)
+    cases = []
+    for _ in range(n):
+        metric = ['ndcg@5', 'rmse'][rs.randint(2)]
+        length = int(rs.randint(1, 45))
+        kind = rs.randint(4)
+        base = rs.random_sample(length)
+        if kind == 1:
+            base = np.sort(base)                                 # monotone up
+        elif kind == 2:
+            base = np.sort(base)[::-1]                           # monotone down
+        elif kind == 3 and length > 25:
+            base[int(rs.randint(0, length - 21))] = 2.0 if metric == 'ndcg@5' else -1.0   # an early best
+        hist = [[float(np.round(v, 4)), float(np.round(rs.random_sample(), 4))] for v in base]
+        runner = ref.BaseRunner(optimizer='Adam', learning_rate=1e-3, epoch=1, batch_size=8, eval_batch_size=8, dropout=0.0,
+                                l2=0.0, metrics=metric + ',recall@5', check_epoch=1, early_stop=1)
+        runner.valid_results = [list(h) for h in hist]
+        cases.append({'metric': metric, 'history': hist, 'stop': bool(runner.eva_termination(None)),
+                      'best': ref.utils.best_result(metric, [list(h) for h in hist]),
+                      'fmt': ref.utils.format_metric(hist[-1])})
+    with open(os.path.join(GOLDEN, name + '.json'), 'w') as f:
+        json.dump(cases, f)
+    print(name, n, 'cases,', sum(c['stop'] for c in cases), 'stops')
+
+
 def make_metrics_fixture(name='metrics', seed=5):
     ref = rh.load_reference()
     rs = np.random.RandomState(seed)
@@ -521,4 +551,5 @@ if __name__ == '__main__':
     make_run_fixture()
     make_run_fixture(name='run_recmodel_rank0', rank=0)
     make_run_fixture_dccf()
+    make_termination_fixture()
     make_metrics_fixture()

@@ -703,3 +703,18 @@ def test_reference_checkpoint_loads(golden, tmp_path):
     model.save_model(str(tmp_path / 'again.pt'))
     again = torch.load(str(tmp_path / 'again.pt'))
     assert sorted(again) == sorted(sd) and all(torch.equal(again[k], sd[k]) for k in sd)
+
+
+def test_early_stop_and_model_selection_equal_reference():
+    """eva_termination / best_result / format_metric on 300 random validation histories (monotone runs, early bests,
+    both metric polarities) decided by the unmodified reference (tests/golden/termination.json)."""
+    import json
+    from conftest import GOLDEN
+    cases = json.load(open(os.path.join(GOLDEN, 'termination.json')))
+    assert len(cases) >= 300 and any(c['stop'] for c in cases) and not all(c['stop'] for c in cases)
+    for c in cases:
+        r = BaseRunner(optimizer='Adam', learning_rate=1e-3, metrics=c['metric'] + ',recall@5', dropout=0.0)
+        r.valid_results = [list(h) for h in c['history']]
+        assert bool(r.eva_termination(None)) == c['stop'], c
+        assert utils.best_result(c['metric'], [list(h) for h in c['history']]) == c['best']
+        assert utils.format_metric(c['history'][-1]) == c['fmt']
