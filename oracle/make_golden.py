@@ -506,6 +506,26 @@ def make_termination_fixture(name='termination', seed=11, n=300):
     print(name, n, 'cases,', sum(c['stop'] for c in cases), 'stops')
 
 
+def make_cli_fixture(name='cli_flags'):
+    """Every command-line flag the reference defines for the DCCF path — option strings, destination, default, type —
+    from its own parsers in main.py's order (src/main.py:52-59): global, DataLoader, DCCF (-> DMF -> RecModel ->
+    BaseModel), BaseRunner, DataProcessor."""
+    import argparse
+    import json
+    ref = rh.load_reference()
+    p = argparse.ArgumentParser()
+    p = ref.utils.parse_global_args(p)
+    p = ref.DataLoader.parse_data_args(p)
+    p = ref.DCCF.parse_model_args(p, model_name='DCCF')
+    p = ref.BaseRunner.parse_runner_args(p)
+    p = ref.DataProcessor.parse_dp_args(p)
+    flags = [{'options': list(a.option_strings), 'dest': a.dest, 'default': a.default,
+              'type': getattr(a.type, '__name__', None)} for a in p._actions if a.dest != 'help']
+    with open(os.path.join(GOLDEN, name + '.json'), 'w') as f:
+        json.dump(flags, f, indent=1)
+    print(name, len(flags), 'flags')
+
+
 def make_metrics_fixture(name='metrics', seed=5):
     ref = rh.load_reference()
     rs = np.random.RandomState(seed)
@@ -552,4 +572,5 @@ if __name__ == '__main__':
     make_run_fixture(name='run_recmodel_rank0', rank=0)
     make_run_fixture_dccf()
     make_termination_fixture()
+    make_cli_fixture()
     make_metrics_fixture()

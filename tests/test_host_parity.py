@@ -718,3 +718,24 @@ def test_early_stop_and_model_selection_equal_reference():
         assert bool(r.eva_termination(None)) == c['stop'], c
         assert utils.best_result(c['metric'], [list(h) for h in c['history']]) == c['best']
         assert utils.format_metric(c['history'][-1]) == c['fmt']
+
+
+def test_every_cli_flag_equals_reference():
+    """All flags of the reference's parsers for the DCCF path (tests/golden/cli_flags.json: option strings, destination,
+    default, type — 30-odd flags) exist here with the same spelling, default and type."""
+    import json
+    from conftest import GOLDEN
+    want = json.load(open(os.path.join(GOLDEN, 'cli_flags.json')))
+    p = argparse.ArgumentParser()
+    utils.parse_global_args(p)
+    DataLoader.parse_data_args(p)
+    DCCF.parse_model_args(p, model_name='DCCF')
+    BaseRunner.parse_runner_args(p)
+    DataProcessor.parse_dp_args(p)
+    got = {a.dest: a for a in p._actions if a.dest != 'help'}
+    assert sorted(got) == sorted(w['dest'] for w in want)
+    for w in want:
+        a = got[w['dest']]
+        assert list(a.option_strings) == w['options'], w
+        assert a.default == w['default'], w
+        assert getattr(a.type, '__name__', None) == w['type'], w
