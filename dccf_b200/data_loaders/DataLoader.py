@@ -99,9 +99,10 @@ class DataLoader(object):
         self.item_num = self.column_max['iid'] + 1 if 'iid' in self.column_max else 0
         logging.info('# of users: %d' % self.user_num)
         logging.info('# of items: %d' % self.item_num)
-        self.user_features = [f for f in self.column_max if f.startswith('u_')]
-        self.item_features = [f for f in self.column_max if f.startswith('i_')]
-        self.context_features = [f for f in self.column_max if f.startswith('c_')]
+        for kind, prefix in (('user', 'u_'), ('item', 'i_'), ('context', 'c_')):
+            found = [f for f in self.column_max if f.startswith(prefix)]
+            setattr(self, kind + '_features', found)
+            logging.info('# of %s features: %d' % (kind, len(found)))
         self.features = self.context_features + self.user_features + self.item_features
         logging.info('# of features: %d' % len(self.features))
 

@@ -376,6 +376,21 @@ def make_ipsmf_fixture(name='ipsmf', U=70, I=110, seed=2019, M=0.1):
         shutil.rmtree(tmp)
 
 
+def log_lines(messages, root):
+    """The log of a run as comparable lines: the messages whose wording and numbers are part of the interface (data
+    sizes, parameter count, optimizer, Init / Epoch / Best Iter lines with their %.4f metrics, early stop, model save /
+    load), wall-clock durations masked, the temporary directory replaced by <root>."""
+    import re
+    keep = ('load ', 'size of ', 'label:', '# of ', 'Model # of', 'Drop Neg', 'Prepare ', 'Optimizer:', 'Init:', 'Epoch ',
+            'Best Iter', 'Early stop', 'Save model', 'Load model', 'building ')
+    out = []
+    for m in messages:
+        m = m.strip()
+        if m.startswith(keep):
+            out.append(re.sub(r'\[\d+\.\d+ s\]', '[T s]', m.replace(root, '<root>')))
+    return out
+
+
 def make_run_fixture(name='run_recmodel', rank=1, seed=2019, epochs=3, n_users=120, n_items=150, per_user=10, test_neg_n=5,
                      batch_size=64, lr=0.01, l2=1e-4):
     """A WHOLE RUN of the unmodified reference, src/main.py's sequence (main.py:101-192) with its own DataLoader,
@@ -390,6 +405,17 @@ def make_run_fixture(name='run_recmodel', rank=1, seed=2019, epochs=3, n_users=1
         synth.write_dataset(tmp, 'toy', n_users, n_items, per_user, feat_dim=64, seed=seed + 5)
         model_path = os.path.join(tmp, 'model', 'm.pt')
         os.makedirs(os.path.dirname(model_path))
+        import logging
+        messages = []
+
+        class _Collect(logging.Handler):
+            def emit(self, record):
+                messages.append(record.getMessage())
+
+        collector = _Collect(level=logging.INFO)
+        logging.getLogger().addHandler(collector)
+        old_level = logging.getLogger().level
+        logging.getLogger().setLevel(logging.INFO)
         with rh.cpu_shims():
             torch.manual_seed(seed)
             np.random.seed(seed)
@@ -410,9 +436,12 @@ def make_run_fixture(name='run_recmodel', rank=1, seed=2019, epochs=3, n_users=1
             rank_text = open(os.path.join(dl.path, ref.global_p.RANK_FILE_NAME)).read()
             pred = runner.predict(model, dp.get_test_data(), dp)
             sd = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+        logging.getLogger().removeHandler(collector)
+        logging.getLogger().setLevel(old_level)
         rank_lines = rank_text.strip().split(chr(10))
         rank_rows = np.array([[float(x) for x in ln.split(chr(9))] for ln in rank_lines[1:]])
-        out = {'rank_header': np.array(rank_lines[0]), 'rank_rows': rank_rows, 'seed': seed, 'rank': rank, 'epochs': epochs, 'n_users': n_users, 'n_items': n_items, 'per_user': per_user,
+        out = {'log': np.array(log_lines(messages, tmp)), 'rank_header': np.array(rank_lines[0]), 'rank_rows': rank_rows,
+               'seed': seed, 'rank': rank, 'epochs': epochs, 'n_users': n_users, 'n_items': n_items, 'per_user': per_user,
                'test_neg_n': test_neg_n, 'batch_size': batch_size, 'lr': lr, 'l2': l2,
                'before': np.array(before, dtype=np.float64), 'after': np.array(after, dtype=np.float64),
                'train_results': np.array(runner.train_results, dtype=np.float64),

@@ -472,6 +472,19 @@ def test_whole_run_equals_reference_run(golden, tmp_path, fixture):
     synth.write_dataset(str(tmp_path), 'toy', int(g['n_users']), int(g['n_items']), int(g['per_user']), feat_dim=64,
                         seed=seed + 5)
     model_path = str(tmp_path / 'model' / 'm.pt')
+    import logging
+    import re
+    messages = []
+
+    class Collect(logging.Handler):
+        def emit(self, record):
+            messages.append(record.getMessage())
+
+    collector = Collect(level=logging.INFO)
+    root_logger = logging.getLogger()
+    old_level = root_logger.level
+    root_logger.addHandler(collector)
+    root_logger.setLevel(logging.INFO)
     torch.manual_seed(seed)
     np.random.seed(seed)
     dl = DataLoader(path=str(tmp_path), dataset='toy', label='label', sep=',')
@@ -489,6 +502,14 @@ def test_whole_run_equals_reference_run(golden, tmp_path, fixture):
     runner.train(model, dp, skip_eval=0)
     after = runner.evaluate(model, dp.get_test_data(), dp, write_rank=True)
     pred = runner.predict(model, dp.get_test_data(), dp)
+    root_logger.removeHandler(collector)
+    root_logger.setLevel(old_level)
+    # the log: same lines in the same order, same wording, same %.4f numbers (durations masked)
+    keep = ('load ', 'size of ', 'label:', '# of ', 'Model # of', 'Drop Neg', 'Prepare ', 'Optimizer:', 'Init:', 'Epoch ',
+            'Best Iter', 'Early stop', 'Save model', 'Load model', 'building ')
+    ours = [re.sub(r'\[\d+\.\d+ s\]', '[T s]', m.strip().replace(str(tmp_path), '<root>')) for m in messages
+            if m.strip().startswith(keep)]
+    assert ours == [str(x) for x in g['log']]
     # rank.csv (BaseRunner.py:315-323): tab separated uid / iid / score / label, sorted by uid
     lines = open(os.path.join(dl.path, 'rank.csv')).read().strip().split(chr(10))
     assert lines[0] == str(g['rank_header'])
