@@ -382,7 +382,7 @@ def log_lines(messages, root):
     load), wall-clock durations masked, the temporary directory replaced by <root>."""
     import re
     keep = ('load ', 'size of ', 'label:', '# of ', 'Model # of', 'Drop Neg', 'Prepare ', 'Optimizer:', 'Init:', 'Epoch ',
-            'Best Iter', 'Early stop', 'Save model', 'Load model', 'building ')
+            'Best Iter', 'Early stop', 'Save model', 'Load model', 'building ', 'loss = ', 'l2 inappropriate')
     out = []
     for m in messages:
         m = m.strip()
