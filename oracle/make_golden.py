@@ -382,7 +382,8 @@ def log_lines(messages, root):
     load), wall-clock durations masked, the temporary directory replaced by <root>."""
     import re
     keep = ('load ', 'size of ', 'label:', '# of ', 'Model # of', 'Drop Neg', 'Prepare ', 'Optimizer:', 'Init:', 'Epoch ',
-            'Best Iter', 'Early stop', 'Save model', 'Load model', 'building ', 'loss = ', 'l2 inappropriate')
+            'Best Iter', 'Early stop', 'Save model', 'Load model', 'building ', 'loss = ', 'l2 inappropriate', 'Test Before', 'Test After', 'Save Test Results', '# cuda devices',
+            'DataLoader:', 'Model:', 'Runner:', 'DataProcessor:')
     out = []
     for m in messages:
         m = m.strip()
@@ -555,6 +556,55 @@ def make_cli_fixture(name='cli_flags'):
     print(name, len(flags), 'flags')
 
 
+MAIN_ARGS = ['--rank', '1', '--model_name', 'RecModel', '--optimizer', 'Adam', '--lr', '0.01', '--dataset', 'toy',
+             '--metric', 'rmse,mae', '--gpu', '', '--epoch', '2', '--batch_size', '64', '--test_neg_n', '5',
+             '--random_seed', '7']
+
+
+def make_main_fixture(name='main_recmodel'):
+    """The reference's src/main.py ITSELF, run as a script (RecModel on CPU, default log / model / result locations
+    relative to the working directory `<tmp>/src`): which files it creates — their names are derived from the
+    hyper-parameters (main.py:63-84) —, what it logs and what it saves as the result."""
+    import json
+    import logging
+    import runpy
+    ref = rh.load_reference()
+    tmp = tempfile.mkdtemp()
+    cwd = os.getcwd()
+    argv = list(sys.argv)
+    try:
+        synth.write_dataset(os.path.join(tmp, 'datasets'), 'toy', 120, 150, 10, feat_dim=64, seed=9)
+        os.makedirs(os.path.join(tmp, 'src'))
+        os.makedirs(os.path.join(tmp, 'result'))          # the reference never creates it (SURVEY.md 8c, breakage 5)
+        os.chdir(os.path.join(tmp, 'src'))
+        sys.argv = ['main.py'] + MAIN_ARGS + ['--path', '../datasets/']
+        sys.path.insert(0, rh.REFERENCE_SRC)
+        try:
+            with rh.cpu_shims():
+                runpy.run_path(os.path.join(rh.REFERENCE_SRC, 'main.py'), run_name='__main__')
+        finally:
+            sys.path.remove(rh.REFERENCE_SRC)
+            for h in logging.root.handlers[:]:
+                logging.root.removeHandler(h)
+                h.close()
+        files = sorted(os.path.relpath(os.path.join(r, f), tmp) for sub in ('log', 'model', 'result')
+                       for r, _, fs in os.walk(os.path.join(tmp, sub)) for f in fs)
+        log_path = [f for f in files if f.startswith('log')][0]
+        res_path = [f for f in files if f.startswith('result')][0]
+        import re
+        messages = [re.sub(r'^(INFO|WARNING|ERROR|DEBUG):root:', '', ln)
+                    for ln in open(os.path.join(tmp, log_path)).read().split(chr(10))]
+        out = {'args': MAIN_ARGS, 'files': files, 'log': log_lines(messages, tmp),
+               'result': [float(x) for x in np.load(os.path.join(tmp, res_path))]}
+        with open(os.path.join(GOLDEN, name + '.json'), 'w') as f:
+            json.dump(out, f)
+        print(name, files)
+    finally:
+        os.chdir(cwd)
+        sys.argv = argv
+        shutil.rmtree(tmp)
+
+
 def make_metrics_fixture(name='metrics', seed=5):
     ref = rh.load_reference()
     rs = np.random.RandomState(seed)
@@ -602,4 +652,5 @@ if __name__ == '__main__':
     make_run_fixture_dccf()
     make_termination_fixture()
     make_cli_fixture()
+    make_main_fixture()
     make_metrics_fixture()

@@ -34,3 +34,33 @@ def test_main_cli_runs_recmodel_on_cpu(tmp_path, rank, metric):
     assert os.path.exists(os.path.join(data_root, 'toy', 'rank.csv'))
     for generated in ('toy.info.json', 'toy.train_group.csv', 'toy.vt_group.csv'):
         assert os.path.exists(os.path.join(data_root, 'toy', generated))
+
+
+def test_main_script_equals_reference_main_script(tmp_path):
+    """src/main.py run as a script with the reference's default output locations (`../log`, `../model`, `../result`
+    relative to the working directory) against the reference's own main.py run the same way
+    (tests/golden/main_recmodel.json, oracle/make_golden.py::make_main_fixture): the same files under the same
+    hyper-parameter-derived names (src/main.py:63-84), the same log lines (wording, order, %.4f metrics; durations
+    masked), the same saved predictions."""
+    import json
+    import re
+    from conftest import GOLDEN
+    want = json.load(open(os.path.join(GOLDEN, 'main_recmodel.json')))
+    synth.write_dataset(str(tmp_path / 'datasets'), 'toy', 120, 150, 10, feat_dim=64, seed=9)
+    os.makedirs(str(tmp_path / 'src'))
+    cmd = [sys.executable, os.path.join(ROOT, 'src', 'main.py')] + want['args'] + ['--path', '../datasets/']
+    r = subprocess.run(cmd, cwd=str(tmp_path / 'src'), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    files = sorted(os.path.relpath(os.path.join(d, f), str(tmp_path)) for sub in ('log', 'model', 'result')
+                   for d, _, fs in os.walk(str(tmp_path / sub)) for f in fs)
+    assert files == want['files']
+    keep = ('load ', 'size of ', 'label:', '# of ', 'Model # of', 'Drop Neg', 'Prepare ', 'Optimizer:', 'Init:', 'Epoch ',
+            'Best Iter', 'Early stop', 'Save model', 'Load model', 'building ', 'loss = ', 'l2 inappropriate', 'Test Before',
+            'Test After', 'Save Test Results', '# cuda devices', 'DataLoader:', 'Model:', 'Runner:', 'DataProcessor:')
+    log = open(str(tmp_path / [f for f in files if f.startswith('log')][0])).read().split(chr(10))
+    log = [re.sub(r'^(INFO|WARNING|ERROR|DEBUG):root:', '', ln).strip() for ln in log]
+    ours = [re.sub(r'\[\d+\.\d+ s\]', '[T s]', ln.replace(str(tmp_path), '<root>')) for ln in log if ln.startswith(keep)]
+    assert ours == want['log']
+    res = np.load(str(tmp_path / [f for f in files if f.startswith('result')][0]))
+    assert res.shape == (len(want['result']),)
+    assert np.abs(res - np.array(want['result'])).max() <= 1e-6 * np.abs(want['result']).max()

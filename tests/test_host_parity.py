@@ -506,7 +506,8 @@ def test_whole_run_equals_reference_run(golden, tmp_path, fixture):
     root_logger.setLevel(old_level)
     # the log: same lines in the same order, same wording, same %.4f numbers (durations masked)
     keep = ('load ', 'size of ', 'label:', '# of ', 'Model # of', 'Drop Neg', 'Prepare ', 'Optimizer:', 'Init:', 'Epoch ',
-            'Best Iter', 'Early stop', 'Save model', 'Load model', 'building ', 'loss = ', 'l2 inappropriate')
+            'Best Iter', 'Early stop', 'Save model', 'Load model', 'building ', 'loss = ', 'l2 inappropriate', 'Test Before', 'Test After', 'Save Test Results', '# cuda devices',
+            'DataLoader:', 'Model:', 'Runner:', 'DataProcessor:')
     ours = [re.sub(r'\[\d+\.\d+ s\]', '[T s]', m.strip().replace(str(tmp_path), '<root>')) for m in messages
             if m.strip().startswith(keep)]
     assert ours == [str(x) for x in g['log']]
