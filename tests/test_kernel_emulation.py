@@ -21,6 +21,16 @@ def half_sum(v):
 def half_max(v):
     for o in (8, 4, 2, 1): v = np.maximum(v, shfl_xor(v, o))
     return v
+def expo_of(params, u, it):
+    """backdoor.cuh::expo_value: the dense matrix, or the IPSBiasedMF formula on the fly (mode 1)"""
+    fac = params.get('ipsmf')
+    if fac is None:
+        return params['expo'][u, it]
+    pred = np.float32(np.dot(fac['mf_user'][u], fac['mf_item'][it])) + fac['mf_user_bias'][u] + fac['mf_item_bias'][it] \
+        + fac['mf_global_bias']
+    return np.float32(pred / max(fac['propensity'][it], fac['mf_min_propensity']))
+
+
 def warp(params, PI, PF, X, si, n_pairs, warp_index, out):
     lane = np.arange(32); sub = lane & 15; half_base = lane & 16
     p_raw = warp_index * 2 + (lane >> 4)
@@ -38,7 +48,7 @@ def warp(params, PI, PF, X, si, n_pairs, warp_index, out):
         for l in range(32):
             if z_mine[l] < Z:
                 if z_mine[l] > 0: it_mine[l] = si[p[l], z_mine[l] - 1]
-                x_mine[l] = params['expo'][u[l], it_mine[l]]
+                x_mine[l] = expo_of(params, u[l], it_mine[l])
         nz = min(16, Z - z0)
         s_mine = np.zeros(32, np.float32)
         for j0 in range(0, nz, 4):
@@ -74,10 +84,16 @@ def _problem(seed, U, I, F, P, S):
     return params, X, si
 
 
-@pytest.mark.parametrize('P,S,A', [(7, 10, 2), (5, 40, 1), (3, 0, 2), (4, 15, 1), (6, 16, 3), (1, 10, 2)])
-def test_gather_scorer_schedule_emulated(P, S, A):
+@pytest.mark.parametrize('P,S,A,ipsmf', [(7, 10, 2, False), (5, 40, 1, False), (3, 0, 2, False), (4, 15, 1, False),
+                                        (6, 16, 3, False), (1, 10, 2, False), (9, 10, 2, True)])
+def test_gather_scorer_schedule_emulated(P, S, A, ipsmf):
     U, I, F = 30, 50, 64
     params, X, si = _problem(21 + S, U, I, F, P, S)
+    fac = None
+    if ipsmf:
+        from dccf_b200 import synth
+        fac = synth.make_ipsmf_factors(U, I, seed=3)
+        params['ipsmf'] = fac
     W = params['W'].astype(np.float64)
     PI = (params['E_item'].astype(np.float64) @ W[:, :64].T).astype(np.float32)              # dccf_tc_prepare's tables
     PF = (params['Feat'].astype(np.float64) @ W[:, 64:].T + params['b']).astype(np.float32)
@@ -85,6 +101,6 @@ def test_gather_scorer_schedule_emulated(P, S, A):
     with np.errstate(invalid='ignore'):
         for w in range((P + 1) // 2 + 1):                # + one fully idle warp
             warp(params, PI, PF, X, si, P, w, out)
-    ref = O.predict(params, X, si, None, None, A, dtype=np.float64)['pred']
+    ref = O.predict(params, X, si, None, None, A, dtype=np.float64, expo=fac)['pred']
     assert np.isfinite(out).all()
     assert np.abs(out - ref).max() / np.abs(ref).max() < 1e-5
