@@ -12,7 +12,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 _VARIANT = os.environ.get('DCCF_LIB_VARIANT', '')          # A/B build variants, see dccf_b200/build.py
 LIB_PATH = os.path.join(HERE, 'libdccf_b200%s.so' % (('_' + _VARIANT) if _VARIANT else ''))
-ABI_VERSION = 29
+ABI_VERSION = 30
 DIM = 64
 
 
@@ -128,6 +128,9 @@ _SIGNATURES = {
     'dccf_confounder_draw': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, ctypes.c_int64, _P]),
     'dccf_confounder_draw_dev': (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int64, _P, _P]),
     'dccf_rank_eval': (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, _P, _P]),
+    'dccf_rank_eval_ws_bytes': (ctypes.c_int64, [ctypes.c_int64]),
+    'dccf_rank_eval_multi': (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32),
+                                            ctypes.c_int32, _P, _P, _P, _P, _P, _P]),
 }
 
 _LIB = None

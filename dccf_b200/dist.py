@@ -29,7 +29,9 @@ class SegmentExchange(object):
         self.send = torch.zeros(self.seg, dtype=torch.float32, device=device)
         self.mode = 'collective'
         self.recv = None
-        if world > 1 and torch.device(device).type == 'cuda' and use_p2p:
+        # the peer-memory protocol keeps int32[8] arrival / consumed flags (DP_MAX_WORLD in csrc/dp_exchange.cu): larger
+        # worlds (more than one NVSwitch domain of 8) use the collective
+        if world > 1 and world <= 8 and torch.device(device).type == 'cuda' and use_p2p:
             try:
                 self._init_p2p(device)
                 self.mode = 'p2p'

@@ -318,12 +318,40 @@ def state_advance(step_dev, offset_dev, offset_inc=1):
 
 
 def rank_eval(scores, labels, iids, cand_rows, user_off, k, out_metrics, out_topk_iid=None, out_topk_row=None):
+    """One k; cand_rows None = rows already grouped by user (candidate c is row c)."""
     lib = _lib.load()
     n_users = user_off.shape[0] - 1
     check(lib.dccf_rank_eval(ptr(scores), ptr(labels), ptr(iids), ptr(cand_rows), ptr(user_off), n_users, int(k),
                              ptr(out_topk_iid), ptr(out_topk_row), ptr(out_metrics), stream_ptr()), 'dccf_rank_eval')
-    LAUNCHES[0] += 1
+    LAUNCHES[0] += 1 if n_users > 0 else 0
     return out_metrics
+
+
+RANK_MAX_NK, RANK_STREAM_MAX_K = 4, 16
+_RANK_WS = {}
+
+
+def rank_workspace(device):
+    """Zero-initialised workspace of dccf_rank_eval_multi (partial sums + CTA counter), one per device and stream."""
+    key = (torch.device(device).index, torch.cuda.current_stream().cuda_stream)
+    ws = _RANK_WS.get(key)
+    if ws is None:
+        ws = _RANK_WS[key] = torch.zeros(int(_lib.load().dccf_rank_eval_ws_bytes(0)), dtype=torch.uint8, device=device)
+    return ws
+
+
+def rank_eval_multi(scores, labels, iids, cand_rows, user_off, ks, out_metrics=None, out_sums=None, out_topk_iid=None,
+                    out_topk_row=None):
+    """Every metric at every k of `ks` (ascending, <= 4 values, each <= 16) in one launch: per-user values
+    [n_users, n_k, 5] and / or their sums over users [n_k, 5] (dccf_rank_eval_multi)."""
+    lib = _lib.load()
+    n_users = user_off.shape[0] - 1
+    arr = (ctypes.c_int32 * len(ks))(*[int(k) for k in ks])
+    ws = rank_workspace(scores.device) if out_sums is not None else None
+    check(lib.dccf_rank_eval_multi(ptr(scores), ptr(labels), ptr(iids), ptr(cand_rows), ptr(user_off), n_users, arr,
+                                   len(ks), ptr(out_topk_iid), ptr(out_topk_row), ptr(out_metrics), ptr(ws),
+                                   ptr(out_sums), stream_ptr()), 'dccf_rank_eval_multi')
+    LAUNCHES[0] += 1 if n_users > 0 else 0
 
 
 def full_scores(A, B, row_bias=None, col_bias=None, col_scale=None, g=0.0, materialise=True, k=0):

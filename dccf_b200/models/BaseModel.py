@@ -24,13 +24,36 @@ def group_candidates(uid):
 
 
 def rank_metrics_device(scores, labels, iids, cand_rows, user_off, k, want_topk=False):
-    """Launch dccf_rank_eval; all arguments are CUDA tensors.  Returns per-user metrics [n_users,5] f64
-    (ndcg, hit, precision, recall, f1 at k) and optionally the top-k item ids."""
+    """Launch dccf_rank_eval; all arguments are CUDA tensors (cand_rows None: rows already grouped by user).
+    Returns per-user metrics [n_users,5] f64 (ndcg, hit, precision, recall, f1 at k) and optionally the top-k
+    item ids."""
     n_users = user_off.shape[0] - 1
     out = torch.empty((n_users, 5), dtype=torch.float64, device=scores.device)
     topk = torch.empty((n_users, k), dtype=torch.int64, device=scores.device) if want_topk else None
     kernels.rank_eval(scores, labels, iids, cand_rows, user_off, k, out, out_topk_iid=topk)
     return (out, topk) if want_topk else out
+
+
+def rank_sums_device(scores, labels, iids, cand_rows, user_off, ks):
+    """Sums over users of (ndcg, hit, precision, recall, f1) at every k of `ks` -> CUDA tensor [len(ks), 5] f64, rows in
+    the order of `ks`.  One launch of dccf_rank_eval_multi per group of up to four values of k <= 16 (a metric list such
+    as ndcg@5,recall@5,precision@5 is ONE launch; the reference loops over the users once per metric,
+    src/models/BaseModel.py:90-126); larger k go through dccf_rank_eval one at a time."""
+    ks = [int(k) for k in ks]
+    out = torch.empty((len(ks), 5), dtype=torch.float64, device=scores.device)
+    small = sorted(set(k for k in ks if k <= kernels.RANK_STREAM_MAX_K))
+    where = {}
+    for a in range(0, len(small), kernels.RANK_MAX_NK):
+        group = small[a:a + kernels.RANK_MAX_NK]
+        sums = torch.empty((len(group), 5), dtype=torch.float64, device=scores.device)
+        kernels.rank_eval_multi(scores, labels, iids, cand_rows, user_off, group, out_sums=sums)
+        for j, k in enumerate(group):
+            where[k] = sums[j]
+    for k in set(ks) - set(small):
+        where[k] = rank_metrics_device(scores, labels, iids, cand_rows, user_off, k).sum(dim=0)
+    for j, k in enumerate(ks):
+        out[j] = where[k]
+    return out
 
 
 METRIC_COLUMN = {'ndcg': 0, 'hit': 1, 'precision': 2, 'recall': 3, 'f1': 4}
@@ -48,15 +71,41 @@ def rank_context(data, dev):
         return hit[1]
     import weakref
     _, rows, off = group_candidates(uid)
+    # the evaluation set is built user-major (DataProcessor: positives of a user, then its negatives): when the
+    # grouping permutation is the identity the ranker reads scores / labels contiguously, with no indirection
+    grouped = bool(len(rows) == 0 or np.array_equal(rows, np.arange(len(rows), dtype=rows.dtype)))
     ctx = {'dev': dev, 'n': len(uid),
            'labels': torch.from_numpy(np.ascontiguousarray(data['Y'], dtype=np.float32)).to(dev),
            'iids': torch.from_numpy(np.ascontiguousarray(data['iid'], dtype=np.int64)).to(dev),
-           'rows': torch.from_numpy(rows).to(dev), 'off': torch.from_numpy(off).to(dev)}
+           'rows': None if grouped else torch.from_numpy(rows).to(dev), 'off': torch.from_numpy(off).to(dev),
+           'n_users': len(off) - 1}
     try:
         _RANK_CTX[key] = (weakref.ref(uid, lambda _r, k=key: _RANK_CTX.pop(k, None)), ctx)
     except TypeError:
         pass
     return ctx
+
+
+def _rank_metric_sums(p, data, metrics):
+    """{(name, k): sum over users} for every '<name>@k' metric of the list, plus the user count — one ranker launch
+    and one device -> host copy for the whole list."""
+    wanted = []
+    for metric in metrics:
+        if '@' in metric:
+            name, k = metric.split('@')
+            if name in METRIC_COLUMN:
+                wanted.append((name, int(k)))
+    if not wanted:
+        return {}, 0
+    if not torch.cuda.is_available():
+        raise RuntimeError('ranking metrics run on the GPU (dccf_rank_eval); no CUDA device is visible')
+    dev = p.device if (torch.is_tensor(p) and p.is_cuda) else torch.device('cuda', torch.cuda.current_device())
+    ctx = rank_context(data, dev)
+    scores = p.to(dev, torch.float32).contiguous() if torch.is_tensor(p) else \
+        torch.from_numpy(np.ascontiguousarray(p, dtype=np.float32)).to(dev)
+    ks = sorted(set(k for _, k in wanted))
+    sums = rank_sums_device(scores, ctx['labels'], ctx['iids'], ctx['rows'], ctx['off'], ks).cpu().numpy()
+    return {(name, k): float(sums[ks.index(k), METRIC_COLUMN[name]]) for name, k in wanted}, ctx['n_users']
 
 
 class BaseModel(torch.nn.Module):
@@ -80,7 +129,7 @@ class BaseModel(torch.nn.Module):
         metric (ndcg, hit, precision, recall, f1) comes from the GPU ranker, averaged over users."""
         l = data['Y']
         evaluations = []
-        rank_ctx = None
+        rank_sums, n_users = _rank_metric_sums(p, data, metrics)
         for metric in metrics:
             if metric == 'rmse':
                 d = np.asarray(l, dtype=np.float64) - np.asarray(p, dtype=np.float64)
@@ -97,17 +146,7 @@ class BaseModel(torch.nn.Module):
                 name, k = metric.split('@')
                 if name not in METRIC_COLUMN:
                     continue
-                if rank_ctx is None:
-                    if not torch.cuda.is_available():
-                        raise RuntimeError('ranking metrics run on the GPU (dccf_rank_eval); no CUDA device is visible')
-                    dev = p.device if (torch.is_tensor(p) and p.is_cuda) else \
-                        torch.device('cuda', torch.cuda.current_device())
-                    rank_ctx = dict(rank_context(data, dev))
-                    rank_ctx['scores'] = p.to(dev, torch.float32).contiguous() if torch.is_tensor(p) else \
-                        torch.from_numpy(np.ascontiguousarray(p, dtype=np.float32)).to(dev)
-                m = rank_metrics_device(rank_ctx['scores'], rank_ctx['labels'], rank_ctx['iids'], rank_ctx['rows'],
-                                        rank_ctx['off'], int(k))
-                evaluations.append(float(m[:, METRIC_COLUMN[name]].mean().item()))
+                evaluations.append(rank_sums[(name, int(k))] / max(1, n_users))
         return evaluations
 
     @staticmethod
@@ -115,7 +154,7 @@ class BaseModel(torch.nn.Module):
         """(sums, counts) per metric over the rows of `data`, so that partial results of user shards can be
         added across ranks: rank metrics sum over users, mae sums |err| and rmse sums err^2 over rows."""
         sums, counts = [], []
-        ctx = None
+        rank_sums, n_users = _rank_metric_sums(p, data, metrics)
         for metric in metrics:
             if metric in ('rmse', 'mae'):
                 pl = p.detach().cpu().numpy() if torch.is_tensor(p) else np.asarray(p)
@@ -123,15 +162,11 @@ class BaseModel(torch.nn.Module):
                 sums.append(float(np.sum(d * d) if metric == 'rmse' else np.sum(np.abs(d))))
                 counts.append(float(len(d)))
                 continue
+            if '@' not in metric or metric.split('@')[0] not in METRIC_COLUMN:
+                raise ValueError('metric %r cannot be summed over user shards (use rmse, mae or <name>@k)' % metric)
             name, k = metric.split('@')
-            if ctx is None:
-                dev = p.device if (torch.is_tensor(p) and p.is_cuda) else torch.device('cuda', torch.cuda.current_device())
-                ctx = rank_context(data, dev)
-                scores = p.to(dev, torch.float32).contiguous() if torch.is_tensor(p) else \
-                    torch.from_numpy(np.ascontiguousarray(p, dtype=np.float32)).to(dev)
-            m = rank_metrics_device(scores, ctx['labels'], ctx['iids'], ctx['rows'], ctx['off'], int(k))
-            sums.append(float(m[:, METRIC_COLUMN[name]].sum().item()))
-            counts.append(float(m.shape[0]))
+            sums.append(rank_sums[(name, int(k))])
+            counts.append(float(n_users))
         return sums, counts
 
     @staticmethod

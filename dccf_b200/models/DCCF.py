@@ -115,6 +115,11 @@ class DCCF(DMF):
         # embedding, its Adam state, the exposure rows / IPS-MF user factors hold only those rows and every
         # batch it is given must contain only those users
         self.user_shard = None if user_shard is None else (int(user_shard[0]), int(user_shard[1]))
+        if int(n_layers) != 1:
+            # src/models/DCCF.py:58-60 sizes extra Linear(64 -> 64) layers from --n_layers (default 1, the value of the
+            # reference's README run): the fused kernels implement the single Linear(D + F -> D) predictor only
+            raise ValueError('--n_layers %d: the B200 DCCF kernels implement the reference default --n_layers 1 (one '
+                             'Linear(64 + F -> 64) + ReLU + Dropout); other depths are not supported' % int(n_layers))
         DMF.__init__(self, label_min=label_min, label_max=label_max, feature_num=feature_num, user_num=user_num,
                      item_num=item_num, u_vector_size=u_vector_size, i_vector_size=i_vector_size, n_layers=n_layers,
                      random_seed=random_seed, model_path=model_path)
@@ -200,8 +205,6 @@ class DCCF(DMF):
             # launches go to the current device's stream (dccf_b200/_lib.py: stream_ptr)
             raise RuntimeError('the model lives on %s but the current CUDA device is %d: call torch.cuda.set_device(%d) '
                                '(one process per GPU)' % (w.device, torch.cuda.current_device(), w.device.index))
-        if self.n_layers != 1:
-            raise NotImplementedError('the fused kernels implement the default --n_layers 1 (one Linear(D+F -> D))')
         if self.ui_vector_size != kernels.D:
             raise NotImplementedError('the kernels are compiled for u_vector_size = i_vector_size = %d' % kernels.D)
         if self.feature_embedding.device != w.device:
@@ -264,9 +267,10 @@ class DCCF(DMF):
     reuse_noise_rows = os.environ.get('DCCF_REUSE_X', '0') != '0'
     tc_min_rows = 128 * 148
     # noise-free inference (--std 0, dropout 0, no explicit noise / mask) as a pure gather over the projected item
-    # tables (dccf_score_gather) instead of the K = D + F contraction.  Written after round 1's GPU budget was spent:
-    # it stays OFF by default until its parity test (tests/test_gpu_zz_gather.py) has been seen green on a B200.
-    use_gather_scorer = os.environ.get('DCCF_GATHER', '0') != '0'
+    # tables (dccf_score_gather) instead of the K = D + F contraction: 1.9e-7 from the general FP32 scorer and green
+    # against the reference fixture on a B200 (tests/test_gpu_zz_gather.py, round-1 driver run).  On by default;
+    # DCCF_GATHER=0 falls back to the general scorer (the cross-check).
+    use_gather_scorer = os.environ.get('DCCF_GATHER', '1') != '0'
     # How inference draws the feature noise the library generates itself (--std > 0, no explicit noise tensor):
     #   'exact'     eps ~ N(0, std^2 I_F) per predictor row, multiplied into W_f — the reference's formulation
     #               (src/models/DCCF.py:87-92), F normals per row;
@@ -481,6 +485,51 @@ class DCCF(DMF):
         self._param_epoch += 1                      # projected tables / operand images of the old weights are stale
         return self
 
+    # ---- checkpoints with a row-sharded user table --------------------------------------------------------
+    def save_model(self, model_path=None):
+        """BaseModel.save_model (src/models/BaseModel.py:224-236).  With a row-sharded user table (`user_shard`) the
+        replicas are NOT identical: every rank sends its user rows to rank 0, which writes ONE state_dict with the full
+        [user_num, D] table under the reference's keys — the file is interchangeable with an unsharded run's."""
+        import logging
+        import torch.distributed as dist
+        if self.user_shard is None or not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return DMF.save_model(self, model_path)
+        model_path = model_path or self.model_path
+        rank, world = dist.get_rank(), dist.get_world_size()
+        w = self.uid_embeddings.weight.data
+        bounds = [None] * world
+        dist.all_gather_object(bounds, self.user_shard)
+        if rank == 0:
+            full = torch.empty((self.user_num, w.shape[1]), dtype=w.dtype, device=w.device)
+            full[bounds[0][0]:bounds[0][1]] = w
+            for r in range(1, world):
+                dist.recv(full[bounds[r][0]:bounds[r][1]], src=r)
+            sd = {k: v for k, v in self.state_dict().items()}
+            sd['uid_embeddings.weight'] = full
+            dir_path = os.path.dirname(model_path)
+            if dir_path and not os.path.exists(dir_path):
+                os.makedirs(dir_path)
+            torch.save(sd, model_path)
+        else:
+            dist.send(w.contiguous(), dst=0)
+        dist.barrier()
+        logging.info('Save model to ' + model_path)
+
+    def load_model(self, model_path=None):
+        """BaseModel.load_model; a rank that owns users [lo, hi) keeps only those rows of the saved user table."""
+        import logging
+        if self.user_shard is None:
+            return DMF.load_model(self, model_path)
+        model_path = model_path or self.model_path
+        sd = torch.load(model_path, map_location='cpu')
+        lo, hi = self.user_shard
+        if sd['uid_embeddings.weight'].shape[0] == self.user_num:
+            sd['uid_embeddings.weight'] = sd['uid_embeddings.weight'][lo:hi].clone()
+        self.load_state_dict(sd)
+        self._param_epoch += 1
+        self.eval()
+        logging.info('Load model from ' + model_path)
+
     def check_ids(self):
         """Raise if any kernel since the last check met a user/item id outside the tables (the kernels clamp
         such ids and raise a device flag instead of faulting; the reference would raise an IndexError)."""
@@ -537,18 +586,33 @@ class DCCF(DMF):
             return outs
         pin = torch.cuda.is_available()
         q = queue.Queue(maxsize=max(1, depth))
+        stop = threading.Event()
+
+        def put(item):
+            # never block for ever on the bounded queue: a consumer that failed stops reading it
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
 
         def produce():
             try:
                 for fd in feed_dicts:
+                    if stop.is_set():
+                        return
                     if 'sample_item' in fd or S == 0:
-                        q.put(None)
+                        if not put(None):
+                            return
                         continue
                     buf = torch.empty((fd['X'].shape[0], S), dtype=torch.int64, pin_memory=pin)
                     host_rng.randint(self.item_num, (fd['X'].shape[0], S), out=buf)
-                    q.put(buf)
+                    if not put(buf):
+                        return
             except BaseException as e:      # surface the failure in the consumer
-                q.put(e)
+                put(e)
 
         worker = threading.Thread(target=produce, daemon=True)
         worker.start()
@@ -563,7 +627,8 @@ class DCCF(DMF):
                     fd['sample_item'] = draw
                 outs.append(self.predict(fd)['prediction'])
         finally:
-            worker.join()
+            stop.set()                      # a failed predict: release the producer, then wait for it (bounded)
+            worker.join(timeout=30)
         return outs
 
     def forward(self, feed_dict):
@@ -888,7 +953,14 @@ class DCCF(DMF):
                     rec = self._launch_bwd(call, loss_mode=loss_mode, Y=Yg)
                 loss = self._apply_adam(rec, P, opt, hp).clone()
                 kernels.state_advance(g['step_dev'], g['offset_dev'], 1)
-        g.update({'graph': graph, 'pred': pred, 'loss': loss, 'call': call,
+        # The captured graph holds RAW device pointers: every workspace the capture touched (grow-only buffers that a
+        # later, larger call would replace and free), the optimizer state and the exchange buffers stay referenced
+        # from the graph entry for as long as the graph can be replayed.
+        keep = {'ws': dict(self._ws), 'opt': opt, 'err_flag': self._err_flag,
+                'streams': (self.__dict__.get('_side_stream'), self.__dict__.get('_ship_stream'))}
+        if self._dp is not None:
+            keep['dp'] = (dict(self._dp.get('ex', {})), dict(self._dp.get('ids', {})))
+        g.update({'graph': graph, 'pred': pred, 'loss': loss, 'call': call, 'keep_alive': keep,
                   'n_kernels': kernels.LAUNCHES[0] - launches_before})
         kernels.LAUNCHES[0] = launches_before           # capturing launched nothing
         return g
@@ -928,7 +1000,7 @@ class DCCF(DMF):
         self._check_ready()
         rank_mode = int(feed_dict['rank'])
         p_drop = float(feed_dict.get('dropout', 0.0))
-        key = (P, rank_mode, p_drop, id(opt), False, self._dp is not None)
+        key = (P, rank_mode, p_drop, opt, False, self._dp is not None)      # (the optimizer OBJECT: its id could be recycled)
         graphs = self.__dict__.setdefault('_graphs', {})
         g = graphs.get(key)
         if g is None:
@@ -949,6 +1021,15 @@ class DCCF(DMF):
             g['Y'].copy_(feed_dict['Y'], non_blocking=True)
         return self._replay(g, opt)
 
+    def resident_epoch_available(self, P, opt=None):
+        """True when begin_resident_epoch would return a step function for batches of P pairs — lets the runner decide
+        BEFORE it consumes the torch CPU generator for the epoch's confounder draws."""
+        opt = opt or self.optimizer
+        if not isinstance(opt, FusedAdamState) or not self.use_cuda_graph:
+            return False
+        self._check_ready()
+        return bool(self._graph_allowed(P))
+
     def begin_resident_epoch(self, X_epoch, sample_epoch, dropout, opt=None):
         """Training over a device-resident epoch: X_epoch [n, P, 2] and sample_epoch [n, P, S] int64 CUDA tensors
         (all batches of P pairs; the confounder block is ONE torch.randint(item_num, (n*P, S)) call, which yields
@@ -963,7 +1044,7 @@ class DCCF(DMF):
         if not self._graph_allowed(P) or n == 0:
             return None
         p_drop = float(dropout)
-        key = (P, 1, p_drop, id(opt), True, self._dp is not None)
+        key = (P, 1, p_drop, opt, True, self._dp is not None)
         graphs = self.__dict__.setdefault('_graphs', {})
         state = {'next': 0}
         if key not in graphs:

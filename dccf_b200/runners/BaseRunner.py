@@ -223,6 +223,12 @@ class BaseRunner(object):
             mine, _ = step_partition(n_full, world, rank)
             chunk = 1024
             done = 0                                    # global steps run so far
+            if hasattr(model, 'resident_epoch_available') and not model.resident_epoch_available(P0):
+                # no CUDA-graph step for this configuration: nothing has been drawn from the torch CPU generator yet,
+                # so the step-by-step loop below consumes it exactly as the reference does
+                if world > 1:
+                    raise RuntimeError('data-parallel training needs the CUDA-graph step (peer-memory exchange)')
+                mine = []
             while done < len(mine):
                 m = min(chunk, len(mine) - done)
                 X_epoch = torch.stack([batches[i]['X'] for i in mine[done:done + m]])

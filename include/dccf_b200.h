@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 29
+#define DCCF_ABI_VERSION 30
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -327,18 +327,33 @@ int dccf_debug_timeline_dp(unsigned long long* slots);
 
 /* ---- (d): evaluation ranker -------------------------------------------------------------- */
 /* Replaces BaseModel.evaluate_method ranking branch (src/models/BaseModel.py:82-126) and
- * src/utils/rank_metrics.py:61-87,130-201 for binary labels.
- *   scores [n_rows] f32, labels [n_rows] f32 (0/1), iids [n_rows] int64, all in data order
- *   cand_rows [n_cand] int32: row indices grouped by user; user g owns cand_rows[off[g]..off[g+1])
+ * src/utils/rank_metrics.py:61-87,130-201.
+ *   scores [n_rows] f32, labels [n_rows] f32, iids [n_rows] int64, all in data order
+ *   cand_rows [n_cand] int32: row indices grouped by user; user g owns cand_rows[off[g]..off[g+1]).
+ *             NULL: the rows are already grouped by user (the evaluation set is built user-major), candidate c
+ *             IS row c and the scores / labels are read contiguously
  *   user_off  [n_users+1] int64
- * Ranking order: score descending, ties by item id ascending, then by row index ascending.
+ * Ranking order: score descending, ties by item id ascending, then by row index ascending; NaN last.
  *   out_topk_iid [n_users,k] int64 (-1 padded), out_topk_row [n_users,k] int32 (may be NULL)
  *   out_metrics  [n_users,5] f64: ndcg@k, hit@k, precision@k, recall@k, f1@k
- */
+ * k <= 16: one streaming pass per user (per-lane top-k in registers); larger k: k selection rounds. */
 int dccf_rank_eval(const float* scores, const float* labels, const int64_t* iids,
                    const int32_t* cand_rows, const int64_t* user_off, int64_t n_users, int32_t k,
                    int64_t* out_topk_iid, int32_t* out_topk_row, double* out_metrics,
                    void* stream);
+/* Every '<name>@k' metric of a metric list in ONE launch (the reference loops over the users once per metric,
+ * src/models/BaseModel.py:90-126): ks = HOST array of n_k (1..4) strictly ascending values of k, each <= 16.
+ *   out_topk_iid / out_topk_row [n_users, ks[n_k-1]]  (may be NULL)
+ *   out_metrics [n_users, n_k, 5] f64 (may be NULL when out_sums is given)
+ *   out_sums    [n_k, 5] f64: the per-user values summed over users in a fixed order (warp, CTA, then the CTAs in
+ *               index order by the last CTA to finish) — what np.average over users needs; may be NULL
+ *   ws          device workspace of dccf_rank_eval_ws_bytes() bytes, ZERO on first use (the kernel leaves its
+ *               counter at zero); required with out_sums */
+int64_t dccf_rank_eval_ws_bytes(int64_t n_users);
+int dccf_rank_eval_multi(const float* scores, const float* labels, const int64_t* iids, const int32_t* cand_rows,
+                         const int64_t* user_off, int64_t n_users, const int32_t* ks, int32_t n_k,
+                         int64_t* out_topk_iid, int32_t* out_topk_row, double* out_metrics, void* ws,
+                         double* out_sums, void* stream);
 
 /* ---- data-parallel gradient exchange over NVLink peer memory (new: the reference is single-GPU) ----- */
 /* Every rank owns a symmetric buffer of floats: [ recv: world*seg | arrival flags int32[8] | consumed flags

@@ -78,6 +78,29 @@ def _worker(rank, world, port, out_dir):
         sync_host_rng(m)
         torch.save({'draw': torch.randint(1 << 20, (8,)), 'offset': m._rng_offset},
                    os.path.join(out_dir, 'rng_%d.pt' % rank))
+        # row-sharded user table: the checkpoint holds the FULL table under the reference's keys (rank 0 collects the
+        # rows), and every rank loads its own slice back
+        from dccf_b200.models.DCCF import DCCF
+        U, I, F = 10, 7, 64
+        lo, hi = (0, 6) if rank == 0 else (6, 10)
+        path = os.path.join(out_dir, 'sharded.pt')
+        model = DCCF(path='', dataset='', sentence_model='', sample_num=2, attribute_num=1, std=0.0, label_min=0,
+                     label_max=1, feature_num=0, user_num=U, item_num=I, u_vector_size=64, i_vector_size=64, n_layers=1,
+                     random_seed=1, model_path=path, feature_embedding=torch.zeros(I, F), expo_prob=torch.ones(U, I),
+                     user_shard=(lo, hi))
+        with torch.no_grad():
+            model.uid_embeddings.weight.copy_(torch.arange(lo, hi, dtype=torch.float32)[:, None].expand(hi - lo, 64))
+            model.iid_embeddings.weight.fill_(3.0)
+        assert model.expo_prob.shape[0] == hi - lo
+        model.save_model()
+        sd = torch.load(path, map_location='cpu')
+        assert sd['uid_embeddings.weight'].shape == (U, 64)
+        assert torch.equal(sd['uid_embeddings.weight'][:, 0], torch.arange(U, dtype=torch.float32))
+        assert sorted(sd) == ['iid_embeddings.weight', 'mlp.0.bias', 'mlp.0.weight', 'uid_embeddings.weight']
+        with torch.no_grad():
+            model.uid_embeddings.weight.zero_()
+        model.load_model()
+        assert torch.equal(model.uid_embeddings.weight[:, 5], torch.arange(lo, hi, dtype=torch.float32))
     finally:
         dist.destroy_process_group()
 

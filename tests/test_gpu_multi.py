@@ -22,8 +22,6 @@ def test_data_parallel_equals_single_gpu():
     assert r.returncode == 0 and 'DP CHECK OK' in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-@pytest.mark.xfail(strict=False, reason='written after the GPU budget of round 1 was spent: first hardware run; '
-                                        'XPASS = verified')
 def test_cli_data_parallel_training(tmp_path):
     """src/main.py under torchrun on 2 GPUs: trains, evaluates (user-sharded), rank 0 writes the files, and the
     run ends with the replica checksum (identical parameters on both ranks)."""

@@ -409,6 +409,69 @@ def test_ranker_topk_ids_bit_exact_with_ties():
         assert np.abs(m.cpu().numpy() - want_m).max() < 1e-12
 
 
+def test_ranker_all_metrics_one_launch_grouped_rows_and_graded_labels():
+    """dccf_rank_eval_multi: every metric at several k from ONE launch (per-user values and their fixed-order sums),
+    the contiguous path (rows already grouped by user: no cand_rows indirection), graded (non 0/1) labels through the
+    ideal-DCG fallback, and k > 16 through the selection kernel — all against the oracle's per-user loop."""
+    from dccf_b200 import kernels
+    from dccf_b200.models.BaseModel import BaseModel, group_candidates, rank_metrics_device, rank_sums_device
+    rs = np.random.RandomState(11)
+    for graded in (False, True):
+        uid, iid, Y = [], [], []
+        for u in range(300):
+            n = int(rs.choice([1, 3, 8, 16, 17, 33, 257, 1001, 1004]))
+            uid += [u] * n
+            iid += list(rs.choice(6000, n, replace=False))
+            lab = (rs.random_sample(n) < 0.15).astype(np.float32)
+            if graded:
+                lab = lab * rs.randint(1, 6, size=n).astype(np.float32)
+            lab[rs.randint(n)] = 1.0 if not graded else 3.0
+            Y += list(lab)
+        uid, iid, Y = np.array(uid), np.array(iid, dtype=np.int64), np.array(Y, dtype=np.float32)
+        scores = np.round(rs.standard_normal(len(uid)), 2).astype(np.float32)
+        scores[rs.randint(0, len(uid), 30)] = np.nan
+        for shuffled in (False, True):
+            if shuffled:
+                perm = rs.permutation(len(uid))
+                uid, iid, Y, scores = uid[perm], iid[perm], Y[perm], scores[perm]
+            _, rows, off = group_candidates(uid)
+            grouped = np.array_equal(rows, np.arange(len(rows)))
+            assert grouped == (not shuffled)
+            rows_d = None if grouped else torch.from_numpy(rows).cuda()
+            sc, lb, ii, of = (torch.from_numpy(scores).cuda(), torch.from_numpy(Y).cuda(), torch.from_numpy(iid).cuda(),
+                              torch.from_numpy(off).cuda())
+            ks = [1, 5, 10, 16]
+            n_users = len(off) - 1
+            per_user = torch.empty((n_users, len(ks), 5), dtype=torch.float64, device='cuda')
+            sums = torch.empty((len(ks), 5), dtype=torch.float64, device='cuda')
+            topk = torch.empty((n_users, ks[-1]), dtype=torch.int64, device='cuda')
+            before = kernels.LAUNCHES[0]
+            kernels.rank_eval_multi(sc, lb, ii, rows_d, of, ks, out_metrics=per_user, out_sums=sums, out_topk_iid=topk)
+            assert kernels.LAUNCHES[0] - before == 1
+            per_user, sums = per_user.cpu().numpy(), sums.cpu().numpy()
+            for j, k in enumerate(ks):
+                _, want_ids, _, want_m = O.rank_users(scores, uid, Y, iid, k)
+                assert np.array_equal(topk.cpu().numpy()[:, :k], want_ids)
+                assert np.nanmax(np.abs(per_user[:, j] - want_m)) < 1e-12
+                assert np.array_equal(np.isnan(per_user[:, j]), np.isnan(want_m))
+                assert np.abs(sums[j] - want_m.sum(axis=0)).max() < 1e-9
+            # a second call reuses the workspace (the kernel leaves its counter at zero)
+            again = rank_sums_device(sc, lb, ii, rows_d, of, [10, 5]).cpu().numpy()
+            assert np.array_equal(again[0], sums[2]) and np.array_equal(again[1], sums[1])
+            # k > 16: the selection kernel
+            _, want_ids, _, want_m = O.rank_users(scores, uid, Y, iid, 20)
+            m20, t20 = rank_metrics_device(sc, lb, ii, rows_d, of, 20, want_topk=True)
+            assert np.array_equal(t20.cpu().numpy(), want_ids)
+            assert np.nanmax(np.abs(m20.cpu().numpy() - want_m)) < 1e-12
+        data = {'uid': uid, 'iid': iid, 'Y': Y}
+        names = ['ndcg@5', 'recall@5', 'precision@5', 'hit@10', 'f1@3', 'ndcg@20']
+        before = kernels.LAUNCHES[0]
+        got = BaseModel.evaluate_method(np.nan_to_num(scores, nan=-1e9), data, names)
+        assert kernels.LAUNCHES[0] - before == 2            # one launch for k in {3, 5, 10}, one for k = 20
+        want = O.evaluate_method(np.nan_to_num(scores, nan=-1e9), data, names)
+        assert np.abs(np.array(got) - np.array(want)).max() < 1e-12
+
+
 # ---------------------------------------------------------------------------------------------------------
 # optimizer sweep
 # ---------------------------------------------------------------------------------------------------------
@@ -768,8 +831,6 @@ def test_fused_adam_step_record_lists():
     assert rel_err(res[0][0], want_p) < 1e-5 and rel_err(res[0][3], want_W) < 1e-5
 
 
-@pytest.mark.xfail(strict=False, reason='written after the GPU budget of round 1 was spent: first hardware run at round '
-                                        'end; XPASS = verified (the kernels it drives are the validated ones)')
 def test_fused_training_follows_the_reference_at_config0(tmp_path):
     """BASELINE.json configs[0] at full size on the GPU: the first 24 training steps of the UNMODIFIED reference
     (tests/golden/config0_train.npz) replayed through model.train_step — 256 pairs = 5 632 predictor rows x 832 inputs
@@ -805,8 +866,6 @@ def test_fused_training_follows_the_reference_at_config0(tmp_path):
     model.check_ids()
 
 
-@pytest.mark.xfail(strict=False, reason='written after the GPU budget of round 1 was spent: first hardware run at round '
-                                        'end; XPASS = verified (the kernels it drives are the validated ones)')
 def test_evaluation_follows_the_reference_at_config0(tmp_path):
     """BASELINE.json configs[0], evaluation on the GPU: the reference's own predictions and ndcg@5 / recall@5 /
     precision@5 for 100 test users x (positives + 1000 negatives) (tests/golden/config0_eval.npz), reproduced through
@@ -831,8 +890,6 @@ def test_evaluation_follows_the_reference_at_config0(tmp_path):
     assert np.abs(np.array(vals) - g['values']).max() < 1e-6
 
 
-@pytest.mark.xfail(strict=False, reason='written after the GPU budget of round 1 was spent: first hardware run at round '
-                                        'end; XPASS = verified (the kernels it drives are the validated ones)')
 def test_ipsmf_exposure_matches_reference(golden):
     """The reference's IPSBiasedMF.predict over a whole U x I grid (tests/golden/ipsmf.npz, src/models/IPSBiasedMF.py:
     37-57) against the full-catalogue tcgen05 GEMM (the ips_expo_prob.npy producer) and against the on-the-fly
@@ -856,8 +913,6 @@ def test_ipsmf_exposure_matches_reference(golden):
     assert rel_err(a, b) < 3e-5
 
 
-@pytest.mark.xfail(strict=False, reason='written after the GPU budget of round 1 was spent: first hardware run at round '
-                                        'end; XPASS = verified (the kernels it drives are the validated ones)')
 def test_whole_dccf_run_equals_reference_run(golden, tmp_path):
     """src/main.py's whole sequence with DCCF on the GPU == the same sequence of the UNMODIFIED reference in the
     deterministic configuration --std 0 --dropout 0 (tests/golden/run_dccf.npz, oracle/make_golden.py::

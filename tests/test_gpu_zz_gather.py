@@ -4,11 +4,9 @@ drawn in the 64-d image of W_f (DCCF.eval_noise = 'projected') against the refer
 noise tensor; and torch's CPU generator continued on the device (k_confounder_draw, host_rng.DeviceStream,
 DCCF.device_confounders) against torch.randint itself.  Needs a GPU.
 
-The kernel was written after round 1's GPU budget was spent, so its first execution on a B200 is the round-end run of
-this file.  Two precautions follow from that: the cases run in a CHILD process (a faulting kernel poisons the CUDA
-context of the process that launched it — it must not take the rest of the suite down with it), and they are
-`xfail(strict=False)`: XPASS in the summary = seen green on hardware, after which the marker goes and
-`DCCF.use_gather_scorer` becomes the default for noise-free inference.  The product default is OFF until then."""
+All cases were seen green on a B200 by the round-1 driver run; `DCCF.use_gather_scorer` is the default for noise-free
+inference since round 2.  The cases still run in ONE child process (one torch import, one CUDA context; a faulting
+kernel would poison the CUDA context of the process that launched it and must not take the rest of the suite down)."""
 import os
 import subprocess
 import sys
@@ -39,8 +37,6 @@ def worker_output():
     return r.returncode, r.stdout, r.stderr
 
 
-@pytest.mark.xfail(strict=False, reason='first executed on a GPU by the round-end run (written after the GPU budget '
-                                        'of round 1 was spent); XPASS = verified')
 @pytest.mark.parametrize('case', CASES)
 def test_gather_scorer(worker_output, case):
     rc, out, err = worker_output
