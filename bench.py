@@ -5,14 +5,23 @@
 
 One JSON line on stdout (rank 0).  A "step" is one training batch of the reference configuration
 (--batch_size 128 -> 256 scored pairs: 128 positives + their sampled negatives; S=10 confounders, A=2,
-std 0.1, dropout 0.2, Adam lr 1e-3, l2 1e-4) on synthetic Electronics-shaped data; `value` is train
-samples/s with the batches already in HBM, `e2e` the same through the public API from pinned host
-buffers (confounder draw on the CPU generator, H2D of ids, D2H of the loss every step).  The `eval`
-object holds the evaluation half of the metric: users/s for ranking each test user's positive against
-test_neg_n = 1000 sampled negatives (scoring + on-device top-k/ndcg/recall/precision@5).
-`eval_noise_free` (a --std 0 model scored by the gather kernel) and `eval_projected_noise` (the reference defaults with
-the feature noise drawn in the 64-d image of W_f, opt-in) are measured by a child process on rank 0 at N = 1 and
-reported next to it (--no-extra-legs skips them); the headline objects keep the reference's formulation.
+std 0.1, dropout 0.2, Adam lr 1e-3, l2 1e-4) on synthetic Electronics-shaped data (BASELINE.json configs[1]);
+`value` is train samples/s with the batches already in HBM, `e2e` the same through the public API
+(model.train_step) from pinned host buffers — ids staged and uploaded every step, confounders drawn on the torch
+CPU generator every step, the loss copied back every step.  The `eval` object holds the evaluation half of the
+metric: users/s for ranking each test user's positive against test_neg_n = 1000 sampled negatives (scoring +
+on-device top-k/ndcg/recall/precision@5 in one ranker launch).
+
+Further objects on the same line (tools/bench_legs.py):
+  dp_parity            N > 1: the data-parallel step equals the single-GPU step on the concatenated batch (checked BEFORE
+                       timing; the process exits with rc 3 when it does not) + replica checksum after the timed steps
+  config3_cds          BASELINE.json configs[2]: the same train / eval pair at the CDs_and_Vinyl shape
+  config4_full_catalogue  configs[3]: Yelp shape, full-catalogue tcgen05 GEMM + top-k, users sharded over the N ranks
+  config5_scaled       configs[4]: 10 M x 1 M, row-sharded user table, on-the-fly IPSBiasedMF exposure
+  eval_noise_free / eval_projected_noise / gpu_eager_reference / cpu_baseline   N = 1 only (child process for the first two)
+--legs selects them (default: all that apply); --no-extra-legs / --no-cpu-baseline skip groups.
+Every roofline object reports `frac` on ALGORITHMIC work (SURVEY.md §8d flops / bytes); `frac_issued` counts the three
+TF32 products the tensor cores actually execute per FP32 product.
 """
 import argparse
 import json
@@ -52,6 +61,10 @@ NCU_EVAL_TRAFFIC_SOURCE = ('profiles/r1c_ncu_full_tc_summary.csv (ncu --set full
                            'cache; the later tuning of the kernel did not change what it reads)')
 NCU_TRAFFIC_BYTES = {'k_train_fwd_tc': 1.89e6, 'k_train_mid': 4.47e6, 'k_train_bwd_tc': 2.92e6, 'k_adam_touched': 7.91e6,
                      'k_adam_untouched': 47.35e6 + 0.81e6}
+# round 2 captures (profiles/r2a_ncu_legs_summary.csv, r2a_ncu_full_catalogue_summary.csv): per launch, cold cache
+NCU_R2 = {'source': 'profiles/r2a_ncu_legs_summary.csv (ncu --set full --clock-control none, per launch, cold cache)',
+          'k_gather_scores': None, 'k_row_scores_tc_64': None, 'k_rank_stream': None, 'k_confounder_draw': None,
+          'k_full_scores_topk': None, 'k_full_scores_materialise': None}
 FLOP_FWD_PAIR = R * (2 * (D + F) * D + 4 * D)
 FLOP_BWD_PAIR = R * (2 * (D + F) * D + 2 * D * D + 2 * D)
 BYTES_PAIR = 16 + 4 * D + 4 * D * Z + 4 * F + 4 * Z
@@ -288,54 +301,76 @@ def bench_train(model, X_all, steps, warmup, world, flush):
                 stage_ms[st] += evs[i][st].elapsed_time(evs[i][st + 1])
         stage_ms /= max(1, n_s - warmup)
 
-    # ---- e2e: public API from pinned host memory, loss read back every step ---------------------
+    # ---- e2e: the public API (model.train_step) fed from the host every step ------------------------------------
+    # Per step: ids in pinned host memory -> staged with the step's confounder draw (torch CPU generator, DCCF.py:72)
+    # and uploaded by one asynchronous copy, one CUDA-graph launch, the loss copied back into a pinned slot.  The
+    # host does not wait for the device inside the loop (the reference's loop does not either: it reads the loss at
+    # check_epoch, src/runners/BaseRunner.py:247-248); the timed region ends with a synchronise.  The L2 flush between
+    # steps is kept (same kernels as `value`); its device time, measured by events around every flush, is subtracted.
     X_pin = torch.from_numpy(X_all[:n]).pin_memory()
-    e2e_s = 0.0
+    losses = torch.zeros(n, dtype=torch.float32).pin_memory()
     torch.manual_seed(SEED + 12)
+    fl_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(n)]
+
+    def e2e_step(i):
+        fl_ev[i][0].record()
+        flush()
+        fl_ev[i][1].record()
+        out = model.train_step({'X': X_pin[i], 'Y': Y, 'rank': 1, 'train': True, 'dropout': DROPOUT})
+        losses[i:i + 1].copy_(out['loss'].view(1), non_blocking=True)
+
     barrier(world)
-    draw = model.draw_confounders(2 * BATCH)                            # DCCF.py:72 on the CPU generator
-    for i in range(n):
+    for i in range(warmup):
+        e2e_step(i)
+    barrier(world)
+    t0 = time.perf_counter()
+    for i in range(warmup, n):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    flush_s = sum(fl_ev[i][0].elapsed_time(fl_ev[i][1]) for i in range(warmup, n)) / 1e3
+    e2e_s = dist_max(max(t1 - t0 - flush_s, 1e-9), world)
+    loss = float(losses[n - 1])
+    assert np.isfinite(losses.numpy()).all()
+    # the same loop with the host waiting for every step's loss before it starts the next (latency-bound)
+    n_sync = min(steps, 50)
+    sync_s = 0.0
+    for i in range(n_sync):
         flush()
         torch.cuda.synchronize()
-        if i == warmup:
-            barrier(world)
         t0 = time.perf_counter()
-        fd = {'X': X_pin[i], 'Y': Y, 'rank': 1, 'train': True, 'dropout': DROPOUT,     # pinned host ids: the step
-              'sample_item': draw}                                                   # copies them in (H2D)
-        out = model.train_step(fd)
-        draw = model.draw_confounders(2 * BATCH)                        # next step's draw overlaps this step
-        loss = float(out['loss'].item())                                # D2H + sync
-        t1 = time.perf_counter()
-        if i >= warmup:
-            e2e_s += t1 - t0
-    assert np.isfinite(loss)
-    e2e_s = dist_max(e2e_s, world)
+        out = model.train_step({'X': X_pin[warmup + i], 'Y': Y, 'rank': 1, 'train': True, 'dropout': DROPOUT})
+        float(out['loss'].item())
+        sync_s += time.perf_counter() - t0
+    sync_s = dist_max(sync_s / max(1, n_sync), world)
     return {'total_ms': total_ms, 'stage_ms': stage_ms, 'kernels_us': kernels_us, 'timeline_step_us': timeline_step_us,
-            'launches': launches, 'e2e_s': e2e_s, 'b2b_ms': b2b_ms,
+            'launches': launches, 'e2e_s': e2e_s, 'e2e_sync_s_per_step': sync_s, 'b2b_ms': b2b_ms,
             'h2d': 2 * BATCH * 2 * 8 + 2 * BATCH * S * 8, 'd2h': 4, 'last_loss': loss}
 
 
 def bench_eval(model, n_users, warm_batches, world, rank, flush):
     """Scores n_users x 1001 candidates in eval batches of 16384 pairs and ranks them on the device."""
-    from dccf_b200.models.BaseModel import group_candidates, rank_metrics_device
+    from dccf_b200.models.BaseModel import candidate_layout, rank_sums_device
     dev = next(model.parameters()).device
     U, I = model.user_num, model.item_num
     X, uid, iid, Y = synth_eval_set(n_users, U, I, SEED + 100 * rank)
     rows = X.shape[0]
     bounds = [(a, min(rows, a + EVAL_BATCH)) for a in range(0, rows, EVAL_BATCH)]
-    _, cand, off = group_candidates(uid)
-    cand_d, off_d = torch.from_numpy(cand).to(dev), torch.from_numpy(off).to(dev)
+    cand, off = candidate_layout(uid)
+    cand_d, off_d = (None if cand is None else torch.from_numpy(cand).to(dev)), torch.from_numpy(off).to(dev)
     Y_d, iid_d = torch.from_numpy(Y).to(dev), torch.from_numpy(iid).to(dev)
     X_d = torch.from_numpy(X).to(dev)
     torch.manual_seed(SEED + 13)
     si_d = torch.randint(I, size=(rows, S)).to(dev)
     model.eval()
 
-    def rank_and_sum(pred):
+    def rank_and_sum(pred, flushed=False):
+        """all metrics @5 of every user + their sums over users: ONE ranker launch (dccf_rank_eval_multi)"""
+        if flushed:
+            flush()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        m = rank_metrics_device(pred, Y_d, iid_d, cand_d, off_d, 5)
-        sums = m.sum(dim=0)
+        sums = rank_sums_device(pred, Y_d, iid_d, cand_d, off_d, [5])[0]
         e1.record()
         return sums, (e0, e1)
 
@@ -350,7 +385,7 @@ def bench_eval(model, n_users, warm_batches, world, rank, flush):
                                         'sample_item': si_d[a:b]})['prediction'])
             e1.record()
             ev_pairs.append((e0, e1))
-        sums, ev = rank_and_sum(torch.cat(preds))
+        sums, ev = rank_and_sum(torch.cat(preds), flushed=True)
         return sums, ev_pairs + [ev]
 
     def run_from_host(X_pin):
@@ -366,7 +401,7 @@ def bench_eval(model, n_users, warm_batches, world, rank, flush):
     for _ in range(3):
         model.predict({'X': X_d[:EVAL_BATCH], 'rank': 1, 'train': False, 'dropout': 0.0,
                             'sample_item': si_d[:EVAL_BATCH]})
-        rank_metrics_device(torch.zeros(rows, device=dev), Y_d, iid_d, cand_d, off_d, 5).sum(dim=0)
+        rank_sums_device(torch.zeros(rows, device=dev), Y_d, iid_d, cand_d, off_d, [5])
     barrier(world)
     sums, evs = run_resident()
     barrier(world)
@@ -427,15 +462,15 @@ def noise_free_eval(U, I, n_users, dev):
     """Same evaluation workload (n_users x 1001 candidates, batches of 16384 pairs, on-device ranking) for a model
     with --std 0: scoring is dccf_score_gather.  Returns the object reported as `eval_noise_free`.  Runs in its own
     process (see main): the kernel had not run on hardware when the round's GPU budget ended."""
-    from dccf_b200.models.BaseModel import group_candidates, rank_metrics_device
+    from dccf_b200.models.BaseModel import candidate_layout, rank_sums_device
     model = build_model(U, I, dev, std=0.0)
     model.eval()
     flush = L2Flusher(dev)
     X, uid, iid, Y = synth_eval_set(n_users, U, I, SEED)
     rows = X.shape[0]
     bounds = [(a, min(rows, a + EVAL_BATCH)) for a in range(0, rows, EVAL_BATCH)]
-    _, cand, off = group_candidates(uid)
-    cand_d, off_d = torch.from_numpy(cand).to(dev), torch.from_numpy(off).to(dev)
+    cand, off = candidate_layout(uid)
+    cand_d, off_d = (None if cand is None else torch.from_numpy(cand).to(dev)), torch.from_numpy(off).to(dev)
     Y_d, iid_d, X_d = torch.from_numpy(Y).to(dev), torch.from_numpy(iid).to(dev), torch.from_numpy(X).to(dev)
     torch.manual_seed(SEED + 13)
     si_d = torch.randint(I, size=(rows, S)).to(dev)
@@ -463,7 +498,7 @@ def noise_free_eval(U, I, n_users, dev):
             evs.append((e0, e1))
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record()
-        sums = rank_metrics_device(torch.cat(preds), Y_d, iid_d, cand_d, off_d, 5).sum(dim=0)
+        sums = rank_sums_device(torch.cat(preds), Y_d, iid_d, cand_d, off_d, [5])[0]
         r1.record()
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in evs), r0.elapsed_time(r1), sums.cpu().numpy()
@@ -476,7 +511,7 @@ def noise_free_eval(U, I, n_users, dev):
         return [model.predict(fd(a, b))['prediction'] for a, b in bounds]
 
     def whole_pass():
-        return rank_metrics_device(torch.cat(score_only()), Y_d, iid_d, cand_d, off_d, 5).sum(dim=0)
+        return rank_sums_device(torch.cat(score_only()), Y_d, iid_d, cand_d, off_d, [5])[0]
 
     graph_score_ms = graph_pass_ms(score_only)
     graph_total_ms = graph_pass_ms(whole_pass)
@@ -506,15 +541,15 @@ def projected_noise_eval(U, I, n_users, dev):
     drawn in the 64-dimensional image of W_f (identically distributed predictions, 64 instead of 768 normals per
     predictor row) and goes through the same tcgen05 scorer with a 64-wide operand.  Reported NEXT TO the headline
     `eval` object, which keeps the reference's formulation."""
-    from dccf_b200.models.BaseModel import group_candidates, rank_metrics_device
+    from dccf_b200.models.BaseModel import candidate_layout, rank_sums_device
     model = build_model(U, I, dev)
     model.eval()
     flush = L2Flusher(dev)
     X, uid, iid, Y = synth_eval_set(n_users, U, I, SEED)
     rows = X.shape[0]
     bounds = [(a, min(rows, a + EVAL_BATCH)) for a in range(0, rows, EVAL_BATCH)]
-    _, cand, off = group_candidates(uid)
-    cand_d, off_d = torch.from_numpy(cand).to(dev), torch.from_numpy(off).to(dev)
+    cand, off = candidate_layout(uid)
+    cand_d, off_d = (None if cand is None else torch.from_numpy(cand).to(dev)), torch.from_numpy(off).to(dev)
     Y_d, iid_d, X_d = torch.from_numpy(Y).to(dev), torch.from_numpy(iid).to(dev), torch.from_numpy(X).to(dev)
     torch.manual_seed(SEED + 13)
     si_d = torch.randint(I, size=(rows, S)).to(dev)
@@ -533,7 +568,7 @@ def projected_noise_eval(U, I, n_users, dev):
         pred = torch.cat(preds)
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record()
-        sums = rank_metrics_device(pred, Y_d, iid_d, cand_d, off_d, 5).sum(dim=0)
+        sums = rank_sums_device(pred, Y_d, iid_d, cand_d, off_d, [5])[0]
         r1.record()
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in evs), r0.elapsed_time(r1), sums.cpu().numpy(), pred
@@ -550,7 +585,7 @@ def projected_noise_eval(U, I, n_users, dev):
                                'sample_item': si_d[a:b]})['prediction'] for a, b in bounds]
 
     def whole_pass():
-        return rank_metrics_device(torch.cat(score_only()), Y_d, iid_d, cand_d, off_d, 5).sum(dim=0)
+        return rank_sums_device(torch.cat(score_only()), Y_d, iid_d, cand_d, off_d, [5])[0]
 
     graph_score_ms = graph_pass_ms(score_only)
     graph_total_ms = graph_pass_ms(whole_pass)
@@ -569,7 +604,7 @@ def projected_noise_eval(U, I, n_users, dev):
     def from_host():
         fds = [{'X': X_pin[a:b].to(dev, non_blocking=True), 'rank': 1, 'train': False, 'dropout': 0.0} for a, b in bounds]
         pred = torch.cat(model.predict_many(fds))
-        return rank_metrics_device(pred, Y_d, iid_d, cand_d, off_d, 5).sum(dim=0).cpu().numpy()
+        return rank_sums_device(pred, Y_d, iid_d, cand_d, off_d, [5])[0].cpu().numpy()
 
     e2e = {}
     for name, flag in (('host_draw', False), ('device_draw', True)):
@@ -607,11 +642,12 @@ def projected_noise_eval(U, I, n_users, dev):
 EXTRA_LEGS = {'eval_noise_free': noise_free_eval, 'eval_projected_noise': projected_noise_eval}
 
 
-def extra_legs_subprocess(preset, n_users, timeout_s=420):
+def extra_legs_subprocess(preset, n_users, legs, timeout_s=420):
     """Run the legs that had not run on hardware when round 1's GPU budget ended in a CHILD process and return
     {leg: object or {'error': ...}}: a fault there must not cost the bench line of the paths that have."""
     cmd = [sys.executable, os.path.abspath(__file__), '--extra-legs-only', '--preset', preset, '--eval-users',
-           str(n_users)]
+           str(n_users), '--legs', legs]
+    legs_wanted = set(legs.split(','))
     out, err, rc = '', '', None
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
@@ -628,15 +664,28 @@ def extra_legs_subprocess(preset, n_users, timeout_s=420):
             except ValueError:
                 pass
     for name in EXTRA_LEGS:
-        legs.setdefault(name, {'error': 'rc=%s: %s' % (rc, err[-300:])})
+        if {'eval_noise_free': 'noise_free', 'eval_projected_noise': 'projected'}[name] in legs_wanted:
+            legs.setdefault(name, {'error': 'rc=%s: %s' % (rc, err[-300:])})
     return legs
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU arm: eager-PyTorch port of the reference path on the host cores (oracle/torch_port.py)
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """All host cores for the CPU arm, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except (AttributeError, OSError):
+        pass
+    torch.set_num_threads(n)
+    return n
+
+
 def cpu_arm(U, I, X_all, budget_s, steps=None, warmup=1, eval_rows=4096):
     from oracle import torch_port
+    host_cores = host_threads()
     threads = torch.get_num_threads()
     g = torch.Generator(device='cpu').manual_seed(SEED + 5)
     feat = torch.randn((I, F), generator=g) / (F ** 0.5)
@@ -671,96 +720,30 @@ def cpu_arm(U, I, X_all, budget_s, steps=None, warmup=1, eval_rows=4096):
         torch_port.evaluate_users(pred, uid, iid, Yl, 5)
         t1 = time.perf_counter()
     n_eval_users = len(set(uid.tolist()))
-    return {'train_samples_per_s': train_sps, 'train_steps': len(times), 'eval_users_per_s': n_eval_users / (t1 - t0),
-            'eval_users': n_eval_users, 'cores': threads}
+    return {'train_samples_per_s': train_sps, 'train_steps': len(times), 'warmup': warmup,
+            'eval_users_per_s': n_eval_users / (t1 - t0), 'eval_users': n_eval_users, 'cores': threads,
+            'host_cores': host_cores}
+
+
+CPU_ARM_NOTE = ('device math of the reference path only (src/models/DCCF.py:66-127 + BaseRunner.fit:175-188 as the same ATen '
+                'calls, oracle/torch_port.py, validated against reference fixtures): the reference is Python with hard-coded '
+                'CUDA and cannot travel to this box.  NOT included: the reference\'s host pipeline — the per-interaction Python '
+                'negative sampler (src/data_processor/DataProcessor.py:446-524) and the pandas ranking of '
+                'src/models/BaseModel.py:83-112 — which SURVEY.md §6 measured as the larger part of its wall time; the '
+                'reference end to end is therefore slower than this number')
 
 
 # ------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=10)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--preset', default='electronics', choices=sorted(PRESETS))
-    ap.add_argument('--eval-users', type=int, default=1024)
-    ap.add_argument('--cpu-budget', type=float, default=12.0, help='seconds of CPU work for the cpu_baseline sample')
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-extra-legs', action='store_true',
-                    help='skip eval_noise_free / eval_projected_noise (measured by a child process)')
-    ap.add_argument('--extra-legs-only', action='store_true', help='run only those legs, one JSON line each')
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
-    U, I = PRESETS[args.preset]
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    config = {'workload': 'DCCF Adam lr=1e-3 on synthetic %s-shape data: U=%d I=%d F=768 D=64, batch 128 (+128 sampled '
-                          'negatives), S=10 A=2 std=0.1 dropout=0.2 l2=1e-4; eval test_neg_n=1000, eval_batch 16384, '
-                          'ndcg/recall/precision@5' % (args.preset, U, I),
-              'preset': args.preset, 'users': U, 'items': I, 'batch_size': BATCH, 'eval_users_per_rank': args.eval_users,
-              'parallelism': 'dp%d' % world, 'l2_cache': 'flushed between timed iterations (256 MiB write)'}
-
-    if args.impl == 'reference':
-        if rank != 0:
-            return
-        X_all = synth_batches(64, U, I, SEED)
-        steps = args.steps if args.steps <= 50 else None
-        r = cpu_arm(U, I, X_all, budget_s=max(args.cpu_budget, 20.0), steps=steps, warmup=min(args.warmup, 3))
-        sample = '%d train steps of 128 samples; eval of %d users x 1001 candidates' % (r['train_steps'], r['eval_users'])
-        line = {'impl': 'reference', 'metric': 'train_samples_per_s', 'value': r['train_samples_per_s'],
-                'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': r['train_steps'], 'warmup': min(args.warmup, 3),
-                'ms_per_step': 1e3 * BATCH / r['train_samples_per_s'], 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
-                'cpu_baseline': {'value': r['train_samples_per_s'], 'unit': 'samples/s', 'cores': r['cores'],
-                                 'kind': 'port', 'sample': sample},
-                'e2e': {'value': r['train_samples_per_s'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0,
-                        'd2h_bytes_per_step': 0},
-                'eval': {'metric': 'eval_users_per_s', 'value': r['eval_users_per_s'], 'unit': 'users/s'},
-                'note': 'reference CPU path = eager-PyTorch port of src/models/DCCF.py + BaseRunner.fit '
-                        '(oracle/torch_port.py): the reference is Python and hard-codes CUDA, it cannot travel'}
-        print(json.dumps(line))
-        return
-
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if args.extra_legs_only:
-        for name, fn in EXTRA_LEGS.items():
-            try:
-                o = fn(U, I, args.eval_users, dev)
-            except Exception as exc:        # noqa: BLE001 — reported; a sticky CUDA error fails the next leg too
-                o = {'error': '%s: %s' % (type(exc).__name__, str(exc)[:300])}
-            print(json.dumps(dict(leg=name, **o)), flush=True)
-        return
-    if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: ONE JSON line
-        torch.distributed.init_process_group('nccl', device_id=dev)
-    from dccf_b200 import kernels
-    model = build_model(U, I, dev)
-    if world > 1:
-        model.enable_data_parallel()
-    flush = L2Flusher(dev)
-    X_all = synth_batches(args.warmup + args.steps, U, I, SEED + rank)
-    with ClockSampler(local_rank) as clocks:
-        tr = bench_train(model, X_all, args.steps, args.warmup, world, flush)
-        evl = bench_eval(model, args.eval_users, 3, world, rank, flush)
-    clk = clocks.summary()
-
-    hbm_peak, bf16_peak, peak_src = measured_peaks()
-    tf32_peak = bf16_peak / 2.0          # kind::tf32 runs at half the bf16 rate
-    ms_per_step = tr['total_ms'] / args.steps
-    value = world * BATCH * args.steps / (tr['total_ms'] / 1e3)
-    e2e_value = world * BATCH * args.steps / tr['e2e_s']
-    n_params = (U + I) * D + D * (D + F) + D
+# roofline objects
+# ------------------------------------------------------------------------------------------------
+def train_roofline(tr, U, I, hbm_peak, tf32_peak, peak_src):
+    """Roofline of the dominant kernel of the captured step + per-kernel table.  `achieved` / `frac` count ALGORITHMIC
+    work (SURVEY.md §8d: forward 2.349 MFLOP, backward 2.526 MFLOP per pair; 24 B per parameter for the sweep);
+    `achieved_issued` / `frac_issued` the three TF32 products the tensor cores execute per FP32 product."""
     pairs = 2 * BATCH
     n_rows = pairs * R
+    n_params = (U + I) * D + D * (D + F) + D
     if tr['kernels_us']:
-        # per-kernel roofline of the captured step.  Algorithmic work: forward 2.349 MFLOP and backward
-        # 2.526 MFLOP per pair; the two contractions are issued as 3 TF32 products each (error-compensated) on the
-        # tensor cores; the sweep streams 24 B per parameter.
         ku = tr['kernels_us']
         n_touched = pairs * (1 + Z)                      # upper bound of the rows the step touches
         work = {
@@ -781,8 +764,8 @@ def main():
                 o['gbs'] = w['mbytes'] / 1e3 / (k['us'] / 1e6) if k['us'] > 0 else 0.0
             if 'gflop' in w:
                 o['gflop'] = w['gflop']
-                o['fp32_equivalent_tflops'] = w['gflop'] / 1e3 / (k['us'] / 1e6)
-                o['tensor_tflops'] = w['tensor_gflop'] / 1e3 / (k['us'] / 1e6)
+                o['algorithmic_tflops'] = w['gflop'] / 1e3 / (k['us'] / 1e6)
+                o['issued_tf32_tflops'] = w['tensor_gflop'] / 1e3 / (k['us'] / 1e6)
             kernels_obj[name] = o
         for name, tb in NCU_TRAFFIC_BYTES.items():
             if name in kernels_obj:
@@ -790,16 +773,19 @@ def main():
         crit = [n_ for n_ in ('k_train_fwd_tc', 'k_train_mid', 'k_train_bwd_tc', 'k_adam_touched') if n_ in ku]
         dom = max(crit, key=lambda n_: ku[n_]['us'])
         d = kernels_obj[dom]
-        if 'tensor_tflops' in d:
-            roof = {'kernel': dom + ' (tcgen05 3xTF32)', 'bound': 'tensor', 'achieved': d['tensor_tflops'],
-                    'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': d['tensor_tflops'] / tf32_peak,
+        if 'algorithmic_tflops' in d:
+            roof = {'kernel': dom + ' (tcgen05 3xTF32)', 'bound': 'tensor', 'achieved': d['algorithmic_tflops'],
+                    'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': d['algorithmic_tflops'] / tf32_peak,
+                    'achieved_issued': d['issued_tf32_tflops'], 'frac_issued': d['issued_tf32_tflops'] / tf32_peak,
                     'traffic': NCU_TRAFFIC_BYTES.get(dom), 'traffic_source': NCU_TRAFFIC_SOURCE,
                     'peak_source': peak_src + ': bf16 burst / 2 for kind::tf32',
-                    'limiter': 'the operand tile is generated, not loaded: Philox4x32-10 + Box-Muller for 4.3 M normals '
-                               'per step in each of the two contractions, on 16 producer warps per SM (instruction '
-                               'latency, not the tensor pipe or HBM)',
-                    'fp32_equivalent': {'achieved': d['fp32_equivalent_tflops'], 'peak': FP32_PEAK_TFLOPS,
-                                        'unit': 'TFLOP/s', 'frac': d['fp32_equivalent_tflops'] / FP32_PEAK_TFLOPS}}
+                    'work_note': 'achieved / frac = algorithmic flops of the reference formulation (SURVEY.md §8d) per launch / '
+                                 'kernel time; *_issued = the 3 TF32 products per FP32 product actually executed',
+                    'limiter': 'the operand tile is generated, not loaded (Philox4x32-10 + Box-Muller, 4.3 M normals per step in '
+                               'each of the two contractions, 16 producer warps per SM): latency of the producer loop, not the '
+                               'tensor pipe or HBM',
+                    'fp32_simt': {'achieved': d['algorithmic_tflops'], 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+                                  'frac': d['algorithmic_tflops'] / FP32_PEAK_TFLOPS}}
         else:
             roof = {'kernel': dom, 'bound': 'hbm', 'achieved': d.get('gbs', 0.0), 'peak': hbm_peak, 'unit': 'GB/s',
                     'frac': d.get('gbs', 0.0) / hbm_peak, 'traffic': NCU_TRAFFIC_BYTES.get(dom),
@@ -811,83 +797,266 @@ def main():
                                          'note': 'l2 + clip + Adam over the untouched rows on a side stream, one small CTA per SM '
                                                  'beside the tensor-core kernels (128 threads; 256 under data parallelism); '
                                                  'off the critical path by design, so its rate is a floor, not a target'}
+        step_us = tr['timeline_step_us']
+        roof['whole_step'] = {'us': step_us, 'hbm_frac': 24.0 * n_params / 1e9 / (step_us / 1e6) / hbm_peak if step_us else None,
+                              'fp32_simt_frac': pairs * (FLOP_FWD_PAIR + FLOP_BWD_PAIR) / 1e12 / (step_us / 1e6) / FP32_PEAK_TFLOPS
+                              if step_us else None,
+                              'note': 'algorithmic bytes (24 B per parameter) and flops (forward + backward) of the whole step '
+                                      'over the step length by the same stamps'}
         roof['kernels_note'] = ('per-kernel %%globaltimer stamps inside extra replays of the captured step, L2 flushed '
-                                'before each measured step; step length by the same stamps: %.1f us' % tr['timeline_step_us'])
+                                'before each measured step; step length by the same stamps: %.1f us' % step_us)
         roof['kernels'] = kernels_obj
-    else:
-        stage = tr['stage_ms']                               # fwd, bwd, adam  (ms per step)
-        stages = {
-            'score_fwd': {'ms': float(stage[0]), 'gflop': pairs * FLOP_FWD_PAIR / 1e9, 'mbytes': pairs * BYTES_PAIR / 1e6},
-            'bpr_bwd': {'ms': float(stage[1]), 'gflop': pairs * FLOP_BWD_PAIR / 1e9,
-                        'mbytes': pairs * (BYTES_PAIR + 4 * D * (1 + Z)) / 1e6},
-            'adam_sweep': {'ms': float(stage[2]), 'gflop': 0.0, 'mbytes': 24.0 * n_params / 1e6},
-        }
-        for st in stages.values():
-            st['gbs'] = st['mbytes'] / 1e3 / (st['ms'] / 1e3) if st['ms'] > 0 else 0.0
-            st['tflops'] = st['gflop'] / 1e3 / (st['ms'] / 1e3) if st['ms'] > 0 else 0.0
-        dom = max(stages, key=lambda k: stages[k]['ms'])
-        roof = {'kernel': dom, 'bound': 'hbm', 'achieved': stages[dom]['gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': stages[dom]['gbs'] / hbm_peak, 'traffic': None, 'peak_source': peak_src,
-                'fp32_simt': {'achieved': stages[dom]['tflops'], 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s',
-                              'frac': stages[dom]['tflops'] / FP32_PEAK_TFLOPS},
-                'stages_note': 'per-stage CUDA events of the same step launched kernel by kernel (includes launch gaps; '
-                               'the timed value replays the step as one CUDA graph)',
-                'stages': stages}
+        return roof
+    stage = tr['stage_ms']                               # fwd, bwd, adam  (ms per step)
+    stages = {
+        'score_fwd': {'ms': float(stage[0]), 'gflop': pairs * FLOP_FWD_PAIR / 1e9, 'mbytes': pairs * BYTES_PAIR / 1e6},
+        'bpr_bwd': {'ms': float(stage[1]), 'gflop': pairs * FLOP_BWD_PAIR / 1e9,
+                    'mbytes': pairs * (BYTES_PAIR + 4 * D * (1 + Z)) / 1e6},
+        'adam_sweep': {'ms': float(stage[2]), 'gflop': 0.0, 'mbytes': 24.0 * n_params / 1e6},
+    }
+    for st in stages.values():
+        st['gbs'] = st['mbytes'] / 1e3 / (st['ms'] / 1e3) if st['ms'] > 0 else 0.0
+        st['tflops'] = st['gflop'] / 1e3 / (st['ms'] / 1e3) if st['ms'] > 0 else 0.0
+    dom = max(stages, key=lambda k: stages[k]['ms'])
+    return {'kernel': dom, 'bound': 'hbm', 'achieved': stages[dom]['gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
+            'frac': stages[dom]['gbs'] / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+            'fp32_simt': {'achieved': stages[dom]['tflops'], 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+                          'frac': stages[dom]['tflops'] / FP32_PEAK_TFLOPS},
+            'stages_note': 'per-stage CUDA events of the same step launched kernel by kernel (includes launch gaps; '
+                           'the timed value replays the step as one CUDA graph)',
+            'stages': stages}
+
+
+def eval_object(model, evl, n_users_total, world, hbm_peak, tf32_peak, peak_src):
     eval_pairs = evl['rows']
-    eval_users_s = world * args.eval_users / (evl['dev_ms'] / 1e3)
+    eval_users_s = n_users_total / (evl['dev_ms'] / 1e3)
     eval_tflops = eval_pairs * FLOP_FWD_PAIR / 1e12 / (evl['score_ms'] / 1e3)
     used_tc = bool(getattr(model, 'use_tensor_cores', False)) and eval_pairs * R >= model.tc_min_rows
     noise_tflop = 3 * eval_pairs * R * 2.0 * F * D / 1e12          # the three TF32 products actually issued
+    hbm = {'achieved': eval_pairs * BYTES_PAIR / 1e9 / (evl['score_ms'] / 1e3), 'peak': hbm_peak, 'unit': 'GB/s',
+           'frac': eval_pairs * BYTES_PAIR / 1e9 / (evl['score_ms'] / 1e3) / hbm_peak}
     if used_tc:
         eval_roof = {'kernel': 'k_row_scores_tc (tcgen05 3xTF32)', 'bound': 'tensor',
-                     'achieved': noise_tflop / (evl['score_ms'] / 1e3), 'peak': tf32_peak, 'unit': 'TFLOP/s',
-                     'frac': noise_tflop / (evl['score_ms'] / 1e3) / tf32_peak,
+                     'achieved': eval_tflops, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': eval_tflops / tf32_peak,
+                     'achieved_issued': noise_tflop / (evl['score_ms'] / 1e3),
+                     'frac_issued': noise_tflop / (evl['score_ms'] / 1e3) / tf32_peak,
                      'traffic': NCU_EVAL_TRAFFIC_BYTES if EVAL_BATCH == 16384 else None,
                      'traffic_source': NCU_EVAL_TRAFFIC_SOURCE,
                      'peak_source': peak_src + ': bf16 burst / 2 for kind::tf32',
+                     'work_note': 'achieved / frac = algorithmic FP32 flops of the reference formulation (2.349 MFLOP per pair) / '
+                                  'scoring time; *_issued = the 3 TF32 products per FP32 product actually executed',
                      'limiter': 'Gaussian noise generation (Philox4x32-10 + Box-Muller, 16.9 M normals per user) on '
                                 'the SIMT ALU/XU pipes, not the tensor pipe',
-                     'fp32_equivalent': {'achieved': eval_tflops, 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s',
-                                         'frac': eval_tflops / FP32_PEAK_TFLOPS,
-                                         'note': 'algorithmic FP32 flops of the reference formulation / time, against '
-                                                 'the FP32 SIMT peak a non-tensor-core kernel is bounded by'},
-                     'hbm': {'achieved': eval_pairs * BYTES_PAIR / 1e9 / (evl['score_ms'] / 1e3), 'peak': hbm_peak,
-                             'unit': 'GB/s', 'frac': eval_pairs * BYTES_PAIR / 1e9 / (evl['score_ms'] / 1e3) / hbm_peak}}
-    else:
-        eval_roof = {'kernel': 'k_row_scores', 'bound': 'hbm',
-                     'achieved': eval_pairs * BYTES_PAIR / 1e9 / (evl['score_ms'] / 1e3), 'peak': hbm_peak,
-                     'unit': 'GB/s', 'frac': eval_pairs * BYTES_PAIR / 1e9 / (evl['score_ms'] / 1e3) / hbm_peak,
-                     'traffic': None,
                      'fp32_simt': {'achieved': eval_tflops, 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s',
-                                   'frac': eval_tflops / FP32_PEAK_TFLOPS}}
-    eval_obj = {'metric': 'eval_users_per_s', 'value': eval_users_s, 'unit': 'users/s',
-                'users': world * args.eval_users, 'candidates_per_user': 1 + TEST_NEG_N,
-                'ms_per_batch': evl['score_ms'] / evl['n_batches'], 'rank_ms': evl['rank_ms'],
-                'e2e': {'value': world * args.eval_users / evl['e2e_s'], 'unit': 'users/s',
-                        'h2d_bytes': evl['h2d'], 'd2h_bytes': evl['d2h']},
-                'roofline': eval_roof,
-                'ndcg@5': evl['ndcg@5'], 'recall@5': evl['recall@5'], 'precision@5': evl['precision@5']}
+                                   'frac': eval_tflops / FP32_PEAK_TFLOPS,
+                                   'note': 'the same algorithmic flops against the FP32 SIMT peak a non-tensor-core kernel is '
+                                           'bounded by'},
+                     'hbm': hbm}
+    else:
+        eval_roof = dict(hbm, kernel='k_row_scores', bound='hbm', traffic=None,
+                         fp32_simt={'achieved': eval_tflops, 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+                                    'frac': eval_tflops / FP32_PEAK_TFLOPS})
+    rank_bytes = 8.0 * eval_pairs
+    return {'metric': 'eval_users_per_s', 'value': eval_users_s, 'unit': 'users/s',
+            'users': n_users_total, 'candidates_per_user': 1 + TEST_NEG_N,
+            'ms_per_batch': evl['score_ms'] / evl['n_batches'], 'rank_ms': evl['rank_ms'],
+            'ranker': {'kernel': 'k_rank_stream (one pass, all metrics, one launch)', 'ms': evl['rank_ms'], 'bound': 'hbm',
+                       'achieved': rank_bytes / 1e9 / (evl['rank_ms'] / 1e3), 'peak': hbm_peak, 'unit': 'GB/s',
+                       'frac': rank_bytes / 1e9 / (evl['rank_ms'] / 1e3) / hbm_peak,
+                       'note': 'algorithmic bytes = 8 B per candidate (score + label) of this rank; CUDA events around the '
+                               'launch, L2 flushed before it'},
+            'e2e': {'value': n_users_total / evl['e2e_s'], 'unit': 'users/s',
+                    'h2d_bytes': evl['h2d'], 'd2h_bytes': evl['d2h']},
+            'roofline': eval_roof,
+            'ndcg@5': evl['ndcg@5'], 'recall@5': evl['recall@5'], 'precision@5': evl['precision@5']}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--preset', default='electronics', choices=sorted(PRESETS))
+    ap.add_argument('--eval-users', type=int, default=1024)
+    ap.add_argument('--cpu-budget', type=float, default=12.0, help='seconds of CPU work for the cpu_baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra-legs', action='store_true',
+                    help='skip every leg beyond the headline train / eval pair (and the data-parallel parity check)')
+    ap.add_argument('--legs', default='all',
+                    help='comma list of: config3,config4,config5,eager,noise_free,projected (default all that apply)')
+    ap.add_argument('--extra-legs-only', action='store_true', help='run only the child-process legs, one JSON line each')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    U, I = PRESETS[args.preset]
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    legs = set(['config3', 'config4', 'config5', 'eager', 'noise_free', 'projected']) if args.legs == 'all' else \
+        set(x for x in args.legs.split(',') if x)
+    if args.no_extra_legs:
+        legs = set()
+
+    def workload(preset, U_, I_):
+        return {'workload': 'DCCF Adam lr=1e-3 on synthetic %s-shape data: U=%d I=%d F=768 D=64, batch 128 (+128 sampled '
+                            'negatives) per rank, S=10 A=2 std=0.1 dropout=0.2 l2=1e-4; eval test_neg_n=1000, eval_batch 16384, '
+                            'ndcg/recall/precision@5' % (preset, U_, I_),
+                'preset': preset, 'users': U_, 'items': I_, 'batch_size': BATCH, 'eval_users_per_rank': args.eval_users,
+                'parallelism': 'dp%d' % world, 'l2_cache': 'flushed between timed iterations (256 MiB write)'}
+
+    config = workload(args.preset, U, I)
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        X_all = synth_batches(64, U, I, SEED)
+        r = cpu_arm(U, I, X_all, budget_s=0.0, steps=args.steps, warmup=args.warmup)
+        sample = '%d train steps of 128 samples after %d warm-up steps; eval of %d users x 1001 candidates' \
+                 % (r['train_steps'], r['warmup'], r['eval_users'])
+        line = {'impl': 'reference', 'metric': 'train_samples_per_s', 'value': r['train_samples_per_s'],
+                'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': r['train_steps'], 'warmup': r['warmup'],
+                'ms_per_step': 1e3 * BATCH / r['train_samples_per_s'], 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': dict(config, parallelism='cpu'),
+                'cpu_baseline': {'value': r['train_samples_per_s'], 'unit': 'samples/s', 'cores': r['cores'],
+                                 'host_cores': r['host_cores'], 'kind': 'port', 'sample': sample, 'note': CPU_ARM_NOTE},
+                'e2e': {'value': r['train_samples_per_s'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0},
+                'eval': {'metric': 'eval_users_per_s', 'value': r['eval_users_per_s'], 'unit': 'users/s'},
+                'note': 'reference CPU path = eager-PyTorch port of src/models/DCCF.py + BaseRunner.fit '
+                        '(oracle/torch_port.py) on ONE process with all host cores whatever --gpus says (a CPU arm does not '
+                        'scale with the GPU count: only the N = 1 ratio is meaningful)'}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if args.extra_legs_only:
+        for name, fn in EXTRA_LEGS.items():
+            if {'eval_noise_free': 'noise_free', 'eval_projected_noise': 'projected'}[name] not in legs:
+                continue
+            try:
+                o = fn(U, I, args.eval_users, dev)
+            except Exception as exc:        # noqa: BLE001 — reported; a sticky CUDA error fails the next leg too
+                o = {'error': '%s: %s' % (type(exc).__name__, str(exc)[:300])}
+            print(json.dumps(dict(leg=name, **o)), flush=True)
+        return
+    if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: ONE JSON line
+        torch.distributed.init_process_group('nccl', device_id=dev)
+    from dccf_b200 import kernels  # noqa: F401  (fails loudly here when the library is missing)
+    from tools import bench_legs
+    peaks = measured_peaks()
+    hbm_peak, bf16_peak, peak_src = peaks
+    tf32_peak = bf16_peak / 2.0          # kind::tf32 runs at half the bf16 rate
+
+    # ---- data parallel: equality with the single-GPU step BEFORE any timing --------------------------------------
+    dp_parity = None
+    if world > 1:
+        dp_parity = bench_legs.dp_parity_check(world, rank, dev)
+        if not dp_parity['ok']:
+            if rank == 0:
+                print(json.dumps({'metric': 'train_samples_per_s', 'value': None, 'n_gpus': world, 'dp_parity_ok': False,
+                                  'dp_parity': dp_parity, 'error': 'data-parallel step differs from the single-GPU step'}))
+            torch.distributed.destroy_process_group()
+            sys.exit(3)
+
+    def train_eval(preset, steps, warmup, eval_users):
+        """The headline pair at one shape: (model, train result, eval result, clocks)."""
+        U_, I_ = PRESETS[preset]
+        model = build_model(U_, I_, dev)
+        if world > 1:
+            model.enable_data_parallel()
+        flush = L2Flusher(dev)
+        X_all = synth_batches(warmup + steps, U_, I_, SEED + rank)
+        with ClockSampler(local_rank) as clocks:
+            tr = bench_train(model, X_all, steps, warmup, world, flush)
+            evl = bench_eval(model, eval_users, 3, world, rank, flush)
+        return model, tr, evl, clocks.summary()
+
+    model, tr, evl, clk = train_eval(args.preset, args.steps, args.warmup, args.eval_users)
+    ms_per_step = tr['total_ms'] / args.steps
+    value = world * BATCH * args.steps / (tr['total_ms'] / 1e3)
+    e2e_value = world * BATCH * args.steps / tr['e2e_s']
     line = {'metric': 'train_samples_per_s', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': tr['h2d'],
-                    'd2h_bytes_per_step': tr['d2h']},
+                    'd2h_bytes_per_step': tr['d2h'],
+                    'timing': 'model.train_step per step from pinned host ids: staging + confounder draw on the torch CPU '
+                              'generator + one H2D copy + one CUDA-graph launch + D2H copy of the loss, every step; the host '
+                              'does not wait inside the loop (one synchronise ends the timed region); wall clock minus the '
+                              'device time of the L2 flushes between the steps (CUDA events around each flush)',
+                    'sync_every_step': {'value': world * BATCH / tr['e2e_sync_s_per_step'], 'unit': 'samples/s',
+                                        'note': 'same call, host blocked on loss.item() after every step (latency of one '
+                                                'step end to end, no overlap of host and device)'}},
             'back_to_back': {'ms_per_step': tr['b2b_ms'], 'value': world * BATCH / (tr['b2b_ms'] / 1e3), 'unit': 'samples/s',
                              'note': 'same steps without the L2 flush between them (parameters stay L2-resident), one '
                                      'CUDA-event pair around all of them'},
-            'gpu_launches': int(tr['launches']), 'clocks': clk, 'roofline': roof, 'eval': eval_obj,
+            'gpu_launches': int(tr['launches']), 'clocks': clk,
+            'roofline': train_roofline(tr, U, I, hbm_peak, tf32_peak, peak_src),
+            'eval': eval_object(model, evl, world * args.eval_users, world, hbm_peak, tf32_peak, peak_src),
             'last_loss': tr['last_loss']}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        X_cpu = synth_batches(32, U, I, SEED)
-        c = cpu_arm(U, I, X_cpu, budget_s=args.cpu_budget)
-        line['cpu_baseline'] = {'value': c['train_samples_per_s'], 'unit': 'samples/s', 'cores': c['cores'],
-                                'kind': 'port',
-                                'sample': '%d train steps of 128 samples (eager-PyTorch port of the reference path, '
-                                          'oracle/torch_port.py); eval sample %d users -> %.3f users/s'
-                                          % (c['train_steps'], c['eval_users'], c['eval_users_per_s']),
-                                'eval_users_per_s': c['eval_users_per_s']}
-    if rank == 0 and world == 1 and not args.no_extra_legs:
-        line.update(extra_legs_subprocess(args.preset, args.eval_users))
+    if world > 1:
+        dp_parity['replicas_identical_after_timed_steps'] = bench_legs.replica_checksum(model, world, dev)
+        line['dp_parity_ok'] = bool(dp_parity['ok'] and dp_parity['replicas_identical_after_timed_steps'])
+        line['dp_parity'] = dp_parity
+    del model
+    torch.cuda.empty_cache()
+
+    def guarded(name, fn):
+        """A leg must not cost the line: its failure is reported in its own object.  (All ranks run every leg.)"""
+        try:
+            line[name] = fn()
+        except Exception as exc:            # noqa: BLE001
+            line[name] = {'error': '%s: %s' % (type(exc).__name__, str(exc)[:300])}
+        torch.cuda.empty_cache()
+
+    if 'config3' in legs and args.preset != 'cds':
+        def config3():
+            steps3, warm3 = min(args.steps, 100), min(args.warmup, 5)
+            m3, tr3, ev3, _ = train_eval('cds', steps3, warm3, min(args.eval_users, 512))
+            U3, I3 = PRESETS['cds']
+            o = {'metric': 'train_samples_per_s', 'value': world * BATCH * steps3 / (tr3['total_ms'] / 1e3),
+                 'unit': 'samples/s', 'n_gpus': world, 'steps': steps3, 'warmup': warm3,
+                 'ms_per_step': tr3['total_ms'] / steps3, 'scaling': 'weak', 'config': workload('cds', U3, I3),
+                 'e2e': {'value': world * BATCH * steps3 / tr3['e2e_s'], 'unit': 'samples/s'},
+                 'back_to_back_ms_per_step': tr3['b2b_ms'],
+                 'eval': {'value': world * min(args.eval_users, 512) / (ev3['dev_ms'] / 1e3), 'unit': 'users/s',
+                          'ms_per_batch': ev3['score_ms'] / ev3['n_batches'], 'rank_ms': ev3['rank_ms']},
+                 'last_loss': tr3['last_loss']}
+            if world > 1:
+                o['replicas_identical'] = bench_legs.replica_checksum(m3, world, dev)
+            return o
+        guarded('config3_cds', config3)
+    if 'config4' in legs:
+        guarded('config4_full_catalogue', lambda: bench_legs.full_catalogue_leg(world, rank, dev, peaks))
+    if 'config5' in legs:
+        guarded('config5_scaled', lambda: bench_legs.scaled_leg(world, rank, dev, peaks))
+    if rank == 0 and world == 1:
+        if 'eager' in legs:
+            cfg = {'D': D, 'F': F, 'S': S, 'A': A, 'std': STD, 'seed': SEED, 'lr': LR, 'l2': L2, 'batch': BATCH,
+                   'dropout': DROPOUT, 'eval_batch': EVAL_BATCH, 'test_neg_n': TEST_NEG_N}
+            guarded('gpu_eager_reference', lambda: bench_legs.gpu_eager_reference(U, I, dev, cfg))
+            g = line.get('gpu_eager_reference', {})
+            if 'train_samples_per_s' in g:
+                g['ours_over_eager'] = {'train': value / g['train_samples_per_s'],
+                                        'eval_scoring': line['eval']['value'] / g['eval_users_per_s']}
+        if not args.no_cpu_baseline:
+            X_cpu = synth_batches(32, U, I, SEED)
+            c = cpu_arm(U, I, X_cpu, budget_s=args.cpu_budget)
+            line['cpu_baseline'] = {'value': c['train_samples_per_s'], 'unit': 'samples/s', 'cores': c['cores'],
+                                    'host_cores': c['host_cores'], 'kind': 'port',
+                                    'sample': '%d train steps of 128 samples (eager-PyTorch port of the reference path, '
+                                              'oracle/torch_port.py); eval sample %d users -> %.3f users/s'
+                                              % (c['train_steps'], c['eval_users'], c['eval_users_per_s']),
+                                    'eval_users_per_s': c['eval_users_per_s'], 'note': CPU_ARM_NOTE}
+        child = [n for n in ('noise_free', 'projected') if n in legs]
+        if child:
+            line.update(extra_legs_subprocess(args.preset, args.eval_users, ','.join(child)))
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

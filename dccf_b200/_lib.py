@@ -12,7 +12,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 _VARIANT = os.environ.get('DCCF_LIB_VARIANT', '')          # A/B build variants, see dccf_b200/build.py
 LIB_PATH = os.path.join(HERE, 'libdccf_b200%s.so' % (('_' + _VARIANT) if _VARIANT else ''))
-ABI_VERSION = 30
+ABI_VERSION = 31
 DIM = 64
 
 
@@ -51,6 +51,25 @@ class AdamTable(ctypes.Structure):
                 ('rec_keys', ctypes.c_void_p), ('rec_grads', ctypes.c_void_p), ('n_seg', ctypes.c_int32),
                 ('_pad', ctypes.c_int32), ('seg_len', ctypes.c_int64), ('key_seg_stride', ctypes.c_int64),
                 ('grad_seg_stride', ctypes.c_int64), ('head', ctypes.c_void_p), ('next', ctypes.c_void_p)]
+
+
+class DpChannel(ctypes.Structure):
+    _fields_ = [('peer_bases', ctypes.c_uint64 * 8), ('flag_off', ctypes.c_int64), ('epoch_dev', ctypes.c_void_p)]
+
+
+class DpSync(ctypes.Structure):
+    _fields_ = [('world', ctypes.c_int32), ('rank', ctypes.c_int32), ('n_wait', ctypes.c_int32), ('n_done', ctypes.c_int32),
+                ('wait', DpChannel * 3), ('done', DpChannel * 3), ('loss_parts', ctypes.c_void_p),
+                ('loss_stride', ctypes.c_int64), ('n_loss', ctypes.c_int32), ('_pad', ctypes.c_int32),
+                ('loss_out', ctypes.c_void_p)]
+
+
+class LinkExtra(ctypes.Structure):
+    _fields_ = [('epoch_ptrs_dev', ctypes.c_void_p), ('cursor_dev', ctypes.c_void_p), ('X_out', ctypes.c_void_p),
+                ('sample_item_out', ctypes.c_void_p), ('stage_counter', ctypes.c_void_p),
+                ('pf_user', ctypes.c_void_p * 3), ('pf_item', ctypes.c_void_p * 3), ('pf_feat', ctypes.c_void_p),
+                ('pf_dense', ctypes.c_void_p * 4), ('pf_dense_bytes', ctypes.c_int64 * 4),
+                ('sync', ctypes.POINTER(DpSync))]
 
 
 class AdamTensor(ctypes.Structure):
@@ -102,12 +121,13 @@ _SIGNATURES = {
     'dccf_adam_step': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(AdamTensor),
                                       ctypes.c_int32, ctypes.POINTER(Adam), _P]),
     'dccf_adam_link_ids': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
-                                          ctypes.c_int32, _P, _P, _P, _P, ctypes.POINTER(Expo), _P, _P, _P, _P, _P]),
+                                          ctypes.c_int32, _P, _P, _P, _P, ctypes.POINTER(Expo), _P, _P, _P, _P,
+                                          ctypes.POINTER(LinkExtra), _P]),
     'dccf_adam_untouched': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(Adam), ctypes.c_int32,
                                            _P]),
     'dccf_adam_touched': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(AdamTensor),
                                          ctypes.c_int32, ctypes.POINTER(Adam), ctypes.c_int32, _P, ctypes.c_int32,
-                                         ctypes.c_int32, _P, _P, _P, _P]),
+                                         ctypes.c_int32, _P, _P, _P, ctypes.POINTER(DpSync), _P]),
     'dccf_train_prep_w_image': (ctypes.c_int, [_P, ctypes.c_int32, _P, _P]),
     'dccf_debug_timeline_train': (ctypes.c_int, [_P]),
     'dccf_debug_timeline_adam': (ctypes.c_int, [_P]),

@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "backdoor.cuh"
+#include "dp_sync.cuh"
 
 namespace dccf {
 
@@ -371,43 +372,117 @@ struct LinkIdsArgs {
     int32_t* head_i;
     int32_t* next_i;
     int32_t link_blocks;     // blocks [0, link_blocks) link; the rest evaluate the exposure softmax (warp per pair)
+    int32_t expo_blocks;     // then expo_blocks blocks of exposure softmax, then the dense-range prefetch blocks
     dccf_expo ex;
     float* expo_e;           // [P, Z]
     float* expo_den;         // [P]
+    dccf_link_extra extra;   // staging + L2 prefetch (all-null: none)
+    int32_t feat_dim;
+    DpSync sync;             // data-parallel global link: wait for the ids, hand the buffer back (n_wait = n_done = 0: none)
 };
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// one 256-byte table row of each of up to three tensors (parameter + its two Adam moments)
+__device__ __forceinline__ void prefetch_rows(const float* const (&t)[3], int32_t row) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (t[k] != nullptr) {
+            const char* p = reinterpret_cast<const char*>(t[k] + (size_t)row * D);
+            prefetch_l2(p);
+            prefetch_l2(p + 128);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256) k_link_ids(const LinkIdsArgs a) {
     tl_begin(0);
     tl_end(0);      // (short single wave: start and end are indistinguishable at the timer's resolution)
-    if ((int)blockIdx.x >= a.link_blocks) {
-        // exposure softmax of every local pair: depends on the ids only, so it is taken off the critical path here
-        const int64_t p = (int64_t)((int)blockIdx.x - a.link_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        if (p >= a.n_pairs) return;   // warp-uniform
-        backdoor_weights(a.ex, a.X_local, a.si_local, p, threadIdx.x & 31, a.n_users, a.user_base, a.n_items, a.S, a.A,
-                         a.expo_e + p * (a.S + 1), a.expo_den + p, nullptr);
-        return;
+    __shared__ int64_t s_batch;
+    const bool staged = a.extra.epoch_ptrs_dev != nullptr;
+    const int64_t *X = a.X, *si = a.sample_item, *X_local = a.X_local, *si_local = a.si_local;
+    if (staged) {
+        // the batch is number *cursor of a device-resident epoch (what k_stage_batch does in a launch of its own)
+        if (threadIdx.x == 0) s_batch = *a.extra.cursor_dev;
+        __syncthreads();
+        X = reinterpret_cast<const int64_t*>(a.extra.epoch_ptrs_dev[0]) + s_batch * a.n_pairs * 2;
+        si = reinterpret_cast<const int64_t*>(a.extra.epoch_ptrs_dev[1]) + s_batch * a.n_pairs * a.S;
+        X_local = X;
+        si_local = si;
     }
-    // record index (the one the gradient records will have): segment-major, as the Adam tables number them
-    const int Z = a.S + 1;
-    const int64_t per_seg = a.n_pairs * (Z + 1);
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= per_seg * a.n_seg) return;
-    const int seg = (int)(i / per_seg);
-    const int64_t il = i - (int64_t)seg * per_seg;
-    const int64_t p = il / (Z + 1);
-    const int slot = (int)(il - p * (Z + 1));   // 0 = the user record of pair p, 1 + z = its item record of slot z
-    const int64_t* X = a.X + (int64_t)seg * a.seg_stride;
-    const int64_t* si = a.sample_item + (int64_t)seg * a.seg_stride;
-    if (slot == 0) {
-        if (a.user_seg >= 0 && seg != a.user_seg) return;
-        const int32_t u = checked_id(X[2 * p] - a.user_base, a.n_users, nullptr);
-        const int32_t r = (int32_t)((a.user_seg >= 0 ? 0 : (int64_t)seg * a.n_pairs) + p);
-        a.next_u[r] = atomicExch(&a.head_u[u], r);
+    dp_wait_inline(a.sync);      // (data parallel) the peers' ids have arrived
+    const int bid = (int)blockIdx.x;
+    if (bid >= a.link_blocks + a.expo_blocks) {
+        // dense ranges (W, its moments, its operand images) into L2, one 128-byte line per thread and trip
+        const int64_t t0 = (int64_t)(bid - a.link_blocks - a.expo_blocks) * blockDim.x + threadIdx.x;
+        const int64_t nt = (int64_t)(gridDim.x - a.link_blocks - a.expo_blocks) * blockDim.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const char* base = reinterpret_cast<const char*>(a.extra.pf_dense[k]);
+            if (base == nullptr) continue;
+            for (int64_t off = t0 * 128; off < a.extra.pf_dense_bytes[k]; off += nt * 128) prefetch_l2(base + off);
+        }
+    } else if (bid >= a.link_blocks) {
+        // exposure softmax of every local pair: depends on the ids only, so it is taken off the critical path here
+        const int64_t p = (int64_t)(bid - a.link_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        if (p < a.n_pairs)   // warp-uniform
+            backdoor_weights(a.ex, X_local, si_local, p, threadIdx.x & 31, a.n_users, a.user_base, a.n_items, a.S, a.A,
+                             a.expo_e + p * (a.S + 1), a.expo_den + p, nullptr);
     } else {
-        const int z = slot - 1;
-        const int32_t it = checked_id(slot_item(X, si, p, z, a.S), a.n_items, nullptr);
-        const int32_t r = (int32_t)(((int64_t)seg * a.n_pairs + p) * Z + z);
-        a.next_i[r] = atomicExch(&a.head_i[it], r);
+        // record index (the one the gradient records will have): segment-major, as the Adam tables number them
+        const int Z = a.S + 1;
+        const int64_t per_seg = a.n_pairs * (Z + 1);
+        const int64_t i = (int64_t)bid * blockDim.x + threadIdx.x;
+        if (i < per_seg * a.n_seg) {
+            const int seg = (int)(i / per_seg);
+            const int64_t il = i - (int64_t)seg * per_seg;
+            const int64_t p = il / (Z + 1);
+            const int slot = (int)(il - p * (Z + 1));   // 0 = the user record of pair p, 1 + z = its item record of slot z
+            const int64_t* Xs = X + (int64_t)seg * a.seg_stride;
+            const int64_t* sis = si + (int64_t)seg * a.seg_stride;
+            if (slot == 0) {
+                const int64_t uid = Xs[2 * p];
+                if (staged) a.extra.X_out[2 * p] = uid;
+                if (!(a.user_seg >= 0 && seg != a.user_seg)) {
+                    const int32_t u = checked_id(uid - a.user_base, a.n_users, nullptr);
+                    const int32_t r = (int32_t)((a.user_seg >= 0 ? 0 : (int64_t)seg * a.n_pairs) + p);
+                    a.next_u[r] = atomicExch(&a.head_u[u], r);
+                    prefetch_rows(a.extra.pf_user, u);
+                }
+            } else {
+                const int z = slot - 1;
+                const int64_t id = slot_item(Xs, sis, p, z, a.S);
+                if (staged) {
+                    if (z == 0) a.extra.X_out[2 * p + 1] = id;
+                    else a.extra.sample_item_out[p * a.S + (z - 1)] = id;
+                }
+                const int32_t it = checked_id(id, a.n_items, nullptr);
+                const int32_t r = (int32_t)(((int64_t)seg * a.n_pairs + p) * Z + z);
+                a.next_i[r] = atomicExch(&a.head_i[it], r);
+                prefetch_rows(a.extra.pf_item, it);
+            }
+            if (a.extra.pf_feat != nullptr && a.n_seg == 1) {
+                // the true item's feature row (feat_dim * 4 bytes), its 128-byte lines shared out over the pair's Z + 1
+                // threads (one GPU only: under data parallelism the other ranks' pairs are not multiplied here)
+                const int32_t fi = checked_id(Xs[2 * p + 1], a.n_items, nullptr);
+                const char* row = reinterpret_cast<const char*>(a.extra.pf_feat + (size_t)fi * a.feat_dim);
+                for (int off = slot * 128; off < a.feat_dim * 4; off += (Z + 1) * 128) prefetch_l2(row + off);
+            }
+        }
+    }
+    if (staged || a.sync.n_done > 0) {
+        // the last CTA to finish moves the cursor (every CTA has read it above) / hands the id buffer back to the peers
+        __shared__ int s_last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = (atomicAdd(a.extra.stage_counter, 1) == (int32_t)gridDim.x - 1) ? 1 : 0;
+            if (s_last) {
+                if (staged) *a.extra.cursor_dev = s_batch + 1;
+                *a.extra.stage_counter = 0;
+            }
+        }
+        __syncthreads();
+        if (s_last && a.sync.n_done > 0) dp_done_inline(a.sync);
     }
 }
 
@@ -468,23 +543,30 @@ struct WImageArgs {
     uint64_t* offset_dev;
 };
 
-__device__ __forceinline__ void touched_cta_done(const WImageArgs& wi) {
+__device__ __forceinline__ void touched_cta_done(const WImageArgs& wi, const DpSync& sync) {
+    __shared__ int s_last;
     __syncthreads();
     tl_end(5);
     if (wi.cta_counter == nullptr) return;                       // every thread of this CTA has read the counters it needs and stored its rows
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(wi.cta_counter, 1) == (int32_t)gridDim.x - 1) {
+        s_last = (atomicAdd(wi.cta_counter, 1) == (int32_t)gridDim.x - 1) ? 1 : 0;
+        if (s_last) {
             if (wi.step_dev) wi.step_dev[0] += 1;
             if (wi.offset_dev) wi.offset_dev[0] += 1;
             *wi.cta_counter = 0;
         }
     }
+    if (sync.n_done > 0 || sync.loss_out != nullptr) {           // (kernel-uniform)
+        __syncthreads();
+        if (s_last) dp_done_inline(sync);
+    }
 }
 
-__global__ void __launch_bounds__(256) k_adam_touched(const AdamAllArgs a, const WImageArgs wi) {
+__global__ void __launch_bounds__(256) k_adam_touched(const AdamAllArgs a, const WImageArgs wi, const DpSync sync) {
     __shared__ int32_t list_s[16][2][ADAM_LIST_CAP];
     tl_begin(5);
+    dp_wait_inline(sync);        // (data parallel) every rank's gradient records and dW / db / loss have arrived
     const AdamScalars s = resolve_adam(a.hp);
     const int bid = (int)blockIdx.x;
     for (int i = 0; i < a.n_tables; ++i) {
@@ -509,7 +591,7 @@ __global__ void __launch_bounds__(256) k_adam_touched(const AdamAllArgs a, const
             adam_elem(p.z, m.z, q.z, g.z, s); adam_elem(p.w, m.w, q.w, g.w, s);
             st4(t.table + o, p); st4(t.m + o, m); st4(t.v + o, q);
         }
-        touched_cta_done(wi);
+        touched_cta_done(wi, sync);
         return;
     }
     for (int i = 0; i < a.n_dense; ++i) {
@@ -544,7 +626,7 @@ __global__ void __launch_bounds__(256) k_adam_touched(const AdamAllArgs a, const
                 base[2048 + off] = __fsub_rn(p, hi);
             }
         }
-        touched_cta_done(wi);
+        touched_cta_done(wi, sync);
         return;
     }
 }
@@ -595,6 +677,33 @@ __global__ void __launch_bounds__(1024) k_stage_batch(const uint64_t* __restrict
     }
     __syncthreads();
     if (threadIdx.x == 0) *cursor = b + 1;
+}
+
+static int marshal_sync(const char* who, const dccf_dp_sync* in, DpSync* out) {
+    out->world = 1; out->rank = 0; out->n_wait = 0; out->n_done = 0;
+    out->loss_parts = nullptr; out->loss_stride = 0; out->n_loss = 0; out->loss_out = nullptr;
+    if (in == nullptr) return DCCF_OK;
+    DCCF_CHECK_ARG(in->world >= 1 && in->world <= DP_MAX_WORLD && in->rank >= 0 && in->rank < in->world,
+                   "%s: sync: world %d / rank %d outside [1,%d]", who, in->world, in->rank, DP_MAX_WORLD);
+    DCCF_CHECK_ARG(in->n_wait >= 0 && in->n_wait <= 3 && in->n_done >= 0 && in->n_done <= 3, "%s: sync: at most 3 channels", who);
+    DCCF_CHECK_ARG(in->loss_out == nullptr || (in->loss_parts != nullptr && in->n_loss >= 1), "%s: sync: loss_out needs loss_parts", who);
+    out->world = in->world; out->rank = in->rank; out->n_wait = in->n_wait; out->n_done = in->n_done;
+    for (int k = 0; k < 3; ++k) {
+        const dccf_dp_channel* src[2] = {&in->wait[k], &in->done[k]};
+        DpChannel* dst[2] = {&out->wait[k], &out->done[k]};
+        const int used[2] = {k < in->n_wait, k < in->n_done};
+        for (int w = 0; w < 2; ++w) {
+            for (int p = 0; p < DP_MAX_WORLD; ++p) dst[w]->base[p] = (used[w] && p < in->world) ? reinterpret_cast<float*>(src[w]->peer_bases[p]) : nullptr;
+            dst[w]->flag_off = used[w] ? src[w]->flag_off : 0;
+            dst[w]->epoch_dev = used[w] ? src[w]->epoch_dev : nullptr;
+            if (used[w]) {
+                DCCF_CHECK_ARG(src[w]->epoch_dev != nullptr, "%s: sync: channel %d has no epoch counter", who, k);
+                for (int p = 0; p < in->world; ++p) DCCF_CHECK_ARG(src[w]->peer_bases[p] != 0, "%s: sync: channel %d peer %d is null", who, k, p);
+            }
+        }
+    }
+    out->loss_parts = in->loss_parts; out->loss_stride = in->loss_stride; out->n_loss = in->n_loss; out->loss_out = in->loss_out;
+    return DCCF_OK;
 }
 
 static int check_hp(const dccf_adam* hp, AdamHost* out, const char* who) {
@@ -704,7 +813,7 @@ static int marshal_adam(const char* who, const dccf_adam_table* tables, int32_t 
     int64_t total_rows = 0;
     for (int i = 0; i < n_tables; ++i) total_rows += tables[i].n_rows > 0 ? tables[i].n_rows : 0;
     int32_t blocks = 0, link_blocks = 0;
-    const int64_t budget = (mode == 1) ? 148 : 148 * 8;   // CTAs for the table sweeps, shared in proportion to the row counts
+    const int64_t budget = (mode == 1) ? 148 : 148 * 8;   // CTAs for the table sweeps, shared in proportion to the row counts (mode 3: the wide untouched-row sweep)
     for (int i = 0; i < n_tables; ++i) {
         const dccf_adam_table& t = tables[i];
         DCCF_CHECK_ARG(t.table && t.m && t.v && t.head, "%s: table %d has a null buffer", who, i);
@@ -778,13 +887,17 @@ extern "C" int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const
                                   int32_t n_seg, int64_t seg_stride, int32_t user_seg, int32_t* head_user,
                                   int32_t* next_user, int32_t* head_item, int32_t* next_item, const dccf_expo* expo,
                                   const int64_t* X_local, const int64_t* sample_item_local, float* expo_e,
-                                  float* expo_den, void* stream_) {
-    DCCF_CHECK_ARG(dims && X && head_user && next_user && head_item && next_item, "dccf_adam_link_ids: null argument");
-    DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item, "dccf_adam_link_ids: sample_item is null");
+                                  float* expo_den, const dccf_link_extra* extra, void* stream_) {
+    const bool staged = extra != nullptr && extra->epoch_ptrs_dev != nullptr;
+    DCCF_CHECK_ARG(dims && (X || staged) && head_user && next_user && head_item && next_item, "dccf_adam_link_ids: null argument");
+    DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item || staged, "dccf_adam_link_ids: sample_item is null");
     DCCF_CHECK_ARG(n_seg >= 0 && (n_seg <= 1 || seg_stride > 0) && (n_seg == 0 || user_seg < n_seg), "dccf_adam_link_ids: bad segment layout");
     DCCF_CHECK_ARG(n_seg > 0 || expo != nullptr, "dccf_adam_link_ids: nothing to do (n_seg == 0 and no exposure source)");
     DCCF_CHECK_ARG(n_pairs * n_seg * (dims->n_samples + 1) < ((int64_t)1 << 31), "dccf_adam_link_ids: too many records");
     DCCF_CHECK_ARG(expo == nullptr || (expo_e && expo_den), "dccf_adam_link_ids: expo needs expo_e and expo_den");
+    DCCF_CHECK_ARG(!staged || (n_seg == 1 && extra->cursor_dev && extra->X_out && extra->stage_counter &&
+                               (dims->n_samples == 0 || extra->sample_item_out)),
+                   "dccf_adam_link_ids: staging needs n_seg == 1, cursor, output buffers and the CTA counter");
     if (n_pairs <= 0) return DCCF_OK;
     LinkIdsArgs a;
     a.X = X; a.sample_item = sample_item; a.n_pairs = n_pairs; a.S = dims->n_samples; a.A = dims->n_attr;
@@ -792,15 +905,36 @@ extern "C" int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const
     a.n_seg = n_seg; a.seg_stride = seg_stride; a.user_seg = user_seg;
     a.user_base = dims->user_base; a.n_users = dims->n_users; a.n_items = dims->n_items;
     a.head_u = head_user; a.next_u = next_user; a.head_i = head_item; a.next_i = next_item;
+    a.feat_dim = dims->feat_dim;
+    if (extra != nullptr) {
+        a.extra = *extra;
+    } else {
+        a.extra.epoch_ptrs_dev = nullptr; a.extra.cursor_dev = nullptr; a.extra.X_out = nullptr;
+        a.extra.sample_item_out = nullptr; a.extra.stage_counter = nullptr; a.extra.pf_feat = nullptr; a.extra.sync = nullptr;
+        for (int k = 0; k < 3; ++k) { a.extra.pf_user[k] = nullptr; a.extra.pf_item[k] = nullptr; }
+        for (int k = 0; k < 4; ++k) { a.extra.pf_dense[k] = nullptr; a.extra.pf_dense_bytes[k] = 0; }
+    }
+    int rc_sync = marshal_sync("dccf_adam_link_ids", extra != nullptr ? extra->sync : nullptr, &a.sync);
+    if (rc_sync != DCCF_OK) return rc_sync;
+    DCCF_CHECK_ARG(a.sync.n_done == 0 || a.extra.stage_counter != nullptr, "dccf_adam_link_ids: sync needs stage_counter (the CTA counter)");
+    a.extra.sync = nullptr;
     const int64_t n = n_pairs * n_seg * (dims->n_samples + 2);
     a.link_blocks = (int32_t)((n + 255) / 256);
     int64_t blocks = a.link_blocks;
     a.expo_e = expo_e; a.expo_den = expo_den;
+    a.expo_blocks = 0;
     if (expo != nullptr) {
         a.ex = *expo;
-        blocks += (n_pairs + 7) / 8;
+        a.expo_blocks = (int32_t)((n_pairs + 7) / 8);
+        blocks += a.expo_blocks;
     } else {
         a.ex.mode = 0; a.ex.dense = nullptr;
+    }
+    int64_t dense_bytes = 0;
+    for (int k = 0; k < 4; ++k) dense_bytes += a.extra.pf_dense[k] != nullptr ? a.extra.pf_dense_bytes[k] : 0;
+    if (dense_bytes > 0) {
+        int64_t pf = (dense_bytes / 128 + 255) / 256;
+        blocks += pf > 16 ? 16 : (pf < 1 ? 1 : pf);
     }
     k_link_ids<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(a);
     DCCF_CHECK_LAUNCH("k_link_ids");
@@ -818,8 +952,17 @@ extern "C" int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tabl
         local[i] = tables[i];
         local[i].n_seg = 0; local[i].seg_len = 0;
     }
-    int rc = marshal_adam("dccf_adam_untouched", local, n_tables, nullptr, 0, hp, 1, a, &blocks, &link_blocks);
+    // threads_per_cta < 0: WIDE sweep — the tables are so large (scaled configuration: 10^7 user rows) that the sweep,
+    // not the forward / backward, bounds the step: full occupancy (8 CTAs of 256 threads per SM, no shared-memory
+    // limiter) instead of one small CTA per SM hidden beside the tensor-core kernels.
+    const bool wide = threads_per_cta < 0;
+    int rc = marshal_adam("dccf_adam_untouched", local, n_tables, nullptr, 0, hp, wide ? 3 : 1, a, &blocks, &link_blocks);
     if (rc != DCCF_OK) return rc;
+    if (blocks > 0 && wide) {
+        k_adam_untouched<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(a);
+        DCCF_CHECK_LAUNCH("k_adam_untouched");
+        return DCCF_OK;
+    }
     if (blocks > 0) {
         // Occupancy limiter: the sweep runs beside the tensor-core kernels of the forward / backward (96 KB of shared
         // memory, ~48 K registers per CTA).  Two sweep CTAs on one SM would leave no room for such a CTA and push it
@@ -854,7 +997,7 @@ extern "C" int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tabl
 extern "C" int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
                                  int32_t n_dense, const dccf_adam* hp, int32_t already_linked, float* w_image,
                                  int32_t w_image_tensor, int32_t w_image_K, int32_t* cta_counter, int32_t* advance_step_dev,
-                                 uint64_t* advance_offset_dev, void* stream_) {
+                                 uint64_t* advance_offset_dev, const dccf_dp_sync* sync, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     AdamAllArgs a;
     int32_t blocks = 0, link_blocks = 0;
@@ -868,12 +1011,16 @@ extern "C" int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables
     wi.cta_counter = cta_counter; wi.step_dev = advance_step_dev; wi.offset_dev = advance_offset_dev;
     DCCF_CHECK_ARG(cta_counter != nullptr || (advance_step_dev == nullptr && advance_offset_dev == nullptr),
                    "dccf_adam_touched: advancing the counters needs cta_counter");
+    DpSync ds;
+    rc = marshal_sync("dccf_adam_touched", sync, &ds);
+    if (rc != DCCF_OK) return rc;
+    DCCF_CHECK_ARG((ds.n_done == 0 && ds.loss_out == nullptr) || cta_counter != nullptr, "dccf_adam_touched: sync needs cta_counter");
     if (link_blocks > 0 && !already_linked) {
         k_link_all<<<(unsigned)link_blocks, 256, 0, stream>>>(a);
         DCCF_CHECK_LAUNCH("k_link_all");
     }
     if (blocks > 0) {
-        k_adam_touched<<<(unsigned)blocks, 256, 0, stream>>>(a, wi);
+        k_adam_touched<<<(unsigned)blocks, 256, 0, stream>>>(a, wi, ds);
         DCCF_CHECK_LAUNCH("k_adam_touched");
     }
     return DCCF_OK;

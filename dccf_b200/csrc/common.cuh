@@ -160,7 +160,10 @@ __device__ __forceinline__ float4 dropout_quad(const RngKey& key, uint32_t row, 
 // kernel records the earliest start / latest end of its kernel in nanoseconds of %globaltimer:
 // slot s -> {min start, max end}.  A null pointer (the default) costs one uniform load per CTA.
 // ------------------------------------------------------------------------------------------
-static __device__ unsigned long long* g_timeline = nullptr;
+// (__constant__, not __device__: the pointer is read by thread 0 of EVERY CTA before the CTA's first barrier and again
+// before it exits — as a global-memory word it cost a dependent L2 / DRAM round trip at both ends of every kernel of the
+// step (ncu: 4-7 % of the stall samples of the training kernels); the constant cache serves it in a few cycles)
+static __constant__ unsigned long long* g_timeline = nullptr;
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -11,31 +11,13 @@
 //   k_dp_done : tell every peer this rank is done reading, advance the step counter
 // No NCCL call and no host involvement: the whole step, exchange included, is capturable in one CUDA graph.
 #include "common.cuh"
+#include "dp_sync.cuh"
 
 namespace dccf {
 
-constexpr int DP_MAX_WORLD = 8;
 struct DpPeers {
     float* base[DP_MAX_WORLD];
 };
-
-__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
-    int32_t v;
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-// Spin until *p >= want.  A peer that died (or never reaches this step) must not leave this GPU spinning for ever:
-// after 60 s — four orders of magnitude beyond any legitimate wait, start-up skew included — the kernel traps, the
-// process sees a CUDA error and the job fails loudly instead of hanging the box.
-__device__ __forceinline__ void spin_until(const int32_t* p, int32_t want) {
-    const unsigned long long t0 = global_ns();
-    while (ld_acquire_sys(p) < want) {
-        if (global_ns() - t0 > 60ull * 1000000000ull) __trap();
-    }
-}
-__device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 // Up to two ranges of the segment are not copied from `send` but summed on the fly from row-split partial buffers
 // (the dW / db partials of the backward, ascending split order — the fold dccf_sum_parts would do in two more launches).
@@ -93,13 +75,13 @@ __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send,
     // one system-scope fence per CTA, by the thread that publishes the CTA's arrival, after the CTA barrier has
     // ordered every thread's stores before it (a fence in each of the 13 K threads made the push take ~17 us)
     __syncthreads();
-#ifdef DCCF_DP_PARALLEL_FLAGS
-    // Build variant (round-2 experiment, python -m dccf_b200.build with DCCF_BUILD_DEFS=-DDCCF_DP_PARALLEL_FLAGS): the
-    // last CTA publishes the arrival to the peers with one release store per LANE instead of `world` release stores in
-    // sequence by one thread — each st.release.sys waits for the NVLink round trip of what precedes it, and eight of
-    // them back to back are the likely bulk of the ~14 us a push costs whatever its size.  Ordering: every CTA's data
-    // stores -> its barrier -> thread 0's system fence -> counter increment; the last CTA's thread 0 observes all
-    // increments, fences, and the CTA barrier below orders the publishing lanes after it (release is cumulative).
+#ifndef DCCF_DP_SERIAL_FLAGS
+    // The last CTA publishes the arrival to the peers with one release store per LANE, not `world` release stores in
+    // sequence by one thread: each st.release.sys waits for the NVLink round trip of what precedes it, and eight of them
+    // back to back were the bulk of what a push cost whatever its size (measured on 8 x B200: 42 us between the end of
+    // the dW kernel and the start of the touched-row sweep).  Ordering: every CTA's data stores -> its barrier ->
+    // thread 0's system fence -> counter increment; the last CTA's thread 0 observes all increments, fences, and the
+    // CTA barrier below orders the publishing lanes after it (release is cumulative).
     __shared__ int s_last;
     if (threadIdx.x == 0) {
         __threadfence_system();

@@ -1,0 +1,77 @@
+// dp_sync.cuh — the flag protocol of the data-parallel exchange (dp_exchange.cu), usable from inside OTHER kernels:
+// a consumer kernel waits for the peers' segments in its own prologue (no k_dp_wait launch between producer and
+// consumer) and its last CTA hands the receive buffers back to the peers (no k_dp_done launches after it).
+#pragma once
+#include "common.cuh"
+
+namespace dccf {
+
+constexpr int DP_MAX_WORLD = 8;
+
+__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
+    int32_t v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Spin until *p >= want.  A peer that died (or never reaches this step) must not leave this GPU spinning for ever:
+// after 60 s — four orders of magnitude beyond any legitimate wait, start-up skew included — the kernel traps, the
+// process sees a CUDA error and the job fails loudly instead of hanging the box.
+__device__ __forceinline__ void spin_until(const int32_t* p, int32_t want) {
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(p) < want) {
+        if (global_ns() - t0 > 60ull * 1000000000ull) __trap();
+    }
+}
+
+// device-side image of dccf_dp_sync (include/dccf_b200.h)
+struct DpChannel {
+    float* base[DP_MAX_WORLD];   // the symmetric buffer on every rank (own at index rank)
+    int64_t flag_off;            // floats: [arrival int32[8] | consumed int32[8]] start here
+    int32_t* epoch_dev;          // completed exchanges on this channel
+};
+struct DpSync {
+    int32_t world, rank, n_wait, n_done;
+    DpChannel wait[3];
+    DpChannel done[3];
+    const float* loss_parts;     // optional: n_loss values loss_stride floats apart, summed into loss_out by the last CTA
+    int64_t loss_stride;
+    int32_t n_loss;
+    float* loss_out;
+};
+
+// Prologue of a consumer CTA: every peer's segment of the current exchange has arrived on all wait channels.
+// Call from all threads of the CTA (contains a barrier).
+__device__ __forceinline__ void dp_wait_inline(const DpSync& s) {
+    if (s.n_wait > 0) {
+        const int t = threadIdx.x;
+        if (t < s.n_wait * s.world) {
+            const DpChannel& c = s.wait[t / s.world];
+            const int32_t* arrival = reinterpret_cast<const int32_t*>(c.base[s.rank] + c.flag_off);
+            spin_until(arrival + (t % s.world), __ldg(c.epoch_dev) + 1);
+        }
+        __syncthreads();
+    }
+}
+
+// Tail of the LAST CTA of the consumer (all other CTAs have finished reading): total loss, then consumed flags to
+// every peer (one release store per lane) and the channels' epoch counters.  Call from all threads of that CTA.
+__device__ __forceinline__ void dp_done_inline(const DpSync& s) {
+    const int t = threadIdx.x;
+    if (s.loss_out != nullptr && t == 0) {
+        float acc = 0.f;
+        for (int i = 0; i < s.n_loss; ++i) acc += __ldcg(s.loss_parts + (size_t)i * s.loss_stride);
+        s.loss_out[0] = acc;
+    }
+    if (t < s.n_done * s.world) {
+        const DpChannel& c = s.done[t / s.world];
+        const int peer = t % s.world;
+        st_release_sys(reinterpret_cast<int32_t*>(c.base[peer] + c.flag_off) + DP_MAX_WORLD + s.rank, *c.epoch_dev + 1);
+    }
+    __syncthreads();
+    if (t < s.n_done) *s.done[t].epoch_dev += 1;
+}
+
+}  // namespace dccf

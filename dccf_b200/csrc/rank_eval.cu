@@ -6,10 +6,11 @@
 // calls, src/utils/rank_metrics.py:61-87 (precision_at_k) and :130-201 (dcg_at_k / ndcg_at_k, method=1).
 //
 // k_rank_stream (k <= 16): one warp per user, ONE streaming pass over the user's candidates.  Lane l reads
-// candidates l, l+32, ... (coalesced; eight loads in flight) and keeps its own best KCAP entries (score, item id,
-// row) sorted in registers; a candidate is compared against the lane's current worst entry first, its item id
-// is only loaded when it can enter the list.  The 32 sorted lists are merged by k shuffle tournaments over the
-// list heads (the winning lane pops).  Labels are read once: total relevance, number of positives (ideal DCG
+// candidates l, l+32, ... (coalesced; sixteen loads in flight) and keeps its own best KCAP entries (score, row)
+// sorted in registers; a candidate is compared against the lane's current worst entry first.  Item ids are read
+// ONLY to break exact score ties (a dependent load on the insertion path made the warp wait for the L2 once per
+// candidate batch: 74 us instead of < 10 for 1 024 users).  The 32 sorted lists are merged by k shuffle
+// tournaments over the list heads (the winning lane pops).  Labels are read once: total relevance, number of positives (ideal DCG
 // of 0/1 labels is a count; other label values take a second pass that keeps the k largest labels), and the
 // labels of the k winners.  Every metric (ndcg, hit, precision, recall, f1) at every requested k (up to 4
 // values of k per launch) comes out of that one pass; per-user values are optional, the per-metric SUMS over
@@ -57,31 +58,34 @@ struct RankKs {
     int32_t n_k, kmax;
 };
 
-// entry of a lane's sorted list (no label: loaded for the k winners only)
+// entry of a lane's sorted list: score and row only.  The item id decides exact score ties and is fetched then
+// (the rows are in L1 / L2: they were just streamed); the label is loaded for the k winners only.
 struct Ent {
     float s;
-    int64_t iid;
-    int32_t row;
+    int32_t row;      // INT32_MAX = sentinel, ranks after every real candidate
 };
-__device__ __forceinline__ bool ent_before(const Ent& a, const Ent& b) {
+__device__ __forceinline__ bool ent_before(const Ent& a, const Ent& b, const int64_t* __restrict__ iids) {
+    if (b.row == INT32_MAX) return a.row != INT32_MAX;
+    if (a.row == INT32_MAX) return false;
     if (a.s != b.s) return a.s > b.s;
-    if (a.iid != b.iid) return a.iid < b.iid;
+    const int64_t ia = __ldg(iids + a.row), ib = __ldg(iids + b.row);
+    if (ia != ib) return ia < ib;
     return a.row < b.row;
 }
 __device__ __forceinline__ Ent ent_sentinel() {
     Ent e;
-    e.s = -INFINITY; e.iid = INT64_MAX; e.row = INT32_MAX;      // after every real candidate
+    e.s = -INFINITY; e.row = INT32_MAX;
     return e;
 }
 
 template <int KCAP>
-__device__ __forceinline__ void list_insert(Ent (&L)[KCAP], const Ent& cur) {
+__device__ __forceinline__ void list_insert(Ent (&L)[KCAP], const Ent& cur, const int64_t* __restrict__ iids) {
     // precondition: cur ranks before L[KCAP-1]
     bool placed = false;
 #pragma unroll
     for (int i = KCAP - 1; i >= 1; --i) {
         if (!placed) {
-            if (ent_before(cur, L[i - 1])) L[i] = L[i - 1];
+            if (ent_before(cur, L[i - 1], iids)) L[i] = L[i - 1];
             else { L[i] = cur; placed = true; }
         }
     }
@@ -126,24 +130,25 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
         int n_pos = 0;
         bool nonbinary = false;
 
-        // ---- the streaming pass: eight candidates per lane in flight ---------------------------------
-        for (int64_t c0 = lo + lane; c0 < hi; c0 += 32 * 8) {
-            int32_t row[8];
-            float s[8], l[8];
+        // ---- the streaming pass: sixteen candidates per lane in flight ----------------------------------
+        constexpr int NF = 16;
+        for (int64_t c0 = lo + lane; c0 < hi; c0 += 32 * NF) {
+            int32_t row[NF];
+            float s[NF], l[NF];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < NF; ++j) {
                 const int64_t c = c0 + 32 * j;
                 row[j] = (c < hi) ? (cand_rows != nullptr ? __ldg(cand_rows + c) : (int32_t)c) : -1;
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < NF; ++j) {
                 if (row[j] >= 0) {
                     s[j] = __ldg(scores + row[j]);
                     l[j] = __ldg(labels + row[j]);
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < NF; ++j) {
                 if (row[j] < 0) continue;
                 label_sum += (double)l[j];
                 n_pos += (l[j] == 1.f) ? 1 : 0;
@@ -151,10 +156,7 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
                 Ent cur;
                 cur.s = order_score(s[j]);
                 cur.row = row[j];
-                if (cur.s >= L[KCAP - 1].s) {               // may enter the list: only now is the item id needed
-                    cur.iid = __ldg(iids + row[j]);
-                    if (ent_before(cur, L[KCAP - 1])) list_insert<KCAP>(L, cur);
-                }
+                if (cur.s >= L[KCAP - 1].s && ent_before(cur, L[KCAP - 1], iids)) list_insert<KCAP>(L, cur, iids);
             }
         }
 #pragma unroll
@@ -173,9 +175,8 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
             for (int o = 16; o > 0; o >>= 1) {
                 Ent other;
                 other.s = __shfl_xor_sync(0xffffffffu, best.s, o);
-                other.iid = __shfl_xor_sync(0xffffffffu, best.iid, o);
                 other.row = __shfl_xor_sync(0xffffffffu, best.row, o);
-                if (ent_before(other, best)) best = other;
+                if (ent_before(other, best, iids)) best = other;
             }
             if (L[0].row == best.row) {                      // rows are unique: exactly one lane pops
 #pragma unroll
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
             if (lane == t) mine = best;
         }
         const float my_label = (lane < kk) ? __ldg(labels + mine.row) : 0.f;
-        if (out_topk_iid != nullptr && lane < kmax) out_topk_iid[g * kmax + lane] = (lane < kk) ? mine.iid : -1;
+        if (out_topk_iid != nullptr && lane < kmax) out_topk_iid[g * kmax + lane] = (lane < kk) ? __ldg(iids + mine.row) : -1;
         if (out_topk_row != nullptr && lane < kmax) out_topk_row[g * kmax + lane] = (lane < kk) ? mine.row : -1;
 
         // ---- ideal ordering of the labels: 0/1 labels -> the first n_pos positions are 1; otherwise the kmax

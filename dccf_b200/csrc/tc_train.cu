@@ -171,19 +171,26 @@ __global__ void __launch_bounds__(TC_NT, 2) k_train_fwd_tc(const TrainFwdParams 
         const float* nptr = (NOISE_MODE == 1) ? prm.noise + (size_t)grow * prm.F + kq * 8 : nullptr;
         RngKey key_noise = make_rng_key(0, 0, DOMAIN_NOISE);
         if (NOISE_MODE == 2) key_noise = resolve_rng_key(prm.rng, DOMAIN_NOISE);
+        // the table values of chunk c (this thread's 8 columns of its row): E_item columns for c < D / 32, Feat after
+        auto fetch = [&](int c, float4 (&v)[2]) {
+            const int k0 = c * TC_KC;                 // first column of the chunk in [E_item | Feat]
+            const float* src = (k0 < D) ? item_ptr + k0 : feat_ptr + (k0 - D);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) v[q] = ldg4(src + 4 * q);
+        };
+        float4 v[2];
+        if (n_local > 0) fetch(c_lo, v);
         for (int i = 0; i < n_local; ++i) {
             const int c = c_lo + i;
             const int s = i % TT_STAGES;
             const uint32_t ph = (uint32_t)(i / TT_STAGES) & 1u;
-            const int k0 = c * TC_KC;                 // first column of the chunk in [E_item | Feat]
-            float4 v[2];
-            if (k0 < D) {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) v[q] = ldg4(item_ptr + k0 + 4 * q);
-            } else {
+            const int k0 = c * TC_KC;
+            // the next chunk's loads are in flight while this chunk's noise is generated (the loop used to expose one
+            // L2 / DRAM round trip per stage: ncu long-scoreboard stalls on the first use of the loaded values)
+            float4 vn[2];
+            if (i + 1 < n_local) fetch(c + 1, vn);
+            if (k0 >= D) {
                 const int f0 = k0 - D;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) v[q] = ldg4(feat_ptr + f0 + 4 * q);
                 if (NOISE_MODE != 0) {
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
@@ -210,6 +217,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_train_fwd_tc(const TrainFwdParams 
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&full_bar[s]);
+            if (i + 1 < n_local) { v[0] = vn[0]; v[1] = vn[1]; }
         }
     } else if (warp == TC_PRODUCERS / 32) {
         // ===== MMA issuer =====

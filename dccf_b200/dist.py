@@ -60,19 +60,28 @@ class SegmentExchange(object):
         self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=device)
         self.cta_counter = torch.zeros(1, dtype=torch.int32, device=device)
 
+    def push(self, folds=None):
+        """Peer-memory mode: store this rank's segment into every peer's receive buffer and publish its arrival — no
+        wait: the consumer kernel waits for the peers' segments itself (kernels.make_dp_sync) or `wait` is called."""
+        from . import kernels
+        if folds:
+            kernels.dp_push_fold(self.send, self.seg, self.peer_bases, self.world, self.rank, self.flag_off,
+                                 self.epoch_dev, self.cta_counter, folds)
+        else:
+            kernels.dp_push(self.send, self.seg, self.peer_bases, self.world, self.rank, self.flag_off,
+                            self.epoch_dev, self.cta_counter)
+
+    def wait(self):
+        from . import kernels
+        kernels.dp_wait(self.sym, self.world, self.flag_off, self.epoch_dev)
+
     def exchange(self, folds=None):
         """All ranks' segments, rank-major, in self.recv.  folds (peer-memory mode only): ranges of the segment that
         are summed from partial buffers on the way out instead of being read from `send`:
         [(parts, n_parts, stride, offset_in_segment, n_floats), ...] (csrc/dp_exchange.cu)."""
         if self.mode == 'p2p':
-            from . import kernels
-            if folds:
-                kernels.dp_push_fold(self.send, self.seg, self.peer_bases, self.world, self.rank, self.flag_off,
-                                     self.epoch_dev, self.cta_counter, folds)
-            else:
-                kernels.dp_push(self.send, self.seg, self.peer_bases, self.world, self.rank, self.flag_off,
-                                self.epoch_dev, self.cta_counter)
-            kernels.dp_wait(self.sym, self.world, self.flag_off, self.epoch_dev)
+            self.push(folds)
+            self.wait()
         elif self.world == 1:
             self.recv.copy_(self.send)
         else:

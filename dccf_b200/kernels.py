@@ -6,7 +6,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import Adam, AdamTable, AdamTensor, Dims, Expo, Rng, check, ptr, stream_ptr
+from ._lib import Adam, AdamTable, AdamTensor, Dims, DpSync, Expo, LinkExtra, Rng, check, ptr, stream_ptr
 
 D = _lib.DIM
 
@@ -263,17 +263,64 @@ def adam_step(tables, dense, hp):
     LAUNCHES[0] += 2 if any(t.n_seg * t.seg_len > 0 for t in tables) else 1
 
 
+def make_dp_sync(world, rank, wait=(), done=(), loss=None):
+    """dccf_dp_sync: `wait` / `done` = exchange channels (objects with peer_bases, flag_off, epoch_dev: the p2p
+    SegmentExchange of dccf_b200/dist.py) a consumer kernel waits on in its prologue / hands back from its last CTA;
+    loss = (parts tensor, stride in floats, n, out tensor): the ranks' loss terms summed by that last CTA."""
+    s = DpSync()
+    s.world, s.rank, s.n_wait, s.n_done = int(world), int(rank), len(wait), len(done)
+    for arr, chans in ((s.wait, wait), (s.done, done)):
+        for k, c in enumerate(chans):
+            for p in range(world):
+                arr[k].peer_bases[p] = int(c.peer_bases[p])
+            arr[k].flag_off = int(c.flag_off)
+            arr[k].epoch_dev = ptr(c.epoch_dev).value
+    if loss is not None:
+        parts, stride, n, out = loss
+        s.loss_parts, s.loss_stride, s.n_loss, s.loss_out = ptr(parts).value, int(stride), int(n), ptr(out).value
+    return s
+
+
+def make_link_extra(stage=None, prefetch_user=None, prefetch_item=None, prefetch_feat=None, prefetch_dense=None,
+                    sync=None, counter=None):
+    """Extras of dccf_adam_link_ids.  stage = (epoch_ptrs_dev, cursor_dev, X_out, si_out, counter): the batch is read
+    from a device-resident epoch (replaces dccf_stage_batch).  prefetch_user / prefetch_item = up to three [rows, D]
+    tensors each (parameter, exp_avg, exp_avg_sq), prefetch_feat = Feat, prefetch_dense = up to four tensors: what the
+    step will touch, requested into L2 ahead of its use."""
+    e = LinkExtra()
+    if stage is not None:
+        ep, cur, X_out, si_out, counter = stage
+        e.epoch_ptrs_dev, e.cursor_dev = ptr(ep).value, ptr(cur).value
+        e.X_out, e.sample_item_out, e.stage_counter = ptr(X_out).value, ptr(si_out).value, ptr(counter).value
+    for k, t in enumerate(prefetch_user or ()):
+        e.pf_user[k] = ptr(t).value
+    for k, t in enumerate(prefetch_item or ()):
+        e.pf_item[k] = ptr(t).value
+    if prefetch_feat is not None:
+        e.pf_feat = ptr(prefetch_feat).value
+    for k, t in enumerate(prefetch_dense or ()):
+        e.pf_dense[k] = ptr(t).value
+        e.pf_dense_bytes[k] = t.numel() * t.element_size()
+    if sync is not None:                # (data parallel) wait for the ids / hand the id buffer back inside the kernel
+        e.sync = ctypes.pointer(sync)
+        e._keep_sync = sync
+        e.stage_counter = ptr(counter).value
+    return e
+
+
 def adam_link_ids(dims, X, sample_item, head_user, next_user, head_item, next_item, expo=None, expo_e=None,
-                  expo_den=None, n_pairs=None, n_seg=1, seg_stride=0, user_seg=-1, X_local=None, si_local=None):
+                  expo_den=None, n_pairs=None, n_seg=1, seg_stride=0, user_seg=-1, X_local=None, si_local=None,
+                  extra=None):
     """Record lists of the step from the ids alone (before any gradient exists); with `expo` also the exposure
     softmax of every local pair (expo_e [P, Z], expo_den [P]).  Data parallel: X / sample_item point at segment 0
-    of the gathered ids, n_seg segments seg_stride int64 apart."""
+    of the gathered ids, n_seg segments seg_stride int64 apart.  extra: make_link_extra(...)."""
     lib = _lib.load()
     n_pairs = X.shape[0] if n_pairs is None else int(n_pairs)
     check(lib.dccf_adam_link_ids(ctypes.byref(dims), ptr(X), ptr(sample_item), n_pairs, int(n_seg), int(seg_stride),
                                  int(user_seg), ptr(head_user), ptr(next_user), ptr(head_item), ptr(next_item),
                                  ctypes.byref(expo) if expo is not None else None, ptr(X_local), ptr(si_local),
-                                 ptr(expo_e), ptr(expo_den), stream_ptr()), 'dccf_adam_link_ids')
+                                 ptr(expo_e), ptr(expo_den), ctypes.byref(extra) if extra is not None else None,
+                                 stream_ptr()), 'dccf_adam_link_ids')
     LAUNCHES[0] += 1 if n_pairs > 0 else 0
 
 
@@ -287,14 +334,17 @@ def adam_untouched(tables, hp, threads=0):
 
 
 def adam_touched(tables, dense, hp, already_linked=False, w_image=None, w_image_tensor=0, w_image_K=0, cta_counter=None,
-                 advance_step_dev=None, advance_offset_dev=None):
-    """Adam over the touched rows and the dense tensors (one launch, two when the records still need linking)."""
+                 advance_step_dev=None, advance_offset_dev=None, sync=None):
+    """Adam over the touched rows and the dense tensors (one launch, two when the records still need linking).
+    sync (make_dp_sync): data-parallel step — wait for the peers' gradient segments in the kernel's prologue, total loss
+    and hand-back of the exchange buffers by its last CTA."""
     lib = _lib.load()
     ta = (AdamTable * max(1, len(tables)))(*tables)
     da = (AdamTensor * max(1, len(dense)))(*dense)
     check(lib.dccf_adam_touched(ta, len(tables), da, len(dense), ctypes.byref(hp), int(bool(already_linked)),
                                 ptr(w_image), int(w_image_tensor), int(w_image_K), ptr(cta_counter),
-                                ptr(advance_step_dev), ptr(advance_offset_dev), stream_ptr()), 'dccf_adam_touched')
+                                ptr(advance_step_dev), ptr(advance_offset_dev),
+                                ctypes.byref(sync) if sync is not None else None, stream_ptr()), 'dccf_adam_touched')
     LAUNCHES[0] += 1 if already_linked or not any(t.n_seg * t.seg_len > 0 for t in tables) else 2
 
 

@@ -23,6 +23,22 @@ def group_candidates(uid):
     return users, order.astype(np.int32), off
 
 
+def candidate_layout(uid):
+    """(cand_rows or None, user_off) for the ranker.  When every user's rows already form ONE contiguous run of the data
+    (an evaluation set written user by user) the ranker reads scores / labels in place: cand_rows is None and user_off
+    holds the run boundaries (users in data order).  Otherwise (the reference's layout: all positives, then the blocks
+    of negatives, src/data_processor/DataProcessor.py:92-111) rows are grouped through an index array."""
+    uid = np.asarray(uid)
+    n = len(uid)
+    if n == 0:
+        return None, np.zeros(1, dtype=np.int64)
+    starts = np.concatenate([[0], np.flatnonzero(uid[1:] != uid[:-1]) + 1])
+    if len(np.unique(uid[starts])) == len(starts):
+        return None, np.concatenate([starts, [n]]).astype(np.int64)
+    _, rows, off = group_candidates(uid)
+    return rows, off
+
+
 def rank_metrics_device(scores, labels, iids, cand_rows, user_off, k, want_topk=False):
     """Launch dccf_rank_eval; all arguments are CUDA tensors (cand_rows None: rows already grouped by user).
     Returns per-user metrics [n_users,5] f64 (ndcg, hit, precision, recall, f1 at k) and optionally the top-k
@@ -40,8 +56,12 @@ def rank_sums_device(scores, labels, iids, cand_rows, user_off, ks):
     as ndcg@5,recall@5,precision@5 is ONE launch; the reference loops over the users once per metric,
     src/models/BaseModel.py:90-126); larger k go through dccf_rank_eval one at a time."""
     ks = [int(k) for k in ks]
-    out = torch.empty((len(ks), 5), dtype=torch.float64, device=scores.device)
     small = sorted(set(k for k in ks if k <= kernels.RANK_STREAM_MAX_K))
+    if ks == small and len(ks) <= kernels.RANK_MAX_NK:          # the usual case: one launch, its output is the result
+        sums = torch.empty((len(ks), 5), dtype=torch.float64, device=scores.device)
+        kernels.rank_eval_multi(scores, labels, iids, cand_rows, user_off, ks, out_sums=sums)
+        return sums
+    out = torch.empty((len(ks), 5), dtype=torch.float64, device=scores.device)
     where = {}
     for a in range(0, len(small), kernels.RANK_MAX_NK):
         group = small[a:a + kernels.RANK_MAX_NK]
@@ -70,14 +90,11 @@ def rank_context(data, dev):
     if hit is not None and hit[0]() is uid and hit[1]['dev'] == dev and hit[1]['n'] == len(uid):
         return hit[1]
     import weakref
-    _, rows, off = group_candidates(uid)
-    # the evaluation set is built user-major (DataProcessor: positives of a user, then its negatives): when the
-    # grouping permutation is the identity the ranker reads scores / labels contiguously, with no indirection
-    grouped = bool(len(rows) == 0 or np.array_equal(rows, np.arange(len(rows), dtype=rows.dtype)))
+    rows, off = candidate_layout(uid)
     ctx = {'dev': dev, 'n': len(uid),
            'labels': torch.from_numpy(np.ascontiguousarray(data['Y'], dtype=np.float32)).to(dev),
            'iids': torch.from_numpy(np.ascontiguousarray(data['iid'], dtype=np.int64)).to(dev),
-           'rows': None if grouped else torch.from_numpy(rows).to(dev), 'off': torch.from_numpy(off).to(dev),
+           'rows': None if rows is None else torch.from_numpy(rows).to(dev), 'off': torch.from_numpy(off).to(dev),
            'n_users': len(off) - 1}
     try:
         _RANK_CTX[key] = (weakref.ref(uid, lambda _r, k=key: _RANK_CTX.pop(k, None)), ctx)

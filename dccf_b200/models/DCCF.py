@@ -714,14 +714,19 @@ class DCCF(DMF):
                  kernels.adam_tensor(b, ea['b'], es['b'], rec['gb_part'], rec['n_splits'], b.numel())]
         return tables, dense
 
-    def _exchange_dense(self, rec):
+    def _exchange_dense(self, rec, push_only=False):
         """Data parallel: all-gather dW / db / loss; the row-split partials of dW / db are folded into the segment by
-        the push kernel itself (peer-memory mode) or by two dccf_sum_parts launches."""
+        the push kernel itself (peer-memory mode) or by two dccf_sum_parts launches.  push_only: the consumer kernel
+        waits for the peers itself."""
         ex, v = rec['exchange'], rec['send']
         W, b = self.mlp[0].weight.data, self.mlp[0].bias.data
         if ex.mode == 'p2p':
-            ex.exchange_dense(folds=[(rec['gW_part'], rec['n_splits'], W.numel(), ex.off['gW'][0], W.numel()),
-                                     (rec['gb_part'], rec['n_splits'], b.numel(), ex.off['gb'][0], b.numel())])
+            folds = [(rec['gW_part'], rec['n_splits'], W.numel(), ex.off['gW'][0], W.numel()),
+                     (rec['gb_part'], rec['n_splits'], b.numel(), ex.off['gb'][0], b.numel())]
+            if push_only:
+                ex.dense.push(folds=folds)
+            else:
+                ex.exchange_dense(folds=folds)
             return
         kernels.sum_parts(rec['gW_part'], rec['n_splits'], W.numel(), W.numel(), v['gW'])
         kernels.sum_parts(rec['gb_part'], rec['n_splits'], b.numel(), b.numel(), v['gb'])
@@ -746,6 +751,16 @@ class DCCF(DMF):
     use_split_adam = os.environ.get('DCCF_SPLIT_ADAM', '1') != '0'
     overlap_split_adam = os.environ.get('DCCF_SPLIT_OVERLAP', '1') != '0'
 
+    def _sweep_threads(self, dp):
+        """Launch shape of the untouched-row Adam sweep: one small CTA per SM hidden beside the tensor-core kernels
+        (128 threads; 256 under data parallelism, where it starts later) while the tables are small enough for that to
+        finish in time; -1 = the wide, full-occupancy sweep once the sweep itself bounds the step (scaled configuration:
+        24 B x 64 x 10^6..10^7 rows per step — at the ~2 TB/s of the narrow launch that is milliseconds)."""
+        rows = self.uid_embeddings.weight.shape[0] + self.item_num
+        if rows * self.ui_vector_size * 24 > 400e6:
+            return -1
+        return 256 if dp else 0
+
     def _wimg_key(self):
         W = self.mlp[0].weight
         return (W._version, W.data_ptr(), self._param_epoch)
@@ -767,7 +782,12 @@ class DCCF(DMF):
             self._dp['ids'][P] = ix
         return ix
 
-    def _fused_split_step(self, call, loss_mode, Y, opt, hp, w_image_valid, overlap, counters=None):
+    # k_link_ids also requests what the step will touch into L2 (rows of the tables and their Adam moments, the true
+    # items' feature rows, W with its moments and operand images): DCCF_L2_PREFETCH=0 switches it off (A/B)
+    l2_prefetch = os.environ.get('DCCF_L2_PREFETCH', '1') != '0'
+    dp_fold_sync = os.environ.get('DCCF_DP_FOLD', '1') != '0'
+
+    def _fused_split_step(self, call, loss_mode, Y, opt, hp, w_image_valid, overlap, counters=None, stage=None):
         """Forward + loss + backward + optimizer with the optimizer split around the backward.  overlap=True: the
         sweep of the untouched rows goes to a side stream (forked from / joined to the current stream with events,
         so it is also legal under CUDA-graph capture).  Data parallel: the ranks first gather each other's ids
@@ -796,15 +816,41 @@ class DCCF(DMF):
         # The exposure softmax of the local pairs (read by the middle kernel) and, on one GPU, the record lists: first,
         # on the main stream.  (On the side stream this kernel would run beside the first CTAs of the partial-product
         # kernel — measured: that kernel then takes 22 us instead of 13.)
+        eu, ei = self.uid_embeddings.weight.data, self.iid_embeddings.weight.data
+        W = self.mlp[0].weight.data
+        pf_user = (eu, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user']) if self.l2_prefetch else None
+        pf_item = (ei, opt.exp_avg['E_item'], opt.exp_avg_sq['E_item']) if self.l2_prefetch else None
+        extra = None
+        if not dp and (self.l2_prefetch or stage is not None):
+            extra = kernels.make_link_extra(
+                stage=stage, prefetch_user=pf_user, prefetch_item=pf_item,
+                prefetch_feat=self.feature_embedding if self.l2_prefetch else None,
+                prefetch_dense=(wimg, W, opt.exp_avg['W'], opt.exp_avg_sq['W']) if self.l2_prefetch else None)
         kernels.adam_link_ids(self._dims(), call['X'], call['sample_item'], opt.head_u, next_u, opt.head_i, next_i,
-                              self._expo(), expo_e, expo_den, n_seg=0 if dp else 1)
+                              self._expo(), expo_e, expo_den, n_seg=0 if dp else 1, extra=extra)
+
+        # data parallel, folded synchronisation (DCCF_DP_FOLD=0: the round-1 sequence push / wait / consume / done as
+        # separate launches): consumers wait for the peers' segments in their own prologue and their last CTA hands the
+        # buffers back — four launches fewer on the main stream of every step
+        fold = dp and self.dp_fold_sync
 
         def link_global():
             # data parallel: every rank's ids, then the record lists of the GLOBAL step
-            ids = ix.exchange().view(torch.int64)
+            pf = dict(prefetch_user=pf_user, prefetch_item=pf_item,
+                      prefetch_dense=(W, opt.exp_avg['W'], opt.exp_avg_sq['W'])) if self.l2_prefetch else {}
+            if fold:
+                ix.push()
+                if opt.__dict__.get('link_counter') is None:
+                    opt.link_counter = torch.zeros(1, dtype=torch.int32, device=eu.device)
+                ids = ix.recv.view(torch.int64)
+                extra_g = kernels.make_link_extra(sync=kernels.make_dp_sync(ix.world, ix.rank, wait=(ix,), done=(ix,)),
+                                                  counter=opt.link_counter, **pf)
+            else:
+                ids = ix.exchange().view(torch.int64)
+                extra_g = kernels.make_link_extra(**pf) if pf else None
             kernels.adam_link_ids(self._dims(), ids, ids[ix.si_off_i64:], opt.head_u, next_u, opt.head_i, next_i,
                                   n_pairs=P, n_seg=ix.world, seg_stride=ix.seg_i64,
-                                  user_seg=-1 if ex.user_records else ix.rank)
+                                  user_seg=-1 if ex.user_records else ix.rank, extra=extra_g)
 
         between = None
         if overlap:
@@ -819,8 +865,8 @@ class DCCF(DMF):
             with torch.cuda.stream(side):
                 if dp:                      # the id exchange waits for the peers: never on the critical path
                     link_global()
-                kernels.adam_untouched(tables, hp, 256 if dp else 0)
-                if dp:
+                kernels.adam_untouched(tables, hp, self._sweep_threads(dp))
+                if dp and not fold:
                     ix.done()
                 done.record(side)
             if dp:
@@ -831,27 +877,41 @@ class DCCF(DMF):
                         mid_done.record(main)
                         ship.wait_event(mid_done)
                         with torch.cuda.stream(ship):
-                            ex.exchange_records()
+                            if fold:
+                                ex.rec.push()
+                            else:
+                                ex.exchange_records()
                             shipped.record(ship)
         else:
             if dp:
                 link_global()
-            kernels.adam_untouched(tables, hp)
-            if dp:
+            kernels.adam_untouched(tables, hp, self._sweep_threads(dp))
+            if dp and not fold:
                 ix.done()
         pred, rec = self._launch_fwd_bwd(call, loss_mode, Y, rec=rec, w_image_valid=w_image_valid, expo_e=expo_e,
                                          expo_den=expo_den, between=between)
+        sync = None
         if dp:
             if not overlap:
-                ex.exchange_records()
-            self._exchange_dense(rec)
+                if fold:
+                    ex.rec.push()
+                else:
+                    ex.exchange_records()
+            self._exchange_dense(rec, push_only=fold)
             if overlap:
                 main.wait_event(shipped)
+            if fold:
+                total = self._buf('dp_total_loss', (1,), torch.float32)
+                a_loss, _ = ex.off['loss']
+                sync = kernels.make_dp_sync(ex.world, ex.rank, wait=(ex.rec, ex.dense), done=(ex.rec, ex.dense),
+                                            loss=(ex.dense.recv[a_loss:], ex.dense.seg, ex.world, total))
         if overlap:
             main.wait_event(done)
         step_dev, offset_dev = counters if counters is not None else (None, None)
-        kernels.adam_touched(tables, dense, hp, True, wimg, 0, D + F, opt.cta_counter, step_dev, offset_dev)
+        kernels.adam_touched(tables, dense, hp, True, wimg, 0, D + F, opt.cta_counter, step_dev, offset_dev, sync=sync)
         if dp:
+            if fold:
+                return pred, total[0]
             loss = ex.total_loss()
             ex.done()
             return pred, loss
@@ -912,17 +972,21 @@ class DCCF(DMF):
         the graph's first node copies the batch from a device-resident epoch (dccf_stage_batch)."""
         dev = self.uid_embeddings.weight.device
         S = self.sample_num
-        g = {'X': torch.zeros((P, 2), dtype=torch.int64, device=dev),
-             'si': torch.zeros((P, S), dtype=torch.int64, device=dev),
+        # ids and confounder draws of the step in ONE buffer [X (P x 2) | sample_item (P x S)]: a batch that arrives from
+        # the host is staged in pinned memory with the same layout and uploaded by a single copy
+        ids = torch.zeros(2 * P + P * S, dtype=torch.int64, device=dev)
+        g = {'ids': ids, 'X': ids[:2 * P].view(P, 2), 'si': ids[2 * P:].view(P, S),
              'Y': torch.zeros(P, dtype=torch.float32, device=dev),
              'step_dev': torch.zeros(1, dtype=torch.int32, device=dev),
              'offset_dev': torch.zeros(1, dtype=torch.int64, device=dev), 'synced': None}
         if staged:
             g['epoch_ptrs'] = torch.zeros(2, dtype=torch.int64, device=dev)
             g['cursor'] = torch.zeros(1, dtype=torch.int64, device=dev)
+            g['stage_counter'] = torch.zeros(1, dtype=torch.int32, device=dev)
         if self._dp is not None and self._split_step_ok(0 if rank_mode == 1 else 1, P):
             ix = self._id_exchange_for(P)       # the step's input buffers ARE the send segment of the id exchange
             g['X'], g['si'] = ix.send_X, ix.send_si
+            g['ids'] = ix.send[:4 * P + 2 * P * S].view(torch.int64)
         seed = self.random_seed
         if self._dp is not None:
             seed = (seed + 0x9E3779B97F4A7C15 * self._dp['rank']) & 0xffffffffffffffff
@@ -936,14 +1000,21 @@ class DCCF(DMF):
         graph = torch.cuda.CUDAGraph()
         launches_before = kernels.LAUNCHES[0]
         with torch.cuda.graph(graph, capture_error_mode='thread_local'):
-            if staged:
-                kernels.stage_batch(g['epoch_ptrs'], g['cursor'], P, S, g['X'], g['si'])
             loss_mode = 0 if rank_mode == 1 else 1
             Yg = g['Y'] if rank_mode != 1 else None
-            if self._split_step_ok(loss_mode, P):
+            split = self._split_step_ok(loss_mode, P)
+            # a batch read from a device-resident epoch: fetched by k_link_ids itself on one GPU (each linking thread
+            # copies the id it links), by a launch of its own otherwise (the id exchange pushes the staged buffers)
+            stage_in_link = staged and split and self._dp is None
+            if staged and not stage_in_link:
+                kernels.stage_batch(g['epoch_ptrs'], g['cursor'], P, S, g['X'], g['si'])
+            if split:
                 # the W operand images are kept current by dccf_adam_touched (checked before every replay)
+                stage = None
+                if stage_in_link:
+                    stage = (g['epoch_ptrs'], g['cursor'], g['X'], g['si'], g['stage_counter'])
                 pred, loss = self._fused_split_step(call, loss_mode, Yg, opt, hp, True, overlap=True,
-                                                    counters=(g['step_dev'], g['offset_dev']))
+                                                    counters=(g['step_dev'], g['offset_dev']), stage=stage)
                 g['w_image'] = True     # loss: the step's own output buffer (valid until the next train_step)
             else:
                 if self._fused_step_ok(loss_mode):
@@ -1010,13 +1081,37 @@ class DCCF(DMF):
         S = self.sample_num
         if g == 'warm':
             g = graphs[key] = self._build_step_graph(P, rank_mode, p_drop, opt, staged=False)
-        # inputs into the graph's static buffers (async copies on the current stream)
         Xs = X if torch.is_tensor(X) else torch.as_tensor(np.asarray(X))
-        g['X'].copy_(Xs[:, :2] if Xs.shape[1] != 2 else Xs, non_blocking=True)
         si = feed_dict.get('sample_item')
-        if si is None:
-            si = torch.randint(self.item_num, size=(P, S))          # DCCF.py:72, CPU generator
-        g['si'].copy_(si, non_blocking=True)
+        if not Xs.is_cuda and (si is None or not si.is_cuda) and Xs.dtype == torch.int64 and Xs.shape[1] == 2:
+            # a batch from the host: ids and confounder draw (DCCF.py:72, the torch CPU generator) are assembled in a
+            # pinned staging slot with the layout of the graph's input buffer and uploaded by ONE asynchronous copy;
+            # a small ring of slots, each guarded by an event, lets the host run ahead of the device
+            ring = g.get('stage')
+            if ring is None:
+                ring = g['stage'] = {'slots': [[torch.empty(2 * P + P * S, dtype=torch.int64, pin_memory=True), None]
+                                                for _ in range(8)], 'next': 0}
+            slot = ring['slots'][ring['next'] % len(ring['slots'])]
+            ring['next'] += 1
+            if slot[1] is not None:
+                slot[1].synchronize()           # the upload that last used this slot has completed
+            else:
+                slot[1] = torch.cuda.Event()
+            slot[0][:2 * P].view(P, 2).copy_(Xs)
+            if S > 0:
+                dst = slot[0][2 * P:].view(P, S)
+                if si is None:
+                    host_rng.randint(self.item_num, (P, S), out=dst)
+                else:
+                    dst.copy_(si)
+            g['ids'].copy_(slot[0], non_blocking=True)
+            slot[1].record()
+        else:
+            # inputs already on the device (async copies on the current stream into the graph's static buffers)
+            g['X'].copy_(Xs[:, :2] if Xs.shape[1] != 2 else Xs, non_blocking=True)
+            if si is None:
+                si = torch.randint(self.item_num, size=(P, S))          # DCCF.py:72, CPU generator
+            g['si'].copy_(si, non_blocking=True)
         if rank_mode != 1:
             g['Y'].copy_(feed_dict['Y'], non_blocking=True)
         return self._replay(g, opt)

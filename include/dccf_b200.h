@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 30
+#define DCCF_ABI_VERSION 31
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -293,17 +293,59 @@ int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, const dccf_a
  *                           scratch.  cta_counter (optional, int32 zero on entry / exit): the last CTA to finish does
  *                           advance_step_dev[0] += 1 and advance_offset_dev[0] += 1 (replaces dccf_state_advance in a
  *                           captured step; every other reader of the counters must have completed).
+ *                           sync (optional, needs cta_counter): data-parallel step — every CTA first waits for the peers'
+ *                           gradient segments, the last CTA sums the ranks' loss terms and hands the buffers back.
  * Every row is updated exactly once, with the arithmetic of dccf_adam_step. */
+/* Data-parallel synchronisation folded into a consumer kernel (NULL: none).  A channel is one symmetric exchange buffer
+ * of dccf_dp_push.  The kernel that receives a dccf_dp_sync
+ *   - waits in the prologue of every CTA until all `world` arrival flags of each wait channel show the current exchange
+ *     (what dccf_dp_wait does in a launch of its own between producer and consumer);
+ *   - in its LAST CTA: sums n_loss values loss_stride floats apart into loss_out (the ranks' loss terms), marks every
+ *     done channel as consumed on every peer and advances its epoch counter (what dccf_dp_done does, one launch per
+ *     channel, after the consumer). */
+typedef struct dccf_dp_channel {
+    uint64_t peer_bases[8];      /* device address of the buffer on every rank (this rank's own at index rank) */
+    int64_t flag_off;            /* floats */
+    int32_t* epoch_dev;
+} dccf_dp_channel;
+typedef struct dccf_dp_sync {
+    int32_t world, rank, n_wait, n_done;
+    dccf_dp_channel wait[3];
+    dccf_dp_channel done[3];
+    const float* loss_parts; int64_t loss_stride; int32_t n_loss; int32_t _pad; float* loss_out;
+} dccf_dp_sync;
+/* Optional extras of dccf_adam_link_ids (NULL: none), all device pointers:
+ *   staging (epoch_ptrs_dev != NULL): the step reads its batch from a device-resident epoch — what dccf_stage_batch does
+ *     in a launch of its own: X / sample_item arguments are ignored, the batch is [*cursor] of the arrays whose
+ *     addresses sit in epoch_ptrs_dev {X_epoch [n,P,2], sample_epoch [n,P,S]}; every id is copied into X_out /
+ *     sample_item_out (the buffers the other kernels of the step read) by the thread that links it, and the last CTA
+ *     to finish advances *cursor (stage_counter: int32, zero on entry / exit).  Needs n_seg == 1.
+ *   L2 prefetch (any pointer may be NULL): the rows this step will touch — the pairs' user rows, the slot items' rows
+ *     and their Adam moments, the true items' feature rows — and up to four dense ranges (W, its moments, its operand
+ *     images) are requested into L2 (prefetch.global.L2) while the step's first kernels run, so that the forward, the
+ *     middle kernel and the touched-row sweep find them there instead of in DRAM.  No effect on results.
+ *   sync: data-parallel link of the GLOBAL step — wait for the peers' ids in the prologue, hand the id buffer back in
+ *     the last CTA (stage_counter doubles as the CTA counter). */
+typedef struct dccf_link_extra {
+    const uint64_t* epoch_ptrs_dev; int64_t* cursor_dev; int64_t* X_out; int64_t* sample_item_out;
+    int32_t* stage_counter;
+    const float* pf_user[3];     /* E_user, exp_avg, exp_avg_sq   [n_users, D] */
+    const float* pf_item[3];     /* E_item, exp_avg, exp_avg_sq   [n_items, D] */
+    const float* pf_feat;        /* Feat [n_items, feat_dim] */
+    const void* pf_dense[4]; int64_t pf_dense_bytes[4];
+    const dccf_dp_sync* sync;    /* HOST pointer, copied at launch */
+} dccf_link_extra;
 int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const int64_t* sample_item, int64_t n_pairs,
                        int32_t n_seg, int64_t seg_stride, int32_t user_seg, int32_t* head_user, int32_t* next_user,
                        int32_t* head_item, int32_t* next_item, const dccf_expo* expo, const int64_t* X_local,
-                       const int64_t* sample_item_local, float* expo_e, float* expo_den, void* stream);
+                       const int64_t* sample_item_local, float* expo_e, float* expo_den,
+                       const dccf_link_extra* extra, void* stream);
 int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam* hp,
                         int32_t threads_per_cta, void* stream);
 int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
                       int32_t n_dense, const dccf_adam* hp, int32_t already_linked, float* w_image,
                       int32_t w_image_tensor, int32_t w_image_K, int32_t* cta_counter, int32_t* advance_step_dev,
-                      uint64_t* advance_offset_dev, void* stream);
+                      uint64_t* advance_offset_dev, const dccf_dp_sync* sync, void* stream);
 int dccf_train_prep_w_image(const float* W, int32_t feat_dim, float* w_image, void* stream);
 /* First node of a captured training step that reads its inputs from a device-resident epoch:
  * epoch_ptrs_dev = device array {address of X_epoch [n_batches,P,2], address of sample_epoch [n_batches,P,S]},

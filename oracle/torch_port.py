@@ -5,6 +5,11 @@ as src/models/DCCF.py:66-127 and src/runners/BaseRunner.py:175-188), used ONLY b
 `cpu_baseline` / `--impl reference` arm: the reference itself is Python under /root/reference and cannot
 travel to the GPU box, and its DCCF class hard-codes CUDA (DCCF.py:55,64,72,87).  Validated against the
 reference fixtures in tests/test_oracle_golden.py::test_torch_port_matches_reference.
+
+`to_device('cuda')` moves the parameters AND the two plain-attribute tables, after which the same op sequence runs
+eagerly on the GPU exactly as the reference does on its own hardware (confounders on the CPU generator then copied,
+noise / dropout on the CUDA generator): bench.py's `gpu_eager_reference` object — SURVEY.md §8d's "what eager PyTorch
+can reach on the same B200".
 """
 import numpy as np
 import torch
@@ -30,13 +35,21 @@ class DCCFPort(torch.nn.Module):
             elif type(m) == torch.nn.Embedding:
                 torch.nn.init.normal_(m.weight, mean=0.0, std=0.01)
 
+    def to_device(self, device):
+        self.to(device)
+        self.feature_embedding = self.feature_embedding.to(device)      # plain attributes, as in DCCF.py:55,64
+        self.expo_prob = self.expo_prob.to(device)
+        return self
+
     def predict(self, feed_dict):
+        dev = self.uid_embeddings.weight.device
         u_ids = feed_dict['X'][:, 0]
         i_ids = feed_dict['X'][:, 1]
         S, A = self.sample_num, self.attribute_num
         sample_item = feed_dict.get('sample_item')
         if sample_item is None:
-            sample_item = torch.randint(self.item_num, size=(u_ids.shape[0], S))                    # DCCF.py:72
+            sample_item = torch.randint(self.item_num, size=(u_ids.shape[0], S))                    # DCCF.py:72 (CPU)
+        sample_item = sample_item.to(dev)
         items = torch.cat((i_ids.view(-1, 1), sample_item), 1)                                      # :74
         items = items.view(-1, S + 1, 1).expand(items.shape[0], S + 1, A)                           # :76
         users = u_ids.view(-1, 1, 1).expand(items.shape[0], items.shape[1], items.shape[2])         # :77
@@ -47,7 +60,7 @@ class DCCFPort(torch.nn.Module):
         feature_embeddings = self.feature_embedding[fid]                                            # :86
         noise = feed_dict.get('noise')
         if noise is None:
-            noise = torch.empty(feature_embeddings.shape).normal_(std=self.std)                     # :87
+            noise = torch.empty(feature_embeddings.shape, device=dev).normal_(std=self.std)         # :87
         x = torch.cat((item_embeddings, feature_embeddings + noise), 1)                             # :89
         mask = feed_dict.get('dropout_mask')
         for layer in self.mlp:                                                                      # :91-94
