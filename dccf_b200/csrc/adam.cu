@@ -936,6 +936,13 @@ extern "C" int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const
         int64_t pf = (dense_bytes / 128 + 255) / 256;
         blocks += pf > 16 ? 16 : (pf < 1 ? 1 : pf);
     }
+    // same shared-memory carveout as the tensor-core kernels that follow it in the step: a kernel that asks for another
+    // L1 / shared split makes its successor wait for the SMs to be reconfigured
+    static PerDeviceOnce carve_once;
+    if (carve_once.need()) {
+        cudaFuncSetAttribute(k_link_ids, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve_once.mark();
+    }
     k_link_ids<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(a);
     DCCF_CHECK_LAUNCH("k_link_ids");
     return DCCF_OK;
@@ -1019,6 +1026,11 @@ extern "C" int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables
         k_link_all<<<(unsigned)link_blocks, 256, 0, stream>>>(a);
         DCCF_CHECK_LAUNCH("k_link_all");
     }
+    static PerDeviceOnce carve_once;
+    if (carve_once.need()) {
+        cudaFuncSetAttribute(k_adam_touched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve_once.mark();
+    }
     if (blocks > 0) {
         k_adam_touched<<<(unsigned)blocks, 256, 0, stream>>>(a, wi, ds);
         DCCF_CHECK_LAUNCH("k_adam_touched");
@@ -1031,6 +1043,11 @@ extern "C" int dccf_stage_batch(const uint64_t* epoch_ptrs_dev, int64_t* cursor_
     DCCF_CHECK_ARG(epoch_ptrs_dev && cursor_dev && X_out && (n_samples == 0 || sample_item_out), "dccf_stage_batch: null argument");
     DCCF_CHECK_ARG(n_pairs >= 0 && n_samples >= 0, "dccf_stage_batch: negative size");
     if (n_pairs == 0) return DCCF_OK;
+    static PerDeviceOnce carve_once;
+    if (carve_once.need()) {
+        cudaFuncSetAttribute(k_stage_batch, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve_once.mark();
+    }
     k_stage_batch<<<1, 1024, 0, (cudaStream_t)stream_>>>(epoch_ptrs_dev, cursor_dev, n_pairs * 2, n_pairs * n_samples, X_out,
                                                          sample_item_out);
     DCCF_CHECK_LAUNCH("k_stage_batch");

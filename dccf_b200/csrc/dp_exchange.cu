@@ -162,6 +162,11 @@ static int dp_push_impl(const float* send, int64_t seg_floats, const uint64_t* p
     DCCF_CHECK_ARG(rank >= 0 && rank < world, "dccf_dp_push: rank %d outside [0,%d)", rank, world);
     int64_t ctas = (seg_floats / 4 + 255) / 256;
     if (ctas > 148) ctas = 148;
+    static PerDeviceOnce carve_once;      // (same carveout as its neighbours in the step, see dccf_adam_link_ids)
+    if (carve_once.need()) {
+        cudaFuncSetAttribute(k_dp_push, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve_once.mark();
+    }
     k_dp_push<<<(unsigned)ctas, 256, 0, stream>>>(send, seg_floats, peers, world, rank, flag_off, epoch_dev, cta_counter, folds);
     DCCF_CHECK_LAUNCH("k_dp_push");
     return DCCF_OK;

@@ -105,6 +105,8 @@ __device__ __forceinline__ void label_insert(float (&L)[KCAP], float v) {
     if (!placed) L[0] = v;
 }
 
+constexpr int RANK_CHUNK = 1024;     // candidates of a user staged in shared memory at a time (4 KB per warp)
+
 template <int KCAP>
 __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
     const float* __restrict__ scores, const float* __restrict__ labels, const int64_t* __restrict__ iids,
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
     int64_t* __restrict__ out_topk_iid, int32_t* __restrict__ out_topk_row, double* __restrict__ out_metrics,
     double* __restrict__ part_sums, int32_t* __restrict__ cta_counter, double* __restrict__ out_sums) {
     __shared__ double acc_s[RANK_WARPS][RANK_MAX_NK * RANK_NCOL];
+    __shared__ float sc_s[RANK_WARPS][RANK_CHUNK];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ncol = ks.n_k * RANK_NCOL;
@@ -119,6 +122,7 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
     __syncwarp();
     const int kmax = ks.kmax;
     const int64_t n_warps = (int64_t)gridDim.x * RANK_WARPS;
+    float* my_s = sc_s[warp];
 
     for (int64_t g = (int64_t)blockIdx.x * RANK_WARPS + warp; g < n_users; g += n_warps) {   // warp-uniform
         const int64_t lo = user_off[g], hi = user_off[g + 1];
@@ -130,34 +134,49 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
         int n_pos = 0;
         bool nonbinary = false;
 
-        // ---- the streaming pass: sixteen candidates per lane in flight ----------------------------------
-        constexpr int NF = 16;
-        for (int64_t c0 = lo + lane; c0 < hi; c0 += 32 * NF) {
-            int32_t row[NF];
-            float s[NF], l[NF];
+        for (int64_t base = lo; base < hi; base += RANK_CHUNK) {
+            const int m = (int)min((int64_t)RANK_CHUNK, hi - base);
+            // ---- phase 1, the streaming pass: scores -> shared memory, label statistics; eight candidates per lane in
+            // flight.  (Deliberately SMALL code: a first version that kept 16 candidates in registers and inlined the
+            // insertion 16 times was 13 k instructions long and spent 63 % of its stall samples waiting for the
+            // instruction cache.)
+            for (int c0 = lane; c0 < m; c0 += 32 * 8) {
+                int32_t row[8];
+                float s[8], l[8];
 #pragma unroll
-            for (int j = 0; j < NF; ++j) {
-                const int64_t c = c0 + 32 * j;
-                row[j] = (c < hi) ? (cand_rows != nullptr ? __ldg(cand_rows + c) : (int32_t)c) : -1;
-            }
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c0 + 32 * j;
+                    row[j] = (c < m) ? (cand_rows != nullptr ? __ldg(cand_rows + base + c) : (int32_t)(base + c)) : -1;
+                }
 #pragma unroll
-            for (int j = 0; j < NF; ++j) {
-                if (row[j] >= 0) {
-                    s[j] = __ldg(scores + row[j]);
-                    l[j] = __ldg(labels + row[j]);
+                for (int j = 0; j < 8; ++j) {
+                    if (row[j] >= 0) {
+                        s[j] = __ldg(scores + row[j]);
+                        l[j] = __ldg(labels + row[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (row[j] >= 0) {
+                        my_s[c0 + 32 * j] = order_score(s[j]);
+                        label_sum += (double)l[j];
+                        n_pos += (l[j] == 1.f) ? 1 : 0;
+                        nonbinary |= (l[j] != 0.f && l[j] != 1.f);
+                    }
                 }
             }
-#pragma unroll
-            for (int j = 0; j < NF; ++j) {
-                if (row[j] < 0) continue;
-                label_sum += (double)l[j];
-                n_pos += (l[j] == 1.f) ? 1 : 0;
-                nonbinary |= (l[j] != 0.f && l[j] != 1.f);
+            __syncwarp();
+            // ---- phase 2, selection from shared memory: one copy of the insertion code ----
+#pragma unroll 1
+            for (int c = lane; c < m; c += 32) {
                 Ent cur;
-                cur.s = order_score(s[j]);
-                cur.row = row[j];
-                if (cur.s >= L[KCAP - 1].s && ent_before(cur, L[KCAP - 1], iids)) list_insert<KCAP>(L, cur, iids);
+                cur.s = my_s[c];
+                if (cur.s >= L[KCAP - 1].s) {
+                    cur.row = cand_rows != nullptr ? __ldg(cand_rows + base + c) : (int32_t)(base + c);
+                    if (ent_before(cur, L[KCAP - 1], iids)) list_insert<KCAP>(L, cur, iids);
+                }
             }
+            __syncwarp();
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -169,9 +188,10 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
         // ---- merge: kmax tournaments over the heads of the 32 sorted lists; lane t keeps winner t ------
         const int kk = (int)min((int64_t)kmax, n);
         Ent mine = ent_sentinel();
+#pragma unroll 1
         for (int t = 0; t < kk; ++t) {
             Ent best = L[0];
-#pragma unroll
+#pragma unroll 1
             for (int o = 16; o > 0; o >>= 1) {
                 Ent other;
                 other.s = __shfl_xor_sync(0xffffffffu, best.s, o);
@@ -196,11 +216,13 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
             float T[KCAP];
 #pragma unroll
             for (int i = 0; i < KCAP; ++i) T[i] = -INFINITY;
+#pragma unroll 1
             for (int64_t c = lo + lane; c < hi; c += 32) {
                 const float v = __ldg(labels + (cand_rows != nullptr ? __ldg(cand_rows + c) : (int32_t)c));
                 if (v > T[KCAP - 1]) label_insert<KCAP>(T, v);
             }
             ideal = 0.f;
+#pragma unroll 1
             for (int t = 0; t < kk; ++t) {
                 float best = T[0];
                 int who = lane;
@@ -222,6 +244,7 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
         // ---- metrics at every requested k: sequential float64 sums over positions 0 .. k-1 ---------------
         double dcg = 0.0, idcg = 0.0, hit_sum = 0.0;
         int nonzero = 0, next_k = 0;
+#pragma unroll 1
         for (int t = 0; t < kmax; ++t) {
             const float lab = __shfl_sync(0xffffffffu, my_label, t);
             const float idl = __shfl_sync(0xffffffffu, ideal, t);

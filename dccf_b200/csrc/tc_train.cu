@@ -32,6 +32,11 @@ namespace dccf {
 #ifndef DCCF_TRAIN_STAGES
 #define DCCF_TRAIN_STAGES TC_STAGES
 #endif
+// Producers generate two stages per trip (four independent Philox chains per thread instead of two); wants a
+// three-stage ring.  Build-time knob like the above.
+#ifndef DCCF_TRAIN_PAIR
+#define DCCF_TRAIN_PAIR 0
+#endif
 constexpr int TT_STAGES = DCCF_TRAIN_STAGES;
 constexpr uint32_t TT_SMEM_BYTES = TT_STAGES * TC_STAGE_BYTES + 256;
 static_assert(TT_SMEM_BYTES <= 227 * 1024, "training ring does not fit the shared memory of an SM");
@@ -123,7 +128,7 @@ struct TrainFwdParams {
 };
 
 template <int NOISE_MODE>
-__global__ void __launch_bounds__(TC_NT, 2) k_train_fwd_tc(const TrainFwdParams prm) {
+__global__ void __launch_bounds__(TC_NT, DCCF_TRAIN_PAIR ? 1 : 2) k_train_fwd_tc(const TrainFwdParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TT_STAGES * TC_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + TT_STAGES;
@@ -178,38 +183,34 @@ __global__ void __launch_bounds__(TC_NT, 2) k_train_fwd_tc(const TrainFwdParams 
 #pragma unroll
             for (int q = 0; q < 2; ++q) v[q] = ldg4(src + 4 * q);
         };
-        float4 v[2];
-        if (n_local > 0) fetch(c_lo, v);
-        for (int i = 0; i < n_local; ++i) {
-            const int c = c_lo + i;
-            const int s = i % TT_STAGES;
-            const uint32_t ph = (uint32_t)(i / TT_STAGES) & 1u;
+        // chunk c's noise added to its table values (and the optional copy for the dW kernel)
+        auto add_noise = [&](int c, float4 (&v)[2]) {
             const int k0 = c * TC_KC;
-            // the next chunk's loads are in flight while this chunk's noise is generated (the loop used to expose one
-            // L2 / DRAM round trip per stage: ncu long-scoreboard stalls on the first use of the loaded values)
-            float4 vn[2];
-            if (i + 1 < n_local) fetch(c + 1, vn);
-            if (k0 >= D) {
-                const int f0 = k0 - D;
-                if (NOISE_MODE != 0) {
+            if (k0 < D) return;
+            const int f0 = k0 - D;
+            if (NOISE_MODE != 0) {
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        float4 e;
-                        if (NOISE_MODE == 1) e = ldg4(nptr + f0 + 4 * q);
-                        else e = noise_quad(key_noise, (uint32_t)grow, (uint32_t)(f0 / 4 + kq * 2 + q), prm.noise_std);
-                        v[q].x = __fadd_rn(v[q].x, e.x); v[q].y = __fadd_rn(v[q].y, e.y);
-                        v[q].z = __fadd_rn(v[q].z, e.z); v[q].w = __fadd_rn(v[q].w, e.w);
-                    }
-                }
-                if (prm.x_save != nullptr) {
-                    // tile-major copy of what is multiplied: [row tile][feature chunk][kq][row][8 floats] — a warp
-                    // (32 consecutive rows, one kq) stores 1 KB contiguous
-                    float* dst = prm.x_save + ((((size_t)blockIdx.x * (prm.F / TC_KC) + (size_t)(f0 / TC_KC)) * 4 + kq) * TC_BM + row) * 8;
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) st4(dst + 4 * q, v[q]);
+                for (int q = 0; q < 2; ++q) {
+                    float4 e;
+                    if (NOISE_MODE == 1) e = ldg4(nptr + f0 + 4 * q);
+                    else e = noise_quad(key_noise, (uint32_t)grow, (uint32_t)(f0 / 4 + kq * 2 + q), prm.noise_std);
+                    v[q].x = __fadd_rn(v[q].x, e.x); v[q].y = __fadd_rn(v[q].y, e.y);
+                    v[q].z = __fadd_rn(v[q].z, e.z); v[q].w = __fadd_rn(v[q].w, e.w);
                 }
             }
-            tc::mbar_wait(&empty_bar[s], ph ^ 1u);   // the MMAs that read this stage have completed
+            if (prm.x_save != nullptr) {
+                // tile-major copy of what is multiplied: [row tile][feature chunk][kq][row][8 floats] — a warp
+                // (32 consecutive rows, one kq) stores 1 KB contiguous
+                float* dst = prm.x_save + ((((size_t)blockIdx.x * (prm.F / TC_KC) + (size_t)(f0 / TC_KC)) * 4 + kq) * TC_BM + row) * 8;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) st4(dst + 4 * q, v[q]);
+            }
+        };
+        // stage i of this CTA's sequence: wait until the MMAs that read its slot have completed, store, publish
+        auto commit = [&](int i, const float4 (&v)[2]) {
+            const int s = i % TT_STAGES;
+            const uint32_t ph = (uint32_t)(i / TT_STAGES) & 1u;
+            tc::mbar_wait(&empty_bar[s], ph ^ 1u);
             uint8_t* a_hi = smem + s * TC_STAGE_BYTES;
             uint8_t* a_lo = a_hi + TC_A_BYTES;
 #pragma unroll
@@ -217,8 +218,37 @@ __global__ void __launch_bounds__(TC_NT, 2) k_train_fwd_tc(const TrainFwdParams 
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&full_bar[s]);
+        };
+#if DCCF_TRAIN_PAIR
+        // Two stages per trip: their four Philox / Box-Muller chains are independent, so the scheduler interleaves them
+        // (the producer loop is bound by the LATENCY of its dependent chains at 4 warps per scheduler, not by issue
+        // slots: seven Philox rounds instead of ten bought 4 %), and the loads of the NEXT pair are in flight meanwhile.
+        float4 v0[2], v1[2];
+        if (n_local > 0) fetch(c_lo, v0);
+        if (n_local > 1) fetch(c_lo + 1, v1);
+        for (int i = 0; i < n_local; i += 2) {
+            const bool two = i + 1 < n_local;
+            float4 n0[2], n1[2];
+            if (i + 2 < n_local) fetch(c_lo + i + 2, n0);
+            if (i + 3 < n_local) fetch(c_lo + i + 3, n1);
+            add_noise(c_lo + i, v0);
+            if (two) add_noise(c_lo + i + 1, v1);
+            commit(i, v0);
+            if (two) commit(i + 1, v1);
+            v0[0] = n0[0]; v0[1] = n0[1]; v1[0] = n1[0]; v1[1] = n1[1];
+        }
+#else
+        float4 v[2];
+        if (n_local > 0) fetch(c_lo, v);
+        for (int i = 0; i < n_local; ++i) {
+            // the next chunk's loads are in flight while this chunk's noise is generated
+            float4 vn[2];
+            if (i + 1 < n_local) fetch(c_lo + i + 1, vn);
+            add_noise(c_lo + i, v);
+            commit(i, v);
             if (i + 1 < n_local) { v[0] = vn[0]; v[1] = vn[1]; }
         }
+#endif
     } else if (warp == TC_PRODUCERS / 32) {
         // ===== MMA issuer =====
         if (lane == 0) {
@@ -613,7 +643,7 @@ __device__ __forceinline__ void quad_transpose(float4& a, int j) {
 }
 
 template <int NOISE_MODE>
-__global__ void __launch_bounds__(TB_NT, 2) k_train_bwd_tc(const TrainBwdParams prm) {
+__global__ void __launch_bounds__(TB_NT, DCCF_TRAIN_PAIR ? 1 : 2) k_train_bwd_tc(const TrainBwdParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TT_STAGES * TC_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + TT_STAGES;
@@ -705,17 +735,12 @@ __global__ void __launch_bounds__(TB_NT, 2) k_train_bwd_tc(const TrainBwdParams 
             }
         };
 
-        float4 v[2], dv;
-        if (n_st > 0) fetch(0, v, dv);
-        for (int st = 0; st < n_st; ++st) {
+        // stage st of this CTA: transpose, wait until the MMAs that read its slot have completed, store, publish
+        auto commit = [&](int st, float4 (&v)[2], const float4& dv) {
             const int s = st % TT_STAGES;
             const uint32_t ph = (uint32_t)(st / TT_STAGES) & 1u;
-            // the next stage's operands are in flight while this one is transposed, stored and multiplied
-            float4 vn[2], dvn;
-            if (st + 1 < n_st) fetch(st + 1, vn, dvn);
             quad_transpose(v[0], j);
             quad_transpose(v[1], j);
-
             tc::mbar_wait(&empty_bar[s], ph ^ 1u);
             uint8_t* a_hi = smem + s * TC_STAGE_BYTES;
             uint8_t* a_lo = a_hi + TC_A_BYTES;
@@ -730,10 +755,36 @@ __global__ void __launch_bounds__(TB_NT, 2) k_train_bwd_tc(const TrainBwdParams 
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&full_bar[s]);
+        };
+#if DCCF_TRAIN_PAIR
+        // two stages per trip: the operands of the NEXT pair (four independent Philox chains, the loads behind their id
+        // lookups) are produced while this pair is transposed, stored and multiplied — see k_train_fwd_tc
+        float4 v0[2], v1[2], dv0, dv1;
+        if (n_st > 0) fetch(0, v0, dv0);
+        if (n_st > 1) fetch(1, v1, dv1);
+        for (int st = 0; st < n_st; st += 2) {
+            const bool two = st + 1 < n_st;
+            float4 n0[2], n1[2], dn0, dn1;
+            if (st + 2 < n_st) fetch(st + 2, n0, dn0);
+            if (st + 3 < n_st) fetch(st + 3, n1, dn1);
+            commit(st, v0, dv0);
+            if (two) commit(st + 1, v1, dv1);
+            v0[0] = n0[0]; v0[1] = n0[1]; dv0 = dn0;
+            v1[0] = n1[0]; v1[1] = n1[1]; dv1 = dn1;
+        }
+#else
+        float4 v[2], dv;
+        if (n_st > 0) fetch(0, v, dv);
+        for (int st = 0; st < n_st; ++st) {
+            // the next stage's operands are in flight while this one is transposed, stored and multiplied
+            float4 vn[2], dvn;
+            if (st + 1 < n_st) fetch(st + 1, vn, dvn);
+            commit(st, v, dv);
             if (st + 1 < n_st) {
                 v[0] = vn[0]; v[1] = vn[1]; dv = dvn;
             }
         }
+#endif
         // the scalar loss of the fused step: per-term values summed in a fixed order (lane-strided, then a shuffle
         // tree) by one warp that is idle during the epilogue
         if (warp == 4 && mt == 0 && sp == 0 && prm.loss_terms != nullptr) {
