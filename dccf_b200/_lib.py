@@ -12,7 +12,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 _VARIANT = os.environ.get('DCCF_LIB_VARIANT', '')          # A/B build variants, see dccf_b200/build.py
 LIB_PATH = os.path.join(HERE, 'libdccf_b200%s.so' % (('_' + _VARIANT) if _VARIANT else ''))
-ABI_VERSION = 31
+ABI_VERSION = 32
 DIM = 64
 
 
@@ -50,7 +50,9 @@ class AdamTable(ctypes.Structure):
     _fields_ = [('table', ctypes.c_void_p), ('m', ctypes.c_void_p), ('v', ctypes.c_void_p), ('n_rows', ctypes.c_int64),
                 ('rec_keys', ctypes.c_void_p), ('rec_grads', ctypes.c_void_p), ('n_seg', ctypes.c_int32),
                 ('_pad', ctypes.c_int32), ('seg_len', ctypes.c_int64), ('key_seg_stride', ctypes.c_int64),
-                ('grad_seg_stride', ctypes.c_int64), ('head', ctypes.c_void_p), ('next', ctypes.c_void_p)]
+                ('grad_seg_stride', ctypes.c_int64), ('head', ctypes.c_void_p), ('next', ctypes.c_void_p),
+                ('rec_row', ctypes.c_void_p), ('csr_off', ctypes.c_void_p), ('csr', ctypes.c_void_p),
+                ('csr_pool', ctypes.c_void_p)]
 
 
 class DpChannel(ctypes.Structure):
@@ -69,7 +71,7 @@ class LinkExtra(ctypes.Structure):
                 ('sample_item_out', ctypes.c_void_p), ('stage_counter', ctypes.c_void_p),
                 ('pf_user', ctypes.c_void_p * 3), ('pf_item', ctypes.c_void_p * 3), ('pf_feat', ctypes.c_void_p),
                 ('pf_dense', ctypes.c_void_p * 4), ('pf_dense_bytes', ctypes.c_int64 * 4),
-                ('sync', ctypes.POINTER(DpSync))]
+                ('sync', ctypes.POINTER(DpSync)), ('rec_row_user', ctypes.c_void_p), ('rec_row_item', ctypes.c_void_p)]
 
 
 class AdamTensor(ctypes.Structure):
@@ -125,6 +127,7 @@ _SIGNATURES = {
                                           ctypes.POINTER(LinkExtra), _P]),
     'dccf_adam_untouched': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(Adam), ctypes.c_int32,
                                            _P]),
+    'dccf_adam_csr_build': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, _P]),
     'dccf_adam_touched': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(AdamTensor),
                                          ctypes.c_int32, ctypes.POINTER(Adam), ctypes.c_int32, _P, ctypes.c_int32,
                                          ctypes.c_int32, _P, _P, _P, ctypes.POINTER(DpSync), _P]),

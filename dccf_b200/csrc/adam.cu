@@ -191,6 +191,10 @@ struct AdamTableArgs {
     RecLayout L;
     int32_t* head;
     int32_t* next;
+    int32_t* rec_row;             // CSR mode (all four non-null), see dccf_adam_table
+    int32_t* csr_off;
+    int32_t* csr;
+    int32_t* csr_pool;
     int32_t block_lo, block_n;    // block range of the sweep kernel
     int32_t link_lo, link_n;      // block range of the link kernel
 };
@@ -285,6 +289,78 @@ __device__ __forceinline__ float4 gather_row_grad(const AdamTableArgs& t, int32_
     return g;
 }
 
+// The same sum from a CSR list: the row's record ids sit at csr[o .. o + n) in arrival order (no walk: sixteen lanes
+// load them at once), are ranked in shared memory and added in ascending index, four loads in flight.
+__device__ __forceinline__ float4 gather_row_grad_csr(const AdamTableArgs& t, int32_t first, int32_t o, int32_t n, int sub,
+                                                      uint32_t half_mask, int32_t* idx_s, int32_t* ord_s) {
+    if (n == 1) return ldg4(t.grads + rec_grad_index(t.L, first) + sub * 4);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n > ADAM_LIST_CAP) {
+        // longer than the buffer: n rounds of "smallest id above the last one", each a strided scan by the half-warp
+        int32_t last = -1;
+        for (int k = 0; k < n; ++k) {
+            int32_t best = 0x7fffffff;
+            for (int e = sub; e < n; e += 16) {
+                const int32_t q = __ldg(t.csr + o + e);
+                if (q > last && q < best) best = q;
+            }
+#pragma unroll
+            for (int w = 8; w > 0; w >>= 1) best = min(best, __shfl_xor_sync(half_mask, best, w));
+            const float4 rg = ldg4(t.grads + rec_grad_index(t.L, best) + sub * 4);
+            g.x += rg.x; g.y += rg.y; g.z += rg.z; g.w += rg.w;
+            last = best;
+        }
+        return g;
+    }
+    for (int e = sub; e < n; e += 16) idx_s[e] = __ldg(t.csr + o + e);
+    __syncwarp(half_mask);
+    for (int e = sub; e < n; e += 16) {
+        const int32_t mine = idx_s[e];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (idx_s[j] < mine) ? 1 : 0;
+        ord_s[rank] = mine;
+    }
+    __syncwarp(half_mask);
+    int q = 0;
+    for (; q + 4 <= n; q += 4) {
+        float4 rg[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rg[j] = ldg4(t.grads + rec_grad_index(t.L, ord_s[q + j]) + sub * 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { g.x += rg[j].x; g.y += rg[j].y; g.z += rg[j].z; g.w += rg[j].w; }
+    }
+    for (; q < n; ++q) {
+        const float4 rg = ldg4(t.grads + rec_grad_index(t.L, ord_s[q]) + sub * 4);
+        g.x += rg.x; g.y += rg.y; g.z += rg.z; g.w += rg.w;
+    }
+    __syncwarp(half_mask);
+    return g;
+}
+
+// CSR build after the counting link: phase 0 — the first record of every row reserves the row's range in the pool;
+// phase 1 — every record drops its id at (range start + its arrival position).
+__global__ void k_csr_build(const AdamAllArgs a, int phase) {
+    tl_begin(13);
+    tl_end(13);
+    for (int i = 0; i < a.n_tables; ++i) {
+        const AdamTableArgs& t = a.t[i];
+        const int b = (int)blockIdx.x - t.link_lo;
+        if (b < 0 || b >= t.link_n) continue;
+        if (t.csr == nullptr) return;
+        const int64_t r = (int64_t)b * blockDim.x + threadIdx.x;
+        if (r >= t.n_rec) return;
+        const int32_t pos = t.next[r];
+        if (pos < 0) return;                                   // (a record no link touched)
+        const int32_t row = t.rec_row[r];
+        if (phase == 0) {
+            if (pos == 0) t.csr_off[row] = atomicAdd(t.csr_pool, t.head[row] + 1);
+        } else {
+            t.csr[t.csr_off[row] + pos] = (int32_t)r;
+        }
+        return;
+    }
+}
+
 __global__ void __launch_bounds__(256, 4) k_adam_all(const AdamAllArgs a) {
     __shared__ int32_t list_s[16][2][ADAM_LIST_CAP];   // per half-warp: record indices as linked / in ascending order
     const AdamScalars s = resolve_adam(a.hp);
@@ -376,7 +452,7 @@ struct LinkIdsArgs {
     dccf_expo ex;
     float* expo_e;           // [P, Z]
     float* expo_den;         // [P]
-    dccf_link_extra extra;   // staging + L2 prefetch (all-null: none)
+    dccf_link_extra extra;   // staging + L2 prefetch + counting mode (all-null: none)
     int32_t feat_dim;
     DpSync sync;             // data-parallel global link: wait for the ids, hand the buffer back (n_wait = n_done = 0: none)
 };
@@ -398,16 +474,27 @@ __global__ void __launch_bounds__(256) k_link_ids(const LinkIdsArgs a) {
     tl_begin(0);
     tl_end(0);      // (short single wave: start and end are indistinguishable at the timer's resolution)
     __shared__ int64_t s_batch;
-    const bool staged = a.extra.epoch_ptrs_dev != nullptr;
+    // epoch_ptrs_dev given: X_out given -> this launch STAGES batch *cursor of the rank's own epoch (and advances the
+    // cursor); X_out null -> data-parallel link of the global step from the epoch-wide gather of every rank's ids
+    // (slots 2..5: base addresses of X_all [world, n, P, 2] / si_all [world, n, P, S] and their per-rank strides), batch
+    // *cursor - 1: the staging launch of this step has already advanced the cursor
+    const bool staged = a.extra.epoch_ptrs_dev != nullptr && a.extra.X_out != nullptr;
+    const bool epoch_global = a.extra.epoch_ptrs_dev != nullptr && a.extra.X_out == nullptr;
     const int64_t *X = a.X, *si = a.sample_item, *X_local = a.X_local, *si_local = a.si_local;
-    if (staged) {
-        // the batch is number *cursor of a device-resident epoch (what k_stage_batch does in a launch of its own)
-        if (threadIdx.x == 0) s_batch = *a.extra.cursor_dev;
+    int64_t seg_stride_x = a.seg_stride, seg_stride_s = a.seg_stride;
+    if (staged || epoch_global) {
+        if (threadIdx.x == 0) s_batch = *a.extra.cursor_dev - (epoch_global ? 1 : 0);
         __syncthreads();
-        X = reinterpret_cast<const int64_t*>(a.extra.epoch_ptrs_dev[0]) + s_batch * a.n_pairs * 2;
-        si = reinterpret_cast<const int64_t*>(a.extra.epoch_ptrs_dev[1]) + s_batch * a.n_pairs * a.S;
-        X_local = X;
-        si_local = si;
+        const int base = epoch_global ? 2 : 0;
+        X = reinterpret_cast<const int64_t*>(a.extra.epoch_ptrs_dev[base]) + s_batch * a.n_pairs * 2;
+        si = reinterpret_cast<const int64_t*>(a.extra.epoch_ptrs_dev[base + 1]) + s_batch * a.n_pairs * a.S;
+        if (epoch_global) {
+            seg_stride_x = (int64_t)a.extra.epoch_ptrs_dev[4];
+            seg_stride_s = (int64_t)a.extra.epoch_ptrs_dev[5];
+        } else {
+            X_local = X;
+            si_local = si;
+        }
     }
     dp_wait_inline(a.sync);      // (data parallel) the peers' ids have arrived
     const int bid = (int)blockIdx.x;
@@ -432,20 +519,27 @@ __global__ void __launch_bounds__(256) k_link_ids(const LinkIdsArgs a) {
         const int Z = a.S + 1;
         const int64_t per_seg = a.n_pairs * (Z + 1);
         const int64_t i = (int64_t)bid * blockDim.x + threadIdx.x;
-        if (i < per_seg * a.n_seg) {
+        // (a staging launch with n_seg == 0 — the local launch of a data-parallel step — copies the ids, links nothing)
+        if (i < per_seg * max(a.n_seg, staged ? 1 : 0)) {
             const int seg = (int)(i / per_seg);
+            const bool do_link = seg < a.n_seg;
             const int64_t il = i - (int64_t)seg * per_seg;
             const int64_t p = il / (Z + 1);
             const int slot = (int)(il - p * (Z + 1));   // 0 = the user record of pair p, 1 + z = its item record of slot z
-            const int64_t* Xs = X + (int64_t)seg * a.seg_stride;
-            const int64_t* sis = si + (int64_t)seg * a.seg_stride;
+            const int64_t* Xs = X + (int64_t)seg * seg_stride_x;
+            const int64_t* sis = si + (int64_t)seg * seg_stride_s;
             if (slot == 0) {
                 const int64_t uid = Xs[2 * p];
                 if (staged) a.extra.X_out[2 * p] = uid;
-                if (!(a.user_seg >= 0 && seg != a.user_seg)) {
+                if (do_link && !(a.user_seg >= 0 && seg != a.user_seg)) {
                     const int32_t u = checked_id(uid - a.user_base, a.n_users, nullptr);
                     const int32_t r = (int32_t)((a.user_seg >= 0 ? 0 : (int64_t)seg * a.n_pairs) + p);
-                    a.next_u[r] = atomicExch(&a.head_u[u], r);
+                    if (a.extra.rec_row_user != nullptr) {       // counting mode: arrival position + the row itself
+                        a.next_u[r] = atomicAdd(&a.head_u[u], 1) + 1;
+                        a.extra.rec_row_user[r] = u;
+                    } else {
+                        a.next_u[r] = atomicExch(&a.head_u[u], r);
+                    }
                     prefetch_rows(a.extra.pf_user, u);
                 }
             } else {
@@ -455,12 +549,19 @@ __global__ void __launch_bounds__(256) k_link_ids(const LinkIdsArgs a) {
                     if (z == 0) a.extra.X_out[2 * p + 1] = id;
                     else a.extra.sample_item_out[p * a.S + (z - 1)] = id;
                 }
-                const int32_t it = checked_id(id, a.n_items, nullptr);
-                const int32_t r = (int32_t)(((int64_t)seg * a.n_pairs + p) * Z + z);
-                a.next_i[r] = atomicExch(&a.head_i[it], r);
-                prefetch_rows(a.extra.pf_item, it);
+                if (do_link) {
+                    const int32_t it = checked_id(id, a.n_items, nullptr);
+                    const int32_t r = (int32_t)(((int64_t)seg * a.n_pairs + p) * Z + z);
+                    if (a.extra.rec_row_item != nullptr) {
+                        a.next_i[r] = atomicAdd(&a.head_i[it], 1) + 1;
+                        a.extra.rec_row_item[r] = it;
+                    } else {
+                        a.next_i[r] = atomicExch(&a.head_i[it], r);
+                    }
+                    prefetch_rows(a.extra.pf_item, it);
+                }
             }
-            if (a.extra.pf_feat != nullptr && a.n_seg == 1) {
+            if (a.extra.pf_feat != nullptr && (a.n_seg == 1 || (staged && a.n_seg == 0))) {
                 // the true item's feature row (feat_dim * 4 bytes), its 128-byte lines shared out over the pair's Z + 1
                 // threads (one GPU only: under data parallelism the other ranks' pairs are not multiplied here)
                 const int32_t fi = checked_id(Xs[2 * p + 1], a.n_items, nullptr);
@@ -543,7 +644,7 @@ struct WImageArgs {
     uint64_t* offset_dev;
 };
 
-__device__ __forceinline__ void touched_cta_done(const WImageArgs& wi, const DpSync& sync) {
+__device__ __forceinline__ void touched_cta_done(const AdamAllArgs& a, const WImageArgs& wi, const DpSync& sync) {
     __shared__ int s_last;
     __syncthreads();
     tl_end(5);
@@ -554,6 +655,8 @@ __device__ __forceinline__ void touched_cta_done(const WImageArgs& wi, const DpS
         if (s_last) {
             if (wi.step_dev) wi.step_dev[0] += 1;
             if (wi.offset_dev) wi.offset_dev[0] += 1;
+            for (int i = 0; i < a.n_tables; ++i)
+                if (a.t[i].csr_pool != nullptr) *a.t[i].csr_pool = 0;      // the CSR ranges of this step are released
             *wi.cta_counter = 0;
         }
     }
@@ -567,6 +670,7 @@ __global__ void __launch_bounds__(256) k_adam_touched(const AdamAllArgs a, const
     __shared__ int32_t list_s[16][2][ADAM_LIST_CAP];
     tl_begin(5);
     dp_wait_inline(sync);        // (data parallel) every rank's gradient records and dW / db / loss have arrived
+    if (sync.n_wait > 0) { tl_begin(12); tl_end(12); }
     const AdamScalars s = resolve_adam(a.hp);
     const int bid = (int)blockIdx.x;
     for (int i = 0; i < a.n_tables; ++i) {
@@ -578,20 +682,30 @@ __global__ void __launch_bounds__(256) k_adam_touched(const AdamAllArgs a, const
         const int sub = threadIdx.x & 15;
         const uint32_t half_mask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
         const int64_t hw_stride = ((int64_t)t.block_n * blockDim.x) >> 4;
+        const bool csr = t.csr != nullptr;
         for (int64_t r = ((int64_t)b * blockDim.x + threadIdx.x) >> 4; r < t.n_rec; r += hw_stride) {
-            int32_t row = t.keys[rec_key_index(t.L, r)];
-            if (row < 0 || row >= t.n_rows || t.head[row] != (int32_t)r) row = -1;
+            int32_t row, n_list = 0;
+            if (csr) {
+                // the record that arrived first at its row owns the row
+                row = (t.next[r] == 0) ? t.rec_row[r] : -1;
+                if (row >= 0) n_list = t.head[row] + 1;
+            } else {
+                row = t.keys[rec_key_index(t.L, r)];
+                if (row < 0 || row >= t.n_rows || t.head[row] != (int32_t)r) row = -1;
+            }
             if (row < 0) continue;          // (uniform over the half-warp: all 16 lanes read the same key and head)
             __syncwarp(half_mask);          // every lane of the half-warp has read the head before lane 0 resets it
             const size_t o = (size_t)row * D + sub * 4;
             float4 p = ld4(t.table + o), m = ld4(t.m + o), q = ld4(t.v + o);
-            const float4 g = gather_row_grad(t, (int32_t)r, sub, half_mask, list_s[threadIdx.x >> 4][0], list_s[threadIdx.x >> 4][1]);
+            const float4 g = csr ? gather_row_grad_csr(t, (int32_t)r, t.csr_off[row], n_list, sub, half_mask,
+                                                       list_s[threadIdx.x >> 4][0], list_s[threadIdx.x >> 4][1])
+                                 : gather_row_grad(t, (int32_t)r, sub, half_mask, list_s[threadIdx.x >> 4][0], list_s[threadIdx.x >> 4][1]);
             if (sub == 0) t.head[row] = -1;
             adam_elem(p.x, m.x, q.x, g.x, s); adam_elem(p.y, m.y, q.y, g.y, s);
             adam_elem(p.z, m.z, q.z, g.z, s); adam_elem(p.w, m.w, q.w, g.w, s);
             st4(t.table + o, p); st4(t.m + o, m); st4(t.v + o, q);
         }
-        touched_cta_done(wi, sync);
+        touched_cta_done(a, wi, sync);
         return;
     }
     for (int i = 0; i < a.n_dense; ++i) {
@@ -626,7 +740,7 @@ __global__ void __launch_bounds__(256) k_adam_touched(const AdamAllArgs a, const
                 base[2048 + off] = __fsub_rn(p, hi);
             }
         }
-        touched_cta_done(wi, sync);
+        touched_cta_done(a, wi, sync);
         return;
     }
 }
@@ -827,6 +941,9 @@ static int marshal_adam(const char* who, const dccf_adam_table* tables, int32_t 
         o.keys = t.rec_keys; o.grads = t.rec_grads; o.n_rec = n_rec;
         o.L.seg_len = t.seg_len > 0 ? t.seg_len : 1; o.L.key_seg_stride = t.key_seg_stride; o.L.grad_seg_stride = t.grad_seg_stride;
         o.head = t.head; o.next = t.next;
+        const int n_csr = (t.rec_row != nullptr) + (t.csr_off != nullptr) + (t.csr != nullptr) + (t.csr_pool != nullptr);
+        DCCF_CHECK_ARG(n_csr == 0 || n_csr == 4, "%s: table %d: the CSR buffers (rec_row, csr_off, csr, csr_pool) go together", who, i);
+        o.rec_row = t.rec_row; o.csr_off = t.csr_off; o.csr = t.csr; o.csr_pool = t.csr_pool;
         int64_t want;
         if (mode == 2) {
             want = (n_rec + 15) / 16;                              // 16 records (half-warps) per 256-thread CTA per trip
@@ -892,12 +1009,14 @@ extern "C" int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const
     DCCF_CHECK_ARG(dims && (X || staged) && head_user && next_user && head_item && next_item, "dccf_adam_link_ids: null argument");
     DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item || staged, "dccf_adam_link_ids: sample_item is null");
     DCCF_CHECK_ARG(n_seg >= 0 && (n_seg <= 1 || seg_stride > 0) && (n_seg == 0 || user_seg < n_seg), "dccf_adam_link_ids: bad segment layout");
-    DCCF_CHECK_ARG(n_seg > 0 || expo != nullptr, "dccf_adam_link_ids: nothing to do (n_seg == 0 and no exposure source)");
+    DCCF_CHECK_ARG(n_seg > 0 || expo != nullptr || staged, "dccf_adam_link_ids: nothing to do (n_seg == 0 and no exposure source)");
     DCCF_CHECK_ARG(n_pairs * n_seg * (dims->n_samples + 1) < ((int64_t)1 << 31), "dccf_adam_link_ids: too many records");
     DCCF_CHECK_ARG(expo == nullptr || (expo_e && expo_den), "dccf_adam_link_ids: expo needs expo_e and expo_den");
-    DCCF_CHECK_ARG(!staged || (n_seg == 1 && extra->cursor_dev && extra->X_out && extra->stage_counter &&
-                               (dims->n_samples == 0 || extra->sample_item_out)),
-                   "dccf_adam_link_ids: staging needs n_seg == 1, cursor, output buffers and the CTA counter");
+    const bool epoch_global = staged && extra->X_out == nullptr;
+    DCCF_CHECK_ARG(!staged || epoch_global || (n_seg <= 1 && extra->cursor_dev && extra->stage_counter &&
+                                               (dims->n_samples == 0 || extra->sample_item_out)),
+                   "dccf_adam_link_ids: staging needs n_seg <= 1, cursor, output buffers and the CTA counter");
+    DCCF_CHECK_ARG(!epoch_global || (extra->cursor_dev != nullptr && n_seg >= 1), "dccf_adam_link_ids: the epoch-wide link needs the cursor and n_seg >= 1");
     if (n_pairs <= 0) return DCCF_OK;
     LinkIdsArgs a;
     a.X = X; a.sample_item = sample_item; a.n_pairs = n_pairs; a.S = dims->n_samples; a.A = dims->n_attr;
@@ -911,14 +1030,16 @@ extern "C" int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const
     } else {
         a.extra.epoch_ptrs_dev = nullptr; a.extra.cursor_dev = nullptr; a.extra.X_out = nullptr;
         a.extra.sample_item_out = nullptr; a.extra.stage_counter = nullptr; a.extra.pf_feat = nullptr; a.extra.sync = nullptr;
+        a.extra.rec_row_user = nullptr; a.extra.rec_row_item = nullptr;
         for (int k = 0; k < 3; ++k) { a.extra.pf_user[k] = nullptr; a.extra.pf_item[k] = nullptr; }
         for (int k = 0; k < 4; ++k) { a.extra.pf_dense[k] = nullptr; a.extra.pf_dense_bytes[k] = 0; }
     }
     int rc_sync = marshal_sync("dccf_adam_link_ids", extra != nullptr ? extra->sync : nullptr, &a.sync);
     if (rc_sync != DCCF_OK) return rc_sync;
     DCCF_CHECK_ARG(a.sync.n_done == 0 || a.extra.stage_counter != nullptr, "dccf_adam_link_ids: sync needs stage_counter (the CTA counter)");
+    DCCF_CHECK_ARG((a.extra.rec_row_user == nullptr) == (a.extra.rec_row_item == nullptr), "dccf_adam_link_ids: counting mode needs rec_row of both tables");
     a.extra.sync = nullptr;
-    const int64_t n = n_pairs * n_seg * (dims->n_samples + 2);
+    const int64_t n = n_pairs * (n_seg > 0 ? n_seg : ((staged && !epoch_global) ? 1 : 0)) * (dims->n_samples + 2);
     a.link_blocks = (int32_t)((n + 255) / 256);
     int64_t blocks = a.link_blocks;
     a.expo_e = expo_e; a.expo_den = expo_den;
@@ -1001,6 +1122,24 @@ extern "C" int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tabl
     return DCCF_OK;
 }
 
+extern "C" int dccf_adam_csr_build(const dccf_adam_table* tables, int32_t n_tables, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AdamAllArgs a;
+    int32_t blocks = 0, link_blocks = 0;
+    dccf_adam hp;
+    hp.lr = 0; hp.beta1 = 0.9; hp.beta2 = 0.999; hp.eps = 0; hp.l2 = 0; hp.weight_decay = 0; hp.clip = 0; hp.step = 1; hp.step_dev = nullptr;
+    int rc = marshal_adam("dccf_adam_csr_build", tables, n_tables, nullptr, 0, &hp, 2, a, &blocks, &link_blocks);
+    if (rc != DCCF_OK) return rc;
+    for (int i = 0; i < n_tables; ++i)
+        DCCF_CHECK_ARG(tables[i].csr != nullptr || (int64_t)tables[i].n_seg * tables[i].seg_len == 0, "dccf_adam_csr_build: table %d has records but no CSR buffers", i);
+    if (link_blocks == 0) return DCCF_OK;
+    k_csr_build<<<(unsigned)link_blocks, 256, 0, stream>>>(a, 0);
+    DCCF_CHECK_LAUNCH("k_csr_build");
+    k_csr_build<<<(unsigned)link_blocks, 256, 0, stream>>>(a, 1);
+    DCCF_CHECK_LAUNCH("k_csr_build");
+    return DCCF_OK;
+}
+
 extern "C" int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
                                  int32_t n_dense, const dccf_adam* hp, int32_t already_linked, float* w_image,
                                  int32_t w_image_tensor, int32_t w_image_K, int32_t* cta_counter, int32_t* advance_step_dev,
@@ -1023,6 +1162,8 @@ extern "C" int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables
     if (rc != DCCF_OK) return rc;
     DCCF_CHECK_ARG((ds.n_done == 0 && ds.loss_out == nullptr) || cta_counter != nullptr, "dccf_adam_touched: sync needs cta_counter");
     if (link_blocks > 0 && !already_linked) {
+        for (int i = 0; i < n_tables; ++i)
+            DCCF_CHECK_ARG(tables[i].csr == nullptr, "dccf_adam_touched: CSR tables need dccf_adam_link_ids + dccf_adam_csr_build (already_linked = 1)");
         k_link_all<<<(unsigned)link_blocks, 256, 0, stream>>>(a);
         DCCF_CHECK_LAUNCH("k_link_all");
     }

@@ -35,7 +35,9 @@ struct DpFolds {
 __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send, int64_t seg, DpPeers peers, int world,
                                                  int rank, int64_t flag_off, const int32_t* __restrict__ epoch_dev,
                                                  int32_t* cta_counter, const DpFolds folds) {
-    tl_begin(8);
+    // debug timeline slot by what is pushed: 8 ids (small segment), 10 gradient records, 11 dW / db / loss (folded partials)
+    const int tl_slot = folds.n > 0 ? 11 : (seg < 16384 ? 8 : 10);
+    tl_begin(tl_slot);
     const int32_t epoch = __ldg(epoch_dev) + 1;
     if (threadIdx.x < world) {
         // peers have finished reading what this rank pushed last step
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send,
         }
     }
 #endif
-    tl_end(8);
+    tl_end(tl_slot);
 }
 
 __global__ void k_dp_wait(const float* my_base, int world, int64_t flag_off, const int32_t* __restrict__ epoch_dev) {

@@ -232,8 +232,12 @@ def adam_dense(p, m, v, g_parts, n_parts, part_stride, hp):
     LAUNCHES[0] += 1
 
 
-def adam_table(table, m, v, rec_keys, rec_grads, n_seg, seg_len, key_seg_stride, grad_seg_stride, head, nxt):
+def adam_table(table, m, v, rec_keys, rec_grads, n_seg, seg_len, key_seg_stride, grad_seg_stride, head, nxt, csr=None):
+    """csr = (rec_row [n_rec], csr_off [n_rows], csr [n_rec], csr_pool [1]) int32 tensors: CSR record lists (counting
+    link + dccf_adam_csr_build) instead of linked lists."""
     t = AdamTable()
+    if csr is not None:
+        t.rec_row, t.csr_off, t.csr, t.csr_pool = (ptr(x).value for x in csr)
     t.table, t.m, t.v = ptr(table).value, ptr(m).value, ptr(v).value
     t.n_rows = table.shape[0]
     t.rec_keys = ptr(rec_keys).value if rec_keys is not None else None
@@ -281,17 +285,29 @@ def make_dp_sync(world, rank, wait=(), done=(), loss=None):
     return s
 
 
+def adam_csr_build(tables):
+    """Record ids grouped by row after a counting link (dccf_adam_csr_build, 2 launches)."""
+    lib = _lib.load()
+    ta = (AdamTable * max(1, len(tables)))(*tables)
+    check(lib.dccf_adam_csr_build(ta, len(tables), stream_ptr()), 'dccf_adam_csr_build')
+    LAUNCHES[0] += 2 if any(t.n_seg * t.seg_len > 0 for t in tables) else 0
+
+
 def make_link_extra(stage=None, prefetch_user=None, prefetch_item=None, prefetch_feat=None, prefetch_dense=None,
-                    sync=None, counter=None):
+                    sync=None, counter=None, rec_rows=None, epoch_global=None):
     """Extras of dccf_adam_link_ids.  stage = (epoch_ptrs_dev, cursor_dev, X_out, si_out, counter): the batch is read
     from a device-resident epoch (replaces dccf_stage_batch).  prefetch_user / prefetch_item = up to three [rows, D]
     tensors each (parameter, exp_avg, exp_avg_sq), prefetch_feat = Feat, prefetch_dense = up to four tensors: what the
-    step will touch, requested into L2 ahead of its use."""
+    step will touch, requested into L2 ahead of its use.  epoch_global = (epoch_ptrs_dev with six slots, cursor_dev): the
+    data-parallel link reads every rank's ids of the current batch from an epoch-wide gather (no per-step id exchange)."""
     e = LinkExtra()
     if stage is not None:
         ep, cur, X_out, si_out, counter = stage
         e.epoch_ptrs_dev, e.cursor_dev = ptr(ep).value, ptr(cur).value
         e.X_out, e.sample_item_out, e.stage_counter = ptr(X_out).value, ptr(si_out).value, ptr(counter).value
+    if epoch_global is not None:        # data-parallel link from the epoch-wide gather of every rank's ids
+        ep, cur = epoch_global
+        e.epoch_ptrs_dev, e.cursor_dev = ptr(ep).value, ptr(cur).value
     for k, t in enumerate(prefetch_user or ()):
         e.pf_user[k] = ptr(t).value
     for k, t in enumerate(prefetch_item or ()):
@@ -301,6 +317,8 @@ def make_link_extra(stage=None, prefetch_user=None, prefetch_item=None, prefetch
     for k, t in enumerate(prefetch_dense or ()):
         e.pf_dense[k] = ptr(t).value
         e.pf_dense_bytes[k] = t.numel() * t.element_size()
+    if rec_rows is not None:            # counting link (CSR record lists): (rec_row_user, rec_row_item)
+        e.rec_row_user, e.rec_row_item = ptr(rec_rows[0]).value, ptr(rec_rows[1]).value
     if sync is not None:                # (data parallel) wait for the ids / hand the id buffer back inside the kernel
         e.sync = ctypes.pointer(sync)
         e._keep_sync = sync

@@ -684,32 +684,52 @@ class DCCF(DMF):
         self._check_ready()
         return FusedAdamState(self, lr=lr, l2=l2, weight_decay=l2 if weight_decay is None else weight_decay, **kw)
 
-    def _step_tables(self, rec, P, opt):
+    # record lists of the split optimizer step as CSR ranges (counting link + dccf_adam_csr_build off the critical path)
+    # instead of linked lists: DCCF_ADAM_CSR=0 restores the lists (A/B; same summation order, same bits)
+    use_csr_lists = os.environ.get('DCCF_ADAM_CSR', '1') != '0'
+
+    def _csr_bufs(self, which, n_rec, n_rows, opt):
+        if opt.__dict__.get('csr_pool') is None:
+            opt.csr_pool = torch.zeros(2, dtype=torch.int32, device=self.uid_embeddings.weight.device)
+        k = 0 if which == 'u' else 1
+        return (self._buf('rec_row_' + which, (n_rec,), torch.int32), self._buf('csr_off_' + which, (n_rows,), torch.int32),
+                self._buf('csr_' + which, (n_rec,), torch.int32), opt.csr_pool[k:k + 1])
+
+    def _step_tables(self, rec, P, opt, csr=False):
         """Descriptors of the optimizer step's tensors: the two embedding tables with their gradient records and W, b
         with their partial sums.  Data parallel: records / dW / db of every rank, read from the receive buffer of the
-        gradient exchange (static addresses, so the descriptors can be built before the exchange runs)."""
+        gradient exchange (static addresses, so the descriptors can be built before the exchange runs).  csr: record
+        lists as CSR ranges (the split step)."""
         Z, D = self.sample_num + 1, self.ui_vector_size
         W, b = self.mlp[0].weight.data, self.mlp[0].bias.data
         eu, ei = self.uid_embeddings.weight.data, self.iid_embeddings.weight.data
         ea, es = opt.exp_avg, opt.exp_avg_sq
-        local_user = kernels.adam_table(eu, ea['E_user'], es['E_user'], rec['keys_u'], rec['gu_rec'], 1, P, P, P * D,
-                                        opt.head_u, self._buf('next_u', (P,), torch.int32))
-        if 'exchange' in rec:
+        dp = 'exchange' in rec
+        world = rec['exchange'].world if dp else 1
+        n_u = (world if (dp and rec['exchange'].user_records) else 1) * P
+        n_i = world * P * Z
+        next_u, next_i = self._buf('next_u', (n_u,), torch.int32), self._buf('next_i', (n_i,), torch.int32)
+        csr_u = self._csr_bufs('u', n_u, eu.shape[0], opt) if csr else None
+        csr_i = self._csr_bufs('i', n_i, ei.shape[0], opt) if csr else None
+        if dp:
             ex = rec['exchange']
-            world, rseg, dseg = ex.world, ex.seg_of('gi'), ex.seg_of('gW')
-            user = local_user if not ex.user_records else \
-                kernels.adam_table(eu, ea['E_user'], es['E_user'], ex.recv_part('keys_u'), ex.recv_part('gu'), world, P,
-                                   rseg, rseg, opt.head_u, self._buf('next_u', (world * P,), torch.int32))
+            rseg, dseg = ex.seg_of('gi'), ex.seg_of('gW')
+            if ex.user_records:
+                user = kernels.adam_table(eu, ea['E_user'], es['E_user'], ex.recv_part('keys_u'), ex.recv_part('gu'), world, P,
+                                          rseg, rseg, opt.head_u, next_u, csr=csr_u)
+            else:
+                user = kernels.adam_table(eu, ea['E_user'], es['E_user'], rec['keys_u'], rec['gu_rec'], 1, P, P, P * D,
+                                          opt.head_u, next_u, csr=csr_u)
             tables = [user,
                       kernels.adam_table(ei, ea['E_item'], es['E_item'], ex.recv_part('keys_i'), ex.recv_part('gi'),
-                                         world, P * Z, rseg, rseg, opt.head_i,
-                                         self._buf('next_i', (world * P * Z,), torch.int32))]
+                                         world, P * Z, rseg, rseg, opt.head_i, next_i, csr=csr_i)]
             dense = [kernels.adam_tensor(W, ea['W'], es['W'], ex.recv_part('gW'), world, dseg),
                      kernels.adam_tensor(b, ea['b'], es['b'], ex.recv_part('gb'), world, dseg)]
             return tables, dense
-        tables = [local_user,
+        tables = [kernels.adam_table(eu, ea['E_user'], es['E_user'], rec['keys_u'], rec['gu_rec'], 1, P, P, P * D,
+                                     opt.head_u, next_u, csr=csr_u),
                   kernels.adam_table(ei, ea['E_item'], es['E_item'], rec['keys_i'], rec['gi_rec'], 1, P * Z, P * Z,
-                                     P * Z * D, opt.head_i, self._buf('next_i', (P * Z,), torch.int32))]
+                                     P * Z * D, opt.head_i, next_i, csr=csr_i)]
         dense = [kernels.adam_tensor(W, ea['W'], es['W'], rec['gW_part'], rec['n_splits'], W.numel()),
                  kernels.adam_tensor(b, ea['b'], es['b'], rec['gb_part'], rec['n_splits'], b.numel())]
         return tables, dense
@@ -786,8 +806,12 @@ class DCCF(DMF):
     # items' feature rows, W with its moments and operand images): DCCF_L2_PREFETCH=0 switches it off (A/B)
     l2_prefetch = os.environ.get('DCCF_L2_PREFETCH', '1') != '0'
     dp_fold_sync = os.environ.get('DCCF_DP_FOLD', '1') != '0'
+    # data-parallel training over a device-resident epoch: every rank's ids of the WHOLE epoch (chunk) are all-gathered
+    # once, outside the steps, so no step waits for an id exchange (DCCF_DP_EPOCH_IDS=0: one id exchange per step)
+    dp_epoch_ids = os.environ.get('DCCF_DP_EPOCH_IDS', '1') != '0'
 
-    def _fused_split_step(self, call, loss_mode, Y, opt, hp, w_image_valid, overlap, counters=None, stage=None):
+    def _fused_split_step(self, call, loss_mode, Y, opt, hp, w_image_valid, overlap, counters=None, stage=None,
+                          epoch_ids=None):
         """Forward + loss + backward + optimizer with the optimizer split around the backward.  overlap=True: the
         sweep of the untouched rows goes to a side stream (forked from / joined to the current stream with events,
         so it is also legal under CUDA-graph capture).  Data parallel: the ranks first gather each other's ids
@@ -797,7 +821,8 @@ class DCCF(DMF):
         P, N = call['P'], call['N']
         D, F = self.ui_vector_size, self.feature_embedding.shape[1]
         rec = self._rec_buffers(call, loss_mode, kernels.train_bwd_splits(N, F))
-        tables, dense = self._step_tables(rec, P, opt)
+        csr = self.use_csr_lists
+        tables, dense = self._step_tables(rec, P, opt, csr=csr)
         world = rec['exchange'].world if 'exchange' in rec else 1
         next_u = self._buf('next_u', ((world if ('exchange' in rec and rec['exchange'].user_records) else 1) * P,), torch.int32)
         next_i = self._buf('next_i', (world * P * (self.sample_num + 1),), torch.int32)
@@ -820,12 +845,18 @@ class DCCF(DMF):
         W = self.mlp[0].weight.data
         pf_user = (eu, opt.exp_avg['E_user'], opt.exp_avg_sq['E_user']) if self.l2_prefetch else None
         pf_item = (ei, opt.exp_avg['E_item'], opt.exp_avg_sq['E_item']) if self.l2_prefetch else None
+        rec_rows = (self._ws['rec_row_u'], self._ws['rec_row_i']) if csr else None      # (allocated by _step_tables)
         extra = None
-        if not dp and (self.l2_prefetch or stage is not None):
+        if not dp and (self.l2_prefetch or stage is not None or csr):
             extra = kernels.make_link_extra(
-                stage=stage, prefetch_user=pf_user, prefetch_item=pf_item,
+                stage=stage, prefetch_user=pf_user, prefetch_item=pf_item, rec_rows=rec_rows,
                 prefetch_feat=self.feature_embedding if self.l2_prefetch else None,
                 prefetch_dense=(wimg, W, opt.exp_avg['W'], opt.exp_avg_sq['W']) if self.l2_prefetch else None)
+        elif dp and (stage is not None or self.l2_prefetch):
+            # data parallel: the local launch stages the batch (device-resident epoch) and evaluates the exposure softmax;
+            # the record lists of the GLOBAL step are linked on the side stream
+            extra = kernels.make_link_extra(stage=stage, prefetch_feat=self.feature_embedding if self.l2_prefetch else None,
+                                            prefetch_dense=(wimg,) if self.l2_prefetch else None)
         kernels.adam_link_ids(self._dims(), call['X'], call['sample_item'], opt.head_u, next_u, opt.head_i, next_i,
                               self._expo(), expo_e, expo_den, n_seg=0 if dp else 1, extra=extra)
 
@@ -838,16 +869,22 @@ class DCCF(DMF):
             # data parallel: every rank's ids, then the record lists of the GLOBAL step
             pf = dict(prefetch_user=pf_user, prefetch_item=pf_item,
                       prefetch_dense=(W, opt.exp_avg['W'], opt.exp_avg_sq['W'])) if self.l2_prefetch else {}
+            if epoch_ids is not None:
+                # every rank's ids of the whole epoch were gathered once (begin_resident_epoch): no id exchange in the step
+                kernels.adam_link_ids(self._dims(), None, None, opt.head_u, next_u, opt.head_i, next_i, n_pairs=P,
+                                      n_seg=ex.world, seg_stride=0, user_seg=-1 if ex.user_records else ex.rank,
+                                      extra=kernels.make_link_extra(epoch_global=epoch_ids, rec_rows=rec_rows, **pf))
+                return
             if fold:
                 ix.push()
                 if opt.__dict__.get('link_counter') is None:
                     opt.link_counter = torch.zeros(1, dtype=torch.int32, device=eu.device)
                 ids = ix.recv.view(torch.int64)
                 extra_g = kernels.make_link_extra(sync=kernels.make_dp_sync(ix.world, ix.rank, wait=(ix,), done=(ix,)),
-                                                  counter=opt.link_counter, **pf)
+                                                  counter=opt.link_counter, rec_rows=rec_rows, **pf)
             else:
                 ids = ix.exchange().view(torch.int64)
-                extra_g = kernels.make_link_extra(**pf) if pf else None
+                extra_g = kernels.make_link_extra(rec_rows=rec_rows, **pf) if (pf or csr) else None
             kernels.adam_link_ids(self._dims(), ids, ids[ix.si_off_i64:], opt.head_u, next_u, opt.head_i, next_i,
                                   n_pairs=P, n_seg=ix.world, seg_stride=ix.seg_i64,
                                   user_seg=-1 if ex.user_records else ix.rank, extra=extra_g)
@@ -865,10 +902,21 @@ class DCCF(DMF):
             with torch.cuda.stream(side):
                 if dp:                      # the id exchange waits for the peers: never on the critical path
                     link_global()
-                kernels.adam_untouched(tables, hp, self._sweep_threads(dp))
-                if dp and not fold:
+                if csr:
+                    linked = torch.cuda.Event()
+                    linked.record(side)
+                kernels.adam_untouched(tables, hp, self._sweep_threads(dp and epoch_ids is None))
+                if dp and not fold and epoch_ids is None:
                     ix.done()
                 done.record(side)
+            if csr:
+                # the CSR ranges of the step's record lists: two small launches on the third stream, beside the sweep
+                # and the forward (the touched-row sweep that needs them runs after the backward)
+                csr_done = torch.cuda.Event()
+                ship.wait_event(linked)
+                with torch.cuda.stream(ship):
+                    kernels.adam_csr_build(tables)
+                    csr_done.record(ship)
             if dp:
                 mid_done, shipped = torch.cuda.Event(), torch.cuda.Event()
 
@@ -885,8 +933,10 @@ class DCCF(DMF):
         else:
             if dp:
                 link_global()
-            kernels.adam_untouched(tables, hp, self._sweep_threads(dp))
-            if dp and not fold:
+            kernels.adam_untouched(tables, hp, self._sweep_threads(dp and epoch_ids is None))
+            if csr:
+                kernels.adam_csr_build(tables)
+            if dp and not fold and epoch_ids is None:
                 ix.done()
         pred, rec = self._launch_fwd_bwd(call, loss_mode, Y, rec=rec, w_image_valid=w_image_valid, expo_e=expo_e,
                                          expo_den=expo_den, between=between)
@@ -907,6 +957,8 @@ class DCCF(DMF):
                                             loss=(ex.dense.recv[a_loss:], ex.dense.seg, ex.world, total))
         if overlap:
             main.wait_event(done)
+            if csr:
+                main.wait_event(csr_done)
         step_dev, offset_dev = counters if counters is not None else (None, None)
         kernels.adam_touched(tables, dense, hp, True, wimg, 0, D + F, opt.cta_counter, step_dev, offset_dev, sync=sync)
         if dp:
@@ -980,7 +1032,7 @@ class DCCF(DMF):
              'step_dev': torch.zeros(1, dtype=torch.int32, device=dev),
              'offset_dev': torch.zeros(1, dtype=torch.int64, device=dev), 'synced': None}
         if staged:
-            g['epoch_ptrs'] = torch.zeros(2, dtype=torch.int64, device=dev)
+            g['epoch_ptrs'] = torch.zeros(6, dtype=torch.int64, device=dev)     # [X, si, X_all, si_all, stride_X, stride_si]
             g['cursor'] = torch.zeros(1, dtype=torch.int64, device=dev)
             g['stage_counter'] = torch.zeros(1, dtype=torch.int32, device=dev)
         if self._dp is not None and self._split_step_ok(0 if rank_mode == 1 else 1, P):
@@ -1005,7 +1057,9 @@ class DCCF(DMF):
             split = self._split_step_ok(loss_mode, P)
             # a batch read from a device-resident epoch: fetched by k_link_ids itself on one GPU (each linking thread
             # copies the id it links), by a launch of its own otherwise (the id exchange pushes the staged buffers)
-            stage_in_link = staged and split and self._dp is None
+            # the id exchange pushes the staged buffers; with the epoch-wide id gather (dp_epoch_ids) there is none)
+            epoch_ids = staged and split and self._dp is not None and self.dp_epoch_ids
+            stage_in_link = staged and split and (self._dp is None or epoch_ids)
             if staged and not stage_in_link:
                 kernels.stage_batch(g['epoch_ptrs'], g['cursor'], P, S, g['X'], g['si'])
             if split:
@@ -1013,8 +1067,10 @@ class DCCF(DMF):
                 stage = None
                 if stage_in_link:
                     stage = (g['epoch_ptrs'], g['cursor'], g['X'], g['si'], g['stage_counter'])
+                g['epoch_ids'] = bool(epoch_ids)
                 pred, loss = self._fused_split_step(call, loss_mode, Yg, opt, hp, True, overlap=True,
-                                                    counters=(g['step_dev'], g['offset_dev']), stage=stage)
+                                                    counters=(g['step_dev'], g['offset_dev']), stage=stage,
+                                                    epoch_ids=(g['epoch_ptrs'], g['cursor']) if epoch_ids else None)
                 g['w_image'] = True     # loss: the step's own output buffer (valid until the next train_step)
             else:
                 if self._fused_step_ok(loss_mode):
@@ -1155,9 +1211,22 @@ class DCCF(DMF):
             state['first'] = first
             graphs[key] = self._build_step_graph(P, 1, p_drop, opt, staged=True)
         g = graphs[key]
-        g['epoch_ptrs'].copy_(torch.tensor([X_epoch.data_ptr(), sample_epoch.data_ptr()], dtype=torch.int64))
+        X_epoch, sample_epoch = X_epoch.contiguous(), sample_epoch.contiguous()
+        ptrs = [X_epoch.data_ptr(), sample_epoch.data_ptr(), 0, 0, 0, 0]
+        keep = [X_epoch, sample_epoch]
+        if g.get('epoch_ids'):
+            # every rank's batches of this epoch (chunk), gathered ONCE: [world, n, P, 2] / [world, n, P, S]
+            import torch.distributed as dist
+            world = self._dp['world']
+            X_all = torch.empty((world,) + tuple(X_epoch.shape), dtype=torch.int64, device=X_epoch.device)
+            si_all = torch.empty((world,) + tuple(sample_epoch.shape), dtype=torch.int64, device=X_epoch.device)
+            dist.all_gather_into_tensor(X_all, X_epoch, group=self._dp['group'])
+            dist.all_gather_into_tensor(si_all, sample_epoch, group=self._dp['group'])
+            ptrs[2:] = [X_all.data_ptr(), si_all.data_ptr(), X_epoch.numel(), sample_epoch.numel()]
+            keep += [X_all, si_all]
+        g['epoch_ptrs'].copy_(torch.tensor(ptrs, dtype=torch.int64))
         g['cursor'].fill_(state['next'])
-        g['keep'] = (X_epoch, sample_epoch)                 # the graph reads these buffers: keep them alive
+        g['keep'] = tuple(keep)                             # the graph reads these buffers: keep them alive
 
         def step():
             if state['next'] >= n:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 31
+#define DCCF_ABI_VERSION 32
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -258,6 +258,13 @@ typedef struct dccf_adam_table {
     int32_t n_seg; int32_t _pad;
     int64_t seg_len, key_seg_stride, grad_seg_stride;
     int32_t* head; int32_t* next;      /* next: n_seg*seg_len entries, private to this table */
+    /* CSR record lists (all four NULL: linked lists through head / next).  With them dccf_adam_link_ids COUNTS instead of
+     * linking — head[row] = (records of the row) - 1, next[r] = arrival position of record r in its row, rec_row[r] = the
+     * row — dccf_adam_csr_build groups the record ids by row (csr_off [n_rows], csr [n_seg*seg_len]; csr_pool: one
+     * int32, zero between steps), and dccf_adam_touched reads a row's records with parallel loads instead of walking
+     * a list (the walk of the hottest item's list was the critical path of the data-parallel step).  Same summation
+     * order (ascending record index), same bits. */
+    int32_t* rec_row; int32_t* csr_off; int32_t* csr; int32_t* csr_pool;
 } dccf_adam_table;
 typedef struct dccf_adam_tensor {
     float* p; float* m; float* v;
@@ -334,6 +341,7 @@ typedef struct dccf_link_extra {
     const float* pf_feat;        /* Feat [n_items, feat_dim] */
     const void* pf_dense[4]; int64_t pf_dense_bytes[4];
     const dccf_dp_sync* sync;    /* HOST pointer, copied at launch */
+    int32_t* rec_row_user; int32_t* rec_row_item;   /* counting mode (CSR lists, see dccf_adam_table): both non-NULL */
 } dccf_link_extra;
 int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const int64_t* sample_item, int64_t n_pairs,
                        int32_t n_seg, int64_t seg_stride, int32_t user_seg, int32_t* head_user, int32_t* next_user,
@@ -342,6 +350,8 @@ int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const int64_t* s
                        const dccf_link_extra* extra, void* stream);
 int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam* hp,
                         int32_t threads_per_cta, void* stream);
+/* Between dccf_adam_link_ids (counting mode) and dccf_adam_touched, any stream: record ids grouped by row (2 launches). */
+int dccf_adam_csr_build(const dccf_adam_table* tables, int32_t n_tables, void* stream);
 int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
                       int32_t n_dense, const dccf_adam* hp, int32_t already_linked, float* w_image,
                       int32_t w_image_tensor, int32_t w_image_K, int32_t* cta_counter, int32_t* advance_step_dev,
@@ -357,10 +367,11 @@ int dccf_stage_batch(const uint64_t* epoch_ptrs_dev, int64_t* cursor_dev, int64_
 int dccf_state_advance(int32_t* step_dev, uint64_t* offset_dev, uint64_t offset_inc, void* stream);
 
 /* ---- debug ------------------------------------------------------------------------------- */
-/* Install (or remove, with NULL) a device buffer of 2 x 12 uint64 slots in which the kernels of the fused training
+/* Install (or remove, with NULL) a device buffer of 2 x 16 uint64 slots in which the kernels of the fused training
  * step record {earliest CTA start, latest CTA end} in nanoseconds of %globaltimer: slot 0 k_link_ids,
  * 1 k_adam_untouched, 2 k_train_fwd_tc, 3 k_train_mid, 4 k_train_bwd_tc, 5 k_adam_touched, 6 k_stage_batch,
- * 8 k_dp_push, 9 k_dp_wait (first start / last end over the exchanges of the step).
+ * 8 k_dp_push (ids), 9 k_dp_wait, 10 k_dp_push (records), 11 k_dp_push (dW / db / loss), 12 the moment the peers'
+ * segments had arrived in k_adam_touched, 13 k_csr_build.
  * The caller initialises every slot to {UINT64_MAX, 0} (tools/step_timeline.py).  One entry point per
  * translation unit that owns instrumented kernels. */
 int dccf_debug_timeline_train(unsigned long long* slots);

@@ -831,6 +831,37 @@ def test_fused_adam_step_record_lists():
     assert rel_err(res[0][0], want_p) < 1e-5 and rel_err(res[0][3], want_W) < 1e-5
 
 
+def test_csr_record_lists_equal_linked_lists_with_hot_rows():
+    """The split optimizer step with CSR record lists (counting link + dccf_adam_csr_build) against the same step with
+    linked lists: rows with 1, a few, ~100 and > 700 records (the hot item of every slot of 64 pairs — beyond the
+    shared-memory ranking buffer), eager and CUDA-graph replay: identical bits (same summation order)."""
+    U, I, F, P, S, A = 50, 60, 128, 128, 10, 2
+    params, X, si, _, _ = random_problem(31, U, I, F, P, S, A, 0.1, 0.2)
+    si[:64, :] = 7                          # 640 confounder slots on item 7
+    X[:64, 1] = 7                           # + 64 true-item slots
+    si[64:, :3] = 11                        # ~190 records on item 11
+    X[:10, 0] = 3                           # a user with many pairs
+    X[64:74, 0] = 3
+    outs = []
+    for csr in (True, False):
+        model = make_model(params, S, A, 0.1)
+        model.use_csr_lists = csr
+        model.optimizer = model.make_fused_optimizer(lr=1e-3, l2=1e-4)
+        for t in range(4):                  # step 1 eager, step 2 captures, steps 3-4 replay the graph
+            fd = {'X': torch.from_numpy(np.roll(X, t, axis=0).copy()).cuda(), 'rank': 1, 'train': True, 'dropout': 0.2,
+                  'Y': torch.zeros(P).cuda(), 'sample_item': torch.from_numpy(np.roll(si, t, axis=0).copy())}
+            out = model.train_step(fd)
+        torch.cuda.synchronize()
+        model.check_ids()
+        assert int((model.optimizer.head_i != -1).sum()) == 0 and int((model.optimizer.head_u != -1).sum()) == 0
+        if csr:
+            assert int(model.optimizer.csr_pool.abs().sum()) == 0          # the ranges were released
+        outs.append((model_params(model), float(out['loss'])))
+    for k in outs[0][0]:
+        assert np.array_equal(outs[0][0][k], outs[1][0][k]), k
+    assert outs[0][1] == outs[1][1]
+
+
 def test_fused_training_follows_the_reference_at_config0(tmp_path):
     """BASELINE.json configs[0] at full size on the GPU: the first 24 training steps of the UNMODIFIED reference
     (tests/golden/config0_train.npz) replayed through model.train_step — 256 pairs = 5 632 predictor rows x 832 inputs
