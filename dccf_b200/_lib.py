@@ -56,7 +56,8 @@ class AdamTable(ctypes.Structure):
 
 
 class DpChannel(ctypes.Structure):
-    _fields_ = [('peer_bases', ctypes.c_uint64 * 8), ('flag_off', ctypes.c_int64), ('epoch_dev', ctypes.c_void_p)]
+    _fields_ = [('peer_bases', ctypes.c_uint64 * 8), ('flag_off', ctypes.c_int64), ('epoch_dev', ctypes.c_void_p),
+                ('seg_floats', ctypes.c_int64)]
 
 
 class DpSync(ctypes.Structure):
@@ -141,7 +142,8 @@ _SIGNATURES = {
     'dccf_dp_push_fold': (ctypes.c_int, [_P, ctypes.c_int64, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, _P, _P,
                                          _P, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                          _P, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _P]),
-    'dccf_dp_wait': (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int64, _P, _P]),
+    'dccf_dp_wait': (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, _P, _P]),
+    'dccf_dp_flag_floats': (ctypes.c_int64, []),
     'dccf_dp_done': (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, _P, _P]),
     'dccf_full_scores_splits': (ctypes.c_int32, [ctypes.c_int32, ctypes.c_int32]),
     'dccf_full_scores': (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P, _P, ctypes.c_float, _P,

@@ -810,6 +810,7 @@ static int marshal_sync(const char* who, const dccf_dp_sync* in, DpSync* out) {
             for (int p = 0; p < DP_MAX_WORLD; ++p) dst[w]->base[p] = (used[w] && p < in->world) ? reinterpret_cast<float*>(src[w]->peer_bases[p]) : nullptr;
             dst[w]->flag_off = used[w] ? src[w]->flag_off : 0;
             dst[w]->epoch_dev = used[w] ? src[w]->epoch_dev : nullptr;
+            dst[w]->n_ctas = used[w] ? dp_push_ctas(src[w]->seg_floats) : 0;
             if (used[w]) {
                 DCCF_CHECK_ARG(src[w]->epoch_dev != nullptr, "%s: sync: channel %d has no epoch counter", who, k);
                 for (int p = 0; p < in->world; ++p) DCCF_CHECK_ARG(src[w]->peer_bases[p] != 0, "%s: sync: channel %d peer %d is null", who, k, p);
@@ -1008,7 +1009,8 @@ extern "C" int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const
     const bool staged = extra != nullptr && extra->epoch_ptrs_dev != nullptr;
     DCCF_CHECK_ARG(dims && (X || staged) && head_user && next_user && head_item && next_item, "dccf_adam_link_ids: null argument");
     DCCF_CHECK_ARG(dims->n_samples == 0 || sample_item || staged, "dccf_adam_link_ids: sample_item is null");
-    DCCF_CHECK_ARG(n_seg >= 0 && (n_seg <= 1 || seg_stride > 0) && (n_seg == 0 || user_seg < n_seg), "dccf_adam_link_ids: bad segment layout");
+    const bool epoch_link = staged && extra->X_out == nullptr;      // segments come from the epoch-wide gather (strides in device memory)
+    DCCF_CHECK_ARG(n_seg >= 0 && (n_seg <= 1 || seg_stride > 0 || epoch_link) && (n_seg == 0 || user_seg < n_seg), "dccf_adam_link_ids: bad segment layout");
     DCCF_CHECK_ARG(n_seg > 0 || expo != nullptr || staged, "dccf_adam_link_ids: nothing to do (n_seg == 0 and no exposure source)");
     DCCF_CHECK_ARG(n_pairs * n_seg * (dims->n_samples + 1) < ((int64_t)1 << 31), "dccf_adam_link_ids: too many records");
     DCCF_CHECK_ARG(expo == nullptr || (expo_e && expo_den), "dccf_adam_link_ids: expo needs expo_e and expo_den");

@@ -38,87 +38,79 @@ __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send,
     // debug timeline slot by what is pushed: 8 ids (small segment), 10 gradient records, 11 dW / db / loss (folded partials)
     const int tl_slot = folds.n > 0 ? 11 : (seg < 16384 ? 8 : 10);
     tl_begin(tl_slot);
+    (void)cta_counter;
     const int32_t epoch = __ldg(epoch_dev) + 1;
-    if (threadIdx.x < world) {
-        // peers have finished reading what this rank pushed last step
-        const int32_t* consumed = reinterpret_cast<const int32_t*>(peers.base[rank] + flag_off) + DP_MAX_WORLD;
-        spin_until(consumed + threadIdx.x, epoch - 1);
-    }
-    __syncthreads();
     const int64_t n4 = seg >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const float4* src = reinterpret_cast<const float4*>(send);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        float4 v;
-        int which = -1;
-        for (int k = 0; k < folds.n; ++k)
-            if (i >= folds.f[k].off4 && i < folds.f[k].off4 + folds.f[k].n4) which = k;
-        if (which < 0) {
-            v = src[i];
-        } else {
-            const DpFold& f = folds.f[which];
-            const float* pp = f.parts + (i - f.off4) * 4;
-            v = make_float4(0.f, 0.f, 0.f, 0.f);
-            int32_t q = 0;
-            for (; q + 8 <= f.n_parts; q += 8) {       // eight loads in flight, added in ascending order
-                float4 t8[8];
+    // What this thread ships is read (or folded from the partial buffers) BEFORE the wait for the peers' consumed flags:
+    // the flag round trip hides behind the loads.  A thread owns at most DP_PER_THREAD float4 (a segment is at most
+    // 148 x 256 x DP_PER_THREAD float4 = 2.4 MB; longer segments take the loop below one batch at a time).
+    constexpr int DP_PER_THREAD = 4;
+    bool waited = false;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4 || !waited; i0 += stride * DP_PER_THREAD) {
+        float4 v[DP_PER_THREAD];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) t8[j] = __ldg(reinterpret_cast<const float4*>(pp + (size_t)(q + j) * f.stride));
+        for (int q = 0; q < DP_PER_THREAD; ++q) {
+            const int64_t i = i0 + q * stride;
+            if (i >= n4) continue;
+            int which = -1;
+            for (int k = 0; k < folds.n; ++k)
+                if (i >= folds.f[k].off4 && i < folds.f[k].off4 + folds.f[k].n4) which = k;
+            if (which < 0) {
+                v[q] = src[i];
+            } else {
+                const DpFold& f = folds.f[which];
+                const float* pp = f.parts + (i - f.off4) * 4;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                int32_t p8 = 0;
+                for (; p8 + 8 <= f.n_parts; p8 += 8) {       // eight loads in flight, added in ascending order
+                    float4 t8[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { v.x += t8[j].x; v.y += t8[j].y; v.z += t8[j].z; v.w += t8[j].w; }
+                    for (int j = 0; j < 8; ++j) t8[j] = __ldg(reinterpret_cast<const float4*>(pp + (size_t)(p8 + j) * f.stride));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { a.x += t8[j].x; a.y += t8[j].y; a.z += t8[j].z; a.w += t8[j].w; }
+                }
+                for (; p8 < f.n_parts; ++p8) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(pp + (size_t)p8 * f.stride));
+                    a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+                }
+                v[q] = a;
             }
-            for (; q < f.n_parts; ++q) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(pp + (size_t)q * f.stride));
-                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        if (!waited) {
+            // peers have finished reading what this rank pushed last step (checked once per CTA, after the first loads)
+            if ((int)threadIdx.x < world) {
+                const int32_t* consumed = reinterpret_cast<const int32_t*>(peers.base[rank] + flag_off) + DP_FLAG_CONSUMED;
+                spin_until(consumed + threadIdx.x, epoch - 1);
             }
+            __syncthreads();
+            waited = true;
         }
-        for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(peers.base[p] + (int64_t)rank * seg)[i] = v;
+#pragma unroll
+        for (int q = 0; q < DP_PER_THREAD; ++q) {
+            const int64_t i = i0 + q * stride;
+            if (i >= n4) continue;
+            for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(peers.base[p] + (int64_t)rank * seg)[i] = v[q];
+        }
     }
-    // one system-scope fence per CTA, by the thread that publishes the CTA's arrival, after the CTA barrier has
-    // ordered every thread's stores before it (a fence in each of the 13 K threads made the push take ~17 us)
+    // Arrival: ONE flag per (source rank, source CTA) on every peer, published by `world` lanes of the CTA with a release
+    // store each — the CTA barrier orders every thread's data stores before them and release is cumulative, so a peer
+    // that observes the flag observes the CTA's data.  No grid-wide counter, no second fence: the round-1 protocol
+    // (fence, atomic counter, last CTA fences again and writes the flags one after the other) cost 8-14 us per push
+    // whatever its size; this is one drain of the CTA's remote stores.  The consumer waits for all of a push's flags.
     __syncthreads();
-#ifndef DCCF_DP_SERIAL_FLAGS
-    // The last CTA publishes the arrival to the peers with one release store per LANE, not `world` release stores in
-    // sequence by one thread: each st.release.sys waits for the NVLink round trip of what precedes it, and eight of them
-    // back to back were the bulk of what a push cost whatever its size (measured on 8 x B200: 42 us between the end of
-    // the dW kernel and the start of the touched-row sweep).  Ordering: every CTA's data stores -> its barrier ->
-    // thread 0's system fence -> counter increment; the last CTA's thread 0 observes all increments, fences, and the
-    // CTA barrier below orders the publishing lanes after it (release is cumulative).
-    __shared__ int s_last;
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        const int32_t prev = atomicAdd(cta_counter, 1);
-        s_last = (prev == (int32_t)gridDim.x - 1) ? 1 : 0;
-        if (s_last) {
-            __threadfence_system();
-            *cta_counter = 0;
-        }
-    }
-    __syncthreads();
-    if (s_last && (int)threadIdx.x < world)
-        st_release_sys(reinterpret_cast<int32_t*>(peers.base[threadIdx.x] + flag_off) + rank, epoch);
-#else
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        const int32_t prev = atomicAdd(cta_counter, 1);
-        if (prev == (int32_t)gridDim.x - 1) {
-            __threadfence_system();
-            for (int p = 0; p < world; ++p)
-                st_release_sys(reinterpret_cast<int32_t*>(peers.base[p] + flag_off) + rank, epoch);
-            *cta_counter = 0;
-        }
-    }
-#endif
+    if ((int)threadIdx.x < world)
+        st_release_sys(reinterpret_cast<int32_t*>(peers.base[threadIdx.x] + flag_off) + rank * DP_MAX_CTAS + blockIdx.x, epoch);
     tl_end(tl_slot);
 }
 
-__global__ void k_dp_wait(const float* my_base, int world, int64_t flag_off, const int32_t* __restrict__ epoch_dev) {
+__global__ void k_dp_wait(const float* my_base, int world, int64_t flag_off, const int32_t* __restrict__ epoch_dev, int n_ctas) {
     tl_begin(9);
     const int32_t epoch = __ldg(epoch_dev) + 1;
-    if ((int)threadIdx.x < world) {
-        const int32_t* arrival = reinterpret_cast<const int32_t*>(my_base + flag_off);
-        spin_until(arrival + threadIdx.x, epoch);
-    }
+    const int32_t* arrival = reinterpret_cast<const int32_t*>(my_base + flag_off);
+    for (int i = threadIdx.x; i < world * n_ctas; i += blockDim.x)
+        spin_until(arrival + (i / n_ctas) * DP_MAX_CTAS + (i % n_ctas), epoch);
     __syncthreads();
     tl_end(9);
 }
@@ -127,7 +119,7 @@ __global__ void k_dp_done(DpPeers peers, int world, int rank, int64_t flag_off, 
     const int32_t epoch = *epoch_dev + 1;
     __syncthreads();
     if ((int)threadIdx.x < world)
-        st_release_sys(reinterpret_cast<int32_t*>(peers.base[threadIdx.x] + flag_off) + DP_MAX_WORLD + rank, epoch);
+        st_release_sys(reinterpret_cast<int32_t*>(peers.base[threadIdx.x] + flag_off) + DP_FLAG_CONSUMED + rank, epoch);
     __syncthreads();
     if (threadIdx.x == 0) *epoch_dev = epoch;
 }
@@ -162,8 +154,7 @@ static int dp_push_impl(const float* send, int64_t seg_floats, const uint64_t* p
     DCCF_CHECK_ARG(send && epoch_dev && cta_counter, "dccf_dp_push: null buffer");
     DCCF_CHECK_ARG(seg_floats > 0 && seg_floats % 4 == 0, "dccf_dp_push: segment length must be a positive multiple of 4 floats");
     DCCF_CHECK_ARG(rank >= 0 && rank < world, "dccf_dp_push: rank %d outside [0,%d)", rank, world);
-    int64_t ctas = (seg_floats / 4 + 255) / 256;
-    if (ctas > 148) ctas = 148;
+    const int64_t ctas = dp_push_ctas(seg_floats);
     static PerDeviceOnce carve_once;      // (same carveout as its neighbours in the step, see dccf_adam_link_ids)
     if (carve_once.need()) {
         cudaFuncSetAttribute(k_dp_push, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -206,9 +197,12 @@ extern "C" int dccf_dp_push_fold(const float* send, int64_t seg_floats, const ui
                         (cudaStream_t)stream_);
 }
 
-extern "C" int dccf_dp_wait(const float* my_base, int32_t world, int64_t flag_off, const int32_t* epoch_dev, void* stream_) {
-    DCCF_CHECK_ARG(my_base && epoch_dev && world >= 1 && world <= DP_MAX_WORLD, "dccf_dp_wait: bad argument");
-    k_dp_wait<<<1, 32, 0, (cudaStream_t)stream_>>>(my_base, world, flag_off, epoch_dev);
+extern "C" int64_t dccf_dp_flag_floats(void) { return DP_FLAG_WORDS; }
+
+extern "C" int dccf_dp_wait(const float* my_base, int64_t seg_floats, int32_t world, int64_t flag_off, const int32_t* epoch_dev,
+                            void* stream_) {
+    DCCF_CHECK_ARG(my_base && epoch_dev && world >= 1 && world <= DP_MAX_WORLD && seg_floats > 0, "dccf_dp_wait: bad argument");
+    k_dp_wait<<<1, 256, 0, (cudaStream_t)stream_>>>(my_base, world, flag_off, epoch_dev, dp_push_ctas(seg_floats));
     DCCF_CHECK_LAUNCH("k_dp_wait");
     return DCCF_OK;
 }

@@ -7,10 +7,26 @@
 namespace dccf {
 
 constexpr int DP_MAX_WORLD = 8;
+constexpr int DP_MAX_CTAS = 148;       // CTAs of one push (one arrival flag each)
+// Flag area of a symmetric exchange buffer, in int32 words from flag_off:
+//   arrival  [DP_MAX_WORLD][DP_MAX_CTAS]   arrival[src][c] = epoch: CTA c of rank src's push of that epoch has landed here
+//   consumed [DP_MAX_WORLD]                consumed[dst]   = epoch: rank dst has finished reading what this rank pushed
+constexpr int DP_FLAG_CONSUMED = DP_MAX_WORLD * DP_MAX_CTAS;
+constexpr int DP_FLAG_WORDS = DP_FLAG_CONSUMED + DP_MAX_WORLD;
+
+__host__ __device__ inline int dp_push_ctas(int64_t seg_floats) {
+    int64_t c = (seg_floats / 4 + 255) / 256;
+    return (int)(c > DP_MAX_CTAS ? DP_MAX_CTAS : (c < 1 ? 1 : c));
+}
 
 __device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
     int32_t v;
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int32_t ld_relaxed_sys(const int32_t* p) {
+    int32_t v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
@@ -29,8 +45,9 @@ __device__ __forceinline__ void spin_until(const int32_t* p, int32_t want) {
 // device-side image of dccf_dp_sync (include/dccf_b200.h)
 struct DpChannel {
     float* base[DP_MAX_WORLD];   // the symmetric buffer on every rank (own at index rank)
-    int64_t flag_off;            // floats: [arrival int32[8] | consumed int32[8]] start here
+    int64_t flag_off;            // floats: the flag area (see DP_FLAG_*) starts here
     int32_t* epoch_dev;          // completed exchanges on this channel
+    int32_t n_ctas;              // CTAs of every rank's push on this channel (dp_push_ctas of its segment)
 };
 struct DpSync {
     int32_t world, rank, n_wait, n_done;
@@ -42,16 +59,25 @@ struct DpSync {
     float* loss_out;
 };
 
-// Prologue of a consumer CTA: every peer's segment of the current exchange has arrived on all wait channels.
-// Call from all threads of the CTA (contains a barrier).
+// Prologue of a consumer CTA: every CTA of every rank's push of the current exchange has landed, on all wait channels.
+// The flags are polled with relaxed loads (independent, all in flight together), one system-scope fence then orders
+// the CTA's later reads after them.  Call from all threads of the CTA (contains a barrier).
 __device__ __forceinline__ void dp_wait_inline(const DpSync& s) {
     if (s.n_wait > 0) {
-        const int t = threadIdx.x;
-        if (t < s.n_wait * s.world) {
-            const DpChannel& c = s.wait[t / s.world];
-            const int32_t* arrival = reinterpret_cast<const int32_t*>(c.base[s.rank] + c.flag_off);
-            spin_until(arrival + (t % s.world), __ldg(c.epoch_dev) + 1);
+        const unsigned long long t0 = global_ns();
+        for (int c = 0; c < s.n_wait; ++c) {
+            const DpChannel& ch = s.wait[c];
+            const int32_t want = __ldg(ch.epoch_dev) + 1;
+            const int32_t* arrival = reinterpret_cast<const int32_t*>(ch.base[s.rank] + ch.flag_off);
+            const int total = s.world * ch.n_ctas;
+            for (int i = threadIdx.x; i < total; i += blockDim.x) {
+                const int32_t* p = arrival + (i / ch.n_ctas) * DP_MAX_CTAS + (i % ch.n_ctas);
+                while (ld_relaxed_sys(p) < want) {
+                    if (global_ns() - t0 > 60ull * 1000000000ull) __trap();      // a peer died: fail loudly (see spin_until)
+                }
+            }
         }
+        __threadfence_system();
         __syncthreads();
     }
 }
@@ -68,7 +94,7 @@ __device__ __forceinline__ void dp_done_inline(const DpSync& s) {
     if (t < s.n_done * s.world) {
         const DpChannel& c = s.done[t / s.world];
         const int peer = t % s.world;
-        st_release_sys(reinterpret_cast<int32_t*>(c.base[peer] + c.flag_off) + DP_MAX_WORLD + s.rank, *c.epoch_dev + 1);
+        st_release_sys(reinterpret_cast<int32_t*>(c.base[peer] + c.flag_off) + DP_FLAG_CONSUMED + s.rank, *c.epoch_dev + 1);
     }
     __syncthreads();
     if (t < s.n_done) *s.done[t].epoch_dev += 1;

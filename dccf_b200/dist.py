@@ -43,11 +43,11 @@ class SegmentExchange(object):
 
     def _init_p2p(self, device):
         """Symmetric receive buffer mapped on every peer (torch symmetric memory = CUDA VMM/IPC over NVLink):
-        [ recv: world x seg floats | arrival flags int32[8] | consumed flags int32[8] ]."""
+        [ recv: world x seg floats | flag area: an arrival flag per (source rank, CTA of its push), consumed flags ]."""
         import torch.distributed._symmetric_memory as symm
-        from . import kernels  # noqa: F401  (fail early if the library is missing)
+        from . import kernels               # (fails early if the library is missing)
         self.flag_off = self.world * self.seg
-        buf = symm.empty(self.flag_off + 16, dtype=torch.float32, device=device)
+        buf = symm.empty(self.flag_off + (kernels.dp_flag_floats() + 3) // 4 * 4, dtype=torch.float32, device=device)
         hdl = symm.rendezvous(buf, dist.group.WORLD if self.group is None else self.group)
         buf.zero_()
         torch.cuda.synchronize()
@@ -73,7 +73,7 @@ class SegmentExchange(object):
 
     def wait(self):
         from . import kernels
-        kernels.dp_wait(self.sym, self.world, self.flag_off, self.epoch_dev)
+        kernels.dp_wait(self.sym, self.seg, self.world, self.flag_off, self.epoch_dev)
 
     def exchange(self, folds=None):
         """All ranks' segments, rank-major, in self.recv.  folds (peer-memory mode only): ranges of the segment that

@@ -279,6 +279,7 @@ def make_dp_sync(world, rank, wait=(), done=(), loss=None):
                 arr[k].peer_bases[p] = int(c.peer_bases[p])
             arr[k].flag_off = int(c.flag_off)
             arr[k].epoch_dev = ptr(c.epoch_dev).value
+            arr[k].seg_floats = int(c.seg)
     if loss is not None:
         parts, stride, n, out = loss
         s.loss_parts, s.loss_stride, s.n_loss, s.loss_out = ptr(parts).value, int(stride), int(n), ptr(out).value
@@ -465,9 +466,13 @@ def dp_push_fold(send, seg, peer_bases, world, rank, flag_off, epoch_dev, cta_co
     LAUNCHES[0] += 1
 
 
-def dp_wait(my_buf, world, flag_off, epoch_dev):
+def dp_flag_floats():
+    return int(_lib.load().dccf_dp_flag_floats())
+
+
+def dp_wait(my_buf, seg, world, flag_off, epoch_dev):
     lib = _lib.load()
-    check(lib.dccf_dp_wait(ptr(my_buf), int(world), int(flag_off), ptr(epoch_dev), stream_ptr()), 'dccf_dp_wait')
+    check(lib.dccf_dp_wait(ptr(my_buf), int(seg), int(world), int(flag_off), ptr(epoch_dev), stream_ptr()), 'dccf_dp_wait')
     LAUNCHES[0] += 1
 
 

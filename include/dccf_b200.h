@@ -314,6 +314,7 @@ typedef struct dccf_dp_channel {
     uint64_t peer_bases[8];      /* device address of the buffer on every rank (this rank's own at index rank) */
     int64_t flag_off;            /* floats */
     int32_t* epoch_dev;
+    int64_t seg_floats;          /* segment length of the channel's pushes (fixes the number of arrival flags) */
 } dccf_dp_channel;
 typedef struct dccf_dp_sync {
     int32_t world, rank, n_wait, n_done;
@@ -409,14 +410,18 @@ int dccf_rank_eval_multi(const float* scores, const float* labels, const int64_t
                          double* out_sums, void* stream);
 
 /* ---- data-parallel gradient exchange over NVLink peer memory (new: the reference is single-GPU) ----- */
-/* Every rank owns a symmetric buffer of floats: [ recv: world*seg | arrival flags int32[8] | consumed flags
- * int32[8] ] mapped on all peers; peer_bases is a HOST array with its device address on each rank.
- *   dccf_dp_push: waits for the peers to have consumed the previous step, stores `send` (seg floats) into slot
- *                 `rank` of every peer's recv region with 128-bit stores, publishes the step in their arrival flags
- *   dccf_dp_wait: spins until all `world` arrival flags of this rank show the current step
+/* Every rank owns a symmetric buffer of floats: [ recv: world*seg | flag area of dccf_dp_flag_floats() words ] mapped on
+ * all peers; peer_bases is a HOST array with its device address on each rank.  Flag area: one ARRIVAL flag per (source
+ * rank, CTA of its push) + one CONSUMED flag per reader.
+ *   dccf_dp_push: stores `send` (seg floats) into slot `rank` of every peer's recv region with 128-bit stores after the
+ *                 peers have consumed the previous step; every CTA publishes its own arrival on every peer (a release
+ *                 store per peer after the CTA barrier — no grid-wide counter)
+ *   dccf_dp_wait: spins until every CTA of every rank's push of the current step has arrived (or fold it into the
+ *                 consumer kernel: dccf_dp_sync)
  *   dccf_dp_done: marks this rank's recv region as consumed on every peer and advances epoch_dev (device int32,
  *                 the number of completed exchanges; starts at 0)
- * flag_off: offset of the flag area in floats (>= world*seg, multiple of 4).  cta_counter: device int32, zero. */
+ * flag_off: offset of the flag area in floats (>= world*seg, multiple of 4).  cta_counter: unused (kept for ABI). */
+int64_t dccf_dp_flag_floats(void);
 int dccf_dp_push(const float* send, int64_t seg_floats, const uint64_t* peer_bases, int32_t world, int32_t rank,
                  int64_t flag_off, const int32_t* epoch_dev, int32_t* cta_counter, void* stream);
 /* Same as dccf_dp_push, but up to two ranges [off, off + n) (floats) of the segment are not read from `send`: they
@@ -428,7 +433,8 @@ int dccf_dp_push_fold(const float* send, int64_t seg_floats, const uint64_t* pee
                       const float* parts_a, int32_t n_parts_a, int64_t stride_a, int64_t off_a, int64_t n_a,
                       const float* parts_b, int32_t n_parts_b, int64_t stride_b, int64_t off_b, int64_t n_b,
                       void* stream);
-int dccf_dp_wait(const float* my_base, int32_t world, int64_t flag_off, const int32_t* epoch_dev, void* stream);
+int dccf_dp_wait(const float* my_base, int64_t seg_floats, int32_t world, int64_t flag_off, const int32_t* epoch_dev,
+                 void* stream);
 int dccf_dp_done(const uint64_t* peer_bases, int32_t world, int32_t rank, int64_t flag_off, int32_t* epoch_dev,
                  void* stream);
 

@@ -1,9 +1,10 @@
 #!/bin/bash
-# Round 2, GPU call D (2 GPUs): CSR record lists, epoch-wide id gather, finer exchange timeline.
+# Round 2, GPU call D/E (2 GPUs): CSR record lists, epoch-wide id gather, per-CTA arrival flags, finer exchange timeline.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 > gpurun_out/tests_r2d.log
 tail -4 gpurun_out/tests_r2d.log
 timeout 120 python tools/rank_bench.py --users 1024 16384 2>&1 | tee gpurun_out/rank_bench_r2d.json
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_rank_stream --launch-skip 10 -c 1 -f -o gpurun_out/prof_r2e_rank python tools/rank_bench.py --users 1024 > gpurun_out/ncu_r2e_rank.log 2>&1
 echo "== timeline 1 GPU"; timeout 300 python tools/step_timeline.py --steps 40 2>&1 | tail -9
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533"
 show() {
