@@ -60,24 +60,29 @@ struct DpSync {
 };
 
 // Prologue of a consumer CTA: every CTA of every rank's push of the current exchange has landed, on all wait channels.
-// The flags are polled with relaxed loads (independent, all in flight together), one system-scope fence then orders
-// the CTA's later reads after them.  Call from all threads of the CTA (contains a barrier).
+// ONE warp polls (relaxed loads, all of a lane's flags in flight together), ONE lane then issues the system-scope fence
+// that orders the CTA's later reads after the observed flags, the CTA barrier hands that order to the other warps.
+// (A first version fenced in every thread of every CTA: 87 K system fences made the consumer 16 us slower.)
+// Call from all threads of the CTA (contains a barrier).
 __device__ __forceinline__ void dp_wait_inline(const DpSync& s) {
     if (s.n_wait > 0) {
-        const unsigned long long t0 = global_ns();
-        for (int c = 0; c < s.n_wait; ++c) {
-            const DpChannel& ch = s.wait[c];
-            const int32_t want = __ldg(ch.epoch_dev) + 1;
-            const int32_t* arrival = reinterpret_cast<const int32_t*>(ch.base[s.rank] + ch.flag_off);
-            const int total = s.world * ch.n_ctas;
-            for (int i = threadIdx.x; i < total; i += blockDim.x) {
-                const int32_t* p = arrival + (i / ch.n_ctas) * DP_MAX_CTAS + (i % ch.n_ctas);
-                while (ld_relaxed_sys(p) < want) {
+        if (threadIdx.x < 32) {
+            const unsigned long long t0 = global_ns();
+            for (int c = 0; c < s.n_wait; ++c) {
+                const DpChannel& ch = s.wait[c];
+                const int32_t want = __ldg(ch.epoch_dev) + 1;
+                const int32_t* arrival = reinterpret_cast<const int32_t*>(ch.base[s.rank] + ch.flag_off);
+                const int total = s.world * ch.n_ctas;
+                bool ok;
+                do {
+                    ok = true;
+                    for (int i = threadIdx.x; i < total; i += 32)
+                        ok = ok && (ld_relaxed_sys(arrival + (i / ch.n_ctas) * DP_MAX_CTAS + (i % ch.n_ctas)) >= want);
                     if (global_ns() - t0 > 60ull * 1000000000ull) __trap();      // a peer died: fail loudly (see spin_until)
-                }
+                } while (!__all_sync(0xffffffffu, ok));
             }
+            if (threadIdx.x == 0) __threadfence_system();
         }
-        __threadfence_system();
         __syncthreads();
     }
 }

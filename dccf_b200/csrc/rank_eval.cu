@@ -5,17 +5,20 @@
 // global pandas sort by score, groupby uid, one Python loop per user PER METRIC) and the helpers it
 // calls, src/utils/rank_metrics.py:61-87 (precision_at_k) and :130-201 (dcg_at_k / ndcg_at_k, method=1).
 //
-// k_rank_stream (k <= 16): one warp per user, ONE streaming pass over the user's candidates.  Lane l reads
-// candidates l, l+32, ... (coalesced; sixteen loads in flight) and keeps its own best KCAP entries (score, row)
-// sorted in registers; a candidate is compared against the lane's current worst entry first.  Item ids are read
-// ONLY to break exact score ties (a dependent load on the insertion path made the warp wait for the L2 once per
-// candidate batch: 74 us instead of < 10 for 1 024 users).  The 32 sorted lists are merged by k shuffle
-// tournaments over the list heads (the winning lane pops).  Labels are read once: total relevance, number of positives (ideal DCG
-// of 0/1 labels is a count; other label values take a second pass that keeps the k largest labels), and the
-// labels of the k winners.  Every metric (ndcg, hit, precision, recall, f1) at every requested k (up to 4
-// values of k per launch) comes out of that one pass; per-user values are optional, the per-metric SUMS over
-// users are accumulated in a fixed order (warp -> CTA -> last CTA), so a metric list such as
-// "ndcg@5,recall@5,precision@5" costs one launch and one 120-byte read-back.
+// k_rank_stream (k <= 16): one warp per user, ONE streaming pass over the user's candidates: lane l reads
+// candidates l, l+32, ... (coalesced, eight loads in flight), stages the scores in shared memory and keeps only its
+// maximum.  The k-th largest of the 32 lane maxima is a threshold no member of the top k can be below; a second
+// pass over shared memory compacts the survivors (typically k .. 3k of 1001) with ballots, and only those get
+// their item ids loaded and are ordered exactly (score desc, item id asc, row asc) by k shuffle tournaments.
+// About six instructions per candidate.  (Two earlier designs, kept out: k selection rounds over global memory —
+// 2k+1 passes, 110-145 us per 1 024 users; per-lane sorted top-k lists in registers — one pass, but ~1 700
+// instructions per candidate-iteration of divergent insertion code, 52 us.)  Users with more candidates than the
+// staging buffer, or with more than 128 candidates tied at the threshold, take the general selection rounds.
+// Labels are read once: total relevance, number of positives (ideal DCG of 0/1 labels is a count; graded labels
+// take selection rounds over the labels), and the labels of the k winners.  Every metric (ndcg, hit, precision,
+// recall, f1) at every requested k (up to 4 values of k per launch) comes out of that one pass; per-user values are
+// optional, the per-metric SUMS over users are accumulated in a fixed order (warp -> CTA -> last CTA), so a metric
+// list such as "ndcg@5,recall@5,precision@5" costs one launch and one 120-byte read-back.
 // Order: score descending, then item id ascending, then row ascending — a total order, so the result is
 // deterministic (the reference's quicksort leaves ties unordered).  NaN scores rank last, as pandas does.
 // k_rank_select (any k <= 1024): the k-rounds selection kernel, kept for k > 16.
@@ -58,56 +61,53 @@ struct RankKs {
     int32_t n_k, kmax;
 };
 
-// entry of a lane's sorted list: score and row only.  The item id decides exact score ties and is fetched then
-// (the rows are in L1 / L2: they were just streamed); the label is loaded for the k winners only.
-struct Ent {
-    float s;
-    int32_t row;      // INT32_MAX = sentinel, ranks after every real candidate
-};
-__device__ __forceinline__ bool ent_before(const Ent& a, const Ent& b, const int64_t* __restrict__ iids) {
-    if (b.row == INT32_MAX) return a.row != INT32_MAX;
-    if (a.row == INT32_MAX) return false;
-    if (a.s != b.s) return a.s > b.s;
-    const int64_t ia = __ldg(iids + a.row), ib = __ldg(iids + b.row);
-    if (ia != ib) return ia < ib;
-    return a.row < b.row;
-}
-__device__ __forceinline__ Ent ent_sentinel() {
-    Ent e;
-    e.s = -INFINITY; e.row = INT32_MAX;
-    return e;
+constexpr int RANK_CHUNK = 2048;     // candidates of one user staged in shared memory (8 KB per warp); more: fallback
+constexpr int RANK_SURV = 128;       // survivors of the threshold test kept per user; more (massive ties): fallback
+
+__device__ __forceinline__ RankKey key_sentinel() {
+    RankKey k;
+    k.s = -INFINITY; k.iid = INT64_MAX; k.row = INT32_MAX; k.label = 0.f;      // after every real candidate
+    return k;
 }
 
-template <int KCAP>
-__device__ __forceinline__ void list_insert(Ent (&L)[KCAP], const Ent& cur, const int64_t* __restrict__ iids) {
-    // precondition: cur ranks before L[KCAP-1]
-    bool placed = false;
-#pragma unroll
-    for (int i = KCAP - 1; i >= 1; --i) {
-        if (!placed) {
-            if (ent_before(cur, L[i - 1], iids)) L[i] = L[i - 1];
-            else { L[i] = cur; placed = true; }
-        }
+// warp-wide best of one key per lane (lanes without a candidate carry the sentinel)
+__device__ __forceinline__ RankKey warp_best(RankKey best) {
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+        const RankKey other = shfl_key(best, o);
+        if (key_before(other, best)) best = other;
     }
-    if (!placed) L[0] = cur;
+    return best;
 }
 
-template <int KCAP>
-__device__ __forceinline__ void label_insert(float (&L)[KCAP], float v) {
-    bool placed = false;
-#pragma unroll
-    for (int i = KCAP - 1; i >= 1; --i) {
-        if (!placed) {
-            if (v > L[i - 1]) L[i] = L[i - 1];
-            else { L[i] = v; placed = true; }
+// The general selection: kk rounds of "best key strictly after the previous winner" over the user's candidates in
+// global memory (L1 / L2 after the streaming pass).  Used when a user has more candidates than the staging buffer or
+// when the threshold test leaves too many survivors (massive score ties).  Lane t returns winner t.
+__device__ __forceinline__ RankKey select_rounds(const float* __restrict__ scores, const int64_t* __restrict__ iids,
+                                                 const int32_t* __restrict__ cand_rows, int64_t lo, int64_t hi, int kk,
+                                                 int lane) {
+    RankKey mine = key_sentinel(), last;
+    last.s = INFINITY; last.iid = -1; last.row = -1; last.label = 0.f;
+#pragma unroll 1
+    for (int t = 0; t < kk; ++t) {
+        RankKey best = key_sentinel();
+#pragma unroll 1
+        for (int64_t c = lo + lane; c < hi; c += 32) {
+            RankKey cur;
+            cur.row = cand_rows != nullptr ? __ldg(cand_rows + c) : (int32_t)c;
+            cur.s = order_score(__ldg(scores + cur.row));
+            cur.label = 0.f;
+            if (cur.s > last.s || cur.s < best.s) continue;          // not after the last winner / cannot beat the best
+            cur.iid = __ldg(iids + cur.row);
+            if ((t == 0 || key_before(last, cur)) && key_before(cur, best)) best = cur;
         }
+        best = warp_best(best);
+        if (lane == t) mine = best;
+        last = best;
     }
-    if (!placed) L[0] = v;
+    return mine;
 }
 
-constexpr int RANK_CHUNK = 1024;     // candidates of a user staged in shared memory at a time (4 KB per warp)
-
-template <int KCAP>
 __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
     const float* __restrict__ scores, const float* __restrict__ labels, const int64_t* __restrict__ iids,
     const int32_t* __restrict__ cand_rows, const int64_t* __restrict__ user_off, int64_t n_users, const RankKs ks,
@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
     double* __restrict__ part_sums, int32_t* __restrict__ cta_counter, double* __restrict__ out_sums) {
     __shared__ double acc_s[RANK_WARPS][RANK_MAX_NK * RANK_NCOL];
     __shared__ float sc_s[RANK_WARPS][RANK_CHUNK];
+    __shared__ int32_t surv_s[RANK_WARPS][RANK_SURV];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ncol = ks.n_k * RANK_NCOL;
@@ -123,60 +124,47 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
     const int kmax = ks.kmax;
     const int64_t n_warps = (int64_t)gridDim.x * RANK_WARPS;
     float* my_s = sc_s[warp];
+    int32_t* my_surv = surv_s[warp];
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (int64_t g = (int64_t)blockIdx.x * RANK_WARPS + warp; g < n_users; g += n_warps) {   // warp-uniform
         const int64_t lo = user_off[g], hi = user_off[g + 1];
         const int64_t n = hi - lo;
-        Ent L[KCAP];
-#pragma unroll
-        for (int i = 0; i < KCAP; ++i) L[i] = ent_sentinel();
+        const int kk = (int)min((int64_t)kmax, n);
+        const bool fits = n <= RANK_CHUNK;
         double label_sum = 0.0;
         int n_pos = 0;
         bool nonbinary = false;
+        float lane_max = -INFINITY;
 
-        for (int64_t base = lo; base < hi; base += RANK_CHUNK) {
-            const int m = (int)min((int64_t)RANK_CHUNK, hi - base);
-            // ---- phase 1, the streaming pass: scores -> shared memory, label statistics; eight candidates per lane in
-            // flight.  (Deliberately SMALL code: a first version that kept 16 candidates in registers and inlined the
-            // insertion 16 times was 13 k instructions long and spent 63 % of its stall samples waiting for the
-            // instruction cache.)
-            for (int c0 = lane; c0 < m; c0 += 32 * 8) {
-                int32_t row[8];
-                float s[8], l[8];
+        // ---- phase 1, the streaming pass: scores -> shared memory, the lane's maximum, label statistics; eight
+        // candidates per lane in flight.  About three instructions per candidate.
+        for (int64_t c0 = lo + lane; c0 < hi; c0 += 32 * 8) {
+            int32_t row[8];
+            float s[8], l[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int c = c0 + 32 * j;
-                    row[j] = (c < m) ? (cand_rows != nullptr ? __ldg(cand_rows + base + c) : (int32_t)(base + c)) : -1;
-                }
+            for (int j = 0; j < 8; ++j) {
+                const int64_t c = c0 + 32 * j;
+                row[j] = (c < hi) ? (cand_rows != nullptr ? __ldg(cand_rows + c) : (int32_t)c) : -1;
+            }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (row[j] >= 0) {
-                        s[j] = __ldg(scores + row[j]);
-                        l[j] = __ldg(labels + row[j]);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (row[j] >= 0) {
-                        my_s[c0 + 32 * j] = order_score(s[j]);
-                        label_sum += (double)l[j];
-                        n_pos += (l[j] == 1.f) ? 1 : 0;
-                        nonbinary |= (l[j] != 0.f && l[j] != 1.f);
-                    }
+            for (int j = 0; j < 8; ++j) {
+                if (row[j] >= 0) {
+                    s[j] = __ldg(scores + row[j]);
+                    l[j] = __ldg(labels + row[j]);
                 }
             }
-            __syncwarp();
-            // ---- phase 2, selection from shared memory: one copy of the insertion code ----
-#pragma unroll 1
-            for (int c = lane; c < m; c += 32) {
-                Ent cur;
-                cur.s = my_s[c];
-                if (cur.s >= L[KCAP - 1].s) {
-                    cur.row = cand_rows != nullptr ? __ldg(cand_rows + base + c) : (int32_t)(base + c);
-                    if (ent_before(cur, L[KCAP - 1], iids)) list_insert<KCAP>(L, cur, iids);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (row[j] >= 0) {
+                    const float os = order_score(s[j]);
+                    if (fits) my_s[c0 - lo + 32 * j] = os;
+                    lane_max = fmaxf(lane_max, os);
+                    label_sum += (double)l[j];
+                    n_pos += (l[j] == 1.f) ? 1 : 0;
+                    nonbinary |= (l[j] != 0.f && l[j] != 1.f);
                 }
             }
-            __syncwarp();
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -184,60 +172,103 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
             n_pos += __shfl_xor_sync(0xffffffffu, n_pos, o);
         }
         nonbinary = __any_sync(0xffffffffu, nonbinary);
+        __syncwarp();
 
-        // ---- merge: kmax tournaments over the heads of the 32 sorted lists; lane t keeps winner t ------
-        const int kk = (int)min((int64_t)kmax, n);
-        Ent mine = ent_sentinel();
+        RankKey mine = key_sentinel();     // lane t: the candidate at rank t
+        bool have = false;                 // warp-uniform
+        if (fits) {
+            // ---- phase 2, a threshold nothing in the top kk can be below: the kk-th largest of the 32 lane maxima
+            // (kk distinct candidates are >= it) ----
+            float lm = lane_max, thr = -INFINITY;
 #pragma unroll 1
-        for (int t = 0; t < kk; ++t) {
-            Ent best = L[0];
-#pragma unroll 1
-            for (int o = 16; o > 0; o >>= 1) {
-                Ent other;
-                other.s = __shfl_xor_sync(0xffffffffu, best.s, o);
-                other.row = __shfl_xor_sync(0xffffffffu, best.row, o);
-                if (ent_before(other, best, iids)) best = other;
+            for (int t = 0; t < kk; ++t) {
+                thr = warp_max(lm);
+                if (thr == -INFINITY) break;
+                const uint32_t b = __ballot_sync(0xffffffffu, lm == thr);
+                if (lane == __ffs(b) - 1) lm = -INFINITY;
             }
-            if (L[0].row == best.row) {                      // rows are unique: exactly one lane pops
+            // ---- phase 3, the survivors (score >= threshold: typically kk .. 3 kk of the 1001), compacted in candidate
+            // order by ballots ----
+            int n_s = 0;
+#pragma unroll 1
+            for (int c = lane; c < (int)((n + 31) & ~(int64_t)31); c += 32) {
+                const bool pred = c < n && my_s[c] >= thr;
+                const uint32_t m = __ballot_sync(0xffffffffu, pred);
+                if (pred) {
+                    const int pos = n_s + __popc(m & lt_mask);
+                    if (pos < RANK_SURV) my_surv[pos] = c;
+                }
+                n_s += __popc(m);
+            }
+            __syncwarp();
+            if (n_s <= RANK_SURV) {
+                // ---- phase 4, exact order of the survivors (score desc, item id asc, row asc): each lane holds up to
+                // four of them, kk tournaments, the winning lane retires its entry ----
+                RankKey key[RANK_SURV / 32];
 #pragma unroll
-                for (int i = 0; i + 1 < KCAP; ++i) L[i] = L[i + 1];
-                L[KCAP - 1] = ent_sentinel();
+                for (int q = 0; q < RANK_SURV / 32; ++q) {
+                    key[q] = key_sentinel();
+                    const int j = lane + 32 * q;
+                    if (j < n_s) {
+                        const int c = my_surv[j];
+                        key[q].row = cand_rows != nullptr ? __ldg(cand_rows + lo + c) : (int32_t)(lo + c);
+                        key[q].s = my_s[c];
+                        key[q].iid = __ldg(iids + key[q].row);
+                    }
+                }
+#pragma unroll 1
+                for (int t = 0; t < kk; ++t) {
+                    RankKey best = key[0];
+#pragma unroll
+                    for (int q = 1; q < RANK_SURV / 32; ++q)
+                        if (key_before(key[q], best)) best = key[q];
+                    best = warp_best(best);
+#pragma unroll
+                    for (int q = 0; q < RANK_SURV / 32; ++q)
+                        if (key[q].row == best.row) key[q] = key_sentinel();      // rows are unique: one entry retires
+                    if (lane == t) mine = best;
+                }
+                have = true;
             }
-            if (lane == t) mine = best;
         }
+        if (!have) mine = select_rounds(scores, iids, cand_rows, lo, hi, kk, lane);
         const float my_label = (lane < kk) ? __ldg(labels + mine.row) : 0.f;
-        if (out_topk_iid != nullptr && lane < kmax) out_topk_iid[g * kmax + lane] = (lane < kk) ? __ldg(iids + mine.row) : -1;
+        if (out_topk_iid != nullptr && lane < kmax) out_topk_iid[g * kmax + lane] = (lane < kk) ? mine.iid : -1;
         if (out_topk_row != nullptr && lane < kmax) out_topk_row[g * kmax + lane] = (lane < kk) ? mine.row : -1;
 
         // ---- ideal ordering of the labels: 0/1 labels -> the first n_pos positions are 1; otherwise the kmax
         // largest labels by a second pass (values only) --------------------------------------------------------
         float ideal = (lane < min(kk, n_pos)) ? 1.f : 0.f;    // lane t: label at ideal position t
         if (nonbinary) {                                       // warp-uniform
-            float T[KCAP];
-#pragma unroll
-            for (int i = 0; i < KCAP; ++i) T[i] = -INFINITY;
-#pragma unroll 1
-            for (int64_t c = lo + lane; c < hi; c += 32) {
-                const float v = __ldg(labels + (cand_rows != nullptr ? __ldg(cand_rows + c) : (int32_t)c));
-                if (v > T[KCAP - 1]) label_insert<KCAP>(T, v);
-            }
+            // graded labels: kk rounds of "largest label after the previous one" over (label desc, position asc)
             ideal = 0.f;
+            float last_l = INFINITY;
+            int64_t last_c = -1;
 #pragma unroll 1
             for (int t = 0; t < kk; ++t) {
-                float best = T[0];
-                int who = lane;
-#pragma unroll
+                float best_l = -INFINITY;
+                int64_t best_c = -1;
+#pragma unroll 1
+                for (int64_t c = lo + lane; c < hi; c += 32) {
+                    const float l = __ldg(labels + (cand_rows != nullptr ? __ldg(cand_rows + c) : (int32_t)c));
+                    const bool below = (t == 0) || (l < last_l) || (l == last_l && c > last_c);
+                    if (below && (best_c < 0 || l > best_l || (l == best_l && c < best_c))) {
+                        best_l = l;
+                        best_c = c;
+                    }
+                }
+#pragma unroll 1
                 for (int o = 16; o > 0; o >>= 1) {
-                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int ow = __shfl_xor_sync(0xffffffffu, who, o);
-                    if (ob > best || (ob == best && ow < who)) { best = ob; who = ow; }
+                    const float ol = __shfl_xor_sync(0xffffffffu, best_l, o);
+                    const int64_t oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+                    if (oc >= 0 && (best_c < 0 || ol > best_l || (ol == best_l && oc < best_c))) {
+                        best_l = ol;
+                        best_c = oc;
+                    }
                 }
-                if (lane == who) {
-#pragma unroll
-                    for (int i = 0; i + 1 < KCAP; ++i) T[i] = T[i + 1];
-                    T[KCAP - 1] = -INFINITY;
-                }
-                if (lane == t) ideal = best;
+                if (lane == t) ideal = best_l;
+                last_l = best_l;
+                last_c = best_c;
             }
         }
 
@@ -438,14 +469,9 @@ extern "C" int dccf_rank_eval_multi(const float* scores, const float* labels, co
     if (ctas > 148 * 4) ctas = 148 * 4;
     double* part = reinterpret_cast<double*>(ws);
     int32_t* counter = ws ? reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(ws) + (size_t)(148 * 4) * RANK_MAX_NK * RANK_NCOL * sizeof(double)) : nullptr;
-#define DCCF_RANK_LAUNCH(KC)                                                                                              \
-    k_rank_stream<KC><<<(unsigned)ctas, RANK_WARPS * 32, 0, stream>>>(scores, labels, iids, cand_rows, user_off, n_users, \
-                                                                      ks, out_topk_iid, out_topk_row, out_metrics, part,  \
-                                                                      counter, out_sums)
-    if (ks.kmax <= 4) DCCF_RANK_LAUNCH(4);
-    else if (ks.kmax <= 8) DCCF_RANK_LAUNCH(8);
-    else DCCF_RANK_LAUNCH(16);
-#undef DCCF_RANK_LAUNCH
+    k_rank_stream<<<(unsigned)ctas, RANK_WARPS * 32, 0, stream>>>(scores, labels, iids, cand_rows, user_off, n_users, ks,
+                                                                  out_topk_iid, out_topk_row, out_metrics, part, counter,
+                                                                  out_sums);
     DCCF_CHECK_LAUNCH("k_rank_stream");
     return DCCF_OK;
 }
