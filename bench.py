@@ -61,10 +61,12 @@ NCU_EVAL_TRAFFIC_SOURCE = ('profiles/r1c_ncu_full_tc_summary.csv (ncu --set full
                            'cache; the later tuning of the kernel did not change what it reads)')
 NCU_TRAFFIC_BYTES = {'k_train_fwd_tc': 1.89e6, 'k_train_mid': 4.47e6, 'k_train_bwd_tc': 2.92e6, 'k_adam_touched': 7.91e6,
                      'k_adam_untouched': 47.35e6 + 0.81e6}
-# round 2 captures (profiles/r2a_ncu_legs_summary.csv, r2a_ncu_full_catalogue_summary.csv): per launch, cold cache
-NCU_R2 = {'source': 'profiles/r2a_ncu_legs_summary.csv (ncu --set full --clock-control none, per launch, cold cache)',
-          'k_gather_scores': None, 'k_row_scores_tc_64': None, 'k_rank_stream': None, 'k_confounder_draw': None,
-          'k_full_scores_topk': None, 'k_full_scores_materialise': None}
+# round 2 captures (per launch, cold cache, `ncu --set full --clock-control none`): dram__bytes_read.sum + dram__bytes_write.sum
+NCU_R2 = {'source': 'profiles/r2_ncu_eval_summary.csv (ncu --set full --clock-control none, per launch, cold cache)',
+          'k_gather_scores': 9.33e6,          # one 16384-pair batch; L2 hit rate 72 %
+          'k_row_scores_tc_64': 8.26e6,       # one 16384-pair batch, 64-wide operand; L2 hit rate 87 %
+          'k_confounder_draw': 1.0e4,         # one 163 840-id draw: nothing read, ids written through L2
+          'k_full_scores_topk': 18.4e6}       # Yelp shape, one GPU: factors in, k ids out
 FLOP_FWD_PAIR = R * (2 * (D + F) * D + 4 * D)
 FLOP_BWD_PAIR = R * (2 * (D + F) * D + 2 * D * D + 2 * D)
 BYTES_PAIR = 16 + 4 * D + 4 * D * Z + 4 * F + 4 * Z
@@ -518,20 +520,48 @@ def noise_free_eval(U, I, n_users, dev):
     score_ms = graph_score_ms if graph_score_ms is not None else eager_score_ms
     total_ms = graph_total_ms if graph_total_ms is not None else eager_score_ms + rank_ms
     hbm_peak, _, peak_src = measured_peaks()
-    gbs = rows * BYTES_PAIR_GATHER / 1e9 / (score_ms / 1e3)
+    # L2 read rate of this GPU, measured here: sum over an L2-resident 32 MiB tensor, best of 20 (a torch reduction: a
+    # floor of the L2 roof, not the roof itself)
+    probe = torch.ones(8 * 1024 * 1024, dtype=torch.float32, device=dev)
+    best = 1e9
+    for _ in range(20):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        probe.sum()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    l2_gbs = probe.numel() * 4 / 1e9 / (best / 1e3)
+    pairs_per_batch = min(rows, EVAL_BATCH)
+    flushed_ms = eager_score_ms / len(bounds)           # CUDA events per batch, L2 flushed before every batch
+    warm_ms = score_ms / len(bounds)                    # batches back to back inside one graph (tables L2-resident)
+    alg_gb = pairs_per_batch * BYTES_PAIR_GATHER / 1e9
+    traffic = NCU_R2['k_gather_scores'] if pairs_per_batch == 16384 else None
+    roof = {'kernel': 'k_gather_scores', 'bound': 'hbm', 'achieved': alg_gb / (flushed_ms / 1e3), 'peak': hbm_peak,
+            'unit': 'GB/s', 'frac': alg_gb / (flushed_ms / 1e3) / hbm_peak, 'traffic': traffic,
+            'traffic_source': NCU_R2['source'], 'peak_source': peak_src, 'bytes_per_pair': BYTES_PAIR_GATHER,
+            'note': 'achieved = algorithmic bytes per batch (ids 96, user row 256, PF row 256, 11 PI rows 2816, 11 exposure '
+                    'values 44 = 3468 B per pair) / time per batch with the L2 FLUSHED before every batch.  Most of those '
+                    'bytes are gathers from the two projected tables (2 x I x 256 B = 8 MB), which L2 serves: DRAM sees '
+                    '`traffic` (ids, exposure sectors, first touch of the tables) — the `dram` object; the `l2` object '
+                    'rates the algorithmic bytes against an L2 read rate measured in this process',
+            'dram': {'achieved': (traffic / 1e9 / (flushed_ms / 1e3)) if traffic else None, 'peak': hbm_peak, 'unit': 'GB/s',
+                     'frac': (traffic / 1e9 / (flushed_ms / 1e3) / hbm_peak) if traffic else None},
+            'l2': {'achieved': alg_gb / (flushed_ms / 1e3), 'peak': l2_gbs, 'unit': 'GB/s',
+                   'frac': alg_gb / (flushed_ms / 1e3) / l2_gbs,
+                   'peak_source': 'torch.sum over an L2-resident 32 MiB tensor, best of 20, this process'},
+            'warm': {'ms_per_batch': warm_ms, 'achieved': alg_gb / (warm_ms / 1e3), 'unit': 'GB/s',
+                     'frac_of_hbm': alg_gb / (warm_ms / 1e3) / hbm_peak, 'frac_of_l2': alg_gb / (warm_ms / 1e3) / l2_gbs,
+                     'note': 'all batches of the pass replayed as one CUDA graph, no flush in between'}}
     return {'metric': 'eval_users_per_s', 'value': n_users / (total_ms / 1e3), 'unit': 'users/s',
-            'config': 'same evaluation workload with --std 0 (no feature noise): dccf_score_gather + dccf_rank_eval',
+            'config': 'same evaluation workload with --std 0 (no feature noise): dccf_score_gather + dccf_rank_eval_multi '
+                      '(DCCF.use_gather_scorer, the default for noise-free inference)',
             'timing': ('one CUDA graph per pass (scoring of all batches + ranking), inputs larger than L2'
                        if graph_total_ms is not None else 'eager loop, CUDA events per batch, L2 flushed between batches'),
-            'users': n_users, 'candidates_per_user': 1 + TEST_NEG_N, 'ms_per_batch': score_ms / len(bounds),
-            'eager_ms_per_batch': eager_score_ms / len(bounds), 'pass_ms': total_ms,
-            'rank_ms': rank_ms, 'max_rel_diff_vs_general_scorer': rel, 'parity_ok': bool(rel < 1e-5),
-            'roofline': {'kernel': 'k_gather_scores', 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-                         'frac': gbs / hbm_peak, 'traffic': None, 'peak_source': peak_src,
-                         'bytes_per_pair': BYTES_PAIR_GATHER,
-                         'note': 'algorithmic bytes (ids, user row, PF row, Z PI rows, Z exposure values) / scoring time of '
-                                 'the pass; the two projected tables (2 x I x 256 B) are re-read from L2 once warm, so the '
-                                 'fraction is not capped at 1'},
+            'users': n_users, 'candidates_per_user': 1 + TEST_NEG_N, 'ms_per_batch': warm_ms,
+            'flushed_ms_per_batch': flushed_ms, 'value_flushed': n_users / ((eager_score_ms + rank_ms) / 1e3),
+            'pass_ms': total_ms, 'rank_ms': rank_ms, 'max_rel_diff_vs_general_scorer': rel, 'parity_ok': bool(rel < 1e-5),
+            'roofline': roof,
             'ndcg@5': float(sums[0] / n_users), 'recall@5': float(sums[3] / n_users),
             'precision@5': float(sums[2] / n_users)}
 
@@ -630,8 +660,11 @@ def projected_noise_eval(U, I, n_users, dev):
             'eager_ms_per_batch': eager_score_ms / len(bounds), 'pass_ms': total_ms,
             'rank_ms': rank_ms, 'prediction_stats': stats, 'e2e': e2e,
             'roofline': {'kernel': 'k_row_scores_tc (64-wide operand)', 'bound': 'tensor',
-                         'achieved': tflop / (score_ms / 1e3), 'peak': tf32_peak, 'unit': 'TFLOP/s',
-                         'frac': tflop / (score_ms / 1e3) / tf32_peak, 'traffic': None,
+                         'achieved': tflop / 3 / (score_ms / 1e3), 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                         'frac': tflop / 3 / (score_ms / 1e3) / tf32_peak,
+                         'achieved_issued': tflop / (score_ms / 1e3), 'frac_issued': tflop / (score_ms / 1e3) / tf32_peak,
+                         'traffic': NCU_R2['k_row_scores_tc_64'] if min(rows, EVAL_BATCH) == 16384 else None,
+                         'traffic_source': NCU_R2['source'],
                          'peak_source': peak_src + ': bf16 burst / 2 for kind::tf32',
                          'hbm': {'achieved': rows * BYTES_PAIR_GATHER / 1e9 / (score_ms / 1e3), 'unit': 'GB/s',
                                  'bytes_per_pair': BYTES_PAIR_GATHER}},

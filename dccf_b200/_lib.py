@@ -146,8 +146,9 @@ _SIGNATURES = {
     'dccf_dp_flag_floats': (ctypes.c_int64, []),
     'dccf_dp_done': (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, _P, _P]),
     'dccf_full_scores_splits': (ctypes.c_int32, [ctypes.c_int32, ctypes.c_int32]),
+    'dccf_full_scores_ws_floats': (ctypes.c_int64, [ctypes.c_int32]),
     'dccf_full_scores': (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P, _P, ctypes.c_float, _P,
-                                        ctypes.c_int32, _P, _P, _P, _P, _P]),
+                                        ctypes.c_int32, _P, _P, _P, _P, _P, _P]),
     'dccf_sample_negatives': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                              ctypes.c_int64, _P, _P, _P, _P, _P]),
     'dccf_confounder_draw': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, ctypes.c_int64, _P]),

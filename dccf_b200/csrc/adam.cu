@@ -947,8 +947,16 @@ static int marshal_adam(const char* who, const dccf_adam_table* tables, int32_t 
         o.rec_row = t.rec_row; o.csr_off = t.csr_off; o.csr = t.csr; o.csr_pool = t.csr_pool;
         int64_t want;
         if (mode == 2) {
-            want = (n_rec + 15) / 16;                              // 16 records (half-warps) per 256-thread CTA per trip
-            if (want > 148 * 3) want = 148 * 3;                    // one wave (three 256-thread CTAs fit an SM)
+            // 16 records (half-warps) per 256-thread CTA per trip; ALL tables and dense tensors of the launch together stay
+            // within one wave (three 256-thread CTAs of this kernel fit an SM: 444, of which the dense tensors take up to
+            // 149) — a second wave started only when first-wave CTAs retired (data-parallel steps: 533 CTAs)
+            int64_t n_rec_all = 0;
+            for (int j = 0; j < n_tables; ++j) n_rec_all += (int64_t)tables[j].n_seg * tables[j].seg_len;
+            const int64_t table_budget = 148 * 3 - 150;
+            want = (n_rec + 15) / 16;
+            const int64_t share = n_rec_all > 0 ? (table_budget * n_rec + n_rec_all - 1) / n_rec_all : 0;
+            if (want > share) want = share;
+            if (want < 1 && n_rec > 0) want = 1;
         } else {
             want = (o.n_rows + 31) / 32;                           // 32 rows per 256-thread CTA per trip
             int64_t share = total_rows > 0 ? (budget * o.n_rows + total_rows - 1) / total_rows : 0;

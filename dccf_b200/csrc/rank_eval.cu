@@ -22,6 +22,8 @@
 // Order: score descending, then item id ascending, then row ascending — a total order, so the result is
 // deterministic (the reference's quicksort leaves ties unordered).  NaN scores rank last, as pandas does.
 // k_rank_select (any k <= 1024): the k-rounds selection kernel, kept for k > 16.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace dccf {
@@ -60,6 +62,10 @@ struct RankKs {
     int32_t k[RANK_MAX_NK];
     int32_t n_k, kmax;
 };
+
+// log2(t + 2) for the first RANK_STREAM_MAX_K rank positions, as float64 (filled by the host: std::log2 of the exact
+// integers, the values np.log2 gives): a table instead of a software FP64 log2 per position and user
+__constant__ double c_log2_pos[16];
 
 constexpr int RANK_CHUNK = 2048;     // candidates of one user staged in shared memory (8 KB per warp); more: fallback
 constexpr int RANK_SURV = 128;       // survivors of the threshold test kept per user; more (massive ties): fallback
@@ -137,25 +143,27 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
         bool nonbinary = false;
         float lane_max = -INFINITY;
 
-        // ---- phase 1, the streaming pass: scores -> shared memory, the lane's maximum, label statistics; eight
-        // candidates per lane in flight.  About three instructions per candidate.
-        for (int64_t c0 = lo + lane; c0 < hi; c0 += 32 * 8) {
-            int32_t row[8];
-            float s[8], l[8];
+        // ---- phase 1, the streaming pass: scores -> shared memory, the lane's maximum, label statistics.  All of a
+        // 1001-candidate user's loads are in flight at once (32 scores + 32 labels per lane): ONE memory round trip per
+        // user instead of four — with one warp per user the pass is bound by that latency, not by bandwidth.
+        constexpr int NF = 32;
+        for (int64_t c0 = lo + lane; c0 < hi; c0 += 32 * NF) {
+            int32_t row[NF];
+            float s[NF], l[NF];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < NF; ++j) {
                 const int64_t c = c0 + 32 * j;
                 row[j] = (c < hi) ? (cand_rows != nullptr ? __ldg(cand_rows + c) : (int32_t)c) : -1;
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < NF; ++j) {
                 if (row[j] >= 0) {
                     s[j] = __ldg(scores + row[j]);
                     l[j] = __ldg(labels + row[j]);
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < NF; ++j) {
                 if (row[j] >= 0) {
                     const float os = order_score(s[j]);
                     if (fits) my_s[c0 - lo + 32 * j] = os;
@@ -280,7 +288,7 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
             const float lab = __shfl_sync(0xffffffffu, my_label, t);
             const float idl = __shfl_sync(0xffffffffu, ideal, t);
             if (t < kk) {
-                const double disc = log2((double)(t + 2));
+                const double disc = c_log2_pos[t];       // log2(t + 2), rank_metrics.py:160 (np.log2 of positions 2, 3, ...)
                 dcg += (double)lab / disc;
                 idcg += (double)idl / disc;
                 hit_sum += (double)lab;
@@ -464,6 +472,17 @@ extern "C" int dccf_rank_eval_multi(const float* scores, const float* labels, co
     if (n_users <= 0) {
         if (out_sums) cudaMemsetAsync(out_sums, 0, sizeof(double) * n_k * RANK_NCOL, stream);
         return DCCF_OK;
+    }
+    static PerDeviceOnce table_once;
+    if (table_once.need()) {
+        double h[16];
+        for (int t = 0; t < 16; ++t) h[t] = log2((double)(t + 2));
+        cudaError_t e = cudaMemcpyToSymbol(c_log2_pos, h, sizeof(h));
+        if (e != cudaSuccess) {
+            set_error("dccf_rank_eval_multi: cannot install the log2 table: %s", cudaGetErrorString(e));
+            return DCCF_ERR_CUDA;
+        }
+        table_once.mark();
     }
     int64_t ctas = (n_users + RANK_WARPS - 1) / RANK_WARPS;
     if (ctas > 148 * 4) ctas = 148 * 4;

@@ -423,6 +423,9 @@ def rank_eval_multi(scores, labels, iids, cand_rows, user_off, ks, out_metrics=N
     LAUNCHES[0] += 1 if n_users > 0 else 0
 
 
+_FS_WS = {}
+
+
 def full_scores(A, B, row_bias=None, col_bias=None, col_scale=None, g=0.0, materialise=True, k=0):
     """Full-catalogue scoring on the tensor cores (dccf_full_scores).  Returns (matrix [U,I] or None,
     topk_score [U,k] or None, topk_id [U,k] or None)."""
@@ -434,13 +437,17 @@ def full_scores(A, B, row_bias=None, col_bias=None, col_scale=None, g=0.0, mater
     if k > 0:
         ts = torch.empty((U, k), dtype=torch.float32, device=dev)
         ti = torch.empty((U, k), dtype=torch.int64, device=dev)
-        splits = int(lib.dccf_full_scores_splits(U, I))
-        if splits > 1:
-            ws = torch.empty((splits, U, k), dtype=torch.float32, device=dev)
-            wi = torch.empty((splits, U, k), dtype=torch.int64, device=dev)
+        lists = int(lib.dccf_full_scores_splits(U, I))
+        ws = torch.empty((lists, U, k), dtype=torch.float32, device=dev)
+        wi = torch.empty((lists, U, k), dtype=torch.int64, device=dev)
+    # pre-split operand images of the item side: one workspace per (device, catalogue size), rewritten by every call
+    key = (dev.index, I)
+    items = _FS_WS.get(key)
+    if items is None:
+        items = _FS_WS[key] = torch.empty(int(lib.dccf_full_scores_ws_floats(I)), dtype=torch.float32, device=dev)
     check(lib.dccf_full_scores(U, I, ptr(A), ptr(B), ptr(row_bias), ptr(col_bias), ptr(col_scale), float(g), ptr(out),
-                               int(k), ptr(ts), ptr(ti), ptr(ws), ptr(wi), stream_ptr()), 'dccf_full_scores')
-    LAUNCHES[0] += 2 if ws is not None else 1
+                               int(k), ptr(ts), ptr(ti), ptr(ws), ptr(wi), ptr(items), stream_ptr()), 'dccf_full_scores')
+    LAUNCHES[0] += 3 if k > 0 else 2
     return out, ts, ti
 
 

@@ -447,11 +447,16 @@ int dccf_dp_done(const uint64_t* peer_bases, int32_t world, int32_t rank, int64_
  *   out        [U,I]  the materialised matrix (or NULL)
  *   topk_score [U,k] f32, topk_id [U,k] int64 (-1 padded): fused per-user top-k, score descending, ties by
  *              item id ascending, NaN last; 1 <= k <= 16 (or NULL)
- *   ws_score / ws_id: [dccf_full_scores_splits(U,I), U, k] workspaces, needed when that count is > 1 */
+ *   ws_score / ws_id: [dccf_full_scores_splits(U,I), U, k] workspaces of the fused top-k (one partial list per item
+ *              split and half of an item tile, merged by a second launch); required with topk_score
+ *   ws_items:  dccf_full_scores_ws_floats(n_items) floats, 128-byte aligned: the item side pre-split into the TF32 hi / lo
+ *              operand images the tensor cores read (written once per call by k_fs_prep_b, streamed by the GEMM's
+ *              CTAs with cp.async.bulk) */
 int32_t dccf_full_scores_splits(int32_t n_users, int32_t n_items);
+int64_t dccf_full_scores_ws_floats(int32_t n_items);
 int dccf_full_scores(int32_t n_users, int32_t n_items, const float* A, const float* B, const float* row_bias,
                      const float* col_bias, const float* col_scale, float g, float* out, int32_t k,
-                     float* topk_score, int64_t* topk_id, float* ws_score, int64_t* ws_id, void* stream);
+                     float* topk_score, int64_t* topk_id, float* ws_score, int64_t* ws_id, float* ws_items, void* stream);
 
 /* ---- host side: exact replay of the reference's negative sampler ---------------------------- */
 /* Replaces the Python loop of src/data_processor/DataProcessor.py:446-524 draw for draw.  HOST pointers.
