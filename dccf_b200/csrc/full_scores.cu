@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(128) k_fs_prep_b(const float* __restrict__ B, 
     put(64 + khalf * 4, (khalf == 0) ? make_float4(cs, cs * cb, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f));
 }
 
+// TOPK: fused per-user top-k (k <= KCAP); the matrix is written when prm.out is given (either or both).
+template <bool TOPK, int KCAP>
 __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stage0 = smem;
@@ -215,13 +217,16 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
         const int quarter = warp & 3, chalf = warp >> 2;
         const int64_t u = u0 + quarter * 32 + lane;
         const bool valid = u < prm.n_users;
-        float best_s[FS_KMAX];
-        int32_t best_i[FS_KMAX];
+        // running top-k of this (row, column half), ASCENDING: top_s[0] is the worst kept score = the threshold an item
+        // must beat (-inf until k items are in), top_s[k-1] the best.  Every index below is a compile-time constant
+        // (a first version kept the list descending and read its k-th entry: the compiler put the list in local
+        // memory, and the insertion path — taken by some lane in 61 % of the tiles — was most of the kernel's 660 M
+        // instructions).
+        float top_s[KCAP];
+        int32_t top_i[KCAP];
 #pragma unroll
-        for (int j = 0; j < FS_KMAX; ++j) { best_s[j] = -INFINITY; best_i[j] = -1; }
+        for (int j = 0; j < KCAP; ++j) { top_s[j] = -INFINITY; top_i[j] = -1; }
         const int k = prm.k;
-        float thr = -INFINITY;      // score of the current k-th entry; an item enters only when it beats it
-        int filled = 0;
         float* my_out = out_s + warp * 32 * FS_OUT_LD;
         for (int t = t_lo; t < t_hi; ++t) {
             const int n = t - t_lo, a = n & 1;
@@ -242,48 +247,40 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rm[j]) + __uint_as_float(rc[j]);
-            // this row's scores go to the warp's staging tile (write-out and dynamic re-reads below)
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                st4(my_out + lane * FS_OUT_LD + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-            if (prm.topk_score != nullptr) {
-                // cheap, fully unrolled filter: which of the 32 beat the current k-th score (or fill an empty
-                // slot)?  NaN never compares greater and is left out (ranked last).
-                uint32_t hits = 0;
+            if (TOPK) {
+                // columns beyond the catalogue (last tile only) never rank; NaN never compares greater and stays out
+                const int64_t live = (int64_t)prm.n_items - i0;
+                float best = -INFINITY;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const bool take = (filled < k) ? (v[j] == v[j]) : (v[j] > thr);
-                    hits |= take ? (1u << j) : 0u;
+                    if (live < 32 && j >= live) v[j] = -INFINITY;
+                    best = fmaxf(best, v[j]);
                 }
-                const int64_t live = (int64_t)prm.n_items - i0;          // columns that exist (last tile only: < 32)
-                if (live < 32) hits &= live <= 0 ? 0u : ((1u << live) - 1u);
-                // rare path, ONE copy of the insertion code: items arrive in ascending id, so an equal score
-                // never displaces an earlier one
-                while (hits) {
-                    const int j = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    float sc = my_out[lane * FS_OUT_LD + j];
-                    if (!(filled < k || sc > thr)) continue;        // the threshold moved since the filter
-                    int32_t ci = (int32_t)(i0 + j);
+                if (best > top_s[0]) {
+                    // some item of this row's 32 beats the threshold: items arrive in ascending id, so an equal score
+                    // never displaces an earlier one (strict comparisons)
 #pragma unroll
-                    for (int q = 0; q < FS_KMAX; ++q) {
-                        if (q < k && (best_i[q] < 0 || sc > best_s[q])) {
-                            const float ts = best_s[q];
-                            const int32_t ti = best_i[q];
-                            best_s[q] = sc;
-                            best_i[q] = ci;
-                            sc = ts;
-                            ci = ti;
+                    for (int j = 0; j < 32; ++j) {
+                        if (v[j] > top_s[0]) {
+                            top_s[0] = v[j];
+                            top_i[0] = (int32_t)(i0 + j);
+#pragma unroll
+                            for (int q = 0; q + 1 < KCAP; ++q) {
+                                if (q + 1 < k && top_s[q] > top_s[q + 1]) {
+                                    const float ts = top_s[q]; top_s[q] = top_s[q + 1]; top_s[q + 1] = ts;
+                                    const int32_t ti = top_i[q]; top_i[q] = top_i[q + 1]; top_i[q + 1] = ti;
+                                }
+                            }
                         }
                     }
-                    filled = min(filled + 1, k);
-#pragma unroll
-                    for (int q = 0; q < FS_KMAX; ++q)
-                        if (q == k - 1 && filled == k) thr = best_s[q];
                 }
             }
             if (prm.out != nullptr) {
-                // coalesced write-out of this warp's 32 x 32 tile: four rows (4 x 128 B) per instruction
+                // this row's scores go through the warp's staging tile: coalesced write-out of the 32 x 32 tile, four
+                // rows (4 x 128 B) per instruction
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    st4(my_out + lane * FS_OUT_LD + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
                 __syncwarp();
                 const int rsub = lane >> 3, c4 = (lane & 7) * 4;
                 const bool vec_ok = ((prm.n_items & 3) == 0);
@@ -308,13 +305,14 @@ __global__ void __launch_bounds__(FS_NT, 1) k_full_scores(const FsParams prm) {
                 __syncwarp();
             }
         }
-        if (prm.topk_score != nullptr && valid) {
+        if (TOPK && valid) {
+            // best first (the merge kernel reads descending lists, unfilled slots last)
             const size_t list = (size_t)(split * 2 + chalf);
             float* ds = prm.topk_score + (list * prm.n_users + u) * k;
             int64_t* di = prm.topk_id + (list * prm.n_users + u) * k;
 #pragma unroll
-            for (int q = 0; q < FS_KMAX; ++q)
-                if (q < k) { ds[q] = best_s[q]; di[q] = best_i[q]; }
+            for (int q = 0; q < KCAP; ++q)
+                if (q < k) { ds[k - 1 - q] = top_s[q]; di[k - 1 - q] = top_i[q]; }
         }
     }
 
@@ -392,7 +390,9 @@ extern "C" int dccf_full_scores(int32_t n_users, int32_t n_items, const float* A
     prm.topk_id = topk_score ? ws_id : nullptr;
     static PerDeviceOnce attr_once;
     if (attr_once.need()) {
-        cudaError_t e = cudaFuncSetAttribute(k_full_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_full_scores<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_full_scores<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_full_scores<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM);
         if (e != cudaSuccess) {
             set_error("dccf_full_scores: cannot opt in to %u bytes of shared memory: %s", FS_SMEM, cudaGetErrorString(e));
             return DCCF_ERR_CUDA;
@@ -402,7 +402,9 @@ extern "C" int dccf_full_scores(int32_t n_users, int32_t n_items, const float* A
     k_fs_prep_b<<<(unsigned)prm.n_tiles, 128, 0, stream>>>(B, col_bias, col_scale, n_items, ws_items);
     DCCF_CHECK_LAUNCH("k_fs_prep_b");
     dim3 grid((unsigned)((n_users + FS_BM - 1) / FS_BM), (unsigned)splits);
-    k_full_scores<<<grid, FS_NT, FS_SMEM, stream>>>(prm);
+    if (!topk_score) k_full_scores<false, 1><<<grid, FS_NT, FS_SMEM, stream>>>(prm);
+    else if (k <= 8) k_full_scores<true, 8><<<grid, FS_NT, FS_SMEM, stream>>>(prm);
+    else k_full_scores<true, 16><<<grid, FS_NT, FS_SMEM, stream>>>(prm);
     DCCF_CHECK_LAUNCH("k_full_scores");
     if (topk_score) {
         k_topk_merge<<<(unsigned)((n_users + 127) / 128), 128, 0, stream>>>(ws_score, ws_id, lists, n_users, k, topk_score, topk_id);

@@ -66,6 +66,7 @@ struct RankKs {
 // log2(t + 2) for the first RANK_STREAM_MAX_K rank positions, as float64 (filled by the host: std::log2 of the exact
 // integers, the values np.log2 gives): a table instead of a software FP64 log2 per position and user
 __constant__ double c_log2_pos[16];
+__constant__ double c_inv_log2_pos[16];      // 1 / log2(t + 2), correctly rounded (host division)
 
 constexpr int RANK_CHUNK = 2048;     // candidates of one user staged in shared memory (8 KB per warp); more: fallback
 constexpr int RANK_SURV = 128;       // survivors of the threshold test kept per user; more (massive ties): fallback
@@ -288,9 +289,12 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) k_rank_stream(
             const float lab = __shfl_sync(0xffffffffu, my_label, t);
             const float idl = __shfl_sync(0xffffffffu, ideal, t);
             if (t < kk) {
-                const double disc = c_log2_pos[t];       // log2(t + 2), rank_metrics.py:160 (np.log2 of positions 2, 3, ...)
-                dcg += (double)lab / disc;
-                idcg += (double)idl / disc;
+                // rel / log2(position + 1), rank_metrics.py:160.  0/1 labels (the ranking path's labels) take the tabulated
+                // reciprocal — 1 / x is the correctly rounded quotient either way, so the bits are those of the division;
+                // graded labels divide.  (The software FP64 division was half of the kernel's instructions.)
+                const double disc = c_log2_pos[t], inv = c_inv_log2_pos[t];
+                dcg += (lab == 0.f) ? 0.0 : (lab == 1.f ? inv : (double)lab / disc);
+                idcg += (idl == 0.f) ? 0.0 : (idl == 1.f ? inv : (double)idl / disc);
                 hit_sum += (double)lab;
                 nonzero += (lab != 0.f) ? 1 : 0;
             }
@@ -475,9 +479,13 @@ extern "C" int dccf_rank_eval_multi(const float* scores, const float* labels, co
     }
     static PerDeviceOnce table_once;
     if (table_once.need()) {
-        double h[16];
-        for (int t = 0; t < 16; ++t) h[t] = log2((double)(t + 2));
+        double h[16], hi[16];
+        for (int t = 0; t < 16; ++t) {
+            h[t] = log2((double)(t + 2));
+            hi[t] = 1.0 / h[t];
+        }
         cudaError_t e = cudaMemcpyToSymbol(c_log2_pos, h, sizeof(h));
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_inv_log2_pos, hi, sizeof(hi));
         if (e != cudaSuccess) {
             set_error("dccf_rank_eval_multi: cannot install the log2 table: %s", cudaGetErrorString(e));
             return DCCF_ERR_CUDA;
