@@ -289,6 +289,13 @@ def bench_train(model, X_all, steps, warmup, world, flush):
                 step3()
                 tl.collect()
             kernels_us, timeline_step_us = tl.summary()
+        if world > 1 and os.environ.get('DCCF_BENCH_RANK_TIMELINES'):
+            # diagnostics: every rank's own timeline of the captured step (stderr), absolute globaltimer of the first kernel
+            rank_ = int(os.environ.get('RANK', '0'))
+            starts = [int(min(int(r[i, 0]) for i in range(r.shape[0]) if r[i, 1] != 0)) for r in tl.rows]
+            print(json.dumps({'rank': rank_, 'step_us': timeline_step_us, 'first_kernel_ns_mod': [s_ % 10**9 for s_ in starts[:6]],
+                              'kernels': {k_: [round(v_['start_us'], 1), round(v_['end_us'], 1)] for k_, v_ in kernels_us.items()}}),
+                  file=sys.stderr, flush=True)
     else:
         n_s = min(n, warmup + 50)
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_s)]

@@ -353,7 +353,12 @@ __global__ void k_csr_build(const AdamAllArgs a, int phase) {
         if (pos < 0) return;                                   // (a record no link touched)
         const int32_t row = t.rec_row[r];
         if (phase == 0) {
-            if (pos == 0) t.csr_off[row] = atomicAdd(t.csr_pool, t.head[row] + 1);
+            if (pos == 0) {
+                t.csr_off[row] = atomicAdd(t.csr_pool, t.head[row] + 1);
+                // compact list of the step's touched rows (second half of the csr buffer, count in csr_pool[1]): the
+                // touched-row sweep walks THIS list — one half-warp per row, no pass over the records that own nothing
+                t.csr[t.n_rec + atomicAdd(t.csr_pool + 1, 1)] = row;
+            }
         } else {
             t.csr[t.csr_off[row] + pos] = (int32_t)r;
         }
@@ -656,7 +661,7 @@ __device__ __forceinline__ void touched_cta_done(const AdamAllArgs& a, const WIm
             if (wi.step_dev) wi.step_dev[0] += 1;
             if (wi.offset_dev) wi.offset_dev[0] += 1;
             for (int i = 0; i < a.n_tables; ++i)
-                if (a.t[i].csr_pool != nullptr) *a.t[i].csr_pool = 0;      // the CSR ranges of this step are released
+                if (a.t[i].csr_pool != nullptr) { a.t[i].csr_pool[0] = 0; a.t[i].csr_pool[1] = 0; }   // ranges and row list released
             *wi.cta_counter = 0;
         }
     }
@@ -683,12 +688,15 @@ __global__ void __launch_bounds__(256) k_adam_touched(const AdamAllArgs a, const
         const uint32_t half_mask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
         const int64_t hw_stride = ((int64_t)t.block_n * blockDim.x) >> 4;
         const bool csr = t.csr != nullptr;
-        for (int64_t r = ((int64_t)b * blockDim.x + threadIdx.x) >> 4; r < t.n_rec; r += hw_stride) {
-            int32_t row, n_list = 0;
+        // CSR mode: one half-warp per TOUCHED ROW (compact list built by k_csr_build); list mode: per record, the head
+        // record of a row's list owns the row
+        const int64_t n_work = csr ? (int64_t)__ldcg(t.csr_pool + 1) : t.n_rec;
+        for (int64_t r = ((int64_t)b * blockDim.x + threadIdx.x) >> 4; r < n_work; r += hw_stride) {
+            int32_t row, n_list = 0, off = 0, first = (int32_t)r;
             if (csr) {
-                // the record that arrived first at its row owns the row
-                row = (t.next[r] == 0) ? t.rec_row[r] : -1;
-                if (row >= 0) n_list = t.head[row] + 1;
+                row = __ldcg(t.csr + t.n_rec + r);
+                n_list = t.head[row] + 1;
+                off = t.csr_off[row];
             } else {
                 row = t.keys[rec_key_index(t.L, r)];
                 if (row < 0 || row >= t.n_rows || t.head[row] != (int32_t)r) row = -1;
@@ -697,7 +705,8 @@ __global__ void __launch_bounds__(256) k_adam_touched(const AdamAllArgs a, const
             __syncwarp(half_mask);          // every lane of the half-warp has read the head before lane 0 resets it
             const size_t o = (size_t)row * D + sub * 4;
             float4 p = ld4(t.table + o), m = ld4(t.m + o), q = ld4(t.v + o);
-            const float4 g = csr ? gather_row_grad_csr(t, (int32_t)r, t.csr_off[row], n_list, sub, half_mask,
+            if (csr && n_list == 1) first = __ldcg(t.csr + off);
+            const float4 g = csr ? gather_row_grad_csr(t, first, off, n_list, sub, half_mask,
                                                        list_s[threadIdx.x >> 4][0], list_s[threadIdx.x >> 4][1])
                                  : gather_row_grad(t, (int32_t)r, sub, half_mask, list_s[threadIdx.x >> 4][0], list_s[threadIdx.x >> 4][1]);
             if (sub == 0) t.head[row] = -1;

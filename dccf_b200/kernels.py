@@ -233,7 +233,7 @@ def adam_dense(p, m, v, g_parts, n_parts, part_stride, hp):
 
 
 def adam_table(table, m, v, rec_keys, rec_grads, n_seg, seg_len, key_seg_stride, grad_seg_stride, head, nxt, csr=None):
-    """csr = (rec_row [n_rec], csr_off [n_rows], csr [n_rec], csr_pool [1]) int32 tensors: CSR record lists (counting
+    """csr = (rec_row [n_rec], csr_off [n_rows], csr [2 * n_rec], csr_pool [2]) int32 tensors: CSR record lists (counting
     link + dccf_adam_csr_build) instead of linked lists."""
     t = AdamTable()
     if csr is not None:

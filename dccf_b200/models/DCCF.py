@@ -690,10 +690,10 @@ class DCCF(DMF):
 
     def _csr_bufs(self, which, n_rec, n_rows, opt):
         if opt.__dict__.get('csr_pool') is None:
-            opt.csr_pool = torch.zeros(2, dtype=torch.int32, device=self.uid_embeddings.weight.device)
-        k = 0 if which == 'u' else 1
+            opt.csr_pool = torch.zeros(4, dtype=torch.int32, device=self.uid_embeddings.weight.device)
+        k = 0 if which == 'u' else 2
         return (self._buf('rec_row_' + which, (n_rec,), torch.int32), self._buf('csr_off_' + which, (n_rows,), torch.int32),
-                self._buf('csr_' + which, (n_rec,), torch.int32), opt.csr_pool[k:k + 1])
+                self._buf('csr_' + which, (2 * n_rec,), torch.int32), opt.csr_pool[k:k + 2])
 
     def _step_tables(self, rec, P, opt, csr=False):
         """Descriptors of the optimizer step's tensors: the two embedding tables with their gradient records and W, b

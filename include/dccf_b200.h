@@ -260,10 +260,11 @@ typedef struct dccf_adam_table {
     int32_t* head; int32_t* next;      /* next: n_seg*seg_len entries, private to this table */
     /* CSR record lists (all four NULL: linked lists through head / next).  With them dccf_adam_link_ids COUNTS instead of
      * linking — head[row] = (records of the row) - 1, next[r] = arrival position of record r in its row, rec_row[r] = the
-     * row — dccf_adam_csr_build groups the record ids by row (csr_off [n_rows], csr [n_seg*seg_len]; csr_pool: one
-     * int32, zero between steps), and dccf_adam_touched reads a row's records with parallel loads instead of walking
-     * a list (the walk of the hottest item's list was the critical path of the data-parallel step).  Same summation
-     * order (ascending record index), same bits. */
+     * row — dccf_adam_csr_build groups the record ids by row (csr_off [n_rows]; csr [2 * n_seg*seg_len]: the grouped
+     * record ids, then the compact list of the step's touched rows; csr_pool: int32[2] = {ids used, rows touched}, zero
+     * between steps), and dccf_adam_touched runs one half-warp per TOUCHED ROW, reading its records with parallel
+     * loads instead of walking a list (the walk of the hottest item's list was the critical path of the data-parallel
+     * step).  Same summation order (ascending record index), same bits. */
     int32_t* rec_row; int32_t* csr_off; int32_t* csr; int32_t* csr_pool;
 } dccf_adam_table;
 typedef struct dccf_adam_tensor {

@@ -16,5 +16,6 @@ except Exception as e:
     print(sys.argv[1], 'parse failed', e)
 P
 }
-timeout 600 $TR bench.py --gpus 8 --steps 100 --warmup 5 --no-extra-legs > gpurun_out/bench_r2h_dp8.json 2> gpurun_out/bench_r2h_dp8.err; echo rc=$?; tail -c 400 gpurun_out/bench_r2h_dp8.err; show gpurun_out/bench_r2h_dp8.json
-DCCF_ADAM_CSR=0 timeout 600 $TR bench.py --gpus 8 --steps 100 --warmup 5 --no-extra-legs > gpurun_out/bench_r2h_dp8_nocsr.json 2>/dev/null; show gpurun_out/bench_r2h_dp8_nocsr.json
+DCCF_BENCH_RANK_TIMELINES=1 timeout 600 $TR bench.py --gpus 8 --steps 100 --warmup 5 --no-extra-legs > gpurun_out/bench_r2h_dp8.json 2> gpurun_out/bench_r2h_dp8.err; echo rc=$?; grep '"rank"' gpurun_out/bench_r2h_dp8.err | cut -c1-900; show gpurun_out/bench_r2h_dp8.json
+nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,temperature.gpu --format=csv,noheader
+
