@@ -43,7 +43,10 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-constexpr int DP_PIECE4 = 1024;      // float4 per piece staged in shared memory (16 KB)
+// float4 per piece staged in shared memory: 4 KB.  Not more: the push of the gradient records runs BESIDE the dW kernel
+// (96 KB of shared memory per CTA) and the side-stream Adam sweep (120 KB) — with a 16 KB piece the three no longer fit
+// an SM together and the dW kernel started 7 us later.
+constexpr int DP_PIECE4 = 256;
 
 // Each CTA owns a CONTIGUOUS range of the segment: it reads (or folds from the partial buffers) the range piece by piece
 // into shared memory and ships every piece to every peer with ONE bulk copy per peer issued by one lane — the TMA engine
