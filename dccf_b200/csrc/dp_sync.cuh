@@ -75,9 +75,14 @@ __device__ __forceinline__ void dp_wait_inline(const DpSync& s) {
                 const int total = s.world * ch.n_ctas;
                 bool ok;
                 do {
-                    ok = true;
+                    // every flag of the lane is loaded unconditionally, eight loads in flight: `ok = ok && load(..)` made
+                    // each load wait for the previous one — 50 dependent system-scope loads per lane at 8 ranks, 22 us
+                    // between the last push and the consumer noticing it
+                    int32_t lowest = 0x7fffffff;
+#pragma unroll 8
                     for (int i = threadIdx.x; i < total; i += 32)
-                        ok = ok && (ld_relaxed_sys(arrival + (i / ch.n_ctas) * DP_MAX_CTAS + (i % ch.n_ctas)) >= want);
+                        lowest = min(lowest, ld_relaxed_sys(arrival + (i / ch.n_ctas) * DP_MAX_CTAS + (i % ch.n_ctas)));
+                    ok = lowest >= want;
                     if (global_ns() - t0 > 60ull * 1000000000ull) __trap();      // a peer died: fail loudly (see spin_until)
                 } while (!__all_sync(0xffffffffu, ok));
             }
