@@ -691,6 +691,47 @@ __global__ void __launch_bounds__(256) k_adam_touched(const AdamAllArgs a, const
         // CSR mode: one half-warp per TOUCHED ROW (compact list built by k_csr_build); list mode: per record, the head
         // record of a row's list owns the row
         const int64_t n_work = csr ? (int64_t)__ldcg(t.csr_pool + 1) : t.n_rec;
+        if (csr) {
+            // TWO rows per half-warp and trip: their independent chains (row id -> count / range -> parameters, moments,
+            // record ids -> gradients) are in flight together — the sweep is bound by the latency of these dependent
+            // loads, not by their bytes
+            int32_t* idx_s = list_s[threadIdx.x >> 4][0];
+            int32_t* ord_s = list_s[threadIdx.x >> 4][1];
+            for (int64_t r = ((int64_t)b * blockDim.x + threadIdx.x) >> 4; r < n_work; r += 2 * hw_stride) {
+                const bool two = r + hw_stride < n_work;
+                const int32_t rowA = __ldcg(t.csr + t.n_rec + r);
+                const int32_t rowB = two ? __ldcg(t.csr + t.n_rec + r + hw_stride) : rowA;
+                const int32_t nA = t.head[rowA] + 1, nB = t.head[rowB] + 1;
+                const int32_t offA = t.csr_off[rowA], offB = t.csr_off[rowB];
+                __syncwarp(half_mask);      // every lane of the half-warp has read the heads before lane 0 resets them
+                const size_t oA = (size_t)rowA * D + sub * 4, oB = (size_t)rowB * D + sub * 4;
+                float4 pA = ld4(t.table + oA), mA = ld4(t.m + oA), qA = ld4(t.v + oA);
+                float4 pB = ld4(t.table + oB), mB = ld4(t.m + oB), qB = ld4(t.v + oB);
+                const int32_t fA = __ldcg(t.csr + offA), fB = __ldcg(t.csr + offB);
+                float4 gA, gB;
+                if (nA == 1 && nB == 1) {   // the common case: both single records, both loads in flight
+                    gA = ldg4(t.grads + rec_grad_index(t.L, fA) + sub * 4);
+                    gB = ldg4(t.grads + rec_grad_index(t.L, fB) + sub * 4);
+                } else {
+                    gA = gather_row_grad_csr(t, fA, offA, nA, sub, half_mask, idx_s, ord_s);
+                    gB = gather_row_grad_csr(t, fB, offB, nB, sub, half_mask, idx_s, ord_s);
+                }
+                if (sub == 0) {
+                    t.head[rowA] = -1;
+                    if (two) t.head[rowB] = -1;
+                }
+                adam_elem(pA.x, mA.x, qA.x, gA.x, s); adam_elem(pA.y, mA.y, qA.y, gA.y, s);
+                adam_elem(pA.z, mA.z, qA.z, gA.z, s); adam_elem(pA.w, mA.w, qA.w, gA.w, s);
+                st4(t.table + oA, pA); st4(t.m + oA, mA); st4(t.v + oA, qA);
+                if (two) {
+                    adam_elem(pB.x, mB.x, qB.x, gB.x, s); adam_elem(pB.y, mB.y, qB.y, gB.y, s);
+                    adam_elem(pB.z, mB.z, qB.z, gB.z, s); adam_elem(pB.w, mB.w, qB.w, gB.w, s);
+                    st4(t.table + oB, pB); st4(t.m + oB, mB); st4(t.v + oB, qB);
+                }
+            }
+            touched_cta_done(a, wi, sync);
+            return;
+        }
         for (int64_t r = ((int64_t)b * blockDim.x + threadIdx.x) >> 4; r < n_work; r += hw_stride) {
             int32_t row, n_list = 0, off = 0, first = (int32_t)r;
             if (csr) {

@@ -806,7 +806,6 @@ class DCCF(DMF):
     # items' feature rows, W with its moments and operand images): DCCF_L2_PREFETCH=0 switches it off (A/B)
     l2_prefetch = os.environ.get('DCCF_L2_PREFETCH', '1') != '0'
     dp_fold_sync = os.environ.get('DCCF_DP_FOLD', '1') != '0'
-    expo_on_side_stream = os.environ.get('DCCF_EXPO_SIDE', '1') != '0'
     # data-parallel training over a device-resident epoch: every rank's ids of the WHOLE epoch (chunk) are all-gathered
     # once, outside the steps, so no step waits for an id exchange (DCCF_DP_EPOCH_IDS=0: one id exchange per step)
     dp_epoch_ids = os.environ.get('DCCF_DP_EPOCH_IDS', '1') != '0'
@@ -858,13 +857,8 @@ class DCCF(DMF):
             # the record lists of the GLOBAL step are linked on the side stream
             extra = kernels.make_link_extra(stage=stage, prefetch_feat=self.feature_embedding if self.l2_prefetch else None,
                                             prefetch_dense=(wimg,) if self.l2_prefetch else None)
-        # The exposure softmax of the local pairs is read by the middle kernel only: with the streams available it is
-        # evaluated on the third stream BESIDE the forward (its two passes of dependent loads — ids -> exposure values —
-        # were most of k_link_ids' 5 us, all of them in front of the forward); DCCF_EXPO_SIDE=0: inside k_link_ids.
-        expo_side = overlap and self.overlap_split_adam and self.expo_on_side_stream
         kernels.adam_link_ids(self._dims(), call['X'], call['sample_item'], opt.head_u, next_u, opt.head_i, next_i,
-                              None if expo_side else self._expo(), None if expo_side else expo_e,
-                              None if expo_side else expo_den, n_seg=0 if dp else 1, extra=extra)
+                              self._expo(), expo_e, expo_den, n_seg=0 if dp else 1, extra=extra)
 
         # data parallel, folded synchronisation (DCCF_DP_FOLD=0: the round-1 sequence push / wait / consume / done as
         # separate launches): consumers wait for the peers' segments in their own prologue and their last CTA hands the
@@ -915,14 +909,6 @@ class DCCF(DMF):
                 if dp and not fold and epoch_ids is None:
                     ix.done()
                 done.record(side)
-            expo_done = None
-            if expo_side:
-                expo_done = torch.cuda.Event()
-                ship.wait_event(fork)
-                with torch.cuda.stream(ship):
-                    kernels.adam_link_ids(self._dims(), call['X'], call['sample_item'], opt.head_u, next_u, opt.head_i,
-                                          next_i, self._expo(), expo_e, expo_den, n_seg=0)
-                    expo_done.record(ship)
             if csr:
                 # the CSR ranges of the step's record lists: two small launches on the third stream, beside the sweep
                 # and the forward (the touched-row sweep that needs them runs after the backward)
@@ -931,20 +917,19 @@ class DCCF(DMF):
                 with torch.cuda.stream(ship):
                     kernels.adam_csr_build(tables)
                     csr_done.record(ship)
-            mid_done, shipped = torch.cuda.Event(), torch.cuda.Event()
+            if dp:
+                mid_done, shipped = torch.cuda.Event(), torch.cuda.Event()
 
-            def between(phase):        # noqa: E306
-                if phase == 1 and expo_done is not None:
-                    main.wait_event(expo_done)         # the middle kernel reads the exposure softmax
-                if phase == 2 and dp:                  # the gradient records leave while the dW kernel runs
-                    mid_done.record(main)
-                    ship.wait_event(mid_done)
-                    with torch.cuda.stream(ship):
-                        if fold:
-                            ex.rec.push()
-                        else:
-                            ex.exchange_records()
-                        shipped.record(ship)
+                def between(phase):        # noqa: E306  the gradient records leave while the dW kernel runs
+                    if phase == 2:
+                        mid_done.record(main)
+                        ship.wait_event(mid_done)
+                        with torch.cuda.stream(ship):
+                            if fold:
+                                ex.rec.push()
+                            else:
+                                ex.exchange_records()
+                            shipped.record(ship)
         else:
             if dp:
                 link_global()

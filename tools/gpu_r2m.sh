@@ -1,11 +1,9 @@
 #!/bin/bash
-# Round 2, GPU call M (2 GPUs): exposure softmax on the third stream (A/B), polling fix at N = 2.
+# Round 2, GPU call M/N (2 GPUs): two rows per half-warp in the touched-row sweep, polling fix at N = 2.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 > gpurun_out/tests_r2m.log
 tail -3 gpurun_out/tests_r2m.log
-for e in 1 0; do
-  echo "== timeline DCCF_EXPO_SIDE=$e"; DCCF_EXPO_SIDE=$e timeout 300 python tools/step_timeline.py --steps 40 2>&1 | tail -9
-done
+timeout 300 python tools/step_timeline.py --steps 40 2>&1 | tail -9
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533"
 show() {
 python - "$1" <<'P'
