@@ -761,3 +761,34 @@ def test_every_cli_flag_equals_reference():
         assert list(a.option_strings) == w['options'], w
         assert a.default == w['default'], w
         assert getattr(a.type, '__name__', None) == w['type'], w
+
+
+def test_candidate_layout_contiguous_runs_and_reference_layout():
+    """Host side of the ranker call (dccf_b200/models/BaseModel.py::candidate_layout): users whose rows are one
+    contiguous run are ranked in place (no index array), the reference's evaluation-set layout — all positives, then
+    the blocks of negatives (src/data_processor/DataProcessor.py:92-111) — goes through the grouping index."""
+    from dccf_b200.models.BaseModel import candidate_layout, group_candidates
+    uid = np.repeat([7, 3, 9, 4], [5, 1, 1001, 2])                    # contiguous, users NOT ascending
+    rows, off = candidate_layout(uid)
+    assert rows is None and off.tolist() == [0, 5, 6, 1007, 1009]
+    rows, off = candidate_layout(np.array([], dtype=np.int64))
+    assert rows is None and off.tolist() == [0]
+    pos = np.array([1, 1, 2, 5])                                       # positives first, negatives of each user after
+    uid = np.concatenate([pos, np.repeat([1, 2, 5], 3)])
+    rows, off = candidate_layout(uid)
+    users, want_rows, want_off = group_candidates(uid)
+    assert rows is not None and np.array_equal(rows, want_rows) and np.array_equal(off, want_off)
+    for g, u in enumerate(users):
+        assert set(uid[rows[off[g]:off[g + 1]]].tolist()) == {u}
+    assert off.tolist() == [0, 5, 9, 13]
+
+
+def test_n_layers_other_than_one_is_rejected_at_construction():
+    """--n_layers is parsed like the reference's (src/models/DMF.py:13-16) but the kernels implement the default single
+    Linear(64 + F -> 64): any other depth fails when the model is built, with a message — not at the first predict."""
+    import pytest
+    from dccf_b200.models.DCCF import DCCF
+    with pytest.raises(ValueError, match='n_layers'):
+        DCCF(path='', dataset='', sentence_model='', sample_num=2, attribute_num=1, std=0.0, label_min=0, label_max=1,
+             feature_num=0, user_num=4, item_num=5, u_vector_size=64, i_vector_size=64, n_layers=2, random_seed=1,
+             model_path='/tmp/x.pt', feature_embedding=torch.zeros(5, 64), expo_prob=torch.ones(4, 5))
