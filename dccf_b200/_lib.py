@@ -12,7 +12,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 _VARIANT = os.environ.get('DCCF_LIB_VARIANT', '')          # A/B build variants, see dccf_b200/build.py
 LIB_PATH = os.path.join(HERE, 'libdccf_b200%s.so' % (('_' + _VARIANT) if _VARIANT else ''))
-ABI_VERSION = 32
+ABI_VERSION = 33
 DIM = 64
 
 
@@ -75,6 +75,10 @@ class LinkExtra(ctypes.Structure):
                 ('sync', ctypes.POINTER(DpSync)), ('rec_row_user', ctypes.c_void_p), ('rec_row_item', ctypes.c_void_p)]
 
 
+class BatchRef(ctypes.Structure):
+    _fields_ = [('epoch_ptrs_dev', ctypes.c_void_p), ('cursor_dev', ctypes.c_void_p)]
+
+
 class AdamTensor(ctypes.Structure):
     _fields_ = [('p', ctypes.c_void_p), ('m', ctypes.c_void_p), ('v', ctypes.c_void_p), ('n', ctypes.c_int64),
                 ('g_parts', ctypes.c_void_p), ('n_parts', ctypes.c_int32), ('_pad', ctypes.c_int32),
@@ -113,7 +117,7 @@ _SIGNATURES = {
     'dccf_train_fwd_bwd_tc': (ctypes.c_int, [ctypes.POINTER(Dims), _P, _P, _P, _P, _P, ctypes.POINTER(Expo), _P, _P, _P,
                                              ctypes.c_int64, ctypes.POINTER(Rng), ctypes.c_int32, _P, _P, _P,
                                              ctypes.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
-                                             ctypes.c_int32, _P, _P]),
+                                             ctypes.POINTER(BatchRef), ctypes.c_int32, _P, _P]),
     'dccf_adam_sweep': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int64, _P, _P,
                                        ctypes.POINTER(Adam), _P]),
     'dccf_adam_sweep_seg': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int32, ctypes.c_int64,
@@ -131,7 +135,7 @@ _SIGNATURES = {
     'dccf_adam_csr_build': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, _P]),
     'dccf_adam_touched': (ctypes.c_int, [ctypes.POINTER(AdamTable), ctypes.c_int32, ctypes.POINTER(AdamTensor),
                                          ctypes.c_int32, ctypes.POINTER(Adam), ctypes.c_int32, _P, ctypes.c_int32,
-                                         ctypes.c_int32, _P, _P, _P, ctypes.POINTER(DpSync), _P]),
+                                         ctypes.c_int32, _P, _P, _P, _P, ctypes.POINTER(DpSync), _P]),
     'dccf_train_prep_w_image': (ctypes.c_int, [_P, ctypes.c_int32, _P, _P]),
     'dccf_debug_timeline_train': (ctypes.c_int, [_P]),
     'dccf_debug_timeline_adam': (ctypes.c_int, [_P]),

@@ -477,18 +477,20 @@ __device__ __forceinline__ void prefetch_rows(const float* const (&t)[3], int32_
 
 __global__ void __launch_bounds__(256) k_link_ids(const LinkIdsArgs a) {
     tl_begin(0);
-    tl_end(0);      // (short single wave: start and end are indistinguishable at the timer's resolution)
+    // the next kernel on the stream may have been launched as a programmatic dependent (the partial-product kernel of the
+    // step reads nothing this launch writes): it may start now
+    asm volatile("griddepcontrol.launch_dependents;");
     __shared__ int64_t s_batch;
-    // epoch_ptrs_dev given: X_out given -> this launch STAGES batch *cursor of the rank's own epoch (and advances the
-    // cursor); X_out null -> data-parallel link of the global step from the epoch-wide gather of every rank's ids
-    // (slots 2..5: base addresses of X_all [world, n, P, 2] / si_all [world, n, P, S] and their per-rank strides), batch
-    // *cursor - 1: the staging launch of this step has already advanced the cursor
+    // epoch_ptrs_dev given: X_out given -> this launch STAGES batch *cursor of the rank's own epoch; X_out null ->
+    // data-parallel link of the global step from the epoch-wide gather of every rank's ids (slots 2..5: base addresses of
+    // X_all [world, n, P, 2] / si_all [world, n, P, S] and their per-rank strides).  Nobody moves the cursor before the
+    // end of the step (dccf_adam_touched, advance_cursor_dev): the forward reads the same batch beside this launch.
     const bool staged = a.extra.epoch_ptrs_dev != nullptr && a.extra.X_out != nullptr;
     const bool epoch_global = a.extra.epoch_ptrs_dev != nullptr && a.extra.X_out == nullptr;
     const int64_t *X = a.X, *si = a.sample_item, *X_local = a.X_local, *si_local = a.si_local;
     int64_t seg_stride_x = a.seg_stride, seg_stride_s = a.seg_stride;
     if (staged || epoch_global) {
-        if (threadIdx.x == 0) s_batch = *a.extra.cursor_dev - (epoch_global ? 1 : 0);
+        if (threadIdx.x == 0) s_batch = *a.extra.cursor_dev;
         __syncthreads();
         const int base = epoch_global ? 2 : 0;
         X = reinterpret_cast<const int64_t*>(a.extra.epoch_ptrs_dev[base]) + s_batch * a.n_pairs * 2;
@@ -575,21 +577,19 @@ __global__ void __launch_bounds__(256) k_link_ids(const LinkIdsArgs a) {
             }
         }
     }
-    if (staged || a.sync.n_done > 0) {
-        // the last CTA to finish moves the cursor (every CTA has read it above) / hands the id buffer back to the peers
+    if (a.sync.n_done > 0) {
+        // the last CTA to finish hands the id buffer back to the peers
         __shared__ int s_last;
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
             s_last = (atomicAdd(a.extra.stage_counter, 1) == (int32_t)gridDim.x - 1) ? 1 : 0;
-            if (s_last) {
-                if (staged) *a.extra.cursor_dev = s_batch + 1;
-                *a.extra.stage_counter = 0;
-            }
+            if (s_last) *a.extra.stage_counter = 0;
         }
         __syncthreads();
-        if (s_last && a.sync.n_done > 0) dp_done_inline(a.sync);
+        if (s_last) dp_done_inline(a.sync);
     }
+    tl_end(0);
 }
 
 #ifndef DCCF_ADAM_SIDE_SMEM_KB
@@ -602,7 +602,7 @@ constexpr int ADAM_SIDE_SMEM = DCCF_ADAM_SIDE_SMEM_KB * 1024;
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void stcg4(float* p, const float4& v) { __stcg(reinterpret_cast<float4*>(p), v); }
 
-__global__ void __launch_bounds__(256, 1) k_adam_untouched(const AdamAllArgs a) {
+__global__ void __maxnreg__(64) k_adam_untouched(const AdamAllArgs a) {
     tl_begin(1);
     const AdamScalars s = resolve_adam(a.hp);
     const int bid = (int)blockIdx.x;
@@ -614,10 +614,22 @@ __global__ void __launch_bounds__(256, 1) k_adam_untouched(const AdamAllArgs a) 
         const int half = (threadIdx.x >> 4) & 1;
         const int64_t warp = ((int64_t)b * blockDim.x + threadIdx.x) >> 5;   // (block size: see dccf_adam_untouched)
         const int64_t n_warps = ((int64_t)t.block_n * blockDim.x) >> 5;
+        // One trip = 4 rows per warp (two per half-warp).  The touched flags of the NEXT trip are loaded, and its rows
+        // requested into L2, before this trip's rows are read: a trip then costs one memory round trip that mostly ends
+        // in L2 instead of two that end in DRAM.
+        auto row_ok = [&](int64_t r) { return r < t.n_rows && t.head[r] == -1; };
+        auto request = [&](int64_t r) {
+            if (r >= t.n_rows || (sub & 7) != 0) return;              // one lane per 128-byte line
+            const size_t o = (size_t)r * D + sub * 4;
+            prefetch_l2(t.table + o); prefetch_l2(t.m + o); prefetch_l2(t.v + o);
+        };
+        bool v0 = 4 * warp < t.n_rows && row_ok(4 * warp + half), v1 = 4 * warp < t.n_rows && row_ok(4 * warp + half + 2);
         for (int64_t w = warp; 4 * w < t.n_rows; w += n_warps) {
             const int64_t r0 = 4 * w + half, r1 = r0 + 2;
-            const bool v0 = r0 < t.n_rows && t.head[r0] == -1;
-            const bool v1 = r1 < t.n_rows && t.head[r1] == -1;
+            const int64_t n0 = r0 + 4 * n_warps, n1 = n0 + 2;
+            request(n0);
+            request(n1);
+            const bool nv0 = row_ok(n0), nv1 = row_ok(n1);
             const size_t o0 = (size_t)(v0 ? r0 : 0) * D + sub * 4, o1 = (size_t)(v1 ? r1 : 0) * D + sub * 4;
             float4 p0, m0, q0, p1, m1, q1;
             if (v0) { p0 = ldcg4(t.table + o0); m0 = ldcg4(t.m + o0); q0 = ldcg4(t.v + o0); }
@@ -632,6 +644,7 @@ __global__ void __launch_bounds__(256, 1) k_adam_untouched(const AdamAllArgs a) 
                 adam_elem(p1.z, m1.z, q1.z, 0.f, s); adam_elem(p1.w, m1.w, q1.w, 0.f, s);
                 stcg4(t.table + o1, p1); stcg4(t.m + o1, m1); stcg4(t.v + o1, q1);
             }
+            v0 = nv0; v1 = nv1;
         }
         __syncthreads();
         tl_end(1);
@@ -647,6 +660,7 @@ struct WImageArgs {
     int32_t* cta_counter;    // zero on entry, zero again on exit
     int32_t* step_dev;
     uint64_t* offset_dev;
+    int64_t* cursor_dev;     // batch cursor of a device-resident epoch (dccf_link_extra / dccf_batch_ref): += 1
 };
 
 __device__ __forceinline__ void touched_cta_done(const AdamAllArgs& a, const WImageArgs& wi, const DpSync& sync) {
@@ -660,6 +674,7 @@ __device__ __forceinline__ void touched_cta_done(const AdamAllArgs& a, const WIm
         if (s_last) {
             if (wi.step_dev) wi.step_dev[0] += 1;
             if (wi.offset_dev) wi.offset_dev[0] += 1;
+            if (wi.cursor_dev) wi.cursor_dev[0] += 1;
             for (int i = 0; i < a.n_tables; ++i)
                 if (a.t[i].csr_pool != nullptr) { a.t[i].csr_pool[0] = 0; a.t[i].csr_pool[1] = 0; }   // ranges and row list released
             *wi.cta_counter = 0;
@@ -766,17 +781,18 @@ __global__ void __launch_bounds__(256) k_adam_touched(const AdamAllArgs a, const
         const bool image = wi.img != nullptr && wi.tensor == i;
         for (int64_t e = (int64_t)b * blockDim.x + threadIdx.x; e < d.n; e += stride) {
             float p = d.p[e], m = d.m[e], v = d.v[e];
-            // partials in ascending order, eight loads in flight at a time
+            // partials added in ascending order, up to sixteen loads in flight at a time (the dW kernel of the reference
+            // shape leaves 15: a rolled tail loop waited for them one L2 round trip after the other)
             float g = 0.f;
-            int32_t k = 0;
-            for (; k + 8 <= d.n_parts; k += 8) {
-                float t8[8];
+            for (int32_t k = 0; k < d.n_parts; k += 16) {
+                float t16[16];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) t8[q] = __ldg(d.g_parts + (size_t)(k + q) * d.part_stride + e);
+                for (int q = 0; q < 16; ++q)
+                    if (k + q < d.n_parts) t16[q] = __ldg(d.g_parts + (size_t)(k + q) * d.part_stride + e);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) g += t8[q];
+                for (int q = 0; q < 16; ++q)
+                    if (k + q < d.n_parts) g += t16[q];
             }
-            for (; k < d.n_parts; ++k) g += __ldg(d.g_parts + (size_t)k * d.part_stride + e);
             adam_elem(p, m, v, g, s);
             d.p[e] = p; d.m[e] = m; d.v[e] = v;
             if (image) {
@@ -846,6 +862,8 @@ __global__ void __launch_bounds__(1024) k_stage_batch(const uint64_t* __restrict
 static int marshal_sync(const char* who, const dccf_dp_sync* in, DpSync* out) {
     out->world = 1; out->rank = 0; out->n_wait = 0; out->n_done = 0;
     out->loss_parts = nullptr; out->loss_stride = 0; out->n_loss = 0; out->loss_out = nullptr;
+    static const int fence_mode = [] { const char* v = getenv("DCCF_DP_FENCE"); return v != nullptr ? atoi(v) : 1; }();   // A/B knob (dp_sync.cuh)
+    out->fence_mode = fence_mode;
     if (in == nullptr) return DCCF_OK;
     DCCF_CHECK_ARG(in->world >= 1 && in->world <= DP_MAX_WORLD && in->rank >= 0 && in->rank < in->world,
                    "%s: sync: world %d / rank %d outside [1,%d]", who, in->world, in->rank, DP_MAX_WORLD);
@@ -1073,9 +1091,8 @@ extern "C" int dccf_adam_link_ids(const dccf_dims* dims, const int64_t* X, const
     DCCF_CHECK_ARG(n_pairs * n_seg * (dims->n_samples + 1) < ((int64_t)1 << 31), "dccf_adam_link_ids: too many records");
     DCCF_CHECK_ARG(expo == nullptr || (expo_e && expo_den), "dccf_adam_link_ids: expo needs expo_e and expo_den");
     const bool epoch_global = staged && extra->X_out == nullptr;
-    DCCF_CHECK_ARG(!staged || epoch_global || (n_seg <= 1 && extra->cursor_dev && extra->stage_counter &&
-                                               (dims->n_samples == 0 || extra->sample_item_out)),
-                   "dccf_adam_link_ids: staging needs n_seg <= 1, cursor, output buffers and the CTA counter");
+    DCCF_CHECK_ARG(!staged || epoch_global || (n_seg <= 1 && extra->cursor_dev && (dims->n_samples == 0 || extra->sample_item_out)),
+                   "dccf_adam_link_ids: staging needs n_seg <= 1, the cursor and the output buffers");
     DCCF_CHECK_ARG(!epoch_global || (extra->cursor_dev != nullptr && n_seg >= 1), "dccf_adam_link_ids: the epoch-wide link needs the cursor and n_seg >= 1");
     if (n_pairs <= 0) return DCCF_OK;
     LinkIdsArgs a;
@@ -1166,12 +1183,13 @@ extern "C" int dccf_adam_untouched(const dccf_adam_table* tables, int32_t n_tabl
             }
             attr_once.mark();
         }
-        // threads_per_cta (0 = default 128; DCCF_SIDE_THREADS overrides).  Measured (tools/step_timeline.py, electronics
-        // shape): 256 threads finish the sweep in 29 us but slow the concurrent forward / middle kernels by 4 / 6 us
-        // (L2 bandwidth); 128 threads take 45 us — still hidden behind the 50 us of forward + backward on one GPU — and
-        // cost 2 us; 64 threads (82 us) no longer fit.  Data-parallel steps start the sweep later (after the id exchange)
-        // and ask for 256.
-        int side_threads = (threads_per_cta >= 32 && threads_per_cta <= 256) ? (threads_per_cta / 32) * 32 : 128;
+        // threads_per_cta (0 = default 224; DCCF_SIDE_THREADS overrides).  The CTA has to stay resident beside the
+        // tensor-core kernels AND the middle kernel (768 threads x 64 registers = 3/4 of the register file): 7 warps x 64
+        // registers fit, 8 do not.  Measured (tools/step_timeline.py, electronics shape, L2 flushed): 128 threads swept
+        // the tables in 46 us — the longest chain of the step once k_link_ids had left the forward's way; a launch
+        // that did not fit beside the middle kernel (160 / 192 threads at 70 registers) held that kernel back until the
+        // sweep had finished (+15 us).
+        int side_threads = (threads_per_cta >= 32 && threads_per_cta <= 256) ? (threads_per_cta / 32) * 32 : 224;
         {
             const char* v = getenv("DCCF_SIDE_THREADS");
             if (v != nullptr && atoi(v) >= 32 && atoi(v) <= 256) side_threads = (atoi(v) / 32) * 32;
@@ -1203,7 +1221,8 @@ extern "C" int dccf_adam_csr_build(const dccf_adam_table* tables, int32_t n_tabl
 extern "C" int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
                                  int32_t n_dense, const dccf_adam* hp, int32_t already_linked, float* w_image,
                                  int32_t w_image_tensor, int32_t w_image_K, int32_t* cta_counter, int32_t* advance_step_dev,
-                                 uint64_t* advance_offset_dev, const dccf_dp_sync* sync, void* stream_) {
+                                 uint64_t* advance_offset_dev, int64_t* advance_cursor_dev, const dccf_dp_sync* sync,
+                                 void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     AdamAllArgs a;
     int32_t blocks = 0, link_blocks = 0;
@@ -1215,7 +1234,8 @@ extern "C" int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables
     WImageArgs wi;
     wi.img = w_image; wi.tensor = w_image_tensor; wi.K = w_image_K;
     wi.cta_counter = cta_counter; wi.step_dev = advance_step_dev; wi.offset_dev = advance_offset_dev;
-    DCCF_CHECK_ARG(cta_counter != nullptr || (advance_step_dev == nullptr && advance_offset_dev == nullptr),
+    wi.cursor_dev = advance_cursor_dev;
+    DCCF_CHECK_ARG(cta_counter != nullptr || (advance_step_dev == nullptr && advance_offset_dev == nullptr && advance_cursor_dev == nullptr),
                    "dccf_adam_touched: advancing the counters needs cta_counter");
     DpSync ds;
     rc = marshal_sync("dccf_adam_touched", sync, &ds);

@@ -55,9 +55,12 @@ constexpr int DP_PIECE4 = 256;
 // peer saw the dW / db segment 24 us after the push kernel had ended.)  Lane p then waits for ITS copies to complete and
 // publishes the CTA's arrival on peer p with a release store: one arrival flag per (source rank, source CTA) on every
 // peer, no grid-wide counter, no second fence.  The consumer waits for all of a push's flags.
+// FOLD: some ranges of the segment are sums of partial buffers (dW / db): sixteen float4 loads in flight per thread — a
+// register budget the plain pushes (ids, gradient records: they run beside the dW kernel and the sweep) do not pay for
+template <bool FOLD>
 __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send, int64_t seg, DpPeers peers, int world,
                                                  int rank, int64_t flag_off, const int32_t* __restrict__ epoch_dev,
-                                                 int32_t* cta_counter, const DpFolds folds) {
+                                                 int32_t* cta_counter, const DpFolds folds, const bool strict) {
     __shared__ __align__(128) float4 piece[DP_PIECE4];
     // debug timeline slot by what is pushed: 8 ids (small segment), 10 gradient records, 11 dW / db / loss (folded partials)
     const int tl_slot = folds.n > 0 ? 11 : (seg < 16384 ? 8 : 10);
@@ -73,8 +76,9 @@ __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send,
         const int64_t m = max((int64_t)0, min((int64_t)DP_PIECE4, hi - base));
         for (int64_t i = base + threadIdx.x; i < base + m; i += blockDim.x) {
             int which = -1;
-            for (int k = 0; k < folds.n; ++k)
-                if (i >= folds.f[k].off4 && i < folds.f[k].off4 + folds.f[k].n4) which = k;
+            if (FOLD)
+                for (int k = 0; k < folds.n; ++k)
+                    if (i >= folds.f[k].off4 && i < folds.f[k].off4 + folds.f[k].n4) which = k;
             float4 v;
             if (which < 0) {
                 v = src[i];
@@ -82,17 +86,14 @@ __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send,
                 const DpFold& f = folds.f[which];
                 const float* pp = f.parts + (i - f.off4) * 4;
                 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                int32_t p8 = 0;
-                for (; p8 + 8 <= f.n_parts; p8 += 8) {       // eight loads in flight, added in ascending order
-                    float4 t8[8];
+                for (int32_t p0 = 0; p0 < f.n_parts; p0 += 16) {      // up to sixteen loads in flight, added in ascending order
+                    float4 t16[16];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) t8[j] = __ldg(reinterpret_cast<const float4*>(pp + (size_t)(p8 + j) * f.stride));
+                    for (int j = 0; j < 16; ++j)
+                        if (p0 + j < f.n_parts) t16[j] = __ldg(reinterpret_cast<const float4*>(pp + (size_t)(p0 + j) * f.stride));
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { v.x += t8[j].x; v.y += t8[j].y; v.z += t8[j].z; v.w += t8[j].w; }
-                }
-                for (; p8 < f.n_parts; ++p8) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(pp + (size_t)p8 * f.stride));
-                    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                    for (int j = 0; j < 16; ++j)
+                        if (p0 + j < f.n_parts) { v.x += t16[j].x; v.y += t16[j].y; v.z += t16[j].z; v.w += t16[j].w; }
                 }
             }
             piece[i - base] = v;
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send,
             // peers have finished reading what this rank pushed last step (checked once per CTA, after the first loads)
             if ((int)threadIdx.x < world) {
                 const int32_t* consumed = reinterpret_cast<const int32_t*>(peers.base[rank] + flag_off) + DP_FLAG_CONSUMED;
-                spin_until(consumed + threadIdx.x, epoch - 1);
+                spin_until(consumed + threadIdx.x, epoch - 1, strict);
             }
             waited = true;
         }
@@ -114,10 +115,14 @@ __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send,
         }
         __syncthreads();
     }
+    if (FOLD) { tl_begin(14); tl_end(14); }  // (debug timeline: every piece folded and handed to the copy engine)
     if ((int)threadIdx.x < world) {
         bulk_wait0();                        // this lane's copies to its peer are complete
+        if (FOLD) { tl_begin(15); tl_end(15); }
         asm volatile("fence.proxy.async;" ::: "memory");
-        st_release_sys(reinterpret_cast<int32_t*>(peers.base[threadIdx.x] + flag_off) + rank * DP_MAX_CTAS + blockIdx.x, epoch);
+        int32_t* flag = reinterpret_cast<int32_t*>(peers.base[threadIdx.x] + flag_off) + rank * DP_MAX_CTAS + blockIdx.x;
+        if (strict) st_release_sys(flag, epoch);
+        else st_relaxed_sys(flag, epoch);        // (the copies it announces are complete: lean protocol, dp_sync.cuh)
     }
     tl_end(tl_slot);
 }
@@ -172,12 +177,17 @@ static int dp_push_impl(const float* send, int64_t seg_floats, const uint64_t* p
     DCCF_CHECK_ARG(seg_floats > 0 && seg_floats % 4 == 0, "dccf_dp_push: segment length must be a positive multiple of 4 floats");
     DCCF_CHECK_ARG(rank >= 0 && rank < world, "dccf_dp_push: rank %d outside [0,%d)", rank, world);
     const int64_t ctas = dp_push_ctas(seg_floats);
+    static const bool strict = [] { const char* v = getenv("DCCF_DP_FENCE"); return v != nullptr && atoi(v) == 2; }();
     static PerDeviceOnce carve_once;      // (same carveout as its neighbours in the step, see dccf_adam_link_ids)
     if (carve_once.need()) {
-        cudaFuncSetAttribute(k_dp_push, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_dp_push<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_dp_push<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         carve_once.mark();
     }
-    k_dp_push<<<(unsigned)ctas, 256, 0, stream>>>(send, seg_floats, peers, world, rank, flag_off, epoch_dev, cta_counter, folds);
+    if (folds.n > 0)
+        k_dp_push<true><<<(unsigned)ctas, 256, 0, stream>>>(send, seg_floats, peers, world, rank, flag_off, epoch_dev, cta_counter, folds, strict);
+    else
+        k_dp_push<false><<<(unsigned)ctas, 256, 0, stream>>>(send, seg_floats, peers, world, rank, flag_off, epoch_dev, cta_counter, folds, strict);
     DCCF_CHECK_LAUNCH("k_dp_push");
     return DCCF_OK;
 }

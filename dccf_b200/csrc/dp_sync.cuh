@@ -32,12 +32,27 @@ __device__ __forceinline__ int32_t ld_relaxed_sys(const int32_t* p) {
 __device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(int32_t* p, int32_t v) {
+    asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// System-scope fences are the expensive part of this protocol on B200 (measured on 2 and 8 GPUs, tools/step_timeline
+// stamps): an acquire load or release store at .sys scope stalls its thread 3-4 us, and one fence.sc.sys per CTA from
+// the three CTAs an SM holds serialises to 3 / 6 / 9 us.  The LEAN protocol (default) therefore keeps exactly the
+// ordering each hand-over needs:
+//   producer, data -> arrival flag: the bulk copies are waited for (cp.async.bulk.wait_group 0: performed at the peer's
+//     L2, the point of coherence of its memory) before a relaxed store of the flag travels the same way;
+//   consumer, arrival flag -> data: relaxed polling, CTA barrier, ONE fence.acq_rel.gpu (orders the CTA's later loads and
+//     drops the SM's L1 lines), barrier — the peer's writes are already in this GPU's L2 when its flag is;
+//   consumer -> producer, consumed flag (write-after-read): the readers' loads have returned before the last CTA's
+//     relaxed store is issued (gpu-scope fence + atomic counter between them); the producer polls it relaxed and its
+//     copies are control-dependent on what it saw.
+// DCCF_DP_FENCE=2 restores the strict forms everywhere (acquire loads, release stores, fence.sc.sys) for comparison.
 // Spin until *p >= want.  A peer that died (or never reaches this step) must not leave this GPU spinning for ever:
 // after 60 s — four orders of magnitude beyond any legitimate wait, start-up skew included — the kernel traps, the
 // process sees a CUDA error and the job fails loudly instead of hanging the box.
-__device__ __forceinline__ void spin_until(const int32_t* p, int32_t want) {
+__device__ __forceinline__ void spin_until(const int32_t* p, int32_t want, bool strict = true) {
     const unsigned long long t0 = global_ns();
-    while (ld_acquire_sys(p) < want) {
+    while ((strict ? ld_acquire_sys(p) : ld_relaxed_sys(p)) < want) {
         if (global_ns() - t0 > 60ull * 1000000000ull) __trap();
     }
 }
@@ -56,37 +71,46 @@ struct DpSync {
     const float* loss_parts;     // optional: n_loss values loss_stride floats apart, summed into loss_out by the last CTA
     int64_t loss_stride;
     int32_t n_loss;
+    int32_t fence_mode;          // 1 (default) lean protocol, see above; 0 fence.acq_rel.sys after the flags; 2 strict everywhere
     float* loss_out;
 };
 
 // Prologue of a consumer CTA: every CTA of every rank's push of the current exchange has landed, on all wait channels.
-// ONE warp polls (relaxed loads, all of a lane's flags in flight together), ONE lane then issues the system-scope fence
-// that orders the CTA's later reads after the observed flags, the CTA barrier hands that order to the other warps.
+// ALL threads of the CTA poll (relaxed loads, a thread's flags of all channels in flight together: at 8 ranks a channel
+// has 8 x 148 flags — one warp needed ten dependent rounds of system-scope loads per look, ~8 us even when everything
+// had already arrived; 256 threads need one), the CTA agrees through the barrier, ONE thread then issues the system-scope
+// fence that orders the CTA's later reads after the observed flags and a second barrier hands that order to the others.
 // (A first version fenced in every thread of every CTA: 87 K system fences made the consumer 16 us slower.)
-// Call from all threads of the CTA (contains a barrier).
+// Call from all threads of the CTA (contains barriers).
 __device__ __forceinline__ void dp_wait_inline(const DpSync& s) {
     if (s.n_wait > 0) {
-        if (threadIdx.x < 32) {
-            const unsigned long long t0 = global_ns();
-            for (int c = 0; c < s.n_wait; ++c) {
+        const unsigned long long t0 = global_ns();
+        int32_t want[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) want[c] = c < s.n_wait ? __ldg(s.wait[c].epoch_dev) + 1 : 0;
+        bool ok;
+        do {
+            int32_t slack = 0x7fffffff;           // min over the thread's flags of (flag - epoch wanted)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (c >= s.n_wait) break;
                 const DpChannel& ch = s.wait[c];
-                const int32_t want = __ldg(ch.epoch_dev) + 1;
                 const int32_t* arrival = reinterpret_cast<const int32_t*>(ch.base[s.rank] + ch.flag_off);
                 const int total = s.world * ch.n_ctas;
-                bool ok;
-                do {
-                    // every flag of the lane is loaded unconditionally, eight loads in flight: `ok = ok && load(..)` made
-                    // each load wait for the previous one — 50 dependent system-scope loads per lane at 8 ranks, 22 us
-                    // between the last push and the consumer noticing it
-                    int32_t lowest = 0x7fffffff;
-#pragma unroll 8
-                    for (int i = threadIdx.x; i < total; i += 32)
-                        lowest = min(lowest, ld_relaxed_sys(arrival + (i / ch.n_ctas) * DP_MAX_CTAS + (i % ch.n_ctas)));
-                    ok = lowest >= want;
-                    if (global_ns() - t0 > 60ull * 1000000000ull) __trap();      // a peer died: fail loudly (see spin_until)
-                } while (!__all_sync(0xffffffffu, ok));
+#pragma unroll 4
+                for (int i = threadIdx.x; i < total; i += blockDim.x)
+                    slack = min(slack, ld_relaxed_sys(arrival + (i / ch.n_ctas) * DP_MAX_CTAS + (i % ch.n_ctas)) - want[c]);
             }
-            if (threadIdx.x == 0) __threadfence_system();
+            ok = slack >= 0;
+            if (!ok) {
+                if (global_ns() - t0 > 60ull * 1000000000ull) __trap();      // a peer died: fail loudly (see spin_until)
+                __nanosleep(64);
+            }
+        } while (!__syncthreads_and(ok));
+        if (threadIdx.x == 0) {
+            if (s.fence_mode == 1) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            else if (s.fence_mode == 2) __threadfence_system();
+            else asm volatile("fence.acq_rel.sys;" ::: "memory");
         }
         __syncthreads();
     }
@@ -104,7 +128,9 @@ __device__ __forceinline__ void dp_done_inline(const DpSync& s) {
     if (t < s.n_done * s.world) {
         const DpChannel& c = s.done[t / s.world];
         const int peer = t % s.world;
-        st_release_sys(reinterpret_cast<int32_t*>(c.base[peer] + c.flag_off) + DP_FLAG_CONSUMED + s.rank, *c.epoch_dev + 1);
+        int32_t* flag = reinterpret_cast<int32_t*>(c.base[peer] + c.flag_off) + DP_FLAG_CONSUMED + s.rank;
+        if (s.fence_mode == 2) st_release_sys(flag, *c.epoch_dev + 1);
+        else st_relaxed_sys(flag, *c.epoch_dev + 1);
     }
     __syncthreads();
     if (t < s.n_done) *s.done[t].epoch_dev += 1;

@@ -116,6 +116,8 @@ struct TrainFwdParams {
     const float* gWimg;          // operand images of W, one per 32-wide chunk of K
     const int64_t* X;
     const int64_t* sample_item;
+    const uint64_t* batch_ptrs;  // optional (with batch_cursor): X / sample_item are batch *batch_cursor of the epoch arrays
+    const int64_t* batch_cursor; //   whose base addresses are batch_ptrs[0..1] (the staged copies are written concurrently)
     const float* noise;          // mode 1
     float* pre_part;             // [n_ksplits][N][D]
     float* x_save;               // optional [ceil(N/128)*128 * F], tile-major: Feat[i_r] + eps_r as multiplied, for the dW kernel
@@ -151,8 +153,15 @@ __global__ void __launch_bounds__(TC_NT, DCCF_TRAIN_PAIR ? 1 : 2) k_train_fwd_tc
     if (warp < TC_PRODUCERS / 32) {
         const uint32_t p = (uint32_t)grow / (uint32_t)prm.R;
         const int z = (int)((uint32_t)grow - p * (uint32_t)prm.R) / prm.A;
-        fi = checked_id(prm.X[2 * (int64_t)p + 1], prm.n_items, prm.err_flag);
-        it = (z == 0) ? fi : checked_id(prm.sample_item[(int64_t)p * prm.S + (z - 1)], prm.n_items, prm.err_flag);
+        const int64_t *X = prm.X, *si = prm.sample_item;
+        if (prm.batch_cursor != nullptr) {
+            // the ids straight from the device-resident epoch: the launch that stages them (k_link_ids) runs beside this one
+            const int64_t b = *prm.batch_cursor, n_pairs = (int64_t)((uint32_t)prm.n_rows / (uint32_t)prm.R);
+            X = reinterpret_cast<const int64_t*>(prm.batch_ptrs[0]) + b * n_pairs * 2;
+            si = reinterpret_cast<const int64_t*>(prm.batch_ptrs[1]) + b * n_pairs * prm.S;
+        }
+        fi = checked_id(X[2 * (int64_t)p + 1], prm.n_items, prm.err_flag);
+        it = (z == 0) ? fi : checked_id(si[(int64_t)p * prm.S + (z - 1)], prm.n_items, prm.err_flag);
     }
 
     if (tid == 0) {
@@ -305,6 +314,10 @@ __global__ void __launch_bounds__(TC_NT, DCCF_TRAIN_PAIR ? 1 : 2) k_train_fwd_tc
     __syncthreads();
     tl_end(2);
     if (warp == TC_PRODUCERS / 32) tc::tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    // Launched as a programmatic dependent of the kernel before it on the stream (dccf_train_fwd_bwd_tc, phases bit 8):
+    // this grid started while that kernel was still running and read nothing it writes; it must not COMPLETE before that
+    // kernel has, because the next kernel on the stream depends on both.  (A no-op in a plain launch.)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // One CTA per pair: 8 half-warps take the pair's R rows (lane = 4 columns), then warp 0 runs the backdoor sum.
@@ -416,7 +429,10 @@ __host__ __device__ inline size_t train_mid_smem_floats(int R, int Z, int npc) {
 
 // (no launch bound: the default 1024-thread bound caps the kernel at 64 registers, so that a 256-thread CTA of the
 // side-stream Adam sweep still fits beside its 768 threads)
-__global__ void k_train_mid(const TrainMidParams prm) {
+// 64 registers x 768 threads = 3/4 of the SM's register file: the side sweep's CTA (7 warps x 64 registers) stays resident
+// beside this kernel.  (At 70 registers a sweep CTA wider than 128 threads kept every CTA of this kernel off its SM
+// until the sweep had finished.)
+__global__ void __maxnreg__(64) k_train_mid(const TrainMidParams prm) {
     extern __shared__ __align__(16) float sm[];
     const int R = prm.R, Z = prm.Z, A = prm.A;
     const int npc = (prm.loss_mode == 0) ? 2 : 1;   // pairs per CTA
@@ -460,10 +476,20 @@ __global__ void k_train_mid(const TrainMidParams prm) {
         const int64_t r = p * R + l;
         const float4 e = q == 0 ? eu0 : eu1;
         const float* src = prm.pre_part + (size_t)r * D + sub * 4;
-        float4 acc = ldg4(src);
-        for (int k = 1; k < prm.n_ksplits; ++k) {
-            const float4 t = ldg4(src + (size_t)k * part_stride);
-            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        // the K-split partials (at most 8, fwd_ksplits_for) in two groups of four loads in flight, added in ascending
+        // order (a rolled loop waited for them one L2 round trip after the other; all eight at once spill at 64 registers)
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k0 = 0; k0 < 8; k0 += 4) {
+            float4 part[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k0 + k < prm.n_ksplits) part[k] = ldg4(src + (size_t)(k0 + k) * part_stride);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k0 + k == 0) acc = part[0];
+                else if (k0 + k < prm.n_ksplits) { acc.x += part[k].x; acc.y += part[k].y; acc.z += part[k].z; acc.w += part[k].w; }
+            }
         }
         float4 h = make_float4(fmaxf(acc.x + bia.x, 0.f), fmaxf(acc.y + bia.y, 0.f), fmaxf(acc.z + bia.z, 0.f),
                                fmaxf(acc.w + bia.w, 0.f));
@@ -929,7 +955,7 @@ extern "C" int32_t dccf_train_bwd_splits(int64_t n_rows, int32_t feat_dim) {
 static int launch_fwd_tc(const dccf_dims* dims, const float* E_item, const float* Feat, const float* W, const int64_t* X,
                          const int64_t* sample_item, int64_t n_pairs, const dccf_rng* rng, float* ws_wimg,
                          bool w_image_valid, float* ws_pre_part, float* x_save, int32_t* err_flag, int32_t* n_ks_out,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const dccf_batch_ref* batch = nullptr, bool programmatic = false) {
     const int F = dims->feat_dim, K = D + F, Z = dims->n_samples + 1, R = Z * dims->n_attr;
     const int64_t n_rows = n_pairs * R;
     static PerDeviceOnce attr_once;
@@ -946,6 +972,7 @@ static int launch_fwd_tc(const dccf_dims* dims, const float* E_item, const float
     }
     TrainFwdParams prm;
     prm.E_item = E_item; prm.Feat = Feat; prm.gWimg = ws_wimg; prm.X = X; prm.sample_item = sample_item;
+    prm.batch_ptrs = batch ? batch->epoch_ptrs_dev : nullptr; prm.batch_cursor = batch ? batch->cursor_dev : nullptr;
     prm.noise = rng->noise; prm.pre_part = ws_pre_part; prm.x_save = x_save; prm.err_flag = err_flag; prm.n_rows = n_rows;
     prm.n_items = dims->n_items; prm.F = F; prm.S = dims->n_samples; prm.A = dims->n_attr; prm.R = R;
     prm.n_chunks = K / TC_KC; prm.noise_std = rng->noise_std;
@@ -953,10 +980,21 @@ static int launch_fwd_tc(const dccf_dims* dims, const float* E_item, const float
     const int32_t n_ks = fwd_ksplits_for(n_rows, prm.n_chunks);
     *n_ks_out = n_ks;
     const dim3 grid((unsigned)((n_rows + TC_BM - 1) / TC_BM), (unsigned)n_ks);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(TC_NT); cfg.dynamicSmemBytes = TT_SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = (programmatic && w_image_valid) ? 1 : 0;     // (never over k_prep_w_image: its output is read)
+    cudaError_t le;
     switch (rng->noise_mode) {
-        case 0: k_train_fwd_tc<0><<<grid, TC_NT, TT_SMEM_BYTES, stream>>>(prm); break;
-        case 1: k_train_fwd_tc<1><<<grid, TC_NT, TT_SMEM_BYTES, stream>>>(prm); break;
-        default: k_train_fwd_tc<2><<<grid, TC_NT, TT_SMEM_BYTES, stream>>>(prm); break;
+        case 0: le = cudaLaunchKernelEx(&cfg, k_train_fwd_tc<0>, prm); break;
+        case 1: le = cudaLaunchKernelEx(&cfg, k_train_fwd_tc<1>, prm); break;
+        default: le = cudaLaunchKernelEx(&cfg, k_train_fwd_tc<2>, prm); break;
+    }
+    if (le != cudaSuccess) {
+        set_error("k_train_fwd_tc: launch failed: %s", cudaGetErrorString(le));
+        return DCCF_ERR_CUDA;
     }
     DCCF_CHECK_LAUNCH("k_train_fwd_tc");
     return DCCF_OK;
@@ -1072,10 +1110,12 @@ extern "C" int dccf_train_fwd_bwd_tc(const dccf_dims* dims, const float* E_user,
                                      int32_t w_image_valid, float* ws_pre_part, float* ws_dpre, float* ws_x, float* ws_loss_terms,
                                      float* gW_part, float* gb_part, float* gu_rec, float* gi_rec, int32_t* rec_keys_u,
                                      int32_t* rec_keys_i, float* save_h, float* save_w, const float* expo_e,
-                                     const float* expo_den, int32_t phases, int32_t* err_flag, void* stream_) {
+                                     const float* expo_den, const dccf_batch_ref* batch, int32_t phases, int32_t* err_flag,
+                                     void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = check_fwd_args("dccf_train_fwd_bwd_tc", dims, expo, rng, sample_item, n_pairs);
-    DCCF_CHECK_ARG(phases >= 1 && phases <= 7, "dccf_train_fwd_bwd_tc: phases is a mask of 1 (partial products), 2 (middle kernel), 4 (dW / db)");
+    DCCF_CHECK_ARG(batch == nullptr || (batch->epoch_ptrs_dev != nullptr && batch->cursor_dev != nullptr), "dccf_train_fwd_bwd_tc: batch needs both pointers");
+    DCCF_CHECK_ARG(phases >= 1 && phases <= 15 && (phases & 7) != 0, "dccf_train_fwd_bwd_tc: phases is a mask of 1 (partial products), 2 (middle kernel), 4 (dW / db), + 8 (programmatic launch of phase 1)");
     DCCF_CHECK_ARG((expo_e == nullptr) == (expo_den == nullptr), "dccf_train_fwd_bwd_tc: expo_e and expo_den go together");
     if (rc != DCCF_OK) return rc;
     DCCF_CHECK_ARG(loss_mode == 0 || loss_mode == 1, "dccf_train_fwd_bwd_tc: loss_mode must be 0 (BPR) or 1 (MSE)");
@@ -1104,7 +1144,7 @@ extern "C" int dccf_train_fwd_bwd_tc(const dccf_dims* dims, const float* E_user,
     int32_t n_ks = fwd_ksplits_for(n_pairs * R, K / TC_KC);
     if (phases & 1) {
         rc = launch_fwd_tc(dims, E_item, Feat, W, X, sample_item, n_pairs, rng, ws_wimg, w_image_valid != 0, ws_pre_part, ws_x,
-                           err_flag, &n_ks, stream);
+                           err_flag, &n_ks, stream, batch, (phases & 8) != 0);
         if (rc != DCCF_OK) return rc;
     }
     if (!(phases & 6)) return DCCF_OK;

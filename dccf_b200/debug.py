@@ -12,7 +12,7 @@ from . import _lib
 
 SLOT_NAMES = ['k_link_ids', 'k_adam_untouched', 'k_train_fwd_tc', 'k_train_mid', 'k_train_bwd_tc', 'k_adam_touched',
               'k_stage_batch', 'fwd latest CTA start', 'k_dp_push ids', 'k_dp_wait', 'k_dp_push records', 'k_dp_push dense',
-              'peers arrived (k_adam_touched)', 'k_csr_build']
+              'peers arrived (k_adam_touched)', 'k_csr_build', 'dense push: pieces issued', 'dense push: copies complete']
 N_SLOTS = 16
 
 

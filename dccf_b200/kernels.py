@@ -186,20 +186,30 @@ def train_fused_supported(n_samples, n_attr, loss_mode):
 
 def train_fwd_bwd_tc(dims, E_user, E_item, Feat, W, b, expo, X, sample_item, Y, rng, loss_mode, out_pred, out_loss,
                      ws_wimg, w_image_valid, ws_pre_part, ws_dpre, ws_x, ws_loss_terms, gW_part, gb_part, gu_rec, gi_rec,
-                     rec_keys_u, rec_keys_i, save_h=None, save_w=None, expo_e=None, expo_den=None, err_flag=None, phases=7):
+                     rec_keys_u, rec_keys_i, save_h=None, save_w=None, expo_e=None, expo_den=None, err_flag=None, phases=7,
+                     batch=None):
     """Forward + BPR/MSE loss + backward of a training step: partial products, fused per-loss-term middle kernel,
-    dW / db tiles (3 launches, 4 when the W operand images must be rebuilt)."""
+    dW / db tiles (3 launches, 4 when the W operand images must be rebuilt).  batch = (epoch_ptrs_dev, cursor_dev): the
+    partial-product kernel takes its ids from the device-resident epoch itself (X / sample_item are then the staged
+    copies another launch is writing; the later kernels read those).  phases + 8: the partial-product kernel starts as
+    a programmatic dependent of the kernel launched before it on the stream (see include/dccf_b200.h)."""
     lib = _lib.load()
     n_pairs = X.shape[0]
+    ref = None
+    if batch is not None:
+        ref = _lib.BatchRef()
+        ref.epoch_ptrs_dev, ref.cursor_dev = ptr(batch[0]).value, ptr(batch[1]).value
     check(lib.dccf_train_fwd_bwd_tc(ctypes.byref(dims), ptr(E_user), ptr(E_item), ptr(Feat), ptr(W), ptr(b),
                                     ctypes.byref(expo), ptr(X), ptr(sample_item), ptr(Y), n_pairs, ctypes.byref(rng),
                                     int(loss_mode), ptr(out_pred), ptr(out_loss), ptr(ws_wimg), int(bool(w_image_valid)),
                                     ptr(ws_pre_part), ptr(ws_dpre), ptr(ws_x), ptr(ws_loss_terms), ptr(gW_part), ptr(gb_part),
                                     ptr(gu_rec), ptr(gi_rec), ptr(rec_keys_u), ptr(rec_keys_i), ptr(save_h), ptr(save_w),
-                                    ptr(expo_e), ptr(expo_den), int(phases), ptr(err_flag), stream_ptr()),
+                                    ptr(expo_e), ptr(expo_den), ctypes.byref(ref) if ref is not None else None, int(phases),
+                                    ptr(err_flag), stream_ptr()),
           'dccf_train_fwd_bwd_tc')
     if n_pairs > 0:
         LAUNCHES[0] += ((1 if w_image_valid else 2) if phases & 1 else 0) + (1 if phases & 2 else 0) + (1 if phases & 4 else 0)
+
 
 
 def adam_sweep(table, m, v, rec_keys, rec_grads, n_rec, head, nxt, hp):
@@ -353,7 +363,7 @@ def adam_untouched(tables, hp, threads=0):
 
 
 def adam_touched(tables, dense, hp, already_linked=False, w_image=None, w_image_tensor=0, w_image_K=0, cta_counter=None,
-                 advance_step_dev=None, advance_offset_dev=None, sync=None):
+                 advance_step_dev=None, advance_offset_dev=None, sync=None, advance_cursor_dev=None):
     """Adam over the touched rows and the dense tensors (one launch, two when the records still need linking).
     sync (make_dp_sync): data-parallel step — wait for the peers' gradient segments in the kernel's prologue, total loss
     and hand-back of the exchange buffers by its last CTA."""
@@ -362,7 +372,7 @@ def adam_touched(tables, dense, hp, already_linked=False, w_image=None, w_image_
     da = (AdamTensor * max(1, len(dense)))(*dense)
     check(lib.dccf_adam_touched(ta, len(tables), da, len(dense), ctypes.byref(hp), int(bool(already_linked)),
                                 ptr(w_image), int(w_image_tensor), int(w_image_K), ptr(cta_counter),
-                                ptr(advance_step_dev), ptr(advance_offset_dev),
+                                ptr(advance_step_dev), ptr(advance_offset_dev), ptr(advance_cursor_dev),
                                 ctypes.byref(sync) if sync is not None else None, stream_ptr()), 'dccf_adam_touched')
     LAUNCHES[0] += 1 if already_linked or not any(t.n_seg * t.seg_len > 0 for t in tables) else 2
 

@@ -430,7 +430,7 @@ class DCCF(DMF):
             loss_mode in (0, 1) and kernels.train_fused_supported(self.sample_num, self.attribute_num, loss_mode)
 
     def _launch_fwd_bwd(self, call, loss_mode, Y, rec=None, w_image_valid=False, expo_e=None, expo_den=None,
-                        between=None):
+                        between=None, batch=None, programmatic=False):
         """Forward + loss + backward of one step through dccf_train_fwd_bwd_tc (three launches; the activations
         never leave shared memory).  Returns (prediction, gradient buffers)."""
         P, N = call['P'], call['N']
@@ -452,11 +452,12 @@ class DCCF(DMF):
             self._buf('ws_x', ((N + 127) // 128 * 128, F), torch.float32) if self.reuse_noise_rows else None,
             self._buf('ws_loss_terms', (P,), torch.float32), rec['gW_part'], rec['gb_part'], rec['gu_rec'],
             rec['gi_rec'], rec['keys_u'], rec['keys_i'], None, None, expo_e, expo_den, self._err_flag)
+        pdl = 8 if (programmatic and w_image_valid) else 0     # phase 1 beside the kernel launched just before it
         if between is None:
-            kernels.train_fwd_bwd_tc(*args)
+            kernels.train_fwd_bwd_tc(*args, phases=7 | pdl, batch=batch)
         else:                       # kernel by kernel, with the caller's stream plumbing after each
             for phase in (1, 2, 4):
-                kernels.train_fwd_bwd_tc(*args, phases=phase)
+                kernels.train_fwd_bwd_tc(*args, phases=phase | (pdl if phase == 1 else 0), batch=batch)
                 between(phase)
         call['pred'] = pred
         return pred, rec
@@ -772,14 +773,15 @@ class DCCF(DMF):
     overlap_split_adam = os.environ.get('DCCF_SPLIT_OVERLAP', '1') != '0'
 
     def _sweep_threads(self, dp):
-        """Launch shape of the untouched-row Adam sweep: one small CTA per SM hidden beside the tensor-core kernels
-        (128 threads; 256 under data parallelism, where it starts later) while the tables are small enough for that to
-        finish in time; -1 = the wide, full-occupancy sweep once the sweep itself bounds the step (scaled configuration:
-        24 B x 64 x 10^6..10^7 rows per step — at the ~2 TB/s of the narrow launch that is milliseconds)."""
+        """Launch shape of the untouched-row Adam sweep: one small CTA per SM hidden beside the tensor-core kernels and
+        the middle kernel (0 = the library's default, 224 threads: the widest CTA whose registers fit beside the middle
+        kernel's) while the tables are small enough for that to finish in time; -1 = the wide, full-occupancy sweep once
+        the sweep itself bounds the step (scaled configuration: 24 B x 64 x 10^6..10^7 rows per step — at the ~3 TB/s
+        of the narrow launch that is milliseconds)."""
         rows = self.uid_embeddings.weight.shape[0] + self.item_num
         if rows * self.ui_vector_size * 24 > 400e6:
             return -1
-        return 256 if dp else 0
+        return 0
 
     def _wimg_key(self):
         W = self.mlp[0].weight
@@ -809,6 +811,9 @@ class DCCF(DMF):
     # data-parallel training over a device-resident epoch: every rank's ids of the WHOLE epoch (chunk) are all-gathered
     # once, outside the steps, so no step waits for an id exchange (DCCF_DP_EPOCH_IDS=0: one id exchange per step)
     dp_epoch_ids = os.environ.get('DCCF_DP_EPOCH_IDS', '1') != '0'
+    # k_link_ids (record lists, staging of a resident batch, exposure softmax) on the side stream, beside the forward
+    # instead of ahead of it (DCCF_LINK_BESIDE=0: ahead, as in round 1)
+    link_beside_forward = os.environ.get('DCCF_LINK_BESIDE', '1') != '0'
 
     def _fused_split_step(self, call, loss_mode, Y, opt, hp, w_image_valid, overlap, counters=None, stage=None,
                           epoch_ids=None):
@@ -857,8 +862,20 @@ class DCCF(DMF):
             # the record lists of the GLOBAL step are linked on the side stream
             extra = kernels.make_link_extra(stage=stage, prefetch_feat=self.feature_embedding if self.l2_prefetch else None,
                                             prefetch_dense=(wimg,) if self.l2_prefetch else None)
-        kernels.adam_link_ids(self._dims(), call['X'], call['sample_item'], opt.head_u, next_u, opt.head_i, next_i,
-                              self._expo(), expo_e, expo_den, n_seg=0 if dp else 1, extra=extra)
+
+        def link_local():
+            kernels.adam_link_ids(self._dims(), call['X'], call['sample_item'], opt.head_u, next_u, opt.head_i, next_i,
+                                  self._expo(), expo_e, expo_den, n_seg=0 if dp else 1, extra=extra)
+
+        # The forward needs nothing this launch produces except — with a device-resident epoch — the staged ids, and
+        # those it can read from the epoch arrays itself (dccf_batch_ref): it is launched as a PROGRAMMATIC DEPENDENT of
+        # this kernel and starts beside it (the 5 us of k_link_ids were the head of every step's critical path).  The
+        # forward does not complete before this kernel has, so the middle kernel still finds the exposure softmax and
+        # the staged ids.  (A first version put this launch on the side stream: same overlap, but a graph with two root
+        # nodes and a cross-stream edge into the middle kernel started 3 us later and left 2 us wider gaps.)
+        beside = overlap and self.link_beside_forward and w_image_valid
+        batch = (stage[0], stage[1]) if (stage is not None and beside) else None
+        link_local()
 
         # data parallel, folded synchronisation (DCCF_DP_FOLD=0: the round-1 sequence push / wait / consume / done as
         # separate launches): consumers wait for the peers' segments in their own prologue and their last CTA hands the
@@ -939,7 +956,7 @@ class DCCF(DMF):
             if dp and not fold and epoch_ids is None:
                 ix.done()
         pred, rec = self._launch_fwd_bwd(call, loss_mode, Y, rec=rec, w_image_valid=w_image_valid, expo_e=expo_e,
-                                         expo_den=expo_den, between=between)
+                                         expo_den=expo_den, between=between, batch=batch, programmatic=beside)
         sync = None
         if dp:
             if not overlap:
@@ -960,7 +977,8 @@ class DCCF(DMF):
             if csr:
                 main.wait_event(csr_done)
         step_dev, offset_dev = counters if counters is not None else (None, None)
-        kernels.adam_touched(tables, dense, hp, True, wimg, 0, D + F, opt.cta_counter, step_dev, offset_dev, sync=sync)
+        kernels.adam_touched(tables, dense, hp, True, wimg, 0, D + F, opt.cta_counter, step_dev, offset_dev, sync=sync,
+                             advance_cursor_dev=stage[1] if stage is not None else None)
         if dp:
             if fold:
                 return pred, total[0]

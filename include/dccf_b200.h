@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCCF_ABI_VERSION 32
+#define DCCF_ABI_VERSION 33
 #define DCCF_DIM 64 /* u_vector_size == i_vector_size compiled into the kernels */
 
 typedef enum dccf_status {
@@ -198,9 +198,19 @@ int dccf_train_bwd_tc(const dccf_dims* dims, const float* E_user, const float* E
  *   expo_e [P, Z] / expo_den [P] optional: the exposure softmax precomputed by dccf_adam_link_ids
  *   phases: mask of 1 = the partial products, 2 = the middle kernel, 4 = the dW / db tiles (7 = everything; same
  *        arguments every time) — lets the caller wait for / signal other streams between the kernels (the stream
- *        that produced expo_e before the middle kernel; the stream that ships the gradient records after it)
+ *        that produced expo_e before the middle kernel; the stream that ships the gradient records after it).
+ *        + 8: the partial-product kernel is launched as a PROGRAMMATIC DEPENDENT of the kernel before it on the stream
+ *        (cudaLaunchAttributeProgrammaticStreamSerialization): it starts as soon as that kernel — dccf_adam_link_ids,
+ *        which signals griddepcontrol.launch_dependents first thing — has started, reads nothing it writes (use
+ *        `batch` when the ids are being staged by it) and does not complete before it has; needs w_image_valid
+ *   batch (optional): the partial-product kernel (phase 1) takes its ids from batch *cursor_dev of a device-resident
+ *        epoch (epoch_ptrs_dev[0..1] = base addresses of X_epoch [n, P, 2] / sample_epoch [n, P, S], the arrays
+ *        dccf_link_extra's staging reads) instead of X / sample_item — it then does not have to wait for the launch
+ *        that stages them (dccf_adam_link_ids), which runs beside it (phases + 8); phases 2 and 4 read X /
+ *        sample_item, i.e. the staged copies
  * Needs dccf_train_fused_smem_bytes(S, A, loss_mode) <= 200 KB of shared memory per CTA (else use the two calls
  * above). */
+typedef struct dccf_batch_ref { const uint64_t* epoch_ptrs_dev; const int64_t* cursor_dev; } dccf_batch_ref;
 int64_t dccf_train_fused_smem_bytes(int32_t n_samples, int32_t n_attr, int32_t loss_mode);
 int dccf_train_fwd_bwd_tc(const dccf_dims* dims, const float* E_user, const float* E_item, const float* Feat,
                           const float* W, const float* b, const dccf_expo* expo, const int64_t* X,
@@ -209,7 +219,8 @@ int dccf_train_fwd_bwd_tc(const dccf_dims* dims, const float* E_user, const floa
                           int32_t w_image_valid, float* ws_pre_part, float* ws_dpre, float* ws_x, float* ws_loss_terms,
                           float* gW_part, float* gb_part, float* gu_rec, float* gi_rec, int32_t* rec_keys_u,
                           int32_t* rec_keys_i, float* save_h, float* save_w, const float* expo_e,
-                          const float* expo_den, int32_t phases, int32_t* err_flag, void* stream);
+                          const float* expo_den, const dccf_batch_ref* batch, int32_t phases, int32_t* err_flag,
+                          void* stream);
 
 /* ---- (c) part 2: l2 + clip + Adam, dense over every row --------------------------------- */
 /* Replaces model.l2()*l2 (BaseRunner.py:181, BaseModel.py:179-187), clip_grad_value_
@@ -291,7 +302,7 @@ int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, const dccf_a
  *                           this rank's own batch (X_local / sample_item_local; NULL: segment 0)
  *                           (src/models/DCCF.py:98, a function of the ids only): expo_e [P, Z] = exp(expo - max),
  *                           expo_den [P] = A * sum_z, consumed by dccf_train_fwd_bwd_tc
- *   dccf_adam_untouched     rows whose head is -1; at most 148 CTAs of threads_per_cta threads (0 = 128) so that a
+ *   dccf_adam_untouched     rows whose head is -1; at most 148 CTAs of threads_per_cta threads (0 = 224) so that a
  *                           tensor-core CTA fits beside each
  *   dccf_adam_touched       the head record of each list updates its row (records summed in ascending index) and
  *                           resets head to -1; dense tensors as in dccf_adam_step.  already_linked = 0: links the
@@ -299,8 +310,9 @@ int dccf_adam_step(const dccf_adam_table* tables, int32_t n_tables, const dccf_a
  *                           of the UPDATED W [D, w_image_K] = dense[w_image_tensor] for the next step's
  *                           dccf_train_fwd_bwd_tc(w_image_valid = 1); dccf_train_prep_w_image builds them from
  *                           scratch.  cta_counter (optional, int32 zero on entry / exit): the last CTA to finish does
- *                           advance_step_dev[0] += 1 and advance_offset_dev[0] += 1 (replaces dccf_state_advance in a
- *                           captured step; every other reader of the counters must have completed).
+ *                           advance_step_dev[0] += 1, advance_offset_dev[0] += 1 and advance_cursor_dev[0] += 1 — the
+ *                           batch cursor of a device-resident epoch — each when non-NULL (replaces dccf_state_advance
+ *                           in a captured step; every other reader of the counters must have completed).
  *                           sync (optional, needs cta_counter): data-parallel step — every CTA first waits for the peers'
  *                           gradient segments, the last CTA sums the ranks' loss terms and hands the buffers back.
  * Every row is updated exactly once, with the arithmetic of dccf_adam_step. */
@@ -327,14 +339,15 @@ typedef struct dccf_dp_sync {
  *   staging (epoch_ptrs_dev != NULL): the step reads its batch from a device-resident epoch — what dccf_stage_batch does
  *     in a launch of its own: X / sample_item arguments are ignored, the batch is [*cursor] of the arrays whose
  *     addresses sit in epoch_ptrs_dev {X_epoch [n,P,2], sample_epoch [n,P,S]}; every id is copied into X_out /
- *     sample_item_out (the buffers the other kernels of the step read) by the thread that links it, and the last CTA
- *     to finish advances *cursor (stage_counter: int32, zero on entry / exit).  Needs n_seg == 1.
+ *     sample_item_out (the buffers the later kernels of the step read) by the thread that links it.  The cursor is NOT
+ *     moved here: the partial-product kernel may be reading the same batch beside this launch (dccf_batch_ref);
+ *     dccf_adam_touched (advance_cursor_dev) moves it when the step is over.  Needs n_seg <= 1.
  *   L2 prefetch (any pointer may be NULL): the rows this step will touch — the pairs' user rows, the slot items' rows
  *     and their Adam moments, the true items' feature rows — and up to four dense ranges (W, its moments, its operand
  *     images) are requested into L2 (prefetch.global.L2) while the step's first kernels run, so that the forward, the
  *     middle kernel and the touched-row sweep find them there instead of in DRAM.  No effect on results.
  *   sync: data-parallel link of the GLOBAL step — wait for the peers' ids in the prologue, hand the id buffer back in
- *     the last CTA (stage_counter doubles as the CTA counter). */
+ *     the last CTA (stage_counter: int32 CTA counter, zero on entry / exit). */
 typedef struct dccf_link_extra {
     const uint64_t* epoch_ptrs_dev; int64_t* cursor_dev; int64_t* X_out; int64_t* sample_item_out;
     int32_t* stage_counter;
@@ -357,7 +370,7 @@ int dccf_adam_csr_build(const dccf_adam_table* tables, int32_t n_tables, void* s
 int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables, const dccf_adam_tensor* dense,
                       int32_t n_dense, const dccf_adam* hp, int32_t already_linked, float* w_image,
                       int32_t w_image_tensor, int32_t w_image_K, int32_t* cta_counter, int32_t* advance_step_dev,
-                      uint64_t* advance_offset_dev, const dccf_dp_sync* sync, void* stream);
+                      uint64_t* advance_offset_dev, int64_t* advance_cursor_dev, const dccf_dp_sync* sync, void* stream);
 int dccf_train_prep_w_image(const float* W, int32_t feat_dim, float* w_image, void* stream);
 /* First node of a captured training step that reads its inputs from a device-resident epoch:
  * epoch_ptrs_dev = device array {address of X_epoch [n_batches,P,2], address of sample_epoch [n_batches,P,S]},
