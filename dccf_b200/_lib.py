@@ -63,7 +63,7 @@ class DpChannel(ctypes.Structure):
 class DpSync(ctypes.Structure):
     _fields_ = [('world', ctypes.c_int32), ('rank', ctypes.c_int32), ('n_wait', ctypes.c_int32), ('n_done', ctypes.c_int32),
                 ('wait', DpChannel * 3), ('done', DpChannel * 3), ('loss_parts', ctypes.c_void_p),
-                ('loss_stride', ctypes.c_int64), ('n_loss', ctypes.c_int32), ('_pad', ctypes.c_int32),
+                ('loss_stride', ctypes.c_int64), ('n_loss', ctypes.c_int32), ('flags', ctypes.c_int32),
                 ('loss_out', ctypes.c_void_p)]
 
 

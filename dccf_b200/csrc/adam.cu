@@ -344,10 +344,13 @@ __global__ void k_csr_build(const AdamAllArgs a, int phase) {
     tl_end(13);
     for (int i = 0; i < a.n_tables; ++i) {
         const AdamTableArgs& t = a.t[i];
-        const int b = (int)blockIdx.x - t.link_lo;
+        // the tables' record ranges are laid out in blocks of 256 records; a launch with narrower CTAs (256 / blockDim.x of
+        // them per block) leaves room for other kernels' CTAs beside it (dccf_adam_csr_build)
+        const int per = 256 / (int)blockDim.x;
+        const int b = (int)blockIdx.x / per - t.link_lo;
         if (b < 0 || b >= t.link_n) continue;
         if (t.csr == nullptr) return;
-        const int64_t r = (int64_t)b * blockDim.x + threadIdx.x;
+        const int64_t r = (int64_t)b * 256 + ((int)blockIdx.x % per) * blockDim.x + threadIdx.x;
         if (r >= t.n_rec) return;
         const int32_t pos = t.next[r];
         if (pos < 0) return;                                   // (a record no link touched)
@@ -667,6 +670,9 @@ __device__ __forceinline__ void touched_cta_done(const AdamAllArgs& a, const WIm
     __shared__ int s_last;
     __syncthreads();
     tl_end(5);
+    // (launched as a programmatic dependent of the dW / db push: this grid must not complete before that one has — a
+    // no-op in a plain launch)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (wi.cta_counter == nullptr) return;                       // every thread of this CTA has read the counters it needs and stored its rows
     if (threadIdx.x == 0) {
         __threadfence();
@@ -689,10 +695,22 @@ __device__ __forceinline__ void touched_cta_done(const AdamAllArgs& a, const WIm
 __global__ void __launch_bounds__(256) k_adam_touched(const AdamAllArgs a, const WImageArgs wi, const DpSync sync) {
     __shared__ int32_t list_s[16][2][ADAM_LIST_CAP];
     tl_begin(5);
-    dp_wait_inline(sync);        // (data parallel) every rank's gradient records and dW / db / loss have arrived
-    if (sync.n_wait > 0) { tl_begin(12); tl_end(12); }
-    const AdamScalars s = resolve_adam(a.hp);
     const int bid = (int)blockIdx.x;
+    {
+        // (data parallel) every rank's gradient records and dW / db / loss have arrived.  DCCF_DP_SYNC_OVERLAP_PUSH: the
+        // CTAs that sweep table rows need the records only (wait[0]) and start while this rank's dW / db push — the kernel
+        // before this one on the stream, of which this launch is then a programmatic dependent — is still running; the
+        // CTAs of the dense tensors wait for wait[1..].
+        uint32_t mask = 7u;
+        if ((sync.flags & DCCF_DP_SYNC_OVERLAP_PUSH) && sync.n_wait >= 2) {
+            bool table_cta = false;
+            for (int i = 0; i < a.n_tables; ++i) table_cta = table_cta || (bid >= a.t[i].block_lo && bid < a.t[i].block_lo + a.t[i].block_n);
+            mask = table_cta ? 1u : 6u;
+        }
+        dp_wait_inline(sync, mask);
+        if (sync.n_wait > 0 && (mask & 2u)) { tl_begin(12); tl_end(12); }
+    }
+    const AdamScalars s = resolve_adam(a.hp);
     for (int i = 0; i < a.n_tables; ++i) {
         const AdamTableArgs& t = a.t[i];
         const int b = bid - t.block_lo;
@@ -864,7 +882,9 @@ static int marshal_sync(const char* who, const dccf_dp_sync* in, DpSync* out) {
     out->loss_parts = nullptr; out->loss_stride = 0; out->n_loss = 0; out->loss_out = nullptr;
     static const int fence_mode = [] { const char* v = getenv("DCCF_DP_FENCE"); return v != nullptr ? atoi(v) : 1; }();   // A/B knob (dp_sync.cuh)
     out->fence_mode = fence_mode;
+    out->flags = 0;
     if (in == nullptr) return DCCF_OK;
+    out->flags = in->flags;
     DCCF_CHECK_ARG(in->world >= 1 && in->world <= DP_MAX_WORLD && in->rank >= 0 && in->rank < in->world,
                    "%s: sync: world %d / rank %d outside [1,%d]", who, in->world, in->rank, DP_MAX_WORLD);
     DCCF_CHECK_ARG(in->n_wait >= 0 && in->n_wait <= 3 && in->n_done >= 0 && in->n_done <= 3, "%s: sync: at most 3 channels", who);
@@ -1211,9 +1231,13 @@ extern "C" int dccf_adam_csr_build(const dccf_adam_table* tables, int32_t n_tabl
     for (int i = 0; i < n_tables; ++i)
         DCCF_CHECK_ARG(tables[i].csr != nullptr || (int64_t)tables[i].n_seg * tables[i].seg_len == 0, "dccf_adam_csr_build: table %d has records but no CSR buffers", i);
     if (link_blocks == 0) return DCCF_OK;
-    k_csr_build<<<(unsigned)link_blocks, 256, 0, stream>>>(a, 0);
+    // CTA width: 256, or (DCCF_CSR_THREADS = 64 / 128) narrower CTAs that fit beside the middle kernel and the side sweep
+    static const int csr_threads = [] { const char* v = getenv("DCCF_CSR_THREADS"); const int t = v != nullptr ? atoi(v) : 256;
+                                        return (t == 64 || t == 128) ? t : 256; }();
+    const unsigned ctas = (unsigned)link_blocks * (256 / csr_threads);
+    k_csr_build<<<ctas, csr_threads, 0, stream>>>(a, 0);
     DCCF_CHECK_LAUNCH("k_csr_build");
-    k_csr_build<<<(unsigned)link_blocks, 256, 0, stream>>>(a, 1);
+    k_csr_build<<<ctas, csr_threads, 0, stream>>>(a, 1);
     DCCF_CHECK_LAUNCH("k_csr_build");
     return DCCF_OK;
 }
@@ -1253,7 +1277,18 @@ extern "C" int dccf_adam_touched(const dccf_adam_table* tables, int32_t n_tables
         carve_once.mark();
     }
     if (blocks > 0) {
-        k_adam_touched<<<(unsigned)blocks, 256, 0, stream>>>(a, wi, ds);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = ((ds.flags & DCCF_DP_SYNC_OVERLAP_PUSH) && ds.n_wait >= 2 && already_linked) ? 1 : 0;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, k_adam_touched, a, wi, ds);
+        if (le != cudaSuccess) {
+            set_error("k_adam_touched: launch failed: %s", cudaGetErrorString(le));
+            return DCCF_ERR_CUDA;
+        }
         DCCF_CHECK_LAUNCH("k_adam_touched");
     }
     return DCCF_OK;

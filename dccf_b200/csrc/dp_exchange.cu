@@ -66,7 +66,14 @@ __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send,
     const int tl_slot = folds.n > 0 ? 11 : (seg < 16384 ? 8 : 10);
     tl_begin(tl_slot);
     (void)cta_counter;
+    // (the peers' consumed flags are requested together with the epoch: one round trip instead of two on the way to the
+    // first copy)
+    const int32_t* consumed = reinterpret_cast<const int32_t*>(peers.base[rank] + flag_off) + DP_FLAG_CONSUMED;
+    const int32_t seen = (!strict && (int)threadIdx.x < world) ? ld_relaxed_sys(consumed + threadIdx.x) : (int32_t)0x80000000;
     const int32_t epoch = __ldg(epoch_dev) + 1;
+    // a consumer launched as a programmatic dependent (dccf_adam_touched, DCCF_DP_SYNC_OVERLAP_PUSH) may start once every
+    // CTA of this push is resident and has read the channel's epoch (the consumer's last CTA advances it)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int64_t n4 = seg >> 2;
     const int64_t per = (n4 + gridDim.x - 1) / gridDim.x;
     const int64_t lo = (int64_t)blockIdx.x * per, hi = min(lo + per, n4);
@@ -100,10 +107,7 @@ __global__ void __launch_bounds__(256) k_dp_push(const float* __restrict__ send,
         }
         if (!waited) {
             // peers have finished reading what this rank pushed last step (checked once per CTA, after the first loads)
-            if ((int)threadIdx.x < world) {
-                const int32_t* consumed = reinterpret_cast<const int32_t*>(peers.base[rank] + flag_off) + DP_FLAG_CONSUMED;
-                spin_until(consumed + threadIdx.x, epoch - 1, strict);
-            }
+            if ((int)threadIdx.x < world && seen < epoch - 1) spin_until(consumed + threadIdx.x, epoch - 1, strict);
             waited = true;
         }
         tc::fence_proxy_async_smem();        // this thread's shared-memory writes -> visible to the bulk-copy engine

@@ -71,6 +71,7 @@ struct DpSync {
     const float* loss_parts;     // optional: n_loss values loss_stride floats apart, summed into loss_out by the last CTA
     int64_t loss_stride;
     int32_t n_loss;
+    int32_t flags;               // dccf_dp_sync.flags
     int32_t fence_mode;          // 1 (default) lean protocol, see above; 0 fence.acq_rel.sys after the flags; 2 strict everywhere
     float* loss_out;
 };
@@ -81,9 +82,9 @@ struct DpSync {
 // had already arrived; 256 threads need one), the CTA agrees through the barrier, ONE thread then issues the system-scope
 // fence that orders the CTA's later reads after the observed flags and a second barrier hands that order to the others.
 // (A first version fenced in every thread of every CTA: 87 K system fences made the consumer 16 us slower.)
-// Call from all threads of the CTA (contains barriers).
-__device__ __forceinline__ void dp_wait_inline(const DpSync& s) {
-    if (s.n_wait > 0) {
+// Call from all threads of the CTA (contains barriers).  mask: bit c set = wait for channel c (CTA-uniform).
+__device__ __forceinline__ void dp_wait_inline(const DpSync& s, const uint32_t mask = 7u) {
+    if (s.n_wait > 0 && (mask & ((1u << s.n_wait) - 1u)) != 0u) {
         const unsigned long long t0 = global_ns();
         int32_t want[3];
 #pragma unroll
@@ -94,6 +95,7 @@ __device__ __forceinline__ void dp_wait_inline(const DpSync& s) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 if (c >= s.n_wait) break;
+                if (!((mask >> c) & 1u)) continue;
                 const DpChannel& ch = s.wait[c];
                 const int32_t* arrival = reinterpret_cast<const int32_t*>(ch.base[s.rank] + ch.flag_off);
                 const int total = s.world * ch.n_ctas;
@@ -122,7 +124,15 @@ __device__ __forceinline__ void dp_done_inline(const DpSync& s) {
     const int t = threadIdx.x;
     if (s.loss_out != nullptr && t == 0) {
         float acc = 0.f;
-        for (int i = 0; i < s.n_loss; ++i) acc += __ldcg(s.loss_parts + (size_t)i * s.loss_stride);
+        for (int i0 = 0; i0 < s.n_loss; i0 += 8) {               // the ranks' terms, loaded together, added in rank order
+            float part[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i0 + i < s.n_loss) part[i] = __ldcg(s.loss_parts + (size_t)(i0 + i) * s.loss_stride);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i0 + i < s.n_loss) acc += part[i];
+        }
         s.loss_out[0] = acc;
     }
     if (t < s.n_done * s.world) {

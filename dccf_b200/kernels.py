@@ -277,12 +277,16 @@ def adam_step(tables, dense, hp):
     LAUNCHES[0] += 2 if any(t.n_seg * t.seg_len > 0 for t in tables) else 1
 
 
-def make_dp_sync(world, rank, wait=(), done=(), loss=None):
+DP_SYNC_OVERLAP_PUSH = 1
+
+
+def make_dp_sync(world, rank, wait=(), done=(), loss=None, flags=0):
     """dccf_dp_sync: `wait` / `done` = exchange channels (objects with peer_bases, flag_off, epoch_dev: the p2p
     SegmentExchange of dccf_b200/dist.py) a consumer kernel waits on in its prologue / hands back from its last CTA;
     loss = (parts tensor, stride in floats, n, out tensor): the ranks' loss terms summed by that last CTA."""
     s = DpSync()
     s.world, s.rank, s.n_wait, s.n_done = int(world), int(rank), len(wait), len(done)
+    s.flags = int(flags)
     for arr, chans in ((s.wait, wait), (s.done, done)):
         for k, c in enumerate(chans):
             for p in range(world):

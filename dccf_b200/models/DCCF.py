@@ -808,6 +808,10 @@ class DCCF(DMF):
     # items' feature rows, W with its moments and operand images): DCCF_L2_PREFETCH=0 switches it off (A/B)
     l2_prefetch = os.environ.get('DCCF_L2_PREFETCH', '1') != '0'
     dp_fold_sync = os.environ.get('DCCF_DP_FOLD', '1') != '0'
+    # with the folded synchronisation: table rows are swept while this rank's dW / db push is still running (A/B: =0)
+    dp_overlap_push = os.environ.get('DCCF_DP_OVERLAP_PUSH', '1') != '0'
+    # where dccf_adam_csr_build runs: beside | after_mid | before_sweep (default: by world size, see _fused_split_step)
+    csr_place = os.environ.get('DCCF_CSR_PLACE') or None
     # data-parallel training over a device-resident epoch: every rank's ids of the WHOLE epoch (chunk) are all-gathered
     # once, outside the steps, so no step waits for an id exchange (DCCF_DP_EPOCH_IDS=0: one id exchange per step)
     dp_epoch_ids = os.environ.get('DCCF_DP_EPOCH_IDS', '1') != '0'
@@ -919,27 +923,49 @@ class DCCF(DMF):
             with torch.cuda.stream(side):
                 if dp:                      # the id exchange waits for the peers: never on the critical path
                     link_global()
-                if csr:
+                # The CSR ranges of the step's record lists (two small launches; the touched-row sweep that needs them
+                # runs after the backward).  'beside': on a third stream as soon as the lists are linked, beside the sweep
+                # and the forward — done before the middle kernel starts at 1-2 ranks.  At 8 ranks (8 x the records) they
+                # were still resident when the middle kernel wanted its SMs: sweep CTA + CSR CTA + middle CTA exceed the
+                # register file, and the middle kernel started up to 9 us late on the ranks where that happened —
+                # 'after_mid': on a fourth stream once the middle kernel has ended, beside the dW kernel.  'before_sweep'
+                # (ahead of the sweep on this stream) pushes the sweep under the dW kernel, which it slows by 6 us.
+                csr_place = self.csr_place or ('after_mid' if (dp and world > 2) else 'beside')
+                if not csr or (csr_place == 'after_mid' and not dp):
+                    csr_place = 'beside' if csr else None
+                if csr_place == 'before_sweep':
+                    kernels.adam_csr_build(tables)
+                elif csr_place is not None:
                     linked = torch.cuda.Event()
                     linked.record(side)
                 kernels.adam_untouched(tables, hp, self._sweep_threads(dp and epoch_ids is None))
                 if dp and not fold and epoch_ids is None:
                     ix.done()
                 done.record(side)
-            if csr:
-                # the CSR ranges of the step's record lists: two small launches on the third stream, beside the sweep
-                # and the forward (the touched-row sweep that needs them runs after the backward)
+            csr_done = None
+            if csr_place == 'beside':
                 csr_done = torch.cuda.Event()
                 ship.wait_event(linked)
                 with torch.cuda.stream(ship):
                     kernels.adam_csr_build(tables)
                     csr_done.record(ship)
+            elif csr_place == 'after_mid':
+                csr_done = torch.cuda.Event()
+                if d.get('_aux_stream') is None:
+                    d['_aux_stream'] = torch.cuda.Stream(device=main.device)
+                aux = d['_aux_stream']
             if dp:
                 mid_done, shipped = torch.cuda.Event(), torch.cuda.Event()
 
                 def between(phase):        # noqa: E306  the gradient records leave while the dW kernel runs
                     if phase == 2:
                         mid_done.record(main)
+                        if csr_place == 'after_mid':
+                            aux.wait_event(mid_done)
+                            aux.wait_event(linked)
+                            with torch.cuda.stream(aux):
+                                kernels.adam_csr_build(tables)
+                                csr_done.record(aux)
                         ship.wait_event(mid_done)
                         with torch.cuda.stream(ship):
                             if fold:
@@ -958,23 +984,35 @@ class DCCF(DMF):
         pred, rec = self._launch_fwd_bwd(call, loss_mode, Y, rec=rec, w_image_valid=w_image_valid, expo_e=expo_e,
                                          expo_den=expo_den, between=between, batch=batch, programmatic=beside)
         sync = None
+        joined = False
         if dp:
             if not overlap:
                 if fold:
                     ex.rec.push()
                 else:
                     ex.exchange_records()
+            overlap_push = fold and self.dp_overlap_push
+            if overlap and overlap_push:
+                # The touched-row sweep is launched as a programmatic dependent of the dW / db push and starts beside it:
+                # everything else it depends on (record push, side sweep, CSR ranges) is joined BEFORE the push, which
+                # is then its only — programmatic — predecessor.  (All three end long before the dW kernel does.)
+                main.wait_event(shipped)
+                main.wait_event(done)
+                if csr_done is not None:
+                    main.wait_event(csr_done)
+                joined = True
             self._exchange_dense(rec, push_only=fold)
-            if overlap:
+            if overlap and not joined:
                 main.wait_event(shipped)
             if fold:
                 total = self._buf('dp_total_loss', (1,), torch.float32)
                 a_loss, _ = ex.off['loss']
                 sync = kernels.make_dp_sync(ex.world, ex.rank, wait=(ex.rec, ex.dense), done=(ex.rec, ex.dense),
-                                            loss=(ex.dense.recv[a_loss:], ex.dense.seg, ex.world, total))
-        if overlap:
+                                            loss=(ex.dense.recv[a_loss:], ex.dense.seg, ex.world, total),
+                                            flags=kernels.DP_SYNC_OVERLAP_PUSH if (overlap_push and overlap) else 0)
+        if overlap and not joined:
             main.wait_event(done)
-            if csr:
+            if csr_done is not None:
                 main.wait_event(csr_done)
         step_dev, offset_dev = counters if counters is not None else (None, None)
         kernels.adam_touched(tables, dense, hp, True, wimg, 0, D + F, opt.cta_counter, step_dev, offset_dev, sync=sync,
@@ -1102,7 +1140,8 @@ class DCCF(DMF):
         # later, larger call would replace and free), the optimizer state and the exchange buffers stay referenced
         # from the graph entry for as long as the graph can be replayed.
         keep = {'ws': dict(self._ws), 'opt': opt, 'err_flag': self._err_flag,
-                'streams': (self.__dict__.get('_side_stream'), self.__dict__.get('_ship_stream'))}
+                'streams': (self.__dict__.get('_side_stream'), self.__dict__.get('_ship_stream'),
+                            self.__dict__.get('_aux_stream'))}
         if self._dp is not None:
             keep['dp'] = (dict(self._dp.get('ex', {})), dict(self._dp.get('ids', {})))
         g.update({'graph': graph, 'pred': pred, 'loss': loss, 'call': call, 'keep_alive': keep,

@@ -333,8 +333,14 @@ typedef struct dccf_dp_sync {
     int32_t world, rank, n_wait, n_done;
     dccf_dp_channel wait[3];
     dccf_dp_channel done[3];
-    const float* loss_parts; int64_t loss_stride; int32_t n_loss; int32_t _pad; float* loss_out;
+    const float* loss_parts; int64_t loss_stride; int32_t n_loss; int32_t flags; float* loss_out;
 } dccf_dp_sync;
+/* dccf_dp_sync.flags, dccf_adam_touched only: wait[0] is the channel of the gradient records, wait[1] the channel of
+ * dW / db / loss, and the kernel launched just before dccf_adam_touched on its stream is this rank's push of the latter.
+ * The CTAs that sweep table rows then wait for wait[0] only, the CTAs of the dense tensors for wait[1]; the launch is a
+ * programmatic dependent of that push (it starts when every CTA of the push is resident, and does not complete before
+ * the push has): the table rows are swept WHILE dW / db travel. */
+#define DCCF_DP_SYNC_OVERLAP_PUSH 1
 /* Optional extras of dccf_adam_link_ids (NULL: none), all device pointers:
  *   staging (epoch_ptrs_dev != NULL): the step reads its batch from a device-resident epoch — what dccf_stage_batch does
  *     in a launch of its own: X / sample_item arguments are ignored, the batch is [*cursor] of the arrays whose

@@ -1,0 +1,23 @@
+#!/bin/bash
+# Round 2, GPU call T (2 GPUs): touched-row sweep beside the dW / db push (DCCF_DP_OVERLAP_PUSH=1, default) against after it (0).
+
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q -x 2>&1 | tail -3
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533"
+show() {
+python - "$1" <<'P'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    k = d['roofline'].get('kernels', {})
+    print(sys.argv[1], 'value', round(d['value']), 'ms/step', round(d['ms_per_step'], 5), 'b2b', round(d['back_to_back']['ms_per_step'], 5), 'e2e', round(d['e2e']['value']), 'parity', d.get('dp_parity_ok'))
+    for n, o in sorted(k.items(), key=lambda kv: kv[1]['start_us']):
+        print('    %-32s %6.1f -> %6.1f' % (n, o['start_us'], o['end_us']))
+except Exception as e:
+    print(sys.argv[1], 'parse failed', e)
+P
+}
+for f in 1 0; do
+  echo "== DCCF_DP_OVERLAP_PUSH=$f"
+  DCCF_DP_OVERLAP_PUSH=$f timeout 600 $TR bench.py --gpus 2 --steps 100 --warmup 5 --no-extra-legs --eval-users 256 --no-cpu-baseline > gpurun_out/bench_r2t_dp2_f$f.json 2> gpurun_out/bench_r2t_dp2_f$f.err; echo rc=$?; show gpurun_out/bench_r2t_dp2_f$f.json
+done
