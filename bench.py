@@ -55,18 +55,20 @@ SEED = 2019
 # algorithmic work per scored pair
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the step's kernels at the electronics shape, from ONE
 # `ncu --set full --clock-control none` capture (cold cache before every kernel), see profiles/
-NCU_TRAFFIC_SOURCE = 'profiles/r1e_ncu_full_train_summary.csv (ncu --set full, per launch, cold cache)'
-NCU_EVAL_TRAFFIC_BYTES = 8.783616e6        # k_row_scores_tc<2>, one 16384-pair batch: dram read (0 written), r1c capture
-NCU_EVAL_TRAFFIC_SOURCE = ('profiles/r1c_ncu_full_tc_summary.csv (ncu --set full, per launch of one 16384-pair batch, cold '
-                           'cache; the later tuning of the kernel did not change what it reads)')
-NCU_TRAFFIC_BYTES = {'k_train_fwd_tc': 1.89e6, 'k_train_mid': 4.47e6, 'k_train_bwd_tc': 2.92e6, 'k_adam_touched': 7.91e6,
-                     'k_adam_untouched': 47.35e6 + 0.81e6}
+NCU_TRAFFIC_SOURCE = 'profiles/r2_ncu_train_summary.csv (ncu --set full --clock-control none, mean per launch, cold cache)'
+NCU_EVAL_TRAFFIC_BYTES = 8.779776e6        # k_row_scores_tc<2>, one 16384-pair batch: dram read (0 written)
+NCU_EVAL_TRAFFIC_SOURCE = ('profiles/r2_ncu_eval_summary.csv (ncu --set full --clock-control none, one launch = one '
+                           '16384-pair batch, cold cache)')
+NCU_TRAFFIC_BYTES = {'k_train_fwd_tc': 1.88e6, 'k_train_mid': 6.05e6, 'k_train_bwd_tc': 2.91e6, 'k_adam_touched': 8.02e6,
+                     'k_adam_untouched': 49.26e6 + 0.46e6, 'k_link_ids': 4.37e6}
 # round 2 captures (per launch, cold cache, `ncu --set full --clock-control none`): dram__bytes_read.sum + dram__bytes_write.sum
 NCU_R2 = {'source': 'profiles/r2_ncu_eval_summary.csv (ncu --set full --clock-control none, per launch, cold cache)',
-          'k_gather_scores': 9.33e6,          # one 16384-pair batch; L2 hit rate 72 %
-          'k_row_scores_tc_64': 8.26e6,       # one 16384-pair batch, 64-wide operand; L2 hit rate 87 %
+          'k_gather_scores': 9.47e6,          # one 16384-pair batch (mean of three launches)
+          'k_row_scores_tc_64': 8.40e6,       # one 16384-pair batch, 64-wide operand
           'k_confounder_draw': 1.0e4,         # one 163 840-id draw: nothing read, ids written through L2
-          'k_full_scores_topk': 18.4e6}       # Yelp shape, one GPU: factors in, k ids out
+          'k_rank_stream': 8.96e6,            # 1024 users x 1001 candidates: scores + labels once (8.2 MB algorithmic)
+          'k_full_scores_topk': 30.27e6}      # Yelp shape, one GPU: user factors + the pre-split item images in, k ids out
+                                              # (profiles/r2_ncu_full_catalogue_summary.csv)
 FLOP_FWD_PAIR = R * (2 * (D + F) * D + 4 * D)
 FLOP_BWD_PAIR = R * (2 * (D + F) * D + 2 * D * D + 2 * D)
 BYTES_PAIR = 16 + 4 * D + 4 * D * Z + 4 * F + 4 * Z
@@ -934,6 +936,8 @@ def eval_object(model, evl, n_users_total, world, hbm_peak, tf32_peak, peak_src)
             'ranker': {'kernel': 'k_rank_stream (one pass, all metrics, one launch)', 'ms': evl['rank_ms'], 'bound': 'hbm',
                        'achieved': rank_bytes / 1e9 / (evl['rank_ms'] / 1e3), 'peak': hbm_peak, 'unit': 'GB/s',
                        'frac': rank_bytes / 1e9 / (evl['rank_ms'] / 1e3) / hbm_peak,
+                       'traffic': NCU_R2['k_rank_stream'] if eval_pairs == 1024 * (1 + TEST_NEG_N) else None,
+                       'traffic_source': NCU_R2['source'],
                        'note': 'algorithmic bytes = 8 B per candidate (score + label) of this rank; CUDA events around the '
                                'launch, L2 flushed before it'},
             'e2e': {'value': n_users_total / evl['e2e_s'], 'unit': 'users/s',

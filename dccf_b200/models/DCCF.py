@@ -924,13 +924,15 @@ class DCCF(DMF):
                 if dp:                      # the id exchange waits for the peers: never on the critical path
                     link_global()
                 # The CSR ranges of the step's record lists (two small launches; the touched-row sweep that needs them
-                # runs after the backward).  'beside': on a third stream as soon as the lists are linked, beside the sweep
-                # and the forward — done before the middle kernel starts at 1-2 ranks.  At 8 ranks (8 x the records) they
-                # were still resident when the middle kernel wanted its SMs: sweep CTA + CSR CTA + middle CTA exceed the
-                # register file, and the middle kernel started up to 9 us late on the ranks where that happened —
-                # 'after_mid': on a fourth stream once the middle kernel has ended, beside the dW kernel.  'before_sweep'
-                # (ahead of the sweep on this stream) pushes the sweep under the dW kernel, which it slows by 6 us.
-                csr_place = self.csr_place or ('after_mid' if (dp and world > 2) else 'beside')
+                # runs after the backward).  'beside' (default): on a third stream as soon as the lists are linked, beside
+                # the sweep and the forward — done before the middle kernel starts at 1-2 ranks.  At 8 ranks (8 x the
+                # records) they are still resident when the middle kernel wants its SMs (sweep CTA + CSR CTA + middle
+                # CTA exceed the register file) and that kernel ends 7 us later than on one GPU; the alternatives measured
+                # on 8 x B200 move the cost instead of removing it — 'after_mid' (a fourth stream, once the middle
+                # kernel has ended, beside the dW kernel and the record push: the dW kernel then takes 27 us instead of 23,
+                # 107.6 us per step against 105.4), DCCF_CSR_THREADS=64 (narrower CTAs: 106.5), 'before_sweep' (ahead of
+                # the sweep on this stream: the sweep then runs under the dW kernel, +6 us at 2 ranks).
+                csr_place = self.csr_place or 'beside'
                 if not csr or (csr_place == 'after_mid' and not dp):
                     csr_place = 'beside' if csr else None
                 if csr_place == 'before_sweep':

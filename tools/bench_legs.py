@@ -242,6 +242,9 @@ def full_catalogue_leg(world, rank, dev, peaks, U=32000, I=38000, k=5, iters=10,
                           'achieved': flop / 1e12 / (topk_ms / 1e3), 'peak': tf32_peak, 'unit': 'TFLOP/s',
                           'frac': flop / 1e12 / (topk_ms / 1e3) / tf32_peak,
                           'frac_issued': 3 * flop / 1e12 / (topk_ms / 1e3) / tf32_peak,
+                          # ncu --set full, one launch on one GPU (profiles/r2_ncu_full_catalogue_summary.csv): the user
+                          # factors and the pre-split item images in, k ids out — no re-reads from DRAM
+                          'traffic': 30.27e6 if (world == 1 and U == 32000 and I == 38000) else None,
                           'peak_source': peak_src + ': bf16 burst / 2 for kind::tf32'},
         'roofline_materialise': {'kernel': 'k_full_scores', 'bound': 'hbm', 'achieved': Ul * I * 4 / 1e9 / (mat_ms / 1e3),
                                  'peak': hbm_peak, 'unit': 'GB/s', 'frac': Ul * I * 4 / 1e9 / (mat_ms / 1e3) / hbm_peak,
