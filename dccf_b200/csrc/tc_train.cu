@@ -288,6 +288,9 @@ __global__ void __launch_bounds__(TC_NT, DCCF_TRAIN_PAIR ? 1 : 2) k_train_fwd_tc
         __syncwarp();
     }
 
+    // (DCCF_PDL_CHAIN: the middle kernel may have been launched as a programmatic dependent: its CTAs can be placed from
+    // here on, they wait for this grid's completion before they read anything)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // ===== epilogue: the 16 producer warps; warp w reads TMEM lanes 32*(w%4).. (the only ones it may touch) and
     // columns 16*(w/4)..: one 16-column slice of 32 rows of the partial pre-activations of this K split =====
     if (warp < TC_PRODUCERS / 32) {
@@ -444,6 +447,10 @@ __global__ void __maxnreg__(64) k_train_mid(const TrainMidParams prm) {
     float* pred_s = w_s + npc * Z;                  // [2]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // (DCCF_PDL_CHAIN: launched as a programmatic dependent of the partial-product kernel; the dW kernel behind this one
+    // may be placed as soon as SMs free up — both no-ops in a plain launch)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     tl_begin(3);
     const int hw = tid >> 4, sub = tid & 15;
     const int64_t jt = blockIdx.x;
@@ -696,6 +703,9 @@ __global__ void __launch_bounds__(TB_NT, DCCF_TRAIN_PAIR ? 1 : 2) k_train_bwd_tc
     __syncthreads();
     tc::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    // (DCCF_PDL_CHAIN: barriers and tensor memory were set up while the middle kernel was still running; its outputs are
+    // read from here on)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp < TC_PRODUCERS / 32) {
         // ===== producers =====
@@ -879,6 +889,24 @@ static int env_int(const char* name) {
     return (v != nullptr && v[0] != '\0') ? atoi(v) : 0;
 }
 
+// DCCF_PDL_CHAIN=1: the middle kernel and the dW kernel of the fused step are launched as programmatic dependents of the
+// kernel before them (cudaLaunchAttributeProgrammaticStreamSerialization): each waits (griddepcontrol.wait) before it
+// reads its predecessor's outputs, so only launch latency and the CTA prologues overlap.
+static bool pdl_chain() {
+    static const bool on = [] { const char* v = getenv("DCCF_PDL_CHAIN"); return v != nullptr && atoi(v) != 0; }();
+    return on;
+}
+template <typename Kern, typename Prm>
+static void launch_maybe_programmatic(Kern k, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool programmatic, const Prm& prm) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = programmatic ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k, prm);       // (errors are picked up by DCCF_CHECK_LAUNCH at the call site)
+}
+
 static int32_t fwd_ksplits_for(int64_t n_rows, int n_chunks) {
     if (n_rows <= 0) return 1;
     const int64_t tiles = (n_rows + TC_BM - 1) / TC_BM;
@@ -1004,7 +1032,7 @@ static int launch_fwd_tc(const dccf_dims* dims, const float* E_item, const float
 static int launch_bwd_tc(const dccf_dims* dims, const float* E_item, const float* Feat, const int64_t* X,
                          const int64_t* sample_item, int64_t n_pairs, const dccf_rng* rng, const float* ws_dpre,
                          const float* x_rows, float* gW_part, float* gb_part, const float* loss_terms, int64_t n_loss_terms,
-                         float loss_scale, float* out_loss, cudaStream_t stream) {
+                         float loss_scale, float* out_loss, cudaStream_t stream, bool programmatic = false) {
     static PerDeviceOnce attr_once;
     if (attr_once.need()) {
         int rc = opt_in_smem(k_train_bwd_tc<0>, "dccf_train_bwd_tc");
@@ -1025,9 +1053,9 @@ static int launch_bwd_tc(const dccf_dims* dims, const float* E_item, const float
     bwd_geometry(prm.n_rows, K, &n_mtiles, &n_splits, &prm.rows_per_split);
     const dim3 grid((unsigned)n_mtiles, (unsigned)n_splits);
     switch (rng->noise_mode) {
-        case 0: k_train_bwd_tc<0><<<grid, TB_NT, TT_SMEM_BYTES, stream>>>(prm); break;
-        case 1: k_train_bwd_tc<1><<<grid, TB_NT, TT_SMEM_BYTES, stream>>>(prm); break;
-        default: k_train_bwd_tc<2><<<grid, TB_NT, TT_SMEM_BYTES, stream>>>(prm); break;
+        case 0: launch_maybe_programmatic(k_train_bwd_tc<0>, grid, dim3(TB_NT), TT_SMEM_BYTES, stream, programmatic, prm); break;
+        case 1: launch_maybe_programmatic(k_train_bwd_tc<1>, grid, dim3(TB_NT), TT_SMEM_BYTES, stream, programmatic, prm); break;
+        default: launch_maybe_programmatic(k_train_bwd_tc<2>, grid, dim3(TB_NT), TT_SMEM_BYTES, stream, programmatic, prm); break;
     }
     DCCF_CHECK_LAUNCH("k_train_bwd_tc");
     return DCCF_OK;
@@ -1163,11 +1191,11 @@ extern "C" int dccf_train_fwd_bwd_tc(const dccf_dims* dims, const float* E_user,
     mid.rng.seed = rng->seed; mid.rng.offset = rng->offset; mid.rng.offset_dev = rng->offset_dev;
     const int64_t n_terms = (loss_mode == 0) ? n_pairs / 2 : n_pairs;
     if (phases & 2) {
-        k_train_mid<<<(unsigned)n_terms, TM_NT, smem, stream>>>(mid);
+        launch_maybe_programmatic(k_train_mid, dim3((unsigned)n_terms), dim3(TM_NT), smem, stream, pdl_chain(), mid);
         DCCF_CHECK_LAUNCH("k_train_mid");
     }
     if (!(phases & 4)) return DCCF_OK;
 
     return launch_bwd_tc(dims, E_item, Feat, X, sample_item, n_pairs, rng, ws_dpre, ws_x, gW_part, gb_part, ws_loss_terms,
-                         n_terms, loss_mode == 0 ? 1.f : 1.f / (float)n_pairs, out_loss, stream);
+                         n_terms, loss_mode == 0 ? 1.f : 1.f / (float)n_pairs, out_loss, stream, pdl_chain());
 }
