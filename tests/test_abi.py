@@ -92,3 +92,35 @@ def test_training_kernels_use_tcgen05_and_bulk_copies(lib_path):
         assert body, kernel
         for m in mnemonics:
             assert any(m in c for c in body), (kernel, m)
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """Every ctypes mirror in dccf_b200/_lib.py has the size and the member offsets the C compiler gives the struct of
+    include/dccf_b200.h (the header is compiled as plain C: it is the boundary a C / cgo / JNI host would bind)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc') or shutil.which('cc')
+    if gcc is None:
+        pytest.skip('no C compiler')
+    pairs = {'dccf_dims': _lib.Dims, 'dccf_expo': _lib.Expo, 'dccf_rng': _lib.Rng, 'dccf_adam': _lib.Adam,
+             'dccf_adam_table': _lib.AdamTable, 'dccf_adam_tensor': _lib.AdamTensor, 'dccf_dp_channel': _lib.DpChannel,
+             'dccf_dp_sync': _lib.DpSync, 'dccf_link_extra': _lib.LinkExtra, 'dccf_batch_ref': _lib.BatchRef}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dccf_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append('  printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for field, _ in cls._fields_:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, field, cname, field))
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.run([gcc, '-std=c99', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    got = {}
+    for line in out.splitlines():
+        cname, field, value = line.split()
+        got[(cname, field)] = int(value)
+    for cname, cls in pairs.items():
+        assert got[(cname, 'size')] == ctypes.sizeof(cls), cname
+        for field, _ in cls._fields_:
+            assert got[(cname, field)] == getattr(cls, field).offset, (cname, field)

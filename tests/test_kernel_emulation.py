@@ -104,3 +104,66 @@ def test_gather_scorer_schedule_emulated(P, S, A, ipsmf):
     ref = O.predict(params, X, si, None, None, A, dtype=np.float64, expo=fac)['pred']
     assert np.isfinite(out).all()
     assert np.abs(out - ref).max() / np.abs(ref).max() < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Index arithmetic of two optimizer kernels whose launch shapes changed late in round 2 (adam.cu)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('cta_threads', [256, 128, 64])
+@pytest.mark.parametrize('n_rec', [(1, 1), (256, 2816), (2048, 22528), (300, 0), (257, 513)])
+def test_csr_build_narrow_ctas_visit_every_record_once(cta_threads, n_rec):
+    """k_csr_build: the tables' record ranges are laid out in blocks of 256 records (link_lo / link_n, marshal_adam);
+    dccf_adam_csr_build may launch 256 / blockDim.x narrower CTAs per block (DCCF_CSR_THREADS).  Transcription of the
+    kernel's mapping blockIdx.x, threadIdx.x -> (table, record): every record of every table exactly once, nothing else."""
+    tables, lo = [], 0
+    for n in n_rec:                                   # marshal_adam: link_n = ceil(n_rec / 256) blocks per table
+        link_n = (n + 255) // 256
+        tables.append({'n_rec': n, 'link_lo': lo, 'link_n': link_n})
+        lo += link_n
+    link_blocks = lo
+    per = 256 // cta_threads
+    seen = [np.zeros(t['n_rec'], dtype=np.int64) for t in tables]
+    for block in range(link_blocks * per):            # ctas = link_blocks * (256 / csr_threads)
+        for i, t in enumerate(tables):
+            b = block // per - t['link_lo']
+            if b < 0 or b >= t['link_n']:
+                continue
+            r = b * 256 + (block % per) * cta_threads + np.arange(cta_threads)
+            r = r[r < t['n_rec']]
+            seen[i][r] += 1
+            break                                     # (the kernel returns after the table that owns the block)
+    for s in seen:
+        assert (s == 1).all()
+
+
+@pytest.mark.parametrize('n_rows,block_n,cta_threads', [(64000, 148, 224), (48000, 111, 224), (16000, 37, 224), (5, 3, 128),
+                                                        (4 * 7 * 3 + 1, 3, 224), (1025, 148, 256)])
+def test_untouched_sweep_pipeline_covers_every_row_once(n_rows, block_n, cta_threads):
+    """k_adam_untouched: a warp owns rows 4w .. 4w+3 per trip (two per half-warp); the touched flags of the NEXT trip are
+    read, and its rows requested into L2, one trip ahead.  Transcription of the loop: every untouched row is updated
+    exactly once, no touched row is, and the flags consumed in a trip are the ones loaded for exactly those rows."""
+    rng = np.random.default_rng(n_rows)
+    head = np.where(rng.random(n_rows) < 0.05, 3, -1)                 # -1 = untouched
+    updated = np.zeros(n_rows, dtype=np.int64)
+    n_warps = (block_n * cta_threads) >> 5
+
+    def row_ok(r):
+        return r < n_rows and head[r] == -1
+
+    for warp in range(n_warps):
+        for half in (0, 1):
+            v0 = 4 * warp < n_rows and row_ok(4 * warp + half)
+            v1 = 4 * warp < n_rows and row_ok(4 * warp + half + 2)
+            w = warp
+            while 4 * w < n_rows:
+                r0, r1 = 4 * w + half, 4 * w + half + 2
+                n0, n1 = r0 + 4 * n_warps, r0 + 4 * n_warps + 2
+                nv0, nv1 = row_ok(n0), row_ok(n1)                     # loaded before this trip's rows
+                assert v0 == row_ok(r0) and v1 == row_ok(r1)          # the flags in hand belong to this trip's rows
+                if v0:
+                    updated[r0] += 1
+                if v1:
+                    updated[r1] += 1
+                v0, v1 = nv0, nv1
+                w += n_warps
+    assert (updated[head == -1] == 1).all() and (updated[head != -1] == 0).all()
