@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(256) k_adam_touched(const AdamAllArgs a, const
         for (int64_t e = (int64_t)b * blockDim.x + threadIdx.x; e < d.n; e += stride) {
             float p = d.p[e], m = d.m[e], v = d.v[e];
             // partials added in ascending order, up to sixteen loads in flight at a time (the dW kernel of the reference
-            // shape leaves 15: a rolled tail loop waited for them one L2 round trip after the other)
+            // shape leaves 20: a rolled tail loop waited for the last four one L2 round trip after the other)
             float g = 0.f;
             for (int32_t k = 0; k < d.n_parts; k += 16) {
                 float t16[16];
